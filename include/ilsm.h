@@ -1,0 +1,179 @@
+/* ilsm.h -- C ABI of libilsm_cuda.so: the B200 (sm_100a) implementation of the LOAM-style scan-to-map
+ * registration hot path of himhan34/Intensity_based_LiDAR_SLAM_for_me-.
+ *
+ * The reference has no FFI layer: its "API" for this path is a set of library call sites inside the node
+ * bodies (PCL KdTreeFLANN / ikd-Tree / Ceres / ImageHandler).  Every entry point below replaces one such
+ * call site; the citation after each declaration is the reference file:line it stands in for
+ * (paths relative to the reference tree).  INTEGRATION.md shows the C++ stub a maintainer adds at each site.
+ *
+ * Conventions
+ *  - plain C types only; the caller owns every host buffer; the library owns device memory inside handles.
+ *  - point clouds are arrays of floats with a byte stride: 16 (pcl::PointXYZ / packed xyzi) or 32
+ *    (pcl::PointXYZI: x@0 y@4 z@8 intensity@16, parameters.h_ouster:121).  xyz are the first three floats.
+ *  - poses are Eigen-ordered: q = {x,y,z,w}, t = {x,y,z}, double (laserMapping.cpp:105-107).
+ *  - every function returns ILSM_OK (0) or a negative ilsm_status; ilsm_last_error() gives the text
+ *    (thread-local).  There is NO CPU fallback: without a CUDA device ilsm_create fails.
+ *  - handles are re-entrant per handle: calls on objects of the same ilsm_ctx are serialised by a mutex
+ *    and run on that context's single CUDA stream (the reference runs this path on one thread,
+ *    laserMapping.cpp:1215).
+ *  - *_dev variants take DEVICE pointers (inputs already resident in HBM) and enqueue on the context
+ *    stream without synchronising; call ilsm_sync() before reading results on the host.
+ */
+#ifndef ILSM_H_
+#define ILSM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ILSM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ILSM_API __attribute__((visibility("default")))
+#else
+#define ILSM_API
+#endif
+
+typedef enum ilsm_status {
+  ILSM_OK = 0,
+  ILSM_ERR_INVALID_ARG = -1,
+  ILSM_ERR_CUDA = -2,
+  ILSM_ERR_NO_DEVICE = -3,
+  ILSM_ERR_NOT_ENOUGH_MAP = -4, /* guard of laserMapping.cpp:624 (corner map <= 10 or surf map <= 50) */
+  ILSM_ERR_OUT_OF_MEMORY = -5,
+  ILSM_ERR_STATE = -6
+} ilsm_status;
+
+/* ceres::TerminationType order (ceres/types.h): the reference gates on it at mapOptimization.cpp:448. */
+typedef enum ilsm_termination {
+  ILSM_CONVERGENCE = 0,
+  ILSM_NO_CONVERGENCE = 1,
+  ILSM_FAILURE = 2
+} ilsm_termination;
+
+typedef struct ilsm_ctx ilsm_ctx; /* stream + scratch + LM state */
+typedef struct ilsm_map ilsm_map; /* voxel-hashed local map (replaces KdTreeFLANN / ikd-Tree search) */
+
+ILSM_API int ilsm_abi_version(void);
+ILSM_API const char* ilsm_last_error(void);
+
+/* One context per thread of the reference's mapping loop (laserMapping.cpp:1215 `std::thread mapping_process`). */
+ILSM_API int ilsm_create(int device, ilsm_ctx** out);
+ILSM_API void ilsm_destroy(ilsm_ctx* ctx);
+ILSM_API int ilsm_sync(ilsm_ctx* ctx);
+/* cudaStream_t of the context (for CUDA-event timing by the caller). */
+ILSM_API void* ilsm_stream(ilsm_ctx* ctx);
+
+/* ------------------------------------------------------------------ K1: local map + exact k-NN ------- */
+ILSM_API int ilsm_map_create(ilsm_ctx* ctx, ilsm_map** out);
+ILSM_API void ilsm_map_destroy(ilsm_map* map);
+ILSM_API int ilsm_map_size(const ilsm_map* map);
+
+/* (Re)build the search structure over n points.  `cell` = voxel edge in metres (<= 0 selects the default
+ * 1.0 m, the reference's d2[4] < 1.0 gate radius).  Non-finite points are skipped (the reference strips
+ * NaNs first, mapOptimization.cpp:151).
+ * Replaces: kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud  laserMapping.cpp:631-634
+ *           kdtreeCornerLast/SurfLast->setInputCloud                               laserOdometry.cpp:807-808
+ *           ikdtree->Build(points)                                                mapOptimization.cpp:192 */
+ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell);
+ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int stride_bytes, float cell);
+
+/* Exact k-NN (1 <= k <= 8), ascending squared distance computed in float as ((dx*dx)+(dy*dy))+(dz*dz) without
+ * FMA (FLANN L2_Simple<float>; ikd_Tree.cpp:2224-2230), ties broken by lower point index.  idx/d2 are nq*k;
+ * missing neighbours are idx -1 / d2 +inf.  max_dist <= 0 means unbounded (exact for every query);
+ * with max_dist > 0 only neighbours closer than max_dist are guaranteed exact (ikd-Tree's max_dist argument,
+ * ikd_Tree.h:267).
+ * Replaces: nearestKSearch(pointSel, 5, idx, d2)   laserMapping.cpp:673,753
+ *           nearestKSearch(pointSel, 1, idx, d2)   laserOdometry.cpp:452,574
+ *           ikdtree->Nearest_Search(p, 5, pts, d2) mapOptimization.cpp:393 */
+ILSM_API int ilsm_knn(ilsm_map* map, const float* q_xyz, int nq, int stride_bytes, int k, float max_dist, int32_t* idx,
+             float* d2);
+ILSM_API int ilsm_knn_dev(ilsm_map* map, const float* d_q_xyz, int nq, int stride_bytes, int k, float max_dist,
+                 int32_t* d_idx, float* d_d2);
+
+/* ------------------------------------------------- K2+K3: association, fit, residuals, LM solve ------ */
+typedef struct ilsm_reg_opts {
+  int32_t outer_iterations;   /* re-association passes: 2 (laserMapping.cpp:640), 1 (mapOptimization.cpp:377) */
+  int32_t max_num_iterations; /* Ceres max_num_iterations: 4 (laserMapping.cpp:840), 10 (mapOptimization.cpp:435) */
+  double huber_a;             /* ceres::HuberLoss(0.1) laserMapping.cpp:644 */
+  float knn_gate_sq;          /* pointSearchSqDis[4] < 1.0  laserMapping.cpp:676,758 */
+  float reserved0;
+  double line_eig_ratio;      /* eigenvalues[2] > 3 * eigenvalues[1]  laserMapping.cpp:708 */
+  double plane_tol;           /* fabs(n.p + d) > 0.2 invalidates the plane  laserMapping.cpp:778-788 */
+  int32_t min_corner_map;     /* > 10  laserMapping.cpp:624 (0 disables, as in mapOptimization.cpp) */
+  int32_t min_surf_map;       /* > 50  laserMapping.cpp:624 */
+} ilsm_reg_opts;
+
+ILSM_API void ilsm_reg_opts_default(ilsm_reg_opts* o); /* laserMapping values */
+
+typedef struct ilsm_solve_summary { /* the fields of ceres::Solver::Summary the reference reads or prints */
+  int32_t termination; /* ilsm_termination */
+  int32_t iterations;
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t num_edge_factors;  /* corner_num */
+  int32_t num_plane_factors; /* surf_num */
+  int32_t num_evaluations;
+  int32_t reserved;
+  double initial_cost;
+  double final_cost;
+} ilsm_solve_summary;
+
+#define ILSM_MAX_OUTER 8
+typedef struct ilsm_reg_report {
+  int32_t passes; /* outer passes actually run */
+  int32_t reserved;
+  ilsm_solve_summary pass[ILSM_MAX_OUTER];
+} ilsm_reg_report;
+
+/* The whole association + solve block.  corner/surf are the SENSOR-frame feature stacks
+ * (laserCloudCornerStack / laserCloudSurfStack); q,t are read as the initial guess and overwritten with the
+ * optimised pose (Eigen::Map over `parameters`).  Either stack may be empty (ns == 0 gives the
+ * mapOptimization.cpp plane-only problem when called with the ground/less-flat cloud as `surf`).
+ * Replaces: laserMapping.cpp:640-861 ; mapOptimization.cpp:377-450. */
+ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* corner, int nc,
+                  const float* surf, int ns, int stride_bytes, double q_xyzw[4], double t_xyz[3],
+                  const ilsm_reg_opts* opts, ilsm_reg_report* report);
+/* Device-resident variant: stacks are device pointers, the pose lives in d_pose (7 doubles: q xyzw, t) and is
+ * updated in place; the report is written to the device too (d_report may be NULL).  Nothing is copied to
+ * the host and the call does not synchronise. */
+ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* d_corner, int nc,
+                      const float* d_surf, int ns, int stride_bytes, double* d_pose7, const ilsm_reg_opts* opts,
+                      ilsm_reg_report* d_report);
+
+/* One correspondence record, in the reference functors' own terms (lidarFeaturePointsFunction.hpp). */
+typedef struct ilsm_factor {
+  int32_t type; /* 0 none, 1 LidarEdgeFactor (hpp:243-293), 2 LidarPlaneNormFactor (hpp:199-240) */
+  int32_t src;  /* index of the stack point */
+  double p[3];  /* curr_point (sensor frame) */
+  double a[3];  /* edge: last_point_a ; plane: plane_unit_norm */
+  double b[3];  /* edge: last_point_b ; plane: b[0] = negative_OA_dot_norm */
+} ilsm_factor;
+
+/* One association pass at pose (q,t): k-NN + line/plane fit for every stack point; fills nc+ns records
+ * (corner slots first) and keeps them in the context for ilsm_eval_normal_eq / ilsm_solve.
+ * knn_idx (5 per slot) / knn_d2 may be NULL.
+ * Replaces: laserMapping.cpp:665-797 (one iterCount). */
+ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* corner, int nc,
+                   const float* surf, int ns, int stride_bytes, const double q_xyzw[4], const double t_xyz[3],
+                   const ilsm_reg_opts* opts, ilsm_factor* factors, int32_t* knn_idx, float* knn_d2);
+
+/* One evaluation of the robustified problem at (q,t) over the factors held by the context:
+ * cost = 1/2 sum rho(|r|^2), JtJ (6x6 row-major, tangent order [rotation(3), translation(3)] of
+ * EigenQuaternionParameterization) and Jtr.  This is the single kernel a Gauss-Newton/LM iteration needs.
+ * Replaces: one Evaluate() of the ceres::Problem built at laserMapping.cpp:651-797. */
+ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q_xyzw[4], const double t_xyz[3], double huber_a, double* cost,
+                        double JtJ[36], double Jtr[6]);
+
+/* ceres::Solve(options, &problem, &summary) over the factors held by the context (Levenberg-Marquardt,
+ * trust-region loop run on the device, one kernel per iteration).
+ * Replaces: laserMapping.cpp:836-850 ; mapOptimization.cpp:433-442 ; laserOdometry.cpp:705-710. */
+ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q_xyzw[4], double t_xyz[3], int max_num_iterations, double huber_a,
+               ilsm_solve_summary* summary);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILSM_H_ */

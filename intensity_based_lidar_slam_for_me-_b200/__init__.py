@@ -1,0 +1,11 @@
+"""B200-native LOAM scan-to-map registration hot path (libilsm_cuda.so behind the C ABI of include/ilsm.h).
+
+This package holds only what the path needs: csrc/ (hand-written sm_100a kernels + the C ABI), binding.py (ctypes
+marshalling + host-side mirror of the reference call sites) and synth.py (seeded synthetic inputs).
+"""
+from . import _build, synth  # noqa: F401
+from .binding import (CONVERGENCE, FAILURE, NO_CONVERGENCE, Context, IlsmError, LocalMap, RegOpts, RegReport,  # noqa: F401
+                      SolveSummary, default_opts, load_library, FACTOR_DTYPE)
+
+__all__ = ["Context", "LocalMap", "RegOpts", "RegReport", "SolveSummary", "default_opts", "load_library", "IlsmError",
+           "synth", "CONVERGENCE", "NO_CONVERGENCE", "FAILURE", "FACTOR_DTYPE"]

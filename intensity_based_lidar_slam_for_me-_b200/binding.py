@@ -1,0 +1,240 @@
+"""ctypes binding of the C ABI in include/ilsm.h plus a thin host-side mirror of the reference call sites.
+
+The product path is libilsm_cuda.so; this module only marshals numpy / torch buffers into it.  There is no CPU
+fallback: if the shared library is missing or no CUDA device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+ILSM_OK = 0
+ILSM_ERR_NOT_ENOUGH_MAP = -4
+CONVERGENCE, NO_CONVERGENCE, FAILURE = 0, 1, 2
+MAX_OUTER = 8
+
+
+class IlsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ilsm error {code}: {msg}")
+        self.code = code
+
+
+class RegOpts(C.Structure):
+    _fields_ = [("outer_iterations", C.c_int32), ("max_num_iterations", C.c_int32), ("huber_a", C.c_double),
+                ("knn_gate_sq", C.c_float), ("reserved0", C.c_float), ("line_eig_ratio", C.c_double),
+                ("plane_tol", C.c_double), ("min_corner_map", C.c_int32), ("min_surf_map", C.c_int32)]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("termination", C.c_int32), ("iterations", C.c_int32), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("num_edge_factors", C.c_int32),
+                ("num_plane_factors", C.c_int32), ("num_evaluations", C.c_int32), ("reserved", C.c_int32),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double)]
+
+
+class RegReport(C.Structure):
+    _fields_ = [("passes", C.c_int32), ("reserved", C.c_int32), ("pass_", SolveSummary * MAX_OUTER)]
+
+
+FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen libilsm_cuda.so (built in-tree by _build.build()).  Raises if it is absent: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or _build.LIB
+    if not os.path.exists(path):
+        raise IlsmError(-100, f"{path} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, i32, f32, f64 = C.c_void_p, C.c_int, C.c_float, C.c_double
+    sig = {
+        "ilsm_abi_version": (i32, []),
+        "ilsm_last_error": (C.c_char_p, []),
+        "ilsm_create": (i32, [i32, C.POINTER(vp)]),
+        "ilsm_destroy": (None, [vp]),
+        "ilsm_sync": (i32, [vp]),
+        "ilsm_stream": (vp, [vp]),
+        "ilsm_map_create": (i32, [vp, C.POINTER(vp)]),
+        "ilsm_map_destroy": (None, [vp]),
+        "ilsm_map_size": (i32, [vp]),
+        "ilsm_map_build": (i32, [vp, vp, i32, i32, f32]),
+        "ilsm_map_build_dev": (i32, [vp, vp, i32, i32, f32]),
+        "ilsm_knn": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
+        "ilsm_knn_dev": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
+        "ilsm_reg_opts_default": (None, [C.POINTER(RegOpts)]),
+        "ilsm_register": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport)]),
+        "ilsm_register_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts), vp]),
+        "ilsm_associate": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), vp, vp, vp]),
+        "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
+        "ilsm_solve": (i32, [vp, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != ILSM_OK:
+        raise IlsmError(rc, load_library().ilsm_last_error().decode(errors="replace"))
+
+
+def _cloud(a):
+    """float32 C-contiguous (n, >=3) array -> (array, n, stride_bytes)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("point cloud must be (n, >=3) float32")
+    return a, a.shape[0], a.strides[0] if a.shape[0] else 4 * a.shape[1]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_opts(**kw) -> RegOpts:
+    o = RegOpts()
+    load_library().ilsm_reg_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class Context:
+    """One ilsm_ctx: a CUDA stream, scratch and the device-resident LM state."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.ilsm_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ilsm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._lib.ilsm_stream(self._h) or 0)
+
+    def sync(self):
+        _check(self._lib.ilsm_sync(self._h))
+
+    def new_map(self) -> "LocalMap":
+        return LocalMap(self)
+
+    # -- laserMapping.cpp:640-861 / mapOptimization.cpp:377-450 -----------------------------------
+    def register(self, map_corner, map_surf, corner, surf, q, t, opts: RegOpts | None = None):
+        c, nc, sc = _cloud(corner)
+        s, ns, ss = _cloud(surf)
+        if nc and ns and sc != ss:
+            raise ValueError("corner and surf stacks must share a stride")
+        stride = sc if nc else ss
+        qq = np.array(q, np.float64)
+        tt = np.array(t, np.float64)
+        rep = RegReport()
+        rc = self._lib.ilsm_register(self._h, map_corner._h, map_surf._h, _ptr(c), nc, _ptr(s), ns, stride, _ptr(qq),
+                                     _ptr(tt), C.byref(opts) if opts is not None else None, C.byref(rep))
+        _check(rc)
+        return qq, tt, rep
+
+    def register_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
+                     opts: RegOpts | None = None, d_report_ptr=None):
+        _check(self._lib.ilsm_register_dev(self._h, map_corner._h, map_surf._h, d_corner_ptr, nc, d_surf_ptr, ns, stride,
+                                           d_pose_ptr, C.byref(opts) if opts is not None else None, d_report_ptr))
+
+    def associate(self, map_corner, map_surf, corner, surf, q, t, opts: RegOpts | None = None, want_knn=False):
+        c, nc, sc = _cloud(corner)
+        s, ns, ss = _cloud(surf)
+        stride = sc if nc else ss
+        qq = np.array(q, np.float64)
+        tt = np.array(t, np.float64)
+        fac = np.zeros(nc + ns, FACTOR_DTYPE)
+        idx = np.zeros((nc + ns, 5), np.int32) if want_knn else None
+        d2 = np.zeros((nc + ns, 5), np.float32) if want_knn else None
+        _check(self._lib.ilsm_associate(self._h, map_corner._h, map_surf._h, _ptr(c), nc, _ptr(s), ns, stride, _ptr(qq),
+                                        _ptr(tt), C.byref(opts) if opts is not None else None, _ptr(fac),
+                                        _ptr(idx) if want_knn else None, _ptr(d2) if want_knn else None))
+        return (fac, idx, d2) if want_knn else fac
+
+    def eval_normal_eq(self, q, t, huber_a=0.1):
+        qq = np.array(q, np.float64)
+        tt = np.array(t, np.float64)
+        cost = C.c_double()
+        H = np.zeros((6, 6))
+        g = np.zeros(6)
+        _check(self._lib.ilsm_eval_normal_eq(self._h, _ptr(qq), _ptr(tt), huber_a, C.byref(cost), _ptr(H), _ptr(g)))
+        return cost.value, H, g
+
+    def solve(self, q, t, max_num_iterations=4, huber_a=0.1):
+        qq = np.array(q, np.float64)
+        tt = np.array(t, np.float64)
+        s = SolveSummary()
+        _check(self._lib.ilsm_solve(self._h, _ptr(qq), _ptr(tt), max_num_iterations, huber_a, C.byref(s)))
+        return qq, tt, s
+
+
+class LocalMap:
+    """ilsm_map: the voxel-hashed local map.  Mirrors pcl::KdTreeFLANN (setInputCloud / nearestKSearch) and
+    ikd-Tree (Build / Nearest_Search) as used by the reference."""
+
+    def __init__(self, ctx: Context):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_map_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_map_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.ilsm_map_size(self._h))
+
+    # kdtree->setInputCloud(cloud) / ikdtree->Build(points)
+    def set_input_cloud(self, cloud, cell: float = 0.0):
+        a, n, stride = _cloud(cloud)
+        _check(self._lib.ilsm_map_build(self._h, _ptr(a), n, stride, cell))
+        return self
+
+    build = set_input_cloud
+
+    def build_dev(self, d_ptr: int, n: int, stride: int, cell: float = 0.0):
+        _check(self._lib.ilsm_map_build_dev(self._h, d_ptr, n, stride, cell))
+        return self
+
+    # kdtree->nearestKSearch(point, k, idx, d2) / ikdtree->Nearest_Search(point, k, pts, d2)
+    def nearest_k_search(self, queries, k: int = 5, max_dist: float = 0.0):
+        q, nq, stride = _cloud(queries)
+        idx = np.empty((nq, k), np.int32)
+        d2 = np.empty((nq, k), np.float32)
+        _check(self._lib.ilsm_knn(self._h, _ptr(q), nq, stride, k, max_dist, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def knn_dev(self, d_q_ptr: int, nq: int, stride: int, k: int, max_dist: float, d_idx_ptr: int, d_d2_ptr: int):
+        _check(self._lib.ilsm_knn_dev(self._h, d_q_ptr, nq, stride, k, max_dist, d_idx_ptr, d_d2_ptr))

@@ -1,0 +1,427 @@
+// api.cu -- the C ABI (include/ilsm.h) over the kernels: handle management, staging of caller buffers, errors.
+// No CPU fallback anywhere: without a CUDA device ilsm_create fails and nothing else can be called.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "ilsm_host.hpp"
+
+namespace ilsm {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+  cudaGetLastError();
+  return ILSM_ERR_CUDA;
+}
+int check_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, where);
+  return ILSM_OK;
+}
+
+int eval_only_launch(Ctx* c, double* d_out);
+int factors_export(Ctx* c, ilsm_factor* d_out);
+
+struct Pose7 {
+  double v[7];
+};
+
+__global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double huber_a) {
+  for (int i = 0; i < 4; ++i) st->xq[i] = p.v[i];
+  for (int i = 0; i < 3; ++i) st->xt[i] = p.v[4 + i];
+  if (also_candidate) {
+    for (int i = 0; i < 4; ++i) st->cq[i] = p.v[i];
+    for (int i = 0; i < 3; ++i) st->ct[i] = p.v[4 + i];
+    st->huber_a = huber_a;
+  }
+}
+
+__global__ void lm_arm_kernel(LmState* st, int max_iter, double huber_a, int pass) {
+  for (int i = 0; i < 4; ++i) st->cq[i] = st->xq[i];
+  for (int i = 0; i < 3; ++i) st->ct[i] = st->xt[i];
+  st->status = 0, st->phase = 0, st->iteration = 0, st->max_iter = max_iter;
+  st->invalid_run = 0, st->reuse_diag = 0;
+  st->n_success = st->n_unsuccess = st->n_evals = 0;
+  st->n_edge = st->n_plane = 0;
+  st->radius = 1e4, st->decrease_factor = 2.0, st->model_cost_change = 0.0;
+  st->huber_a = huber_a;
+  st->pass = pass;
+  st->ticket = 0u;
+}
+
+__global__ void pose_io_kernel(LmState* st, double* pose7, ilsm_reg_report* report, int direction) {
+  // direction 0: pose7 -> state ; 1: state -> pose7 (+ report)
+  int t = threadIdx.x;
+  if (direction == 0) {
+    if (t < 4) st->xq[t] = pose7[t];
+    else if (t < 7) st->xt[t - 4] = pose7[t];
+  } else {
+    if (t < 4) pose7[t] = st->xq[t];
+    else if (t < 7) pose7[t] = st->xt[t - 4];
+    if (report) {
+      const int words = (int)(sizeof(ilsm_reg_report) / 4);
+      const int32_t* src = reinterpret_cast<const int32_t*>(&st->report);
+      int32_t* dst = reinterpret_cast<int32_t*>(report);
+      for (int w = t; w < words; w += blockDim.x) dst[w] = src[w];
+    }
+  }
+}
+
+int Ctx::init(int dev) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return fail(ILSM_ERR_NO_DEVICE, "no CUDA device available (libilsm_cuda has no CPU fallback)");
+  }
+  if (dev < 0 || dev >= count) return fail(ILSM_ERR_INVALID_ARG, "ilsm_create: device index out of range");
+  device = dev;
+  ILSM_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  ILSM_CUDA(cudaGetDeviceProperties(&prop, dev));
+  sm_count = prop.multiProcessorCount;
+  ILSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  int rc;
+  if ((rc = lm.reserve(1))) return rc;
+  ILSM_CUDA(cudaMemsetAsync(lm.p, 0, sizeof(LmState), stream));
+  if ((rc = pinned.reserve(4096))) return rc;
+  ILSM_CUDA(cudaStreamSynchronize(stream));
+  return ILSM_OK;
+}
+
+void Ctx::release() {
+  if (stream) cudaStreamSynchronize(stream);
+  lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
+  fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+}
+
+void Map::release() {
+  cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release();
+  bbox.release(), raw.release();
+}
+
+static bool valid_stride(int s) { return s >= 12 && (s % 4) == 0; }
+
+static ilsm_reg_opts sanitize(const ilsm_reg_opts* o) {
+  ilsm_reg_opts r;
+  if (o)
+    r = *o;
+  else
+    ilsm_reg_opts_default(&r);
+  if (r.outer_iterations < 1) r.outer_iterations = 1;
+  if (r.outer_iterations > ILSM_MAX_OUTER) r.outer_iterations = ILSM_MAX_OUTER;
+  if (r.max_num_iterations < 0) r.max_num_iterations = 0;
+  if (r.max_num_iterations > 200) r.max_num_iterations = 200;
+  return r;
+}
+
+}  // namespace ilsm
+
+using namespace ilsm;
+
+struct ilsm_ctx {
+  Ctx c;
+};
+struct ilsm_map {
+  Map m;
+};
+
+extern "C" {
+
+ILSM_API int ilsm_abi_version(void) { return ILSM_ABI_VERSION; }
+ILSM_API const char* ilsm_last_error(void) { return g_err; }
+
+ILSM_API void ilsm_reg_opts_default(ilsm_reg_opts* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->outer_iterations = 2;
+  o->max_num_iterations = 4;
+  o->huber_a = 0.1;
+  o->knn_gate_sq = 1.0f;
+  o->line_eig_ratio = 3.0;
+  o->plane_tol = 0.2;
+  o->min_corner_map = 10;
+  o->min_surf_map = 50;
+}
+
+ILSM_API int ilsm_create(int device, ilsm_ctx** out) {
+  if (!out) return fail(ILSM_ERR_INVALID_ARG, "ilsm_create: out is null");
+  *out = nullptr;
+  ilsm_ctx* h = new (std::nothrow) ilsm_ctx();
+  if (!h) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  int rc = h->c.init(device);
+  if (rc) {
+    h->c.release();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return ILSM_OK;
+}
+
+ILSM_API void ilsm_destroy(ilsm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  ctx->c.release();
+  delete ctx;
+}
+
+ILSM_API int ilsm_sync(ilsm_ctx* ctx) {
+  if (!ctx) return fail(ILSM_ERR_INVALID_ARG, "null ctx");
+  ILSM_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API void* ilsm_stream(ilsm_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+ILSM_API int ilsm_map_create(ilsm_ctx* ctx, ilsm_map** out) {
+  if (!ctx || !out) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_create: null argument");
+  ilsm_map* m = new (std::nothrow) ilsm_map();
+  if (!m) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  m->m.ctx = &ctx->c;
+  *out = m;
+  return ILSM_OK;
+}
+
+ILSM_API void ilsm_map_destroy(ilsm_map* map) {
+  if (!map) return;
+  {
+    std::lock_guard<std::mutex> lk(map->m.ctx->mu);
+    cudaSetDevice(map->m.ctx->device);
+    cudaStreamSynchronize(map->m.ctx->stream);
+    map->m.release();
+  }
+  delete map;
+}
+
+ILSM_API int ilsm_map_size(const ilsm_map* map) { return map ? map->m.n : 0; }
+
+ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int stride_bytes, float cell) {
+  if (!map || (n > 0 && !d_xyz)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_build_dev: null argument");
+  std::lock_guard<std::mutex> lk(map->m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(map->m.ctx->device));
+  return map->m.build_dev(d_xyz, n, stride_bytes, cell);
+}
+
+ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell) {
+  if (!map || (n > 0 && !xyz)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_build: null argument");
+  if (n < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_build: bad n/stride");
+  Map& m = map->m;
+  std::lock_guard<std::mutex> lk(m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(m.ctx->device));
+  size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = m.raw.reserve(bytes / 4 + 4))) return rc;
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(m.raw.p, xyz, bytes, cudaMemcpyHostToDevice, m.ctx->stream));
+  if ((rc = m.build_dev(m.raw.p, n, stride_bytes, cell))) return rc;
+  ILSM_CUDA(cudaStreamSynchronize(m.ctx->stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_knn_dev(ilsm_map* map, const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx,
+                 float* d_d2) {
+  if (!map || (nq > 0 && (!d_q || !d_idx || !d_d2))) return fail(ILSM_ERR_INVALID_ARG, "ilsm_knn_dev: null argument");
+  std::lock_guard<std::mutex> lk(map->m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(map->m.ctx->device));
+  return map->m.knn_dev(d_q, nq, stride_bytes, k, max_dist, d_idx, d_d2);
+}
+
+ILSM_API int ilsm_knn(ilsm_map* map, const float* q, int nq, int stride_bytes, int k, float max_dist, int32_t* idx, float* d2) {
+  if (!map || (nq > 0 && (!q || !idx || !d2))) return fail(ILSM_ERR_INVALID_ARG, "ilsm_knn: null argument");
+  if (nq < 0 || !valid_stride(stride_bytes) || k < 1 || k > 8) return fail(ILSM_ERR_INVALID_ARG, "ilsm_knn: bad nq/k/stride");
+  Map& m = map->m;
+  Ctx& c = *m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (nq == 0) return ILSM_OK;
+  size_t bytes = (size_t)nq * stride_bytes;
+  int rc;
+  if ((rc = c.stack_raw.reserve(bytes / 4 + 4)) || (rc = c.out_idx.reserve((size_t)nq * k)) ||
+      (rc = c.out_d2.reserve((size_t)nq * k)))
+    return rc;
+  ILSM_CUDA(cudaMemcpyAsync(c.stack_raw.p, q, bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = m.knn_dev(c.stack_raw.p, nq, stride_bytes, k, max_dist, c.out_idx.p, c.out_d2.p))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(idx, c.out_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(d2, c.out_d2.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+static int check_reg_args(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf,
+                          int ns, int stride_bytes) {
+  if (!ctx || !mc || !ms) return fail(ILSM_ERR_INVALID_ARG, "register: null handle");
+  if (mc->m.ctx != &ctx->c || ms->m.ctx != &ctx->c) return fail(ILSM_ERR_INVALID_ARG, "register: map belongs to another context");
+  if (nc < 0 || ns < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "register: bad counts/stride");
+  if ((nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ILSM_ERR_INVALID_ARG, "register: null stack");
+  if (mc->m.table_size == 0 || ms->m.table_size == 0) return fail(ILSM_ERR_STATE, "register: map not built");
+  return ILSM_OK;
+}
+
+// stage both stacks into ctx.stack_raw; returns device pointers
+static int stage_stacks(Ctx& c, const float* corner, int nc, const float* surf, int ns, int stride_bytes,
+                        const float** d_corner, const float** d_surf) {
+  size_t bc = (size_t)nc * stride_bytes, bs = (size_t)ns * stride_bytes;
+  size_t off_s = (bc + 255) & ~(size_t)255;
+  int rc;
+  if ((rc = c.stack_raw.reserve((off_s + bs) / 4 + 64))) return rc;
+  char* base = reinterpret_cast<char*>(c.stack_raw.p);
+  if (bc) ILSM_CUDA(cudaMemcpyAsync(base, corner, bc, cudaMemcpyHostToDevice, c.stream));
+  if (bs) ILSM_CUDA(cudaMemcpyAsync(base + off_s, surf, bs, cudaMemcpyHostToDevice, c.stream));
+  *d_corner = reinterpret_cast<const float*>(base);
+  *d_surf = reinterpret_cast<const float*>(base + off_s);
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* d_corner, int nc, const float* d_surf,
+                      int ns, int stride_bytes, double* d_pose7, const ilsm_reg_opts* opts, ilsm_reg_report* d_report) {
+  int rc = check_reg_args(ctx, mc, ms, d_corner, nc, d_surf, ns, stride_bytes);
+  if (rc) return rc;
+  if (!d_pose7) return fail(ILSM_ERR_INVALID_ARG, "register_dev: null pose");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
+    return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
+  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, nullptr, 0);
+  if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
+  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, d_report, 1);
+  return check_launch("register_dev");
+}
+
+ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,
+                  int stride_bytes, double q[4], double t[3], const ilsm_reg_opts* opts, ilsm_reg_report* report) {
+  int rc = check_reg_args(ctx, mc, ms, corner, nc, surf, ns, stride_bytes);
+  if (rc) return rc;
+  if (!q || !t) return fail(ILSM_ERR_INVALID_ARG, "register: null pose");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (report) memset(report, 0, sizeof(*report));
+  if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
+    return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
+  const float *d_corner, *d_surf;
+  if ((rc = stage_stacks(c, corner, nc, surf, ns, stride_bytes, &d_corner, &d_surf))) return rc;
+  Pose7 p;
+  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
+  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
+  if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
+  // pose (7 doubles, xq/xt are adjacent) and the report come back through pinned memory
+  unsigned char* pin = c.pinned.p;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const double* out = reinterpret_cast<const double*>(pin);
+  for (int i = 0; i < 4; ++i) q[i] = out[i];
+  for (int i = 0; i < 3; ++i) t[i] = out[4 + i];
+  if (report) {
+    memcpy(report, pin + 64, sizeof(*report));
+    report->passes = o.outer_iterations;
+  }
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,
+                   int stride_bytes, const double q[4], const double t[3], const ilsm_reg_opts* opts,
+                   ilsm_factor* factors, int32_t* knn_idx, float* knn_d2) {
+  int rc = check_reg_args(ctx, mc, ms, corner, nc, surf, ns, stride_bytes);
+  if (rc) return rc;
+  if (!q || !t) return fail(ILSM_ERR_INVALID_ARG, "associate: null pose");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const float *d_corner, *d_surf;
+  if ((rc = stage_stacks(c, corner, nc, surf, ns, stride_bytes, &d_corner, &d_surf))) return rc;
+  Pose7 p;
+  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
+  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
+  const bool want_knn = knn_idx != nullptr && knn_d2 != nullptr;
+  if ((rc = c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, 0, want_knn))) return rc;
+  const int n = nc + ns;
+  if (factors && n > 0) {
+    // export through out_idx scratch (reinterpreted) to keep allocations few
+    size_t words = ((size_t)n * sizeof(ilsm_factor) + 3) / 4;
+    if ((rc = c.out_idx.reserve(words + 8))) return rc;
+    ilsm_factor* d_f = reinterpret_cast<ilsm_factor*>(c.out_idx.p);
+    if ((rc = factors_export(&c, d_f))) return rc;
+    ILSM_CUDA(cudaMemcpyAsync(factors, d_f, (size_t)n * sizeof(ilsm_factor), cudaMemcpyDeviceToHost, c.stream));
+  }
+  if (want_knn && n > 0) {
+    ILSM_CUDA(cudaMemcpyAsync(knn_idx, c.fac.knn_idx.p, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaMemcpyAsync(knn_d2, c.fac.knn_d2.p, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, c.stream));
+  }
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q[4], const double t[3], double huber_a, double* cost, double JtJ[36],
+                        double Jtr[6]) {
+  if (!ctx || !q || !t || !cost || !JtJ || !Jtr) return fail(ILSM_ERR_INVALID_ARG, "eval: null argument");
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  Pose7 p;
+  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
+  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, huber_a);
+  int rc;
+  if ((rc = c.partials.reserve(64))) return rc;
+  // eval_out lives at the tail of the partials buffer? keep it simple: dedicated 32 doubles in out_d2 scratch
+  if ((rc = c.out_d2.reserve(128))) return rc;
+  double* d_out = reinterpret_cast<double*>(c.out_d2.p);
+  if ((rc = eval_only_launch(&c, d_out))) return rc;
+  double* pin = reinterpret_cast<double*>(c.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, d_out, 32 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  *cost = pin[0];
+  int k = 1;
+  for (int a = 0; a < 6; ++a)
+    for (int b = a; b < 6; ++b) {
+      JtJ[a * 6 + b] = pin[k];
+      JtJ[b * 6 + a] = pin[k];
+      ++k;
+    }
+  for (int a = 0; a < 6; ++a) Jtr[a] = pin[22 + a];
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_iterations, double huber_a,
+               ilsm_solve_summary* summary) {
+  if (!ctx || !q || !t) return fail(ILSM_ERR_INVALID_ARG, "solve: null argument");
+  if (max_num_iterations < 0) max_num_iterations = 0;
+  if (max_num_iterations > 200) max_num_iterations = 200;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  Pose7 p;
+  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
+  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
+  lm_arm_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, max_num_iterations, huber_a, 0);
+  int rc;
+  if ((rc = c.eval_launch(1 + max_num_iterations))) return rc;
+  unsigned char* pin = c.pinned.p;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const double* out = reinterpret_cast<const double*>(pin);
+  for (int i = 0; i < 4; ++i) q[i] = out[i];
+  for (int i = 0; i < 3; ++i) t[i] = out[4 + i];
+  if (summary) memcpy(summary, pin + 64 + offsetof(ilsm_reg_report, pass), sizeof(*summary));
+  return ILSM_OK;
+}
+
+}  // extern "C"

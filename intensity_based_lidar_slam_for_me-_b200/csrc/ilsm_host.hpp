@@ -1,0 +1,152 @@
+// ilsm_host.hpp -- host-side objects behind the opaque C handles (ilsm_ctx, ilsm_map).
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/ilsm.h"
+#include "ilsm_internal.cuh"
+
+namespace ilsm {
+
+int fail(int code, const char* msg);
+int fail_cuda(cudaError_t e, const char* where);
+int check_launch(const char* where);
+
+#define ILSM_CUDA(call)                                        \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return ::ilsm::fail_cuda(e__, #call); \
+  } while (0)
+
+// Grow-only device buffer (HBM is plentiful: 180 GB; reallocation would serialise the stream).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return ILSM_OK;
+    size_t want = n + n / 2 + 64;
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want * sizeof(T));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ILSM_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
+    }
+    if (p) cudaFree(p);  // implicit device sync: only on growth
+    p = np;
+    cap = want;
+    return ILSM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t n) {
+    if (n <= cap) return ILSM_OK;
+    size_t want = n + n / 2 + 64;
+    T* np = nullptr;
+    if (cudaMallocHost(&np, want * sizeof(T)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ILSM_ERR_OUT_OF_MEMORY, "cudaMallocHost failed");
+    }
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = want;
+    return ILSM_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// Levenberg-Marquardt state that lives in HBM for the duration of a registration: the trust-region loop of
+// ceres::Solve runs on the device, one evaluation kernel per iteration, no host round trip.
+struct LmState {
+  double xq[4], xt[3];  // accepted pose (q = x,y,z,w)
+  double cq[4], ct[3];  // candidate pose: what the next evaluation kernel evaluates
+  double cost;          // cost at x
+  double H[21], g[6];   // unscaled J^T J (upper triangle, row-major) and J^T r at x
+  double scale[6];      // Jacobi scaling fixed at iteration 0
+  double diag[6];       // LM diagonal (of the scaled J^T J) kept while reuse_diagonal
+  double radius, decrease_factor, model_cost_change;
+  double huber_a;
+  double initial_cost;
+  int status;  // 0 running, 1 + ilsm_termination when finished
+  int phase;   // 0: next evaluation is the initial one, 1: trial step
+  int iteration, max_iter, invalid_run, reuse_diag;
+  int n_success, n_unsuccess, n_evals;
+  int n_edge, n_plane;
+  int pass;  // which report slot the running solve fills
+  unsigned ticket;
+  int pad;
+  ilsm_reg_report report;
+};
+
+struct Ctx;
+
+struct Map {
+  Ctx* ctx = nullptr;
+  int n = 0;
+  float cell = 1.f, inv_cell = 1.f;
+  uint32_t table_size = 0;
+  int log2_size = 0;
+  DevBuf<GridCell> cells;
+  DevBuf<float4> sorted, orig;
+  DevBuf<uint32_t> slot_of, rank_of, counters;
+  DevBuf<int> bbox;
+  DevBuf<float> raw;  // staging of caller bytes for the host-pointer entry points
+
+  int build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size);
+  int knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2);
+  GridView view() const;
+  void release();
+};
+
+// Device-side factor storage (SoA), one slot per stack point (corner slots first).
+struct FactorBufs {
+  DevBuf<int> type;
+  DevBuf<float4> p;    // curr_point (sensor frame), w unused
+  DevBuf<double4> a;   // edge: point_a        ; plane: unit normal, w = negative_OA_dot_norm
+  DevBuf<double4> b;   // edge: point_b
+  DevBuf<int32_t> knn_idx;  // 5 per slot (debug / parity output)
+  DevBuf<float> knn_d2;
+  int n = 0, nc = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  DevBuf<LmState> lm;
+  DevBuf<double> partials;  // [blocks][32]
+  DevBuf<float> stack_raw;  // staged caller stacks
+  DevBuf<int32_t> out_idx;
+  DevBuf<float> out_d2;
+  PinnedBuf<unsigned char> pinned;
+  FactorBufs fac;
+  size_t partial_blocks = 0;
+
+  int init(int dev);
+  void release();
+  int associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
+                    const ilsm_reg_opts& o, bool begin_solve, int pass, bool want_knn);
+  int eval_launch(int count);  // `count` evaluation kernels at the candidate pose held in LmState
+  int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
+                   const ilsm_reg_opts& o);
+};
+
+}  // namespace ilsm

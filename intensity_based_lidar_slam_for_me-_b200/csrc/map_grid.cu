@@ -1,0 +1,207 @@
+// map_grid.cu -- K1: voxel-hashed local map (build) and the stand-alone exact k-NN kernel.
+//
+// Replaces pcl::KdTreeFLANN::setInputCloud/nearestKSearch (laserMapping.cpp:631-634,673,753;
+// laserOdometry.cpp:452,574,807-808) and ikd-Tree Build/Nearest_Search (mapOptimization.cpp:192,393).
+//
+// Build = 4 short kernels, no sort:
+//   clear   : table slots <- EMPTY, counters <- 0
+//   count   : every point claims its voxel slot with atomicCAS and takes a rank with atomicAdd
+//   alloc   : every occupied slot gets a contiguous range (warp-aggregated atomicAdd on one cursor)
+//   scatter : points are written as float4 {x,y,z,bits(index)} into their voxel's range
+// The memory order of voxels/points is not deterministic, the k-NN result is: selection uses the total
+// order (d2, original index).
+#include "ilsm_host.hpp"
+
+namespace ilsm {
+
+__global__ void grid_clear_kernel(GridCell* cells, uint32_t size, int* bbox, uint32_t* counters) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < size) {
+    uint4 e;
+    e.x = 0xFFFFFFFFu, e.y = 0xFFFFFFFFu, e.z = 0u, e.w = 0u;
+    reinterpret_cast<uint4*>(cells)[i] = e;
+  }
+  if (i < 3) bbox[i] = INT_MAX;
+  if (i >= 3 && i < 6) bbox[i] = INT_MIN;
+  if (i < 4) counters[i] = 0;  // [0] cursor, [1] inserted points, [2] skipped points
+}
+
+__device__ __forceinline__ bool load_point(const float* src, int stride_f, int i, float& x, float& y, float& z) {
+  const float* p = src + (size_t)i * stride_f;
+  x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+  return isfinite(x) && isfinite(y) && isfinite(z);
+}
+
+__global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, float inv_cell, GridCell* cells,
+                                  uint32_t mask, int log2_size, float4* __restrict__ orig,
+                                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of, int* bbox,
+                                  uint32_t* counters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x, y, z;
+  bool ok = load_point(src, stride_f, i, x, y, z);
+  orig[i] = make_float4(x, y, z, 0.f);
+  int cx = 0, cy = 0, cz = 0;
+  if (ok) {
+    float ux = __fmul_rn(x, inv_cell), uy = __fmul_rn(y, inv_cell), uz = __fmul_rn(z, inv_cell);
+    ok = fabsf(ux) < (float)kCoordLim && fabsf(uy) < (float)kCoordLim && fabsf(uz) < (float)kCoordLim;
+    cx = __float2int_rd(ux), cy = __float2int_rd(uy), cz = __float2int_rd(uz);
+  }
+  if (!ok) {
+    slot_of[i] = 0xFFFFFFFFu;
+    atomicAdd(&counters[2], 1u);
+    return;
+  }
+  u64 key = pack_voxel(cx, cy, cz);
+  uint32_t slot = hash_voxel(key, log2_size);
+  for (;;) {
+    u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
+    if (prev == kEmptyKey) {  // first point of this voxel: extend the occupied bounding box
+      atomicMin(&bbox[0], cx), atomicMin(&bbox[1], cy), atomicMin(&bbox[2], cz);
+      atomicMax(&bbox[3], cx), atomicMax(&bbox[4], cy), atomicMax(&bbox[5], cz);
+      break;
+    }
+    if (prev == key) break;
+    slot = (slot + 1) & mask;
+  }
+  slot_of[i] = slot;
+  rank_of[i] = atomicAdd(&cells[slot].count, 1u);
+}
+
+__global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* counters) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cnt = i < size ? cells[i].count : 0u;
+  // warp-aggregated allocation: inclusive scan of the counts, one atomic per warp
+  uint32_t lane = threadIdx.x & 31, inc = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= (uint32_t)off) inc += v;
+  }
+  uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  uint32_t base = 0;
+  if (lane == 31 && total) base = atomicAdd(&counters[0], total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (i < size && cnt) cells[i].start = base + inc - cnt;
+}
+
+__global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, const GridCell* __restrict__ cells,
+                                    const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of,
+                                    float4* __restrict__ sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t slot = slot_of[i];
+  if (slot == 0xFFFFFFFFu) return;
+  float4 p = orig[i];
+  p.w = __uint_as_float((uint32_t)i);
+  sorted[cells[slot].start + rank_of[i]] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone k-NN kernel: one G-lane group per query
+// ---------------------------------------------------------------------------------------------------
+template <int K, int G>
+__global__ void __launch_bounds__(256) knn_kernel(GridView g, const float* __restrict__ q, int nq, int stride_f, int k_out,
+                                                  float max_d2, int32_t* __restrict__ idx, float* __restrict__ d2) {
+  const int groups_per_block = blockDim.x / G;
+  const int gid = blockIdx.x * groups_per_block + threadIdx.x / G;
+  const unsigned lane = threadIdx.x % G;
+  const unsigned wl = threadIdx.x & 31;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl - lane));
+  if (gid >= nq) return;  // whole groups exit together
+  const float* qp = q + (size_t)gid * stride_f;
+  float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+  u64 res[K];
+  knn_search<K, G>(g, qx, qy, qz, max_d2, lane, gmask, res);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < k_out) {
+        bool have = res[k] != kSentinel;
+        idx[(size_t)gid * k_out + k] = have ? cand_idx(res[k]) : -1;
+        d2[(size_t)gid * k_out + k] = have ? cand_d2(res[k]) : __int_as_float(0x7f800000);
+      }
+    }
+  }
+}
+
+static inline int ilog2_ceil(uint32_t v) {
+  int l = 0;
+  while ((1u << l) < v) ++l;
+  return l;
+}
+
+int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size) {
+  if (n_pts < 0 || (stride_bytes % 4) != 0 || stride_bytes < 12) return fail(ILSM_ERR_INVALID_ARG, "map_build: bad n/stride");
+  if (!(cell_size > 0.f)) cell_size = 1.0f;
+  cudaStream_t s = ctx->stream;
+  n = n_pts;
+  cell = cell_size;
+  inv_cell = 1.0f / cell_size;
+  int want_log2 = ilog2_ceil((uint32_t)(n_pts > 0 ? 2u * (uint32_t)n_pts : 2u));
+  if (want_log2 < 10) want_log2 = 10;
+  uint32_t want_size = 1u << want_log2;
+  int rc;
+  if ((rc = cells.reserve(want_size)) || (rc = sorted.reserve(n_pts + 1)) || (rc = orig.reserve(n_pts + 1)) ||
+      (rc = slot_of.reserve(n_pts + 1)) || (rc = rank_of.reserve(n_pts + 1)) || (rc = bbox.reserve(8)) ||
+      (rc = counters.reserve(4)))
+    return rc;
+  log2_size = want_log2;
+  table_size = want_size;
+  const int T = 256;
+  grid_clear_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, bbox.p, counters.p);
+  if (n_pts > 0) {
+    grid_count_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(d_src, n_pts, stride_bytes / 4, inv_cell, cells.p,
+                                                         table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p,
+                                                         bbox.p, counters.p);
+    grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p);
+    grid_scatter_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(orig.p, n_pts, cells.p, slot_of.p, rank_of.p, sorted.p);
+  }
+  return check_launch("map_build");
+}
+
+GridView Map::view() const {
+  GridView g;
+  g.cells = cells.p;
+  g.sorted = sorted.p;
+  g.orig = orig.p;
+  g.bbox = bbox.p;
+  g.mask = table_size - 1;
+  g.log2_size = log2_size;
+  g.cell = cell;
+  g.inv_cell = inv_cell;
+  g.n = n;
+  return g;
+}
+
+template <int K>
+static void launch_knn(const GridView& g, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
+                       float* d_d2, cudaStream_t s, int sm_count) {
+  // few queries: a whole warp per query (latency); many queries: 8 lanes per query (throughput)
+  const int T = 256;
+  if ((long long)nq * 32 <= (long long)sm_count * 2048 * 2) {
+    knn_kernel<K, 32><<<(nq + T / 32 - 1) / (T / 32), T, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
+  } else {
+    knn_kernel<K, 8><<<(nq + T / 8 - 1) / (T / 8), T, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
+  }
+}
+
+int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2) {
+  if (nq < 0 || k < 1 || k > 8 || (stride_bytes % 4) != 0 || stride_bytes < 12)
+    return fail(ILSM_ERR_INVALID_ARG, "knn: bad nq/k/stride");
+  if (table_size == 0) return fail(ILSM_ERR_STATE, "knn: map not built");
+  if (nq == 0) return ILSM_OK;
+  GridView g = view();
+  float max_d2 = max_dist > 0.f ? max_dist * max_dist : 0.f;
+  cudaStream_t s = ctx->stream;
+  int stride_f = stride_bytes / 4;
+  if (k == 1)
+    launch_knn<1>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+  else if (k <= 5)
+    launch_knn<5>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+  else
+    launch_knn<8>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+  return check_launch("knn");
+}
+
+}  // namespace ilsm

@@ -1,0 +1,184 @@
+"""CPU oracle bindings (TEST INFRASTRUCTURE -- never imported by the product path).
+
+ctypes wrappers over ``oracle/_build/libilsm_oracle.so`` (the CPU restatement, ``ilsm_oracle.cpp``) and
+``oracle/_ref/libref_nanoflann.so`` (the reference's own vendored nanoflann 1.3.2, the only reference
+component that compiles here).  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this package.
+
+Parity status: unpinned except k-NN (see header of ``ilsm_oracle.cpp``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    need_ref = (not os.path.exists(_REF)) and os.path.exists("/root/reference/include/nanoflann.hpp")
+    if force or stale or need_ref:
+        subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
+
+
+class Factor(C.Structure):
+    _fields_ = [("type", C.c_int32), ("src", C.c_int32), ("p", C.c_double * 3), ("a", C.c_double * 3),
+                ("b", C.c_double * 3)]
+
+
+FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
+assert FACTOR_DTYPE.itemsize == C.sizeof(Factor) == 80
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("termination", C.c_int32), ("iterations", C.c_int32), ("num_successful", C.c_int32),
+                ("num_unsuccessful", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("num_evals", C.c_int32), ("pad", C.c_int32)]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def ref():
+    """The reference's vendored nanoflann (None when oracle/_ref was never built)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF):
+            build()
+        if not os.path.exists(_REF):
+            return None
+        _ref = C.CDLL(_REF)
+        _ref.ref_kdtree_build.restype = C.c_void_p
+        _ref.ref_kdtree_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _ref.ref_kdtree_free.argtypes = [C.c_void_p]
+        _ref.ref_kdtree_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    return _ref
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def knn_brute(map_xyz, q_xyz, k=5):
+    m, q = _f32(map_xyz), _f32(q_xyz)
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    lib().orc_knn_brute(_p(m), len(m), m.strides[0], _p(q), len(q), q.strides[0], k, _p(idx), _p(d2))
+    return idx, d2
+
+
+def knn_kdtree(map_xyz, q_xyz, k=5):
+    m, q = _f32(map_xyz), _f32(q_xyz)
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    lib().orc_knn_kdtree(_p(m), len(m), m.strides[0], _p(q), len(q), q.strides[0], k, _p(idx), _p(d2))
+    return idx, d2
+
+
+class RefKdTree:
+    """nanoflann::KDTreeSingleIndexAdaptor<L2_Simple<float>,3> from /root/reference/include (prebuilt)."""
+
+    def __init__(self, map_xyz, leaf_max=10):
+        self._m = _f32(map_xyz)
+        self._r = ref()
+        if self._r is None:
+            raise RuntimeError("oracle/_ref/libref_nanoflann.so not built")
+        self._h = self._r.ref_kdtree_build(_p(self._m), len(self._m), self._m.strides[0], leaf_max)
+
+    def knn(self, q_xyz, k=5):
+        q = _f32(q_xyz)
+        idx = np.empty((len(q), k), np.int32)
+        d2 = np.empty((len(q), k), np.float32)
+        self._r.ref_kdtree_knn(self._h, _p(q), len(q), q.strides[0], k, _p(idx), _p(d2))
+        return idx, d2
+
+    def __del__(self):
+        try:
+            self._r.ref_kdtree_free(self._h)
+        except Exception:
+            pass
+
+
+def transform_points(qt, pts):
+    p = _f32(pts)
+    qt = np.ascontiguousarray(qt, np.float64)
+    out = np.empty((len(p), 3), np.float32)
+    lib().orc_transform_points(_p(qt), _p(p), len(p), p.strides[0], _p(out))
+    return out
+
+
+def fit_line(nb5x3):
+    nb = np.ascontiguousarray(nb5x3, np.float32).reshape(15)
+    f = np.zeros(1, FACTOR_DTYPE)
+    ok = lib().orc_fit_line(_p(nb), _p(f))
+    return bool(ok), f[0]
+
+
+def fit_plane(nb5x3):
+    nb = np.ascontiguousarray(nb5x3, np.float32).reshape(15)
+    f = np.zeros(1, FACTOR_DTYPE)
+    ok = lib().orc_fit_plane(_p(nb), _p(f))
+    return bool(ok), f[0]
+
+
+def associate(map_corner, map_surf, corner, surf, qt):
+    mc, ms, c, s = _f32(map_corner), _f32(map_surf), _f32(corner), _f32(surf)
+    assert mc.strides[0] == ms.strides[0] and c.strides[0] == s.strides[0]
+    qt = np.ascontiguousarray(qt, np.float64)
+    out = np.zeros(len(c) + len(s), FACTOR_DTYPE)
+    n = lib().orc_associate(_p(mc), len(mc), _p(ms), len(ms), mc.strides[0], _p(c), len(c), _p(s), len(s),
+                            c.strides[0], _p(qt), _p(out))
+    return out[:n]
+
+
+def evaluate(factors, qt, huber_a=0.1, want_residuals=False):
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    qt = np.ascontiguousarray(qt, np.float64)
+    cost = C.c_double()
+    H = np.zeros((6, 6))
+    g = np.zeros(6)
+    res = np.zeros((len(f), 3)) if want_residuals else None
+    lib().orc_eval(_p(f), len(f), _p(qt), C.c_double(huber_a), C.byref(cost), _p(H), _p(g),
+                   _p(res) if want_residuals else None)
+    return (cost.value, H, g, res) if want_residuals else (cost.value, H, g)
+
+
+def solve(factors, qt, max_iter=4, huber_a=0.1):
+    f = np.ascontiguousarray(factors, FACTOR_DTYPE)
+    x = np.array(qt, np.float64)
+    s = SolveSummary()
+    lib().orc_solve(_p(f), len(f), _p(x), max_iter, C.c_double(huber_a), C.byref(s))
+    return x, s
+
+
+def register_aloam(map_corner, map_surf, corner, surf, qt, outer=2, max_iter=4):
+    mc, ms, c, s = _f32(map_corner), _f32(map_surf), _f32(corner), _f32(surf)
+    x = np.array(qt, np.float64)
+    sums = (SolveSummary * outer)()
+    nf = np.zeros(2 * outer, np.int32)
+    n = lib().orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), mc.strides[0], _p(c), len(c), _p(s), len(s),
+                                 c.strides[0], _p(x), outer, max_iter, sums, _p(nf))
+    return x, list(sums)[:n], nf

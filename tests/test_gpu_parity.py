@@ -1,0 +1,266 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star): k-NN indices bit-exact under the (d2, index)
+tie-break; residual quantities within 1e-5 relative; converged pose within 1e-4 m / 1e-4 rad."""
+import numpy as np
+import pytest
+
+from conftest import pose7
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5        # residual / normal-equation tolerance stated by the north star
+POSE_M = 1e-4     # metres
+POSE_RAD = 1e-4   # radians
+
+
+def _queries(rng, m, n, spread):
+    return (m[rng.integers(0, len(m), n)] + rng.normal(0, spread, (n, 3))).astype(np.float32)
+
+
+@pytest.mark.parametrize("k", [1, 5, 8])
+@pytest.mark.parametrize("cell", [0.0, 0.5, 2.0])
+def test_knn_bit_exact(ctx, oracle_mod, cfg_small, k, cell):
+    rng = np.random.default_rng(100 + k)
+    m = cfg_small["map_surf"]
+    q = np.concatenate([_queries(rng, m, 1500, 0.3), _queries(rng, m, 300, 3.0),
+                        rng.uniform(-150, 150, (60, 3)).astype(np.float32)])  # far queries: ring expansion + brute force
+    lm = ctx.new_map().set_input_cloud(m, cell)
+    assert len(lm) == len(m)
+    idx, d2 = lm.nearest_k_search(q, k)
+    ri, rd = oracle_mod.knn_kdtree(m, q, k)
+    assert np.array_equal(d2, rd)
+    assert np.array_equal(idx, ri)
+    lm.close()
+
+
+def test_knn_strided_pcl_points_and_max_dist(ctx, oracle_mod, cfg_small):
+    """pcl::PointXYZI layout (32-byte stride) for both map and queries; bounded search is exact inside max_dist."""
+    rng = np.random.default_rng(7)
+    m3 = cfg_small["map_corner"]
+    m = np.zeros((len(m3), 8), np.float32)
+    m[:, :3] = m3
+    m[:, 4] = rng.uniform(0, 255, len(m3))
+    q3 = _queries(rng, m3, 2000, 0.5)
+    q = np.zeros((len(q3), 8), np.float32)
+    q[:, :3] = q3
+    lm = ctx.new_map().set_input_cloud(m)
+    idx, d2 = lm.nearest_k_search(q, 5, max_dist=1.0)
+    ri, rd = oracle_mod.knn_kdtree(m3, q3, 5)
+    inside = rd < 1.0
+    assert inside.any() and (~inside).any()
+    assert np.array_equal(idx[inside], ri[inside]) and np.array_equal(d2[inside], rd[inside])
+    full = inside.all(axis=1)
+    assert np.array_equal(idx[full], ri[full])
+    lm.close()
+
+
+def test_knn_edge_cases(ctx, oracle_mod):
+    # fewer map points than k, duplicates (exact ties -> lower index first), empty query set, empty map
+    m = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 0], [0, 2, 0]], np.float32)
+    lm = ctx.new_map().set_input_cloud(m)
+    idx, d2 = lm.nearest_k_search(np.array([[0.9, 0, 0], [50, 50, 50]], np.float32), 5)
+    ri, rd = oracle_mod.knn_brute(m, np.array([[0.9, 0, 0], [50, 50, 50]], np.float32), 5)
+    assert np.array_equal(idx, ri) and np.array_equal(d2, rd)
+    assert idx[0].tolist() == [1, 2, 0, 3, -1]
+    idx, d2 = lm.nearest_k_search(np.zeros((0, 3), np.float32), 5)
+    assert idx.shape == (0, 5)
+    lm.set_input_cloud(np.zeros((0, 3), np.float32))
+    idx, d2 = lm.nearest_k_search(np.zeros((3, 3), np.float32), 5)
+    assert (idx == -1).all() and np.isinf(d2).all()
+    # symmetric ties on a lattice: six neighbours at distance 1 -> indices 0..4
+    m = np.array([[1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [5, 5, 5]], np.float32)
+    lm.set_input_cloud(m)
+    idx, d2 = lm.nearest_k_search(np.zeros((1, 3), np.float32), 5)
+    assert idx[0].tolist() == [0, 1, 2, 3, 4] and (d2 == 1.0).all()
+    # NaN points are skipped at build time (mapOptimization.cpp:151 strips them first)
+    m = np.array([[0, 0, 0], [np.nan, 0, 0], [2, 0, 0]], np.float32)
+    lm.set_input_cloud(m)
+    idx, d2 = lm.nearest_k_search(np.array([[1.2, 0, 0]], np.float32), 2)
+    assert idx[0].tolist() == [2, 0]
+    lm.close()
+
+
+def test_knn_rebuild_reuses_handle(ctx, oracle_mod, cfg_small):
+    """setInputCloud is called every frame on the same kd-tree object (laserMapping.cpp:631-634)."""
+    rng = np.random.default_rng(9)
+    lm = ctx.new_map()
+    for n in (5000, 12000, 800):
+        m = cfg_small["map_surf"][rng.permutation(len(cfg_small["map_surf"]))[:n]]
+        q = _queries(rng, m, 500, 0.4)
+        lm.set_input_cloud(m)
+        idx, d2 = lm.nearest_k_search(q, 5)
+        ri, rd = oracle_mod.knn_kdtree(m, q, 5)
+        assert np.array_equal(idx, ri) and np.array_equal(d2, rd)
+    lm.close()
+
+
+def _maps(ctx, c):
+    return ctx.new_map().set_input_cloud(c["map_corner"]), ctx.new_map().set_input_cloud(c["map_surf"])
+
+
+def _cmp_factors(got, want):
+    assert np.array_equal(got["type"], want["type"])
+    assert np.array_equal(got["src"], want["src"])
+    assert np.array_equal(got["p"], want["p"])
+    pl = want["type"] == 2
+    assert np.allclose(got["a"][pl], want["a"][pl], rtol=0, atol=1e-9)
+    assert np.allclose(got["b"][pl][:, 0], want["b"][pl][:, 0], rtol=1e-9, atol=1e-9)
+    ed = want["type"] == 1
+    # the sign of an eigenvector is arbitrary: (a, b) may come out swapped (same residual up to sign)
+    ga, gb, wa, wb = got["a"][ed], got["b"][ed], want["a"][ed], want["b"][ed]
+    same = np.maximum(np.abs(ga - wa).max(1), np.abs(gb - wb).max(1))
+    swap = np.maximum(np.abs(ga - wb).max(1), np.abs(gb - wa).max(1))
+    assert (np.minimum(same, swap) < 1e-9).all()
+
+
+def test_associate_parity(ctx, oracle_mod, cfg_small):
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    qt = pose7(c["q0"], c["t0"])
+    fac, idx, d2 = ctx.associate(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"], want_knn=True)
+    want = oracle_mod.associate(c["map_corner"], c["map_surf"], c["corner"], c["surf"], qt)
+    # the k-NN behind the factors: bit-exact wherever the 5th neighbour passes the d2 < 1 gate
+    pw_c = oracle_mod.transform_points(qt, c["corner"])
+    pw_s = oracle_mod.transform_points(qt, c["surf"])
+    ri = np.concatenate([oracle_mod.knn_kdtree(c["map_corner"], pw_c, 5)[0], oracle_mod.knn_kdtree(c["map_surf"], pw_s, 5)[0]])
+    rd = np.concatenate([oracle_mod.knn_kdtree(c["map_corner"], pw_c, 5)[1], oracle_mod.knn_kdtree(c["map_surf"], pw_s, 5)[1]])
+    gate = rd[:, 4] < 1.0
+    assert gate.sum() > 500
+    assert np.array_equal(idx[gate], ri[gate]) and np.array_equal(d2[gate], rd[gate])
+    assert (d2[~gate][:, 4] >= 1.0).all() or np.isinf(d2[~gate][:, 4]).any()
+    _cmp_factors(fac, want)
+    assert (fac["type"] == 1).sum() > 50 and (fac["type"] == 2).sum() > 300
+    mc.close(), ms.close()
+
+
+def test_eval_normal_eq_parity(ctx, oracle_mod, cfg_small):
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    qt = pose7(c["q0"], c["t0"])
+    ctx.associate(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    want_f = oracle_mod.associate(c["map_corner"], c["map_surf"], c["corner"], c["surf"], qt)
+    rng = np.random.default_rng(2)
+    for trial in range(4):
+        q = c["q0"] + rng.normal(0, 0.01, 4) * (trial > 0)
+        q /= np.linalg.norm(q)
+        t = c["t0"] + rng.normal(0, 0.1, 3) * (trial > 0)
+        for huber in (0.1, 0.0):
+            cost, H, g = ctx.eval_normal_eq(q, t, huber)
+            wc, wH, wg = oracle_mod.evaluate(want_f, pose7(q, t), huber)
+            assert abs(cost - wc) <= REL * abs(wc)
+            assert np.abs(H - wH).max() <= REL * np.abs(wH).max()
+            assert np.abs(g - wg).max() <= REL * np.abs(wg).max()
+            # far inside the stated tolerance in practice
+            assert abs(cost - wc) <= 1e-10 * abs(wc)
+    mc.close(), ms.close()
+
+
+@pytest.mark.parametrize("max_iter", [0, 1, 4, 10, 50])
+def test_solve_parity(ctx, oracle_mod, cfg_small, max_iter):
+    """Device-resident Levenberg-Marquardt == restated Ceres loop: same accept/reject sequence, same termination."""
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    qt = pose7(c["q0"], c["t0"])
+    ctx.associate(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    want_f = oracle_mod.associate(c["map_corner"], c["map_surf"], c["corner"], c["surf"], qt)
+    q, t, s = ctx.solve(c["q0"], c["t0"], max_iter, 0.1)
+    wx, ws = oracle_mod.solve(want_f, qt, max_iter, 0.1)
+    assert s.termination == ws.termination
+    assert s.iterations == ws.iterations
+    assert s.num_successful_steps == ws.num_successful and s.num_unsuccessful_steps == ws.num_unsuccessful
+    assert s.num_evaluations == ws.num_evals
+    assert abs(s.initial_cost - ws.initial_cost) <= REL * ws.initial_cost
+    assert abs(s.final_cost - ws.final_cost) <= REL * ws.final_cost
+    assert np.linalg.norm(t - wx[4:]) < POSE_M
+    assert np.abs(q - wx[:4]).max() < POSE_RAD / 2
+    mc.close(), ms.close()
+
+
+def _register_both(ctx, oracle_mod, ilsm, c, **kw):
+    mc, ms = _maps(ctx, c)
+    opts = ilsm.default_opts(**kw)
+    q, t, rep = ctx.register(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"], opts)
+    wx, wsum, wnf = oracle_mod.register_aloam(c["map_corner"], c["map_surf"], c["corner"], c["surf"], pose7(c["q0"], c["t0"]),
+                                             outer=opts.outer_iterations, max_iter=opts.max_num_iterations)
+    mc.close(), ms.close()
+    return q, t, rep, wx, wsum, wnf
+
+
+def _check_registration(ilsm, q, t, rep, wx, wsum, wnf):
+    assert rep.passes == len(wsum)
+    for p in range(rep.passes):
+        g, w = rep.pass_[p], wsum[p]
+        assert g.num_edge_factors == wnf[2 * p] and g.num_plane_factors == wnf[2 * p + 1]
+        assert g.termination == w.termination and g.iterations == w.iterations
+        assert abs(g.final_cost - w.final_cost) <= REL * w.final_cost
+    assert np.linalg.norm(t - wx[4:]) < POSE_M
+    assert ilsm.synth.quat_angle(q, wx[:4]) < POSE_RAD
+
+
+def test_register_parity_small(ctx, oracle_mod, ilsm, cfg_small):
+    out = _register_both(ctx, oracle_mod, ilsm, cfg_small)
+    _check_registration(ilsm, *out)
+    q, t = out[0], out[1]
+    assert np.linalg.norm(t - cfg_small["t_true"]) < 0.03  # and it actually registers the frame
+
+
+def test_register_parity_config1_full(ctx, oracle_mod, ilsm, cfg_full):
+    """BASELINE config 1 at full size: OS0-64 frame vs 100k-point map, laserMapping settings (2 x <=4 iterations)."""
+    out = _register_both(ctx, oracle_mod, ilsm, cfg_full)
+    _check_registration(ilsm, *out)
+
+
+def test_register_mapoptimization_settings(ctx, oracle_mod, ilsm, cfg_small):
+    """mapOptimization.cpp:377-450: plane factors only, one pass, max 10 iterations, termination type reported."""
+    c = dict(cfg_small)
+    c["corner"] = np.zeros((0, 4), np.float32)
+    mc, ms = _maps(ctx, c)
+    opts = ilsm.default_opts(outer_iterations=1, max_num_iterations=10, min_corner_map=0, min_surf_map=0)
+    q, t, rep = ctx.register(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"], opts)
+    want_f = oracle_mod.associate(c["map_corner"], c["map_surf"], c["corner"], c["surf"], pose7(c["q0"], c["t0"]))
+    wx, ws = oracle_mod.solve(want_f, pose7(c["q0"], c["t0"]), 10, 0.1)
+    g = rep.pass_[0]
+    assert g.num_edge_factors == 0 and g.num_plane_factors == (want_f["type"] == 2).sum()
+    assert g.termination == ws.termination and g.iterations == ws.iterations
+    assert np.linalg.norm(t - wx[4:]) < POSE_M and ilsm.synth.quat_angle(q, wx[:4]) < POSE_RAD
+    mc.close(), ms.close()
+
+
+def test_register_guard_and_empty_inputs(ctx, ilsm, cfg_small):
+    c = cfg_small
+    mc = ctx.new_map().set_input_cloud(c["map_corner"][:10])
+    ms = ctx.new_map().set_input_cloud(c["map_surf"])
+    with pytest.raises(ilsm.IlsmError) as e:  # laserMapping.cpp:624
+        ctx.register(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    assert e.value.code == -4
+    # no feature points at all: Ceres reports CONVERGENCE with the pose untouched
+    mc.set_input_cloud(c["map_corner"])
+    q, t, rep = ctx.register(mc, ms, np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), c["q0"], c["t0"])
+    assert np.array_equal(q, c["q0"]) and np.array_equal(t, c["t0"])
+    assert rep.pass_[0].termination == ilsm.CONVERGENCE and rep.pass_[0].iterations == 0
+    mc.close(), ms.close()
+
+
+def test_register_is_deterministic(ctx, ilsm, cfg_small):
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    outs = [ctx.register(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"]) for _ in range(3)]
+    for q, t, _ in outs[1:]:
+        assert np.array_equal(q, outs[0][0]) and np.array_equal(t, outs[0][1])
+    mc.close(), ms.close()
+
+
+def test_register_dev_matches_host_entry(ctx, ilsm, cfg_small):
+    import torch
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    q, t, rep = ctx.register(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    dc = torch.from_numpy(c["corner"]).cuda()
+    ds = torch.from_numpy(c["surf"]).cuda()
+    pose = torch.from_numpy(pose7(c["q0"], c["t0"])).cuda()
+    torch.cuda.synchronize()
+    ctx.register_dev(mc, ms, dc.data_ptr(), len(dc), ds.data_ptr(), len(ds), 16, pose.data_ptr())
+    ctx.sync()
+    out = pose.cpu().numpy()
+    assert np.array_equal(out[:4], q) and np.array_equal(out[4:], t)
+    mc.close(), ms.close()
