@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- scan-to-map registrations/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+A "step" is one pass of the reference's per-frame mapping hot section over one synthetic OS0-64 frame
+(laserMapping.cpp:624-861): rebuild the corner and surf search structures over the 100k-point local map
+(kdtree->setInputCloud x2), then 2 x [associate every stack point (pose transform, exact 5-NN, line/plane fit)
++ ceres::Solve (LM, <= 4 iterations)].
+
+  value : device-timed (CUDA events on the library's stream), map + feature stacks already resident in HBM.
+  e2e   : the same step through the host-pointer C ABI (ilsm_map_build x2 + ilsm_register) from pinned host
+          buffers, host<->device copies inside the timed region, wall-clocked around the blocking calls.
+  roofline     : the dominant kernel (associate_kernel: k-NN + fit) timed alone, algorithmic bytes / time.
+  cpu_baseline : the CPU oracle (a port of the reference path, single thread like the reference's mapping
+                 thread) on a bounded sample of the same workload.
+
+`--impl reference` times that CPU path alone (the reference itself cannot be built here).
+N > 1 (torchrun): independent replicas, one per GPU, no data-path collective ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scan-to-map registrations/sec (OS0-64 frame, 100k-pt map)"
+UNIT = "registrations/s"
+N_MAP = 100_000
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(seed_shift=0):
+    import ilsm_b200 as ilsm
+    return ilsm.synth.config1(n_map=N_MAP, seed_shift=seed_shift)
+
+
+def pad4(a):
+    out = np.zeros((len(a), 4), np.float32)
+    out[:, :3] = a[:, :3]
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference path)
+# ----------------------------------------------------------------------------------------------------
+def cpu_registrations_per_s(c, budget_s, min_reps=3):
+    import oracle
+    qt0 = np.concatenate([c["q0"], c["t0"]])
+    mc, ms, co, su = c["map_corner"], c["map_surf"], c["corner"], c["surf"]
+    oracle.register_aloam(mc, ms, co, su, qt0)  # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        oracle.register_aloam(mc, ms, co, su, qt0)
+        reps += 1
+        el = time.perf_counter() - t0
+        if reps >= min_reps and el >= budget_s:
+            break
+    return reps / el, reps, el
+
+
+def run_reference(args, rank, world):
+    """The reference arm: a step is ONE registration of the same frame by the CPU path (same definition as the
+    GPU arm).  Rank 0 alone runs it."""
+    if rank != 0:
+        return
+    import oracle
+    c = workload()
+    qt0 = np.concatenate([c["q0"], c["t0"]])
+    a = (c["map_corner"], c["map_surf"], c["corner"], c["surf"], qt0)
+    for _ in range(max(args.warmup, 1)):
+        oracle.register_aloam(*a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x, sums, nf = oracle.register_aloam(*a)
+    wall = time.perf_counter() - t0
+    assert float(np.linalg.norm(x[4:] - c["t_true"])) < 0.05
+    value = args.steps / wall
+    sample = f"{args.steps} registrations of the config-1 frame in {wall:.2f} s"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 k-NN / f64 fit+solve", "data": "synthetic",
+        "config": {"workload": "configs[0] shape: one OS0-64 frame (64x1024) vs 100k-pt local map per step: "
+                               "2 x k-d tree build + 2 x (5-NN association + LM<=4); CPU oracle port of "
+                               "laserMapping.cpp:624-861 (the reference itself cannot be built here)",
+                   "n_map": N_MAP, "n_corner_stack": int(len(c["corner"])), "n_surf_stack": int(len(c["surf"]))},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "note": "single thread: the reference runs this path on one thread "
+                                 "(laserMapping.cpp:1215 mapping_process, Ceres num_threads default 1)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import ilsm_b200 as ilsm
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+
+    ilsm._build.build()
+    c = workload(seed_shift=rank)  # one independent frame/sequence per rank
+    ctx = ilsm.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
+    mc, ms = ctx.new_map(), ctx.new_map()
+    opts = ilsm.default_opts()
+
+    # ---- device-resident inputs
+    h_mc, h_ms = pad4(c["map_corner"]), pad4(c["map_surf"])
+    h_c, h_s = pad4(c["corner"]), pad4(c["surf"])
+    pose0 = np.concatenate([c["q0"], c["t0"]])
+    d_mc, d_ms = torch.from_numpy(h_mc).to(dev), torch.from_numpy(h_ms).to(dev)
+    d_c, d_s = torch.from_numpy(h_c).to(dev), torch.from_numpy(h_s).to(dev)
+    d_pose0 = torch.from_numpy(pose0).to(dev)
+    d_pose = d_pose0.clone()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_dev():
+        d_pose.copy_(d_pose0, non_blocking=True)
+        mc.build_dev(d_mc.data_ptr(), len(h_mc), 16)
+        ms.build_dev(d_ms.data_ptr(), len(h_ms), 16)
+        ctx.register_dev(mc, ms, d_c.data_ptr(), len(h_c), d_s.data_ptr(), len(h_s), 16, d_pose.data_ptr(), opts)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ext):
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            step_dev()
+        ctx.sync()
+        # sanity: the device path must land on the true pose (no work skipped)
+        pose = d_pose.cpu().numpy()
+        err_t = float(np.linalg.norm(pose[4:] - c["t_true"]))
+        assert err_t < 0.05, f"registration did not converge: {err_t} m"
+
+        sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                               int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+        sampler.start()
+        barrier()
+        launches0 = ilsm.launch_count()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            step_dev()
+            e1.record(ext)
+            evs.append((e0, e1))
+        ctx.sync()
+        barrier()
+        launches = ilsm.launch_count() - launches0
+        ms_steps = [a.elapsed_time(b) for a, b in evs]
+        dev_ms = float(np.sum(ms_steps))
+
+        # ---- e2e through the host-pointer ABI from pinned buffers
+        p_mc, p_ms = torch.from_numpy(h_mc).pin_memory(), torch.from_numpy(h_ms).pin_memory()
+        p_c, p_s = torch.from_numpy(h_c).pin_memory(), torch.from_numpy(h_s).pin_memory()
+        n_mc, n_ms, n_c, n_s = p_mc.numpy(), p_ms.numpy(), p_c.numpy(), p_s.numpy()
+
+        def step_host():
+            mc.set_input_cloud(n_mc)
+            ms.set_input_cloud(n_ms)
+            return ctx.register(mc, ms, n_c, n_s, c["q0"], c["t0"], opts)
+
+        for _ in range(3):
+            step_host()
+        barrier()
+        e2e_times = []
+        for _ in range(args.steps):
+            flush.zero_()
+            ctx.sync()
+            t0 = time.perf_counter()
+            q, t, rep = step_host()
+            e2e_times.append(time.perf_counter() - t0)
+        barrier()
+        e2e_s = float(np.sum(e2e_times))
+        assert float(np.linalg.norm(t - c["t_true"])) < 0.05
+        h2d = h_mc.nbytes + h_ms.nbytes + h_c.nbytes + h_s.nbytes + 56
+        d2h = 56 + 8 + 8 * 48
+
+        # ---- dominant kernel alone (associate_kernel: pose transform + exact 5-NN + fit), CUDA events
+        reps = 20
+        mc.build_dev(d_mc.data_ptr(), len(h_mc), 16)
+        ms.build_dev(d_ms.data_ptr(), len(h_ms), 16)
+        kt = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            for _ in range(reps):
+                ctx.associate_dev(mc, ms, d_c.data_ptr(), len(h_c), d_s.data_ptr(), len(h_s), 16, d_pose0.data_ptr(), opts)
+            e1.record(ext)
+            ctx.sync()
+            kt.append(e0.elapsed_time(e1) / reps)
+        assoc_ms = float(np.median(kt))
+        clocks = sampler.stop()
+
+    # ---- aggregate over ranks (max time)
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = [float(x) for x in t_dev.cpu()]
+    value = world * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = world * args.steps / (e2e_ms_max * 1e-3)
+
+    peak, peak_src = load_peaks()
+    nq = len(h_c) + len(h_s)
+    # algorithmic bytes of one associate launch: map points 16 B each (both maps), stack point 16 B in,
+    # 5 x (idx + d2) = 40 B of k-NN result, factor record 84 B out
+    assoc_bytes = 16 * (len(h_mc) + len(h_ms)) + nq * (16 + 40 + 84)
+    achieved = assoc_bytes / (assoc_ms * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, reps_cpu, el = cpu_registrations_per_s(c, args.cpu_seconds, 5)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{reps_cpu} registrations of the same frame/map in {el:.1f} s (CPU oracle, 1 thread: the "
+                         f"reference's mapping loop is single-threaded, laserMapping.cpp:1215)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 k-NN / f64 fit+solve", "data": "synthetic",
+            "config": {"workload": "configs[0] shape: one OS0-64 frame (64x1024) vs 100k-pt local map per step: "
+                                   "2 x voxel-hash build + 2 x (associate + LM<=4); one independent frame per GPU",
+                       "n_map": N_MAP, "n_corner_stack": int(len(h_c)), "n_surf_stack": int(len(h_s)),
+                       "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"replicas x{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_max / args.steps, "timing": "host wall clock around the blocking C-ABI calls"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "associate_kernel<32>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": int(assoc_bytes), "kernel_ms": assoc_ms,
+                         "note": "config-1 sizes are launch/latency-bound (2.0 MB per launch = 0.3 us at peak); see "
+                                 "DESIGN.md and the config-3 sweep (tools/sweep.py) for the bandwidth regime"},
+            "clocks": clocks,
+            "pose_error_m": err_t,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    mc.close(), ms.close(), ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

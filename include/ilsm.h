@@ -160,6 +160,15 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_s
                    const float* surf, int ns, int stride_bytes, const double q_xyzw[4], const double t_xyz[3],
                    const ilsm_reg_opts* opts, ilsm_factor* factors, int32_t* knn_idx, float* knn_d2);
 
+/* Device-resident association only (no export, no synchronisation): the k-NN + fit kernel on the context stream,
+ * pose read from d_pose7.  Used by bench.py to time the kernel in isolation. */
+ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* d_corner, int nc,
+                                const float* d_surf, int ns, int stride_bytes, const double* d_pose7,
+                                const ilsm_reg_opts* opts);
+
+/* Number of kernels this library has launched since it was loaded (all contexts). */
+ILSM_API long long ilsm_launch_count(void);
+
 /* One evaluation of the robustified problem at (q,t) over the factors held by the context:
  * cost = 1/2 sum rho(|r|^2), JtJ (6x6 row-major, tangent order [rotation(3), translation(3)] of
  * EigenQuaternionParameterization) and Jtr.  This is the single kernel a Gauss-Newton/LM iteration needs.

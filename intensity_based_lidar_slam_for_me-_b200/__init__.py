@@ -5,7 +5,7 @@ marshalling + host-side mirror of the reference call sites) and synth.py (seeded
 """
 from . import _build, synth  # noqa: F401
 from .binding import (CONVERGENCE, FAILURE, NO_CONVERGENCE, Context, IlsmError, LocalMap, RegOpts, RegReport,  # noqa: F401
-                      SolveSummary, default_opts, load_library, FACTOR_DTYPE)
+                      SolveSummary, default_opts, launch_count, load_library, FACTOR_DTYPE)
 
 __all__ = ["Context", "LocalMap", "RegOpts", "RegReport", "SolveSummary", "default_opts", "load_library", "IlsmError",
            "synth", "CONVERGENCE", "NO_CONVERGENCE", "FAILURE", "FACTOR_DTYPE"]

@@ -74,6 +74,8 @@ def load_library(path: str | None = None):
         "ilsm_register": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport)]),
         "ilsm_register_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts), vp]),
         "ilsm_associate": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), vp, vp, vp]),
+        "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
+        "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
         "ilsm_solve": (i32, [vp, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
     }
@@ -82,6 +84,10 @@ def load_library(path: str | None = None):
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    return int(load_library().ilsm_launch_count())
 
 
 def _check(rc):
@@ -159,6 +165,11 @@ class Context:
                      opts: RegOpts | None = None, d_report_ptr=None):
         _check(self._lib.ilsm_register_dev(self._h, map_corner._h, map_surf._h, d_corner_ptr, nc, d_surf_ptr, ns, stride,
                                            d_pose_ptr, C.byref(opts) if opts is not None else None, d_report_ptr))
+
+    def associate_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
+                      opts: RegOpts | None = None):
+        _check(self._lib.ilsm_associate_dev(self._h, map_corner._h, map_surf._h, d_corner_ptr, nc, d_surf_ptr, ns,
+                                            stride, d_pose_ptr, C.byref(opts) if opts is not None else None))
 
     def associate(self, map_corner, map_surf, corner, surf, q, t, opts: RegOpts | None = None, want_knn=False):
         c, nc, sc = _cloud(corner)

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 
 #include "ilsm_host.hpp"
@@ -20,6 +21,9 @@ int fail_cuda(cudaError_t e, const char* where) {
   cudaGetLastError();
   return ILSM_ERR_CUDA;
 }
+static std::atomic<long long> g_launches{0};
+void count_launches(int k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
 int check_launch(const char* where) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, where);
@@ -138,6 +142,7 @@ struct ilsm_map {
 extern "C" {
 
 ILSM_API int ilsm_abi_version(void) { return ILSM_ABI_VERSION; }
+ILSM_API long long ilsm_launch_count(void) { return g_launches.load(); }
 ILSM_API const char* ilsm_last_error(void) { return g_err; }
 
 ILSM_API void ilsm_reg_opts_default(ilsm_reg_opts* o) {
@@ -293,9 +298,25 @@ ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const 
   if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
     return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
   pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, nullptr, 0);
+  count_launches(2);
   if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
   pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, d_report, 1);
   return check_launch("register_dev");
+}
+
+ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* d_corner, int nc,
+                                const float* d_surf, int ns, int stride_bytes, const double* d_pose7,
+                                const ilsm_reg_opts* opts) {
+  int rc = check_reg_args(ctx, mc, ms, d_corner, nc, d_surf, ns, stride_bytes);
+  if (rc) return rc;
+  if (!d_pose7) return fail(ILSM_ERR_INVALID_ARG, "associate_dev: null pose");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, const_cast<double*>(d_pose7), nullptr, 0);
+  count_launches(1);
+  return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, 0, false);
 }
 
 ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,
@@ -316,6 +337,7 @@ ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const floa
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
+  count_launches(1);
   if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
   // pose (7 doubles, xq/xt are adjacent) and the report come back through pinned memory
   unsigned char* pin = c.pinned.p;
@@ -348,6 +370,7 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const flo
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
+  count_launches(1);
   const bool want_knn = knn_idx != nullptr && knn_d2 != nullptr;
   if ((rc = c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, 0, want_knn))) return rc;
   const int n = nc + ns;
@@ -377,6 +400,7 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q[4], const double 
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, huber_a);
+  count_launches(1);
   int rc;
   if ((rc = c.partials.reserve(64))) return rc;
   // eval_out lives at the tail of the partials buffer? keep it simple: dedicated 32 doubles in out_d2 scratch
@@ -411,6 +435,7 @@ ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_ite
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
   lm_arm_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, max_num_iterations, huber_a, 0);
+  count_launches(2);
   int rc;
   if ((rc = c.eval_launch(1 + max_num_iterations))) return rc;
   unsigned char* pin = c.pinned.p;

@@ -15,6 +15,7 @@ namespace ilsm {
 int fail(int code, const char* msg);
 int fail_cuda(cudaError_t e, const char* where);
 int check_launch(const char* where);
+void count_launches(int k);
 
 #define ILSM_CUDA(call)                                        \
   do {                                                         \

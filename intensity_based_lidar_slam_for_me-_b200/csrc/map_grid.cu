@@ -157,6 +157,7 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
     grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p);
     grid_scatter_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(orig.p, n_pts, cells.p, slot_of.p, rank_of.p, sorted.p);
   }
+  count_launches(n_pts > 0 ? 4 : 1);
   return check_launch("map_build");
 }
 
@@ -201,6 +202,7 @@ int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_di
     launch_knn<5>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
   else
     launch_knn<8>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+  count_launches(1);
   return check_launch("knn");
 }
 

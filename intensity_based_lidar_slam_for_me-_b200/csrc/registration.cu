@@ -663,6 +663,7 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
     associate_kernel<8><<<(n + T / 8 - 1) / (T / 8), T, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p,
                                                                        prm, fv);
   }
+  count_launches(1);
   return check_launch("associate");
 }
 
@@ -675,6 +676,7 @@ int Ctx::eval_launch(int count) {
   FactorView fv = factor_view(fac, false);
   for (int k = 0; k < count; ++k)
     eval_kernel<<<blocks, T, 0, stream>>>(fv, fac.n, lm.p, partials.p, nullptr, 0);
+  count_launches(count);
   return check_launch("eval");
 }
 
@@ -697,6 +699,7 @@ int eval_only_launch(Ctx* c, double* d_out) {
   if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
   FactorView fv = factor_view(c->fac, false);
   eval_kernel<<<blocks, T, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out, 1);
+  count_launches(1);
   return check_launch("eval_only");
 }
 
@@ -723,6 +726,7 @@ int factors_export(Ctx* c, ilsm_factor* d_out) {
   if (c->fac.n == 0) return ILSM_OK;
   FactorView fv = factor_view(c->fac, false);
   factors_export_kernel<<<(c->fac.n + 255) / 256, 256, 0, c->stream>>>(fv, c->fac.n, c->fac.nc, d_out);
+  count_launches(1);
   return check_launch("factors_export");
 }
 

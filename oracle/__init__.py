@@ -82,6 +82,10 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _stride(a):
+    return a.strides[0] if len(a) else 4 * a.shape[1]
+
+
 def knn_brute(map_xyz, q_xyz, k=5):
     m, q = _f32(map_xyz), _f32(q_xyz)
     idx = np.empty((len(q), k), np.int32)
@@ -146,11 +150,11 @@ def fit_plane(nb5x3):
 
 def associate(map_corner, map_surf, corner, surf, qt):
     mc, ms, c, s = _f32(map_corner), _f32(map_surf), _f32(corner), _f32(surf)
-    assert mc.strides[0] == ms.strides[0] and c.strides[0] == s.strides[0]
+    assert _stride(mc) == _stride(ms) and (len(c) == 0 or len(s) == 0 or _stride(c) == _stride(s))
     qt = np.ascontiguousarray(qt, np.float64)
     out = np.zeros(len(c) + len(s), FACTOR_DTYPE)
-    n = lib().orc_associate(_p(mc), len(mc), _p(ms), len(ms), mc.strides[0], _p(c), len(c), _p(s), len(s),
-                            c.strides[0], _p(qt), _p(out))
+    n = lib().orc_associate(_p(mc), len(mc), _p(ms), len(ms), _stride(mc), _p(c), len(c), _p(s), len(s),
+                            _stride(c) if len(c) else _stride(s), _p(qt), _p(out))
     return out[:n]
 
 
@@ -179,6 +183,6 @@ def register_aloam(map_corner, map_surf, corner, surf, qt, outer=2, max_iter=4):
     x = np.array(qt, np.float64)
     sums = (SolveSummary * outer)()
     nf = np.zeros(2 * outer, np.int32)
-    n = lib().orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), mc.strides[0], _p(c), len(c), _p(s), len(s),
-                                 c.strides[0], _p(x), outer, max_iter, sums, _p(nf))
+    n = lib().orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), _stride(mc), _p(c), len(c), _p(s), len(s),
+                                 _stride(c) if len(c) else _stride(s), _p(x), outer, max_iter, sums, _p(nf))
     return x, list(sums)[:n], nf
