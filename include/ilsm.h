@@ -63,6 +63,11 @@ ILSM_API const char* ilsm_last_error(void);
 ILSM_API int ilsm_create(int device, ilsm_ctx** out);
 ILSM_API void ilsm_destroy(ilsm_ctx* ctx);
 ILSM_API int ilsm_sync(ilsm_ctx* ctx);
+/* on != 0: ilsm_map_build (host pointers) returns as soon as its copy and kernels are enqueued on the map's own
+ * stream; the caller must leave the source buffer untouched until the next blocking call that uses the map
+ * (ilsm_register / ilsm_knn / ilsm_sync).  laserMapping.cpp keeps laserCloud*FromMap alive until the next
+ * frame, so the two setInputCloud replacements can overlap.  Default 0 (blocking, like setInputCloud). */
+ILSM_API int ilsm_set_async(ilsm_ctx* ctx, int on);
 /* cudaStream_t of the context (for CUDA-event timing by the caller). */
 ILSM_API void* ilsm_stream(ilsm_ctx* ctx);
 

@@ -63,6 +63,7 @@ def load_library(path: str | None = None):
         "ilsm_destroy": (None, [vp]),
         "ilsm_sync": (i32, [vp]),
         "ilsm_stream": (vp, [vp]),
+        "ilsm_set_async": (i32, [vp, i32]),
         "ilsm_map_create": (i32, [vp, C.POINTER(vp)]),
         "ilsm_map_destroy": (None, [vp]),
         "ilsm_map_size": (i32, [vp]),
@@ -142,6 +143,10 @@ class Context:
 
     def sync(self):
         _check(self._lib.ilsm_sync(self._h))
+
+    def set_async(self, on: bool = True):
+        """Host-pointer map builds stop blocking (see ilsm_set_async in include/ilsm.h)."""
+        _check(self._lib.ilsm_set_async(self._h, 1 if on else 0))
 
     def new_map(self) -> "LocalMap":
         return LocalMap(self)

@@ -47,19 +47,6 @@ __global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double
   }
 }
 
-__global__ void lm_arm_kernel(LmState* st, int max_iter, double huber_a, int pass) {
-  for (int i = 0; i < 4; ++i) st->cq[i] = st->xq[i];
-  for (int i = 0; i < 3; ++i) st->ct[i] = st->xt[i];
-  st->status = 0, st->phase = 0, st->iteration = 0, st->max_iter = max_iter;
-  st->invalid_run = 0, st->reuse_diag = 0;
-  st->n_success = st->n_unsuccess = st->n_evals = 0;
-  st->n_edge = st->n_plane = 0;
-  st->radius = 1e4, st->decrease_factor = 2.0, st->model_cost_change = 0.0;
-  st->huber_a = huber_a;
-  st->pass = pass;
-  st->ticket = 0u;
-}
-
 __global__ void pose_io_kernel(LmState* st, double* pose7, ilsm_reg_report* report, int direction) {
   // direction 0: pose7 -> state ; 1: state -> pose7 (+ report)
   int t = threadIdx.x;
@@ -109,6 +96,11 @@ void Ctx::release() {
 }
 
 void Map::release() {
+  if (stream) cudaStreamSynchronize(stream);
+  if (ready) cudaEventDestroy(ready);
+  if (ctx_done) cudaEventDestroy(ctx_done);
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr, ready = nullptr, ctx_done = nullptr;
   cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release();
   bbox.release(), raw.release();
 }
@@ -188,11 +180,27 @@ ILSM_API int ilsm_sync(ilsm_ctx* ctx) {
 
 ILSM_API void* ilsm_stream(ilsm_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 
+ILSM_API int ilsm_set_async(ilsm_ctx* ctx, int on) {
+  if (!ctx) return fail(ILSM_ERR_INVALID_ARG, "null ctx");
+  std::lock_guard<std::mutex> lk(ctx->c.mu);
+  ctx->c.async_build = on != 0;
+  return ILSM_OK;
+}
+
 ILSM_API int ilsm_map_create(ilsm_ctx* ctx, ilsm_map** out) {
   if (!ctx || !out) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_create: null argument");
   ilsm_map* m = new (std::nothrow) ilsm_map();
   if (!m) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
-  m->m.ctx = &ctx->c;
+  {
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    cudaSetDevice(ctx->c.device);
+    int rc = m->m.init(&ctx->c);
+    if (rc) {
+      m->m.release();
+      delete m;
+      return rc;
+    }
+  }
   *out = m;
   return ILSM_OK;
 }
@@ -226,9 +234,12 @@ ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_b
   size_t bytes = (size_t)n * stride_bytes;
   int rc;
   if ((rc = m.raw.reserve(bytes / 4 + 4))) return rc;
-  if (bytes) ILSM_CUDA(cudaMemcpyAsync(m.raw.p, xyz, bytes, cudaMemcpyHostToDevice, m.ctx->stream));
+  // the staging buffer may still be read by users of the previous build on the context stream
+  ILSM_CUDA(cudaEventRecord(m.ctx_done, m.ctx->stream));
+  ILSM_CUDA(cudaStreamWaitEvent(m.stream, m.ctx_done, 0));
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(m.raw.p, xyz, bytes, cudaMemcpyHostToDevice, m.stream));
   if ((rc = m.build_dev(m.raw.p, n, stride_bytes, cell))) return rc;
-  ILSM_CUDA(cudaStreamSynchronize(m.ctx->stream));
+  if (!m.ctx->async_build) ILSM_CUDA(cudaStreamSynchronize(m.stream));
   return ILSM_OK;
 }
 
@@ -316,7 +327,7 @@ ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const
   ILSM_CUDA(cudaSetDevice(c.device));
   pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, const_cast<double*>(d_pose7), nullptr, 0);
   count_launches(1);
-  return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, 0, false);
+  return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false);
 }
 
 ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,
@@ -372,7 +383,7 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const flo
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
   count_launches(1);
   const bool want_knn = knn_idx != nullptr && knn_d2 != nullptr;
-  if ((rc = c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, 0, want_knn))) return rc;
+  if ((rc = c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, want_knn))) return rc;
   const int n = nc + ns;
   if (factors && n > 0) {
     // export through out_idx scratch (reinterpreted) to keep allocations few
@@ -434,10 +445,9 @@ ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_ite
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
   set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
-  lm_arm_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, max_num_iterations, huber_a, 0);
-  count_launches(2);
+  count_launches(1);
   int rc;
-  if ((rc = c.eval_launch(1 + max_num_iterations))) return rc;
+  if ((rc = c.solve_launch(max_num_iterations, huber_a, 0))) return rc;
   unsigned char* pin = c.pinned.p;
   ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));

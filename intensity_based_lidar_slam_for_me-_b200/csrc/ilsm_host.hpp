@@ -109,7 +109,14 @@ struct Map {
   DevBuf<uint32_t> slot_of, rank_of, counters;
   DevBuf<int> bbox;
   DevBuf<float> raw;  // staging of caller bytes for the host-pointer entry points
+  // Each map builds on its own stream so that the corner and surf structures of a frame are built concurrently
+  // (and their H2D copies overlap); users on the context stream wait on `ready`.
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr, ctx_done = nullptr;
+  bool pending = false;
 
+  int init(Ctx* c);
+  int wait_ready(cudaStream_t user);
   int build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size);
   int knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2);
   GridView view() const;
@@ -143,9 +150,10 @@ struct Ctx {
 
   int init(int dev);
   void release();
+  bool async_build = false;  // ilsm_set_async: host-pointer map builds return without synchronising
   int associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                    const ilsm_reg_opts& o, bool begin_solve, int pass, bool want_knn);
-  int eval_launch(int count);  // `count` evaluation kernels at the candidate pose held in LmState
+                    const ilsm_reg_opts& o, bool want_knn);
+  int solve_launch(int max_iter, double huber_a, int pass);  // the whole LM solve, one cluster launch
   int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                    const ilsm_reg_opts& o);
 };

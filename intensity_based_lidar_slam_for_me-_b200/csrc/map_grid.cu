@@ -34,7 +34,7 @@ __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i
 
 __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, float inv_cell, GridCell* cells,
                                   uint32_t mask, int log2_size, float4* __restrict__ orig,
-                                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of, int* bbox,
+                                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
                                   uint32_t* counters) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -56,22 +56,30 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
   uint32_t slot = hash_voxel(key, log2_size);
   for (;;) {
     u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
-    if (prev == kEmptyKey) {  // first point of this voxel: extend the occupied bounding box
-      atomicMin(&bbox[0], cx), atomicMin(&bbox[1], cy), atomicMin(&bbox[2], cz);
-      atomicMax(&bbox[3], cx), atomicMax(&bbox[4], cy), atomicMax(&bbox[5], cz);
-      break;
-    }
-    if (prev == key) break;
+    if (prev == kEmptyKey || prev == key) break;
     slot = (slot + 1) & mask;
   }
   slot_of[i] = slot;
   rank_of[i] = atomicAdd(&cells[slot].count, 1u);
 }
 
-__global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* counters) {
+// Every occupied slot gets a contiguous range of the sorted array (warp-aggregated atomicAdd on one cursor) and
+// the bounding box of occupied voxels is reduced per block (6 atomics per block instead of 6 per voxel).
+__global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* counters, int* bbox) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t cnt = i < size ? cells[i].count : 0u;
-  // warp-aggregated allocation: inclusive scan of the counts, one atomic per warp
+  uint32_t cnt = 0;
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  if (i < size) {
+    uint4 e = *reinterpret_cast<const uint4*>(cells + i);
+    cnt = e.w;
+    if (cnt) {
+      u64 key = ((u64)e.y << 32) | e.x;
+      int c[3] = {(int)((key >> 42) & 0x1FFFFF) - kCoordOff, (int)((key >> 21) & 0x1FFFFF) - kCoordOff,
+                  (int)(key & 0x1FFFFF) - kCoordOff};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) lo[a] = hi[a] = c[a];
+    }
+  }
   uint32_t lane = threadIdx.x & 31, inc = cnt;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -83,6 +91,27 @@ __global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* coun
   if (lane == 31 && total) base = atomicAdd(&counters[0], total);
   base = __shfl_sync(0xffffffffu, base, 31);
   if (i < size && cnt) cells[i].start = base + inc - cnt;
+  // bounding box
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+    }
+  }
+  __shared__ int s_lo[3], s_hi[3];
+  if (threadIdx.x < 3) s_lo[threadIdx.x] = INT_MAX, s_hi[threadIdx.x] = INT_MIN;
+  __syncthreads();
+  if (lane == 0 && total) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicMin(&s_lo[a], lo[a]), atomicMax(&s_hi[a], hi[a]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_lo[threadIdx.x] != INT_MAX) {
+    atomicMin(&bbox[threadIdx.x], s_lo[threadIdx.x]);
+    atomicMax(&bbox[3 + threadIdx.x], s_hi[threadIdx.x]);
+  }
 }
 
 __global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, const GridCell* __restrict__ cells,
@@ -131,10 +160,30 @@ static inline int ilog2_ceil(uint32_t v) {
   return l;
 }
 
+int Map::init(Ctx* c) {
+  ctx = c;
+  ILSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  ILSM_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  ILSM_CUDA(cudaEventCreateWithFlags(&ctx_done, cudaEventDisableTiming));
+  return ILSM_OK;
+}
+
+int Map::wait_ready(cudaStream_t user) {
+  if (pending) {
+    ILSM_CUDA(cudaStreamWaitEvent(user, ready, 0));
+    if (user == ctx->stream) pending = false;
+  }
+  return ILSM_OK;
+}
+
 int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size) {
   if (n_pts < 0 || (stride_bytes % 4) != 0 || stride_bytes < 12) return fail(ILSM_ERR_INVALID_ARG, "map_build: bad n/stride");
   if (!(cell_size > 0.f)) cell_size = 1.0f;
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = stream;
+  // order this (re)build after everything already enqueued on the context stream (previous users of the map,
+  // producers of d_src), then run it on the map's own stream
+  ILSM_CUDA(cudaEventRecord(ctx_done, ctx->stream));
+  ILSM_CUDA(cudaStreamWaitEvent(s, ctx_done, 0));
   n = n_pts;
   cell = cell_size;
   inv_cell = 1.0f / cell_size;
@@ -153,11 +202,13 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
   if (n_pts > 0) {
     grid_count_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(d_src, n_pts, stride_bytes / 4, inv_cell, cells.p,
                                                          table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p,
-                                                         bbox.p, counters.p);
-    grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p);
+                                                         counters.p);
+    grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p, bbox.p);
     grid_scatter_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(orig.p, n_pts, cells.p, slot_of.p, rank_of.p, sorted.p);
   }
   count_launches(n_pts > 0 ? 4 : 1);
+  ILSM_CUDA(cudaEventRecord(ready, s));
+  pending = true;
   return check_launch("map_build");
 }
 
@@ -195,6 +246,10 @@ int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_di
   GridView g = view();
   float max_d2 = max_dist > 0.f ? max_dist * max_dist : 0.f;
   cudaStream_t s = ctx->stream;
+  {
+    int rc = wait_ready(s);
+    if (rc) return rc;
+  }
   int stride_f = stride_bytes / 4;
   if (k == 1)
     launch_knn<1>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);

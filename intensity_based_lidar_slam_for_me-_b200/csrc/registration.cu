@@ -21,9 +21,11 @@ namespace ilsm {
 __device__ __forceinline__ void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq, double& v0p,
                                            double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
   if (apq == 0.0) return;
-  double theta = (aqq - app) / (2.0 * apq);
-  double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-  double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+  // t = tan(phi) of the annihilating rotation, smaller root: sgn(h) 2 apq / (|h| + sqrt(h^2 + 4 apq^2)), h = aqq - app
+  // (one sqrt, one division and one rsqrt per rotation: fp64 div/sqrt are the long-latency ops of this kernel)
+  const double h = aqq - app;
+  const double t = (h >= 0.0 ? 2.0 : -2.0) * apq / (fabs(h) + sqrt(h * h + 4.0 * apq * apq));
+  const double c = rsqrt(t * t + 1.0), s = t * c;
   app -= t * apq;
   aqq += t * apq;
   apq = 0.0;
@@ -80,6 +82,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
     for (int c = 0; c < 3; ++c) A[i][c] = (double)nb[i][c];
   }
   int perm[3] = {0, 1, 2};
+  double rinv[3] = {0, 0, 0};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     double cn[3] = {0, 0, 0};
@@ -107,32 +110,36 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
         perm[j] = tp;
       }
     }
-    double nr = sqrt(best);
-    if (nr == 0.0) continue;
-    double alpha = A[k][k] > 0.0 ? -nr : nr;
+    const double nr = sqrt(best);
+    if (nr == 0.0) {
+      rinv[k] = 0.0;
+      continue;
+    }
+    // reflector v = x - alpha e_k with alpha = -sgn(x_k)|x|;  v^T v = 2(|x|^2 - alpha x_k)  =>  2 / v^T v = beta
+    const double xk = A[k][k];
+    const double alpha = xk > 0.0 ? -nr : nr;
+    const double beta = 1.0 / (best - alpha * xk);
     double v[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) v[i] = i >= k ? A[i][k] : 0.0;
-    v[k] -= alpha;
-    double vtv = 0;
+    v[k] = xk - alpha;
 #pragma unroll
-    for (int i = k; i < 5; ++i) vtv += v[i] * v[i];
-    if (vtv == 0.0) continue;
-#pragma unroll
-    for (int j = k; j < 3; ++j) {
+    for (int j = k + 1; j < 3; ++j) {
       double s = 0;
 #pragma unroll
       for (int i = k; i < 5; ++i) s += v[i] * A[i][j];
-      s = 2.0 * s / vtv;
+      s *= beta;
 #pragma unroll
       for (int i = k; i < 5; ++i) A[i][j] -= s * v[i];
     }
     double s = 0;
 #pragma unroll
     for (int i = k; i < 5; ++i) s += v[i] * b[i];
-    s = 2.0 * s / vtv;
+    s *= beta;
 #pragma unroll
     for (int i = k; i < 5; ++i) b[i] -= s * v[i];
+    A[k][k] = alpha;  // R diagonal
+    rinv[k] = 1.0 / alpha;
   }
   double y[3];
 #pragma unroll
@@ -140,7 +147,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
     double s = b[k];
 #pragma unroll
     for (int j = k + 1; j < 3; ++j) s -= A[k][j] * y[j];
-    y[k] = A[k][k] != 0.0 ? s / A[k][k] : 0.0;
+    y[k] = s * rinv[k];
   }
   double n[3] = {0, 0, 0};
 #pragma unroll
@@ -149,10 +156,10 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
     for (int c = 0; c < 3; ++c)
       if (perm[k] == c) n[c] = y[k];
   }
-  double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-  double d = 1.0 / nn;
-  n[0] /= nn, n[1] /= nn, n[2] /= nn;
-  bool ok = nn > 0.0 && isfinite(d);
+  const double nn2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+  const double d = rsqrt(nn2);  // negative_OA_dot_norm = 1/|n|
+  n[0] *= d, n[1] *= d, n[2] *= d;
+  bool ok = nn2 > 0.0 && isfinite(d);
 #pragma unroll
   for (int j = 0; j < 5; ++j)
     if (fabs(n[0] * (double)nb[j][0] + n[1] * (double)nb[j][1] + n[2] * (double)nb[j][2] + d) > tol) ok = false;
@@ -173,36 +180,12 @@ struct FactorView {
 struct AssocParams {
   float gate_sq;
   double line_ratio, plane_tol;
-  int begin_solve, pass, max_iter;
-  double huber_a;
 };
-
-__device__ void lm_begin(LmState* st, const AssocParams& prm) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) st->cq[i] = st->xq[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) st->ct[i] = st->xt[i];
-  st->status = 0;
-  st->phase = 0;
-  st->iteration = 0;
-  st->max_iter = prm.max_iter;
-  st->invalid_run = 0;
-  st->reuse_diag = 0;
-  st->n_success = st->n_unsuccess = st->n_evals = 0;
-  st->n_edge = st->n_plane = 0;
-  st->radius = 1e4;
-  st->decrease_factor = 2.0;
-  st->model_cost_change = 0.0;
-  st->huber_a = prm.huber_a;
-  st->pass = prm.pass;
-  st->ticket = 0u;
-}
 
 template <int G>
 __global__ void __launch_bounds__(256)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
-                     int ns, int stride_f, LmState* st, AssocParams prm, FactorView fv) {
-  if (prm.begin_solve && blockIdx.x == 0 && threadIdx.x == 0) lm_begin(st, prm);
+                     int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv) {
   const int groups_per_block = blockDim.x / G;
   const int gid = blockIdx.x * groups_per_block + threadIdx.x / G;
   const unsigned lane = threadIdx.x % G;
@@ -270,11 +253,98 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Levenberg-Marquardt state machine (one thread, state staged in shared memory)
+// residual + Jacobian of one factor, accumulated into the 30 running sums
 // ---------------------------------------------------------------------------------------------------
-constexpr int kNumSums = 30;  // cost, H[21], g[6], #edge, #plane
+// running sums per evaluation: [0] cost, [1..21] H (upper triangle), [22..27] g, [28] #edge, [29] #plane
 constexpr int kSumStride = 32;
 
+__device__ __forceinline__ void acc_row(double (&acc)[kSumStride], const double (&j)[6], double r) {
+  int k = 1;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int b = a; b < 6; ++b) acc[k++] += j[a] * j[b];
+    acc[22 + a] += j[a] * r;
+  }
+}
+
+// LidarEdgeFactor (hpp:243-293) / LidarPlaneNormFactor (hpp:199-240) at pose (q,t) with the closed-form tangent
+// Jacobians of EigenQuaternionParameterization and the HuberLoss corrector.
+__device__ __forceinline__ void eval_factor(int type, const float4 pf, const double4 fa, const double4 fb,
+                                            const double (&q)[4], const double (&t)[3], double huber_a,
+                                            double (&acc)[kSumStride]) {
+  D3 Rp = quat_rotate(q, d3((double)pf.x, (double)pf.y, (double)pf.z));
+  D3 lp = d3(Rp.x + t[0], Rp.y + t[1], Rp.z + t[2]);
+  if (type == 1) {
+    D3 u = d3(lp.x - fa.x, lp.y - fa.y, lp.z - fa.z), v = d3(lp.x - fb.x, lp.y - fb.y, lp.z - fb.z);
+    D3 nu = d3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+    const double dex = fa.x - fb.x, dey = fa.y - fb.y, dez = fa.z - fb.z;
+    const double idn = rsqrt(dex * dex + dey * dey + dez * dez);  // 1/|a-b|
+    const double r0 = nu.x * idn, r1 = nu.y * idn, r2 = nu.z * idn;
+    const double mx = -dex * idn, my = -dey * idn, mz = -dez * idn;  // (b - a)/|a-b|
+    const double sq = r0 * r0 + r1 * r1 + r2 * r2;
+    double rho0 = sq, sc = 1.0;
+    if (huber_a > 0.0 && sq > huber_a * huber_a) {  // ceres::HuberLoss + Corrector (rho'' <= 0): scale by sqrt(rho')
+      const double irr = rsqrt(sq);
+      rho0 = 2.0 * huber_a * (sq * irr) - huber_a * huber_a;
+      sc = sqrt(fmax(2.2250738585072014e-308, huber_a * irr));
+    }
+    acc[0] += 0.5 * rho0;
+    acc[28] += 1.0;
+    // J_t = [m]x ; J_delta = J_t * (-2 [Rp]x)
+    const double Jt[3][3] = {{0, -mz, my}, {mz, 0, -mx}, {-my, mx, 0}};
+    const double S[3][3] = {{0, 2 * Rp.z, -2 * Rp.y}, {-2 * Rp.z, 0, 2 * Rp.x}, {2 * Rp.y, -2 * Rp.x, 0}};
+    const double rr[3] = {r0, r1, r2};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double jr[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        jr[c] = sc * (Jt[a][0] * S[0][c] + Jt[a][1] * S[1][c] + Jt[a][2] * S[2][c]);
+        jr[3 + c] = sc * Jt[a][c];
+      }
+      acc_row(acc, jr, sc * rr[a]);
+    }
+  } else if (type == 2) {
+    const double r0 = fa.x * lp.x + fa.y * lp.y + fa.z * lp.z + fa.w;
+    const double sq = r0 * r0;
+    double rho0 = sq, sc = 1.0;
+    if (huber_a > 0.0 && sq > huber_a * huber_a) {
+      const double irr = rsqrt(sq);
+      rho0 = 2.0 * huber_a * (sq * irr) - huber_a * huber_a;
+      sc = sqrt(fmax(2.2250738585072014e-308, huber_a * irr));
+    }
+    acc[0] += 0.5 * rho0;
+    acc[29] += 1.0;
+    double jr[6];
+    jr[0] = sc * 2.0 * (Rp.y * fa.z - Rp.z * fa.y);  // n^T (-2[Rp]x) = 2 (Rp x n)^T
+    jr[1] = sc * 2.0 * (Rp.z * fa.x - Rp.x * fa.z);
+    jr[2] = sc * 2.0 * (Rp.x * fa.y - Rp.y * fa.x);
+    jr[3] = sc * fa.x, jr[4] = sc * fa.y, jr[5] = sc * fa.z;
+    acc_row(acc, jr, sc * r0);
+  }
+}
+
+// Transposing warp reduction: 32 lanes x 32 values -> lane L returns the warp total of value L
+// (31 shuffles per lane instead of 32 x 5).  Fixed order => deterministic.
+__device__ __forceinline__ double warp_reduce_transpose(double (&v)[kSumStride], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const double send = upper ? v[i] : v[i + off];
+      const double keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt state machine (Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy restated on
+// the 6-dof tangent normal equations; DENSE_QR replaced by an LDL^T solve of the damped normal equations)
+// ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void quat_mul_d(const double a[4], const double b[4], double o[4]) {
   o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
   o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
@@ -282,47 +352,85 @@ __device__ __forceinline__ void quat_mul_d(const double a[4], const double b[4],
   o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
 }
 // EigenQuaternionParameterization::Plus
-__device__ void quat_plus_d(const double x[4], const double d[3], double o[4]) {
-  double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-  if (nd > 0.0) {
-    double sbd = sin(nd) / nd;
-    double dq[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cos(nd)};
+__device__ __forceinline__ void quat_plus_d(const double x[4], const double d[3], double o[4]) {
+  const double nd2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  if (nd2 > 0.0) {
+    const double nd = sqrt(nd2);
+    double sn, cs;
+    sincos(nd, &sn, &cs);
+    const double sbd = sn / nd;
+    double dq[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cs};
     quat_mul_d(dq, x, o);
   } else {
     o[0] = x[0], o[1] = x[1], o[2] = x[2], o[3] = x[3];
   }
 }
 
-__device__ bool chol_solve6_d(double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
-  // in-place lower Cholesky
-  for (int i = 0; i < 6; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= A[i][k] * A[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        A[i][i] = sqrt(s);
-      } else {
-        A[i][j] = s / A[j][j];
-      }
+// Packed lower-triangular index of a symmetric 6x6.
+__device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+// Upper-triangle row-major index used by LmState::H.
+__device__ __forceinline__ constexpr int ut(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }  // a <= b
+
+// A y = b for symmetric positive definite 6x6 (packed lower, destroyed) by in-place LDL^T with reciprocal pivots:
+// 6 divisions in all, everything in registers.
+__device__ __forceinline__ bool ldlt_solve6(double (&m)[21], const double (&b)[6], double (&x)[6]) {
+  double dinv[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double dj = m[lt(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj -= m[lt(j, k)] * m[lt(j, k)] * m[lt(k, k)];
+    ok = ok && (dj > 0.0);
+    m[lt(j, j)] = dj;
+    dinv[j] = 1.0 / dj;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s = m[lt(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= m[lt(i, k)] * m[lt(j, k)] * m[lt(k, k)];
+      m[lt(i, j)] = s * dinv[j];
     }
-  double y[6];
+  }
+  if (!ok) return false;
+  double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
-    for (int k = 0; k < i; ++k) s -= A[i][k] * y[k];
-    y[i] = s / A[i][i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= m[lt(i, k)] * z[k];
+    z[i] = s;
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
-    double s = y[i];
-    for (int k = i + 1; k < 6; ++k) s -= A[k][i] * x[k];
-    x[i] = s / A[i][i];
+    double s = z[i] * dinv[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= m[lt(k, i)] * x[k];
+    x[i] = s;
   }
   return true;
 }
 
-__device__ void lm_terminate(LmState* s, LmState* g, int code) {
+__device__ void lm_arm(LmState* s, int max_iter, double huber_a, int pass) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s->cq[i] = s->xq[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s->ct[i] = s->xt[i];
+  s->status = 0, s->phase = 0, s->iteration = 0, s->max_iter = max_iter;
+  s->invalid_run = 0, s->reuse_diag = 0;
+  s->n_success = s->n_unsuccess = s->n_evals = 0;
+  s->n_edge = s->n_plane = 0;
+  s->radius = 1e4, s->decrease_factor = 2.0, s->model_cost_change = 0.0;
+  s->huber_a = huber_a;
+  s->pass = pass;
+  s->ticket = 0u;
+}
+
+// rep == nullptr: this CTA only mirrors the state machine (another CTA writes the report)
+__device__ void lm_terminate(LmState* s, ilsm_reg_report* rep, int code) {
   s->status = 1 + code;
-  ilsm_solve_summary& r = g->report.pass[s->pass < ILSM_MAX_OUTER ? s->pass : ILSM_MAX_OUTER - 1];
+  if (!rep) return;
+  ilsm_solve_summary& r = rep->pass[s->pass < ILSM_MAX_OUTER ? s->pass : ILSM_MAX_OUTER - 1];
   r.termination = code;
   r.iterations = s->iteration;
   r.num_successful_steps = s->n_success;
@@ -333,11 +441,11 @@ __device__ void lm_terminate(LmState* s, LmState* g, int code) {
   r.reserved = 0;
   r.initial_cost = s->initial_cost;
   r.final_cost = s->cost;
-  g->report.passes = s->pass + 1;
+  rep->passes = s->pass + 1;
 }
 
-// s: shared-memory copy of the state (everything except the report), g: the HBM original (report sink).
-__device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
+// Consume the sums of the evaluation at the candidate pose and either terminate or emit the next candidate.
+__device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const double* sums) {
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
   const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16;
   const double min_diag = 1e-6, max_diag = 1e32;
@@ -348,47 +456,56 @@ __device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
     s->n_plane = (int)sums[29];
     s->cost = new_cost;
     s->initial_cost = new_cost;
+#pragma unroll
     for (int i = 0; i < 21; ++i) s->H[i] = sums[1 + i];
+#pragma unroll
     for (int i = 0; i < 6; ++i) s->g[i] = sums[22 + i];
     if (s->n_edge + s->n_plane == 0) {  // Ceres: no residual blocks -> parameter blocks dropped -> CONVERGENCE
-      lm_terminate(s, g, ILSM_CONVERGENCE);
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
     int k = 0;
+#pragma unroll
     for (int a = 0; a < 6; ++a) {
       s->scale[a] = 1.0 / (1.0 + sqrt(s->H[k]));
       k += 6 - a;
     }
   } else {
     double step2 = 0, x2 = 0;
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
       double d = s->xq[i] - s->cq[i];
       step2 += d * d;
       x2 += s->xq[i] * s->xq[i];
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       double d = s->xt[i] - s->ct[i];
       step2 += d * d;
       x2 += s->xt[i] * s->xt[i];
     }
     if (sqrt(step2) <= parameter_tolerance * (sqrt(x2) + parameter_tolerance)) {
-      lm_terminate(s, g, ILSM_CONVERGENCE);
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    double cost_change = s->cost - new_cost;
+    const double cost_change = s->cost - new_cost;
     if (fabs(cost_change) <= function_tolerance * s->cost) {
-      lm_terminate(s, g, ILSM_CONVERGENCE);
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    double rho = cost_change / s->model_cost_change;
+    const double rho = cost_change / s->model_cost_change;
     if (rho > min_relative_decrease) {
+#pragma unroll
       for (int i = 0; i < 4; ++i) s->xq[i] = s->cq[i];
+#pragma unroll
       for (int i = 0; i < 3; ++i) s->xt[i] = s->ct[i];
       s->cost = new_cost;
+#pragma unroll
       for (int i = 0; i < 21; ++i) s->H[i] = sums[1 + i];
+#pragma unroll
       for (int i = 0; i < 6; ++i) s->g[i] = sums[22 + i];
-      double m = 1.0 - pow(2.0 * rho - 1.0, 3.0);
-      s->radius = s->radius / fmax(1.0 / 3.0, m);
+      const double w = 2.0 * rho - 1.0;
+      s->radius = s->radius / fmax(1.0 / 3.0, 1.0 - w * w * w);
       s->radius = fmin(max_radius, s->radius);
       s->decrease_factor = 2.0;
       s->reuse_diag = 0;
@@ -401,52 +518,60 @@ __device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
     }
   }
   // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep, repeated over invalid steps
+#pragma unroll 1
   for (;;) {
     if (s->iteration >= s->max_iter) {
-      lm_terminate(s, g, ILSM_NO_CONVERGENCE);
+      lm_terminate(s, rep, ILSM_NO_CONVERGENCE);
       return;
     }
     {  // gradient_max_norm = |x - Plus(x, -g)|_inf in the ambient space
       double ng[3] = {-s->g[0], -s->g[1], -s->g[2]}, qp[4];
       quat_plus_d(s->xq, ng, qp);
       double m = 0;
+#pragma unroll
       for (int i = 0; i < 4; ++i) m = fmax(m, fabs(s->xq[i] - qp[i]));
+#pragma unroll
       for (int i = 0; i < 3; ++i) m = fmax(m, fabs(s->g[3 + i]));
       if (m <= gradient_tolerance) {
-        lm_terminate(s, g, ILSM_CONVERGENCE);
+        lm_terminate(s, rep, ILSM_CONVERGENCE);
         return;
       }
     }
     if (s->radius <= min_radius) {
-      lm_terminate(s, g, ILSM_CONVERGENCE);
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
     s->iteration += 1;
-    double Hs[6][6], gs[6], A[6][6], y[6], step[6];
-    {
-      int k = 0;
-      for (int a = 0; a < 6; ++a)
-        for (int b = a; b < 6; ++b) {
-          double v = s->H[k++] * s->scale[a] * s->scale[b];
-          Hs[a][b] = v;
-          Hs[b][a] = v;
-        }
-      for (int a = 0; a < 6; ++a) gs[a] = s->g[a] * s->scale[a];
+    double gs[6], m[21], y[6], step[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) gs[a] = s->g[a] * s->scale[a];
+    if (!s->reuse_diag) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double haa = s->H[ut(a, a)] * s->scale[a] * s->scale[a];
+        s->diag[a] = fmin(fmax(haa, min_diag), max_diag);
+      }
     }
-    if (!s->reuse_diag)
-      for (int a = 0; a < 6; ++a) s->diag[a] = fmin(fmax(Hs[a][a], min_diag), max_diag);
-    for (int a = 0; a < 6; ++a)
-      for (int b = 0; b < 6; ++b) A[a][b] = Hs[a][b] + (a == b ? s->diag[a] / s->radius : 0.0);
-    bool ok = chol_solve6_d(A, gs, y);
+    const double inv_radius = 1.0 / s->radius;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j)
+        m[lt(i, j)] = s->H[ut(j, i)] * s->scale[j] * s->scale[i] + (i == j ? s->diag[i] * inv_radius : 0.0);
+    bool ok = ldlt_solve6(m, gs, y);
     s->reuse_diag = 1;
     double mcc = 0;
     if (ok) {
       double sg = 0, sHs = 0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) step[a] = -y[a];
+#pragma unroll
       for (int a = 0; a < 6; ++a) {
         sg += step[a] * gs[a];
         double hv = 0;
-        for (int b = 0; b < 6; ++b) hv += Hs[a][b] * step[b];
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+          hv += s->H[a <= b ? ut(a, b) : ut(b, a)] * s->scale[a] * s->scale[b] * step[b];
         sHs += step[a] * hv;
         ok = ok && isfinite(step[a]);
       }
@@ -455,7 +580,7 @@ __device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
     if (!ok || !(mcc > 0.0)) {  // HandleInvalidStep
       s->n_unsuccess += 1;
       if (++s->invalid_run >= 5) {
-        lm_terminate(s, g, ILSM_FAILURE);
+        lm_terminate(s, rep, ILSM_FAILURE);
         return;
       }
       s->radius = s->radius / s->decrease_factor;
@@ -466,8 +591,10 @@ __device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
     s->invalid_run = 0;
     s->model_cost_change = mcc;
     double delta[6];
+#pragma unroll
     for (int a = 0; a < 6; ++a) delta[a] = step[a] * s->scale[a];
     quat_plus_d(s->xq, delta, s->cq);
+#pragma unroll
     for (int i = 0; i < 3; ++i) s->ct[i] = s->xt[i] + delta[3 + i];
     s->phase = 1;
     return;
@@ -475,145 +602,162 @@ __device__ void lm_advance(LmState* s, LmState* g, const double* sums) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// evaluation kernel
+// solve_cluster_kernel: the whole ceres::Solve in ONE launch on one thread-block cluster (8 CTAs = 8 SMs).
+// Each thread keeps its factor in registers across all evaluations; per evaluation the 30 sums are reduced
+// warp -> CTA (shared memory) -> cluster (distributed shared memory), every CTA advances an identical copy of
+// the LM state machine (no broadcast needed), one cluster barrier per evaluation (double-buffered partials).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void acc_row(double (&acc)[kNumSums], const double (&j)[6], double r) {
-  int k = 1;
+constexpr int kClusterSize = 8;
+constexpr int kSolveThreads = 384;
+constexpr int kCoreWords = (int)(offsetof(LmState, report) / 8);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a double from the shared memory of CTA `rank` of this cluster (DSMEM)
+__device__ __forceinline__ double dsmem_ld_f64(const double* local_ptr, uint32_t rank) {
+  uint32_t a = smem_u32(local_ptr), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+struct SolveParams {
+  int max_iter, pass, arm;
+  double huber_a;
+};
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThreads, 1)
+    solve_cluster_kernel(FactorView fv, int n, LmState* st, SolveParams prm) {
+  __shared__ double core[kCoreWords];
+  __shared__ double red[kSolveThreads / 32][kSumStride];
+  __shared__ double part[2][kSumStride];
+  __shared__ double tot[kSumStride];
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cl_tid = (int)rank * kSolveThreads + tid, cl_n = kClusterSize * kSolveThreads;
+  LmState* s = reinterpret_cast<LmState*>(core);  // only the fields before `report` exist in this copy
+
+  // factor of the first round stays in registers for every evaluation
+  int type0 = 0;
+  float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  double4 a0 = make_double4(0, 0, 0, 0), b0 = a0;
+  if (cl_tid < n) {
+    type0 = fv.type[cl_tid];
+    if (type0) {
+      p0 = fv.p[cl_tid];
+      a0 = fv.a[cl_tid];
+      if (type0 == 1) b0 = fv.b[cl_tid];
+    }
+  }
+  {
+    const double* src = reinterpret_cast<const double*>(st);
+    for (int w = tid; w < kCoreWords; w += kSolveThreads) core[w] = src[w];
+  }
+  __syncthreads();
+  if (tid == 0 && prm.arm) lm_arm(s, prm.max_iter, prm.huber_a, prm.pass);
+  __syncthreads();
+  ilsm_reg_report* rep = rank == 0 ? &st->report : nullptr;
+
+#pragma unroll 1
+  for (int e = 0; s->status == 0; ++e) {
+    const double q[4] = {s->cq[0], s->cq[1], s->cq[2], s->cq[3]};
+    const double t[3] = {s->ct[0], s->ct[1], s->ct[2]};
+    const double huber_a = s->huber_a;
+    double acc[kSumStride];
 #pragma unroll
-  for (int a = 0; a < 6; ++a) {
+    for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
+    if (type0) eval_factor(type0, p0, a0, b0, q, t, huber_a, acc);
+    for (int i = cl_tid + cl_n; i < n; i += cl_n) {  // maps larger than one cluster round (config-3 sizes)
+      const int ty = fv.type[i];
+      if (ty) eval_factor(ty, fv.p[i], fv.a[i], fv.b[i], q, t, huber_a, acc);
+    }
+    const double mine = warp_reduce_transpose(acc, lane);
+    red[warp][lane] = mine;
+    __syncthreads();
+    if (tid < kSumStride) {
+      double v = 0;
 #pragma unroll
-    for (int b = a; b < 6; ++b) acc[k++] += j[a] * j[b];
-    acc[22 + a] += j[a] * r;
+      for (int w = 0; w < kSolveThreads / 32; ++w) v += red[w][tid];
+      part[e & 1][tid] = v;
+    }
+    cluster_sync_all();  // partials of every CTA visible cluster-wide
+    if (tid < kSumStride) {
+      double v = 0;
+#pragma unroll
+      for (uint32_t r = 0; r < (uint32_t)kClusterSize; ++r) v += dsmem_ld_f64(&part[e & 1][tid], r);
+      tot[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) lm_advance(s, rep, tot);
+    __syncthreads();
+  }
+  cluster_sync_all();  // nobody may exit while a peer can still read its shared memory
+  if (rank == 0) {
+    double* dst = reinterpret_cast<double*>(st);
+    for (int w = tid; w < kCoreWords; w += kSolveThreads) dst[w] = core[w];
   }
 }
 
-// mode 0: advance the LM state machine; mode 1: evaluate only (sums -> eval_out)
-__global__ void __launch_bounds__(256) eval_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials,
-                                                   double* __restrict__ eval_out, int mode) {
-  if (mode == 0 && st->status != 0) return;
+// ---------------------------------------------------------------------------------------------------
+// normal_eq_kernel: one evaluation of (cost, J^T J, J^T r) over all factors with an ordinary grid (the
+// "J^T J kernel" of config 3 and of ilsm_eval_normal_eq); deterministic two-stage reduction, last block sums.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) normal_eq_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials,
+                                                        double* __restrict__ eval_out) {
   __shared__ double red[8][kSumStride];
-  __shared__ double tot[kSumStride];
   __shared__ int is_last;
-  constexpr int kCoreWords = (int)(offsetof(LmState, report) / 8);
-  __shared__ double core[kCoreWords];
-
-  double acc[kNumSums];
+  double acc[kSumStride];
 #pragma unroll
-  for (int i = 0; i < kNumSums; ++i) acc[i] = 0.0;
-
+  for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int type = i < n ? fv.type[i] : 0;
   if (type != 0) {
-    const double huber_a = st->huber_a;
-    double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
-    const float4 pf = fv.p[i];
-    const double4 fa = fv.a[i];
-    D3 Rp = quat_rotate(q, d3((double)pf.x, (double)pf.y, (double)pf.z));
-    D3 lp = d3(Rp.x + st->ct[0], Rp.y + st->ct[1], Rp.z + st->ct[2]);
-    double r[3] = {0, 0, 0}, J[3][6];
-    int nres;
-    if (type == 1) {
-      const double4 fb = fv.b[i];
-      D3 u = d3(lp.x - fa.x, lp.y - fa.y, lp.z - fa.z), v = d3(lp.x - fb.x, lp.y - fb.y, lp.z - fb.z);
-      D3 nu = d3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
-      double dex = fa.x - fb.x, dey = fa.y - fb.y, dez = fa.z - fb.z;
-      double dn = sqrt(dex * dex + dey * dey + dez * dez);
-      r[0] = nu.x / dn, r[1] = nu.y / dn, r[2] = nu.z / dn;
-      double mx = -dex / dn, my = -dey / dn, mz = -dez / dn;  // (b - a)/|a-b|
-      double Jt[3][3] = {{0, -mz, my}, {mz, 0, -mx}, {-my, mx, 0}};
-      double S[3][3] = {{0, 2 * Rp.z, -2 * Rp.y}, {-2 * Rp.z, 0, 2 * Rp.x}, {2 * Rp.y, -2 * Rp.x, 0}};
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          J[a][c] = Jt[a][0] * S[0][c] + Jt[a][1] * S[1][c] + Jt[a][2] * S[2][c];
-          J[a][3 + c] = Jt[a][c];
-        }
-      nres = 3;
-      acc[28] = 1.0;
-    } else {
-      r[0] = fa.x * lp.x + fa.y * lp.y + fa.z * lp.z + fa.w;
-      J[0][0] = 2.0 * (Rp.y * fa.z - Rp.z * fa.y);
-      J[0][1] = 2.0 * (Rp.z * fa.x - Rp.x * fa.z);
-      J[0][2] = 2.0 * (Rp.x * fa.y - Rp.y * fa.x);
-      J[0][3] = fa.x, J[0][4] = fa.y, J[0][5] = fa.z;
-#pragma unroll
-      for (int a = 1; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 6; ++c) J[a][c] = 0.0;
-      nres = 1;
-      acc[29] = 1.0;
-    }
-    double sq = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    double rho0 = sq, rho1 = 1.0;
-    if (huber_a > 0.0 && sq > huber_a * huber_a) {  // ceres::HuberLoss + Corrector (rho'' <= 0)
-      double rr = sqrt(sq);
-      rho0 = 2.0 * huber_a * rr - huber_a * huber_a;
-      rho1 = fmax(2.2250738585072014e-308, huber_a / rr);
-    }
-    const double sc = sqrt(rho1);
-    acc[0] = 0.5 * rho0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (a < nres) {
-        double jr[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) jr[c] = sc * J[a][c];
-        acc_row(acc, jr, sc * r[a]);
-      }
-    }
+    const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
+    const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
+    eval_factor(type, fv.p[i], fv.a[i], fv.b[i], q, t, st->huber_a, acc);
   }
-  // warp shuffle reduction, then cross-warp through shared memory (fixed order => deterministic)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int k = 0; k < kNumSums; ++k) {
-    double v = acc[k];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) red[warp][k] = v;
-  }
+  red[warp][lane] = warp_reduce_transpose(acc, lane);
   __syncthreads();
-  const int nwarps = blockDim.x >> 5;
-  if (threadIdx.x < kNumSums) {
+  if (threadIdx.x < kSumStride) {
     double v = 0;
-    for (int w = 0; w < nwarps; ++w) v += red[w][threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
     partials[(size_t)blockIdx.x * kSumStride + threadIdx.x] = v;
   }
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned t = atomicAdd(&st->ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < kNumSums) {
+  // 8 threads per sum, each a strided slice of the blocks, then a fixed-order combine
+  __shared__ double slice[8][kSumStride];
+  {
+    const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
     double v = 0;
-    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t)b * kSumStride + threadIdx.x);
-    tot[threadIdx.x] = v;
-  }
-  if (mode == 1) {
-    __syncthreads();
-    if (threadIdx.x < kNumSums) eval_out[threadIdx.x] = tot[threadIdx.x];
-    if (threadIdx.x == 0) st->ticket = 0u;
-    return;
-  }
-  {
-    const double* src = reinterpret_cast<const double*>(st);
-    for (int w = threadIdx.x; w < kCoreWords; w += blockDim.x) core[w] = src[w];
+    for (unsigned b = sl; b < gridDim.x; b += 8) v += __ldcg(partials + (size_t)b * kSumStride + c);
+    slice[sl][c] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    LmState* s = reinterpret_cast<LmState*>(core);  // only the fields before `report` are touched through s
-    s->ticket = 0u;
-    lm_advance(s, st, tot);
+  if (threadIdx.x < kSumStride) {
+    double v = 0;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) v += slice[sl][threadIdx.x];
+    eval_out[threadIdx.x] = v;
   }
-  __syncthreads();
-  {
-    double* dst = reinterpret_cast<double*>(st);
-    for (int w = threadIdx.x; w < kCoreWords; w += blockDim.x) dst[w] = core[w];
-  }
+  if (threadIdx.x == 0) st->ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -631,7 +775,7 @@ static FactorView factor_view(FactorBufs& f, bool want_knn) {
 }
 
 int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                       const ilsm_reg_opts& o, bool begin_solve, int pass, bool want_knn) {
+                       const ilsm_reg_opts& o, bool want_knn) {
   const int n = nc + ns;
   int rc;
   if ((rc = fac.type.reserve(n + 1)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
@@ -641,22 +785,17 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
     return rc;
   fac.n = n;
   fac.nc = nc;
+  if (n == 0) return ILSM_OK;
+  if ((rc = mc->wait_ready(stream)) || (rc = ms->wait_ready(stream))) return rc;
   AssocParams prm;
   prm.gate_sq = o.knn_gate_sq;
   prm.line_ratio = o.line_eig_ratio;
   prm.plane_tol = o.plane_tol;
-  prm.begin_solve = begin_solve ? 1 : 0;
-  prm.pass = pass;
-  prm.max_iter = o.max_num_iterations;
-  prm.huber_a = o.huber_a;
   GridView gc = mc->view(), gs = ms->view();
   FactorView fv = factor_view(fac, want_knn);
   const int T = 256;
   const int stride_f = stride_bytes / 4;
-  if (n == 0) {
-    // still (re)arm the LM state so that the following evaluation terminates with "no residuals"
-    associate_kernel<32><<<1, 32, 0, stream>>>(gc, gs, d_corner, 0, d_surf, 0, stride_f, lm.p, prm, fv);
-  } else if ((long long)n * 32 <= (long long)sm_count * 2048 * 2) {
+  if ((long long)n * 32 <= (long long)sm_count * 2048 * 2) {
     associate_kernel<32><<<(n + T / 32 - 1) / (T / 32), T, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p,
                                                                          prm, fv);
   } else {
@@ -667,25 +806,24 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   return check_launch("associate");
 }
 
-int Ctx::eval_launch(int count) {
-  const int T = 256;
-  int blocks = (fac.n + T - 1) / T;
-  if (blocks < 1) blocks = 1;
-  int rc;
-  if ((rc = partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
+int Ctx::solve_launch(int max_iter, double huber_a, int pass) {
+  SolveParams prm;
+  prm.max_iter = max_iter;
+  prm.pass = pass;
+  prm.arm = 1;
+  prm.huber_a = huber_a;
   FactorView fv = factor_view(fac, false);
-  for (int k = 0; k < count; ++k)
-    eval_kernel<<<blocks, T, 0, stream>>>(fv, fac.n, lm.p, partials.p, nullptr, 0);
-  count_launches(count);
-  return check_launch("eval");
+  solve_cluster_kernel<<<kClusterSize, kSolveThreads, 0, stream>>>(fv, fac.n, lm.p, prm);
+  count_launches(1);
+  return check_launch("solve");
 }
 
 int Ctx::register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                       const ilsm_reg_opts& o) {
   for (int pass = 0; pass < o.outer_iterations; ++pass) {
-    int rc = associate_dev(mc, ms, d_corner, nc, d_surf, ns, stride_bytes, o, true, pass, false);
+    int rc = associate_dev(mc, ms, d_corner, nc, d_surf, ns, stride_bytes, o, false);
     if (rc) return rc;
-    if ((rc = eval_launch(1 + o.max_num_iterations))) return rc;
+    if ((rc = solve_launch(o.max_num_iterations, o.huber_a, pass))) return rc;
   }
   return ILSM_OK;
 }
@@ -698,9 +836,9 @@ int eval_only_launch(Ctx* c, double* d_out) {
   int rc;
   if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
   FactorView fv = factor_view(c->fac, false);
-  eval_kernel<<<blocks, T, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out, 1);
+  normal_eq_kernel<<<blocks, T, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out);
   count_launches(1);
-  return check_launch("eval_only");
+  return check_launch("normal_eq");
 }
 
 // copy factor SoA -> AoS records on the device for ilsm_associate's host output
