@@ -180,6 +180,15 @@ ILSM_API int ilsm_sync(ilsm_ctx* ctx) {
 
 ILSM_API void* ilsm_stream(ilsm_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
 
+// profiling aid (not in include/ilsm.h): copy the 64 clock64() stamps of the last kernels to the host
+ILSM_API int ilsm_debug_stamps(ilsm_ctx* ctx, long long* out64) {
+  if (!ctx || !out64) return fail(ILSM_ERR_INVALID_ARG, "null");
+  std::lock_guard<std::mutex> lk(ctx->c.mu);
+  ILSM_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  ILSM_CUDA(cudaMemcpy(out64, ctx->c.lm.p->dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return ILSM_OK;
+}
+
 ILSM_API int ilsm_set_async(ilsm_ctx* ctx, int on) {
   if (!ctx) return fail(ILSM_ERR_INVALID_ARG, "null ctx");
   std::lock_guard<std::mutex> lk(ctx->c.mu);

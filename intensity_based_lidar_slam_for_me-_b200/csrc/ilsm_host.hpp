@@ -94,6 +94,7 @@ struct LmState {
   unsigned ticket;
   int pad;
   ilsm_reg_report report;
+  long long dbg[64];  // clock64() phase stamps written when ILSM_DEBUG_TIMING is compiled in (profiling aid)
 };
 
 struct Ctx;

@@ -80,122 +80,208 @@ __device__ __forceinline__ uint32_t probe_voxel(const GridView& g, u64 key, uint
   }
 }
 
-template <int K>
-__device__ __forceinline__ void topk_insert(u64 (&best)[K], u64 key) {
-  if (key < best[K - 1]) {
-    best[K - 1] = key;
+// Per-lane candidate list: K best (d2, idx) keys in ascending order, optionally with the candidates' coordinates
+// (the association kernel needs the 5 neighbours' xyz for the fit and saves a dependent gather by carrying them).
+template <int K, bool XYZ>
+struct CandList {
+  u64 key[K];
+  float x[XYZ ? K : 1], y[XYZ ? K : 1], z[XYZ ? K : 1];
+  __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int s = K - 1; s > 0; --s) {
-      u64 a = best[s - 1], b = best[s];
-      bool sw = b < a;
-      best[s - 1] = sw ? b : a;
-      best[s] = sw ? a : b;
+    for (int k = 0; k < K; ++k) key[k] = kSentinel;
+  }
+  __device__ __forceinline__ void insert(u64 kk, float px, float py, float pz) {
+    if (kk < key[K - 1]) {
+      key[K - 1] = kk;
+      if (XYZ) x[K - 1] = px, y[K - 1] = py, z[K - 1] = pz;
+#pragma unroll
+      for (int s = K - 1; s > 0; --s) {
+        const bool sw = key[s] < key[s - 1];
+        const u64 a = key[s - 1], b = key[s];
+        key[s - 1] = sw ? b : a;
+        key[s] = sw ? a : b;
+        if (XYZ) {
+          const float ax = x[s - 1], bx = x[s], ay = y[s - 1], by = y[s], az = z[s - 1], bz = z[s];
+          x[s - 1] = sw ? bx : ax, x[s] = sw ? ax : bx;
+          y[s - 1] = sw ? by : ay, y[s] = sw ? ay : by;
+          z[s - 1] = sw ? bz : az, z[s] = sw ? az : bz;
+        }
+      }
     }
   }
-}
-
-template <int K>
-__device__ __forceinline__ void scan_voxel(const GridView& g, int cx, int cy, int cz, float qx, float qy, float qz,
-                                           u64 (&best)[K]) {
-  uint32_t start;
-  uint32_t cnt = probe_voxel(g, pack_voxel(cx, cy, cz), start);
-  for (uint32_t j = 0; j < cnt; ++j) {
-    float4 p = __ldg(g.sorted + start + j);
-    float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-    topk_insert<K>(best, pack_cand(d2, __float_as_uint(p.w)));
+  __device__ __forceinline__ void pop_front() {
+#pragma unroll
+    for (int s = 0; s < K - 1; ++s) {
+      key[s] = key[s + 1];
+      if (XYZ) x[s] = x[s + 1], y[s] = y[s + 1], z[s] = z[s + 1];
+    }
+    key[K - 1] = kSentinel;
   }
+};
+
+// Group-uniform result of a search: sorted keys (+ coordinates when requested).
+template <int K, bool XYZ>
+struct KnnResult {
+  u64 key[K];
+  float x[XYZ ? K : 1], y[XYZ ? K : 1], z[XYZ ? K : 1];
+};
+
+// Per-warp shared-memory scratch of the search: the candidate ranges found by the 32 lanes of one probing round.
+struct WarpScratch {
+  uint32_t start[32];
+  uint32_t prefix[33];
+};
+
+__device__ __forceinline__ uint32_t redux_min_u32(unsigned mask, uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.min.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(mask));
+  return r;
 }
 
-// Merge the per-lane sorted lists of a G-lane group into the group-uniform sorted result.
-template <int K, int G>
-__device__ __forceinline__ void group_merge(u64 (&best)[K], u64 (&res)[K], unsigned gmask) {
+// Merge the per-lane sorted lists of a warp into the warp-uniform sorted result: K rounds of a 64-bit arg-min
+// done as two 32-bit REDUX ops (high word = d2 bits, low word = index).
+template <int K, bool XYZ>
+__device__ __forceinline__ void warp_merge(CandList<K, XYZ>& best, KnnResult<K, XYZ>& res) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    u64 m = best[0];
-#pragma unroll
-    for (int off = G / 2; off > 0; off >>= 1) {
-      u64 o = __shfl_xor_sync(gmask, m, off, G);
-      m = o < m ? o : m;
+    const uint32_t hi = (uint32_t)(best.key[0] >> 32), lo = (uint32_t)best.key[0];
+    const uint32_t mhi = redux_min_u32(0xffffffffu, hi);
+    const uint32_t mlo = redux_min_u32(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+    const u64 m = ((u64)mhi << 32) | mlo;
+    res.key[k] = m;
+    const bool mine = best.key[0] == m && m != kSentinel;  // keys are unique: at most one lane
+    if (XYZ) {
+      const unsigned who = __ballot_sync(0xffffffffu, mine);
+      const int src = who ? __ffs(who) - 1 : 0;
+      res.x[k] = __shfl_sync(0xffffffffu, best.x[0], src);
+      res.y[k] = __shfl_sync(0xffffffffu, best.y[0], src);
+      res.z[k] = __shfl_sync(0xffffffffu, best.z[0], src);
     }
-    res[k] = m;
-    if (best[0] == m && m != kSentinel) {
-#pragma unroll
-      for (int s = 0; s < K - 1; ++s) best[s] = best[s + 1];
-      best[K - 1] = kSentinel;
-    }
+    if (mine) best.pop_front();
   }
 }
 
-// Exact K-NN of (qx,qy,qz) by a cooperating group of G lanes (G = 8, 16 or 32, groups aligned inside a warp).
-// Ring expansion over the voxel hash: the first pass visits the 3x3x3 block around the query voxel, further
-// passes add one Chebyshev shell each.  The search stops when (a) the K-th distance is provably smaller than
-// the distance to anything unvisited, (b) the visited block already contains the ball of radius sqrt(max_d2)
-// (results beyond it are "don't care"), or (c) the block covers every occupied voxel.  After kMaxRing rings
-// the group falls back to a coalesced brute-force sweep of the whole map.  res[] is identical in all lanes.
-template <int K, int G>
-__device__ __forceinline__ void knn_search(const GridView& g, float qx, float qy, float qz, float max_d2, unsigned lane,
-                                           unsigned gmask, u64 (&res)[K]) {
-  u64 best[K];
+// Exact K-NN of (qx,qy,qz) by one warp.
+// Ring expansion over the voxel hash.  Each probing round gives every lane one voxel; the (start,count) pairs go
+// through a warp prefix sum into shared memory and the CANDIDATE POINTS (not the voxels) are then dealt out to the
+// lanes, so that all point loads of a round are in flight together and the work is balanced whatever the voxel
+// occupancy.  The first pass visits the 3x3x3 block around the query voxel, further passes add one Chebyshev
+// shell each.  The search stops when (a) the K-th distance is provably smaller than the distance to anything
+// unvisited, (b) the visited block already contains the ball of radius sqrt(max_d2) (results beyond it are
+// "don't care"), or (c) the block covers every occupied voxel.  After kMaxRing rings it falls back to a
+// coalesced brute-force sweep of the whole map (same candidate loop, one range).  res is identical in all lanes.
+// bb = bounding box of occupied voxels (preloaded by the caller so that its latency overlaps the query's).
+template <int K, bool XYZ>
+__device__ __forceinline__ void knn_search(const GridView& g, const int (&bb)[6], float qx, float qy, float qz,
+                                           float max_d2, unsigned lane, WarpScratch& ws, KnnResult<K, XYZ>& res) {
+  CandList<K, XYZ> best;
+  best.clear();
 #pragma unroll
-  for (int k = 0; k < K; ++k) best[k] = kSentinel, res[k] = kSentinel;
+  for (int k = 0; k < K; ++k) res.key[k] = kSentinel;
   if (g.n <= 0) return;
 
-  float ux = __fmul_rn(qx, g.inv_cell), uy = __fmul_rn(qy, g.inv_cell), uz = __fmul_rn(qz, g.inv_cell);
-  if (!(fabsf(ux) < (float)kCoordLim && fabsf(uy) < (float)kCoordLim && fabsf(uz) < (float)kCoordLim)) {
-    // query outside the addressable voxel range (or NaN): brute force keeps the result exact.
-    for (int j = lane; j < g.n; j += G) {
-      float4 p = __ldg(g.sorted + j);
-      topk_insert<K>(best, pack_cand(dist2_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)));
-    }
-    group_merge<K, G>(best, res, gmask);
-    return;
-  }
-  int cx = __float2int_rd(ux), cy = __float2int_rd(uy), cz = __float2int_rd(uz);
-  float fx = ux - (float)cx, fy = uy - (float)cy, fz = uz - (float)cz;
-  float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
-  float umax = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
-  int bx0 = __ldg(g.bbox + 0), by0 = __ldg(g.bbox + 1), bz0 = __ldg(g.bbox + 2);
-  int bx1 = __ldg(g.bbox + 3), by1 = __ldg(g.bbox + 4), bz1 = __ldg(g.bbox + 5);
+  const float ux = __fmul_rn(qx, g.inv_cell), uy = __fmul_rn(qy, g.inv_cell), uz = __fmul_rn(qz, g.inv_cell);
+  // query outside the addressable voxel range (or NaN): brute force keeps the result exact
+  const bool in_range = fabsf(ux) < (float)kCoordLim && fabsf(uy) < (float)kCoordLim && fabsf(uz) < (float)kCoordLim;
+  const int cx = __float2int_rd(ux), cy = __float2int_rd(uy), cz = __float2int_rd(uz);
+  const float fx = ux - (float)cx, fy = uy - (float)cy, fz = uz - (float)cz;
+  const float fmin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+  const float umax = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz));
 
-  int r = 1;
+  int r = in_range ? 1 : kMaxRing + 1;
 #pragma unroll 1
   for (;;) {
-    const int side = 2 * r + 1, total = side * side * side;
+    const bool brute = r > kMaxRing;
+    const int side = 2 * r + 1, total = brute ? 1 : side * side * side;
 #pragma unroll 1
-    for (int t = lane; t < total; t += G) {
-      int dz = t / (side * side), rem = t - dz * side * side;
-      int dy = rem / side, dx = rem - dy * side;
-      dx -= r, dy -= r, dz -= r;
-      if (r > 1 && abs(dx) < r && abs(dy) < r && abs(dz) < r) continue;  // interior: visited by earlier passes
-      int vx = cx + dx, vy = cy + dy, vz = cz + dz;
-      if (vx < bx0 || vx > bx1 || vy < by0 || vy > by1 || vz < bz0 || vz > bz1) continue;
-      scan_voxel<K>(g, vx, vy, vz, qx, qy, qz, best);
+    for (int base = 0; base < total; base += 32) {
+      const int t = base + (int)lane;
+      uint32_t start = 0, cnt = 0;
+      if (brute) {
+        if (lane == 0) cnt = (uint32_t)g.n;
+      } else if (t < total) {
+        int dz = t / (side * side), rem = t - dz * side * side;
+        int dy = rem / side, dx = rem - dy * side;
+        dx -= r, dy -= r, dz -= r;
+        const bool interior = r > 1 && abs(dx) < r && abs(dy) < r && abs(dz) < r;  // visited by earlier passes
+        const int vx = cx + dx, vy = cy + dy, vz = cz + dz;
+        if (!interior && vx >= bb[0] && vx <= bb[3] && vy >= bb[1] && vy <= bb[4] && vz >= bb[2] && vz <= bb[5])
+          cnt = probe_voxel(g, pack_voxel(vx, vy, vz), start);
+      }
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= (unsigned)off) inc += v;
+      }
+      const uint32_t ncand = __shfl_sync(0xffffffffu, inc, 31);
+      ws.start[lane] = start;
+      ws.prefix[lane + 1] = inc;
+      if (lane == 0) ws.prefix[0] = 0;
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t k = lane; k < ncand; k += 32) {
+        int c = 0;  // largest c with prefix[c] <= k: the non-empty range that contains candidate k
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (ws.prefix[c + step] <= k) c += step;
+        const float4 p = __ldg(g.sorted + ws.start[c] + (k - ws.prefix[c]));
+        best.insert(pack_cand(dist2_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)), p.x, p.y, p.z);
+      }
+      __syncwarp();
     }
-    group_merge<K, G>(best, res, gmask);
+    warp_merge<K, XYZ>(best, res);
+    if (brute) return;
 
     // distance (metres) from the query to the nearest unvisited voxel, made conservative against the float
     // rounding of the voxel coordinates of both the query and any map point (2^-24 relative each).
-    float margin = (umax + (float)r + 2.f) * 2.4e-7f;
-    float bound = ((float)r + fmin - margin) * g.cell;
-    float b2 = bound > 0.f ? bound * bound * 0.999999f : 0.f;
-    float dk = cand_d2(res[K - 1]);  // NaN pattern when fewer than K found
-    bool done = (res[K - 1] != kSentinel && dk < b2) || (max_d2 > 0.f && b2 >= max_d2) ||
-                (cx - r <= bx0 && cx + r >= bx1 && cy - r <= by0 && cy + r >= by1 && cz - r <= bz0 && cz + r >= bz1);
+    const float margin = (umax + (float)r + 2.f) * 2.4e-7f;
+    const float bound = ((float)r + fmin - margin) * g.cell;
+    const float b2 = bound > 0.f ? bound * bound * 0.999999f : 0.f;
+    const float dk = cand_d2(res.key[K - 1]);  // NaN pattern when fewer than K found
+    const bool done = (res.key[K - 1] != kSentinel && dk < b2) || (max_d2 > 0.f && b2 >= max_d2) ||
+                      (cx - r <= bb[0] && cx + r >= bb[3] && cy - r <= bb[1] && cy + r >= bb[4] && cz - r <= bb[2] &&
+                       cz + r >= bb[5]);
     if (done) return;
-    if (r >= kMaxRing) break;
     ++r;
+    // re-seed: lane 0 carries the merged result forward (brute force restarts from scratch), others start empty
+    best.clear();
+    if (lane == 0 && r <= kMaxRing) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) best[k] = (lane == 0) ? res[k] : kSentinel;
+      for (int k = 0; k < K; ++k) {
+        best.key[k] = res.key[k];
+        if (XYZ) best.x[k] = res.x[k], best.y[k] = res.y[k], best.z[k] = res.z[k];
+      }
+    }
   }
-  // brute-force fallback (rare: sparse maps / far-away queries with no distance bound)
-#pragma unroll
-  for (int k = 0; k < K; ++k) best[k] = kSentinel;
-  for (int j = lane; j < g.n; j += G) {
-    float4 p = __ldg(g.sorted + j);
-    topk_insert<K>(best, pack_cand(dist2_rn(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)));
-  }
-  group_merge<K, G>(best, res, gmask);
 }
+
+__device__ __forceinline__ void load_bbox(const GridView& g, int (&bb)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) bb[i] = __ldg(g.bbox + i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast fp64 reciprocal / rsqrt: MUFU seed (2^-23 relative) + two Newton steps => ~1 ulp, ~3x shorter dependent
+// chain than the IEEE sequences; used only where the result is compared against the oracle with a tolerance
+// (fits, residuals, LM), never in the float k-NN distance path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double frcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double frsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  y = y * fma(-(h * y), y, 1.5);
+  y = y * fma(-(h * y), y, 1.5);
+  return y;
+}
+__device__ __forceinline__ double fsqrt(double x) { return x > 0.0 ? x * frsqrt(x) : 0.0; }
 
 // ------------------------------------------------------------------------------------------------
 // double-precision helpers (Eigen-compatible operation order, no FMA)

@@ -129,26 +129,27 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, cons
 // ---------------------------------------------------------------------------------------------------
 // stand-alone k-NN kernel: one G-lane group per query
 // ---------------------------------------------------------------------------------------------------
-template <int K, int G>
-__global__ void __launch_bounds__(256) knn_kernel(GridView g, const float* __restrict__ q, int nq, int stride_f, int k_out,
+template <int K>
+__global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __restrict__ q, int nq, int stride_f, int k_out,
                                                   float max_d2, int32_t* __restrict__ idx, float* __restrict__ d2) {
-  const int groups_per_block = blockDim.x / G;
-  const int gid = blockIdx.x * groups_per_block + threadIdx.x / G;
-  const unsigned lane = threadIdx.x % G;
-  const unsigned wl = threadIdx.x & 31;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl - lane));
-  if (gid >= nq) return;  // whole groups exit together
-  const float* qp = q + (size_t)gid * stride_f;
-  float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-  u64 res[K];
-  knn_search<K, G>(g, qx, qy, qz, max_d2, lane, gmask, res);
-  if (lane == 0) {
+  __shared__ WarpScratch scratch[4];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int bb[6];
+  load_bbox(g, bb);
+  const int nwarps = gridDim.x * 4;
+  for (int gid = blockIdx.x * 4 + warp; gid < nq; gid += nwarps) {
+    const float* qp = q + (size_t)gid * stride_f;
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    KnnResult<K, false> res;
+    knn_search<K, false>(g, bb, qx, qy, qz, max_d2, lane, scratch[warp], res);
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (k < k_out) {
-        bool have = res[k] != kSentinel;
-        idx[(size_t)gid * k_out + k] = have ? cand_idx(res[k]) : -1;
-        d2[(size_t)gid * k_out + k] = have ? cand_d2(res[k]) : __int_as_float(0x7f800000);
+      for (int k = 0; k < K; ++k) {
+        if (k < k_out) {
+          bool have = res.key[k] != kSentinel;
+          idx[(size_t)gid * k_out + k] = have ? cand_idx(res.key[k]) : -1;
+          d2[(size_t)gid * k_out + k] = have ? cand_d2(res.key[k]) : __int_as_float(0x7f800000);
+        }
       }
     }
   }
@@ -229,13 +230,10 @@ GridView Map::view() const {
 template <int K>
 static void launch_knn(const GridView& g, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
                        float* d_d2, cudaStream_t s, int sm_count) {
-  // few queries: a whole warp per query (latency); many queries: 8 lanes per query (throughput)
-  const int T = 256;
-  if ((long long)nq * 32 <= (long long)sm_count * 2048 * 2) {
-    knn_kernel<K, 32><<<(nq + T / 32 - 1) / (T / 32), T, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
-  } else {
-    knn_kernel<K, 8><<<(nq + T / 8 - 1) / (T / 8), T, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
-  }
+  // one warp per query; at most ~16 resident warps per SM, further queries are taken grid-stride
+  long long blocks = ((long long)nq + 3) / 4, cap = (long long)sm_count * 4 * 4;
+  if (blocks > cap) blocks = cap;
+  knn_kernel<K><<<(unsigned)blocks, 128, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
 }
 
 int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2) {

@@ -24,8 +24,8 @@ __device__ __forceinline__ void jacobi_rot(double& app, double& aqq, double& apq
   // t = tan(phi) of the annihilating rotation, smaller root: sgn(h) 2 apq / (|h| + sqrt(h^2 + 4 apq^2)), h = aqq - app
   // (one sqrt, one division and one rsqrt per rotation: fp64 div/sqrt are the long-latency ops of this kernel)
   const double h = aqq - app;
-  const double t = (h >= 0.0 ? 2.0 : -2.0) * apq / (fabs(h) + sqrt(h * h + 4.0 * apq * apq));
-  const double c = rsqrt(t * t + 1.0), s = t * c;
+  const double t = (h >= 0.0 ? 2.0 : -2.0) * apq * frcp(fabs(h) + fsqrt(h * h + 4.0 * apq * apq));
+  const double c = frsqrt(t * t + 1.0), s = t * c;
   app -= t * apq;
   aqq += t * apq;
   apq = 0.0;
@@ -42,7 +42,7 @@ __device__ __forceinline__ bool fit_line(const float (&nb)[5][3], double ratio, 
   double cx = 0, cy = 0, cz = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) cx = cx + (double)nb[j][0], cy = cy + (double)nb[j][1], cz = cz + (double)nb[j][2];
-  cx = cx / 5.0, cy = cy / 5.0, cz = cz / 5.0;
+  cx = cx * 0.2, cy = cy * 0.2, cz = cz * 0.2;
   double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
         perm[j] = tp;
       }
     }
-    const double nr = sqrt(best);
+    const double nr = fsqrt(best);
     if (nr == 0.0) {
       rinv[k] = 0.0;
       continue;
@@ -118,7 +118,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
     // reflector v = x - alpha e_k with alpha = -sgn(x_k)|x|;  v^T v = 2(|x|^2 - alpha x_k)  =>  2 / v^T v = beta
     const double xk = A[k][k];
     const double alpha = xk > 0.0 ? -nr : nr;
-    const double beta = 1.0 / (best - alpha * xk);
+    const double beta = frcp(best - alpha * xk);
     double v[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) v[i] = i >= k ? A[i][k] : 0.0;
@@ -139,7 +139,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
 #pragma unroll
     for (int i = k; i < 5; ++i) b[i] -= s * v[i];
     A[k][k] = alpha;  // R diagonal
-    rinv[k] = 1.0 / alpha;
+    rinv[k] = frcp(alpha);
   }
   double y[3];
 #pragma unroll
@@ -157,7 +157,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nb)[5][3], double tol, d
       if (perm[k] == c) n[c] = y[k];
   }
   const double nn2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-  const double d = rsqrt(nn2);  // negative_OA_dot_norm = 1/|n|
+  const double d = frsqrt(nn2);  // negative_OA_dot_norm = 1/|n|
   n[0] *= d, n[1] *= d, n[2] *= d;
   bool ok = nn2 > 0.0 && isfinite(d);
 #pragma unroll
@@ -182,73 +182,83 @@ struct AssocParams {
   double line_ratio, plane_tol;
 };
 
-template <int G>
-__global__ void __launch_bounds__(256)
+constexpr int kAssocThreads = 128;
+
+// One warp per stack point (grid-stride when the stacks exceed one resident wave).
+__global__ void __launch_bounds__(kAssocThreads, 5)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
                      int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv) {
-  const int groups_per_block = blockDim.x / G;
-  const int gid = blockIdx.x * groups_per_block + threadIdx.x / G;
-  const unsigned lane = threadIdx.x % G;
-  const unsigned wl = threadIdx.x & 31;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl - lane));
-  if (gid >= nc + ns) return;
-  const bool is_corner = gid < nc;
-  const float* pp = is_corner ? corner + (size_t)gid * stride_f : surf + (size_t)(gid - nc) * stride_f;
-  const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
-  double q[4] = {st->xq[0], st->xq[1], st->xq[2], st->xq[3]};
-  // pointAssociateToMap: double math, float store
-  D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
-  const float qx = __double2float_rn(dadd(pw.x, st->xt[0]));
-  const float qy = __double2float_rn(dadd(pw.y, st->xt[1]));
-  const float qz = __double2float_rn(dadd(pw.z, st->xt[2]));
-
-  u64 res[5];
-  if (is_corner)
-    knn_search<5, G>(gc, qx, qy, qz, prm.gate_sq, lane, gmask, res);
-  else
-    knn_search<5, G>(gs, qx, qy, qz, prm.gate_sq, lane, gmask, res);
-
-  const bool gate = res[4] != kSentinel && cand_d2(res[4]) < prm.gate_sq;
-  int type = 0;
-  double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, w = 0;
-  if (gate) {  // group-uniform
-    // lanes 0..4 gather one neighbour each (original-order array), then everything is shuffled to lane 0
-    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-      int my = 0;
+  __shared__ WarpScratch scratch[kAssocThreads / 32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * (kAssocThreads / 32);
+  // everything that does not depend on the point is fetched up front so that the latencies overlap
+  int bbc[6], bbs[6];
+  load_bbox(gc, bbc);
+  load_bbox(gs, bbs);
+  const double q[4] = {st->xq[0], st->xq[1], st->xq[2], st->xq[3]};
+  const double tx = st->xt[0], ty = st->xt[1], tz = st->xt[2];
+#ifdef ILSM_DEBUG_TIMING
+#define ASTAMP(k) do { if (lane == 0 && (gid == 5 || gid == nc + 1000)) const_cast<LmState*>(st)->dbg[48 + (gid == 5 ? 0 : 8) + (k)] = clock64(); } while (0)
+#else
+#define ASTAMP(k) do { } while (0)
+#endif
+#pragma unroll 1
+  for (int gid = blockIdx.x * (kAssocThreads / 32) + warp; gid < nc + ns; gid += nwarps) {
+    ASTAMP(0);
+    const bool is_corner = gid < nc;
+    const float* pp = is_corner ? corner + (size_t)gid * stride_f : surf + (size_t)(gid - nc) * stride_f;
+    const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+    // pointAssociateToMap: double math, float store
+    const D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
+    const float qx = __double2float_rn(dadd(pw.x, tx));
+    const float qy = __double2float_rn(dadd(pw.y, ty));
+    const float qz = __double2float_rn(dadd(pw.z, tz));
+    ASTAMP(1);
+    KnnResult<5, true> res;  // the neighbours' coordinates travel with the keys: no dependent gather before the fit
+    GridView g;  // field-wise select keeps everything in registers (no local-memory copy of the parameter structs)
+    g.cells = is_corner ? gc.cells : gs.cells;
+    g.sorted = is_corner ? gc.sorted : gs.sorted;
+    g.orig = nullptr;
+    g.bbox = nullptr;
+    g.mask = is_corner ? gc.mask : gs.mask;
+    g.log2_size = is_corner ? gc.log2_size : gs.log2_size;
+    g.cell = is_corner ? gc.cell : gs.cell;
+    g.inv_cell = is_corner ? gc.inv_cell : gs.inv_cell;
+    g.n = is_corner ? gc.n : gs.n;
+    int bb[6];
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if ((int)lane == k) my = cand_idx(res[k]);
-      if (lane < 5) me = __ldg((is_corner ? gc.orig : gs.orig) + my);
-    }
-    float nb[5][3];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      nb[k][0] = __shfl_sync(gmask, me.x, k, G);
-      nb[k][1] = __shfl_sync(gmask, me.y, k, G);
-      nb[k][2] = __shfl_sync(gmask, me.z, k, G);
-    }
+    for (int i = 0; i < 6; ++i) bb[i] = is_corner ? bbc[i] : bbs[i];
+    knn_search<5, true>(g, bb, qx, qy, qz, prm.gate_sq, lane, scratch[warp], res);
+    ASTAMP(2);
     if (lane == 0) {
-      if (is_corner) {
-        if (fit_line(nb, prm.line_ratio, a, b)) type = 1;
-      } else {
-        if (fit_plane(nb, prm.plane_tol, a, w)) type = 2;
-      }
-    }
-  }
-  if (lane == 0) {
-    fv.type[gid] = type;
-    fv.p[gid] = make_float4(px, py, pz, 0.f);
-    fv.a[gid] = make_double4(a[0], a[1], a[2], w);
-    fv.b[gid] = make_double4(b[0], b[1], b[2], 0.0);
-    if (fv.knn_idx) {
+      const bool gate = res.key[4] != kSentinel && cand_d2(res.key[4]) < prm.gate_sq;
+      int type = 0;
+      double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, w = 0;
+      if (gate) {
+        float nb[5][3];
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        bool have = res[k] != kSentinel;
-        fv.knn_idx[(size_t)gid * 5 + k] = have ? cand_idx(res[k]) : -1;
-        fv.knn_d2[(size_t)gid * 5 + k] = have ? cand_d2(res[k]) : __int_as_float(0x7f800000);
+        for (int k = 0; k < 5; ++k) nb[k][0] = res.x[k], nb[k][1] = res.y[k], nb[k][2] = res.z[k];
+        if (is_corner) {
+          if (fit_line(nb, prm.line_ratio, a, b)) type = 1;
+        } else {
+          if (fit_plane(nb, prm.plane_tol, a, w)) type = 2;
+        }
+      }
+      ASTAMP(3);
+      fv.type[gid] = type;
+      fv.p[gid] = make_float4(px, py, pz, 0.f);
+      fv.a[gid] = make_double4(a[0], a[1], a[2], w);
+      fv.b[gid] = make_double4(b[0], b[1], b[2], 0.0);
+      if (fv.knn_idx) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const bool have = res.key[k] != kSentinel;
+          fv.knn_idx[(size_t)gid * 5 + k] = have ? cand_idx(res.key[k]) : -1;
+          fv.knn_d2[(size_t)gid * 5 + k] = have ? cand_d2(res.key[k]) : __int_as_float(0x7f800000);
+        }
       }
     }
+    __syncwarp();
   }
 }
 
@@ -279,15 +289,15 @@ __device__ __forceinline__ void eval_factor(int type, const float4 pf, const dou
     D3 u = d3(lp.x - fa.x, lp.y - fa.y, lp.z - fa.z), v = d3(lp.x - fb.x, lp.y - fb.y, lp.z - fb.z);
     D3 nu = d3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
     const double dex = fa.x - fb.x, dey = fa.y - fb.y, dez = fa.z - fb.z;
-    const double idn = rsqrt(dex * dex + dey * dey + dez * dez);  // 1/|a-b|
+    const double idn = frsqrt(dex * dex + dey * dey + dez * dez);  // 1/|a-b|
     const double r0 = nu.x * idn, r1 = nu.y * idn, r2 = nu.z * idn;
     const double mx = -dex * idn, my = -dey * idn, mz = -dez * idn;  // (b - a)/|a-b|
     const double sq = r0 * r0 + r1 * r1 + r2 * r2;
     double rho0 = sq, sc = 1.0;
     if (huber_a > 0.0 && sq > huber_a * huber_a) {  // ceres::HuberLoss + Corrector (rho'' <= 0): scale by sqrt(rho')
-      const double irr = rsqrt(sq);
+      const double irr = frsqrt(sq);
       rho0 = 2.0 * huber_a * (sq * irr) - huber_a * huber_a;
-      sc = sqrt(fmax(2.2250738585072014e-308, huber_a * irr));
+      sc = fsqrt(huber_a * irr);
     }
     acc[0] += 0.5 * rho0;
     acc[28] += 1.0;
@@ -310,9 +320,9 @@ __device__ __forceinline__ void eval_factor(int type, const float4 pf, const dou
     const double sq = r0 * r0;
     double rho0 = sq, sc = 1.0;
     if (huber_a > 0.0 && sq > huber_a * huber_a) {
-      const double irr = rsqrt(sq);
+      const double irr = frsqrt(sq);
       rho0 = 2.0 * huber_a * (sq * irr) - huber_a * huber_a;
-      sc = sqrt(fmax(2.2250738585072014e-308, huber_a * irr));
+      sc = fsqrt(huber_a * irr);
     }
     acc[0] += 0.5 * rho0;
     acc[29] += 1.0;
@@ -351,14 +361,29 @@ __device__ __forceinline__ void quat_mul_d(const double a[4], const double b[4],
   o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
   o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
 }
-// EigenQuaternionParameterization::Plus
+// EigenQuaternionParameterization::Plus:  [sin|d|/|d| d, cos|d|] * x.
+// sin(u)/u and cos(u) are even in u: for |d| < 0.5 (every LM step of a converging registration) they are evaluated
+// as Taylor polynomials in |d|^2 (truncation < 1e-17), which drops sqrt, sincos and a division from the critical
+// path of the single-threaded trust-region update; larger steps take the libm path.
 __device__ __forceinline__ void quat_plus_d(const double x[4], const double d[3], double o[4]) {
-  const double nd2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-  if (nd2 > 0.0) {
-    const double nd = sqrt(nd2);
-    double sn, cs;
-    sincos(nd, &sn, &cs);
-    const double sbd = sn / nd;
+  const double u2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  if (u2 > 0.0) {
+    double sbd, cs;
+    if (u2 < 0.25) {
+      // sin(u)/u = sum (-1)^k u^2k/(2k+1)!   cos(u) = sum (-1)^k u^2k/(2k)!
+      sbd = fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, -7.6471637318198164759e-13, 1.6059043836821614599e-10),
+                                                       -2.5052108385441718775e-8), 2.7557319223985890653e-6),
+                                    -1.9841269841269841270e-4), 8.3333333333333333333e-3), -1.6666666666666666667e-1), 1.0);
+      cs = fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, fma(u2, 4.7794773323873852974e-14, -1.1470745597729724714e-11),
+                                                              2.0876756987868098979e-9), -2.7557319223985890653e-7),
+                                           2.4801587301587301587e-5), -1.3888888888888888889e-3), 4.1666666666666666667e-2),
+                       -0.5), 1.0);
+    } else {
+      const double nd = sqrt(u2);
+      double sn;
+      sincos(nd, &sn, &cs);
+      sbd = sn / nd;
+    }
     double dq[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cs};
     quat_mul_d(dq, x, o);
   } else {
@@ -383,7 +408,7 @@ __device__ __forceinline__ bool ldlt_solve6(double (&m)[21], const double (&b)[6
     for (int k = 0; k < j; ++k) dj -= m[lt(j, k)] * m[lt(j, k)] * m[lt(k, k)];
     ok = ok && (dj > 0.0);
     m[lt(j, j)] = dj;
-    dinv[j] = 1.0 / dj;
+    dinv[j] = frcp(dj);
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = m[lt(i, j)];
@@ -467,7 +492,7 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      s->scale[a] = 1.0 / (1.0 + sqrt(s->H[k]));
+      s->scale[a] = frcp(1.0 + fsqrt(s->H[k]));
       k += 6 - a;
     }
   } else {
@@ -484,7 +509,10 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
       step2 += d * d;
       x2 += s->xt[i] * s->xt[i];
     }
-    if (sqrt(step2) <= parameter_tolerance * (sqrt(x2) + parameter_tolerance)) {
+    // |step| <= ptol (|x| + ptol); |x| >= ~1 (unit quaternion) so the square-root test is only reached when the
+    // cheap squared bound says it can possibly hold
+    if (step2 <= 1.001 * parameter_tolerance * parameter_tolerance * (x2 + 1.0) &&
+        sqrt(step2) <= parameter_tolerance * (sqrt(x2) + parameter_tolerance)) {
       lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
@@ -493,7 +521,7 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
       lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    const double rho = cost_change / s->model_cost_change;
+    const double rho = cost_change * frcp(s->model_cost_change);
     if (rho > min_relative_decrease) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) s->xq[i] = s->cq[i];
@@ -505,13 +533,13 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
 #pragma unroll
       for (int i = 0; i < 6; ++i) s->g[i] = sums[22 + i];
       const double w = 2.0 * rho - 1.0;
-      s->radius = s->radius / fmax(1.0 / 3.0, 1.0 - w * w * w);
+      s->radius = s->radius * frcp(fmax(1.0 / 3.0, 1.0 - w * w * w));
       s->radius = fmin(max_radius, s->radius);
       s->decrease_factor = 2.0;
       s->reuse_diag = 0;
       s->n_success += 1;
     } else {
-      s->radius = s->radius / s->decrease_factor;
+      s->radius = s->radius * frcp(s->decrease_factor);  // decrease_factor is a power of two: exact
       s->decrease_factor *= 2.0;
       s->reuse_diag = 1;
       s->n_unsuccess += 1;
@@ -524,17 +552,18 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
       lm_terminate(s, rep, ILSM_NO_CONVERGENCE);
       return;
     }
-    {  // gradient_max_norm = |x - Plus(x, -g)|_inf in the ambient space
-      double ng[3] = {-s->g[0], -s->g[1], -s->g[2]}, qp[4];
-      quat_plus_d(s->xq, ng, qp);
-      double m = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) m = fmax(m, fabs(s->xq[i] - qp[i]));
-#pragma unroll
-      for (int i = 0; i < 3; ++i) m = fmax(m, fabs(s->g[3 + i]));
+    {  // gradient_max_norm = |x - Plus(x, -g)|_inf in the ambient space; the translation rows are exactly |g_t|,
+       // so the quaternion rows (one sincos) only matter when those are already below the tolerance
+      double m = fmax(fmax(fabs(s->g[3]), fabs(s->g[4])), fabs(s->g[5]));
       if (m <= gradient_tolerance) {
-        lm_terminate(s, rep, ILSM_CONVERGENCE);
-        return;
+        double ng[3] = {-s->g[0], -s->g[1], -s->g[2]}, qp[4];
+        quat_plus_d(s->xq, ng, qp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m = fmax(m, fabs(s->xq[i] - qp[i]));
+        if (m <= gradient_tolerance) {
+          lm_terminate(s, rep, ILSM_CONVERGENCE);
+          return;
+        }
       }
     }
     if (s->radius <= min_radius) {
@@ -552,7 +581,7 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
         s->diag[a] = fmin(fmax(haa, min_diag), max_diag);
       }
     }
-    const double inv_radius = 1.0 / s->radius;
+    const double inv_radius = frcp(s->radius);
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -562,20 +591,17 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
     s->reuse_diag = 1;
     double mcc = 0;
     if (ok) {
-      double sg = 0, sHs = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) step[a] = -y[a];
+      // model_cost_change = -(step^T g + 1/2 step^T H step) with step = -y and (H + D) y = g
+      //                   = 1/2 (y^T g + y^T D y)
+      double yg = 0, yDy = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
-        sg += step[a] * gs[a];
-        double hv = 0;
-#pragma unroll
-        for (int b = 0; b < 6; ++b)
-          hv += s->H[a <= b ? ut(a, b) : ut(b, a)] * s->scale[a] * s->scale[b] * step[b];
-        sHs += step[a] * hv;
-        ok = ok && isfinite(step[a]);
+        step[a] = -y[a];
+        yg += y[a] * gs[a];
+        yDy += y[a] * y[a] * (s->diag[a] * inv_radius);
+        ok = ok && isfinite(y[a]);
       }
-      mcc = -(sg + 0.5 * sHs);
+      mcc = 0.5 * (yg + yDy);
     }
     if (!ok || !(mcc > 0.0)) {  // HandleInvalidStep
       s->n_unsuccess += 1;
@@ -583,7 +609,7 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
         lm_terminate(s, rep, ILSM_FAILURE);
         return;
       }
-      s->radius = s->radius / s->decrease_factor;
+      s->radius = s->radius * frcp(s->decrease_factor);
       s->decrease_factor *= 2.0;
       s->reuse_diag = 1;
       continue;
@@ -642,7 +668,9 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   __shared__ double tot[kSumStride];
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cl_tid = (int)rank * kSolveThreads + tid, cl_n = kClusterSize * kSolveThreads;
+  // factor i -> CTA (i % 8), thread (i / 8): the edge factors (3 residual rows, the first nc slots) are spread
+  // evenly over the CTAs instead of all landing on CTA 0
+  const int cl_tid = tid * kClusterSize + (int)rank, cl_n = kClusterSize * kSolveThreads;
   LmState* s = reinterpret_cast<LmState*>(core);  // only the fields before `report` exist in this copy
 
   // factor of the first round stays in registers for every evaluation
@@ -666,22 +694,36 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   __syncthreads();
   ilsm_reg_report* rep = rank == 0 ? &st->report : nullptr;
 
+#ifdef ILSM_DEBUG_TIMING
+#define STAMP(k) do { if (rank == 0 && tid == 0 && e < 6) st->dbg[e * 8 + (k)] = clock64(); } while (0)
+#else
+#define STAMP(k) do { } while (0)
+#endif
 #pragma unroll 1
   for (int e = 0; s->status == 0; ++e) {
+    STAMP(0);
     const double q[4] = {s->cq[0], s->cq[1], s->cq[2], s->cq[3]};
     const double t[3] = {s->ct[0], s->ct[1], s->ct[2]};
     const double huber_a = s->huber_a;
     double acc[kSumStride];
 #pragma unroll
     for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
-    if (type0) eval_factor(type0, p0, a0, b0, q, t, huber_a, acc);
-    for (int i = cl_tid + cl_n; i < n; i += cl_n) {  // maps larger than one cluster round (config-3 sizes)
-      const int ty = fv.type[i];
-      if (ty) eval_factor(ty, fv.p[i], fv.a[i], fv.b[i], q, t, huber_a, acc);
+#pragma unroll 1
+    for (int i = cl_tid, it = 0; i < n; i += cl_n, ++it) {  // it > 0: stacks larger than one cluster round
+      int ty = type0;
+      float4 pf = p0;
+      double4 fa = a0, fb = b0;
+      if (it > 0) {
+        ty = fv.type[i];
+        if (ty) pf = fv.p[i], fa = fv.a[i], fb = fv.b[i];
+      }
+      if (ty) eval_factor(ty, pf, fa, fb, q, t, huber_a, acc);
     }
+    STAMP(1);
     const double mine = warp_reduce_transpose(acc, lane);
     red[warp][lane] = mine;
     __syncthreads();
+    STAMP(2);
     if (tid < kSumStride) {
       double v = 0;
 #pragma unroll
@@ -689,6 +731,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
       part[e & 1][tid] = v;
     }
     cluster_sync_all();  // partials of every CTA visible cluster-wide
+    STAMP(3);
     if (tid < kSumStride) {
       double v = 0;
 #pragma unroll
@@ -696,8 +739,11 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
       tot[tid] = v;
     }
     __syncthreads();
+    STAMP(4);
     if (tid == 0) lm_advance(s, rep, tot);
+    STAMP(5);
     __syncthreads();
+    STAMP(6);
   }
   cluster_sync_all();  // nobody may exit while a peer can still read its shared memory
   if (rank == 0) {
@@ -793,15 +839,11 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   prm.plane_tol = o.plane_tol;
   GridView gc = mc->view(), gs = ms->view();
   FactorView fv = factor_view(fac, want_knn);
-  const int T = 256;
   const int stride_f = stride_bytes / 4;
-  if ((long long)n * 32 <= (long long)sm_count * 2048 * 2) {
-    associate_kernel<32><<<(n + T / 32 - 1) / (T / 32), T, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p,
-                                                                         prm, fv);
-  } else {
-    associate_kernel<8><<<(n + T / 8 - 1) / (T / 8), T, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p,
-                                                                       prm, fv);
-  }
+  // one warp per stack point, capped at one resident wave (5 blocks x 4 warps per SM at this register budget)
+  long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
+  if (blocks > cap) blocks = cap;
+  associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p, prm, fv);
   count_launches(1);
   return check_launch("associate");
 }
