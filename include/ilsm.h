@@ -187,6 +187,56 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q_xyzw[4], const do
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q_xyzw[4], double t_xyz[3], int max_num_iterations, double huber_a,
                ilsm_solve_summary* summary);
 
+/* ------------------------------------------------------------- K4: front end (projection + features) ---- */
+
+/* Organised H x W cloud -> image_range (u8, min(range*20,255)), image_intensity (u8, min(I,255)) and cloud_track
+ * (H*W packed xyzi floats; zeroed where range < 0.1).  Intensity is read at byte 16 for 32-byte PCL points and at
+ * byte 12 for 16-byte packed points.  image_ambient of the reference stays all-zero and is not produced.
+ * Replaces: ImageHandler::cloud_handler(msg)  image_handler.h_ouster:103-140 (called at scanRegistration.cpp:195,
+ *           mapOptimization.cpp:145). */
+ILSM_API int ilsm_project(ilsm_ctx* ctx, const float* xyzi, int H, int W, int stride_bytes, uint8_t* range_img,
+                          uint8_t* inten_img, float* cloud_track_xyzi);
+ILSM_API int ilsm_project_dev(ilsm_ctx* ctx, const float* d_xyzi, int H, int W, int stride_bytes, uint8_t* d_range_img,
+                              uint8_t* d_inten_img, float* d_cloud_track_xyzi);
+
+typedef struct ilsm_feature_counts {
+  int32_t n_cloud;      /* ring-ordered cloud size (laserCloud) */
+  int32_t n_sharp;      /* cornerPointsSharp */
+  int32_t n_less_sharp; /* cornerPointsLessSharp */
+  int32_t n_flat;       /* surfPointsFlat */
+  int32_t n_less_flat;  /* surfPointsLessFlat (after the per-ring 0.2 m VoxelGrid) */
+  int32_t flags;        /* non-zero: a ring segment exceeded the supported size */
+  int32_t ring_start[64]; /* scanStartInd */
+  int32_t ring_end[64];   /* scanEndInd */
+} ilsm_feature_counts;
+
+/* Caller-provided output arrays, each sized for n input points (any pointer may be NULL to skip that output). */
+typedef struct ilsm_features {
+  float* cloud_xyzi;       /* n x 4: ring-ordered cloud, intensity = scanID + 0.1 * relTime */
+  float* curvature;        /* n     : cloudCurvature */
+  int32_t* label;          /* n     : cloudLabel {2, 1, 0, -1} */
+  int32_t* src_index;      /* n     : index of each ring-ordered point in the input cloud */
+  int32_t* sharp_idx;      /* indices into the ring-ordered cloud, reference push order */
+  int32_t* less_sharp_idx;
+  int32_t* flat_idx;
+  float* less_flat_xyzi;   /* n x 4 */
+  ilsm_feature_counts counts;
+} ilsm_features;
+
+/* The numeric body of laserCloudHandler for a 64-ring sensor: min-range filter, ring (scanID) bucketing, curvature,
+ * per-ring 6-segment sort (ties broken by point index) and sharp / less-sharp / flat / less-flat selection with
+ * neighbour suppression, per-ring VoxelGrid(0.2) of the less-flat points.
+ * Replaces: scanRegistration.cpp:235-589 (removeClosedPointCloud :152-186, ring/time tagging :277-374,
+ *           curvature :397-412, labelling :427-577, VoxelGrid :580-589). */
+ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float min_range,
+                                   ilsm_features* out);
+
+/* pcl::VoxelGrid<PointXYZI>::filter with a cubic leaf: centroid of every field per voxel, output in ascending
+ * voxel index; points of one voxel are accumulated in input order.  n <= 16384 per call in this version.
+ * Replaces: downSizeFilterCorner/Surf.filter  laserMapping.cpp:608-616 ; voxel_grid_.filter mapOptimization.cpp:368-370 */
+ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
+                            int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,18 @@ class RegReport(C.Structure):
     _fields_ = [("passes", C.c_int32), ("reserved", C.c_int32), ("pass_", SolveSummary * MAX_OUTER)]
 
 
+class FeatureCounts(C.Structure):
+    _fields_ = [("n_cloud", C.c_int32), ("n_sharp", C.c_int32), ("n_less_sharp", C.c_int32), ("n_flat", C.c_int32),
+                ("n_less_flat", C.c_int32), ("flags", C.c_int32), ("ring_start", C.c_int32 * 64),
+                ("ring_end", C.c_int32 * 64)]
+
+
+class Features(C.Structure):
+    _fields_ = [("cloud_xyzi", C.c_void_p), ("curvature", C.c_void_p), ("label", C.c_void_p), ("src_index", C.c_void_p),
+                ("sharp_idx", C.c_void_p), ("less_sharp_idx", C.c_void_p), ("flat_idx", C.c_void_p),
+                ("less_flat_xyzi", C.c_void_p), ("counts", FeatureCounts)]
+
+
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
 _lib = None
@@ -75,6 +87,10 @@ def load_library(path: str | None = None):
         "ilsm_register": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport)]),
         "ilsm_register_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts), vp]),
         "ilsm_associate": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), vp, vp, vp]),
+        "ilsm_project": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "ilsm_project_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "ilsm_extract_features": (i32, [vp, vp, i32, i32, f32, C.POINTER(Features)]),
+        "ilsm_voxelgrid": (i32, [vp, vp, i32, i32, f32, vp, C.POINTER(i32)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
@@ -170,6 +186,50 @@ class Context:
                      opts: RegOpts | None = None, d_report_ptr=None):
         _check(self._lib.ilsm_register_dev(self._h, map_corner._h, map_surf._h, d_corner_ptr, nc, d_surf_ptr, ns, stride,
                                            d_pose_ptr, C.byref(opts) if opts is not None else None, d_report_ptr))
+
+    # -- ImageHandler::cloud_handler (image_handler.h_ouster:103-140) ----------------------------
+    def cloud_handler(self, cloud, H=64, W=1024):
+        a, n, stride = _cloud(cloud)
+        if n != H * W:
+            raise ValueError("cloud must be organised H*W")
+        rng = np.empty((H, W), np.uint8)
+        inten = np.empty((H, W), np.uint8)
+        track = np.empty((H * W, 4), np.float32)
+        _check(self._lib.ilsm_project(self._h, _ptr(a), H, W, stride, _ptr(rng), _ptr(inten), _ptr(track)))
+        return rng, inten, track
+
+    def project_dev(self, d_cloud_ptr, H, W, stride, d_range_ptr, d_inten_ptr, d_track_ptr):
+        _check(self._lib.ilsm_project_dev(self._h, d_cloud_ptr, H, W, stride, d_range_ptr, d_inten_ptr, d_track_ptr))
+
+    # -- laserCloudHandler numeric body (scanRegistration.cpp:235-589) ---------------------------
+    def extract_features(self, cloud, min_range=0.3):
+        a, n, stride = _cloud(cloud)
+        cl = np.zeros((max(n, 1), 4), np.float32)
+        curv = np.zeros(max(n, 1), np.float32)
+        label = np.zeros(max(n, 1), np.int32)
+        src = np.zeros(max(n, 1), np.int32)
+        sharp = np.zeros(max(n, 1), np.int32)
+        lsharp = np.zeros(max(n, 1), np.int32)
+        flat = np.zeros(max(n, 1), np.int32)
+        lflat = np.zeros((max(n, 1), 4), np.float32)
+        f = Features(cl.ctypes.data, curv.ctypes.data, label.ctypes.data, src.ctypes.data, sharp.ctypes.data,
+                     lsharp.ctypes.data, flat.ctypes.data, lflat.ctypes.data)
+        _check(self._lib.ilsm_extract_features(self._h, _ptr(a), n, stride, min_range, C.byref(f)))
+        k = f.counts
+        N = k.n_cloud
+        return dict(cloud=cl[:N], curvature=curv[:N], label=label[:N], src_index=src[:N], sharp_idx=sharp[:k.n_sharp],
+                    less_sharp_idx=lsharp[:k.n_less_sharp], flat_idx=flat[:k.n_flat], less_flat=lflat[:k.n_less_flat],
+                    ring_start=np.array(k.ring_start[:]), ring_end=np.array(k.ring_end[:]))
+
+    # -- pcl::VoxelGrid::filter -------------------------------------------------------------------
+    def voxelgrid(self, cloud, leaf):
+        a, n, stride = _cloud(cloud)
+        if stride < 16:
+            raise ValueError("voxelgrid needs xyzi points (stride >= 16)")
+        out = np.empty((max(n, 1), 4), np.float32)
+        m = C.c_int(0)
+        _check(self._lib.ilsm_voxelgrid(self._h, _ptr(a), n, stride, leaf, _ptr(out), C.byref(m)))
+        return out[:m.value].copy()
 
     def associate_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
                       opts: RegOpts | None = None):

@@ -89,6 +89,11 @@ int Ctx::init(int dev) {
 
 void Ctx::release() {
   if (stream) cudaStreamSynchronize(stream);
+  fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
+  fe.src_index.release(), fe.label.release(), fe.sort_ind.release(), fe.ring_sharp.release(), fe.ring_lsharp.release();
+  fe.ring_flat.release(), fe.sharp.release(), fe.lsharp.release(), fe.flat.release(), fe.counts.release();
+  fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
+  fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
   lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
   fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
   if (stream) cudaStreamDestroy(stream);
@@ -407,6 +412,112 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const flo
     ILSM_CUDA(cudaMemcpyAsync(knn_d2, c.fac.knn_d2.p, (size_t)n * 5 * 4, cudaMemcpyDeviceToHost, c.stream));
   }
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ front end
+ILSM_API int ilsm_project(ilsm_ctx* ctx, const float* xyzi, int H, int W, int stride_bytes, uint8_t* range_img,
+                          uint8_t* inten_img, float* cloud_track_xyzi) {
+  if (!ctx || !xyzi || !range_img || !inten_img || !cloud_track_xyzi) return fail(ILSM_ERR_INVALID_ARG, "project: null argument");
+  if (H <= 0 || W <= 0 || !valid_stride(stride_bytes) || stride_bytes < 16) return fail(ILSM_ERR_INVALID_ARG, "project: bad H/W/stride");
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const int n = H * W;
+  const size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = c.fe.raw.reserve(bytes / 4 + 4)) || (rc = c.fe.img.reserve((size_t)2 * n + 8)) || (rc = c.fe.track.reserve(n + 4)))
+    return rc;
+  ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  unsigned char* d_r = c.fe.img.p;
+  unsigned char* d_i = c.fe.img.p + (((size_t)n + 3) & ~(size_t)3);
+  if ((rc = c.project_dev(c.fe.raw.p, n, stride_bytes, d_r, d_i, reinterpret_cast<float*>(c.fe.track.p)))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(range_img, d_r, n, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(inten_img, d_i, n, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(cloud_track_xyzi, c.fe.track.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_project_dev(ilsm_ctx* ctx, const float* d_xyzi, int H, int W, int stride_bytes, uint8_t* d_range_img,
+                              uint8_t* d_inten_img, float* d_cloud_track_xyzi) {
+  if (!ctx || !d_xyzi || !d_range_img || !d_inten_img || !d_cloud_track_xyzi) return fail(ILSM_ERR_INVALID_ARG, "project_dev: null argument");
+  if (H <= 0 || W <= 0 || !valid_stride(stride_bytes) || stride_bytes < 16) return fail(ILSM_ERR_INVALID_ARG, "project_dev: bad H/W/stride");
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return c.project_dev(d_xyzi, H * W, stride_bytes, d_range_img, d_inten_img, d_cloud_track_xyzi);
+}
+
+ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float min_range,
+                                   ilsm_features* out) {
+  if (!ctx || !out || (n > 0 && !xyzi)) return fail(ILSM_ERR_INVALID_ARG, "extract_features: null argument");
+  if (n < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "extract_features: bad n/stride");
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = c.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = c.features_dev(c.fe.raw.p, n, stride_bytes, min_range))) return rc;
+  // counts + ring histogram first, then exactly the produced amounts
+  int* pin = reinterpret_cast<int*>(c.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 8, c.fe.stats.p + 4, 64 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  ilsm_feature_counts& k = out->counts;
+  memset(&k, 0, sizeof(k));
+  k.n_cloud = pin[0], k.n_sharp = pin[1], k.n_less_sharp = pin[2], k.n_flat = pin[3], k.n_less_flat = pin[4];
+  k.flags = pin[5];
+  int off = 0;
+  for (int r = 0; r < 64; ++r) {
+    k.ring_start[r] = off + 5;
+    off += pin[8 + r];
+    k.ring_end[r] = off - 6;
+  }
+  if (k.flags) return fail(ILSM_ERR_INVALID_ARG, "extract_features: a ring segment exceeds the supported size");
+  const int N = k.n_cloud;
+  auto d2h = [&](void* dst, const void* src, size_t nbytes) -> cudaError_t {
+    if (!dst || nbytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, c.stream);
+  };
+  ILSM_CUDA(d2h(out->cloud_xyzi, c.fe.cloud.p, (size_t)N * 16));
+  ILSM_CUDA(d2h(out->curvature, c.fe.curv.p, (size_t)N * 4));
+  ILSM_CUDA(d2h(out->label, c.fe.label.p, (size_t)N * 4));
+  ILSM_CUDA(d2h(out->src_index, c.fe.src_index.p, (size_t)N * 4));
+  ILSM_CUDA(d2h(out->sharp_idx, c.fe.sharp.p, (size_t)k.n_sharp * 4));
+  ILSM_CUDA(d2h(out->less_sharp_idx, c.fe.lsharp.p, (size_t)k.n_less_sharp * 4));
+  ILSM_CUDA(d2h(out->flat_idx, c.fe.flat.p, (size_t)k.n_flat * 4));
+  ILSM_CUDA(d2h(out->less_flat_xyzi, c.fe.lflat.p, (size_t)k.n_less_flat * 16));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
+                            int* n_out) {
+  if (!ctx || !n_out || (n > 0 && (!xyzi || !out_xyzi))) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: null argument");
+  if (n < 0 || !valid_stride(stride_bytes) || stride_bytes < 16 || !(leaf > 0.f)) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: bad n/stride/leaf");
+  *n_out = 0;
+  if (n == 0) return ILSM_OK;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = c.fe.raw.reserve(bytes / 4 + 4)) || (rc = c.fe.vox_out.reserve(n + 4)) || (rc = c.fe.vox_n.reserve(4))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = c.voxelgrid_dev(c.fe.raw.p, n, nullptr, 0, stride_bytes, stride_bytes >= 32 ? 4 : 3, leaf, c.fe.vox_out.p,
+                            c.fe.vox_n.p)))
+    return rc;
+  int* pin = reinterpret_cast<int*>(c.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.vox_n.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  *n_out = pin[0];
+  if (pin[0] > 0) {
+    ILSM_CUDA(cudaMemcpyAsync(out_xyzi, c.fe.vox_out.p, (size_t)pin[0] * 16, cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  }
   return ILSM_OK;
 }
 

@@ -1,0 +1,716 @@
+// frontend.cu -- K4: range/intensity image projection, LOAM feature extraction and PCL-style VoxelGrid.
+//
+// Replaces ImageHandler::cloud_handler (image_handler.h_ouster:103-140), laserCloudHandler's numeric body
+// (scanRegistration.cpp:152-186, 244-412, 427-589) and pcl::VoxelGrid::filter (scanRegistration.cpp:580-589,
+// laserMapping.cpp:608-616, mapOptimization.cpp:368-370).
+//
+// Everything here is streaming / small-sort work bound by HBM bandwidth and launch latency; no tensor cores.
+// Float arithmetic that feeds integer decisions (ring id, curvature order, labels, voxel index) uses explicit
+// round-to-nearest intrinsics in the reference's evaluation order (x86-64 SSE2, no FMA).
+#include "ilsm_host.hpp"
+
+namespace ilsm {
+
+// ---------------------------------------------------------------------------------------------------
+// projection: 4 consecutive pixels per thread, float4 loads, uchar4 / float4 stores
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void project_one(float x, float y, float z, float inten, unsigned char& r8, unsigned char& i8,
+                                            float4& track) {
+  const float range = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  const float ic = (255.0f < inten) ? 255.0f : inten;  // std::min(intensity, 255.0f)
+  const float r20m = __fmul_rn(range, 20.f);
+  const float r20 = (255.0f < r20m) ? 255.0f : r20m;  // std::min(range * 20, 255.0f)
+  r8 = (unsigned char)(__float2int_rz(r20) & 0xFF);
+  i8 = (unsigned char)(__float2int_rz(ic) & 0xFF);
+  if ((double)range >= 0.1)
+    track = make_float4(x, y, z, ic);
+  else
+    track = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void project_kernel(const float* __restrict__ cloud, int n, int stride_f, int ioff,
+                               unsigned char* __restrict__ img_range, unsigned char* __restrict__ img_inten,
+                               float4* __restrict__ track) {
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  unsigned char r8[4] = {0, 0, 0, 0}, i8[4] = {0, 0, 0, 0};
+  float4 tr[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = i0 + k;
+    if (i < n) {
+      const float* p = cloud + (size_t)i * stride_f;
+      float x, y, z, it;
+      if ((stride_f & 3) == 0) {  // 16- or 32-byte points: one 128-bit load for xyz(+w)
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        x = v.x, y = v.y, z = v.z;
+        it = ioff == 3 ? v.w : __ldg(p + ioff);
+      } else {
+        x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2), it = __ldg(p + ioff);
+      }
+      project_one(x, y, z, it, r8[k], i8[k], tr[k]);
+    }
+  }
+  if (i0 + 3 < n) {
+    *reinterpret_cast<uchar4*>(img_range + i0) = make_uchar4(r8[0], r8[1], r8[2], r8[3]);
+    *reinterpret_cast<uchar4*>(img_inten + i0) = make_uchar4(i8[0], i8[1], i8[2], i8[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) track[i0 + k] = tr[k];
+  } else {
+    for (int k = 0; k < 4 && i0 + k < n; ++k) {
+      img_range[i0 + k] = r8[k];
+      img_inten[i0 + k] = i8[k];
+      track[i0 + k] = tr[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// feature extraction
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRings = 64;
+constexpr int kMaxSeg = 2048;      // points per (ring, segment) handled by the in-block sort
+constexpr int kMaxRingLF = 4096;   // less-flat points of one ring handled by the in-block VoxelGrid
+
+// FeStats layout (ints): [0] first kept index (min), [1] last kept index (max), [2] first index whose unwrapped
+// azimuth passes startOri + pi (the halfPassed latch), [3] error flags, [4..67] ring counts, [68..131] per-ring
+// sharp / [132..195] less-sharp / [196..259] flat / [260..323] less-flat output counts
+constexpr int kStFirst = 0, kStLast = 1, kStStar = 2, kStErr = 3, kStRing = 4, kStSharp = 68, kStLSharp = 132,
+              kStFlat = 196, kStLFlat = 260, kStInts = 324;
+
+__global__ void fe_init_kernel(int* st) {
+  const int i = threadIdx.x;
+  if (i < kStInts) st[i] = (i == kStFirst || i == kStStar) ? INT_MAX : (i == kStLast ? -1 : 0);
+}
+
+// pass 1: min-range filter, ring id, raw azimuth; ring histogram, first/last kept point
+__global__ void fe_tag_kernel(const float* __restrict__ in, int n, int stride_f, float thr2,
+                              unsigned char* __restrict__ scanid, float* __restrict__ ori_raw, int* st) {
+  __shared__ int hist[kRings];
+  if (threadIdx.x < kRings) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int first = INT_MAX, last = -1;
+  if (i < n) {
+    const float* p = in + (size_t)i * stride_f;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    unsigned char sid = 254;  // removed by the range filter
+    if (!(d2 < thr2)) {
+      first = last = i;
+      const float ratio = __fdiv_rn(z, __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
+      const float at = (float)atan((double)ratio);  // atan evaluated in double, rounded to float
+      const float angle = (float)((double)__fmul_rn(at, 180.f) / 3.14159265358979323846);
+      const int s = __double2int_rz(((double)angle + 22.5) * 1.41 + 0.5) - 1;
+      sid = (s >= 0 && s < kRings) ? (unsigned char)s : 255;
+      if (sid < kRings) atomicAdd(&hist[sid], 1);
+      ori_raw[i] = -atan2f(y, x);
+    }
+    scanid[i] = sid;
+  }
+  first = (int)__reduce_min_sync(0xffffffffu, (unsigned)first);
+  last = __reduce_max_sync(0xffffffffu, last);
+  if ((threadIdx.x & 31) == 0) {
+    if (first != INT_MAX) atomicMin(&st[kStFirst], first);
+    if (last >= 0) atomicMax(&st[kStLast], last);
+  }
+  __syncthreads();
+  if (threadIdx.x < kRings && hist[threadIdx.x]) atomicAdd(&st[kStRing + threadIdx.x], hist[threadIdx.x]);
+}
+
+struct OriRef {
+  float startOri, endOri;
+};
+// scanRegistration.cpp:247-262
+__device__ __forceinline__ OriRef ori_reference(const float* __restrict__ in, int stride_f, const int* st) {
+  OriRef r;
+  const float* p0 = in + (size_t)st[kStFirst] * stride_f;
+  const float* pN = in + (size_t)st[kStLast] * stride_f;
+  r.startOri = -atan2f(__ldg(p0 + 1), __ldg(p0));
+  float endOri = (float)((double)(-atan2f(__ldg(pN + 1), __ldg(pN))) + 2 * 3.14159265358979323846);
+  const double PI = 3.14159265358979323846;
+  if ((double)__fsub_rn(endOri, r.startOri) > 3 * PI)
+    endOri = (float)((double)endOri - 2 * PI);
+  else if ((double)__fsub_rn(endOri, r.startOri) < PI)
+    endOri = (float)((double)endOri + 2 * PI);
+  r.endOri = endOri;
+  return r;
+}
+
+// first-half unwrapping (scanRegistration.cpp:336-349)
+__device__ __forceinline__ float ori_first_half(float ori, float startOri) {
+  const double PI = 3.14159265358979323846;
+  if ((double)ori < (double)startOri - PI / 2)
+    ori = (float)((double)ori + 2 * PI);
+  else if ((double)ori > (double)startOri + PI * 3 / 2)
+    ori = (float)((double)ori - 2 * PI);
+  return ori;
+}
+
+// pass 2: the halfPassed latch = first valid point (input order) whose first-half azimuth exceeds startOri + pi
+__global__ void fe_star_kernel(const float* __restrict__ in, int n, int stride_f, const unsigned char* __restrict__ scanid,
+                               const float* __restrict__ ori_raw, int* st) {
+  if (st[kStLast] < 0) return;
+  const OriRef ref = ori_reference(in, stride_f, st);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cand = INT_MAX;
+  if (i < n && scanid[i] < kRings) {
+    const float o1 = ori_first_half(ori_raw[i], ref.startOri);
+    if ((double)__fsub_rn(o1, ref.startOri) > 3.14159265358979323846) cand = i;
+  }
+  cand = (int)__reduce_min_sync(0xffffffffu, (unsigned)cand);
+  if ((threadIdx.x & 31) == 0 && cand != INT_MAX) atomicMin(&st[kStStar], cand);
+}
+
+// pass 3: one block per ring, ordered compaction of the ring's points (stable in input order) straight into
+// the ring-concatenated cloud; intensity = scanID + 0.1 * relTime (scanRegistration.cpp:334-373)
+__global__ void __launch_bounds__(1024) fe_bucket_kernel(const float* __restrict__ in, int n, int stride_f,
+                                                         const unsigned char* __restrict__ scanid,
+                                                         const float* __restrict__ ori_raw, const int* __restrict__ st,
+                                                         float4* __restrict__ cloud, int* __restrict__ src_index) {
+  const int ring = blockIdx.x;
+  const int count = st[kStRing + ring];
+  if (count == 0) return;
+  int off = 0;
+  for (int r = 0; r < ring; ++r) off += st[kStRing + r];
+  const OriRef ref = ori_reference(in, stride_f, st);
+  const int star = st[kStStar];
+  __shared__ int warp_cnt[32];
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + threadIdx.x;
+    const bool mine = i < n && scanid[i] == ring;
+    const unsigned b = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) warp_cnt[warp] = __popc(b);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int cw = warp_cnt[w];
+      if (w < warp) wbase += cw;
+      tot += cw;
+    }
+    const int base = base_s;
+    if (mine) {
+      const int pos = off + base + wbase + __popc(b & ((1u << lane) - 1u));
+      const float* p = in + (size_t)i * stride_f;
+      float ori = ori_raw[i];
+      const double PI = 3.14159265358979323846;
+      if (i <= star) {
+        ori = ori_first_half(ori, ref.startOri);
+      } else {
+        ori = (float)((double)ori + 2 * PI);
+        if ((double)ori < (double)ref.endOri - PI * 3 / 2)
+          ori = (float)((double)ori + 2 * PI);
+        else if ((double)ori > (double)ref.endOri + PI / 2)
+          ori = (float)((double)ori - 2 * PI);
+      }
+      const float relTime = __fdiv_rn(__fsub_rn(ori, ref.startOri), __fsub_rn(ref.endOri, ref.startOri));
+      const float tag = (float)((double)ring + 0.1 * (double)relTime);
+      cloud[pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), tag);
+      src_index[pos] = i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = base + tot;
+    __syncthreads();
+  }
+}
+
+// pass 4: curvature over the concatenated cloud (scanRegistration.cpp:397-412), exact left-to-right float sums
+__global__ void fe_curvature_kernel(const float4* __restrict__ cloud, const int* __restrict__ st, float* __restrict__ curv,
+                                    int* __restrict__ label, unsigned char* __restrict__ picked) {
+  int N = 0;
+  for (int r = 0; r < kRings; ++r) N += st[kStRing + r];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float c = 0.f;
+  if (i >= 5 && i < N - 5) {
+    float4 p[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) p[k] = __ldg(cloud + i - 5 + k);
+    float d[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#define C_(k) (a == 0 ? p[k].x : (a == 1 ? p[k].y : p[k].z))
+      float s = __fadd_rn(C_(0), C_(1));
+      s = __fadd_rn(s, C_(2));
+      s = __fadd_rn(s, C_(3));
+      s = __fadd_rn(s, C_(4));
+      s = __fsub_rn(s, __fmul_rn(10.f, C_(5)));
+      s = __fadd_rn(s, C_(6));
+      s = __fadd_rn(s, C_(7));
+      s = __fadd_rn(s, C_(8));
+      s = __fadd_rn(s, C_(9));
+      s = __fadd_rn(s, C_(10));
+#undef C_
+      d[a] = s;
+    }
+    c = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+  }
+  curv[i] = c;
+  label[i] = 0;
+  picked[i] = 0;
+}
+
+__device__ __forceinline__ void ring_bounds(const int* st, int ring, int& S, int& E) {
+  int off = 0;
+  for (int r = 0; r < ring; ++r) off += st[kStRing + r];
+  S = off + 5;
+  E = off + st[kStRing + ring] - 6;
+}
+
+// in-block bitonic sort of P (power of two) 64-bit keys in shared memory
+__device__ __forceinline__ void bitonic_sort_smem(u64* keys, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        const int ixj = t ^ j;
+        if (ixj > t) {
+          const u64 a = keys[t], b = keys[ixj];
+          const bool up = (t & k) == 0;
+          if ((a > b) == up) {
+            keys[t] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// pass 5: one block per (ring, segment): sort the segment's points by (curvature, index)
+// (std::sort(cloudSortInd + sp, cloudSortInd + ep + 1, comp) with the tie order fixed by index)
+__global__ void __launch_bounds__(256) fe_sort_kernel(const float* __restrict__ curv, int* __restrict__ st,
+                                                      int* __restrict__ sort_ind) {
+  __shared__ u64 keys[kMaxSeg];
+  const int ring = blockIdx.x / 6, j = blockIdx.x % 6;
+  int S, E;
+  ring_bounds(st, ring, S, E);
+  if (E - S < 6) return;
+  const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+  const int L = ep - sp + 1;
+  if (L <= 0) return;
+  if (L > kMaxSeg) {
+    if (threadIdx.x == 0) atomicOr(&st[kStErr], 1);
+    return;
+  }
+  int P = 1;
+  while (P < L) P <<= 1;
+  for (int t = threadIdx.x; t < P; t += blockDim.x)
+    keys[t] = t < L ? (((u64)__float_as_uint(curv[sp + t]) << 32) | (uint32_t)(sp + t)) : ~0ull;
+  __syncthreads();
+  bitonic_sort_smem(keys, P);
+  for (int t = threadIdx.x; t < L; t += blockDim.x) sort_ind[sp + t] = (int)(uint32_t)keys[t];
+}
+
+// neighbour suppression of scanRegistration.cpp:481-504 by one warp: lanes 1..5 test the forward gaps,
+// lanes 6..10 the backward gaps; marking stops at the first gap^2 > 0.05
+__device__ __forceinline__ void mark_neighbours(const float4* __restrict__ cloud, unsigned char* picked, int ind, int lane) {
+  bool gap = false;
+  int a = 0;
+  if (lane >= 1 && lane <= 10) {
+    const int l = lane <= 5 ? lane : -(lane - 5);
+    a = ind + l;
+    const int b = l > 0 ? a - 1 : a + 1;
+    const float4 pa = __ldg(cloud + a), pb = __ldg(cloud + b);
+    const float dx = __fsub_rn(pa.x, pb.x), dy = __fsub_rn(pa.y, pb.y), dz = __fsub_rn(pa.z, pb.z);
+    const float g = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    gap = (double)g > 0.05;
+  }
+  const unsigned gm = __ballot_sync(0xffffffffu, gap);
+  const unsigned fwd = (gm >> 1) & 0x1Fu, bwd = (gm >> 6) & 0x1Fu;
+  const int nf = fwd ? __ffs(fwd) - 1 : 5, nb = bwd ? __ffs(bwd) - 1 : 5;  // neighbours marked on each side
+  if (lane == 0) picked[ind] = 1;
+  if (lane >= 1 && lane <= 5 && lane <= nf) picked[a] = 1;
+  if (lane >= 6 && lane <= 10 && lane - 5 <= nb) picked[a] = 1;
+  __syncwarp();
+}
+
+// pass 6: one warp per ring walks the six segments in order (the picks of one segment suppress neighbours that
+// may belong to the next, so segments stay sequential; rings are independent).  32 sorted entries are tested per
+// step, the first eligible one is taken, its neighbours are marked, and the test is repeated.
+__global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ cloud, const float* __restrict__ curv,
+                                                     const int* __restrict__ sort_ind, int* __restrict__ st,
+                                                     int* __restrict__ label, unsigned char* __restrict__ picked,
+                                                     int* __restrict__ ring_sharp, int* __restrict__ ring_lsharp,
+                                                     int* __restrict__ ring_flat) {
+  const int ring = blockIdx.x, lane = threadIdx.x;
+  int S, E;
+  ring_bounds(st, ring, S, E);
+  if (E - S < 6) return;
+  int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+  for (int j = 0; j < 6; ++j) {
+    const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
+    if (ep - sp + 1 > kMaxSeg) continue;  // flagged by the sort kernel
+    // ---- sharp / less sharp: descending curvature
+    int largest = 0;
+    int k = ep;
+    while (k >= sp) {
+      const int kk = k - lane;
+      int ind = -1;
+      bool elig = false, low = false;
+      if (kk >= sp) {
+        ind = sort_ind[kk];
+        const float c = curv[ind];
+        low = !((double)c > 0.1);
+        elig = !low && picked[ind] == 0;
+      }
+      const unsigned em = __ballot_sync(0xffffffffu, elig), lm = __ballot_sync(0xffffffffu, low);
+      const int fe = em ? __ffs(em) - 1 : 32, fl = lm ? __ffs(lm) - 1 : 32;
+      if (fe < fl) {  // an eligible point before the curvature drops to <= 0.1
+        const int pick = __shfl_sync(0xffffffffu, ind, fe);
+        ++largest;
+        if (largest <= 2) {
+          if (lane == 0) {
+            label[pick] = 2;
+            ring_sharp[ring * 12 + n_sharp] = pick;
+            ring_lsharp[ring * 120 + n_lsharp] = pick;
+          }
+          ++n_sharp, ++n_lsharp;
+        } else if (largest <= 20) {
+          if (lane == 0) {
+            label[pick] = 1;
+            ring_lsharp[ring * 120 + n_lsharp] = pick;
+          }
+          ++n_lsharp;
+        } else {
+          break;
+        }
+        mark_neighbours(cloud, picked, pick, lane);
+        k -= fe + 1;
+      } else if (fl < 32) {
+        break;  // sorted: everything further has curvature <= 0.1 and can never qualify
+      } else {
+        k -= 32;
+      }
+    }
+    // ---- flat: ascending curvature, four picks, the fourth does not suppress its neighbours
+    int smallest = 0;
+    k = sp;
+    while (k <= ep) {
+      const int kk = k + lane;
+      int ind = -1;
+      bool elig = false, high = false;
+      if (kk <= ep) {
+        ind = sort_ind[kk];
+        const float c = curv[ind];
+        high = !((double)c < 0.1);
+        elig = !high && picked[ind] == 0;
+      }
+      const unsigned em = __ballot_sync(0xffffffffu, elig), hm = __ballot_sync(0xffffffffu, high);
+      const int fe = em ? __ffs(em) - 1 : 32, fh = hm ? __ffs(hm) - 1 : 32;
+      if (fe < fh) {
+        const int pick = __shfl_sync(0xffffffffu, ind, fe);
+        if (lane == 0) {
+          label[pick] = -1;
+          ring_flat[ring * 24 + n_flat] = pick;
+        }
+        ++n_flat;
+        ++smallest;
+        if (smallest >= 4) break;
+        mark_neighbours(cloud, picked, pick, lane);
+        k += fe + 1;
+      } else if (fh < 32) {
+        break;
+      } else {
+        k += 32;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    st[kStSharp + ring] = n_sharp;
+    st[kStLSharp + ring] = n_lsharp;
+    st[kStFlat + ring] = n_flat;
+  }
+}
+
+// PCL 1.10 VoxelGrid over one contiguous set of points held by the block (PCL 1.10 applyFilter restated):
+// bounding box -> voxel index -> stable sort by (voxel, point order) -> float centroid per voxel in that order.
+// pts: m points (global), out: centroids in ascending voxel index; returns the number of voxels (block-uniform).
+// keys: shared scratch of P >= m (power of two) entries.
+__device__ int voxelgrid_block(const float4* __restrict__ pts, int m, float leaf, u64* keys, int P, float4* __restrict__ out,
+                               int* err) {
+  __shared__ float s_min[3], s_max[3];
+  __shared__ int s_count, s_bad;
+  if (threadIdx.x < 3) s_min[threadIdx.x] = __int_as_float(0x7f800000), s_max[threadIdx.x] = __int_as_float(0xff800000);
+  if (threadIdx.x == 0) s_count = 0, s_bad = 0;
+  __syncthreads();
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    const float4 p = pts[t];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      mn[0] = fminf(mn[0], p.x), mn[1] = fminf(mn[1], p.y), mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x), mx[1] = fmaxf(mx[1], p.y), mx[2] = fmaxf(mx[2], p.z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      // float atomic min/max through the ordered-int trick (values finite or +-inf)
+      int* pmn = reinterpret_cast<int*>(&s_min[a]);
+      int* pmx = reinterpret_cast<int*>(&s_max[a]);
+      if (mn[a] >= 0.f) atomicMin(pmn, __float_as_int(mn[a])); else atomicMax(reinterpret_cast<unsigned*>(pmn), __float_as_uint(mn[a]));
+      if (mx[a] >= 0.f) atomicMax(pmx, __float_as_int(mx[a])); else atomicMin(reinterpret_cast<unsigned*>(pmx), __float_as_uint(mx[a]));
+    }
+  }
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = __float2int_rd(__fmul_rn(s_min[a], inv));
+    div_b[a] = __float2int_rd(__fmul_rn(s_max[a], inv)) - min_b[a] + 1;
+  }
+  const long long mul1 = div_b[0], mul2 = (long long)div_b[0] * div_b[1];
+  if (mul2 * div_b[2] >= (1ll << 31)) {  // pcl: "Leaf size is too small for the input dataset"
+    if (threadIdx.x == 0) atomicOr(err, 2);
+    return 0;
+  }
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    u64 key = ~0ull;
+    if (t < m) {
+      const float4 p = pts[t];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)min_b[0]));
+        const int i1 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)min_b[1]));
+        const int i2 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)min_b[2]));
+        const long long idx = i0 + i1 * mul1 + i2 * mul2;
+        key = ((u64)idx << 24) | (uint32_t)t;  // (voxel, point order): stable by construction
+      }
+    }
+    keys[t] = key;
+  }
+  __syncthreads();
+  bitonic_sort_smem(keys, P);
+  // run heads -> output slot = number of heads before; each head accumulates its run in order (float, like
+  // pcl::CentroidPoint) and divides by the count
+  for (int t0 = 0; t0 < P; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    bool head = false;
+    if (t < P && keys[t] != ~0ull) head = t == 0 || (keys[t] >> 24) != (keys[t - 1] >> 24);
+    // block-wide exclusive count of heads in this chunk
+    const unsigned b = __ballot_sync(0xffffffffu, head);
+    __shared__ int wc[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(b);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {
+      if (w < warp) wbase += wc[w];
+      tot += wc[w];
+    }
+    const int base = s_count;
+    if (head) {
+      const int slot = base + wbase + __popc(b & ((1u << lane) - 1u));
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int cnt = 0;
+      const u64 vox = keys[t] >> 24;
+      for (int e = t; e < P && keys[e] != ~0ull && (keys[e] >> 24) == vox; ++e) {
+        const float4 p = pts[(int)(keys[e] & 0xFFFFFF)];
+        sx = __fadd_rn(sx, p.x), sy = __fadd_rn(sy, p.y), sz = __fadd_rn(sz, p.z), si = __fadd_rn(si, p.w);
+        ++cnt;
+      }
+      const float c = (float)cnt;
+      out[slot] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_count = base + tot;
+    __syncthreads();
+  }
+  return s_count;
+}
+
+// pass 7: one block per ring: collect the ring's less-flat points (label <= 0 inside the six segments, in index
+// order) and run VoxelGrid(0.2) on them (scanRegistration.cpp:570-589)
+__global__ void __launch_bounds__(256) fe_lessflat_kernel(const float4* __restrict__ cloud, const int* __restrict__ label,
+                                                          int* __restrict__ st, float4* __restrict__ ring_pts,
+                                                          float4* __restrict__ ring_out, int ring_cap, float leaf) {
+  __shared__ u64 keys[kMaxRingLF];
+  __shared__ int s_m;
+  const int ring = blockIdx.x;
+  int S, E;
+  ring_bounds(st, ring, S, E);
+  if (E - S < 6) return;
+  // the six segments tile [S, S + (E-S)*6/6 - 1] = [S, E-1] contiguously
+  const int lo = S, hi = S + (E - S) * 6 / 6 - 1;
+  if (threadIdx.x == 0) s_m = 0;
+  __syncthreads();
+  float4* mine = ring_pts + (size_t)ring * ring_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int wc[8];
+  for (int c0 = lo; c0 <= hi; c0 += blockDim.x) {
+    const int k = c0 + threadIdx.x;
+    const bool take = k <= hi && label[k] <= 0;
+    const unsigned b = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) wc[warp] = __popc(b);
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) wbase += wc[w];
+      tot += wc[w];
+    }
+    const int base = s_m;
+    if (take) {
+      const int pos = base + wbase + __popc(b & ((1u << lane) - 1u));
+      if (pos < ring_cap) mine[pos] = cloud[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_m = base + tot;
+    __syncthreads();
+  }
+  const int m = s_m;
+  if (m > kMaxRingLF || m > ring_cap) {
+    if (threadIdx.x == 0) atomicOr(&st[kStErr], 4);
+    return;
+  }
+  int P = 1;
+  while (P < m) P <<= 1;
+  const int nvox = m > 0 ? voxelgrid_block(mine, m, leaf, keys, P, ring_out + (size_t)ring * ring_cap, &st[kStErr]) : 0;
+  if (threadIdx.x == 0) st[kStLFlat + ring] = nvox;
+}
+
+// pass 8: concatenate the per-ring outputs in ring order (the reference appends ring by ring)
+__global__ void fe_compact_kernel(const int* __restrict__ st, const int* __restrict__ ring_sharp,
+                                  const int* __restrict__ ring_lsharp, const int* __restrict__ ring_flat,
+                                  const float4* __restrict__ ring_out, int ring_cap, int* __restrict__ sharp,
+                                  int* __restrict__ lsharp, int* __restrict__ flat, float4* __restrict__ lflat,
+                                  int* __restrict__ counts /* n_cloud, n_sharp, n_lsharp, n_flat, n_lflat */) {
+  const int ring = blockIdx.x;
+  int o_s = 0, o_ls = 0, o_f = 0, o_lf = 0;
+  for (int r = 0; r < ring; ++r) {
+    o_s += st[kStSharp + r], o_ls += st[kStLSharp + r], o_f += st[kStFlat + r], o_lf += st[kStLFlat + r];
+  }
+  const int ns = st[kStSharp + ring], nls = st[kStLSharp + ring], nf = st[kStFlat + ring], nlf = st[kStLFlat + ring];
+  for (int t = threadIdx.x; t < ns; t += blockDim.x) sharp[o_s + t] = ring_sharp[ring * 12 + t];
+  for (int t = threadIdx.x; t < nls; t += blockDim.x) lsharp[o_ls + t] = ring_lsharp[ring * 120 + t];
+  for (int t = threadIdx.x; t < nf; t += blockDim.x) flat[o_f + t] = ring_flat[ring * 24 + t];
+  for (int t = threadIdx.x; t < nlf; t += blockDim.x) lflat[o_lf + t] = ring_out[(size_t)ring * ring_cap + t];
+  if (ring == kRings - 1 && threadIdx.x == 0) {
+    int N = 0;
+    for (int r = 0; r < kRings; ++r) N += st[kStRing + r];
+    counts[0] = N;
+    counts[1] = o_s + ns, counts[2] = o_ls + nls, counts[3] = o_f + nf, counts[4] = o_lf + nlf;
+    counts[5] = st[kStErr];
+  }
+}
+
+// gather selected points of a cloud by index (less-sharp / sharp / flat clouds)
+__global__ void gather_points_kernel(const float4* __restrict__ cloud, const int* __restrict__ idx, const int* __restrict__ n_ptr,
+                                     int slot, float4* __restrict__ out) {
+  const int n = n_ptr[slot];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = cloud[idx[i]];
+}
+
+// stand-alone VoxelGrid of one cloud by one block (n <= kVoxelMax); n may come from device memory (n_ptr)
+constexpr int kVoxelMax = 16384;
+__global__ void __launch_bounds__(1024) voxelgrid_kernel(const float* __restrict__ in, int n_host, const int* __restrict__ n_ptr,
+                                                         int n_slot, int stride_f, int ioff, float leaf,
+                                                         float4* __restrict__ packed, float4* __restrict__ out,
+                                                         int* __restrict__ n_out, int* err) {
+  extern __shared__ u64 dyn_keys[];
+  const int n = n_ptr ? n_ptr[n_slot] : n_host;
+  if (n > kVoxelMax) {
+    if (threadIdx.x == 0) atomicOr(err, 8), *n_out = 0;
+    return;
+  }
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const float* p = in + (size_t)t * stride_f;
+    packed[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + ioff));
+  }
+  __syncthreads();
+  int P = 1;
+  while (P < n) P <<= 1;
+  const int nvox = n > 0 ? voxelgrid_block(packed, n, leaf, dyn_keys, P, out, err) : 0;
+  if (threadIdx.x == 0) *n_out = nvox;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int Ctx::project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
+                     float* d_track) {
+  if (n <= 0) return ILSM_OK;
+  const int stride_f = stride_bytes / 4, ioff = stride_bytes >= 32 ? 4 : 3;
+  const int threads = 256, blocks = ((n + 3) / 4 + threads - 1) / threads;
+  project_kernel<<<blocks, threads, 0, stream>>>(d_cloud, n, stride_f, ioff, d_range, d_inten,
+                                                 reinterpret_cast<float4*>(d_track));
+  count_launches(1);
+  return check_launch("project");
+}
+
+int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_range) {
+  int rc;
+  FeBufs& f = fe;
+  const int ring_cap = n < kMaxRingLF ? (n > 0 ? n : 1) : kMaxRingLF;
+  if ((rc = f.scanid.reserve(n + 4)) || (rc = f.ori.reserve(n + 4)) || (rc = f.stats.reserve(kStInts + 8)) ||
+      (rc = f.cloud.reserve(n + 4)) || (rc = f.src_index.reserve(n + 4)) || (rc = f.curv.reserve(n + 4)) ||
+      (rc = f.label.reserve(n + 4)) || (rc = f.picked.reserve(n + 4)) || (rc = f.sort_ind.reserve(n + 4)) ||
+      (rc = f.ring_sharp.reserve(kRings * 12)) || (rc = f.ring_lsharp.reserve(kRings * 120)) ||
+      (rc = f.ring_flat.reserve(kRings * 24)) || (rc = f.ring_pts.reserve((size_t)kRings * ring_cap)) ||
+      (rc = f.ring_out.reserve((size_t)kRings * ring_cap)) || (rc = f.sharp.reserve(kRings * 12)) ||
+      (rc = f.lsharp.reserve(kRings * 120)) || (rc = f.flat.reserve(kRings * 24)) || (rc = f.lflat.reserve(n + 4)) ||
+      (rc = f.counts.reserve(8)))
+    return rc;
+  f.n_in = n;
+  f.ring_cap = ring_cap;
+  const int stride_f = stride_bytes / 4;
+  const int T = 256, B = (n + T - 1) / T;
+  fe_init_kernel<<<1, 352, 0, stream>>>(f.stats.p);
+  if (n > 0) {
+    fe_tag_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, min_range * min_range, f.scanid.p, f.ori.p, f.stats.p);
+    fe_star_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p);
+    fe_bucket_kernel<<<kRings, 1024, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.cloud.p,
+                                                  f.src_index.p);
+    fe_curvature_kernel<<<B, T, 0, stream>>>(f.cloud.p, f.stats.p, f.curv.p, f.label.p, f.picked.p);
+    fe_sort_kernel<<<kRings * 6, 256, 0, stream>>>(f.curv.p, f.stats.p, f.sort_ind.p);
+    fe_pick_kernel<<<kRings, 32, 0, stream>>>(f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p,
+                                              f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p);
+    fe_lessflat_kernel<<<kRings, 256, 0, stream>>>(f.cloud.p, f.label.p, f.stats.p, f.ring_pts.p, f.ring_out.p, ring_cap,
+                                                   0.2f);
+    count_launches(7);
+  }
+  fe_compact_kernel<<<kRings, 128, 0, stream>>>(f.stats.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p, f.ring_out.p,
+                                                ring_cap, f.sharp.p, f.lsharp.p, f.flat.p, f.lflat.p, f.counts.p);
+  count_launches(2);
+  return check_launch("extract_features");
+}
+
+int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
+                       float4* d_out, int* d_n_out) {
+  int rc;
+  const int cap = d_n ? kVoxelMax : n;
+  if (!d_n && n > kVoxelMax) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: more than 16384 points per call");
+  if ((rc = fe.vox_packed.reserve(cap + 4)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
+  const size_t smem = (size_t)kVoxelMax * sizeof(u64);
+  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int P = 1;
+  while (P < cap) P <<= 1;
+  voxelgrid_kernel<<<1, 1024, (size_t)P * sizeof(u64), stream>>>(d_in, n, d_n, n_slot, stride_bytes / 4, ioff, leaf,
+                                                                  fe.vox_packed.p, d_out, d_n_out, fe.stats.p + kStErr);
+  count_launches(1);
+  return check_launch("voxelgrid");
+}
+
+int Ctx::gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out) {
+  if (max_n <= 0) return ILSM_OK;
+  gather_points_kernel<<<(max_n + 255) / 256, 256, 0, stream>>>(d_cloud, d_idx, d_counts, slot, d_out);
+  count_launches(1);
+  return check_launch("gather");
+}
+
+}  // namespace ilsm

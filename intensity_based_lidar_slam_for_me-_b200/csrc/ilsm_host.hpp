@@ -135,6 +135,20 @@ struct FactorBufs {
   int n = 0, nc = 0;
 };
 
+// Front-end scratch and outputs (device-resident between the front end and the registration).
+struct FeBufs {
+  DevBuf<unsigned char> scanid, picked;
+  DevBuf<float> ori, curv;
+  DevBuf<int> stats, src_index, label, sort_ind, ring_sharp, ring_lsharp, ring_flat, sharp, lsharp, flat, counts;
+  DevBuf<float4> cloud, ring_pts, ring_out, lflat, vox_packed;
+  DevBuf<float> raw;                 // staged caller frame
+  DevBuf<unsigned char> img;         // projection outputs (range | intensity)
+  DevBuf<float4> track;
+  DevBuf<float4> vox_out;
+  DevBuf<int> vox_n;
+  int n_in = 0, ring_cap = 0;
+};
+
 struct Ctx {
   int device = 0;
   int sm_count = 148;
@@ -147,6 +161,7 @@ struct Ctx {
   DevBuf<float> out_d2;
   PinnedBuf<unsigned char> pinned;
   FactorBufs fac;
+  FeBufs fe;
   size_t partial_blocks = 0;
 
   int init(int dev);
@@ -155,6 +170,13 @@ struct Ctx {
   int associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                     const ilsm_reg_opts& o, bool want_knn);
   int solve_launch(int max_iter, double huber_a, int pass);  // the whole LM solve, one cluster launch
+  // front end (frontend.cu)
+  int project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
+                  float* d_track);
+  int features_dev(const float* d_in, int n, int stride_bytes, float min_range);
+  int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
+                    float4* d_out, int* d_n_out);
+  int gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out);
   int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                    const ilsm_reg_opts& o);
 };

@@ -186,3 +186,57 @@ def register_aloam(map_corner, map_surf, corner, surf, qt, outer=2, max_iter=4):
     n = lib().orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), _stride(mc), _p(c), len(c), _p(s), len(s),
                                  _stride(c) if len(c) else _stride(s), _p(x), outer, max_iter, sums, _p(nf))
     return x, list(sums)[:n], nf
+
+
+# ------------------------------------------------------------------------------------------------
+# front end
+# ------------------------------------------------------------------------------------------------
+class FeatureCounts(C.Structure):
+    _fields_ = [("n_cloud", C.c_int32), ("n_sharp", C.c_int32), ("n_less_sharp", C.c_int32), ("n_flat", C.c_int32),
+                ("n_less_flat", C.c_int32), ("ring_start", C.c_int32 * 64), ("ring_end", C.c_int32 * 64)]
+
+
+def _ioff(a):
+    return 4 if a.shape[1] >= 8 else 3
+
+
+def project(cloud, H=64, W=1024):
+    """ImageHandler::cloud_handler: (image_range u8, image_intensity u8, cloud_track (H*W,4) f32)."""
+    c = _f32(cloud)
+    assert len(c) == H * W
+    rng = np.zeros((H, W), np.uint8)
+    inten = np.zeros((H, W), np.uint8)
+    track = np.zeros((H * W, 4), np.float32)
+    lib().orc_project(_p(c), H, W, c.strides[0], _ioff(c), _p(rng), _p(inten), _p(track))
+    return rng, inten, track
+
+
+def voxelgrid(cloud, leaf):
+    """pcl::VoxelGrid (PCL 1.10 restated): centroids (m,4) xyzi in ascending voxel index."""
+    c = _f32(cloud)
+    out = np.zeros((max(len(c), 1), 4), np.float32)
+    if len(c) == 0:
+        return out[:0]
+    m = lib().orc_voxelgrid(_p(c), len(c), c.strides[0], _ioff(c), C.c_float(leaf), _p(out))
+    return out[:m].copy()
+
+
+def extract_features(cloud, min_range=0.3):
+    """scanRegistration.cpp laserCloudHandler (64-ring path).  Returns a dict of arrays."""
+    c = _f32(cloud)
+    n = len(c)
+    cl = np.zeros((n, 4), np.float32)
+    curv = np.zeros(n, np.float32)
+    label = np.zeros(n, np.int32)
+    src = np.zeros(n, np.int32)
+    sharp = np.zeros(n, np.int32)
+    lsharp = np.zeros(n, np.int32)
+    flat = np.zeros(n, np.int32)
+    lflat = np.zeros((n, 4), np.float32)
+    cnt = FeatureCounts()
+    lib().orc_extract_features(_p(c), n, c.strides[0], C.c_float(min_range), _p(cl), _p(curv), _p(label), _p(src),
+                               _p(sharp), _p(lsharp), _p(flat), _p(lflat), C.byref(cnt))
+    N = cnt.n_cloud
+    return dict(cloud=cl[:N], curvature=curv[:N], label=label[:N], src_index=src[:N], sharp_idx=sharp[:cnt.n_sharp],
+                less_sharp_idx=lsharp[:cnt.n_less_sharp], flat_idx=flat[:cnt.n_flat], less_flat=lflat[:cnt.n_less_flat],
+                ring_start=np.array(cnt.ring_start[:]), ring_end=np.array(cnt.ring_end[:]))
