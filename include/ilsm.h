@@ -237,6 +237,37 @@ ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int 
 ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
                             int* n_out);
 
+/* ------------------------------------------------------ K5: ScanContext loop-closure candidate scoring ---- */
+typedef struct ilsm_sc ilsm_sc; /* keyframe descriptor database (one shard when split across ranks) */
+
+ILSM_API int ilsm_sc_create(ilsm_ctx* ctx, ilsm_sc** out);
+ILSM_API void ilsm_sc_destroy(ilsm_sc* sc);
+ILSM_API int ilsm_sc_size(const ilsm_sc* sc);
+
+/* Points -> 20x60 polar max-height descriptor, row-major float (ring, sector); empty bins 0.
+ * Replaces: SCManager::makeScancontext  Scancontext.cpp:160-204 */
+ILSM_API int ilsm_sc_make(ilsm_sc* sc, const float* xyz, int n, int stride_bytes, float* desc_20x60);
+
+/* Append `count` descriptors (ring/sector keys are recomputed on the fly when scoring).
+ * Replaces: the push_backs of makeAndSaveScancontextAndKeys  Scancontext.cpp:237-251 */
+ILSM_API int ilsm_sc_add(ilsm_sc* sc, const float* desc_20x60, int count);
+ILSM_API int ilsm_sc_add_dev(ilsm_sc* sc, const float* d_desc_20x60, int count);
+
+/* Score the query against database entries [0, n_search) (n_search < 0: all; the caller excludes the most recent
+ * NUM_EXCLUDE_RECENT = 50 entries like Scancontext.cpp:270-275) with distanceBtnScanContext -- sector-key alignment
+ * over 60 shifts, column-cosine distance on the 7 shifts around it, first minimum wins -- and return the k <= 16
+ * best by (distance, id).  id_offset is added to the returned ids (global id of this shard's first entry).
+ * Replaces: Scancontext.cpp:79-157 and the candidate loop :299-312 (scored over every entry, a superset of the
+ *           reference's 10 ring-key candidates). */
+ILSM_API int ilsm_sc_query_topk(ilsm_sc* sc, const float* desc_20x60, int n_search, int id_offset, int k, double* dist,
+                                int32_t* id, int32_t* shift);
+ILSM_API int ilsm_sc_query_topk_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_search, int id_offset, int k,
+                                    double* d_dist, int32_t* d_id, int32_t* d_shift);
+
+/* Host-side deterministic merge of gathered per-shard top-k lists (n_entries = shards * k). */
+ILSM_API int ilsm_sc_merge_topk(const double* dist, const int32_t* id, const int32_t* shift, int n_entries, int k,
+                                double* out_dist, int32_t* out_id, int32_t* out_shift);
+
 #ifdef __cplusplus
 }
 #endif

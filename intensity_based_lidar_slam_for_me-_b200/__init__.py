@@ -4,8 +4,9 @@ This package holds only what the path needs: csrc/ (hand-written sm_100a kernels
 marshalling + host-side mirror of the reference call sites) and synth.py (seeded synthetic inputs).
 """
 from . import _build, synth  # noqa: F401
+from .sharding import allgather_topk, shard_range  # noqa: F401
 from .binding import (CONVERGENCE, FAILURE, NO_CONVERGENCE, Context, IlsmError, LocalMap, RegOpts, RegReport,  # noqa: F401
-                      SolveSummary, default_opts, launch_count, load_library, FACTOR_DTYPE)
+                      SolveSummary, ScanContextDb, default_opts, merge_topk, launch_count, load_library, FACTOR_DTYPE)
 
-__all__ = ["Context", "LocalMap", "RegOpts", "RegReport", "SolveSummary", "default_opts", "load_library", "IlsmError",
+__all__ = ["Context", "LocalMap", "RegOpts", "RegReport", "SolveSummary", "default_opts", "load_library", "ScanContextDb", "merge_topk", "IlsmError",
            "synth", "CONVERGENCE", "NO_CONVERGENCE", "FAILURE", "FACTOR_DTYPE"]

@@ -91,6 +91,15 @@ def load_library(path: str | None = None):
         "ilsm_project_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_extract_features": (i32, [vp, vp, i32, i32, f32, C.POINTER(Features)]),
         "ilsm_voxelgrid": (i32, [vp, vp, i32, i32, f32, vp, C.POINTER(i32)]),
+        "ilsm_sc_create": (i32, [vp, C.POINTER(vp)]),
+        "ilsm_sc_destroy": (None, [vp]),
+        "ilsm_sc_size": (i32, [vp]),
+        "ilsm_sc_make": (i32, [vp, vp, i32, i32, vp]),
+        "ilsm_sc_add": (i32, [vp, vp, i32]),
+        "ilsm_sc_add_dev": (i32, [vp, vp, i32]),
+        "ilsm_sc_query_topk": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "ilsm_sc_query_topk_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "ilsm_sc_merge_topk": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
@@ -314,3 +323,64 @@ class LocalMap:
 
     def knn_dev(self, d_q_ptr: int, nq: int, stride: int, k: int, max_dist: float, d_idx_ptr: int, d_d2_ptr: int):
         _check(self._lib.ilsm_knn_dev(self._h, d_q_ptr, nq, stride, k, max_dist, d_idx_ptr, d_d2_ptr))
+
+
+def merge_topk(dist, ids, shifts, k):
+    """Deterministic merge of gathered per-shard top-k lists (host code of the library, no GPU needed)."""
+    d = np.ascontiguousarray(dist, np.float64).ravel()
+    i = np.ascontiguousarray(ids, np.int32).ravel()
+    s = np.ascontiguousarray(shifts, np.int32).ravel()
+    od, oi, os_ = np.zeros(k), np.zeros(k, np.int32), np.zeros(k, np.int32)
+    _check(load_library().ilsm_sc_merge_topk(_ptr(d), _ptr(i), _ptr(s), len(d), k, _ptr(od), _ptr(oi), _ptr(os_)))
+    return od, oi, os_
+
+
+class ScanContextDb:
+    """ilsm_sc: mirrors SCManager (makeScancontext / makeAndSaveScancontextAndKeys / detectLoopClosureID candidate
+    scoring).  One instance holds one shard of the keyframe database."""
+    NUM_EXCLUDE_RECENT = 50  # Scancontext.h:86
+    SC_DIST_THRES = 0.13     # Scancontext.h:91
+
+    def __init__(self, ctx: Context):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_sc_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_sc_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.ilsm_sc_size(self._h))
+
+    def make_scancontext(self, points):
+        a, n, stride = _cloud(points)
+        d = np.empty((20, 60), np.float32)
+        _check(self._lib.ilsm_sc_make(self._h, _ptr(a), n, stride, _ptr(d)))
+        return d
+
+    def add(self, descs):
+        d = np.ascontiguousarray(descs, np.float32).reshape(-1, 1200)
+        _check(self._lib.ilsm_sc_add(self._h, _ptr(d), len(d)))
+
+    def add_dev(self, d_ptr, count):
+        _check(self._lib.ilsm_sc_add_dev(self._h, d_ptr, count))
+
+    def query_topk(self, desc, k=10, n_search=-1, id_offset=0):
+        q = np.ascontiguousarray(desc, np.float32).reshape(1200)
+        dist, ids, sh = np.zeros(k), np.zeros(k, np.int32), np.zeros(k, np.int32)
+        _check(self._lib.ilsm_sc_query_topk(self._h, _ptr(q), n_search, id_offset, k, _ptr(dist), _ptr(ids), _ptr(sh)))
+        return dist, ids, sh
+
+    def query_topk_dev(self, d_desc_ptr, k, n_search, id_offset, d_dist_ptr, d_id_ptr, d_shift_ptr):
+        _check(self._lib.ilsm_sc_query_topk_dev(self._h, d_desc_ptr, n_search, id_offset, k, d_dist_ptr, d_id_ptr,
+                                                d_shift_ptr))

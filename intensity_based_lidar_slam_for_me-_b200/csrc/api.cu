@@ -135,6 +135,9 @@ struct ilsm_ctx {
 struct ilsm_map {
   Map m;
 };
+struct ilsm_sc {
+  ScDb d;
+};
 
 extern "C" {
 
@@ -517,6 +520,124 @@ ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_
   if (pin[0] > 0) {
     ILSM_CUDA(cudaMemcpyAsync(out_xyzi, c.fe.vox_out.p, (size_t)pin[0] * 16, cudaMemcpyDeviceToHost, c.stream));
     ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  return ILSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ ScanContext
+ILSM_API int ilsm_sc_create(ilsm_ctx* ctx, ilsm_sc** out) {
+  if (!ctx || !out) return fail(ILSM_ERR_INVALID_ARG, "sc_create: null argument");
+  ilsm_sc* h = new (std::nothrow) ilsm_sc();
+  if (!h) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  h->d.ctx = &ctx->c;
+  *out = h;
+  return ILSM_OK;
+}
+
+ILSM_API void ilsm_sc_destroy(ilsm_sc* sc) {
+  if (!sc) return;
+  {
+    std::lock_guard<std::mutex> lk(sc->d.ctx->mu);
+    cudaSetDevice(sc->d.ctx->device);
+    cudaStreamSynchronize(sc->d.ctx->stream);
+    ScDb& d = sc->d;
+    d.db.release(), d.bins.release(), d.query.release(), d.dist.release(), d.out_dist.release(), d.shift.release();
+    d.out_id.release(), d.out_shift.release(), d.stage.release();
+  }
+  delete sc;
+}
+
+ILSM_API int ilsm_sc_size(const ilsm_sc* sc) { return sc ? sc->d.count : 0; }
+
+ILSM_API int ilsm_sc_make(ilsm_sc* sc, const float* xyz, int n, int stride_bytes, float* desc_20x60) {
+  if (!sc || !desc_20x60 || (n > 0 && !xyz)) return fail(ILSM_ERR_INVALID_ARG, "sc_make: null argument");
+  if (n < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "sc_make: bad n/stride");
+  ScDb& d = sc->d;
+  Ctx& c = *d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const size_t words = (size_t)n * stride_bytes / 4;
+  int rc;
+  if ((rc = d.stage.reserve(words + 1200 + 8))) return rc;
+  float* d_desc = d.stage.p;
+  float* d_pts = d.stage.p + 1200;
+  if (n) ILSM_CUDA(cudaMemcpyAsync(d_pts, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = d.make_dev(d_pts, n, stride_bytes, d_desc))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(desc_20x60, d_desc, 1200 * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_sc_add(ilsm_sc* sc, const float* desc_20x60, int count) {
+  if (!sc || (count > 0 && !desc_20x60) || count < 0) return fail(ILSM_ERR_INVALID_ARG, "sc_add: bad argument");
+  Ctx& c = *sc->d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  int rc = sc->d.append_dev(desc_20x60, count, true);
+  if (rc) return rc;
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_sc_add_dev(ilsm_sc* sc, const float* d_desc_20x60, int count) {
+  if (!sc || (count > 0 && !d_desc_20x60) || count < 0) return fail(ILSM_ERR_INVALID_ARG, "sc_add_dev: bad argument");
+  Ctx& c = *sc->d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return sc->d.append_dev(d_desc_20x60, count, false);
+}
+
+ILSM_API int ilsm_sc_query_topk_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_search, int id_offset, int k,
+                                    double* d_dist, int32_t* d_id, int32_t* d_shift) {
+  if (!sc || !d_desc_20x60 || !d_dist || !d_id || !d_shift) return fail(ILSM_ERR_INVALID_ARG, "sc_query_dev: null argument");
+  Ctx& c = *sc->d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (n_search < 0) n_search = sc->d.count;
+  return sc->d.query_dev(d_desc_20x60, n_search, id_offset, k, d_dist, d_id, d_shift);
+}
+
+ILSM_API int ilsm_sc_query_topk(ilsm_sc* sc, const float* desc_20x60, int n_search, int id_offset, int k, double* dist,
+                                int32_t* id, int32_t* shift) {
+  if (!sc || !desc_20x60 || !dist || !id || !shift) return fail(ILSM_ERR_INVALID_ARG, "sc_query: null argument");
+  ScDb& d = sc->d;
+  Ctx& c = *d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (n_search < 0) n_search = d.count;
+  int rc;
+  if ((rc = d.stage.reserve(1200 + 8)) || (rc = d.out_dist.reserve(16)) || (rc = d.out_id.reserve(16)) ||
+      (rc = d.out_shift.reserve(16)))
+    return rc;
+  ILSM_CUDA(cudaMemcpyAsync(d.stage.p, desc_20x60, 1200 * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  if ((rc = d.query_dev(d.stage.p, n_search, id_offset, k, d.out_dist.p, d.out_id.p, d.out_shift.p))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(dist, d.out_dist.p, k * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(id, d.out_id.p, k * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(shift, d.out_shift.p, k * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
+// Deterministic merge of per-shard top-k lists (what every rank does after the all-gather): ascending
+// (distance, id); entries with id < 0 are padding.  Pure host code, no device work.
+ILSM_API int ilsm_sc_merge_topk(const double* dist, const int32_t* id, const int32_t* shift, int n_entries, int k,
+                                double* out_dist, int32_t* out_id, int32_t* out_shift) {
+  if (!dist || !id || !shift || !out_dist || !out_id || !out_shift || n_entries < 0 || k < 1)
+    return fail(ILSM_ERR_INVALID_ARG, "sc_merge: bad argument");
+  for (int j = 0; j < k; ++j) {
+    int best = -1;
+    for (int i = 0; i < n_entries; ++i) {
+      if (id[i] < 0) continue;
+      bool taken = false;
+      for (int t = 0; t < j; ++t) taken = taken || out_id[t] == id[i];
+      if (taken) continue;
+      if (best < 0 || dist[i] < dist[best] || (dist[i] == dist[best] && id[i] < id[best])) best = i;
+    }
+    if (best < 0) {
+      out_dist[j] = 1.0 / 0.0, out_id[j] = -1, out_shift[j] = 0;
+    } else {
+      out_dist[j] = dist[best], out_id[j] = id[best], out_shift[j] = shift[best];
+    }
   }
   return ILSM_OK;
 }

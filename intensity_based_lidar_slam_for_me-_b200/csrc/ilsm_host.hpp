@@ -181,4 +181,20 @@ struct Ctx {
                    const ilsm_reg_opts& o);
 };
 
+// ScanContext keyframe database (one shard when the database is split across ranks).
+struct ScQuery;
+struct ScDb {
+  Ctx* ctx = nullptr;
+  int count = 0;
+  DevBuf<float> db;        // [count][20][60] float32
+  DevBuf<int> bins;        // makeScancontext scratch
+  DevBuf<ScQuery> query;
+  DevBuf<double> dist, out_dist;
+  DevBuf<int> shift, out_id, out_shift;
+  DevBuf<float> stage;     // staged caller descriptors / points
+  int append_dev(const float* desc, int n_add, bool from_host);
+  int make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc);
+  int query_dev(const float* d_qdesc, int n_search, int id_offset, int k, double* d_dist, int* d_id, int* d_shift);
+};
+
 }  // namespace ilsm

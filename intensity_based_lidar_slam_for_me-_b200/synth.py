@@ -281,3 +281,32 @@ def config1(n_map=100_000, seed_shift=0):
     q0, t0 = perturb_pose(q, t, SEED_GUESS + seed_shift)
     return dict(scene=scene, map_corner=map_corner, map_surf=map_surf, cloud=cloud, tag=tag, corner=corner,
                 surf=surf, q_true=q, t_true=t, q0=q0, t0=t0)
+
+
+# ------------------------------------------------------------------------------------------------
+# ScanContext database
+# ------------------------------------------------------------------------------------------------
+SEED_SC = 0x5EED0200
+
+
+def sc_database(n, seed=SEED_SC):
+    """n synthetic 20x60 descriptors: each bin empty (0) w.p. 0.4, else a max-height value U(0,6) m; float32."""
+    rng = np.random.default_rng(seed)
+    d = rng.uniform(0.0, 6.0, size=(n, 20, 60)).astype(np.float32)
+    d[rng.random((n, 20, 60)) < 0.4] = 0.0
+    return d
+
+
+def sc_queries(db, n_q, seed=SEED_SC + 1, noise=0.05):
+    """Queries = database entries re-rendered with a yaw shift of U{0..59} sectors plus N(0, noise) on the occupied
+    bins, so the true id and shift are known.  Returns (queries, true ids, true shifts)."""
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(0, len(db), n_q)
+    shifts = rng.integers(0, 60, n_q)
+    q = np.empty((n_q, 20, 60), np.float32)
+    for j, (i, s) in enumerate(zip(ids, shifts)):
+        d = np.roll(db[i], int(s), axis=1).astype(np.float32)  # == circshift(candidate, s) (Scancontext.cpp:44-68)
+        occ = d != 0
+        d = d + (rng.normal(0.0, noise, d.shape).astype(np.float32) * occ)
+        q[j] = d
+    return q, ids.astype(np.int32), shifts.astype(np.int32)

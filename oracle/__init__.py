@@ -240,3 +240,62 @@ def extract_features(cloud, min_range=0.3):
     return dict(cloud=cl[:N], curvature=curv[:N], label=label[:N], src_index=src[:N], sharp_idx=sharp[:cnt.n_sharp],
                 less_sharp_idx=lsharp[:cnt.n_less_sharp], flat_idx=flat[:cnt.n_flat], less_flat=lflat[:cnt.n_less_flat],
                 ring_start=np.array(cnt.ring_start[:]), ring_end=np.array(cnt.ring_end[:]))
+
+
+# ------------------------------------------------------------------------------------------------
+# ScanContext
+# ------------------------------------------------------------------------------------------------
+def sc_make(points):
+    """SCManager::makeScancontext -> (20, 60) float64 (values are floats widened to double)."""
+    p = _f32(points)
+    d = np.zeros((20, 60), np.float64)
+    lib().orc_sc_make(_p(p), len(p), _stride(p), _p(d))
+    return d
+
+
+def sc_keys(desc):
+    d = np.ascontiguousarray(desc, np.float64)
+    rk, sk = np.zeros(20), np.zeros(60)
+    lib().orc_sc_keys(_p(d), _p(rk), _p(sk))
+    return rk, sk
+
+
+def sc_distance(q, c):
+    q = np.ascontiguousarray(q, np.float64)
+    c = np.ascontiguousarray(c, np.float64)
+    d = C.c_double()
+    s = C.c_int32()
+    lib().orc_sc_distance(_p(q), _p(c), C.byref(d), C.byref(s))
+    return d.value, s.value
+
+
+def sc_topk(db, q, k=10):
+    db = np.ascontiguousarray(db, np.float64).reshape(-1, 1200)
+    q = np.ascontiguousarray(q, np.float64)
+    dist = np.zeros(k)
+    idx = np.zeros(k, np.int32)
+    sh = np.zeros(k, np.int32)
+    lib().orc_sc_topk(_p(db), len(db), _p(q), k, _p(dist), _p(idx), _p(sh))
+    return dist, idx, sh
+
+
+def sc_detect_loop_reference(db, q, num_candidates=10):
+    """detectLoopClosureID (Scancontext.cpp:253-344) at a tree-refresh boundary: 10-NN of the float ring key in the
+    reference's own nanoflann tree (oracle/_ref), then the best candidate by distanceBtnScanContext.
+    Returns (nn_idx, min_dist, nn_align, candidate ids)."""
+    r = ref()
+    if r is None:
+        raise RuntimeError("oracle/_ref not built")
+    db = np.ascontiguousarray(db, np.float64).reshape(-1, 20, 60)
+    keys = np.stack([sc_keys(d)[0] for d in db]).astype(np.float32)  # eig2stdvec: double -> float
+    qk = sc_keys(q)[0].astype(np.float32)
+    idx = np.zeros(num_candidates, np.uint64)
+    d2 = np.zeros(num_candidates, np.float32)
+    r.ref_ringkey_knn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    r.ref_ringkey_knn(_p(keys), len(keys), 20, _p(qk), num_candidates, _p(idx), _p(d2))
+    best, arg, align = 10000000.0, 0, 0
+    for ci in idx:
+        d, s = sc_distance(q, db[int(ci)])
+        if d < best:
+            best, arg, align = d, int(ci), s
+    return arg, best, align, idx.astype(np.int64)

@@ -1,0 +1,151 @@
+"""ScanContext (K5): oracle sanity on CPU, GPU parity (-m gpu), and the sharded top-k exchange with gloo on CPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+
+def test_oracle_sc_recovers_known_shift(oracle_mod, ilsm):
+    db = ilsm.synth.sc_database(300)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 12)
+    for j in range(len(q)):
+        dist, idx, sh = oracle_mod.sc_topk(db.astype(np.float64), q[j].astype(np.float64), 3)
+        assert idx[0] == ids[j] and sh[0] == shifts[j] and dist[0] < 0.13  # SC_DIST_THRES, Scancontext.h:91
+        assert dist[1] > 0.3
+
+
+def test_oracle_sc_superset_of_reference_candidates(oracle_mod, ilsm):
+    """detectLoopClosureID scores 10 ring-key candidates (reference nanoflann); brute-force scoring of every entry is
+    a superset: same distance/shift for those ids, and a top-1 at least as good."""
+    if oracle_mod.ref() is None:
+        pytest.skip("oracle/_ref not built")
+    db = ilsm.synth.sc_database(400).astype(np.float64)
+    q, ids, _ = ilsm.synth.sc_queries(db.astype(np.float32), 6)
+    for j in range(len(q)):
+        nn, best, align, cands = oracle_mod.sc_detect_loop_reference(db, q[j].astype(np.float64))
+        dist, idx, sh = oracle_mod.sc_topk(db, q[j].astype(np.float64), len(db))
+        lut = {int(i): (d, s) for d, i, s in zip(dist, idx, sh)}
+        for c in cands:
+            d, s = oracle_mod.sc_distance(q[j].astype(np.float64), db[int(c)])
+            assert lut[int(c)] == (d, s)
+        assert dist[0] <= best
+
+
+def test_oracle_sc_make(oracle_mod):
+    pts = np.array([[10.0, 0.1, 1.0], [10.0, 0.2, 3.0], [-5.0, -5.0, -1.0], [100.0, 0.0, 9.0], [0.0, 30.0, 0.5]], np.float32)
+    d = oracle_mod.sc_make(pts)
+    assert d.shape == (20, 60) and d.max() == 5.0 and (d != 0).sum() == 3  # two points share a bin, one is beyond 80 m
+    rk, sk = oracle_mod.sc_keys(d)
+    assert np.isclose(rk.sum() * 60, d.sum()) and np.isclose(sk.sum() * 20, d.sum())
+
+
+def test_merge_topk_is_deterministic(ilsm):
+    dist = np.array([0.5, 0.1, 0.1, np.inf, 0.3, 0.7])
+    ids = np.array([7, 9, 3, -1, 11, 2], np.int32)
+    sh = np.array([1, 2, 3, 0, 5, 6], np.int32)
+    od, oi, os_ = ilsm.merge_topk(dist, ids, sh, 4)
+    assert oi.tolist() == [3, 9, 11, 7] and os_.tolist() == [3, 2, 5, 1] and od.tolist() == [0.1, 0.1, 0.3, 0.5]
+
+
+def _shard_worker(rank, world, port, n_db, k, out):
+    """One rank of the sharded query path with the CPU oracle standing in for the GPU scorer: local top-k on the
+    rank's contiguous shard, one all_gather of k x (dist, id, shift), identical merge on every rank."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import ilsm_b200 as ilsm
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    db = ilsm.synth.sc_database(n_db)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 3)
+    lo, hi = ilsm.shard_range(n_db, rank, world)
+    results = []
+    for j in range(len(q)):
+        d, i, s = oracle.sc_topk(db[lo:hi].astype(np.float64), q[j].astype(np.float64), k)
+        i = np.where(i >= 0, i + lo, -1).astype(np.int32)
+        gd, gi, gs = ilsm.allgather_topk(d, i, s)
+        results.append(ilsm.merge_topk(gd, gi, gs, k))
+    if rank == 0:
+        np.savez(out, dist=np.stack([r[0] for r in results]), ids=np.stack([r[1] for r in results]),
+                 shifts=np.stack([r[2] for r in results]), true_ids=ids, true_shifts=shifts)
+    dist.destroy_process_group()
+
+
+def test_sharded_topk_gloo_world2(tmp_path, oracle_mod, ilsm):
+    import torch.multiprocessing as mp
+    n_db, k = 240, 5
+    out = str(tmp_path / "merged.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(2, port, n_db, k, out), nprocs=2, join=True)
+    r = np.load(out)
+    db = ilsm.synth.sc_database(n_db)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 3)
+    for j in range(3):
+        d, i, s = oracle_mod.sc_topk(db.astype(np.float64), q[j].astype(np.float64), k)
+        assert np.array_equal(r["ids"][j], i) and np.array_equal(r["shifts"][j], s) and np.array_equal(r["dist"][j], d)
+        assert r["ids"][j][0] == ids[j] and r["shifts"][j][0] == shifts[j]
+
+
+# ------------------------------------------------------------------------------------------------- GPU parity
+@pytest.mark.gpu
+def test_gpu_sc_make_matches_oracle(ctx, oracle_mod, ilsm, cfg_full):
+    sc = ilsm.ScanContextDb(ctx)
+    for pts in (cfg_full["cloud"], cfg_full["map_surf"][:30000], np.zeros((0, 3), np.float32)):
+        got = sc.make_scancontext(pts)
+        want = oracle_mod.sc_make(pts) if len(pts) else np.zeros((20, 60))
+        assert np.array_equal(got.astype(np.float64), want)
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sc_topk_matches_oracle(ctx, oracle_mod, ilsm):
+    db = ilsm.synth.sc_database(2000)
+    db[17] = 0.0                      # an all-empty descriptor: no effective column -> "no match" distance
+    db[18, :, 10:20] = 0.0            # partially empty columns
+    q, ids, shifts = ilsm.synth.sc_queries(db, 8)
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db[:700])
+    sc.add(db[700:])                  # growth keeps the contents
+    assert len(sc) == 2000
+    for j in range(len(q)):
+        d, i, s = sc.query_topk(q[j], k=10)
+        wd, wi, ws = oracle_mod.sc_topk(db.astype(np.float64), q[j].astype(np.float64), 10)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws)
+        assert np.allclose(d, wd, rtol=1e-12, atol=1e-14)
+        assert i[0] == ids[j] and s[0] == shifts[j]
+    # excluding the most recent entries (NUM_EXCLUDE_RECENT) and a shard offset
+    d, i, s = sc.query_topk(q[0], k=5, n_search=1950, id_offset=1000)
+    wd, wi, ws = oracle_mod.sc_topk(db[:1950].astype(np.float64), q[0].astype(np.float64), 5)
+    assert np.array_equal(i, wi + 1000) and np.array_equal(s, ws)
+    # fewer entries than k
+    d, i, s = sc.query_topk(q[0], k=8, n_search=3)
+    assert (i[3:] == -1).all() and np.isinf(d[3:]).all()
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sc_sharded_equals_unsharded(ctx, oracle_mod, ilsm):
+    """R shards simulated in one process: per-shard local top-k + merge == top-k over the whole database."""
+    db = ilsm.synth.sc_database(3000, seed=99)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 4, seed=100)
+    whole = ilsm.ScanContextDb(ctx)
+    whole.add(db)
+    for R in (2, 4, 8):
+        shards = []
+        for r in range(R):
+            lo, hi = ilsm.shard_range(len(db), r, R)
+            s = ilsm.ScanContextDb(ctx)
+            s.add(db[lo:hi])
+            shards.append((s, lo))
+        for j in range(len(q)):
+            parts = [s.query_topk(q[j], k=10, id_offset=lo) for s, lo in shards]
+            md, mi, ms = ilsm.merge_topk(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]),
+                                         np.concatenate([p[2] for p in parts]), 10)
+            wd, wi, ws = whole.query_topk(q[j], k=10)
+            assert np.array_equal(mi, wi) and np.array_equal(ms, ws) and np.array_equal(md, wd)
+        for s, _ in shards:
+            s.close()
+    whole.close()
