@@ -187,6 +187,21 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q_xyzw[4], const do
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q_xyzw[4], double t_xyz[3], int max_num_iterations, double huber_a,
                ilsm_solve_summary* summary);
 
+/* ------------------------------------------------------------------- scan-to-scan odometry (laserOdometry) ---- */
+
+/* One frame of the A-LOAM odometry optimisation.  last_corner / last_surf are maps built (ilsm_map_build) over the
+ * PREVIOUS frame's cornerPointsLessSharp / surfPointsLessFlat clouds, xyzi with intensity = scanID + 0.1*relTime and
+ * ring-sorted as scanRegistration emits them; sharp / flat are the CURRENT frame's cornerPointsSharp /
+ * surfPointsFlat.  q,t = para_q / para_t (q_last_curr, t_last_curr): read as the initial value, overwritten with
+ * the optimised one.  Per pass: TransformToStart (s = 1), 1-NN (d2 < 25), second/third point on the neighbouring
+ * rings (+-2.5), LidarEdgeFactor / LidarPlaneFactor, ceres::Solve (max 4 iterations, Huber 0.1); 2 passes.
+ * If `factors` is non-NULL only the association at (q,t) is run and the nsh+nfl records are returned (plane factors
+ * as unit normal + offset: r = n.lp + d == (lp - j).ljm).
+ * Replaces: laserOdometry.cpp:417-711 (TransformToStart :147-170, edge search :446-565, plane search :568-689). */
+ILSM_API int ilsm_odometry(ilsm_ctx* ctx, ilsm_map* last_corner, ilsm_map* last_surf, const float* sharp, int nsh,
+                           const float* flat, int nfl, int stride_bytes, double q_xyzw[4], double t_xyz[3],
+                           const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_factor* factors);
+
 /* ------------------------------------------------------------- K4: front end (projection + features) ---- */
 
 /* Organised H x W cloud -> image_range (u8, min(range*20,255)), image_intensity (u8, min(I,255)) and cloud_track

@@ -100,6 +100,7 @@ def load_library(path: str | None = None):
         "ilsm_sc_query_topk": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_query_topk_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_merge_topk": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
+        "ilsm_odometry": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport), vp]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
@@ -239,6 +240,21 @@ class Context:
         m = C.c_int(0)
         _check(self._lib.ilsm_voxelgrid(self._h, _ptr(a), n, stride, leaf, _ptr(out), C.byref(m)))
         return out[:m.value].copy()
+
+    # -- laserOdometry.cpp:417-711 ----------------------------------------------------------------
+    def odometry(self, last_corner_map, last_surf_map, sharp, flat, q, t, opts: RegOpts | None = None,
+                 factors_only=False):
+        sh, nsh, s1 = _cloud(sharp)
+        fl, nfl, s2 = _cloud(flat)
+        stride = s1 if nsh else s2
+        qq = np.array(q, np.float64)
+        tt = np.array(t, np.float64)
+        rep = RegReport()
+        fac = np.zeros(nsh + nfl, FACTOR_DTYPE) if factors_only else None
+        _check(self._lib.ilsm_odometry(self._h, last_corner_map._h, last_surf_map._h, _ptr(sh), nsh, _ptr(fl), nfl,
+                                       stride, _ptr(qq), _ptr(tt), C.byref(opts) if opts is not None else None,
+                                       C.byref(rep), _ptr(fac) if factors_only else None))
+        return fac if factors_only else (qq, tt, rep)
 
     def associate_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
                       opts: RegOpts | None = None):

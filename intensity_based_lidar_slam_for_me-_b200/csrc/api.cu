@@ -418,6 +418,54 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const flo
   return ILSM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ odometry
+ILSM_API int ilsm_odometry(ilsm_ctx* ctx, ilsm_map* last_corner, ilsm_map* last_surf, const float* sharp, int nsh,
+                           const float* flat, int nfl, int stride_bytes, double q[4], double t[3],
+                           const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_factor* factors) {
+  int rc = check_reg_args(ctx, last_corner, last_surf, sharp, nsh, flat, nfl, stride_bytes);
+  if (rc) return rc;
+  if (!q || !t) return fail(ILSM_ERR_INVALID_ARG, "odometry: null pose");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (report) memset(report, 0, sizeof(*report));
+  const float *d_sharp, *d_flat;
+  if ((rc = stage_stacks(c, sharp, nsh, flat, nfl, stride_bytes, &d_sharp, &d_flat))) return rc;
+  Pose7 p;
+  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
+  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
+  count_launches(1);
+  const int n = nsh + nfl;
+  if (factors) {
+    // association only at the given pose (parity aid): export the factor records, no solve
+    if ((rc = c.odom_associate_dev(&last_corner->m, &last_surf->m, d_sharp, nsh, d_flat, nfl, stride_bytes))) return rc;
+    if (n > 0) {
+      size_t words = ((size_t)n * sizeof(ilsm_factor) + 3) / 4;
+      if ((rc = c.out_idx.reserve(words + 8))) return rc;
+      ilsm_factor* d_f = reinterpret_cast<ilsm_factor*>(c.out_idx.p);
+      if ((rc = factors_export(&c, d_f))) return rc;
+      ILSM_CUDA(cudaMemcpyAsync(factors, d_f, (size_t)n * sizeof(ilsm_factor), cudaMemcpyDeviceToHost, c.stream));
+    }
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));
+    return ILSM_OK;
+  }
+  if ((rc = c.odometry_dev(&last_corner->m, &last_surf->m, d_sharp, nsh, d_flat, nfl, stride_bytes, o))) return rc;
+  unsigned char* pin = c.pinned.p;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const double* out = reinterpret_cast<const double*>(pin);
+  for (int i = 0; i < 4; ++i) q[i] = out[i];
+  for (int i = 0; i < 3; ++i) t[i] = out[4 + i];
+  if (report) {
+    memcpy(report, pin + 64, sizeof(*report));
+    report->passes = o.outer_iterations;
+  }
+  return ILSM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ front end
 ILSM_API int ilsm_project(ilsm_ctx* ctx, const float* xyzi, int H, int W, int stride_bytes, uint8_t* range_img,
                           uint8_t* inten_img, float* cloud_track_xyzi) {

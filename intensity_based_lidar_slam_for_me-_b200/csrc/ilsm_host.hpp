@@ -170,6 +170,9 @@ struct Ctx {
   int associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                     const ilsm_reg_opts& o, bool want_knn);
   int solve_launch(int max_iter, double huber_a, int pass);  // the whole LM solve, one cluster launch
+  int odom_associate_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl, int stride_bytes);
+  int odometry_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl, int stride_bytes,
+                   const ilsm_reg_opts& o);
   // front end (frontend.cu)
   int project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
                   float* d_track);

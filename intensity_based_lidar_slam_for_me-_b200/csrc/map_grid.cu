@@ -32,7 +32,7 @@ __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i
   return isfinite(x) && isfinite(y) && isfinite(z);
 }
 
-__global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, float inv_cell, GridCell* cells,
+__global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, int ioff, float inv_cell, GridCell* cells,
                                   uint32_t mask, int log2_size, float4* __restrict__ orig,
                                   uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
                                   uint32_t* counters) {
@@ -40,7 +40,8 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
   if (i >= n) return;
   float x, y, z;
   bool ok = load_point(src, stride_f, i, x, y, z);
-  orig[i] = make_float4(x, y, z, 0.f);
+  // w keeps the caller's intensity channel (LOAM clouds carry scanID + 0.1*relTime there, laserOdometry.cpp:461)
+  orig[i] = make_float4(x, y, z, ioff >= 0 ? __ldg(src + (size_t)i * stride_f + ioff) : 0.f);
   int cx = 0, cy = 0, cz = 0;
   if (ok) {
     float ux = __fmul_rn(x, inv_cell), uy = __fmul_rn(y, inv_cell), uz = __fmul_rn(z, inv_cell);
@@ -201,7 +202,8 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
   const int T = 256;
   grid_clear_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, bbox.p, counters.p);
   if (n_pts > 0) {
-    grid_count_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(d_src, n_pts, stride_bytes / 4, inv_cell, cells.p,
+    const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
+    grid_count_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(d_src, n_pts, stride_bytes / 4, ioff, inv_cell, cells.p,
                                                          table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p,
                                                          counters.p);
     grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p, bbox.p);

@@ -263,6 +263,147 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// scan-to-scan odometry association (laserOdometry.cpp:446-565 edges, :568-689 planes)
+// The previous frame's less-sharp / less-flat clouds are ring-sorted (scanRegistration appends ring by ring) and
+// carry the ring id in int(intensity); after the 1-NN the reference walks the cloud up and down from the closest
+// point until the ring id leaves closest +- NEARBY_SCAN.  One warp per feature point: the walk is done 32 points
+// per step, candidates are ranked by (float d2, visiting order) so that ties resolve like the sequential strict `<`.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  const uint32_t mhi = redux_min_u32(0xffffffffu, hi);
+  const uint32_t mlo = redux_min_u32(0xffffffffu, hi == mhi ? lo : 0xFFFFFFFFu);
+  return ((u64)mhi << 32) | mlo;
+}
+
+// walk one direction; plane == false: edge rule (other rings only -> slot A); plane == true: slot A = same side or
+// same ring, slot B = other side (see the reference loops).  order_base keeps upward visits ahead of downward ones.
+template <bool kPlane, bool kUp>
+__device__ __forceinline__ void ring_walk(const float4* __restrict__ pts, int n, int closest, int cring, float sx, float sy,
+                                          float sz, unsigned lane, uint32_t order_base, u64& bestA, u64& bestB) {
+  int base = kUp ? closest + 1 : closest - 1;
+#pragma unroll 1
+  for (;;) {
+    const int j = kUp ? base + (int)lane : base - (int)lane;
+    const bool in = kUp ? j < n : j >= 0;
+    bool stop = false;
+    u64 ka = ~0ull, kb = ~0ull;
+    if (in) {
+      const float4 p = __ldg(pts + j);
+      const int rj = (int)p.w;
+      stop = kUp ? (double)rj > (double)cring + 2.5 : (double)rj < (double)cring - 2.5;
+      const float dx = __fsub_rn(p.x, sx), dy = __fsub_rn(p.y, sy), dz = __fsub_rn(p.z, sz);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const uint32_t order = order_base + (uint32_t)(kUp ? j - closest : closest - j);
+      const u64 key = ((u64)__float_as_uint(d) << 32) | order;
+      const bool near = (double)d < 25.0;  // DISTANCE_SQ_THRESHOLD seeds minPointSqDis2/3
+      if (!kPlane) {
+        if (near && (kUp ? rj > cring : rj < cring)) ka = key;
+      } else {
+        if (near && (kUp ? rj <= cring : rj >= cring)) ka = key;
+        if (near && (kUp ? rj > cring : rj < cring)) kb = key;
+      }
+    }
+    const unsigned sm = __ballot_sync(0xffffffffu, stop || !in);
+    const int first_stop = sm ? __ffs(sm) - 1 : 32;
+    if ((int)lane >= first_stop) ka = ~0ull, kb = ~0ull;  // the sequential loop breaks there
+    const u64 ma = warp_min_u64(ka);
+    bestA = ma < bestA ? ma : bestA;
+    if (kPlane) {
+      const u64 mb = warp_min_u64(kb);
+      bestB = mb < bestB ? mb : bestB;
+    }
+    if (first_stop < 32) break;
+    base = kUp ? base + 32 : base - 32;
+  }
+}
+
+__global__ void __launch_bounds__(kAssocThreads, 5)
+    odom_associate_kernel(GridView gc, GridView gs, const float* __restrict__ sharp, int nsh, const float* __restrict__ flat,
+                          int nfl, int stride_f, const LmState* __restrict__ st, FactorView fv) {
+  __shared__ WarpScratch scratch[kAssocThreads / 32];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * (kAssocThreads / 32);
+  int bbc[6], bbs[6];
+  load_bbox(gc, bbc);
+  load_bbox(gs, bbs);
+  const double q[4] = {st->xq[0], st->xq[1], st->xq[2], st->xq[3]};
+  const double tx = st->xt[0], ty = st->xt[1], tz = st->xt[2];
+#pragma unroll 1
+  for (int gid = blockIdx.x * (kAssocThreads / 32) + warp; gid < nsh + nfl; gid += nwarps) {
+    const bool is_corner = gid < nsh;
+    const float* pp = is_corner ? sharp + (size_t)gid * stride_f : flat + (size_t)(gid - nsh) * stride_f;
+    const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+    // TransformToStart with s = 1 (DISTORTION 0): q_last_curr * p + t_last_curr, double math, float store
+    const D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
+    const float sx = __double2float_rn(dadd(pw.x, tx)), sy = __double2float_rn(dadd(pw.y, ty)),
+                sz = __double2float_rn(dadd(pw.z, tz));
+    GridView g;
+    g.cells = is_corner ? gc.cells : gs.cells;
+    g.sorted = is_corner ? gc.sorted : gs.sorted;
+    g.orig = is_corner ? gc.orig : gs.orig;
+    g.bbox = nullptr;
+    g.mask = is_corner ? gc.mask : gs.mask;
+    g.log2_size = is_corner ? gc.log2_size : gs.log2_size;
+    g.cell = is_corner ? gc.cell : gs.cell;
+    g.inv_cell = is_corner ? gc.inv_cell : gs.inv_cell;
+    g.n = is_corner ? gc.n : gs.n;
+    int bb[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bb[i] = is_corner ? bbc[i] : bbs[i];
+    KnnResult<1, false> res;
+    knn_search<1, false>(g, bb, sx, sy, sz, 25.0f, lane, scratch[warp], res);
+    int type = 0;
+    double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, w = 0;
+    if (res.key[0] != kSentinel && (double)cand_d2(res.key[0]) < 25.0) {  // warp-uniform
+      const int closest = cand_idx(res.key[0]);
+      const float4 pc = __ldg(g.orig + closest);
+      const int cring = (int)pc.w;
+      u64 bestA = ~0ull, bestB = ~0ull;
+      if (is_corner) {
+        ring_walk<false, true>(g.orig, g.n, closest, cring, sx, sy, sz, lane, 0u, bestA, bestB);
+        ring_walk<false, false>(g.orig, g.n, closest, cring, sx, sy, sz, lane, 0x40000000u, bestA, bestB);
+        if (bestA != ~0ull) {
+          const uint32_t ord = (uint32_t)bestA;
+          const int j2 = ord < 0x40000000u ? closest + (int)ord : closest - (int)(ord - 0x40000000u);
+          const float4 pb = __ldg(g.orig + j2);
+          type = 1;
+          a[0] = pc.x, a[1] = pc.y, a[2] = pc.z;
+          b[0] = pb.x, b[1] = pb.y, b[2] = pb.z;
+        }
+      } else {
+        ring_walk<true, true>(g.orig, g.n, closest, cring, sx, sy, sz, lane, 0u, bestA, bestB);
+        ring_walk<true, false>(g.orig, g.n, closest, cring, sx, sy, sz, lane, 0x40000000u, bestA, bestB);
+        if (bestA != ~0ull && bestB != ~0ull) {
+          const uint32_t oa = (uint32_t)bestA, ob = (uint32_t)bestB;
+          const int j2 = oa < 0x40000000u ? closest + (int)oa : closest - (int)(oa - 0x40000000u);
+          const int j3 = ob < 0x40000000u ? closest + (int)ob : closest - (int)(ob - 0x40000000u);
+          const float4 pl = __ldg(g.orig + j2), pm = __ldg(g.orig + j3);
+          // ljm_norm = normalize((j - l) x (j - m));  r = (lp - j) . ljm  ==  ljm . lp + (-j . ljm)
+          const double ux = (double)pc.x - (double)pl.x, uy = (double)pc.y - (double)pl.y, uz = (double)pc.z - (double)pl.z;
+          const double vx = (double)pc.x - (double)pm.x, vy = (double)pc.y - (double)pm.y, vz = (double)pc.z - (double)pm.z;
+          const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+          const double inv = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+          const double n0 = nx * inv, n1 = ny * inv, n2 = nz * inv;
+          if (isfinite(n0) && isfinite(n1) && isfinite(n2)) {
+            type = 2;
+            a[0] = n0, a[1] = n1, a[2] = n2;
+            w = -((double)pc.x * n0 + (double)pc.y * n1 + (double)pc.z * n2);
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      fv.type[gid] = type;
+      fv.p[gid] = make_float4(px, py, pz, 0.f);
+      fv.a[gid] = make_double4(a[0], a[1], a[2], w);
+      fv.b[gid] = make_double4(b[0], b[1], b[2], 0.0);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // residual + Jacobian of one factor, accumulated into the 30 running sums
 // ---------------------------------------------------------------------------------------------------
 // running sums per evaluation: [0] cost, [1..21] H (upper triangle), [22..27] g, [28] #edge, [29] #plane
@@ -846,6 +987,36 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p, prm, fv);
   count_launches(1);
   return check_launch("associate");
+}
+
+int Ctx::odom_associate_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl,
+                            int stride_bytes) {
+  const int n = nsh + nfl;
+  int rc;
+  if ((rc = fac.type.reserve(n + 1)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
+      (rc = fac.b.reserve(n + 1)))
+    return rc;
+  fac.n = n;
+  fac.nc = nsh;
+  if (n == 0) return ILSM_OK;
+  if ((rc = mc->wait_ready(stream)) || (rc = ms->wait_ready(stream))) return rc;
+  FactorView fv = factor_view(fac, false);
+  long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
+  if (blocks > cap) blocks = cap;
+  odom_associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(mc->view(), ms->view(), d_sharp, nsh, d_flat, nfl,
+                                                                        stride_bytes / 4, lm.p, fv);
+  count_launches(1);
+  return check_launch("odom_associate");
+}
+
+int Ctx::odometry_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl, int stride_bytes,
+                      const ilsm_reg_opts& o) {
+  for (int pass = 0; pass < o.outer_iterations; ++pass) {
+    int rc = odom_associate_dev(mc, ms, d_sharp, nsh, d_flat, nfl, stride_bytes);
+    if (rc) return rc;
+    if ((rc = solve_launch(o.max_num_iterations, o.huber_a, pass))) return rc;
+  }
+  return ILSM_OK;
 }
 
 int Ctx::solve_launch(int max_iter, double huber_a, int pass) {

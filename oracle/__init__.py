@@ -299,3 +299,26 @@ def sc_detect_loop_reference(db, q, num_candidates=10):
         if d < best:
             best, arg, align = d, int(ci), s
     return arg, best, align, idx.astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------
+# scan-to-scan odometry
+# ------------------------------------------------------------------------------------------------
+def odom_associate(last_corner, last_surf, sharp, flat, qt):
+    lc, ls, sh, fl = _f32(last_corner), _f32(last_surf), _f32(sharp), _f32(flat)
+    assert lc.shape[1] >= 4 and _stride(lc) == _stride(ls)
+    qt = np.ascontiguousarray(qt, np.float64)
+    out = np.zeros(len(sh) + len(fl), FACTOR_DTYPE)
+    n = lib().orc_odom_associate(_p(lc), len(lc), _p(ls), len(ls), _stride(lc), _ioff(lc), _p(sh), len(sh), _p(fl), len(fl),
+                                 _stride(sh) if len(sh) else _stride(fl), _p(qt), _p(out))
+    return out[:n]
+
+
+def odometry(last_corner, last_surf, sharp, flat, qt, outer=2, max_iter=4):
+    lc, ls, sh, fl = _f32(last_corner), _f32(last_surf), _f32(sharp), _f32(flat)
+    x = np.array(qt, np.float64)
+    sums = (SolveSummary * outer)()
+    nf = np.zeros(2 * outer, np.int32)
+    lib().orc_odometry(_p(lc), len(lc), _p(ls), len(ls), _stride(lc), _ioff(lc), _p(sh), len(sh), _p(fl), len(fl),
+                       _stride(sh) if len(sh) else _stride(fl), _p(x), outer, max_iter, sums, _p(nf))
+    return x, list(sums), nf

@@ -758,3 +758,145 @@ ORC_API int orc_register_aloam(const float* map_corner, int n_mc, const float* m
   }
   return outer;
 }
+
+// ================================================================================================
+// Scan-to-scan odometry (laserOdometry.cpp:147-194, 417-717): correspondence search on the previous frame's
+// ring-sorted less-sharp / less-flat clouds, LidarEdgeFactor / LidarPlaneFactor with s = 1 (DISTORTION 0).
+// Clouds are xyzi with intensity = scanID + 0.1 * relTime; int(intensity) is the ring id (:461,470).
+// LidarPlaneFactor (hpp:143-196) r = (lp - j) . ljm is stored as a plane-norm record: n = ljm, d = -j . ljm.
+// ================================================================================================
+namespace {
+
+inline int ring_of(const float* p, int ioff) { return int(p[ioff]); }
+
+int odom_associate(const KdTree& kc, const KdTree& ks, int ioff, const float* sharp, int n_sharp, const float* flat,
+                   int n_flat, int stride_f, const double qt[7], OrcFactor* out) {
+  const double DISTANCE_SQ_THRESHOLD = 25, NEARBY_SCAN = 2.5;
+  Quat q{qt[0], qt[1], qt[2], qt[3]};
+  V3 t{qt[4], qt[5], qt[6]};
+  int nf = 0;
+  auto sqd = [](const float* a, const float* sel) {
+    // float expression, evaluated left to right, widened to double afterwards (laserOdometry.cpp:478-483)
+    return (double)((a[0] - sel[0]) * (a[0] - sel[0]) + (a[1] - sel[1]) * (a[1] - sel[1]) +
+                    (a[2] - sel[2]) * (a[2] - sel[2]));
+  };
+  for (int i = 0; i < n_sharp; ++i) {
+    const float* pi = pt(sharp, stride_f, i);
+    OrcFactor f;
+    std::memset(&f, 0, sizeof(f));
+    f.src = i;
+    f.p[0] = pi[0], f.p[1] = pi[1], f.p[2] = pi[2];
+    float sel[3];
+    associate_to_map(q, t, pi, sel);  // TransformToStart with s = 1
+    int32_t ci;
+    float cd;
+    kc.knn(sel, 1, &ci, &cd);
+    int closest = -1, min2 = -1;
+    if (ci >= 0 && cd < DISTANCE_SQ_THRESHOLD) {
+      closest = ci;
+      const int cring = ring_of(pt(kc.base, kc.stride_f, closest), ioff);
+      double best2 = DISTANCE_SQ_THRESHOLD;
+      for (int j = closest + 1; j < kc.n; ++j) {
+        const float* pj = pt(kc.base, kc.stride_f, j);
+        if (ring_of(pj, ioff) <= cring) continue;
+        if (ring_of(pj, ioff) > (cring + NEARBY_SCAN)) break;
+        const double d = sqd(pj, sel);
+        if (d < best2) best2 = d, min2 = j;
+      }
+      for (int j = closest - 1; j >= 0; --j) {
+        const float* pj = pt(kc.base, kc.stride_f, j);
+        if (ring_of(pj, ioff) >= cring) continue;
+        if (ring_of(pj, ioff) < (cring - NEARBY_SCAN)) break;
+        const double d = sqd(pj, sel);
+        if (d < best2) best2 = d, min2 = j;
+      }
+    }
+    if (min2 >= 0) {
+      const float* a = pt(kc.base, kc.stride_f, closest);
+      const float* b = pt(kc.base, kc.stride_f, min2);
+      f.type = 1;
+      for (int k = 0; k < 3; ++k) f.a[k] = a[k], f.b[k] = b[k];
+    }
+    out[nf++] = f;
+  }
+  for (int i = 0; i < n_flat; ++i) {
+    const float* pi = pt(flat, stride_f, i);
+    OrcFactor f;
+    std::memset(&f, 0, sizeof(f));
+    f.src = i;
+    f.p[0] = pi[0], f.p[1] = pi[1], f.p[2] = pi[2];
+    float sel[3];
+    associate_to_map(q, t, pi, sel);
+    int32_t ci;
+    float cd;
+    ks.knn(sel, 1, &ci, &cd);
+    int closest = -1, min2 = -1, min3 = -1;
+    if (ci >= 0 && cd < DISTANCE_SQ_THRESHOLD) {
+      closest = ci;
+      const int cring = ring_of(pt(ks.base, ks.stride_f, closest), ioff);
+      double best2 = DISTANCE_SQ_THRESHOLD, best3 = DISTANCE_SQ_THRESHOLD;
+      for (int j = closest + 1; j < ks.n; ++j) {
+        const float* pj = pt(ks.base, ks.stride_f, j);
+        if (ring_of(pj, ioff) > (cring + NEARBY_SCAN)) break;
+        const double d = sqd(pj, sel);
+        if (ring_of(pj, ioff) <= cring && d < best2)
+          best2 = d, min2 = j;
+        else if (ring_of(pj, ioff) > cring && d < best3)
+          best3 = d, min3 = j;
+      }
+      for (int j = closest - 1; j >= 0; --j) {
+        const float* pj = pt(ks.base, ks.stride_f, j);
+        if (ring_of(pj, ioff) < (cring - NEARBY_SCAN)) break;
+        const double d = sqd(pj, sel);
+        if (ring_of(pj, ioff) >= cring && d < best2)
+          best2 = d, min2 = j;
+        else if (ring_of(pj, ioff) < cring && d < best3)
+          best3 = d, min3 = j;
+      }
+    }
+    if (min2 >= 0 && min3 >= 0) {
+      const float* pa = pt(ks.base, ks.stride_f, closest);
+      const float* pb = pt(ks.base, ks.stride_f, min2);
+      const float* pc = pt(ks.base, ks.stride_f, min3);
+      V3 j{pa[0], pa[1], pa[2]}, l{pb[0], pb[1], pb[2]}, m{pc[0], pc[1], pc[2]};
+      V3 n = cross(j - l, j - m);
+      const double nn = norm(n);
+      n = {n.x / nn, n.y / nn, n.z / nn};  // ljm_norm.normalize()
+      if (std::isfinite(n.x) && std::isfinite(n.y) && std::isfinite(n.z)) {
+        f.type = 2;
+        f.a[0] = n.x, f.a[1] = n.y, f.a[2] = n.z;
+        f.b[0] = -dot(j, n);
+      }
+    }
+    out[nf++] = f;
+  }
+  return nf;
+}
+}  // namespace
+
+ORC_API int orc_odom_associate(const float* last_corner, int n_lc, const float* last_surf, int n_ls, int last_stride_bytes,
+                               int ioff, const float* sharp, int n_sharp, const float* flat, int n_flat, int stride_bytes,
+                               const double qt[7], OrcFactor* out) {
+  KdTree kc, ks;
+  kc.build(last_corner, n_lc, last_stride_bytes / 4);
+  ks.build(last_surf, n_ls, last_stride_bytes / 4);
+  return odom_associate(kc, ks, ioff, sharp, n_sharp, flat, n_flat, stride_bytes / 4, qt, out);
+}
+
+// laserOdometry.cpp:417-711: 2 x (correspondences + Solve(max 4)); qt = (para_q, para_t) updated in place
+ORC_API int orc_odometry(const float* last_corner, int n_lc, const float* last_surf, int n_ls, int last_stride_bytes, int ioff,
+                         const float* sharp, int n_sharp, const float* flat, int n_flat, int stride_bytes, double qt[7],
+                         int outer, int max_iter, OrcSolveSummary* summaries, int32_t* nfactors) {
+  KdTree kc, ks;
+  kc.build(last_corner, n_lc, last_stride_bytes / 4);
+  ks.build(last_surf, n_ls, last_stride_bytes / 4);
+  std::vector<OrcFactor> f((size_t)n_sharp + n_flat);
+  for (int it = 0; it < outer; ++it) {
+    const int nf = odom_associate(kc, ks, ioff, sharp, n_sharp, flat, n_flat, stride_bytes / 4, qt, f.data());
+    int ne = 0, np = 0;
+    for (int i = 0; i < nf; ++i) ne += f[i].type == 1, np += f[i].type == 2;
+    nfactors[2 * it] = ne, nfactors[2 * it + 1] = np;
+    lm_solve(f.data(), nf, qt, max_iter, 0.1, &summaries[it]);
+  }
+  return outer;
+}
