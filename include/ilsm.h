@@ -85,6 +85,22 @@ ILSM_API int ilsm_map_size(const ilsm_map* map);
 ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell);
 ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int stride_bytes, float cell);
 
+/* Incremental insertion.
+ *   ILSM_INSERT_NEAREST_TO_CENTRE: ikd-Tree's down-sampled insertion -- per cubic box of edge `leaf` around each new
+ *     point, the point of {box contents, new point} nearest to the box centre survives (strict <: a new point wins
+ *     ties against existing ones, a later new point against an earlier one); equivalent to processing the batch
+ *     point by point.  Boxes not touched by the batch are left alone (a Build-seeded box may hold several points).
+ *   ILSM_INSERT_APPEND: downsample_on = false.
+ * The k-NN cell size chosen at build time is kept.  Blocking.
+ * Replaces: ikdtree->Add_Points(points, true)  mapOptimization.cpp:475,479 (ikd_Tree.cpp:570-640) */
+#define ILSM_INSERT_APPEND 0
+#define ILSM_INSERT_NEAREST_TO_CENTRE 1
+ILSM_API int ilsm_map_insert(ilsm_map* map, const float* xyz, int n, int stride_bytes, int policy, float leaf);
+
+/* Copy the current map points (packed xyzi, map order) to the host; *n_out = map size (may exceed capacity).
+ * Replaces: ikdtree->flatten(Root_Node, storage, NOT_RECORD)  mapOptimization.cpp:224 */
+ILSM_API int ilsm_map_points(ilsm_map* map, float* out_xyzi, int capacity, int* n_out);
+
 /* Exact k-NN (1 <= k <= 8), ascending squared distance computed in float as ((dx*dx)+(dy*dy))+(dz*dz) without
  * FMA (FLANN L2_Simple<float>; ikd_Tree.cpp:2224-2230), ties broken by lower point index.  idx/d2 are nq*k;
  * missing neighbours are idx -1 / d2 +inf.  max_dist <= 0 means unbounded (exact for every query);

@@ -82,6 +82,8 @@ def load_library(path: str | None = None):
         "ilsm_map_build": (i32, [vp, vp, i32, i32, f32]),
         "ilsm_map_build_dev": (i32, [vp, vp, i32, i32, f32]),
         "ilsm_knn": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
+        "ilsm_map_insert": (i32, [vp, vp, i32, i32, i32, f32]),
+        "ilsm_map_points": (i32, [vp, vp, i32, C.POINTER(i32)]),
         "ilsm_knn_dev": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
         "ilsm_reg_opts_default": (None, [C.POINTER(RegOpts)]),
         "ilsm_register": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport)]),
@@ -328,6 +330,20 @@ class LocalMap:
     def build_dev(self, d_ptr: int, n: int, stride: int, cell: float = 0.0):
         _check(self._lib.ilsm_map_build_dev(self._h, d_ptr, n, stride, cell))
         return self
+
+    # ikdtree->Add_Points(points, downsample_on)  (mapOptimization.cpp:475; ikd_Tree.cpp:570-640)
+    def add_points(self, cloud, downsample=True, downsample_size=0.4):
+        a, n, stride = _cloud(cloud)
+        _check(self._lib.ilsm_map_insert(self._h, _ptr(a), n, stride, 1 if downsample else 0, downsample_size))
+        return self
+
+    # ikdtree->flatten(...)
+    def points(self):
+        n = C.c_int(0)
+        _check(self._lib.ilsm_map_points(self._h, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _check(self._lib.ilsm_map_points(self._h, _ptr(out), n.value, C.byref(n)))
+        return out[:n.value]
 
     # kdtree->nearestKSearch(point, k, idx, d2) / ikdtree->Nearest_Search(point, k, pts, d2)
     def nearest_k_search(self, queries, k: int = 5, max_dist: float = 0.0):

@@ -108,6 +108,8 @@ void Map::release() {
   stream = nullptr, ready = nullptr, ctx_done = nullptr;
   cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release();
   bbox.release(), raw.release();
+  vox_table.release(), ins_new.release(), ins_out.release(), ins_slot_new.release(), ins_slot_old.release();
+  ins_keep.release(), ins_pos.release(), ins_bsum.release();
 }
 
 static bool valid_stride(int s) { return s >= 12 && (s % 4) == 0; }
@@ -257,6 +259,41 @@ ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_b
   if (bytes) ILSM_CUDA(cudaMemcpyAsync(m.raw.p, xyz, bytes, cudaMemcpyHostToDevice, m.stream));
   if ((rc = m.build_dev(m.raw.p, n, stride_bytes, cell))) return rc;
   if (!m.ctx->async_build) ILSM_CUDA(cudaStreamSynchronize(m.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_map_insert(ilsm_map* map, const float* xyz, int n, int stride_bytes, int policy, float leaf) {
+  if (!map || (n > 0 && !xyz)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_insert: null argument");
+  if (n < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_insert: bad n/stride");
+  Map& m = map->m;
+  std::lock_guard<std::mutex> lk(m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(m.ctx->device));
+  if (m.table_size == 0) {  // Add_Points on an empty tree behaves like Build
+    int rc0 = m.build_dev(nullptr, 0, 16, m.cell);
+    if (rc0) return rc0;
+  }
+  size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = m.raw.reserve(bytes / 4 + 4))) return rc;
+  ILSM_CUDA(cudaEventRecord(m.ctx_done, m.ctx->stream));
+  ILSM_CUDA(cudaStreamWaitEvent(m.stream, m.ctx_done, 0));
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(m.raw.p, xyz, bytes, cudaMemcpyHostToDevice, m.stream));
+  if ((rc = m.insert_dev(m.raw.p, n, stride_bytes, policy, leaf))) return rc;
+  ILSM_CUDA(cudaStreamSynchronize(m.stream));
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_map_points(ilsm_map* map, float* out_xyzi, int capacity, int* n_out) {
+  if (!map || !n_out || (capacity > 0 && !out_xyzi)) return fail(ILSM_ERR_INVALID_ARG, "ilsm_map_points: null argument");
+  Map& m = map->m;
+  std::lock_guard<std::mutex> lk(m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(m.ctx->device));
+  *n_out = m.n;
+  const int k = m.n < capacity ? m.n : capacity;
+  if (k > 0) {
+    ILSM_CUDA(cudaStreamSynchronize(m.stream));
+    ILSM_CUDA(cudaMemcpy(out_xyzi, m.orig.p, (size_t)k * 16, cudaMemcpyDeviceToHost));
+  }
   return ILSM_OK;
 }
 

@@ -116,6 +116,12 @@ struct Map {
   cudaEvent_t ready = nullptr, ctx_done = nullptr;
   bool pending = false;
 
+  // Add_Points scratch (ikdmap.cu)
+  DevBuf<u64> vox_table;
+  DevBuf<float4> ins_new, ins_out;
+  DevBuf<uint32_t> ins_slot_new, ins_slot_old, ins_keep, ins_pos, ins_bsum;
+  int insert_dev(const float* d_src, int n_new, int stride_bytes, int policy, float ds);
+
   int init(Ctx* c);
   int wait_ready(cudaStream_t user);
   int build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size);

@@ -322,3 +322,14 @@ def odometry(last_corner, last_surf, sharp, flat, qt, outer=2, max_iter=4):
     lib().orc_odometry(_p(lc), len(lc), _p(ls), len(ls), _stride(lc), _ioff(lc), _p(sh), len(sh), _p(fl), len(fl),
                        _stride(sh) if len(sh) else _stride(fl), _p(x), outer, max_iter, sums, _p(nf))
     return x, list(sums), nf
+
+
+# ------------------------------------------------------------------------------------------------
+# ikd-Tree Add_Points
+# ------------------------------------------------------------------------------------------------
+def ikd_add_points(existing_xyz, add_xyz, ds, downsample=True):
+    e = np.ascontiguousarray(np.asarray(existing_xyz, np.float32)[:, :3]).reshape(-1, 3)
+    a = np.ascontiguousarray(np.asarray(add_xyz, np.float32)[:, :3]).reshape(-1, 3)
+    out = np.zeros((len(e) + len(a) + 1, 3), np.float32)
+    n = lib().orc_ikd_add_points(_p(e), len(e), _p(a), len(a), C.c_float(ds), 1 if downsample else 0, _p(out), len(out))
+    return out[:n].copy()

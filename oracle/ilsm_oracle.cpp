@@ -900,3 +900,73 @@ ORC_API int orc_odometry(const float* last_corner, int n_lc, const float* last_s
   }
   return outer;
 }
+
+// ================================================================================================
+// ikd-Tree Add_Points with down-sampling (ikd_Tree.cpp:570-640), literal point-by-point restatement on a flat
+// point list (the tree shape, lazy deletion and re-balancing do not change the resulting point SET).
+// Storage order of Search_by_range is the tree's traversal order (unspecified here): ties between existing points
+// of one box are broken by lower list position.  in/out: packed xyz (3 floats).
+// ================================================================================================
+ORC_API int orc_ikd_add_points(const float* existing, int n_old, const float* add, int n_add, float ds, int downsample,
+                               float* out_xyz, int out_cap) {
+  struct P {
+    float x, y, z;
+  };
+  std::vector<P> pts(n_old);
+  for (int i = 0; i < n_old; ++i) pts[i] = {existing[3 * i], existing[3 * i + 1], existing[3 * i + 2]};
+  auto calc_dist = [](const P& a, const P& b) {
+    return (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y) + (a.z - b.z) * (a.z - b.z);
+  };
+  for (int i = 0; i < n_add; ++i) {
+    const P p{add[3 * i], add[3 * i + 1], add[3 * i + 2]};
+    if (!downsample) {
+      pts.push_back(p);
+      continue;
+    }
+    float mn[3], mx[3];
+    const float c[3] = {p.x, p.y, p.z};
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = std::floor(c[a] / ds) * ds;
+      mx[a] = mn[a] + ds;
+    }
+    P mid;
+    mid.x = (float)(mn[0] + (mx[0] - mn[0]) / 2.0);
+    mid.y = (float)(mn[1] + (mx[1] - mn[1]) / 2.0);
+    mid.z = (float)(mn[2] + (mx[2] - mn[2]) / 2.0);
+    std::vector<int> storage;  // Search_by_range: min <= x && max > x (ikd_Tree.cpp:1607-1637)
+    for (int j = 0; j < (int)pts.size(); ++j) {
+      const P& s = pts[j];
+      if (mn[0] <= s.x && mx[0] > s.x && mn[1] <= s.y && mx[1] > s.y && mn[2] <= s.z && mx[2] > s.z) storage.push_back(j);
+    }
+    float min_dist = calc_dist(p, mid);
+    P result = p;
+    for (int j : storage) {
+      const float d = calc_dist(pts[j], mid);
+      if (d < min_dist) min_dist = d, result = pts[j];
+    }
+    const bool same = std::fabs(p.x - result.x) < 1e-6 && std::fabs(p.y - result.y) < 1e-6 && std::fabs(p.z - result.z) < 1e-6;
+    if (storage.size() > 1 || same) {
+      // Delete_by_range + Add_by_point: the survivor keeps its place when it was already stored, else is appended
+      std::vector<P> next;
+      next.reserve(pts.size() + 1);
+      size_t k = 0;
+      bool placed = false;
+      for (int j = 0; j < (int)pts.size(); ++j) {
+        if (k < storage.size() && storage[k] == j) {
+          ++k;
+          if (!placed && pts[j].x == result.x && pts[j].y == result.y && pts[j].z == result.z) {
+            next.push_back(pts[j]);
+            placed = true;
+          }
+          continue;
+        }
+        next.push_back(pts[j]);
+      }
+      if (!placed) next.push_back(result);
+      pts.swap(next);
+    }
+  }
+  const int n = (int)pts.size();
+  for (int i = 0; i < n && i < out_cap; ++i) out_xyz[3 * i] = pts[i].x, out_xyz[3 * i + 1] = pts[i].y, out_xyz[3 * i + 2] = pts[i].z;
+  return n;
+}
