@@ -203,6 +203,43 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q_xyzw[4], const do
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q_xyzw[4], double t_xyz[3], int max_num_iterations, double huber_a,
                ilsm_solve_summary* summary);
 
+/* ---------------------------------------------------------- laserMapping: device-resident rolling cube map ---- */
+typedef struct ilsm_cubemap ilsm_cubemap;
+
+typedef struct ilsm_cubemap_stats {
+  int32_t n_map_corner;     /* laserCloudCornerFromMapNum */
+  int32_t n_map_surf;       /* laserCloudSurfFromMapNum */
+  int32_t n_stack_corner;   /* laserCloudCornerStackNum */
+  int32_t n_stack_surf;     /* laserCloudSurfStackNum */
+  int32_t ran_optimization; /* 0 when the guard of laserMapping.cpp:624 skipped the solve */
+  int32_t n_valid;          /* laserCloudValidNum */
+  int32_t cen[3];           /* laserCloudCenWidth / Height / Depth after the roll */
+  int32_t flags;            /* non-zero: a cube or a stack exceeded its capacity */
+} ilsm_cubemap_stats;
+
+/* The 21x21x11 map of 50 m cubes (laserMapping.cpp:70-78), resident in HBM: every cube owns a slab of
+ * cube_capacity points (<= 16384; 0 selects 16384).  line_res / plane_res = mapping_line_resolution /
+ * mapping_plane_resolution (spot.launch:4-5). */
+ILSM_API int ilsm_cubemap_create(ilsm_ctx* ctx, float line_res, float plane_res, int cube_capacity, ilsm_cubemap** out);
+ILSM_API void ilsm_cubemap_destroy(ilsm_cubemap* cm);
+
+/* Insert WORLD-frame points (e.g. a prior map) after rolling the window around `centre`, then VoxelGrid the valid
+ * cubes (the tail of process(), laserMapping.cpp:880-1002, without a registration). */
+ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, int nc, const float* surf, int ns,
+                                       int stride_bytes, const double centre_xyz[3]);
+
+/* One iteration of process() (laserMapping.cpp:327-1002) for one frame: corner_last / surf_last are the frame's
+ * less-sharp / less-flat clouds in the sensor frame, (q_wodom, t_wodom) the odometry pose; returns the mapped pose
+ * (q_w, t_w).  transformAssociateToMap, window roll, 5x5x3 gather, stack VoxelGrid, guarded 2 x (associate + Solve),
+ * transformUpdate, insertion of the stack at the optimised pose and per-cube VoxelGrid of the valid cubes.  The
+ * map and q/t_wmap_wodom persist in the handle.  At most 16384 points per feature cloud. */
+ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int nc, const float* surf_last, int ns,
+                                int stride_bytes, const double q_wodom_xyzw[4], const double t_wodom[3], double q_w_xyzw[4],
+                                double t_w[3], const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_cubemap_stats* stats);
+
+/* Copy one cube (array index i + 21*j + 441*k of the current window; which = 0 corner, 1 surf) to the host. */
+ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out);
+
 /* ------------------------------------------------------------------- scan-to-scan odometry (laserOdometry) ---- */
 
 /* One frame of the A-LOAM odometry optimisation.  last_corner / last_surf are maps built (ilsm_map_build) over the

@@ -53,6 +53,12 @@ class Features(C.Structure):
                 ("less_flat_xyzi", C.c_void_p), ("counts", FeatureCounts)]
 
 
+class CubeMapStats(C.Structure):
+    _fields_ = [("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32), ("n_stack_corner", C.c_int32),
+                ("n_stack_surf", C.c_int32), ("ran_optimization", C.c_int32), ("n_valid", C.c_int32),
+                ("cen", C.c_int32 * 3), ("flags", C.c_int32)]
+
+
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
 _lib = None
@@ -103,6 +109,12 @@ def load_library(path: str | None = None):
         "ilsm_sc_query_topk_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_merge_topk": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
         "ilsm_odometry": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport), vp]),
+        "ilsm_cubemap_create": (i32, [vp, f32, f32, i32, C.POINTER(vp)]),
+        "ilsm_cubemap_destroy": (None, [vp]),
+        "ilsm_cubemap_insert_world": (i32, [vp, vp, i32, vp, i32, i32, vp]),
+        "ilsm_cubemap_frame": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport),
+                                     C.POINTER(CubeMapStats)]),
+        "ilsm_cubemap_cube": (i32, [vp, i32, i32, vp, i32, C.POINTER(i32)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
@@ -416,3 +428,57 @@ class ScanContextDb:
     def query_topk_dev(self, d_desc_ptr, k, n_search, id_offset, d_dist_ptr, d_id_ptr, d_shift_ptr):
         _check(self._lib.ilsm_sc_query_topk_dev(self._h, d_desc_ptr, n_search, id_offset, k, d_dist_ptr, d_id_ptr,
                                                 d_shift_ptr))
+
+
+class CubeMap:
+    """ilsm_cubemap: the device-resident rolling 21x21x11 cube map of laserMapping.cpp and one process() iteration per
+    frame() call (transformAssociateToMap -> roll -> gather -> stack VoxelGrid -> guarded registration ->
+    transformUpdate -> insertion -> per-cube VoxelGrid)."""
+
+    def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.8, cube_capacity: int = 0):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_cubemap_create(ctx._h, line_res, plane_res, cube_capacity, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_cubemap_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _x4(a):
+        a = np.asarray(a, np.float32)
+        if a.ndim == 2 and a.shape[1] == 4 and a.flags.c_contiguous:
+            return a
+        out = np.zeros((len(a), 4), np.float32)
+        out[:, :min(4, a.shape[1])] = a[:, :4]
+        return out
+
+    def insert_world(self, corner, surf, centre):
+        c, s = self._x4(corner), self._x4(surf)
+        ctr = np.ascontiguousarray(centre, np.float64)
+        _check(self._lib.ilsm_cubemap_insert_world(self._h, _ptr(c), len(c), _ptr(s), len(s), 16, _ptr(ctr)))
+
+    def frame(self, corner_last, surf_last, q_wodom, t_wodom, opts: RegOpts | None = None):
+        c, s = self._x4(corner_last), self._x4(surf_last)
+        qo, to = np.array(q_wodom, np.float64), np.array(t_wodom, np.float64)
+        qw, tw = np.zeros(4), np.zeros(3)
+        rep, st = RegReport(), CubeMapStats()
+        _check(self._lib.ilsm_cubemap_frame(self._h, _ptr(c), len(c), _ptr(s), len(s), 16, _ptr(qo), _ptr(to), _ptr(qw),
+                                            _ptr(tw), C.byref(opts) if opts is not None else None, C.byref(rep), C.byref(st)))
+        return qw, tw, rep, st
+
+    def cube(self, which: int, index: int):
+        n = C.c_int(0)
+        _check(self._lib.ilsm_cubemap_cube(self._h, which, index, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _check(self._lib.ilsm_cubemap_cube(self._h, which, index, _ptr(out), n.value, C.byref(n)))
+        return out[:n.value]

@@ -131,15 +131,7 @@ static ilsm_reg_opts sanitize(const ilsm_reg_opts* o) {
 
 using namespace ilsm;
 
-struct ilsm_ctx {
-  Ctx c;
-};
-struct ilsm_map {
-  Map m;
-};
-struct ilsm_sc {
-  ScDb d;
-};
+
 
 extern "C" {
 

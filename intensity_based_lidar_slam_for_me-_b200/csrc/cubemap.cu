@@ -1,0 +1,552 @@
+// cubemap.cu -- device-resident rolling cube map of laserMapping.cpp: 21x21x11 cubes of 50 m (:70-78), window roll
+// (:330-565), 5x5x3 gather (:569-603), stack VoxelGrid (:608-616), guarded registration (:624-875), insertion of
+// the registered stack (:880-940) and per-cube VoxelGrid of the valid cubes (:987-1002).
+//
+// Layout: every cube owns a fixed slab of `cap` float4 {x,y,z,intensity} in one big allocation (180 GB of HBM make
+// 2 x 4851 x cap x 16 B a non-issue); the reference's array of cloud pointers becomes a host table
+// array index -> slab id that is rolled exactly like the pointers.  The map never leaves the GPU: per frame the
+// host uploads the two feature clouds and reads back the pose, the report and the per-cube counts.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "ilsm_host.hpp"
+#include "ilsm_voxel.cuh"
+
+namespace ilsm {
+
+constexpr int kCW = 21, kCH = 21, kCD = 11, kCNum = kCW * kCH * kCD;
+
+struct GatherItem {
+  int slab, offset, count;
+};
+
+__global__ void cube_gather_kernel(const float4* __restrict__ slabs, int cap, const GatherItem* __restrict__ items,
+                                   float4* __restrict__ out) {
+  const GatherItem it = items[blockIdx.y];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < it.count; t += gridDim.x * blockDim.x)
+    out[it.offset + t] = slabs[(size_t)it.slab * cap + t];
+}
+
+__global__ void cube_zero_counts_kernel(int* cnt, const int* __restrict__ slabs, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cnt[slabs[i]] = 0;
+}
+
+// laserMapping.cpp:886-896 (float coordinate widened to double, truncation, negative fix-up)
+__device__ __forceinline__ int cube_coord_dev(float v, int cen) {
+  const double s = (double)v + 25.0;
+  int c = __double2int_rz(s / 50.0) + cen;
+  if (s < 0) c--;
+  return c;
+}
+
+// first index of the sorted key array whose key is >= v
+__device__ __forceinline__ int lower_bound_key(const u64* keys, int P, u64 v) {
+  int lo = 0, hi = P;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Insertion of one stack (block 0: corner, block 1: surf): world transform with the pose held in LmState (or none
+// when the points are already in the world frame), cube index, then a stable grouping by cube -- keys
+// (cube index, stack position) sorted in shared memory -- so that every cube receives its new points in stack
+// order, as push_back does.
+__global__ void __launch_bounds__(1024)
+    cube_insert_kernel(const float4* __restrict__ stack_c, const float4* __restrict__ stack_s, const int* __restrict__ d_counts,
+                       int nc_host, int ns_host, const LmState* __restrict__ st, int world_frame, int cenW, int cenH, int cenD,
+                       const int* __restrict__ slab_of, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
+                       float4* __restrict__ world_tmp, int tmp_stride, int* err) {
+  extern __shared__ u64 keys[];
+  const bool corner = blockIdx.x == 0;
+  const float4* stack = corner ? stack_c : stack_s;
+  const int n = d_counts ? d_counts[corner ? 0 : 1] : (corner ? nc_host : ns_host);
+  float4* slabs = corner ? slabs_c : slabs_s;
+  int* cnt = corner ? cnt_c : cnt_s;
+  float4* wtmp = world_tmp + (size_t)blockIdx.x * tmp_stride;
+  if (n > kVoxelBlockMax) {
+    if (threadIdx.x == 0) atomicOr(err, 16);
+    return;
+  }
+  int P = 1;
+  while (P < n) P <<= 1;
+  const double q[4] = {st->xq[0], st->xq[1], st->xq[2], st->xq[3]};
+  const double tx = st->xt[0], ty = st->xt[1], tz = st->xt[2];
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    u64 key = ~0ull;
+    if (t < n) {
+      float4 p = stack[t];
+      if (!world_frame) {  // pointAssociateToMap (:152-161): double math, float store, intensity kept
+        const D3 pw = quat_rotate(q, d3((double)p.x, (double)p.y, (double)p.z));
+        p.x = __double2float_rn(dadd(pw.x, tx)), p.y = __double2float_rn(dadd(pw.y, ty)), p.z = __double2float_rn(dadd(pw.z, tz));
+      }
+      wtmp[t] = p;
+      const int cI = cube_coord_dev(p.x, cenW), cJ = cube_coord_dev(p.y, cenH), cK = cube_coord_dev(p.z, cenD);
+      if (cI >= 0 && cI < kCW && cJ >= 0 && cJ < kCH && cK >= 0 && cK < kCD)
+        key = ((u64)(cI + kCW * cJ + kCW * kCH * cK) << 24) | (uint32_t)t;
+    }
+    keys[t] = key;
+  }
+  __syncthreads();
+  bitonic_sort_smem(keys, P);
+  // run heads know their length by scanning forward; every element finds its rank as (position - run start)
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    const u64 k = keys[t];
+    if (k == ~0ull) continue;
+    const int cube = (int)(k >> 24);
+    const int start = lower_bound_key(keys, P, (u64)cube << 24);
+    const int slab = slab_of[cube];
+    const int base = cnt[slab];  // not modified until every thread is past this loop (the update is below)
+    const int pos = base + (t - start);
+    if (pos < cap)
+      slabs[(size_t)slab * cap + pos] = wtmp[(int)(k & 0xFFFFFF)];
+    else
+      atomicOr(err, 32);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    const u64 k = keys[t];
+    if (k == ~0ull) continue;
+    const int cube = (int)(k >> 24);
+    const bool head = t == 0 || (int)(keys[t - 1] >> 24) != cube;
+    if (head) {
+      const int len = lower_bound_key(keys, P, (u64)(cube + 1) << 24) - t;
+      const int slab = slab_of[cube];
+      const int nv = cnt[slab] + len;
+      cnt[slab] = nv < cap ? nv : cap;
+    }
+  }
+}
+
+// Per-cube VoxelGrid of the valid cubes: block (v, type) filters its slab into scratch and copies it back.
+__global__ void __launch_bounds__(1024)
+    cube_filter_kernel(const int* __restrict__ valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
+                       float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err) {
+  extern __shared__ u64 keys[];
+  const int v = blockIdx.x >> 1;
+  const bool corner = (blockIdx.x & 1) == 0;
+  const int slab = valid_slabs[v];
+  float4* pts = (corner ? slabs_c : slabs_s) + (size_t)slab * cap;
+  int* cnt = (corner ? cnt_c : cnt_s) + slab;
+  const int n = *cnt;
+  if (n <= 0) return;
+  if (n > kVoxelBlockMax) {
+    if (threadIdx.x == 0) atomicOr(err, 64);
+    return;
+  }
+  float4* out = scratch + (size_t)blockIdx.x * cap;
+  int P = 1;
+  while (P < n) P <<= 1;
+  const int m = voxelgrid_block(pts, n, corner ? leaf_c : leaf_s, keys, P, out, err);
+  __syncthreads();
+  for (int t = threadIdx.x; t < m; t += blockDim.x) pts[t] = out[t];
+  if (threadIdx.x == 0) *cnt = m;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct QuatH {
+  double x, y, z, w;
+};
+static QuatH qmul_h(const QuatH& a, const QuatH& b) {
+  return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+static void qrot_h(const QuatH& q, const double v[3], double o[3]) {  // Eigen _transformVector
+  const double ux = q.x, uy = q.y, uz = q.z;
+  double cx = uy * v[2] - uz * v[1], cy = uz * v[0] - ux * v[2], cz = ux * v[1] - uy * v[0];
+  cx += cx, cy += cy, cz += cz;
+  o[0] = (v[0] + q.w * cx) + (uy * cz - uz * cy);
+  o[1] = (v[1] + q.w * cy) + (uz * cx - ux * cz);
+  o[2] = (v[2] + q.w * cz) + (ux * cy - uy * cx);
+}
+
+struct CubeMapH {
+  Ctx* ctx = nullptr;
+  Map map_c, map_s;
+  int cap = 0;
+  float line_res = 0.4f, plane_res = 0.8f;
+  int cenW = 10, cenH = 10, cenD = 5;
+  QuatH q_wmap_wodom{0, 0, 0, 1};
+  double t_wmap_wodom[3] = {0, 0, 0};
+  std::vector<int> slab_of;           // array index -> slab id
+  std::vector<int> cnt_c_h, cnt_s_h;  // host mirror of the per-slab counts
+  int valid[125], n_valid = 0;
+  DevBuf<float4> slabs_c, slabs_s, from_c, from_s, stack_c, stack_s, scratch, world_tmp;
+  DevBuf<int> cnt_c, cnt_s, slab_of_d, stack_n, valid_d, err, zero_list;
+  DevBuf<GatherItem> items;
+  DevBuf<float> raw;
+  PinnedBuf<int> pin;
+
+  int init(Ctx* c, float lres, float pres, int cube_cap);
+  void release();
+  int roll(const double t[3]);
+  int gather(int* n_mc, int* n_ms);
+  int insert(const int* d_counts, int nc_host, int ns_host, int world_frame);
+  int filter_valid();
+  int fetch_counts();
+};
+
+int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
+  ctx = c;
+  cap = cube_cap;
+  line_res = lres, plane_res = pres;
+  int rc;
+  if ((rc = map_c.init(c)) || (rc = map_s.init(c))) return rc;
+  if ((rc = slabs_c.reserve((size_t)kCNum * cap)) || (rc = slabs_s.reserve((size_t)kCNum * cap)) ||
+      (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
+      (rc = stack_n.reserve(4)) || (rc = valid_d.reserve(128)) || (rc = err.reserve(4)) || (rc = items.reserve(256)) ||
+      (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) ||
+      (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)))
+    return rc;
+  slab_of.resize(kCNum);
+  for (int i = 0; i < kCNum; ++i) slab_of[i] = i;
+  cnt_c_h.assign(kCNum, 0), cnt_s_h.assign(kCNum, 0);
+  cudaStream_t s = c->stream;
+  ILSM_CUDA(cudaMemsetAsync(cnt_c.p, 0, kCNum * sizeof(int), s));
+  ILSM_CUDA(cudaMemsetAsync(cnt_s.p, 0, kCNum * sizeof(int), s));
+  ILSM_CUDA(cudaMemsetAsync(err.p, 0, 4 * sizeof(int), s));
+  ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
+  ILSM_CUDA(cudaFuncSetAttribute(cube_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kVoxelBlockMax * sizeof(u64))));
+  ILSM_CUDA(cudaFuncSetAttribute(cube_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kVoxelBlockMax * sizeof(u64))));
+  ILSM_CUDA(cudaStreamSynchronize(s));
+  return ILSM_OK;
+}
+
+void CubeMapH::release() {
+  if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+  map_c.release(), map_s.release();
+  slabs_c.release(), slabs_s.release(), from_c.release(), from_s.release(), stack_c.release(), stack_s.release();
+  scratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release();
+  valid_d.release(), err.release(), zero_list.release(), items.release(), raw.release(), pin.release();
+}
+
+static int cube_coord_h(double v, int cen) {
+  int c = int((v + 25.0) / 50.0) + cen;
+  if (v + 25.0 < 0) c--;
+  return c;
+}
+
+// laserMapping.cpp:330-565: keep the centre cube at least 3 cubes from every border by rolling the pointer grid
+int CubeMapH::roll(const double t[3]) {
+  auto at = [](int i, int j, int k) { return i + kCW * j + kCW * kCH * k; };
+  const int dims[3] = {kCW, kCH, kCD};
+  std::vector<int> recycled;
+  auto shift = [&](int axis, int dir) {
+    for (int a = 0; a < dims[(axis + 1) % 3]; ++a)
+      for (int b = 0; b < dims[(axis + 2) % 3]; ++b) {
+        auto idx = [&](int m) {
+          int ijk[3];
+          ijk[axis] = m, ijk[(axis + 1) % 3] = a, ijk[(axis + 2) % 3] = b;
+          return at(ijk[0], ijk[1], ijk[2]);
+        };
+        const int n = dims[axis];
+        if (dir > 0) {
+          const int last = slab_of[idx(n - 1)];
+          for (int m = n - 1; m >= 1; --m) slab_of[idx(m)] = slab_of[idx(m - 1)];
+          slab_of[idx(0)] = last;
+          recycled.push_back(last);
+        } else {
+          const int first = slab_of[idx(0)];
+          for (int m = 0; m < n - 1; ++m) slab_of[idx(m)] = slab_of[idx(m + 1)];
+          slab_of[idx(n - 1)] = first;
+          recycled.push_back(first);
+        }
+      }
+  };
+  int cI = cube_coord_h(t[0], cenW), cJ = cube_coord_h(t[1], cenH), cK = cube_coord_h(t[2], cenD);
+  while (cI < 3) shift(0, +1), cI++, cenW++;
+  while (cI >= kCW - 3) shift(0, -1), cI--, cenW--;
+  while (cJ < 3) shift(1, +1), cJ++, cenH++;
+  while (cJ >= kCH - 3) shift(1, -1), cJ--, cenH--;
+  while (cK < 3) shift(2, +1), cK++, cenD++;
+  while (cK >= kCD - 3) shift(2, -1), cK--, cenD--;
+  n_valid = 0;
+  for (int i = cI - 2; i <= cI + 2; i++)
+    for (int j = cJ - 2; j <= cJ + 2; j++)
+      for (int k = cK - 1; k <= cK + 1; k++)
+        if (i >= 0 && i < kCW && j >= 0 && j < kCH && k >= 0 && k < kCD) valid[n_valid++] = at(i, j, k);
+  cudaStream_t s = ctx->stream;
+  if (!recycled.empty()) {
+    // a recycled slab may be recycled again by a later shift of the same call: clear by final membership
+    for (int sl : recycled) cnt_c_h[sl] = 0, cnt_s_h[sl] = 0;
+    ILSM_CUDA(cudaStreamSynchronize(s));  // pinned staging reuse; rolls are rare (every ~50 m of travel)
+    int* p = pin.p;
+    const int n = (int)recycled.size() < kCNum ? (int)recycled.size() : kCNum;
+    for (int i = 0; i < n; ++i) p[i] = recycled[i];
+    ILSM_CUDA(cudaMemcpyAsync(zero_list.p, p, n * sizeof(int), cudaMemcpyHostToDevice, s));
+    cube_zero_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(cnt_c.p, zero_list.p, n);
+    cube_zero_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(cnt_s.p, zero_list.p, n);
+    ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
+    ILSM_CUDA(cudaStreamSynchronize(s));
+    count_launches(2);
+  }
+  return ILSM_OK;
+}
+
+// laserMapping.cpp:594-603: concatenate the valid cubes (i outer, j, k inner) into the two "FromMap" clouds
+int CubeMapH::gather(int* n_mc, int* n_ms) {
+  cudaStream_t s = ctx->stream;
+  int tot_c = 0, tot_s = 0;
+  GatherItem* it = reinterpret_cast<GatherItem*>(pin.p + kCNum);
+  for (int v = 0; v < n_valid; ++v) {
+    const int sl = slab_of[valid[v]];
+    it[v] = GatherItem{sl, tot_c, cnt_c_h[sl]};
+    it[125 + v] = GatherItem{sl, tot_s, cnt_s_h[sl]};
+    tot_c += cnt_c_h[sl], tot_s += cnt_s_h[sl];
+  }
+  *n_mc = tot_c, *n_ms = tot_s;
+  int rc;
+  if ((rc = from_c.reserve(tot_c + 4)) || (rc = from_s.reserve(tot_s + 4))) return rc;
+  if (n_valid == 0) return ILSM_OK;
+  ILSM_CUDA(cudaMemcpyAsync(items.p, it, 250 * sizeof(GatherItem), cudaMemcpyHostToDevice, s));
+  if (tot_c > 0) cube_gather_kernel<<<dim3(8, n_valid), 256, 0, s>>>(slabs_c.p, cap, items.p, from_c.p);
+  if (tot_s > 0) cube_gather_kernel<<<dim3(8, n_valid), 256, 0, s>>>(slabs_s.p, cap, items.p + 125, from_s.p);
+  count_launches(2);
+  return check_launch("cube_gather");
+}
+
+int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_frame) {
+  cudaStream_t s = ctx->stream;
+  cube_insert_kernel<<<2, 1024, kVoxelBlockMax * sizeof(u64), s>>>(stack_c.p, stack_s.p, d_counts, nc_host, ns_host, ctx->lm.p,
+                                                                    world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p,
+                                                                    slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p,
+                                                                    kVoxelBlockMax, err.p);
+  count_launches(1);
+  return check_launch("cube_insert");
+}
+
+int CubeMapH::filter_valid() {
+  if (n_valid == 0) return ILSM_OK;
+  cudaStream_t s = ctx->stream;
+  int* p = pin.p + kCNum + 1024;
+  for (int v = 0; v < n_valid; ++v) p[v] = slab_of[valid[v]];
+  ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
+  cube_filter_kernel<<<2 * n_valid, 1024, kVoxelBlockMax * sizeof(u64), s>>>(valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p,
+                                                                             cap, line_res, plane_res, scratch.p, err.p);
+  count_launches(1);
+  return check_launch("cube_filter");
+}
+
+// the host mirror of the counts (needed by the next gather and by the guard of :624)
+int CubeMapH::fetch_counts() {
+  cudaStream_t s = ctx->stream;
+  std::vector<int>& c = cnt_c_h;
+  ILSM_CUDA(cudaMemcpyAsync(c.data(), cnt_c.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ILSM_CUDA(cudaMemcpyAsync(cnt_s_h.data(), cnt_s.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
+  return ILSM_OK;
+}
+
+}  // namespace ilsm
+
+using namespace ilsm;
+
+struct ilsm_cubemap {
+  CubeMapH m;
+};
+
+extern "C" {
+
+ILSM_API int ilsm_cubemap_create(ilsm_ctx* ctx_, float line_res, float plane_res, int cube_capacity, ilsm_cubemap** out) {
+  Ctx* c = ctx_ ? &ctx_->c : nullptr;
+  if (!c || !out) return fail(ILSM_ERR_INVALID_ARG, "cubemap_create: null argument");
+  if (!(line_res > 0.f) || !(plane_res > 0.f)) return fail(ILSM_ERR_INVALID_ARG, "cubemap_create: bad resolution");
+  if (cube_capacity <= 0) cube_capacity = kVoxelBlockMax;
+  if (cube_capacity > kVoxelBlockMax) cube_capacity = kVoxelBlockMax;
+  ilsm_cubemap* h = new (std::nothrow) ilsm_cubemap();
+  if (!h) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  int rc = h->m.init(c, line_res, plane_res, cube_capacity);
+  if (rc) {
+    h->m.release();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return ILSM_OK;
+}
+
+ILSM_API void ilsm_cubemap_destroy(ilsm_cubemap* cm) {
+  if (!cm) return;
+  {
+    std::lock_guard<std::mutex> lk(cm->m.ctx->mu);
+    cudaSetDevice(cm->m.ctx->device);
+    cm->m.release();
+  }
+  delete cm;
+}
+
+static int stage_clouds(CubeMapH& m, const float* corner, int nc, const float* surf, int ns, int stride_bytes) {
+  // caller clouds -> packed float4 stacks on the device (raw staging + the VoxelGrid kernel's packing, or a plain
+  // strided copy when they are inserted as they are)
+  Ctx& c = *m.ctx;
+  const size_t bc = (size_t)nc * stride_bytes, bs = (size_t)ns * stride_bytes;
+  const size_t off_s = (bc + 255) & ~(size_t)255;
+  int rc;
+  if ((rc = m.raw.reserve((off_s + bs) / 4 + 64)) || (rc = m.stack_c.reserve(nc + 4)) || (rc = m.stack_s.reserve(ns + 4))) return rc;
+  char* base = reinterpret_cast<char*>(m.raw.p);
+  if (bc) ILSM_CUDA(cudaMemcpyAsync(base, corner, bc, cudaMemcpyHostToDevice, c.stream));
+  if (bs) ILSM_CUDA(cudaMemcpyAsync(base + off_s, surf, bs, cudaMemcpyHostToDevice, c.stream));
+  return ILSM_OK;
+}
+
+__global__ void pack_xyzi_kernel(const float* __restrict__ in, int n, int stride_f, int ioff, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = in + (size_t)i * stride_f;
+  out[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), ioff >= 0 ? __ldg(p + ioff) : 0.f);
+}
+
+ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, int nc, const float* surf, int ns, int stride_bytes,
+                                       const double centre[3]) {
+  if (!cm || !centre || (nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ILSM_ERR_INVALID_ARG, "cubemap_insert_world: null argument");
+  if (nc < 0 || ns < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "cubemap_insert_world: bad n/stride");
+  CubeMapH& m = cm->m;
+  Ctx& c = *m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  int rc;
+  if ((rc = m.roll(centre))) return rc;
+  const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
+  // large seeds are inserted in chunks of at most kVoxelBlockMax points per stack (the insert kernel sorts in smem)
+  const int chunk = kVoxelBlockMax;
+  for (int oc = 0, os = 0; oc < nc || os < ns; oc += chunk, os += chunk) {
+    const int kc = oc < nc ? (nc - oc < chunk ? nc - oc : chunk) : 0;
+    const int ks = os < ns ? (ns - os < chunk ? ns - os : chunk) : 0;
+    if ((rc = stage_clouds(m, kc ? corner + (size_t)oc * (stride_bytes / 4) : nullptr, kc,
+                           ks ? surf + (size_t)os * (stride_bytes / 4) : nullptr, ks, stride_bytes)))
+      return rc;
+    const size_t off_s = ((size_t)kc * stride_bytes + 255) & ~(size_t)255;
+    const float* d_c = m.raw.p;
+    const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
+    if (kc) pack_xyzi_kernel<<<(kc + 255) / 256, 256, 0, c.stream>>>(d_c, kc, stride_bytes / 4, ioff, m.stack_c.p);
+    if (ks) pack_xyzi_kernel<<<(ks + 255) / 256, 256, 0, c.stream>>>(d_s, ks, stride_bytes / 4, ioff, m.stack_s.p);
+    count_launches(2);
+    if ((rc = m.insert(nullptr, kc, ks, 1))) return rc;
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));  // staging buffers are reused by the next chunk
+  }
+  if ((rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
+  int* pin = m.pin.p + kCNum + 2048;
+  ILSM_CUDA(cudaMemcpyAsync(pin, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  if (pin[0]) return fail(ILSM_ERR_OUT_OF_MEMORY, "cube map: a cube exceeded its slab capacity");
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int nc, const float* surf_last, int ns, int stride_bytes,
+                                const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
+                                const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_cubemap_stats* stats) {
+  if (!cm || !q_wodom || !t_wodom || !q_w || !t_w || (nc > 0 && !corner_last) || (ns > 0 && !surf_last))
+    return fail(ILSM_ERR_INVALID_ARG, "cubemap_frame: null argument");
+  if (nc < 0 || ns < 0 || stride_bytes < 16 || stride_bytes % 4 || nc > kVoxelBlockMax || ns > kVoxelBlockMax)
+    return fail(ILSM_ERR_INVALID_ARG, "cubemap_frame: bad n/stride (at most 16384 points per feature cloud)");
+  CubeMapH& m = cm->m;
+  Ctx& c = *m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  ilsm_reg_opts o;
+  if (opts) o = *opts; else ilsm_reg_opts_default(&o);
+  if (report) memset(report, 0, sizeof(*report));
+  // transformAssociateToMap (laserMapping.cpp:138-142)
+  const QuatH qo{q_wodom[0], q_wodom[1], q_wodom[2], q_wodom[3]};
+  QuatH qw = qmul_h(m.q_wmap_wodom, qo);
+  double tw[3], r[3];
+  qrot_h(m.q_wmap_wodom, t_wodom, r);
+  for (int i = 0; i < 3; ++i) tw[i] = r[i] + m.t_wmap_wodom[i];
+  int rc;
+  if ((rc = m.roll(tw))) return rc;
+  int n_mc = 0, n_ms = 0;
+  if ((rc = m.gather(&n_mc, &n_ms))) return rc;
+  // stacks: VoxelGrid(line_res) / VoxelGrid(plane_res) of the incoming feature clouds (:608-616), sizes stay on the device
+  if ((rc = stage_clouds(m, corner_last, nc, surf_last, ns, stride_bytes))) return rc;
+  const size_t off_s = ((size_t)nc * stride_bytes + 255) & ~(size_t)255;
+  const float* d_c = m.raw.p;
+  const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
+  const int ioff = stride_bytes >= 32 ? 4 : 3;
+  ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
+  if (nc > 0 && (rc = c.voxelgrid_dev(d_c, nc, nullptr, 0, stride_bytes, ioff, m.line_res, m.stack_c.p, m.stack_n.p))) return rc;
+  if (ns > 0 && (rc = c.voxelgrid_dev(d_s, ns, nullptr, 0, stride_bytes, ioff, m.plane_res, m.stack_s.p, m.stack_n.p + 1))) return rc;
+  // pose in
+  double pose[7] = {qw.x, qw.y, qw.z, qw.w, tw[0], tw[1], tw[2]};
+  double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 1024);
+  for (int i = 0; i < 7; ++i) pin_pose[i] = pose[i];
+  ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  const bool optimise = n_mc > o.min_corner_map && n_ms > o.min_surf_map;  // laserMapping.cpp:624
+  if (optimise) {
+    if ((rc = m.map_c.build_dev(reinterpret_cast<const float*>(m.from_c.p), n_mc, 16, 0.f)) ||
+        (rc = m.map_s.build_dev(reinterpret_cast<const float*>(m.from_s.p), n_ms, 16, 0.f)))
+      return rc;
+    c.d_stack_counts = m.stack_n.p;
+    rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.stack_c.p), nc, reinterpret_cast<const float*>(m.stack_s.p),
+                        ns, 16, o);
+    c.d_stack_counts = nullptr;
+    if (rc) return rc;
+  }
+  // insertion with the optimised pose (still on the device) + per-cube VoxelGrid of the valid cubes
+  if ((rc = m.insert(m.stack_n.p, 0, 0, 0)) || (rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
+  unsigned char* pin = c.pinned.p;
+  int* pin_i = m.pin.p + kCNum + 2048;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin_i, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const double* out = reinterpret_cast<const double*>(pin);
+  for (int i = 0; i < 4; ++i) q_w[i] = out[i];
+  for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
+  if (report && optimise) {
+    memcpy(report, pin + 64, sizeof(*report));
+    report->passes = o.outer_iterations;
+  }
+  // transformUpdate (laserMapping.cpp:145-149)
+  const QuatH qwf{q_w[0], q_w[1], q_w[2], q_w[3]};
+  const double n2 = qo.x * qo.x + qo.y * qo.y + qo.z * qo.z + qo.w * qo.w;
+  const QuatH qinv{-qo.x / n2, -qo.y / n2, -qo.z / n2, qo.w / n2};
+  m.q_wmap_wodom = qmul_h(qwf, qinv);
+  qrot_h(m.q_wmap_wodom, t_wodom, r);
+  for (int i = 0; i < 3; ++i) m.t_wmap_wodom[i] = t_w[i] - r[i];
+  if (stats) {
+    stats->n_map_corner = n_mc, stats->n_map_surf = n_ms;
+    stats->n_stack_corner = pin_i[1], stats->n_stack_surf = pin_i[2];
+    stats->ran_optimization = optimise ? 1 : 0;
+    stats->n_valid = m.n_valid;
+    stats->cen[0] = m.cenW, stats->cen[1] = m.cenH, stats->cen[2] = m.cenD;
+    stats->flags = pin_i[0];
+  }
+  if (pin_i[0]) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cube map: capacity exceeded (flags 0x%x: 16 stack>16384, 32 cube slab full, 64 cube>16384, 2 leaf too small)", pin_i[0]);
+    cudaMemsetAsync(m.err.p, 0, sizeof(int), c.stream);
+    return fail(ILSM_ERR_OUT_OF_MEMORY, msg);
+  }
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out) {
+  if (!cm || !n_out || cube_index < 0 || cube_index >= kCNum || (which != 0 && which != 1))
+    return fail(ILSM_ERR_INVALID_ARG, "cubemap_cube: bad argument");
+  CubeMapH& m = cm->m;
+  std::lock_guard<std::mutex> lk(m.ctx->mu);
+  ILSM_CUDA(cudaSetDevice(m.ctx->device));
+  const int sl = m.slab_of[cube_index];
+  const int n = which == 0 ? m.cnt_c_h[sl] : m.cnt_s_h[sl];
+  *n_out = n;
+  const int k = n < capacity ? n : capacity;
+  if (k > 0 && out_xyzi) {
+    ILSM_CUDA(cudaStreamSynchronize(m.ctx->stream));
+    ILSM_CUDA(cudaMemcpy(out_xyzi, (which == 0 ? m.slabs_c.p : m.slabs_s.p) + (size_t)sl * m.cap, (size_t)k * 16,
+                         cudaMemcpyDeviceToHost));
+  }
+  return ILSM_OK;
+}
+
+}  // extern "C"

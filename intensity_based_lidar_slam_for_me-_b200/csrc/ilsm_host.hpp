@@ -168,6 +168,7 @@ struct Ctx {
   PinnedBuf<unsigned char> pinned;
   FactorBufs fac;
   FeBufs fe;
+  const int* d_stack_counts = nullptr;  // when set, associate/solve read {nc, ns} from the device (cube-map path)
   size_t partial_blocks = 0;
 
   int init(int dev);
@@ -207,3 +208,14 @@ struct ScDb {
 };
 
 }  // namespace ilsm
+
+// the opaque handles of include/ilsm.h
+struct ilsm_ctx {
+  ilsm::Ctx c;
+};
+struct ilsm_map {
+  ilsm::Map m;
+};
+struct ilsm_sc {
+  ilsm::ScDb d;
+};

@@ -187,8 +187,10 @@ constexpr int kAssocThreads = 128;
 // One warp per stack point (grid-stride when the stacks exceed one resident wave).
 __global__ void __launch_bounds__(kAssocThreads, 5)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
-                     int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv) {
+                     int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv,
+                     const int* __restrict__ d_counts) {
   __shared__ WarpScratch scratch[kAssocThreads / 32];
+  if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * (kAssocThreads / 32);
   // everything that does not depend on the point is fetched up front so that the latencies overlap
@@ -802,8 +804,9 @@ struct SolveParams {
 };
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThreads, 1)
-    solve_cluster_kernel(FactorView fv, int n, LmState* st, SolveParams prm) {
+    solve_cluster_kernel(FactorView fv, int n, LmState* st, SolveParams prm, const int* __restrict__ d_counts) {
   __shared__ double core[kCoreWords];
+  if (d_counts) n = d_counts[0] + d_counts[1];
   __shared__ double red[kSolveThreads / 32][kSumStride];
   __shared__ double part[2][kSumStride];
   __shared__ double tot[kSumStride];
@@ -984,7 +987,8 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   // one warp per stack point, capped at one resident wave (5 blocks x 4 warps per SM at this register budget)
   long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
   if (blocks > cap) blocks = cap;
-  associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p, prm, fv);
+  associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p, prm, fv,
+                                                                   d_stack_counts);
   count_launches(1);
   return check_launch("associate");
 }
@@ -1026,7 +1030,7 @@ int Ctx::solve_launch(int max_iter, double huber_a, int pass) {
   prm.arm = 1;
   prm.huber_a = huber_a;
   FactorView fv = factor_view(fac, false);
-  solve_cluster_kernel<<<kClusterSize, kSolveThreads, 0, stream>>>(fv, fac.n, lm.p, prm);
+  solve_cluster_kernel<<<kClusterSize, kSolveThreads, 0, stream>>>(fv, fac.n, lm.p, prm, d_stack_counts);
   count_launches(1);
   return check_launch("solve");
 }

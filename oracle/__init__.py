@@ -333,3 +333,60 @@ def ikd_add_points(existing_xyz, add_xyz, ds, downsample=True):
     out = np.zeros((len(e) + len(a) + 1, 3), np.float32)
     n = lib().orc_ikd_add_points(_p(e), len(e), _p(a), len(a), C.c_float(ds), 1 if downsample else 0, _p(out), len(out))
     return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# laserMapping rolling cube map
+# ------------------------------------------------------------------------------------------------
+class CubeFrameStats(C.Structure):
+    _fields_ = [("n_map_corner", C.c_int32), ("n_map_surf", C.c_int32), ("n_stack_corner", C.c_int32),
+                ("n_stack_surf", C.c_int32), ("ran_optimization", C.c_int32), ("n_valid", C.c_int32),
+                ("cen", C.c_int32 * 3), ("pad", C.c_int32)]
+
+
+class CubeMap:
+    """laserMapping.cpp process() hot section (rolling 21x21x11 cube map + guarded registration + insertion)."""
+
+    def __init__(self, line_res=0.4, plane_res=0.8):
+        l = lib()
+        l.orc_cubemap_create.restype = C.c_void_p
+        l.orc_cubemap_create.argtypes = [C.c_float, C.c_float]
+        l.orc_cubemap_destroy.argtypes = [C.c_void_p]
+        l.orc_cubemap_insert_world.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        l.orc_cubemap_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+        l.orc_cubemap_cube.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self._l = l
+        self._h = l.orc_cubemap_create(line_res, plane_res)
+
+    def __del__(self):
+        try:
+            self._l.orc_cubemap_destroy(self._h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _x4(a):
+        a = np.asarray(a, np.float32)
+        out = np.zeros((len(a), 4), np.float32)
+        out[:, :min(4, a.shape[1])] = a[:, :4]
+        return out
+
+    def insert_world(self, corner, surf, centre):
+        c, s = self._x4(corner), self._x4(surf)
+        ctr = np.ascontiguousarray(centre, np.float64)
+        self._l.orc_cubemap_insert_world(self._h, _p(c), len(c), _p(s), len(s), _p(ctr))
+
+    def frame(self, corner_last, surf_last, qt_odom):
+        c, s = self._x4(corner_last), self._x4(surf_last)
+        qo = np.ascontiguousarray(qt_odom, np.float64)
+        out = np.zeros(7)
+        sums = (SolveSummary * 2)()
+        st = CubeFrameStats()
+        self._l.orc_cubemap_frame(self._h, _p(c), len(c), _p(s), len(s), _p(qo), _p(out), sums, C.byref(st))
+        return out, list(sums), st
+
+    def cube(self, which, index, cap=1 << 16):
+        out = np.zeros((cap, 4), np.float32)
+        n = self._l.orc_cubemap_cube(self._h, which, index, _p(out), cap)
+        return out[:n].copy()

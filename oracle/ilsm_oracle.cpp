@@ -970,3 +970,169 @@ ORC_API int orc_ikd_add_points(const float* existing, int n_old, const float* ad
   for (int i = 0; i < n && i < out_cap; ++i) out_xyz[3 * i] = pts[i].x, out_xyz[3 * i + 1] = pts[i].y, out_xyz[3 * i + 2] = pts[i].z;
   return n;
 }
+
+// ================================================================================================
+// laserMapping.cpp process(): rolling 21x21x11 map of 50 m cubes (:330-606), stack VoxelGrid (:608-616),
+// guarded registration (:624-875), insertion (:880-940, once -- the fork's duplicated surf insert :951-979 is a
+// defect, upstream A-LOAM inserts once) and per-cube VoxelGrid of the valid cubes (:987-1002).
+// ================================================================================================
+extern "C" int orc_voxelgrid(const float* in, int n, int stride_bytes, int ioff, float leaf, float* out_xyzi);
+
+namespace {
+struct CubeMap {
+  static constexpr int W = 21, H = 21, D = 11, NUM = W * H * D;
+  int cenW = 10, cenH = 10, cenD = 5;
+  float line_res = 0.4f, plane_res = 0.8f;
+  std::vector<std::vector<float>> corner, surf;  // per cube, packed xyzi
+  Quat q_wmap_wodom{0, 0, 0, 1};
+  V3 t_wmap_wodom{0, 0, 0};
+  int valid[125], n_valid = 0;
+  CubeMap() : corner(NUM), surf(NUM) {}
+
+  static int cube_coord(double v, int cen) {
+    int c = int((v + 25.0) / 50.0) + cen;
+    if (v + 25.0 < 0) c--;
+    return c;
+  }
+  template <class F>
+  void shift(int axis, int dir, F&& at) {
+    // dir = +1: contents move towards higher index along `axis` (centre too low), the lowest slab is cleared
+    const int n[3] = {W, H, D};
+    for (int a = 0; a < n[(axis + 1) % 3]; ++a)
+      for (int b = 0; b < n[(axis + 2) % 3]; ++b) {
+        auto idx = [&](int m) {
+          int ijk[3];
+          ijk[axis] = m, ijk[(axis + 1) % 3] = a, ijk[(axis + 2) % 3] = b;
+          return at(ijk[0], ijk[1], ijk[2]);
+        };
+        if (dir > 0) {
+          std::vector<float> lastC = std::move(corner[idx(n[axis] - 1)]), lastS = std::move(surf[idx(n[axis] - 1)]);
+          for (int m = n[axis] - 1; m >= 1; --m) corner[idx(m)] = std::move(corner[idx(m - 1)]), surf[idx(m)] = std::move(surf[idx(m - 1)]);
+          lastC.clear(), lastS.clear();
+          corner[idx(0)] = std::move(lastC), surf[idx(0)] = std::move(lastS);
+        } else {
+          std::vector<float> firstC = std::move(corner[idx(0)]), firstS = std::move(surf[idx(0)]);
+          for (int m = 0; m < n[axis] - 1; ++m) corner[idx(m)] = std::move(corner[idx(m + 1)]), surf[idx(m)] = std::move(surf[idx(m + 1)]);
+          firstC.clear(), firstS.clear();
+          corner[idx(n[axis] - 1)] = std::move(firstC), surf[idx(n[axis] - 1)] = std::move(firstS);
+        }
+      }
+  }
+  void roll(const V3& t) {
+    auto at = [](int i, int j, int k) { return i + W * j + W * H * k; };
+    int cI = cube_coord(t.x, cenW), cJ = cube_coord(t.y, cenH), cK = cube_coord(t.z, cenD);
+    while (cI < 3) shift(0, +1, at), cI++, cenW++;
+    while (cI >= W - 3) shift(0, -1, at), cI--, cenW--;
+    while (cJ < 3) shift(1, +1, at), cJ++, cenH++;
+    while (cJ >= H - 3) shift(1, -1, at), cJ--, cenH--;
+    while (cK < 3) shift(2, +1, at), cK++, cenD++;
+    while (cK >= D - 3) shift(2, -1, at), cK--, cenD--;
+    n_valid = 0;
+    for (int i = cI - 2; i <= cI + 2; i++)
+      for (int j = cJ - 2; j <= cJ + 2; j++)
+        for (int k = cK - 1; k <= cK + 1; k++)
+          if (i >= 0 && i < W && j >= 0 && j < H && k >= 0 && k < D) valid[n_valid++] = i + W * j + W * H * k;
+  }
+  void insert(std::vector<std::vector<float>>& arr, const float* pw /*xyzi*/) {
+    const int cI = cube_coord(pw[0], cenW), cJ = cube_coord(pw[1], cenH), cK = cube_coord(pw[2], cenD);
+    if (cI >= 0 && cI < W && cJ >= 0 && cJ < H && cK >= 0 && cK < D) {
+      auto& v = arr[cI + W * cJ + W * H * cK];
+      v.insert(v.end(), pw, pw + 4);
+    }
+  }
+  void filter_valid() {
+    std::vector<float> tmp;
+    for (int v = 0; v < n_valid; ++v)
+      for (int pass = 0; pass < 2; ++pass) {
+        auto& c = pass == 0 ? corner[valid[v]] : surf[valid[v]];
+        if (c.empty()) continue;
+        tmp.resize(c.size());
+        const int m = orc_voxelgrid(c.data(), (int)c.size() / 4, 16, 3, pass == 0 ? line_res : plane_res, tmp.data());
+        c.assign(tmp.begin(), tmp.begin() + 4 * (size_t)m);
+      }
+  }
+};
+}  // namespace
+
+struct OrcCubeFrameStats {
+  int32_t n_map_corner, n_map_surf, n_stack_corner, n_stack_surf, ran_optimization, n_valid;
+  int32_t cen[3];
+  int32_t pad;
+};
+
+ORC_API void* orc_cubemap_create(float line_res, float plane_res) {
+  CubeMap* m = new CubeMap();
+  m->line_res = line_res, m->plane_res = plane_res;
+  return m;
+}
+ORC_API void orc_cubemap_destroy(void* h) { delete static_cast<CubeMap*>(h); }
+
+// seed / direct insertion of WORLD-frame points (xyzi packed), then filter the cubes around `centre`
+ORC_API void orc_cubemap_insert_world(void* h, const float* corner, int nc, const float* surf, int ns, const double centre[3]) {
+  CubeMap& m = *static_cast<CubeMap*>(h);
+  m.roll(V3{centre[0], centre[1], centre[2]});
+  for (int i = 0; i < nc; ++i) m.insert(m.corner, corner + 4 * (size_t)i);
+  for (int i = 0; i < ns; ++i) m.insert(m.surf, surf + 4 * (size_t)i);
+  m.filter_valid();
+}
+
+// one process() iteration.  corner_last / surf_last: sensor-frame less-sharp / less-flat clouds (xyzi packed);
+// qt_odom: q_wodom_curr, t_wodom_curr; qt_out: q_w_curr, t_w_curr after the update.
+ORC_API void orc_cubemap_frame(void* h, const float* corner_last, int nc, const float* surf_last, int ns, const double qt_odom[7],
+                               double qt_out[7], OrcSolveSummary* summaries, OrcCubeFrameStats* st) {
+  CubeMap& m = *static_cast<CubeMap*>(h);
+  const Quat q_wodom{qt_odom[0], qt_odom[1], qt_odom[2], qt_odom[3]};
+  const V3 t_wodom{qt_odom[4], qt_odom[5], qt_odom[6]};
+  // transformAssociateToMap (:138-142)
+  Quat q_w = qmul(m.q_wmap_wodom, q_wodom);
+  V3 t_w = rotate(m.q_wmap_wodom, t_wodom) + m.t_wmap_wodom;
+  m.roll(t_w);
+  std::vector<float> map_c, map_s;
+  for (int v = 0; v < m.n_valid; ++v) {
+    map_c.insert(map_c.end(), m.corner[m.valid[v]].begin(), m.corner[m.valid[v]].end());
+    map_s.insert(map_s.end(), m.surf[m.valid[v]].begin(), m.surf[m.valid[v]].end());
+  }
+  std::vector<float> stack_c((size_t)4 * std::max(nc, 1)), stack_s((size_t)4 * std::max(ns, 1));
+  const int nsc = nc ? orc_voxelgrid(corner_last, nc, 16, 3, m.line_res, stack_c.data()) : 0;
+  const int nss = ns ? orc_voxelgrid(surf_last, ns, 16, 3, m.plane_res, stack_s.data()) : 0;
+  std::memset(st, 0, sizeof(*st));
+  st->n_map_corner = (int)map_c.size() / 4, st->n_map_surf = (int)map_s.size() / 4;
+  st->n_stack_corner = nsc, st->n_stack_surf = nss, st->n_valid = m.n_valid;
+  double qt[7] = {q_w.x, q_w.y, q_w.z, q_w.w, t_w.x, t_w.y, t_w.z};
+  if (st->n_map_corner > 10 && st->n_map_surf > 50) {
+    int32_t nfac[4];
+    orc_register_aloam(map_c.data(), st->n_map_corner, map_s.data(), st->n_map_surf, 16, stack_c.data(), nsc, stack_s.data(),
+                       nss, 16, qt, 2, 4, summaries, nfac);
+    st->ran_optimization = 1;
+  }
+  q_w = Quat{qt[0], qt[1], qt[2], qt[3]};
+  t_w = V3{qt[4], qt[5], qt[6]};
+  // transformUpdate (:145-149): q_wmap_wodom = q_w * q_wodom^-1 ; t_wmap_wodom = t_w - q_wmap_wodom * t_wodom
+  const double n2 = q_wodom.x * q_wodom.x + q_wodom.y * q_wodom.y + q_wodom.z * q_wodom.z + q_wodom.w * q_wodom.w;
+  const Quat q_inv{-q_wodom.x / n2, -q_wodom.y / n2, -q_wodom.z / n2, q_wodom.w / n2};
+  m.q_wmap_wodom = qmul(q_w, q_inv);
+  m.t_wmap_wodom = t_w - rotate(m.q_wmap_wodom, t_wodom);
+  // insertion of the stack points in the world frame (pointAssociateToMap keeps the intensity)
+  for (int pass = 0; pass < 2; ++pass) {
+    const std::vector<float>& stck = pass == 0 ? stack_c : stack_s;
+    const int n = pass == 0 ? nsc : nss;
+    for (int i = 0; i < n; ++i) {
+      float pw[4];
+      associate_to_map(q_w, t_w, &stck[4 * (size_t)i], pw);
+      pw[3] = stck[4 * (size_t)i + 3];
+      m.insert(pass == 0 ? m.corner : m.surf, pw);
+    }
+  }
+  m.filter_valid();
+  for (int i = 0; i < 7; ++i) qt_out[i] = qt[i];
+  st->cen[0] = m.cenW, st->cen[1] = m.cenH, st->cen[2] = m.cenD;
+}
+
+// contents of one cube (array index) of the current window; returns the point count
+ORC_API int orc_cubemap_cube(void* h, int which /*0 corner, 1 surf*/, int cube_index, float* out_xyzi, int cap) {
+  CubeMap& m = *static_cast<CubeMap*>(h);
+  const auto& v = which == 0 ? m.corner[cube_index] : m.surf[cube_index];
+  const int n = (int)v.size() / 4;
+  for (int i = 0; i < n && i < cap; ++i) std::memcpy(out_xyzi + 4 * (size_t)i, &v[4 * (size_t)i], 16);
+  return n;
+}
