@@ -84,6 +84,10 @@ ILSM_API int ilsm_map_size(const ilsm_map* map);
  *           ikdtree->Build(points)                                                mapOptimization.cpp:192 */
 ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell);
 ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int stride_bytes, float cell);
+/* Builds run on the map's own stream (the corner and surf structures of a frame are built concurrently); every entry
+ * point that uses a map orders itself after its build.  ilsm_map_join makes the CONTEXT stream wait for the build
+ * without using the map (for CUDA-event timing of the build on the context stream). */
+ILSM_API int ilsm_map_join(ilsm_map* map);
 
 /* Incremental insertion.
  *   ILSM_INSERT_NEAREST_TO_CENTRE: ikd-Tree's down-sampled insertion -- per cubic box of edge `leaf` around each new
@@ -197,6 +201,10 @@ ILSM_API long long ilsm_launch_count(void);
 ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q_xyzw[4], const double t_xyz[3], double huber_a, double* cost,
                         double JtJ[36], double Jtr[6]);
 
+/* Device-resident variant for timing the J^T J kernel alone: pose from d_pose7, the 28 sums {cost, 21 upper-triangle
+ * J^T J entries (row-major), 6 J^T r entries} written to d_out32 (32 doubles); no synchronisation. */
+ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, double huber_a, double* d_out32);
+
 /* ceres::Solve(options, &problem, &summary) over the factors held by the context (Levenberg-Marquardt,
  * trust-region loop run on the device, one kernel per iteration).
  * Replaces: laserMapping.cpp:836-850 ; mapOptimization.cpp:433-442 ; laserOdometry.cpp:705-710. */
@@ -239,6 +247,35 @@ ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int 
 
 /* Copy one cube (array index i + 21*j + 441*k of the current window; which = 0 corner, 1 surf) to the host. */
 ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out);
+
+/* --------------------------------------------- full per-frame loop: scanRegistration -> laserOdometry -> laserMapping ---- */
+typedef struct ilsm_slam ilsm_slam;
+
+typedef struct ilsm_slam_stats {
+  int32_t n_cloud, n_sharp, n_less_sharp, n_flat, n_less_flat; /* sizes of the five clouds scanRegistration publishes */
+  int32_t ran_odometry;        /* 0 on the first frame (systemInited) and when use_aloam == 0 */
+  ilsm_reg_report odometry;    /* the two ceres::Solve summaries of laserOdometry.cpp:705-710 */
+  ilsm_reg_report mapping;     /* those of laserMapping.cpp:836-850 */
+  ilsm_cubemap_stats cubemap;
+} ilsm_slam_stats;
+
+/* The three LOAM nodes of the reference chained on one GPU with the inter-node topics kept in HBM.  line_res / plane_res
+ * = mapping_line_resolution / mapping_plane_resolution (spot.launch:4-5), min_range = MINIMUM_RANGE (scanRegistration),
+ * cube_capacity as in ilsm_cubemap_create. */
+ILSM_API int ilsm_slam_create(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                              ilsm_slam** out);
+ILSM_API void ilsm_slam_destroy(ilsm_slam* slam);
+/* The cube map owned by the pipeline (for ilsm_cubemap_cube / ilsm_cubemap_insert_world). */
+ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam);
+
+/* One LiDAR frame through the whole loop: laserCloudHandler (scanRegistration.cpp:189-669), the laserOdometry iteration
+ * (laserOdometry.cpp:376-845: 2 x (association + Solve) from the previous q/t_last_curr when use_aloam != 0 -- the
+ * fork runs it only on frames flagged "skip_intensity", :406-417 -- then t_w_curr += q_w_curr * t_last_curr,
+ * q_w_curr *= q_last_curr and the swap of the "last" clouds / trees), and the laserMapping iteration (ilsm_cubemap_frame
+ * with the less-sharp / less-flat clouds).  Returns the odometry pose (/laser_odom_to_init) and the mapped pose
+ * (/aft_mapped_to_init).  Replaces: the three node bodies between /os_cloud_node/points and /aft_mapped_to_init. */
+ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom_xyzw[4],
+                             double t_odom[3], double q_map_xyzw[4], double t_map[3], ilsm_slam_stats* stats);
 
 /* ------------------------------------------------------------------- scan-to-scan odometry (laserOdometry) ---- */
 
@@ -335,6 +372,12 @@ ILSM_API int ilsm_sc_query_topk_dev(ilsm_sc* sc, const float* d_desc_20x60, int 
 /* Host-side deterministic merge of gathered per-shard top-k lists (n_entries = shards * k). */
 ILSM_API int ilsm_sc_merge_topk(const double* dist, const int32_t* id, const int32_t* shift, int n_entries, int k,
                                 double* out_dist, int32_t* out_id, int32_t* out_shift);
+
+/* The same merge on the device, for the all-gathered buffer of a sharded query (no host round trip between the
+ * scoring kernels, the NCCL all-gather and the merge).  Packed layout per shard and for the output:
+ * k x f64 distance | k x i32 id | k x i32 shift (16 k bytes); ilsm_sc_query_topk_dev can write it directly with
+ * d_dist = base, d_id = base + 8 k, d_shift = base + 12 k. */
+ILSM_API int ilsm_sc_merge_topk_dev(ilsm_sc* sc, const void* d_packed, int shards, int k, void* d_out_packed);
 
 #ifdef __cplusplus
 }

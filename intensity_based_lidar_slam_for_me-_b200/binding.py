@@ -59,6 +59,12 @@ class CubeMapStats(C.Structure):
                 ("cen", C.c_int32 * 3), ("flags", C.c_int32)]
 
 
+class SlamStats(C.Structure):
+    _fields_ = [("n_cloud", C.c_int32), ("n_sharp", C.c_int32), ("n_less_sharp", C.c_int32), ("n_flat", C.c_int32),
+                ("n_less_flat", C.c_int32), ("ran_odometry", C.c_int32), ("odometry", RegReport), ("mapping", RegReport),
+                ("cubemap", CubeMapStats)]
+
+
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
 _lib = None
@@ -87,6 +93,7 @@ def load_library(path: str | None = None):
         "ilsm_map_size": (i32, [vp]),
         "ilsm_map_build": (i32, [vp, vp, i32, i32, f32]),
         "ilsm_map_build_dev": (i32, [vp, vp, i32, i32, f32]),
+        "ilsm_map_join": (i32, [vp]),
         "ilsm_knn": (i32, [vp, vp, i32, i32, i32, f32, vp, vp]),
         "ilsm_map_insert": (i32, [vp, vp, i32, i32, i32, f32]),
         "ilsm_map_points": (i32, [vp, vp, i32, C.POINTER(i32)]),
@@ -107,6 +114,7 @@ def load_library(path: str | None = None):
         "ilsm_sc_add_dev": (i32, [vp, vp, i32]),
         "ilsm_sc_query_topk": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_query_topk_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "ilsm_sc_merge_topk_dev": (i32, [vp, vp, i32, i32, vp]),
         "ilsm_sc_merge_topk": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
         "ilsm_odometry": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport), vp]),
         "ilsm_cubemap_create": (i32, [vp, f32, f32, i32, C.POINTER(vp)]),
@@ -115,9 +123,14 @@ def load_library(path: str | None = None):
         "ilsm_cubemap_frame": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport),
                                      C.POINTER(CubeMapStats)]),
         "ilsm_cubemap_cube": (i32, [vp, i32, i32, vp, i32, C.POINTER(i32)]),
+        "ilsm_slam_create": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
+        "ilsm_slam_destroy": (None, [vp]),
+        "ilsm_slam_cubemap": (vp, [vp]),
+        "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
+        "ilsm_eval_normal_eq_dev": (i32, [vp, vp, f64, vp]),
         "ilsm_solve": (i32, [vp, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
     }
     for name, (res, args) in sig.items():
@@ -298,6 +311,9 @@ class Context:
         _check(self._lib.ilsm_eval_normal_eq(self._h, _ptr(qq), _ptr(tt), huber_a, C.byref(cost), _ptr(H), _ptr(g)))
         return cost.value, H, g
 
+    def eval_normal_eq_dev(self, d_pose_ptr, d_out32_ptr, huber_a=0.1):
+        _check(self._lib.ilsm_eval_normal_eq_dev(self._h, d_pose_ptr, huber_a, d_out32_ptr))
+
     def solve(self, q, t, max_num_iterations=4, huber_a=0.1):
         qq = np.array(q, np.float64)
         tt = np.array(t, np.float64)
@@ -341,6 +357,10 @@ class LocalMap:
 
     def build_dev(self, d_ptr: int, n: int, stride: int, cell: float = 0.0):
         _check(self._lib.ilsm_map_build_dev(self._h, d_ptr, n, stride, cell))
+        return self
+
+    def join(self):
+        _check(self._lib.ilsm_map_join(self._h))
         return self
 
     # ikdtree->Add_Points(points, downsample_on)  (mapOptimization.cpp:475; ikd_Tree.cpp:570-640)
@@ -430,6 +450,14 @@ class ScanContextDb:
                                                 d_shift_ptr))
 
 
+    def query_packed_dev(self, d_desc_ptr, k, n_search, id_offset, d_packed_ptr):
+        """Local top-k written in the packed all-gather layout (k f64 dist | k i32 id | k i32 shift)."""
+        self.query_topk_dev(d_desc_ptr, k, n_search, id_offset, d_packed_ptr, d_packed_ptr + 8 * k, d_packed_ptr + 12 * k)
+
+    def merge_packed_dev(self, d_gathered_ptr, shards, k, d_out_packed_ptr):
+        _check(self._lib.ilsm_sc_merge_topk_dev(self._h, d_gathered_ptr, shards, k, d_out_packed_ptr))
+
+
 class CubeMap:
     """ilsm_cubemap: the device-resident rolling 21x21x11 cube map of laserMapping.cpp and one process() iteration per
     frame() call (transformAssociateToMap -> roll -> gather -> stack VoxelGrid -> guarded registration ->
@@ -476,9 +504,54 @@ class CubeMap:
                                             _ptr(tw), C.byref(opts) if opts is not None else None, C.byref(rep), C.byref(st)))
         return qw, tw, rep, st
 
-    def cube(self, which: int, index: int):
+    @staticmethod
+    def _cube_of(lib, h, which, index):
         n = C.c_int(0)
-        _check(self._lib.ilsm_cubemap_cube(self._h, which, index, None, 0, C.byref(n)))
+        _check(lib.ilsm_cubemap_cube(h, which, index, None, 0, C.byref(n)))
         out = np.empty((max(n.value, 1), 4), np.float32)
-        _check(self._lib.ilsm_cubemap_cube(self._h, which, index, _ptr(out), n.value, C.byref(n)))
+        _check(lib.ilsm_cubemap_cube(h, which, index, _ptr(out), n.value, C.byref(n)))
         return out[:n.value]
+
+    def cube(self, which: int, index: int):
+        return self._cube_of(self._lib, self._h, which, index)
+
+
+class Slam:
+    """ilsm_slam: scanRegistration -> laserOdometry -> laserMapping for one frame per call, inter-node clouds resident on
+    the GPU.  frame() returns (q_odom, t_odom, q_map, t_map, stats)."""
+
+    def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.8, min_range: float = 0.3,
+                 cube_capacity: int = 0):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_slam_create(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_slam_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cubemap(self) -> "CubeMap":
+        """Non-owning view of the pipeline's cube map."""
+        cm = CubeMap.__new__(CubeMap)
+        cm._ctx, cm._lib = self._ctx, self._lib
+        cm._h = None
+        cm._view = C.c_void_p(self._lib.ilsm_slam_cubemap(self._h))
+        cm.cube = lambda which, index, _cm=cm: CubeMap._cube_of(_cm._lib, _cm._view, which, index)
+        return cm
+
+    def frame(self, cloud, use_aloam: bool = True):
+        a, n, stride = _cloud(cloud)
+        qo, to, qm, tm = np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3)
+        st = SlamStats()
+        _check(self._lib.ilsm_slam_frame(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
+                                         _ptr(tm), C.byref(st)))
+        return qo, to, qm, tm, st

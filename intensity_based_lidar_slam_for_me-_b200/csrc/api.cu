@@ -32,6 +32,7 @@ int check_launch(const char* where) {
 
 int eval_only_launch(Ctx* c, double* d_out);
 int factors_export(Ctx* c, ilsm_factor* d_out);
+int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out);
 
 struct Pose7 {
   double v[7];
@@ -45,6 +46,14 @@ __global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double
     for (int i = 0; i < 3; ++i) st->ct[i] = p.v[4 + i];
     st->huber_a = huber_a;
   }
+}
+
+// candidate pose <- device pose (ilsm_eval_normal_eq_dev)
+__global__ void set_pose_dev_kernel(LmState* st, const double* __restrict__ pose7, double huber_a) {
+  const int i = threadIdx.x;
+  if (i < 4) st->cq[i] = pose7[i];
+  if (i >= 4 && i < 7) st->ct[i - 4] = pose7[i];
+  if (i == 7) st->huber_a = huber_a;
 }
 
 __global__ void pose_io_kernel(LmState* st, double* pose7, ilsm_reg_report* report, int direction) {
@@ -234,6 +243,14 @@ ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int st
   std::lock_guard<std::mutex> lk(map->m.ctx->mu);
   ILSM_CUDA(cudaSetDevice(map->m.ctx->device));
   return map->m.build_dev(d_xyz, n, stride_bytes, cell);
+}
+
+ILSM_API int ilsm_map_join(ilsm_map* map) {
+  if (!map) return fail(ILSM_ERR_INVALID_ARG, "map_join: null map");
+  Ctx& c = *map->m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return map->m.wait_ready(c.stream);
 }
 
 ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell) {
@@ -719,6 +736,15 @@ ILSM_API int ilsm_sc_merge_topk(const double* dist, const int32_t* id, const int
   return ILSM_OK;
 }
 
+ILSM_API int ilsm_sc_merge_topk_dev(ilsm_sc* sc, const void* d_packed, int shards, int k, void* d_out_packed) {
+  if (!sc || !d_packed || !d_out_packed || shards < 1 || k < 1 || k > 16)
+    return fail(ILSM_ERR_INVALID_ARG, "sc_merge_dev: bad argument");
+  Ctx& c = *sc->d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return sc_merge_dev(&c, d_packed, shards, k, d_out_packed);
+}
+
 ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q[4], const double t[3], double huber_a, double* cost, double JtJ[36],
                         double Jtr[6]) {
   if (!ctx || !q || !t || !cost || !JtJ || !Jtr) return fail(ILSM_ERR_INVALID_ARG, "eval: null argument");
@@ -749,6 +775,16 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q[4], const double 
     }
   for (int a = 0; a < 6; ++a) Jtr[a] = pin[22 + a];
   return ILSM_OK;
+}
+
+ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, double huber_a, double* d_out32) {
+  if (!ctx || !d_pose7 || !d_out32) return fail(ILSM_ERR_INVALID_ARG, "eval_dev: null argument");
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  set_pose_dev_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, huber_a);
+  count_launches(1);
+  return eval_only_launch(&c, d_out32);
 }
 
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_iterations, double huber_a,

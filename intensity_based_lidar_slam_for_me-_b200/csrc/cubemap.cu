@@ -12,16 +12,10 @@
 #include <new>
 #include <vector>
 
-#include "ilsm_host.hpp"
+#include "ilsm_cubemap.hpp"
 #include "ilsm_voxel.cuh"
 
 namespace ilsm {
-
-constexpr int kCW = 21, kCH = 21, kCD = 11, kCNum = kCW * kCH * kCD;
-
-struct GatherItem {
-  int slab, offset, count;
-};
 
 __global__ void cube_gather_kernel(const float4* __restrict__ slabs, int cap, const GatherItem* __restrict__ items,
                                    float4* __restrict__ out) {
@@ -151,48 +145,6 @@ __global__ void __launch_bounds__(1024)
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-struct QuatH {
-  double x, y, z, w;
-};
-static QuatH qmul_h(const QuatH& a, const QuatH& b) {
-  return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
-          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
-}
-static void qrot_h(const QuatH& q, const double v[3], double o[3]) {  // Eigen _transformVector
-  const double ux = q.x, uy = q.y, uz = q.z;
-  double cx = uy * v[2] - uz * v[1], cy = uz * v[0] - ux * v[2], cz = ux * v[1] - uy * v[0];
-  cx += cx, cy += cy, cz += cz;
-  o[0] = (v[0] + q.w * cx) + (uy * cz - uz * cy);
-  o[1] = (v[1] + q.w * cy) + (uz * cx - ux * cz);
-  o[2] = (v[2] + q.w * cz) + (ux * cy - uy * cx);
-}
-
-struct CubeMapH {
-  Ctx* ctx = nullptr;
-  Map map_c, map_s;
-  int cap = 0;
-  float line_res = 0.4f, plane_res = 0.8f;
-  int cenW = 10, cenH = 10, cenD = 5;
-  QuatH q_wmap_wodom{0, 0, 0, 1};
-  double t_wmap_wodom[3] = {0, 0, 0};
-  std::vector<int> slab_of;           // array index -> slab id
-  std::vector<int> cnt_c_h, cnt_s_h;  // host mirror of the per-slab counts
-  int valid[125], n_valid = 0;
-  DevBuf<float4> slabs_c, slabs_s, from_c, from_s, stack_c, stack_s, scratch, world_tmp;
-  DevBuf<int> cnt_c, cnt_s, slab_of_d, stack_n, valid_d, err, zero_list;
-  DevBuf<GatherItem> items;
-  DevBuf<float> raw;
-  PinnedBuf<int> pin;
-
-  int init(Ctx* c, float lres, float pres, int cube_cap);
-  void release();
-  int roll(const double t[3]);
-  int gather(int* n_mc, int* n_ms);
-  int insert(const int* d_counts, int nc_host, int ns_host, int world_frame);
-  int filter_valid();
-  int fetch_counts();
-};
-
 int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
   ctx = c;
   cap = cube_cap;
@@ -349,9 +301,83 @@ int CubeMapH::fetch_counts() {
 
 using namespace ilsm;
 
-struct ilsm_cubemap {
-  CubeMapH m;
-};
+namespace ilsm {
+int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
+                       const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats) {
+  Ctx& c = *m.ctx;
+  // transformAssociateToMap (laserMapping.cpp:138-142)
+  const QuatH qo{q_wodom[0], q_wodom[1], q_wodom[2], q_wodom[3]};
+  QuatH qw = qmul_h(m.q_wmap_wodom, qo);
+  double tw[3], r[3];
+  qrot_h(m.q_wmap_wodom, t_wodom, r);
+  for (int i = 0; i < 3; ++i) tw[i] = r[i] + m.t_wmap_wodom[i];
+  int rc;
+  if ((rc = m.roll(tw))) return rc;
+  int n_mc = 0, n_ms = 0;
+  if ((rc = m.gather(&n_mc, &n_ms))) return rc;
+  // stacks: VoxelGrid(line_res) / VoxelGrid(plane_res) of the incoming feature clouds (:608-616), sizes stay on the device
+  if ((rc = m.stack_c.reserve(nc + 4)) || (rc = m.stack_s.reserve(ns + 4))) return rc;
+  const int ioff = stride_bytes >= 32 ? 4 : 3;
+  ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
+  if (nc > 0 && (rc = c.voxelgrid_dev(d_c, nc, nullptr, 0, stride_bytes, ioff, m.line_res, m.stack_c.p, m.stack_n.p))) return rc;
+  if (ns > 0 && (rc = c.voxelgrid_dev(d_s, ns, nullptr, 0, stride_bytes, ioff, m.plane_res, m.stack_s.p, m.stack_n.p + 1))) return rc;
+  // pose in
+  double pose[7] = {qw.x, qw.y, qw.z, qw.w, tw[0], tw[1], tw[2]};
+  double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 1024);
+  for (int i = 0; i < 7; ++i) pin_pose[i] = pose[i];
+  ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  const bool optimise = n_mc > o.min_corner_map && n_ms > o.min_surf_map;  // laserMapping.cpp:624
+  if (optimise) {
+    if ((rc = m.map_c.build_dev(reinterpret_cast<const float*>(m.from_c.p), n_mc, 16, 0.f)) ||
+        (rc = m.map_s.build_dev(reinterpret_cast<const float*>(m.from_s.p), n_ms, 16, 0.f)))
+      return rc;
+    c.d_stack_counts = m.stack_n.p;
+    rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.stack_c.p), nc, reinterpret_cast<const float*>(m.stack_s.p),
+                        ns, 16, o);
+    c.d_stack_counts = nullptr;
+    if (rc) return rc;
+  }
+  // insertion with the optimised pose (still on the device) + per-cube VoxelGrid of the valid cubes
+  if ((rc = m.insert(m.stack_n.p, 0, 0, 0)) || (rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
+  unsigned char* pin = c.pinned.p;
+  int* pin_i = m.pin.p + kCNum + 2048;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin_i, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const double* out = reinterpret_cast<const double*>(pin);
+  for (int i = 0; i < 4; ++i) q_w[i] = out[i];
+  for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
+  if (report && optimise) {
+    memcpy(report, pin + 64, sizeof(*report));
+    report->passes = o.outer_iterations;
+  }
+  // transformUpdate (laserMapping.cpp:145-149)
+  const QuatH qwf{q_w[0], q_w[1], q_w[2], q_w[3]};
+  const double n2 = qo.x * qo.x + qo.y * qo.y + qo.z * qo.z + qo.w * qo.w;
+  const QuatH qinv{-qo.x / n2, -qo.y / n2, -qo.z / n2, qo.w / n2};
+  m.q_wmap_wodom = qmul_h(qwf, qinv);
+  qrot_h(m.q_wmap_wodom, t_wodom, r);
+  for (int i = 0; i < 3; ++i) m.t_wmap_wodom[i] = t_w[i] - r[i];
+  if (stats) {
+    stats->n_map_corner = n_mc, stats->n_map_surf = n_ms;
+    stats->n_stack_corner = pin_i[1], stats->n_stack_surf = pin_i[2];
+    stats->ran_optimization = optimise ? 1 : 0;
+    stats->n_valid = m.n_valid;
+    stats->cen[0] = m.cenW, stats->cen[1] = m.cenH, stats->cen[2] = m.cenD;
+    stats->flags = pin_i[0];
+  }
+  if (pin_i[0]) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cube map: capacity exceeded (flags 0x%x: 16 stack>16384, 32 cube slab full, 64 cube>16384, 2 leaf too small)", pin_i[0]);
+    cudaMemsetAsync(m.err.p, 0, sizeof(int), c.stream);
+    return fail(ILSM_ERR_OUT_OF_MEMORY, msg);
+  }
+  return ILSM_OK;
+}
+}  // namespace ilsm
 
 extern "C" {
 
@@ -456,79 +482,12 @@ ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int 
   ilsm_reg_opts o;
   if (opts) o = *opts; else ilsm_reg_opts_default(&o);
   if (report) memset(report, 0, sizeof(*report));
-  // transformAssociateToMap (laserMapping.cpp:138-142)
-  const QuatH qo{q_wodom[0], q_wodom[1], q_wodom[2], q_wodom[3]};
-  QuatH qw = qmul_h(m.q_wmap_wodom, qo);
-  double tw[3], r[3];
-  qrot_h(m.q_wmap_wodom, t_wodom, r);
-  for (int i = 0; i < 3; ++i) tw[i] = r[i] + m.t_wmap_wodom[i];
   int rc;
-  if ((rc = m.roll(tw))) return rc;
-  int n_mc = 0, n_ms = 0;
-  if ((rc = m.gather(&n_mc, &n_ms))) return rc;
-  // stacks: VoxelGrid(line_res) / VoxelGrid(plane_res) of the incoming feature clouds (:608-616), sizes stay on the device
   if ((rc = stage_clouds(m, corner_last, nc, surf_last, ns, stride_bytes))) return rc;
   const size_t off_s = ((size_t)nc * stride_bytes + 255) & ~(size_t)255;
   const float* d_c = m.raw.p;
   const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
-  const int ioff = stride_bytes >= 32 ? 4 : 3;
-  ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
-  if (nc > 0 && (rc = c.voxelgrid_dev(d_c, nc, nullptr, 0, stride_bytes, ioff, m.line_res, m.stack_c.p, m.stack_n.p))) return rc;
-  if (ns > 0 && (rc = c.voxelgrid_dev(d_s, ns, nullptr, 0, stride_bytes, ioff, m.plane_res, m.stack_s.p, m.stack_n.p + 1))) return rc;
-  // pose in
-  double pose[7] = {qw.x, qw.y, qw.z, qw.w, tw[0], tw[1], tw[2]};
-  double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 1024);
-  for (int i = 0; i < 7; ++i) pin_pose[i] = pose[i];
-  ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-  const bool optimise = n_mc > o.min_corner_map && n_ms > o.min_surf_map;  // laserMapping.cpp:624
-  if (optimise) {
-    if ((rc = m.map_c.build_dev(reinterpret_cast<const float*>(m.from_c.p), n_mc, 16, 0.f)) ||
-        (rc = m.map_s.build_dev(reinterpret_cast<const float*>(m.from_s.p), n_ms, 16, 0.f)))
-      return rc;
-    c.d_stack_counts = m.stack_n.p;
-    rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.stack_c.p), nc, reinterpret_cast<const float*>(m.stack_s.p),
-                        ns, 16, o);
-    c.d_stack_counts = nullptr;
-    if (rc) return rc;
-  }
-  // insertion with the optimised pose (still on the device) + per-cube VoxelGrid of the valid cubes
-  if ((rc = m.insert(m.stack_n.p, 0, 0, 0)) || (rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
-  unsigned char* pin = c.pinned.p;
-  int* pin_i = m.pin.p + kCNum + 2048;
-  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin_i, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaStreamSynchronize(c.stream));
-  const double* out = reinterpret_cast<const double*>(pin);
-  for (int i = 0; i < 4; ++i) q_w[i] = out[i];
-  for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
-  if (report && optimise) {
-    memcpy(report, pin + 64, sizeof(*report));
-    report->passes = o.outer_iterations;
-  }
-  // transformUpdate (laserMapping.cpp:145-149)
-  const QuatH qwf{q_w[0], q_w[1], q_w[2], q_w[3]};
-  const double n2 = qo.x * qo.x + qo.y * qo.y + qo.z * qo.z + qo.w * qo.w;
-  const QuatH qinv{-qo.x / n2, -qo.y / n2, -qo.z / n2, qo.w / n2};
-  m.q_wmap_wodom = qmul_h(qwf, qinv);
-  qrot_h(m.q_wmap_wodom, t_wodom, r);
-  for (int i = 0; i < 3; ++i) m.t_wmap_wodom[i] = t_w[i] - r[i];
-  if (stats) {
-    stats->n_map_corner = n_mc, stats->n_map_surf = n_ms;
-    stats->n_stack_corner = pin_i[1], stats->n_stack_surf = pin_i[2];
-    stats->ran_optimization = optimise ? 1 : 0;
-    stats->n_valid = m.n_valid;
-    stats->cen[0] = m.cenW, stats->cen[1] = m.cenH, stats->cen[2] = m.cenD;
-    stats->flags = pin_i[0];
-  }
-  if (pin_i[0]) {
-    char msg[160];
-    snprintf(msg, sizeof(msg), "cube map: capacity exceeded (flags 0x%x: 16 stack>16384, 32 cube slab full, 64 cube>16384, 2 leaf too small)", pin_i[0]);
-    cudaMemsetAsync(m.err.p, 0, sizeof(int), c.stream);
-    return fail(ILSM_ERR_OUT_OF_MEMORY, msg);
-  }
-  return ILSM_OK;
+  return cubemap_frame_core(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, q_w, t_w, o, report, stats);
 }
 
 ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out) {

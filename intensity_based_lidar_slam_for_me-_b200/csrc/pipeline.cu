@@ -1,0 +1,167 @@
+// pipeline.cu -- the full per-frame loop of the reference's three LOAM nodes chained on one GPU (BASELINE config 2):
+//   scanRegistration  laserCloudHandler          scanRegistration.cpp:189-669   -> Ctx::features_dev
+//   laserOdometry     main loop                  laserOdometry.cpp:256-845      -> Ctx::odometry_dev + pose composition
+//   laserMapping      process()                  laserMapping.cpp:233-1166      -> cubemap_frame_core
+// The topics between the nodes (/laser_cloud_sharp, /laser_cloud_less_sharp, /laser_cloud_flat, /laser_cloud_less_flat,
+// /laser_cloud_corner_last, /laser_cloud_surf_last, /laser_odom_to_init) become device buffers: the organised frame is
+// the only upload, the two poses and a few counters the only downloads.  Host synchronisation points per frame: the
+// feature counts (sizes of the next launches), the odometry pose (the host owns q_w_curr / t_w_curr and the cube
+// window indices, as the reference nodes do) and the mapped pose.
+#include <string.h>
+
+#include <new>
+
+#include "ilsm_cubemap.hpp"
+
+namespace ilsm {
+
+// voxel edge of the "last frame" search structures: the odometry gate is 5 m (DISTANCE_SQ_THRESHOLD 25,
+// laserOdometry.cpp:31), the clouds are sparse (a few thousand points)
+constexpr float kOdomCell = 2.5f;
+
+struct SlamH {
+  Ctx* ctx = nullptr;
+  ilsm_cubemap* cube = nullptr;
+  Map last_corner, last_surf;  // kdtreeCornerLast / kdtreeSurfLast (laserOdometry.cpp:807-808)
+  DevBuf<float4> sharp, flat, lsharp;
+  bool inited = false;        // systemInited (laserOdometry.cpp:384)
+  double para_q[4] = {0, 0, 0, 1}, para_t[3] = {0, 0, 0};  // q_last_curr / t_last_curr, kept between frames (:51-52)
+  QuatH q_w_curr{0, 0, 0, 1};
+  double t_w_curr[3] = {0, 0, 0};
+  float min_range = 0.3f;
+  long long frames = 0;
+};
+
+}  // namespace ilsm
+
+using namespace ilsm;
+
+struct ilsm_slam {
+  SlamH s;
+};
+
+extern "C" {
+
+ILSM_API int ilsm_slam_create(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                              ilsm_slam** out) {
+  if (!ctx || !out) return fail(ILSM_ERR_INVALID_ARG, "slam_create: null argument");
+  ilsm_slam* h = new (std::nothrow) ilsm_slam();
+  if (!h) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
+  h->s.ctx = &ctx->c;
+  h->s.min_range = min_range > 0.f ? min_range : 0.3f;
+  int rc = ilsm_cubemap_create(ctx, line_res, plane_res, cube_capacity, &h->s.cube);
+  if (rc == ILSM_OK) {
+    std::lock_guard<std::mutex> lk(ctx->c.mu);
+    cudaSetDevice(ctx->c.device);
+    if (!(rc = h->s.last_corner.init(&ctx->c))) rc = h->s.last_surf.init(&ctx->c);
+  }
+  if (rc) {
+    if (h->s.cube) ilsm_cubemap_destroy(h->s.cube);
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return ILSM_OK;
+}
+
+ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
+  if (!slam) return;
+  SlamH& s = slam->s;
+  {
+    std::lock_guard<std::mutex> lk(s.ctx->mu);
+    cudaSetDevice(s.ctx->device);
+    cudaStreamSynchronize(s.ctx->stream);
+    s.last_corner.release(), s.last_surf.release();
+    s.sharp.release(), s.flat.release(), s.lsharp.release();
+  }
+  ilsm_cubemap_destroy(s.cube);
+  delete slam;
+}
+
+ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam) { return slam ? slam->s.cube : nullptr; }
+
+ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom[4],
+                             double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+  if (!slam || (n > 0 && !xyzi) || !q_odom || !t_odom || !q_map || !t_map)
+    return fail(ILSM_ERR_INVALID_ARG, "slam_frame: null argument");
+  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: bad n/stride");
+  SlamH& s = slam->s;
+  Ctx& c = *s.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  int rc;
+  // ---- scanRegistration: the frame is the only upload
+  const size_t bytes = (size_t)n * stride_bytes;
+  if ((rc = c.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  // the previous frame's tree builds (on the maps' own streams, overlapping its mapping step) read lsharp / fe.lflat:
+  // order this frame's front end after them
+  if ((rc = s.last_corner.wait_ready(c.stream)) || (rc = s.last_surf.wait_ready(c.stream))) return rc;
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = c.features_dev(c.fe.raw.p, n, stride_bytes, s.min_range))) return rc;
+  int* pin = reinterpret_cast<int*>(c.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  const int n_sharp = pin[1], n_lsharp = pin[2], n_flat = pin[3], n_lflat = pin[4];
+  if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: a ring segment exceeds the supported size");
+  if (stats) {
+    stats->n_cloud = pin[0], stats->n_sharp = n_sharp, stats->n_less_sharp = n_lsharp, stats->n_flat = n_flat;
+    stats->n_less_flat = n_lflat;
+  }
+  if ((rc = s.sharp.reserve(n_sharp + 4)) || (rc = s.flat.reserve(n_flat + 4)) || (rc = s.lsharp.reserve(n_lsharp + 4))) return rc;
+  if ((rc = c.gather_dev(c.fe.cloud.p, c.fe.sharp.p, c.fe.counts.p, 1, n_sharp, s.sharp.p)) ||
+      (rc = c.gather_dev(c.fe.cloud.p, c.fe.lsharp.p, c.fe.counts.p, 2, n_lsharp, s.lsharp.p)) ||
+      (rc = c.gather_dev(c.fe.cloud.p, c.fe.flat.p, c.fe.counts.p, 3, n_flat, s.flat.p)))
+    return rc;
+  // ---- laserOdometry
+  if (!s.inited) {
+    s.inited = true;
+  } else {
+    if (use_aloam) {  // the fork optimises only on frames flagged "skip_intensity" (laserOdometry.cpp:406-417)
+      ilsm_reg_opts oo;
+      ilsm_reg_opts_default(&oo);  // 2 passes x max 4 iterations, Huber 0.1 (laserOdometry.cpp:417,644,705-710)
+      double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 2048);  // para_q / para_t -> LmState::xq, xt
+      for (int i = 0; i < 4; ++i) pin_pose[i] = s.para_q[i];
+      for (int i = 0; i < 3; ++i) pin_pose[4 + i] = s.para_t[i];
+      ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+      if ((rc = c.odometry_dev(&s.last_corner, &s.last_surf, reinterpret_cast<const float*>(s.sharp.p), n_sharp,
+                               reinterpret_cast<const float*>(s.flat.p), n_flat, 16, oo)))
+        return rc;
+      unsigned char* pb = c.pinned.p;
+      ILSM_CUDA(cudaMemcpyAsync(pb, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      ILSM_CUDA(cudaMemcpyAsync(pb + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+      ILSM_CUDA(cudaStreamSynchronize(c.stream));
+      const double* o7 = reinterpret_cast<const double*>(pb);
+      for (int i = 0; i < 4; ++i) s.para_q[i] = o7[i];
+      for (int i = 0; i < 3; ++i) s.para_t[i] = o7[4 + i];
+      if (stats) {
+        memcpy(&stats->odometry, pb + 64, sizeof(ilsm_reg_report));
+        stats->odometry.passes = oo.outer_iterations;
+        stats->ran_odometry = 1;
+      }
+    }
+    // t_w_curr = t_w_curr + q_w_curr * t_last_curr;  q_w_curr = q_w_curr * q_last_curr   (laserOdometry.cpp:716-717)
+    double r[3];
+    qrot_h(s.q_w_curr, s.para_t, r);
+    for (int i = 0; i < 3; ++i) s.t_w_curr[i] = s.t_w_curr[i] + r[i];
+    s.q_w_curr = qmul_h(s.q_w_curr, QuatH{s.para_q[0], s.para_q[1], s.para_q[2], s.para_q[3]});
+  }
+  q_odom[0] = s.q_w_curr.x, q_odom[1] = s.q_w_curr.y, q_odom[2] = s.q_w_curr.z, q_odom[3] = s.q_w_curr.w;
+  for (int i = 0; i < 3; ++i) t_odom[i] = s.t_w_curr[i];
+  // laserCloudCornerLast = cornerPointsLessSharp, laserCloudSurfLast = surfPointsLessFlat; rebuild both trees (:793-808)
+  if ((rc = s.last_corner.build_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, 16, kOdomCell)) ||
+      (rc = s.last_surf.build_dev(reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
+    return rc;
+  // ---- laserMapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
+  if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
+  ilsm_reg_opts mo;
+  ilsm_reg_opts_default(&mo);
+  rc = cubemap_frame_core(s.cube->m, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
+                          reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
+                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr);
+  if (rc) return rc;
+  s.frames++;
+  return ILSM_OK;
+}
+
+}  // extern "C"

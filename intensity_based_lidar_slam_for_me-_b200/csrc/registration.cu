@@ -900,19 +900,44 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
 // normal_eq_kernel: one evaluation of (cost, J^T J, J^T r) over all factors with an ordinary grid (the
 // "J^T J kernel" of config 3 and of ilsm_eval_normal_eq); deterministic two-stage reduction, last block sums.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) normal_eq_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials,
-                                                        double* __restrict__ eval_out) {
-  __shared__ double red[8][kSumStride];
+// 12 warps per SM in ONE block: the same occupancy as 3 x 128 at this register budget, but a third of the per-block
+// partial sums, so the last block's cross-block combine is short (<= 148 x 32 doubles, 12 slices).
+constexpr int kEvalThreads = 384, kEvalBlocksPerSm = 1;
+
+__global__ void __launch_bounds__(kEvalThreads, kEvalBlocksPerSm)
+    normal_eq_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials, double* __restrict__ eval_out) {
+  __shared__ double red[kEvalThreads / 32][kSumStride];
   __shared__ int is_last;
   double acc[kSumStride];
 #pragma unroll
   for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int type = i < n ? fv.type[i] : 0;
-  if (type != 0) {
-    const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
-    const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
-    eval_factor(type, fv.p[i], fv.a[i], fv.b[i], q, t, st->huber_a, acc);
+  const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
+  const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
+  const double huber_a = st->huber_a;
+  // persistent grid-stride loop: the 32 running sums stay in registers across factors, so the reduction cost is paid
+  // once per thread; the next factor's record is in flight while the current one is evaluated.  Only the bytes a
+  // factor type needs are read: type 0 (gate / fit failed) 4 B, plane 52 B, edge 84 B.
+  const int stride = gridDim.x * kEvalThreads;
+  int i = blockIdx.x * kEvalThreads + threadIdx.x;
+  int ty = i < n ? __ldg(fv.type + i) : 0;
+  float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+  double4 fa = make_double4(0, 0, 0, 0), fb = fa;
+  if (ty) {
+    pf = fv.p[i], fa = fv.a[i];
+    if (ty == 1) fb = fv.b[i];
+  }
+#pragma unroll 1
+  while (i < n) {
+    const int ni = i + stride;
+    const int nty = ni < n ? __ldg(fv.type + ni) : 0;
+    float4 npf = pf;
+    double4 nfa = fa, nfb = fb;
+    if (nty) {
+      npf = fv.p[ni], nfa = fv.a[ni];
+      if (nty == 1) nfb = fv.b[ni];
+    }
+    if (ty) eval_factor(ty, pf, fa, fb, q, t, huber_a, acc);
+    ty = nty, pf = npf, fa = nfa, fb = nfb, i = ni;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   red[warp][lane] = warp_reduce_transpose(acc, lane);
@@ -920,31 +945,39 @@ __global__ void __launch_bounds__(256) normal_eq_kernel(FactorView fv, int n, Lm
   if (threadIdx.x < kSumStride) {
     double v = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < kEvalThreads / 32; ++w) v += red[w][threadIdx.x];
     partials[(size_t)blockIdx.x * kSumStride + threadIdx.x] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned t = atomicAdd(&st->ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    unsigned tk = atomicAdd(&st->ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // 8 threads per sum, each a strided slice of the blocks, then a fixed-order combine
-  __shared__ double slice[8][kSumStride];
+  // 12 threads per sum, each a strided slice of the blocks (independent loads, 4 in flight), then a fixed-order combine
+  __shared__ double slice[kEvalThreads / 32][kSumStride];
   {
     const int c = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    double v = 0;
-    for (unsigned b = sl; b < gridDim.x; b += 8) v += __ldcg(partials + (size_t)b * kSumStride + c);
-    slice[sl][c] = v;
+    constexpr int S = kEvalThreads / 32;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    unsigned b = sl;
+    for (; b + 3 * S < gridDim.x; b += 4 * S) {
+      v0 += __ldcg(partials + (size_t)b * kSumStride + c);
+      v1 += __ldcg(partials + (size_t)(b + S) * kSumStride + c);
+      v2 += __ldcg(partials + (size_t)(b + 2 * S) * kSumStride + c);
+      v3 += __ldcg(partials + (size_t)(b + 3 * S) * kSumStride + c);
+    }
+    for (; b < gridDim.x; b += S) v0 += __ldcg(partials + (size_t)b * kSumStride + c);
+    slice[sl][c] = (v0 + v1) + (v2 + v3);
   }
   __syncthreads();
   if (threadIdx.x < kSumStride) {
     double v = 0;
 #pragma unroll
-    for (int sl = 0; sl < 8; ++sl) v += slice[sl][threadIdx.x];
+    for (int sl = 0; sl < kEvalThreads / 32; ++sl) v += slice[sl][threadIdx.x];
     eval_out[threadIdx.x] = v;
   }
   if (threadIdx.x == 0) st->ticket = 0u;
@@ -1047,13 +1080,13 @@ int Ctx::register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const flo
 
 // stand-alone evaluation (ilsm_eval_normal_eq): candidate pose must already be in lm->cq/ct, huber in lm->huber_a
 int eval_only_launch(Ctx* c, double* d_out) {
-  const int T = 256;
-  int blocks = (c->fac.n + T - 1) / T;
+  long long blocks = ((long long)c->fac.n + kEvalThreads - 1) / kEvalThreads, cap = (long long)c->sm_count * kEvalBlocksPerSm;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   int rc;
   if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
   FactorView fv = factor_view(c->fac, false);
-  normal_eq_kernel<<<blocks, T, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out);
+  normal_eq_kernel<<<(unsigned)blocks, kEvalThreads, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out);
   count_launches(1);
   return check_launch("normal_eq");
 }

@@ -269,6 +269,56 @@ __global__ void __launch_bounds__(1024) sc_topk_kernel(const double* __restrict_
   }
 }
 
+// Merge of gathered per-shard top-k lists on the device (what every rank runs after the all-gather).  Packed layout
+// per shard: k x f64 distance | k x i32 id | k x i32 shift (16 k bytes).  One warp; round j picks the smallest
+// (distance, id) strictly above round j-1's winner (ids are unique across shards), so the result is the same
+// ascending (distance, id) order as ilsm_sc_merge_topk on the host.
+__global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int shards, int k, unsigned char* __restrict__ out) {
+  const int lane = threadIdx.x;
+  const size_t rec = (size_t)16 * k;
+  u64 last_d = 0;
+  int last_id = -1;
+  bool first = true;
+  double* o_dist = reinterpret_cast<double*>(out);
+  int* o_id = reinterpret_cast<int*>(out + (size_t)8 * k);
+  int* o_shift = reinterpret_cast<int*>(out + (size_t)12 * k);
+  for (int j = 0; j < k; ++j) {
+    u64 bd = ~0ull;
+    int bid = INT_MAX, bsh = 0;
+    for (int e = lane; e < shards * k; e += 32) {
+      const unsigned char* base = packed + (size_t)(e / k) * rec;
+      const int i = e % k;
+      const int id = reinterpret_cast<const int*>(base + (size_t)8 * k)[i];
+      if (id < 0) continue;
+      const u64 d = (u64)__double_as_longlong(reinterpret_cast<const double*>(base)[i]);
+      const bool above = first || d > last_d || (d == last_d && id > last_id);
+      if (above && (d < bd || (d == bd && id < bid))) bd = d, bid = id, bsh = reinterpret_cast<const int*>(base + (size_t)12 * k)[i];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const u64 od = __shfl_xor_sync(0xffffffffu, bd, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bid, off);
+      const int os = __shfl_xor_sync(0xffffffffu, bsh, off);
+      if (od < bd || (od == bd && oi < bid)) bd = od, bid = oi, bsh = os;
+    }
+    const bool have = bid != INT_MAX;
+    if (lane == 0) {
+      o_dist[j] = have ? __longlong_as_double((long long)bd) : __longlong_as_double(0x7ff0000000000000ll);
+      o_id[j] = have ? bid : -1;
+      o_shift[j] = have ? bsh : 0;
+    }
+    if (have) last_d = bd, last_id = bid, first = false;
+    else last_d = ~0ull, last_id = INT_MAX, first = false;
+  }
+}
+
+int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out) {
+  sc_merge_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned char*>(d_packed), shards, k,
+                                             reinterpret_cast<unsigned char*>(d_out));
+  count_launches(1);
+  return check_launch("sc_merge");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------

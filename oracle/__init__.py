@@ -390,3 +390,53 @@ class CubeMap:
         out = np.zeros((cap, 4), np.float32)
         n = self._l.orc_cubemap_cube(self._h, which, index, _p(out), cap)
         return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# the three nodes chained (scanRegistration -> laserOdometry -> laserMapping), one frame per call
+# ------------------------------------------------------------------------------------------------
+def _qmul(a, b):  # Eigen quaternion product, (x, y, z, w)
+    return np.array([a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1],
+                     a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
+                     a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0],
+                     a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]])
+
+
+def _qrot(q, v):  # Eigen QuaternionBase::_transformVector
+    u = q[:3]
+    uv = 2.0 * np.cross(u, v)
+    return v + q[3] * uv + np.cross(u, uv)
+
+
+class Slam:
+    """laserOdometry.cpp main loop (:376-845) between the front end and CubeMap.frame, restated with the oracle's own
+    pieces: first frame only initialises; afterwards 2 x (association + Solve) from the previous q/t_last_curr (when
+    use_aloam), t_w_curr += q_w_curr * t_last_curr, q_w_curr *= q_last_curr (:716-717), last clouds <- less-sharp /
+    less-flat (:793-808), then one process() iteration of laserMapping with the odometry pose."""
+
+    def __init__(self, line_res=0.4, plane_res=0.8, min_range=0.3):
+        self.cube = CubeMap(line_res, plane_res)
+        self.min_range = min_range
+        self.inited = False
+        self.para = np.array([0, 0, 0, 1, 0, 0, 0.0])
+        self.q_w_curr = np.array([0, 0, 0, 1.0])
+        self.t_w_curr = np.zeros(3)
+        self.last_corner = self.last_surf = None
+
+    def frame(self, cloud, use_aloam=True):
+        f = extract_features(cloud, self.min_range)
+        sharp, flat = f["cloud"][f["sharp_idx"]], f["cloud"][f["flat_idx"]]
+        lsharp, lflat = f["cloud"][f["less_sharp_idx"]], f["less_flat"]
+        odo = None
+        if not self.inited:
+            self.inited = True
+        else:
+            if use_aloam:
+                self.para, sums, nf = odometry(self.last_corner, self.last_surf, sharp, flat, self.para)
+                odo = (sums, nf)
+            self.t_w_curr = self.t_w_curr + _qrot(self.q_w_curr, self.para[4:])
+            self.q_w_curr = _qmul(self.q_w_curr, self.para[:4])
+        self.last_corner, self.last_surf = lsharp.copy(), lflat.copy()
+        qt_odom = np.concatenate([self.q_w_curr, self.t_w_curr])
+        qt_map, msums, st = self.cube.frame(lsharp, lflat, qt_odom)
+        return qt_odom, qt_map, dict(features=f, odometry=odo, mapping=msums, cubemap=st)
