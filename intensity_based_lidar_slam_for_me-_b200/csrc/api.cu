@@ -98,7 +98,7 @@ int Ctx::init(int dev) {
 
 void Ctx::release() {
   if (stream) cudaStreamSynchronize(stream);
-  fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
+  fe.chunk_hist.release(), fe.chunk_base.release(), fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
   fe.src_index.release(), fe.label.release(), fe.sort_ind.release(), fe.ring_sharp.release(), fe.ring_lsharp.release();
   fe.ring_flat.release(), fe.sharp.release(), fe.lsharp.release(), fe.flat.release(), fe.counts.release();
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
@@ -635,7 +635,7 @@ ILSM_API void ilsm_sc_destroy(ilsm_sc* sc) {
     cudaSetDevice(sc->d.ctx->device);
     cudaStreamSynchronize(sc->d.ctx->stream);
     ScDb& d = sc->d;
-    d.db.release(), d.bins.release(), d.query.release(), d.dist.release(), d.out_dist.release(), d.shift.release();
+    d.db.release(), d.bins.release(), d.query.release(), d.out_dist.release(), d.part_d.release(), d.part_id.release(), d.part_sh.release();
     d.out_id.release(), d.out_shift.release(), d.stage.release();
   }
   delete sc;

@@ -86,7 +86,8 @@ __global__ void fe_init_kernel(int* st) {
 
 // pass 1: min-range filter, ring id, raw azimuth; ring histogram, first/last kept point
 __global__ void fe_tag_kernel(const float* __restrict__ in, int n, int stride_f, float thr2,
-                              unsigned char* __restrict__ scanid, float* __restrict__ ori_raw, int* st) {
+                              unsigned char* __restrict__ scanid, float* __restrict__ ori_raw, int* st,
+                              int* __restrict__ chunk_hist) {
   __shared__ int hist[kRings];
   if (threadIdx.x < kRings) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -116,7 +117,10 @@ __global__ void fe_tag_kernel(const float* __restrict__ in, int n, int stride_f,
     if (last >= 0) atomicMax(&st[kStLast], last);
   }
   __syncthreads();
-  if (threadIdx.x < kRings && hist[threadIdx.x]) atomicAdd(&st[kStRing + threadIdx.x], hist[threadIdx.x]);
+  if (threadIdx.x < kRings) {
+    chunk_hist[blockIdx.x * kRings + threadIdx.x] = hist[threadIdx.x];  // ring counts of this 256-point chunk
+    if (hist[threadIdx.x]) atomicAdd(&st[kStRing + threadIdx.x], hist[threadIdx.x]);
+  }
 }
 
 struct OriRef {
@@ -163,59 +167,87 @@ __global__ void fe_star_kernel(const float* __restrict__ in, int n, int stride_f
   if ((threadIdx.x & 31) == 0 && cand != INT_MAX) atomicMin(&st[kStStar], cand);
 }
 
-// pass 3: one block per ring, ordered compaction of the ring's points (stable in input order) straight into
-// the ring-concatenated cloud; intensity = scanID + 0.1 * relTime (scanRegistration.cpp:334-373)
-__global__ void __launch_bounds__(1024) fe_bucket_kernel(const float* __restrict__ in, int n, int stride_f,
-                                                         const unsigned char* __restrict__ scanid,
-                                                         const float* __restrict__ ori_raw, const int* __restrict__ st,
-                                                         float4* __restrict__ cloud, int* __restrict__ src_index) {
-  const int ring = blockIdx.x;
-  const int count = st[kStRing + ring];
-  if (count == 0) return;
-  int off = 0;
-  for (int r = 0; r < ring; ++r) off += st[kStRing + r];
-  const OriRef ref = ori_reference(in, stride_f, st);
-  const int star = st[kStStar];
-  __shared__ int warp_cnt[32];
-  __shared__ int base_s;
-  if (threadIdx.x == 0) base_s = 0;
+// pass 3a: per ring, exclusive prefix of the chunk histograms (one block per ring, chunks scanned 256 at a time)
+constexpr int kFeChunk = 256;
+__global__ void __launch_bounds__(256) fe_scan_kernel(const int* __restrict__ chunk_hist, int chunks, int* __restrict__ chunk_base) {
+  __shared__ int wsum[8];
+  __shared__ int carry_s;
+  const int ring = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c0 = 0; c0 < n; c0 += 1024) {
-    const int i = c0 + threadIdx.x;
-    const bool mine = i < n && scanid[i] == ring;
-    const unsigned b = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) warp_cnt[warp] = __popc(b);
+  for (int c0 = 0; c0 < chunks; c0 += 256) {
+    const int c = c0 + threadIdx.x;
+    const int v = c < chunks ? chunk_hist[c * kRings + ring] : 0;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     int wbase = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) {
-      const int cw = warp_cnt[w];
-      if (w < warp) wbase += cw;
-      tot += cw;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) wbase += wsum[w];
+      tot += wsum[w];
     }
-    const int base = base_s;
-    if (mine) {
-      const int pos = off + base + wbase + __popc(b & ((1u << lane) - 1u));
-      const float* p = in + (size_t)i * stride_f;
-      float ori = ori_raw[i];
-      const double PI = 3.14159265358979323846;
-      if (i <= star) {
-        ori = ori_first_half(ori, ref.startOri);
-      } else {
+    const int carry = carry_s;
+    if (c < chunks) chunk_base[c * kRings + ring] = carry + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+}
+
+// pass 3b: stable scatter of every kept point into the ring-concatenated cloud: position = ring offset + points of
+// the same ring in earlier chunks + in earlier warps of this chunk + in earlier lanes of this warp (match_any);
+// intensity = scanID + 0.1 * relTime (scanRegistration.cpp:334-373)
+__global__ void __launch_bounds__(kFeChunk) fe_bucket_kernel(const float* __restrict__ in, int n, int stride_f,
+                                                             const unsigned char* __restrict__ scanid,
+                                                             const float* __restrict__ ori_raw, const int* __restrict__ st,
+                                                             const int* __restrict__ chunk_base, float4* __restrict__ cloud,
+                                                             int* __restrict__ src_index) {
+  __shared__ int ring_off[kRings];
+  __shared__ int wcnt[kFeChunk / 32][kRings];
+  if (st[kStLast] < 0) return;
+  if (threadIdx.x < kRings) {
+    int off = 0;
+    for (int r = 0; r < (int)threadIdx.x; ++r) off += st[kStRing + r];
+    ring_off[threadIdx.x] = off;
+  }
+  for (int t = threadIdx.x; t < (kFeChunk / 32) * kRings; t += blockDim.x) (&wcnt[0][0])[t] = 0;
+  __syncthreads();
+  const OriRef ref = ori_reference(in, stride_f, st);
+  const int star = st[kStStar];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * kFeChunk + threadIdx.x;
+  const int ring = i < n ? (int)scanid[i] : 255;
+  const bool mine = ring < kRings;
+  const unsigned peers = __match_any_sync(0xffffffffu, mine ? ring : 255);
+  const int rank = __popc(peers & ((1u << lane) - 1u));
+  if (mine && rank == 0) wcnt[warp][ring] = __popc(peers);
+  __syncthreads();
+  if (mine) {
+    int wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += wcnt[w][ring];
+    const int pos = ring_off[ring] + chunk_base[blockIdx.x * kRings + ring] + wbase + rank;
+    const float* p = in + (size_t)i * stride_f;
+    float ori = ori_raw[i];
+    const double PI = 3.14159265358979323846;
+    if (i <= star) {
+      ori = ori_first_half(ori, ref.startOri);
+    } else {
+      ori = (float)((double)ori + 2 * PI);
+      if ((double)ori < (double)ref.endOri - PI * 3 / 2)
         ori = (float)((double)ori + 2 * PI);
-        if ((double)ori < (double)ref.endOri - PI * 3 / 2)
-          ori = (float)((double)ori + 2 * PI);
-        else if ((double)ori > (double)ref.endOri + PI / 2)
-          ori = (float)((double)ori - 2 * PI);
-      }
-      const float relTime = __fdiv_rn(__fsub_rn(ori, ref.startOri), __fsub_rn(ref.endOri, ref.startOri));
-      const float tag = (float)((double)ring + 0.1 * (double)relTime);
-      cloud[pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), tag);
-      src_index[pos] = i;
+      else if ((double)ori > (double)ref.endOri + PI / 2)
+        ori = (float)((double)ori - 2 * PI);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) base_s = base + tot;
-    __syncthreads();
+    const float relTime = __fdiv_rn(__fsub_rn(ori, ref.startOri), __fsub_rn(ref.endOri, ref.startOri));
+    const float tag = (float)((double)ring + 0.1 * (double)relTime);
+    cloud[pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), tag);
+    src_index[pos] = i;
   }
 }
 
@@ -289,14 +321,14 @@ __global__ void __launch_bounds__(256) fe_sort_kernel(const float* __restrict__ 
 
 // neighbour suppression of scanRegistration.cpp:481-504 by one warp: lanes 1..5 test the forward gaps,
 // lanes 6..10 the backward gaps; marking stops at the first gap^2 > 0.05
-__device__ __forceinline__ void mark_neighbours(const float4* __restrict__ cloud, unsigned char* picked, int ind, int lane) {
+__device__ __forceinline__ void mark_neighbours(const float4* cloud, unsigned char* picked, int ind, int lane) {
   bool gap = false;
   int a = 0;
   if (lane >= 1 && lane <= 10) {
     const int l = lane <= 5 ? lane : -(lane - 5);
     a = ind + l;
     const int b = l > 0 ? a - 1 : a + 1;
-    const float4 pa = __ldg(cloud + a), pb = __ldg(cloud + b);
+    const float4 pa = cloud[a], pb = cloud[b];  // generic loads: the ring is staged in shared memory when it fits
     const float dx = __fsub_rn(pa.x, pb.x), dy = __fsub_rn(pa.y, pb.y), dz = __fsub_rn(pa.z, pb.z);
     const float g = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     gap = (double)g > 0.05;
@@ -313,15 +345,37 @@ __device__ __forceinline__ void mark_neighbours(const float4* __restrict__ cloud
 // pass 6: one warp per ring walks the six segments in order (the picks of one segment suppress neighbours that
 // may belong to the next, so segments stay sequential; rings are independent).  32 sorted entries are tested per
 // step, the first eligible one is taken, its neighbours are marked, and the test is repeated.
-__global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ cloud, const float* __restrict__ curv,
-                                                     const int* __restrict__ sort_ind, int* __restrict__ st,
-                                                     int* __restrict__ label, unsigned char* __restrict__ picked,
+constexpr int kPickCap = 1536;  // ring points staged in shared memory (an OS0-64 ring has 1024)
+__global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ g_cloud, const float* __restrict__ g_curv,
+                                                     const int* __restrict__ g_sort_ind, int* __restrict__ st,
+                                                     int* __restrict__ label, unsigned char* __restrict__ g_picked,
                                                      int* __restrict__ ring_sharp, int* __restrict__ ring_lsharp,
                                                      int* __restrict__ ring_flat) {
+  __shared__ float4 s_cloud[kPickCap];
+  __shared__ float s_curv[kPickCap];
+  __shared__ int s_sort[kPickCap];
+  __shared__ unsigned char s_picked[kPickCap];
   const int ring = blockIdx.x, lane = threadIdx.x;
   int S, E;
   ring_bounds(st, ring, S, E);
   if (E - S < 6) return;
+  // every access of this ring's picking falls into [S - 5, E + 6): stage it once, the sequential picks then run on
+  // shared-memory latency instead of a dependent global round trip per step
+  const int base = S - 5, cnt = E + 6 - base;
+  const float4* cloud = g_cloud;
+  const float* curv = g_curv;
+  const int* sort_ind = g_sort_ind;
+  unsigned char* picked = g_picked;
+  if (cnt <= kPickCap) {
+    for (int t = lane; t < cnt; t += 32) {
+      s_cloud[t] = g_cloud[base + t];
+      s_curv[t] = g_curv[base + t];
+      s_sort[t] = g_sort_ind[base + t];
+      s_picked[t] = 0;
+    }
+    __syncwarp();
+    cloud = s_cloud - base, curv = s_curv - base, sort_ind = s_sort - base, picked = s_picked - base;
+  }
   int n_sharp = 0, n_lsharp = 0, n_flat = 0;
   for (int j = 0; j < 6; ++j) {
     const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
@@ -539,7 +593,8 @@ int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_rang
       (rc = f.ring_flat.reserve(kRings * 24)) || (rc = f.ring_pts.reserve((size_t)kRings * ring_cap)) ||
       (rc = f.ring_out.reserve((size_t)kRings * ring_cap)) || (rc = f.sharp.reserve(kRings * 12)) ||
       (rc = f.lsharp.reserve(kRings * 120)) || (rc = f.flat.reserve(kRings * 24)) || (rc = f.lflat.reserve(n + 4)) ||
-      (rc = f.counts.reserve(8)))
+      (rc = f.counts.reserve(8)) || (rc = f.chunk_hist.reserve((size_t)(n / 256 + 2) * kRings)) ||
+      (rc = f.chunk_base.reserve((size_t)(n / 256 + 2) * kRings)))
     return rc;
   f.n_in = n;
   f.ring_cap = ring_cap;
@@ -547,17 +602,19 @@ int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_rang
   const int T = 256, B = (n + T - 1) / T;
   fe_init_kernel<<<1, 352, 0, stream>>>(f.stats.p);
   if (n > 0) {
-    fe_tag_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, min_range * min_range, f.scanid.p, f.ori.p, f.stats.p);
+    fe_tag_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, min_range * min_range, f.scanid.p, f.ori.p, f.stats.p,
+                                       f.chunk_hist.p);
     fe_star_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p);
-    fe_bucket_kernel<<<kRings, 1024, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.cloud.p,
-                                                  f.src_index.p);
+    fe_scan_kernel<<<kRings, 256, 0, stream>>>(f.chunk_hist.p, B, f.chunk_base.p);
+    fe_bucket_kernel<<<B, kFeChunk, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.chunk_base.p,
+                                                 f.cloud.p, f.src_index.p);
     fe_curvature_kernel<<<B, T, 0, stream>>>(f.cloud.p, f.stats.p, f.curv.p, f.label.p, f.picked.p);
     fe_sort_kernel<<<kRings * 6, 256, 0, stream>>>(f.curv.p, f.stats.p, f.sort_ind.p);
     fe_pick_kernel<<<kRings, 32, 0, stream>>>(f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p,
                                               f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p);
     fe_lessflat_kernel<<<kRings, 256, 0, stream>>>(f.cloud.p, f.label.p, f.stats.p, f.ring_pts.p, f.ring_out.p, ring_cap,
                                                    0.2f);
-    count_launches(7);
+    count_launches(8);
   }
   fe_compact_kernel<<<kRings, 128, 0, stream>>>(f.stats.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p, f.ring_out.p,
                                                 ring_cap, f.sharp.p, f.lsharp.p, f.flat.p, f.lflat.p, f.counts.p);

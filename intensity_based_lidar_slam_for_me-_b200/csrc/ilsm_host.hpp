@@ -146,6 +146,7 @@ struct FeBufs {
   DevBuf<unsigned char> scanid, picked;
   DevBuf<float> ori, curv;
   DevBuf<int> stats, src_index, label, sort_ind, ring_sharp, ring_lsharp, ring_flat, sharp, lsharp, flat, counts;
+  DevBuf<int> chunk_hist, chunk_base;  // ring counts per 256-point chunk of the frame and their per-ring prefix
   DevBuf<float4> cloud, ring_pts, ring_out, lflat, vox_packed;
   DevBuf<float> raw;                 // staged caller frame
   DevBuf<unsigned char> img;         // projection outputs (range | intensity)
@@ -199,8 +200,10 @@ struct ScDb {
   DevBuf<float> db;        // [count][20][60] float32
   DevBuf<int> bins;        // makeScancontext scratch
   DevBuf<ScQuery> query;
-  DevBuf<double> dist, out_dist;
-  DevBuf<int> shift, out_id, out_shift;
+  DevBuf<double> out_dist;
+  DevBuf<int> out_id, out_shift;
+  DevBuf<u64> part_d;      // per-block top-k lists of the scoring kernel
+  DevBuf<int> part_id, part_sh;
   DevBuf<float> stage;     // staged caller descriptors / points
   int append_dev(const float* desc, int n_add, bool from_host);
   int make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc);

@@ -7,24 +7,86 @@ namespace ilsm {
 
 constexpr int kVoxelBlockMax = 16384;  // points one block can sort in shared memory (128 KB of u64 keys)
 
-// in-block bitonic sort of P (power of two) 64-bit keys in shared memory
-static __device__ __forceinline__ void bitonic_sort_smem(u64* keys, int P) {
+// In-block bitonic sort of P (power of two) unique 64-bit keys held in shared memory.
+// Every thread owns E = P / blockDim.x consecutive keys in REGISTERS: compare-exchange steps whose partner distance j
+// is below E stay inside the thread, steps with E <= j < 32 E go through warp shuffles, and only the steps with
+// j >= 32 E (15 of the 91 steps at P = 8192 with 1024 threads) exchange through shared memory with a barrier.  The
+// shared-memory exchange uses a striped layout (element e of thread t at e * blockDim + t): conflict-free.
+template <int E>
+static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  u64 r[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = tid * E + e;
+    r[e] = idx < P ? keys[idx] : ~0ull;
+  }
+  __syncthreads();
+  const bool active = tid * E < P;  // P < blockDim.x: the idle threads hold sentinels and stay out of memory
+  const int ns = E == 1 ? P : nt;   // stripe length (E > 1 implies P == E * blockDim.x)
   for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < P; t += blockDim.x) {
-        const int ixj = t ^ j;
-        if (ixj > t) {
-          const u64 a = keys[t], b = keys[ixj];
-          const bool up = (t & k) == 0;
-          if ((a > b) == up) {
-            keys[t] = b;
-            keys[ixj] = a;
-          }
+    int j = k >> 1;
+    for (; j >= 32 * E; j >>= 1) {  // partner in another warp: striped exchange through shared memory
+      const int tj = j / E;
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) keys[e * ns + tid] = r[e];
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int idx = tid * E + e;
+          const u64 o = keys[e * ns + (tid ^ tj)];
+          const bool want_min = ((idx & j) == 0) == ((idx & k) == 0);
+          r[e] = want_min ? (o < r[e] ? o : r[e]) : (o > r[e] ? o : r[e]);
         }
       }
       __syncthreads();
     }
+    for (; j >= E; j >>= 1) {  // partner in another lane of this warp
+      const int lj = j / E;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int idx = tid * E + e;
+        const u64 o = __shfl_xor_sync(0xffffffffu, r[e], lj);
+        const bool want_min = ((idx & j) == 0) == ((idx & k) == 0);
+        r[e] = want_min ? (o < r[e] ? o : r[e]) : (o > r[e] ? o : r[e]);
+      }
+    }
+    // partner inside the thread: compile-time distances keep r[] in registers
+#pragma unroll
+    for (int jj = E / 2; jj > 0; jj >>= 1) {
+      if (jj <= j) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & jj) == 0) {
+            const bool up = ((tid * E + e) & k) == 0;
+            const u64 a = r[e], b = r[e | jj];
+            const bool sw = (a > b) == up;
+            r[e] = sw ? b : a;
+            r[e | jj] = sw ? a : b;
+          }
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int idx = tid * E + e;
+    if (idx < P) keys[idx] = r[e];
+  }
+  __syncthreads();
+}
+
+// P: power of two, at most 16 * blockDim.x; blockDim.x a power of two >= 32.  `keys` holds P entries.
+static __device__ __forceinline__ void bitonic_sort_smem(u64* keys, int P) {
+  const int per = (P + (int)blockDim.x - 1) / (int)blockDim.x;
+  if (per <= 1) bitonic_sort_regs<1>(keys, P);
+  else if (per == 2) bitonic_sort_regs<2>(keys, P);
+  else if (per == 4) bitonic_sort_regs<4>(keys, P);
+  else if (per == 8) bitonic_sort_regs<8>(keys, P);
+  else bitonic_sort_regs<16>(keys, P);
 }
 
 // PCL 1.10 VoxelGrid over one contiguous set of points held by the block (PCL 1.10 applyFilter restated):
@@ -116,12 +178,18 @@ static __device__ int voxelgrid_block(const float4* __restrict__ pts, int m, flo
     if (head) {
       const int slot = base + wbase + __popc(b & ((1u << lane) - 1u));
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      int cnt = 0;
       const u64 vox = keys[t] >> 24;
-      for (int e = t; e < P && keys[e] != ~0ull && (keys[e] >> 24) == vox; ++e) {
-        const float4 p = pts[(int)(keys[e] & 0xFFFFFF)];
-        sx = __fadd_rn(sx, p.x), sy = __fadd_rn(sy, p.y), sz = __fadd_rn(sz, p.z), si = __fadd_rn(si, p.w);
-        ++cnt;
+      int cnt = 1;  // run length first (shared memory only), so that the point loads below are independent of the sums
+      while (t + cnt < P && (keys[t + cnt] >> 24) == vox) ++cnt;
+      for (int e0 = 0; e0 < cnt; e0 += 4) {  // 4 gathers in flight, then the 4 sequential float adds (PCL's order)
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          q[u] = e0 + u < cnt ? pts[(int)(keys[t + e0 + u] & 0xFFFFFF)] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (e0 + u < cnt)
+            sx = __fadd_rn(sx, q[u].x), sy = __fadd_rn(sy, q[u].y), sz = __fadd_rn(sz, q[u].z), si = __fadd_rn(si, q[u].w);
       }
       const float c = (float)cnt;
       out[slot] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));

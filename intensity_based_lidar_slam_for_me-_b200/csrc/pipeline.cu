@@ -17,7 +17,7 @@ namespace ilsm {
 
 // voxel edge of the "last frame" search structures: the odometry gate is 5 m (DISTANCE_SQ_THRESHOLD 25,
 // laserOdometry.cpp:31), the clouds are sparse (a few thousand points)
-constexpr float kOdomCell = 2.5f;
+constexpr float kOdomCell = 1.0f;
 
 struct SlamH {
   Ctx* ctx = nullptr;

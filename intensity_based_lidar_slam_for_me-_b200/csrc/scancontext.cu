@@ -82,57 +82,93 @@ __global__ void sc_query_prep_kernel(const float* __restrict__ qdesc, ScQuery* q
       n2 += v * v;
     }
     q->key[c] = s / kNR;
-    q->norm[c] = sqrt(n2);
+    const double nrm = sqrt(n2);
+    q->norm[c] = nrm != 0.0 ? 1.0 / nrm : 0.0;  // inverse column norm; 0 marks an empty column
   }
 }
 
-constexpr int kScWarps = 4;
+constexpr int kScWarps = 8;
+constexpr int kTopKMax = 16;
 
-// one warp per candidate keyframe, grid-stride
-__global__ void __launch_bounds__(kScWarps * 32)
-    sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, double* __restrict__ out_dist,
-                    int* __restrict__ out_shift) {
-  __shared__ double qd[kDesc];
-  __shared__ double qn[kNS], qk[kNS];
-  __shared__ float cd[kScWarps][kDesc];
-  __shared__ double ck[kScWarps][kNS], cn[kScWarps][kNS];
-  for (int i = threadIdx.x; i < kDesc; i += blockDim.x) qd[i] = q->desc[i];
-  if (threadIdx.x < kNS) qn[threadIdx.x] = q->norm[threadIdx.x], qk[threadIdx.x] = q->key[threadIdx.x];
-  __syncthreads();
+// shared-memory layout of the scoring kernel (dynamic): the query once per block, one candidate per warp.
+// Candidates are staged as doubles (float -> double once, at load) so that the inner products are LDS.64 + DFMA.
+struct ScWarpSmem {
+  double cd[kDesc];     // candidate descriptor
+  double ck2[2 * kNS];  // candidate sector key, stored twice: circshift index c - s + 60 needs no wrap
+  double cin[kNS];      // inverse column norms (0 = empty column)
+  u64 tk_d[kTopKMax];   // this warp's running top-k: distance bits, id, shift (ascending (d, id))
+  int tk_id[kTopKMax];
+  int tk_sh[kTopKMax];
+};
+struct ScBlockSmem {
+  double qd[kDesc];
+  double qin[kNS], qk[kNS];
+  ScWarpSmem w[kScWarps];
+};
+
+__device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { return da < db || (da == db && ia < ib); }
+
+// One warp per candidate keyframe, grid-stride; every warp keeps its k best (distance, id) in shared memory, the
+// block merges its warps' lists at the end and writes k entries, a small second kernel merges the blocks' lists.
+//   fastAlignUsingVkey  (Scancontext.cpp:104-124): argmin_s || qk - circshift(ck, s) ||, first minimum wins
+//   distDirectSC        (:79-101)                : 1 - mean over columns with both norms != 0 of cos(col_q, col_c)
+//   distanceBtnScanContext (:126-157)            : the 7 shifts around the aligned one, ascending, first minimum wins
+__global__ void __launch_bounds__(kScWarps * 32, 2)
+    sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, int k, u64* __restrict__ part_d,
+                    int* __restrict__ part_id, int* __restrict__ part_sh) {
+  extern __shared__ __align__(16) unsigned char sc_smem_raw[];
+  ScBlockSmem& sm = *reinterpret_cast<ScBlockSmem*>(sc_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ScWarpSmem& w = sm.w[warp];
+  for (int i = threadIdx.x; i < kDesc; i += blockDim.x) sm.qd[i] = q->desc[i];
+  if (threadIdx.x < kNS) sm.qin[threadIdx.x] = q->norm[threadIdx.x], sm.qk[threadIdx.x] = q->key[threadIdx.x];
+  if (lane < kTopKMax) w.tk_d[lane] = ~0ull, w.tk_id[lane] = INT_MAX, w.tk_sh[lane] = 0;
+  __syncthreads();
   const int nwarps = gridDim.x * kScWarps;
   for (int cand = blockIdx.x * kScWarps + warp; cand < n; cand += nwarps) {
-    // stage the candidate (4800 B, coalesced 128-bit loads)
+    // stage the candidate: 4800 B of coalesced 128-bit loads, widened to double
     const float4* src = reinterpret_cast<const float4*>(db + (size_t)cand * kDesc);
-    float4* dst = reinterpret_cast<float4*>(cd[warp]);
-    for (int i = lane; i < kDesc / 4; i += 32) dst[i] = __ldg(src + i);
-    __syncwarp();
-    // sector key (column means) and column norms of the candidate
-    for (int c = lane; c < kNS; c += 32) {
-      double s = 0, n2 = 0;
-#pragma unroll 4
-      for (int r = 0; r < kNR; ++r) {
-        const double v = (double)cd[warp][r * kNS + c];
-        s += v;
-        n2 += v * v;
-      }
-      ck[warp][c] = s / kNR;
-      cn[warp][c] = sqrt(n2);
+    for (int i = lane; i < kDesc / 4; i += 32) {
+      const float4 v = __ldg(src + i);
+      double2* dst = reinterpret_cast<double2*>(w.cd + 4 * i);
+      dst[0] = make_double2((double)v.x, (double)v.y);
+      dst[1] = make_double2((double)v.z, (double)v.w);
     }
     __syncwarp();
-    // fastAlignUsingVkey: argmin_s || qk - circshift(ck, s) ||, first minimum wins
+    // sector key (column means) and inverse column norms of the candidate
+    for (int c = lane; c < kNS; c += 32) {
+      double s = 0, n2 = 0;
+      const double* col = w.cd + c;
+#pragma unroll
+      for (int r = 0; r < kNR; ++r) {
+        const double v = col[r * kNS];
+        s += v;
+        n2 = fma(v, v, n2);  // v is a widened float: v * v is exact in double, so the fused form rounds identically
+      }
+      const double key = s / kNR;
+      w.ck2[c] = key, w.ck2[c + kNS] = key;
+      w.cin[c] = n2 != 0.0 ? frsqrt(n2) : 0.0;
+    }
+    __syncwarp();
+    // fastAlignUsingVkey: lane -> shifts s = lane and lane + 32, each a sequential sum over the 60 columns; the two
+    // sums are independent dependency chains and share the query-key load
     double best = 10000000;
     int arg = 0;
-    for (int s = lane; s < kNS; s += 32) {
-      double ss = 0;
+    {
+      const int s1 = lane + 32 < kNS ? lane + 32 : lane;  // lanes 28..31 repeat their first shift (result unused)
+      const double* ckp0 = w.ck2 + (kNS - lane);          // ckp[c] = ck[(c - s) mod 60]
+      const double* ckp1 = w.ck2 + (kNS - s1);
+      double ss0 = 0, ss1 = 0;
+#pragma unroll 10
       for (int c = 0; c < kNS; ++c) {
-        int cb = c - s;
-        cb += cb < 0 ? kNS : 0;
-        const double d = qk[c] - ck[warp][cb];
-        ss += d * d;
+        const double qv = sm.qk[c];
+        const double d0 = qv - ckp0[c], d1 = qv - ckp1[c];
+        ss0 += d0 * d0;
+        ss1 += d1 * d1;
       }
-      const double nrm = sqrt(ss);
-      if (nrm < best) best = nrm, arg = s;  // ascending s within the lane
+      const double n0 = sqrt(ss0), n1 = sqrt(ss1);
+      if (n0 < best) best = n0, arg = lane;  // ascending s within the lane, first minimum wins
+      if (lane + 32 < kNS && n1 < best) best = n1, arg = lane + 32;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -140,130 +176,181 @@ __global__ void __launch_bounds__(kScWarps * 32)
       const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
       if (ob < best || (ob == best && oa < arg)) best = ob, arg = oa;
     }
-    // distDirectSC on the 7 shifts around the aligned one, ascending shift order, first minimum wins
+    // the 7 shifts around the aligned one in ascending order: a run arg-3 .. arg+3 that may wrap once
     int shifts[7];
+    {
+      const int lo = arg - 3, hi = arg + 3;
+      // wrapped members (lo + t < 0 -> +60, lo + t > 59 -> -60) sort before / after the unwrapped ones
+      const int n_hi_wrap = hi > kNS - 1 ? hi - (kNS - 1) : 0;  // values 0 .. n_hi_wrap-1 come first
+      const int n_lo_wrap = lo < 0 ? -lo : 0;                   // values 60+lo .. 59 come last
 #pragma unroll
-    for (int k = 0; k < 7; ++k) shifts[k] = (arg + (k - 3) + kNS) % kNS;
-    // sort ascending (7 values, a rotation: at most one wrap point)
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = 0; b < 6 - a; ++b)
-        if (shifts[b] > shifts[b + 1]) {
-          const int t = shifts[b];
-          shifts[b] = shifts[b + 1];
-          shifts[b + 1] = t;
-        }
+      for (int t = 0; t < 7; ++t) {
+        int v;
+        if (t < n_hi_wrap) v = t;                                    // wrapped high end
+        else if (t >= 7 - n_lo_wrap) v = kNS + lo + (t - (7 - n_lo_wrap));  // wrapped low end
+        else v = lo + n_lo_wrap + (t - n_hi_wrap);                   // the unwrapped run, ascending
+        shifts[t] = v;
+      }
+    }
     double sum[7];
     int eff[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) sum[k] = 0.0, eff[k] = 0;
+    for (int t = 0; t < 7; ++t) sum[t] = 0.0, eff[t] = 0;
     for (int j = lane; j < kNS; j += 32) {
-      const double nq = qn[j];
+      const double iq = sm.qin[j];
+      int jb[7];
+      double dot[7];
+      const double* ccol[7];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        int jb = j - shifts[k];
-        jb += jb < 0 ? kNS : 0;
-        const double nc = cn[warp][jb];
-        if (nq != 0.0 && nc != 0.0) {
-          double dot = 0;
-#pragma unroll 4
-          for (int r = 0; r < kNR; ++r) dot += qd[r * kNS + j] * (double)cd[warp][r * kNS + jb];
-          sum[k] += dot / (nq * nc);
-          eff[k] += 1;
+      for (int t = 0; t < 7; ++t) {
+        int b = j - shifts[t];
+        jb[t] = b + (b < 0 ? kNS : 0);
+        ccol[t] = w.cd + jb[t];
+        dot[t] = 0.0;
+      }
+      const double* qcol = sm.qd + j;
+#pragma unroll
+      for (int r = 0; r < kNR; ++r) {  // fully unrolled: immediate shared-memory offsets, 1 + 7 loads and 7 DFMA per row
+        const double qv = qcol[r * kNS];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) dot[t] = fma(qv, ccol[t][r * kNS], dot[t]);  // products of widened floats are exact
+      }
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const double ic = w.cin[jb[t]];
+        if (iq != 0.0 && ic != 0.0) {
+          sum[t] += dot[t] * (iq * ic);
+          eff[t] += 1;
         }
       }
     }
-    double bd = 10000000;  // min_sc_dist / argmin_shift initial values of distanceBtnScanContext
-    int bs = 0;
+    // warp totals: the 7 effective-column counts (each <= 60) travel packed in one 64-bit word
+    u64 effp = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      double sk = sum[k];
-      int ek = eff[k];
+    for (int t = 0; t < 7; ++t) effp |= (u64)eff[t] << (8 * t);
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        sk += __shfl_xor_sync(0xffffffffu, sk, off);
-        ek += __shfl_xor_sync(0xffffffffu, ek, off);
-      }
-      const double d = ek > 0 ? 1.0 - sk / (double)ek : __longlong_as_double(0x7ff0000000000000ll);
-      if (d < bd) bd = d, bs = shifts[k];
+    for (int off = 16; off > 0; off >>= 1) {
+      effp += __shfl_xor_sync(0xffffffffu, effp, off);
+#pragma unroll
+      for (int t = 0; t < 7; ++t) sum[t] += __shfl_xor_sync(0xffffffffu, sum[t], off);
     }
-    if (lane == 0) {
-      out_dist[cand] = bd;
-      out_shift[cand] = bs;
+    // lane t < 7 turns shift t's totals into a distance (one division per lane instead of seven per warp), then the
+    // first minimum in ascending shift order wins: arg-min on (distance, t)
+    double myd = __longlong_as_double(0x7ff0000000000000ll);
+    int mysh = 0, myt = 99;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      if (lane == t) {
+        const int ek = (int)((effp >> (8 * t)) & 0xFF);
+        if (ek > 0) myd = 1.0 - sum[t] / (double)ek;
+        mysh = shifts[t], myt = t;
+      }
+    }
+    const bool cand_ok = lane < 7 && myd < 10000000.0;  // min_sc_dist starts at 10000000 (strict <)
+    if (!cand_ok) myd = 10000000.0, mysh = 0, myt = 99;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, myd, off);
+      const int os = __shfl_xor_sync(0xffffffffu, mysh, off);
+      const int ot = __shfl_xor_sync(0xffffffffu, myt, off);
+      if (od < myd || (od == myd && ot < myt)) myd = od, mysh = os, myt = ot;
+    }
+    const double bd = __shfl_sync(0xffffffffu, myd, 0);
+    const int bs = __shfl_sync(0xffffffffu, mysh, 0);
+    if (lane == 0) {  // insertion into this warp's sorted top-k
+      const u64 kd = (u64)__double_as_longlong(bd);
+      if (sc_key_less(kd, cand, w.tk_d[k - 1], w.tk_id[k - 1])) {
+        int pos = k - 1;
+        while (pos > 0 && sc_key_less(kd, cand, w.tk_d[pos - 1], w.tk_id[pos - 1])) {
+          w.tk_d[pos] = w.tk_d[pos - 1], w.tk_id[pos] = w.tk_id[pos - 1], w.tk_sh[pos] = w.tk_sh[pos - 1];
+          --pos;
+        }
+        w.tk_d[pos] = kd, w.tk_id[pos] = cand, w.tk_sh[pos] = bs;
+      }
     }
     __syncwarp();
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // k-way merge of the warps' lists (heads only): k x kScWarps comparisons
+    int head[kScWarps];
+#pragma unroll
+    for (int i = 0; i < kScWarps; ++i) head[i] = 0;
+    for (int j = 0; j < k; ++j) {
+      int bw = 0;
+#pragma unroll
+      for (int i = 1; i < kScWarps; ++i) {
+        const ScWarpSmem &a = sm.w[i], &b = sm.w[bw];
+        if (sc_key_less(a.tk_d[head[i]], a.tk_id[head[i]], b.tk_d[head[bw]], b.tk_id[head[bw]])) bw = i;
+      }
+      const ScWarpSmem& b = sm.w[bw];
+      const size_t o = (size_t)blockIdx.x * k + j;
+      part_d[o] = b.tk_d[head[bw]], part_id[o] = b.tk_id[head[bw]], part_sh[o] = b.tk_sh[head[bw]];
+      // exhausted lists present (~0, INT_MAX) sentinels: k <= kTopKMax keeps head within the array
+      if (head[bw] < kTopKMax - 1) head[bw]++;
+      else sm.w[bw].tk_d[kTopKMax - 1] = ~0ull, sm.w[bw].tk_id[kTopKMax - 1] = INT_MAX;
+    }
+  }
 }
 
-// top-k of (dist, id) over n scored candidates by one block; k <= 16
-constexpr int kTopKMax = 16;
-struct ScKey {
-  u64 d;  // distance bits (>= 0 => monotone as unsigned)
-  int id;
-};
-__device__ __forceinline__ bool sc_less(const ScKey& a, const ScKey& b) { return a.d < b.d || (a.d == b.d && a.id < b.id); }
-
-__global__ void __launch_bounds__(1024) sc_topk_kernel(const double* __restrict__ dist, const int* __restrict__ shift, int n,
-                                                       int id_offset, int k, double* __restrict__ o_dist,
-                                                       int* __restrict__ o_id, int* __restrict__ o_shift) {
+// Final merge of the blocks' lists (n = blocks * k entries, a few thousand): every thread holds up to kFinalPer
+// entries, k rounds of a block-wide arg-min on (distance bits, id).
+constexpr int kFinalThreads = 1024, kFinalPer = 8;
+__global__ void __launch_bounds__(kFinalThreads)
+    sc_topk_final_kernel(const u64* __restrict__ part_d, const int* __restrict__ part_id, const int* __restrict__ part_sh, int n,
+                         int id_offset, int k, double* __restrict__ o_dist, int* __restrict__ o_id, int* __restrict__ o_shift) {
   __shared__ u64 s_d[32];
-  __shared__ int s_id[32];
+  __shared__ int s_id[32], s_sh[32];
   __shared__ int s_win;
-  ScKey best[kTopKMax];
+  u64 d[kFinalPer];
+  int id[kFinalPer], sh[kFinalPer];
 #pragma unroll
-  for (int j = 0; j < kTopKMax; ++j) best[j].d = ~0ull, best[j].id = INT_MAX;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    ScKey c;
-    c.d = (u64)__double_as_longlong(dist[i]);
-    c.id = i;
-    if (sc_less(c, best[kTopKMax - 1])) {
-      best[kTopKMax - 1] = c;
-#pragma unroll
-      for (int s = kTopKMax - 1; s > 0; --s) {
-        if (sc_less(best[s], best[s - 1])) {
-          const ScKey t = best[s];
-          best[s] = best[s - 1];
-          best[s - 1] = t;
-        }
-      }
-    }
+  for (int e = 0; e < kFinalPer; ++e) {
+    const int i = threadIdx.x + e * kFinalThreads;
+    const bool in = i < n;
+    d[e] = in ? part_d[i] : ~0ull;
+    id[e] = in ? part_id[i] : INT_MAX;
+    sh[e] = in ? part_sh[i] : 0;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int round = 0; round < k; ++round) {
-    ScKey m = best[0];
+    u64 md = ~0ull;
+    int mi = INT_MAX, ms = 0;
+#pragma unroll
+    for (int e = 0; e < kFinalPer; ++e)
+      if (sc_key_less(d[e], id[e], md, mi)) md = d[e], mi = id[e], ms = sh[e];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      ScKey o;
-      o.d = __shfl_xor_sync(0xffffffffu, m.d, off);
-      o.id = __shfl_xor_sync(0xffffffffu, m.id, off);
-      if (sc_less(o, m)) m = o;
+      const u64 od = __shfl_xor_sync(0xffffffffu, md, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+      const int os = __shfl_xor_sync(0xffffffffu, ms, off);
+      if (sc_key_less(od, oi, md, mi)) md = od, mi = oi, ms = os;
     }
-    if (lane == 0) s_d[warp] = m.d, s_id[warp] = m.id;
+    if (lane == 0) s_d[warp] = md, s_id[warp] = mi, s_sh[warp] = ms;
     __syncthreads();
     if (warp == 0) {
-      ScKey w;
-      w.d = s_d[lane], w.id = s_id[lane];
+      u64 wd = s_d[lane];
+      int wi = s_id[lane], wsft = s_sh[lane];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
-        ScKey o;
-        o.d = __shfl_xor_sync(0xffffffffu, w.d, off);
-        o.id = __shfl_xor_sync(0xffffffffu, w.id, off);
-        if (sc_less(o, w)) w = o;
+        const u64 od = __shfl_xor_sync(0xffffffffu, wd, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, off);
+        const int os = __shfl_xor_sync(0xffffffffu, wsft, off);
+        if (sc_key_less(od, oi, wd, wi)) wd = od, wi = oi, wsft = os;
       }
       if (lane == 0) {
-        s_win = w.id;
-        const bool have = w.id != INT_MAX;
-        o_dist[round] = have ? __longlong_as_double((long long)w.d) : __longlong_as_double(0x7ff0000000000000ll);
-        o_id[round] = have ? w.id + id_offset : -1;
-        o_shift[round] = have ? shift[w.id] : 0;
+        s_win = wi;
+        const bool have = wi != INT_MAX;
+        o_dist[round] = have ? __longlong_as_double((long long)wd) : __longlong_as_double(0x7ff0000000000000ll);
+        o_id[round] = have ? wi + id_offset : -1;
+        o_shift[round] = have ? wsft : 0;
       }
     }
     __syncthreads();
-    if (best[0].id == s_win && s_win != INT_MAX) {
+    const int win = s_win;
+    if (win != INT_MAX) {
 #pragma unroll
-      for (int s = 0; s < kTopKMax - 1; ++s) best[s] = best[s + 1];
-      best[kTopKMax - 1].d = ~0ull, best[kTopKMax - 1].id = INT_MAX;
+      for (int e = 0; e < kFinalPer; ++e)
+        if (id[e] == win) d[e] = ~0ull, id[e] = INT_MAX;
     }
     __syncthreads();
   }
@@ -355,18 +442,24 @@ int ScDb::make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc) {
 int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, double* d_dist, int* d_id, int* d_shift) {
   if (k < 1 || k > kTopKMax) return fail(ILSM_ERR_INVALID_ARG, "sc_query: k must be in [1,16]");
   if (n_search < 0 || n_search > count) return fail(ILSM_ERR_INVALID_ARG, "sc_query: n_search exceeds the database");
+  // two resident blocks of 8 warps per SM; fewer blocks when the shard is small.  The final merge holds at most
+  // kFinalThreads * kFinalPer entries.
+  long long blocks = ((long long)n_search + kScWarps - 1) / kScWarps, cap = (long long)ctx->sm_count * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks * k > (long long)kFinalThreads * kFinalPer) blocks = (long long)kFinalThreads * kFinalPer / k;
+  if (blocks < 1) blocks = 1;
   int rc;
-  if ((rc = query.reserve(1)) || (rc = dist.reserve(n_search + 1)) || (rc = shift.reserve(n_search + 1))) return rc;
+  if ((rc = query.reserve(1)) || (rc = part_d.reserve((size_t)blocks * kTopKMax)) ||
+      (rc = part_id.reserve((size_t)blocks * kTopKMax)) || (rc = part_sh.reserve((size_t)blocks * kTopKMax)))
+    return rc;
   cudaStream_t s = ctx->stream;
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
   sc_query_prep_kernel<<<1, 64, 0, s>>>(d_qdesc, query.p);
-  if (n_search > 0) {
-    long long blocks = ((long long)n_search + kScWarps - 1) / kScWarps, cap = (long long)ctx->sm_count * 4;
-    if (blocks > cap) blocks = cap;
-    sc_score_kernel<<<(unsigned)blocks, kScWarps * 32, 0, s>>>(db.p, n_search, query.p, dist.p, shift.p);
-    count_launches(1);
-  }
-  sc_topk_kernel<<<1, 1024, 0, s>>>(dist.p, shift.p, n_search, id_offset, k, d_dist, d_id, d_shift);
-  count_launches(2);
+  sc_score_kernel<<<(unsigned)blocks, kScWarps * 32, sizeof(ScBlockSmem), s>>>(db.p, n_search, query.p, k, part_d.p, part_id.p,
+                                                                              part_sh.p);
+  sc_topk_final_kernel<<<1, kFinalThreads, 0, s>>>(part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id,
+                                                   d_shift);
+  count_launches(3);
   return check_launch("sc_query");
 }
 

@@ -33,6 +33,39 @@ def test_knn_bit_exact(ctx, oracle_mod, cfg_small, k, cell):
     lm.close()
 
 
+@pytest.mark.parametrize("k,cell,max_dist", [(5, 0.0, 0.0), (5, 0.5, 0.0), (1, 0.0, 0.0), (5, 0.0, 1.0), (8, 2.0, 0.0)])
+def test_knn_large_query_set(ctx, oracle_mod, ilsm, cfg_full, k, cell, max_dist):
+    """A whole organised frame as the query set (grid-stride path, no-returns included) plus far and out-of-map queries;
+    small and large launches agree."""
+    S = ilsm.synth
+    c = cfg_full
+    rng = np.random.default_rng(55 + k)
+    m = c["map_surf"]
+    R = S.quat_to_mat(c["q_true"])
+    frame_world = (c["cloud"][:, :3].astype(np.float64) @ R.T + c["t_true"]).astype(np.float32)  # 65536 coherent queries
+    far = rng.uniform(-400, 400, (500, 3)).astype(np.float32)
+    q = np.concatenate([frame_world, far, _queries(rng, m, 3000, 2.0)])
+    lm = ctx.new_map().set_input_cloud(m, cell)
+    idx, d2 = lm.nearest_k_search(q, k, max_dist=max_dist)
+    sel = np.concatenate([rng.choice(65536, 3000, replace=False), np.arange(65536, len(q))])
+    ri, rd = oracle_mod.knn_kdtree(m, q[sel], k)
+    if max_dist > 0:
+        inside = rd < max_dist * max_dist
+        assert inside.any() and (~inside).any()
+        assert np.array_equal(idx[sel][inside], ri[inside]) and np.array_equal(d2[sel][inside], rd[inside])
+    else:
+        assert np.array_equal(d2[sel], rd)
+        assert np.array_equal(idx[sel], ri)
+    # a small launch (one resident wave) gives the same answers
+    i2, dd2 = lm.nearest_k_search(q[:4000], k, max_dist=max_dist)
+    if max_dist > 0:
+        ins = dd2 < max_dist * max_dist
+        assert np.array_equal(i2[ins], idx[:4000][ins])
+    else:
+        assert np.array_equal(i2, idx[:4000]) and np.array_equal(dd2, d2[:4000])
+    lm.close()
+
+
 def test_knn_strided_pcl_points_and_max_dist(ctx, oracle_mod, cfg_small):
     """pcl::PointXYZI layout (32-byte stride) for both map and queries; bounded search is exact inside max_dist."""
     rng = np.random.default_rng(7)
@@ -263,4 +296,33 @@ def test_register_dev_matches_host_entry(ctx, ilsm, cfg_small):
     ctx.sync()
     out = pose.cpu().numpy()
     assert np.array_equal(out[:4], q) and np.array_equal(out[4:], t)
+    mc.close(), ms.close()
+
+
+def test_knn_matches_reference_nanoflann_golden(ctx):
+    """The CUDA k-NN against the committed outputs of the reference's own vendored nanoflann (tests/golden)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "knn_nanoflann.npz"))
+    for cell in (0.0, 0.7):
+        lm = ctx.new_map().set_input_cloud(g["map"], cell)
+        for k in (1, 5, 8):
+            idx, d2 = lm.nearest_k_search(g["queries"], k)
+            assert np.array_equal(idx, g[f"idx_k{k}"]) and np.array_equal(d2, g[f"d2_k{k}"]), (cell, k)
+        lm.close()
+
+
+def test_register_matches_oracle_regression_golden(ctx, ilsm):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_regression.npz"))
+    cs = ilsm.synth.config1(n_map=6000)
+    mc, ms = ctx.new_map().set_input_cloud(cs["map_corner"]), ctx.new_map().set_input_cloud(cs["map_surf"])
+    q, t, rep = ctx.register(mc, ms, cs["corner"], cs["surf"], cs["q0"], cs["t0"])
+    assert np.linalg.norm(t - g["pose"][4:]) < POSE_M and ilsm.synth.quat_angle(q, g["pose"][:4]) < POSE_RAD
+    assert [rep.pass_[p].termination for p in range(2)] == list(g["term"])
+    assert [rep.pass_[p].num_edge_factors for p in range(2)] == [int(g["factors"][0]), int(g["factors"][2])]
+    assert [rep.pass_[p].num_plane_factors for p in range(2)] == [int(g["factors"][1]), int(g["factors"][3])]
+    f = ctx.extract_features(cs["cloud"])
+    for key in ("sharp_idx", "less_sharp_idx", "flat_idx"):
+        assert np.array_equal(f[key], g[key]), key
+    assert len(f["less_flat"]) == int(g["n_less_flat"])
     mc.close(), ms.close()

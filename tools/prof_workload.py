@@ -2,7 +2,8 @@
 """One pass over every hot kernel at representative sizes, bracketed by cudaProfilerStart/Stop, for
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python tools/prof_workload.py
 Sections (select with --only): reg (config-1 registration: builds, associate, solve), knn (N = 2M, Q = 65536),
-jtj (1M factors), sc (20k-keyframe shard), fe (projection + feature extraction)."""
+jtj (1M factors), sc (20k-keyframe shard), fe (projection + feature extraction), slam (one frame of the full loop after
+20 frames of a corridor sequence)."""
 from __future__ import annotations
 
 import argparse
@@ -89,6 +90,16 @@ def main():
             ctx.cloud_handler(cloud)
             ctx.extract_features(cloud)
         work.append(fe)
+
+    if "slam" in only:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from sequence_bench import corridor_sequence
+        clouds, _ = corridor_sequence(S, 24, 0x5EED0100, 40.0)
+        slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+        for k in range(20):
+            slam.frame(clouds[k])
+        it = iter(clouds[20:])
+        work.append(lambda: slam.frame(next(it)))
 
     for w in work:  # warm-up (allocation, module load)
         w()
