@@ -9,7 +9,8 @@ A "step" is one pass of the reference's per-frame mapping hot section over one s
   value : device-timed (CUDA events on the library's stream), map + feature stacks already resident in HBM.
   e2e   : the same step through the host-pointer C ABI (ilsm_map_build x2 + ilsm_register) from pinned host
           buffers, host<->device copies inside the timed region, wall-clocked around the blocking calls.
-  roofline     : the dominant kernel (associate_kernel: k-NN + fit) timed alone, algorithmic bytes / time.
+  roofline     : the step's kernels timed alone (solve, associate, map build), the dominant one as `roofline`,
+                 algorithmic bytes / time; `config3` adds the bandwidth-regime point of the k-NN and J^T J kernels.
   cpu_baseline : the CPU oracle (a port of the reference path, single thread like the reference's mapping
                  thread) on a bounded sample of the same workload.
 
@@ -60,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -98,6 +99,80 @@ class ClockSampler:
 def workload(seed_shift=0):
     import ilsm_b200 as ilsm
     return ilsm.synth.config1(n_map=N_MAP, seed_shift=seed_shift)
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step's kernels, from the committed ncu --set full
+    capture of this workload (profiles/r01_ncu_traffic.json; null when absent)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        return json.load(open(p))["config1"]
+    except Exception:
+        return {}
+
+
+def config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts):
+    """The bandwidth regime of the two hot kernels (BASELINE configs[2], largest point of tools/sweep.py): exact 5-NN of
+    a whole 65536-point frame in a 2M-point map, and the J^T J kernel on 4M factors (64 frames' worth in one launch)."""
+    S = ilsm.synth
+    c = S.config1(n_map=2_000_000)
+    m = np.zeros((len(c["map_corner"]) + len(c["map_surf"]), 4), np.float32)
+    m[:, :3] = np.concatenate([c["map_corner"], c["map_surf"]])[:, :3]
+    d_m = torch.from_numpy(m).to(dev)
+    R = S.quat_to_mat(c["q_true"])
+    w = np.zeros((65536, 4), np.float32)
+    w[:, :3] = (c["cloud"][:, :3].astype(np.float64) @ R.T + c["t_true"]).astype(np.float32)
+    d_q = torch.from_numpy(w).to(dev)
+    d_idx = torch.empty((65536, 5), dtype=torch.int32, device=dev)
+    d_d2 = torch.empty((65536, 5), dtype=torch.float32, device=dev)
+    out = {}
+
+    def timed(fn, reps=10):
+        ts = []
+        with torch.cuda.stream(ext):
+            for _ in range(3):
+                fn()
+            ctx.sync()
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                fn()
+                e1.record(ext)
+                ctx.sync()
+                ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    gm = ctx.new_map()
+    with torch.cuda.stream(ext):
+        gm.build_dev(d_m.data_ptr(), len(m), 16)
+    t = timed(lambda: gm.knn_dev(d_q.data_ptr(), 65536, 16, 5, 1.0, d_idx.data_ptr(), d_d2.data_ptr()))
+    byt = 16 * len(m) + 56 * 65536
+    out["knn5"] = {"N": len(m), "Q": 65536, "ms": t, "queries_per_s": 65536 / t * 1e3, "algorithmic_bytes": byt,
+                   "achieved_GBs": byt / t / 1e6, "frac": byt / t / 1e6 / peak,
+                   "bound": "instruction issue (ncu: 63% SM throughput, 85% L2 hit, 5 MB of the 32 MB map touched)"}
+    # J^T J: 4M factors produced by associating 64 copies of the frame against the same map
+    hc, hs = np.zeros((len(c["map_corner"]), 4), np.float32), np.zeros((len(c["map_surf"]), 4), np.float32)
+    hc[:, :3], hs[:, :3] = c["map_corner"][:, :3], c["map_surf"][:, :3]
+    d_mc, d_ms = torch.from_numpy(hc).to(dev), torch.from_numpy(hs).to(dev)
+    mc, ms = ctx.new_map(), ctx.new_map()
+    Qb = 1 << 22
+    sens = np.zeros((Qb, 4), np.float32)
+    sens[:, :3] = c["cloud"][np.arange(Qb) % 65536, :3]
+    d_c, d_s = torch.from_numpy(sens[:Qb // 8].copy()).to(dev), torch.from_numpy(sens[Qb // 8:].copy()).to(dev)
+    pose_t = torch.from_numpy(np.concatenate([c["q_true"], c["t_true"]])).to(dev)
+    out32 = torch.zeros(32, dtype=torch.float64, device=dev)
+    with torch.cuda.stream(ext):
+        mc.build_dev(d_mc.data_ptr(), len(hc), 16)
+        ms.build_dev(d_ms.data_ptr(), len(hs), 16)
+        ctx.associate_dev(mc, ms, d_c.data_ptr(), Qb // 8, d_s.data_ptr(), Qb - Qb // 8, 16, pose_t.data_ptr(), opts)
+        ctx.sync()
+    t = timed(lambda: ctx.eval_normal_eq_dev(pose_t.data_ptr(), out32.data_ptr()))
+    byt = Qb * 84
+    out["jtj"] = {"factors": Qb, "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
+                  "achieved_GBs": byt / t / 1e6, "frac": byt / t / 1e6 / peak, "bound": "hbm"}
+    gm.close(), mc.close(), ms.close()
+    return out
 
 
 def pad4(a):
@@ -261,23 +336,30 @@ def run_gpu(args, rank, world, local_rank):
         h2d = h_mc.nbytes + h_ms.nbytes + h_c.nbytes + h_s.nbytes + 56
         d2h = 56 + 8 + 8 * 48
 
-        # ---- dominant kernel alone (associate_kernel: pose transform + exact 5-NN + fit), CUDA events
-        reps = 20
+        # ---- the step's kernels timed alone on the library stream (CUDA events, L2 flushed before each batch)
+        def timed(fn, reps=20, batches=5):
+            ts = []
+            for _ in range(batches):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                for _ in range(reps):
+                    fn()
+                e1.record(ext)
+                ctx.sync()
+                ts.append(e0.elapsed_time(e1) / reps)
+            return float(np.median(ts))
+
         mc.build_dev(d_mc.data_ptr(), len(h_mc), 16)
         ms.build_dev(d_ms.data_ptr(), len(h_ms), 16)
-        kt = []
-        for _ in range(5):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(ext)
-            for _ in range(reps):
-                ctx.associate_dev(mc, ms, d_c.data_ptr(), len(h_c), d_s.data_ptr(), len(h_s), 16, d_pose0.data_ptr(), opts)
-            e1.record(ext)
-            ctx.sync()
-            kt.append(e0.elapsed_time(e1) / reps)
-        assoc_ms = float(np.median(kt))
+        assoc_ms = timed(lambda: ctx.associate_dev(mc, ms, d_c.data_ptr(), len(h_c), d_s.data_ptr(), len(h_s), 16,
+                                                   d_pose0.data_ptr(), opts))
+        # ceres::Solve replacement: factors from the association at the initial guess, LM <= 4 iterations from that guess
+        solve_ms = timed(lambda: ctx.solve_dev(d_pose0.data_ptr(), opts.max_num_iterations, opts.huber_a))
+        solve_ms -= 0.0  # includes the 1-warp pose upload kernel (~2 us), reported as is
+        build_ms = timed(lambda: (mc.build_dev(d_mc.data_ptr(), len(h_mc), 16), ms.build_dev(d_ms.data_ptr(), len(h_ms), 16),
+                                  mc.join(), ms.join()))
         clocks = sampler.stop()
-
     # ---- aggregate over ranks (max time)
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -288,11 +370,24 @@ def run_gpu(args, rank, world, local_rank):
 
     peak, peak_src = load_peaks()
     nq = len(h_c) + len(h_s)
-    # algorithmic bytes of one associate launch: map points 16 B each (both maps), stack point 16 B in,
-    # 5 x (idx + d2) = 40 B of k-NN result, factor record 84 B out
-    assoc_bytes = 16 * (len(h_mc) + len(h_ms)) + nq * (16 + 40 + 84)
-    achieved = assoc_bytes / (assoc_ms * 1e-3) / 1e9
-
+    n_map = len(h_mc) + len(h_ms)
+    step_ms = dev_ms_max / args.steps
+    # algorithmic bytes per launch: every input read once, every output written once
+    assoc_bytes = 16 * n_map + nq * (16 + 84)           # map points + stack point in + factor record out
+    solve_bytes = nq * 84 + 1024                        # factor records read once (kept in registers across the LM evaluations)
+    build_bytes = 48 * n_map                            # points in, keys/ranks r+w, grouped points out (both maps)
+    traffic = ncu_traffic()
+    kernels = []
+    for name, ms_k, byt, per_step in (("solve_cluster_kernel", solve_ms, solve_bytes, 2), ("associate_kernel", assoc_ms, assoc_bytes, 2),
+                                      ("grid_{clear,count,alloc,scatter}_kernel x2 maps", build_ms, build_bytes, 1)):
+        kernels.append({"kernel": name, "launch_ms": ms_k, "launches_per_step": per_step,
+                        "share_of_step": per_step * ms_k / step_ms, "algorithmic_bytes": int(byt),
+                        "achieved_GBs": byt / (ms_k * 1e-3) / 1e9, "frac": byt / (ms_k * 1e-3) / 1e9 / peak,
+                        "ncu_dram_bytes": traffic.get(name.split(" ")[0])})
+    dom = max(kernels[:2], key=lambda k: k["share_of_step"])
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, reps_cpu, el = cpu_registrations_per_s(c, args.cpu_seconds, 5)
@@ -312,14 +407,19 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / args.steps, "timing": "host wall clock around the blocking C-ABI calls"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "associate_kernel<32>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes": int(assoc_bytes), "kernel_ms": assoc_ms,
-                         "note": "config-1 sizes are launch/latency-bound (2.0 MB per launch = 0.3 us at peak); see "
-                                 "DESIGN.md and the config-3 sweep (tools/sweep.py) for the bandwidth regime"},
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBs"], "peak": peak,
+                         "unit": "GB/s", "frac": dom["frac"], "traffic": dom["ncu_dram_bytes"], "peak_source": peak_src,
+                         "algorithmic_bytes": dom["algorithmic_bytes"], "kernel_ms": dom["launch_ms"],
+                         "kernels": kernels,
+                         "note": "config-1 sizes are latency-bound, not bandwidth-bound: one launch moves 0.2-2 MB "
+                                 "(0.03-0.3 us at peak) and the LM loop is a serial chain of <= 5 evaluations with a "
+                                 "cluster barrier each; the bandwidth regime of the same kernels is in `config3` below "
+                                 "and in profiles/ (tools/sweep.py)"},
             "clocks": clocks,
             "pose_error_m": err_t,
         }
+        if sweep is not None:
+            line["config3"] = sweep
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -331,11 +431,12 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 (bandwidth regime) measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -211,6 +211,10 @@ ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, doubl
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q_xyzw[4], double t_xyz[3], int max_num_iterations, double huber_a,
                ilsm_solve_summary* summary);
 
+/* Device-resident variant for timing the solve kernel alone: the factors held by the context, start pose from
+ * d_pose7_in (NULL: continue from the pose in the context); nothing is copied back and the call does not synchronise. */
+ILSM_API int ilsm_solve_dev(ilsm_ctx* ctx, const double* d_pose7_in, int max_num_iterations, double huber_a);
+
 /* ---------------------------------------------------------- laserMapping: device-resident rolling cube map ---- */
 typedef struct ilsm_cubemap ilsm_cubemap;
 

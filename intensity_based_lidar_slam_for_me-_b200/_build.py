@@ -38,16 +38,16 @@ def nvcc_path():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """One nvcc -c per source (in parallel), then one link into libilsm_cuda.so."""
-    if not force and not _stale():
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB, obj_dir: str = OBJ) -> str:
+    """One nvcc -c per source (in parallel), then one link into libilsm_cuda.so (or `lib`, for instrumented variants)."""
+    if not force and lib == LIB and not _stale():
+        return lib
+    os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in sources():
         name = os.path.basename(src)
-        obj = os.path.join(OBJ, name[:-3] + ".o")
-        cmd = ([nvcc_path()] + NVCC_FLAGS + ["-fmad=" + FMAD.get(name, "false")] +
+        obj = os.path.join(obj_dir, name[:-3] + ".o")
+        cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-fmad=" + FMAD.get(name, "false")] +
                (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
         procs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
@@ -58,8 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             print(out)
         objs.append(obj)
-    r = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs,
+    r = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs,
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return LIB
+    return lib

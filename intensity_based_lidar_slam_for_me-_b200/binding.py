@@ -131,6 +131,7 @@ def load_library(path: str | None = None):
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
         "ilsm_eval_normal_eq_dev": (i32, [vp, vp, f64, vp]),
+        "ilsm_solve_dev": (i32, [vp, vp, i32, f64]),
         "ilsm_solve": (i32, [vp, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
     }
     for name, (res, args) in sig.items():
@@ -313,6 +314,9 @@ class Context:
 
     def eval_normal_eq_dev(self, d_pose_ptr, d_out32_ptr, huber_a=0.1):
         _check(self._lib.ilsm_eval_normal_eq_dev(self._h, d_pose_ptr, huber_a, d_out32_ptr))
+
+    def solve_dev(self, d_pose_in_ptr, max_num_iterations=4, huber_a=0.1):
+        _check(self._lib.ilsm_solve_dev(self._h, d_pose_in_ptr, max_num_iterations, huber_a))
 
     def solve(self, q, t, max_num_iterations=4, huber_a=0.1):
         qq = np.array(q, np.float64)

@@ -787,6 +787,20 @@ ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, doubl
   return eval_only_launch(&c, d_out32);
 }
 
+ILSM_API int ilsm_solve_dev(ilsm_ctx* ctx, const double* d_pose7_in, int max_num_iterations, double huber_a) {
+  if (!ctx) return fail(ILSM_ERR_INVALID_ARG, "solve_dev: null argument");
+  if (max_num_iterations < 0) max_num_iterations = 0;
+  if (max_num_iterations > 200) max_num_iterations = 200;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (d_pose7_in) {
+    pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, const_cast<double*>(d_pose7_in), nullptr, 0);
+    count_launches(1);
+  }
+  return c.solve_launch(max_num_iterations, huber_a, 0);
+}
+
 ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_iterations, double huber_a,
                ilsm_solve_summary* summary) {
   if (!ctx || !q || !t) return fail(ILSM_ERR_INVALID_ARG, "solve: null argument");

@@ -36,32 +36,45 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
                                   uint32_t mask, int log2_size, float4* __restrict__ orig,
                                   uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
                                   uint32_t* counters) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float x, y, z;
-  bool ok = load_point(src, stride_f, i, x, y, z);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool in = i < n;
+  float x = 0.f, y = 0.f, z = 0.f;
+  bool ok = in && load_point(src, stride_f, i, x, y, z);
   // w keeps the caller's intensity channel (LOAM clouds carry scanID + 0.1*relTime there, laserOdometry.cpp:461)
-  orig[i] = make_float4(x, y, z, ioff >= 0 ? __ldg(src + (size_t)i * stride_f + ioff) : 0.f);
+  if (in) orig[i] = make_float4(x, y, z, ioff >= 0 ? __ldg(src + (size_t)i * stride_f + ioff) : 0.f);
   int cx = 0, cy = 0, cz = 0;
   if (ok) {
     float ux = __fmul_rn(x, inv_cell), uy = __fmul_rn(y, inv_cell), uz = __fmul_rn(z, inv_cell);
     ok = fabsf(ux) < (float)kCoordLim && fabsf(uy) < (float)kCoordLim && fabsf(uz) < (float)kCoordLim;
     cx = __float2int_rd(ux), cy = __float2int_rd(uy), cz = __float2int_rd(uz);
   }
-  if (!ok) {
+  if (in && !ok) {
     slot_of[i] = 0xFFFFFFFFu;
     atomicAdd(&counters[2], 1u);
-    return;
   }
-  u64 key = pack_voxel(cx, cy, cz);
-  uint32_t slot = hash_voxel(key, log2_size);
-  for (;;) {
-    u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
-    if (prev == kEmptyKey || prev == key) break;
-    slot = (slot + 1) & mask;
+  // warp-aggregated claim: map clouds arrive voxel-ordered (VoxelGrid output, cube by cube), so the lanes of a warp
+  // mostly share a handful of voxels -- one atomicCAS + one atomicAdd per distinct voxel of the warp instead of one
+  // per point.  All 32 lanes take part in the match; lanes without a point carry a key nobody shares.
+  const u64 key = ok ? pack_voxel(cx, cy, cz) : (kEmptyKey - 1ull - (u64)lane);
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  if (ok) {
+    const int leader = __ffs(peers) - 1;
+    uint32_t slot = 0, base = 0;
+    if (lane == leader) {
+      slot = hash_voxel(key, log2_size);
+      for (;;) {
+        u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) break;
+        slot = (slot + 1) & mask;
+      }
+      base = atomicAdd(&cells[slot].count, (uint32_t)__popc(peers));
+    }
+    slot = __shfl_sync(peers, slot, leader);
+    base = __shfl_sync(peers, base, leader);
+    slot_of[i] = slot;
+    rank_of[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   }
-  slot_of[i] = slot;
-  rank_of[i] = atomicAdd(&cells[slot].count, 1u);
 }
 
 // Every occupied slot gets a contiguous range of the sorted array (warp-aggregated atomicAdd on one cursor) and
@@ -81,17 +94,28 @@ __global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* coun
       for (int a = 0; a < 3; ++a) lo[a] = hi[a] = c[a];
     }
   }
-  uint32_t lane = threadIdx.x & 31, inc = cnt;
+  // block-wide exclusive prefix of the counts, ONE atomicAdd on the cursor per block
+  __shared__ uint32_t s_wsum[8];
+  __shared__ uint32_t s_base;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = cnt;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     uint32_t v = __shfl_up_sync(0xffffffffu, inc, off);
     if (lane >= (uint32_t)off) inc += v;
   }
-  uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-  uint32_t base = 0;
-  if (lane == 31 && total) base = atomicAdd(&counters[0], total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  if (i < size && cnt) cells[i].start = base + inc - cnt;
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  uint32_t wbase = 0, btotal = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < (int)warp) wbase += s_wsum[w];
+    btotal += s_wsum[w];
+  }
+  if (threadIdx.x == 0) s_base = btotal ? atomicAdd(&counters[0], btotal) : 0u;
+  __syncthreads();
+  if (i < size && cnt) cells[i].start = s_base + wbase + inc - cnt;
   // bounding box
 #pragma unroll
   for (int a = 0; a < 3; ++a) {

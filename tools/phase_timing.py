@@ -6,8 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ilsm_b200 as ilsm
 from ilsm_b200 import _build
 dbg = os.path.join(_build.HERE, "libilsm_cuda_dbg.so")
-cmd = [_build.nvcc_path()] + _build.NVCC_FLAGS + ["-DILSM_DEBUG_TIMING", "-o", dbg] + _build.sources()
-subprocess.run(cmd, check=True)
+_build.build(force=True, extra_flags=["-DILSM_DEBUG_TIMING"], lib=dbg, obj_dir=_build.OBJ + "_dbg")
 ilsm.binding._lib = None
 lib = ilsm.load_library(dbg)
 lib.ilsm_debug_stamps.argtypes = [C.c_void_p, C.c_void_p]
