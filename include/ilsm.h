@@ -346,6 +346,35 @@ ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int 
 ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
                             int* n_out);
 
+/* --------------------------------------- intensity-image feature back end (ORB matching + 3D-3D alignment) ---- */
+
+/* cv::DMatch layout (queryIdx, trainIdx, imgIdx, distance): a std::vector<cv::DMatch> can be filled in place. */
+typedef struct ilsm_dmatch {
+  int32_t queryIdx;
+  int32_t trainIdx;
+  int32_t imgIdx;
+  float distance;
+} ilsm_dmatch;
+
+/* Brute-force Hamming matching of 256-bit ORB descriptors (rows of cv::Mat CV_8U, 32 bytes each): every query row
+ * takes its nearest train row, first minimum wins; with cross_check != 0 a pair survives only if it is mutual.
+ * matches: the surviving pairs in query order (capacity n_cur); good: the same pairs sorted by (distance, queryIdx),
+ * truncated to ceil(n_matches * keep_fraction) (capacity n_cur).  At most 16384 query descriptors.
+ * Replaces: cv::BFMatcher(cv::NORM_HAMMING, true).match(cur, prev, matches); std::sort(matches); first 30 % / 20 %
+ *           intensity_feature_tracker.cpp:631-648, 678-686. */
+ILSM_API int ilsm_orb_match(ilsm_ctx* ctx, const uint8_t* cur_desc, int n_cur, const uint8_t* prev_desc, int n_prev, int desc_bytes,
+                            int cross_check, double keep_fraction, ilsm_dmatch* matches, int* n_matches, ilsm_dmatch* good,
+                            int* n_good);
+
+/* 3D-3D alignment of matched points: minimise sum rho(|q * src_i + t - dst_i|^2), HuberLoss(huber_a),
+ * EigenQuaternionParameterization, Levenberg-Marquardt on the device (the same solver as ilsm_solve); q, t are read
+ * as the initial value ({0,0,0,1},{0,0,0} in the reference) and overwritten.  Points are 3 floats with a byte stride
+ * (12 for cv::Point3f).  summary->num_edge_factors counts the point pairs.
+ * Replaces: feature_tracker::p2p_calculateRandT  intensity_feature_tracker.cpp:880-928 (front_end_residual,
+ *           lidarFeaturePointsFunction.hpp:21-58; max_num_iterations 20). */
+ILSM_API int ilsm_align_points(ilsm_ctx* ctx, const float* src_xyz, const float* dst_xyz, int n, int stride_bytes, double q_xyzw[4],
+                               double t_xyz[3], int max_num_iterations, double huber_a, ilsm_solve_summary* summary);
+
 /* ------------------------------------------------------ K5: ScanContext loop-closure candidate scoring ---- */
 typedef struct ilsm_sc ilsm_sc; /* keyframe descriptor database (one shard when split across ranks) */
 

@@ -65,6 +65,7 @@ class SlamStats(C.Structure):
                 ("cubemap", CubeMapStats)]
 
 
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
 _lib = None
@@ -127,6 +128,8 @@ def load_library(path: str | None = None):
         "ilsm_slam_destroy": (None, [vp]),
         "ilsm_slam_cubemap": (vp, [vp]),
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
+        "ilsm_orb_match": (i32, [vp, vp, i32, vp, i32, i32, i32, f64, vp, C.POINTER(i32), vp, C.POINTER(i32)]),
+        "ilsm_align_points": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
         "ilsm_launch_count": (C.c_longlong, []),
         "ilsm_eval_normal_eq": (i32, [vp, vp, vp, f64, C.POINTER(f64), vp, vp]),
@@ -283,6 +286,29 @@ class Context:
                                        stride, _ptr(qq), _ptr(tt), C.byref(opts) if opts is not None else None,
                                        C.byref(rep), _ptr(fac) if factors_only else None))
         return fac if factors_only else (qq, tt, rep)
+
+    # -- cv::BFMatcher(NORM_HAMMING, crossCheck).match + sort + best fraction (intensity_feature_tracker.cpp:631-648) --
+    def orb_match(self, cur_desc, prev_desc, cross_check=True, keep_fraction=0.3):
+        a = np.ascontiguousarray(cur_desc, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(prev_desc, np.uint8).reshape(-1, 32)
+        m = np.zeros(max(len(a), 1), DMATCH_DTYPE)
+        g = np.zeros(max(len(a), 1), DMATCH_DTYPE)
+        nm, ng = C.c_int(0), C.c_int(0)
+        _check(self._lib.ilsm_orb_match(self._h, _ptr(a), len(a), _ptr(b), len(b), 32, 1 if cross_check else 0,
+                                        float(keep_fraction), _ptr(m), C.byref(nm), _ptr(g), C.byref(ng)))
+        return m[:nm.value], g[:ng.value]
+
+    # -- feature_tracker::p2p_calculateRandT (intensity_feature_tracker.cpp:880-928) ---------------
+    def align_points(self, src_xyz, dst_xyz, q=(0, 0, 0, 1), t=(0, 0, 0), max_num_iterations=20, huber_a=0.1):
+        s = np.ascontiguousarray(np.asarray(src_xyz, np.float32)[:, :3])
+        d = np.ascontiguousarray(np.asarray(dst_xyz, np.float32)[:, :3])
+        if len(s) != len(d):
+            raise ValueError("src and dst must pair up")
+        qq, tt = np.array(q, np.float64), np.array(t, np.float64)
+        sm = SolveSummary()
+        _check(self._lib.ilsm_align_points(self._h, _ptr(s), _ptr(d), len(s), 12, _ptr(qq), _ptr(tt), max_num_iterations,
+                                           huber_a, C.byref(sm)))
+        return qq, tt, sm
 
     def associate_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
                       opts: RegOpts | None = None):

@@ -475,6 +475,29 @@ __device__ __forceinline__ void eval_factor(int type, const float4 pf, const dou
     jr[2] = sc * 2.0 * (Rp.x * fa.y - Rp.y * fa.x);
     jr[3] = sc * fa.x, jr[4] = sc * fa.y, jr[5] = sc * fa.z;
     acc_row(acc, jr, sc * r0);
+  } else if (type == 3) {
+    // front_end_residual (hpp:21-58): r = q * src + t - dst;  J = [-2 [Rp]x, I]   (fa = destination point)
+    const double rr[3] = {lp.x - fa.x, lp.y - fa.y, lp.z - fa.z};
+    const double sq = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
+    double rho0 = sq, sc = 1.0;
+    if (huber_a > 0.0 && sq > huber_a * huber_a) {
+      const double irr = frsqrt(sq);
+      rho0 = 2.0 * huber_a * (sq * irr) - huber_a * huber_a;
+      sc = fsqrt(huber_a * irr);
+    }
+    acc[0] += 0.5 * rho0;
+    acc[28] += 1.0;  // counted with the 3-row (edge-like) blocks
+    const double S[3][3] = {{0, 2 * Rp.z, -2 * Rp.y}, {-2 * Rp.z, 0, 2 * Rp.x}, {2 * Rp.y, -2 * Rp.x, 0}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      double jr[6];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        jr[c] = sc * S[a][c];
+        jr[3 + c] = a == c ? sc : 0.0;
+      }
+      acc_row(acc, jr, sc * rr[a]);
+    }
   }
 }
 

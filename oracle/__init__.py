@@ -440,3 +440,59 @@ class Slam:
         qt_odom = np.concatenate([self.q_w_curr, self.t_w_curr])
         qt_map, msums, st = self.cube.frame(lsharp, lflat, qt_odom)
         return qt_odom, qt_map, dict(features=f, odometry=odo, mapping=msums, cubemap=st)
+
+
+# ------------------------------------------------------------------------------------------------
+# intensity-image feature matching back end (intensity_feature_tracker.cpp:631-738, 880-928)
+# ------------------------------------------------------------------------------------------------
+_POPC = np.array([bin(i).count("1") for i in range(256)], np.uint16)
+
+
+def hamming_matrix(a, b):
+    """All-pairs Hamming distances of two uint8 descriptor sets (n1 x 32, n2 x 32)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    out = np.zeros((len(a), len(b)), np.int32)
+    for i in range(len(a)):  # row by row keeps memory small
+        out[i] = _POPC[np.bitwise_xor(b, a[i])].sum(axis=1)
+    return out
+
+
+def bf_match_hamming(cur, prev, cross_check=True):
+    """cv::BFMatcher(NORM_HAMMING, crossCheck).match(cur, prev) restated (OpenCV batchDistance, K = 1): every query
+    takes its nearest train descriptor, first minimum wins (lowest train index); with crossCheck the pair is kept only
+    if the query is also the nearest (first minimum = lowest query index) of that train descriptor.
+    Returns (queryIdx, trainIdx, distance) in query order."""
+    if len(cur) == 0 or len(prev) == 0:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, np.float32)
+    d = hamming_matrix(cur, prev)
+    best_t = d.argmin(axis=1)  # numpy argmin returns the first minimum
+    keep = np.ones(len(cur), bool)
+    if cross_check:
+        best_q = d.argmin(axis=0)
+        keep = best_q[best_t] == np.arange(len(cur))
+    qi = np.nonzero(keep)[0].astype(np.int32)
+    return qi, best_t[qi].astype(np.int32), d[qi, best_t[qi]].astype(np.float32)
+
+
+def good_matches(qi, ti, dist, fraction=0.3):
+    """std::sort(matches) + the first `i < matches.size() * fraction` (intensity_feature_tracker.cpp:643-648); DMatch
+    orders by distance only, equal distances keep query order here (the declared tie-break)."""
+    order = np.lexsort((qi, dist))
+    n_good = int(np.ceil(len(qi) * float(fraction)))
+    sel = order[:n_good]
+    return qi[sel], ti[sel], dist[sel]
+
+
+def align_points(src_xyz, dst_xyz, qt0=(0, 0, 0, 1, 0, 0, 0), max_iter=20, huber_a=0.1):
+    """p2p_calculateRandT (intensity_feature_tracker.cpp:880-928): front_end_residual blocks, HuberLoss(0.1),
+    EigenQuaternionParameterization, LM <= 20 iterations from the identity."""
+    src = np.asarray(src_xyz, np.float32)[:, :3]
+    dst = np.asarray(dst_xyz, np.float32)[:, :3]
+    f = np.zeros(len(src), FACTOR_DTYPE)
+    f["type"] = 3
+    f["src"] = np.arange(len(src))
+    f["p"] = src.astype(np.float64)
+    f["a"] = dst.astype(np.float64)
+    return solve(f, np.array(qt0, np.float64), max_iter, huber_a)

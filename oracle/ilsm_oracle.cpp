@@ -387,6 +387,16 @@ void eval_factor(const OrcFactor& f, const Quat& q, const V3& t, double huber_a,
     J[0][0] = jr.x, J[0][1] = jr.y, J[0][2] = jr.z;
     J[0][3] = n.x, J[0][4] = n.y, J[0][5] = n.z;
     nres = 1;
+  } else if (f.type == 3) {
+    // front_end_residual (lidarFeaturePointsFunction.hpp:21-58): r = q * src + t - dst; a = dst point.
+    r[0] = lp.x - f.a[0], r[1] = lp.y - f.a[1], r[2] = lp.z - f.a[2];
+    double S[3][3] = {{0, 2 * Rp.z, -2 * Rp.y}, {-2 * Rp.z, 0, 2 * Rp.x}, {2 * Rp.y, -2 * Rp.x, 0}};  // -2 [Rp]x
+    for (int i = 0; i < 3; ++i)
+      for (int c = 0; c < 3; ++c) {
+        J[i][c] = S[i][c];
+        J[i][3 + c] = i == c ? 1.0 : 0.0;
+      }
+    nres = 3;
   } else {
     return;
   }

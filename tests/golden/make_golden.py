@@ -8,6 +8,8 @@ knn_nanoflann.npz   outputs of the REFERENCE'S OWN vendored nanoflann 1.3.2 (/ro
                     here: a 3000-point map, 400 queries (near, far, exact duplicates), k = 1 / 5 / 8.
 ringkey_nanoflann.npz  the reference's ScanContext ring-key 10-NN set-up (KDTreeVectorOfVectorsAdaptor, Scancontext.cpp:270-295)
                     on 120 synthetic descriptors (regenerated from seeds, checksummed).
+orb_match_cv2.npz   outputs of cv2.BFMatcher(NORM_HAMMING, crossCheck).match -- the very library call the reference makes
+                    (intensity_feature_tracker.cpp:631-635) -- on 300 x 280 synthetic 256-bit descriptors with ties.
 oracle_regression.npz  outputs of the CPU oracle (NOT of the reference: the reference cannot be built) on
                     a small registration / front-end / ScanContext case; they pin the oracle and the CUDA path against
                     silent drift, nothing more.
@@ -64,7 +66,21 @@ def main():
                         n_cloud=len(f["cloud"]), sharp_idx=f["sharp_idx"], less_sharp_idx=f["less_sharp_idx"],
                         flat_idx=f["flat_idx"], n_less_flat=len(f["less_flat"]),
                         label_hist=np.bincount(f["label"] + 1, minlength=4), sc_dist=d10, sc_id=i10, sc_shift=s10)
-    for n in ("knn_nanoflann.npz", "ringkey_nanoflann.npz", "oracle_regression.npz"):
+    # ORB matching: outputs of the real OpenCV (cv2) BFMatcher the reference calls (intensity_feature_tracker.cpp:631-635)
+    import cv2
+    a = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (280, 32), dtype=np.uint8)
+    b[:150] = a[50:200] ^ (rng.random((150, 32)) < 0.04).astype(np.uint8)  # true correspondences with a few flipped bits
+    b[200] = b[3]     # duplicated train rows and query rows: first-minimum tie-breaks
+    a[250] = a[60]
+    og = {"cur": a, "prev": b, "opencv_version": np.array(cv2.__version__)}
+    for cc in (0, 1):
+        m = cv2.BFMatcher(cv2.NORM_HAMMING, bool(cc)).match(a, b)
+        og[f"q_cc{cc}"] = np.array([x.queryIdx for x in m], np.int32)
+        og[f"t_cc{cc}"] = np.array([x.trainIdx for x in m], np.int32)
+        og[f"d_cc{cc}"] = np.array([x.distance for x in m], np.float32)
+    np.savez_compressed(os.path.join(HERE, "orb_match_cv2.npz"), **og)
+    for n in ("knn_nanoflann.npz", "ringkey_nanoflann.npz", "oracle_regression.npz", "orb_match_cv2.npz"):
         print(n, os.path.getsize(os.path.join(HERE, n)), "bytes")
 
 
