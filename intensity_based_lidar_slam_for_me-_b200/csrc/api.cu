@@ -39,6 +39,7 @@ struct Pose7 {
 };
 
 __global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double huber_a) {
+  pdl_entry();
   for (int i = 0; i < 4; ++i) st->xq[i] = p.v[i];
   for (int i = 0; i < 3; ++i) st->xt[i] = p.v[4 + i];
   if (also_candidate) {
@@ -50,6 +51,7 @@ __global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double
 
 // candidate pose <- device pose (ilsm_eval_normal_eq_dev)
 __global__ void set_pose_dev_kernel(LmState* st, const double* __restrict__ pose7, double huber_a) {
+  pdl_entry();
   const int i = threadIdx.x;
   if (i < 4) st->cq[i] = pose7[i];
   if (i >= 4 && i < 7) st->ct[i - 4] = pose7[i];
@@ -57,6 +59,7 @@ __global__ void set_pose_dev_kernel(LmState* st, const double* __restrict__ pose
 }
 
 __global__ void pose_io_kernel(LmState* st, double* pose7, ilsm_reg_report* report, int direction) {
+  pdl_entry();
   // direction 0: pose7 -> state ; 1: state -> pose7 (+ report)
   int t = threadIdx.x;
   if (direction == 0) {
@@ -371,10 +374,10 @@ ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const 
   ILSM_CUDA(cudaSetDevice(c.device));
   if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
     return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
-  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, nullptr, 0);
+  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, (ilsm_reg_report*)nullptr, 0));
   count_launches(2);
   if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
-  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, d_report, 1);
+  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, d_report, 1));
   return check_launch("register_dev");
 }
 
@@ -388,7 +391,7 @@ ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const
   Ctx& c = ctx->c;
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
-  pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, const_cast<double*>(d_pose7), nullptr, 0);
+  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, const_cast<double*>(d_pose7), (ilsm_reg_report*)nullptr, 0));
   count_launches(1);
   return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false);
 }
@@ -410,7 +413,7 @@ ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const floa
   Pose7 p;
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
+  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 0, 0.0));
   count_launches(1);
   if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
   // pose (7 doubles, xq/xt are adjacent) and the report come back through pinned memory
@@ -443,7 +446,7 @@ ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const flo
   Pose7 p;
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
+  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 1, o.huber_a));
   count_launches(1);
   const bool want_knn = knn_idx != nullptr && knn_d2 != nullptr;
   if ((rc = c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, want_knn))) return rc;
@@ -481,7 +484,7 @@ ILSM_API int ilsm_odometry(ilsm_ctx* ctx, ilsm_map* last_corner, ilsm_map* last_
   Pose7 p;
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, o.huber_a);
+  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 1, o.huber_a));
   count_launches(1);
   const int n = nsh + nfl;
   if (factors) {
@@ -754,7 +757,7 @@ ILSM_API int ilsm_eval_normal_eq(ilsm_ctx* ctx, const double q[4], const double 
   Pose7 p;
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 1, huber_a);
+  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 1, huber_a));
   count_launches(1);
   int rc;
   if ((rc = c.partials.reserve(64))) return rc;
@@ -782,7 +785,7 @@ ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, doubl
   Ctx& c = ctx->c;
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
-  set_pose_dev_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, d_pose7, huber_a);
+  ILSM_CUDA(launch_pdl(set_pose_dev_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, huber_a));
   count_launches(1);
   return eval_only_launch(&c, d_out32);
 }
@@ -795,7 +798,7 @@ ILSM_API int ilsm_solve_dev(ilsm_ctx* ctx, const double* d_pose7_in, int max_num
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
   if (d_pose7_in) {
-    pose_io_kernel<<<1, 32, 0, c.stream>>>(c.lm.p, const_cast<double*>(d_pose7_in), nullptr, 0);
+    ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, const_cast<double*>(d_pose7_in), (ilsm_reg_report*)nullptr, 0));
     count_launches(1);
   }
   return c.solve_launch(max_num_iterations, huber_a, 0);
@@ -812,7 +815,7 @@ ILSM_API int ilsm_solve(ilsm_ctx* ctx, double q[4], double t[3], int max_num_ite
   Pose7 p;
   for (int i = 0; i < 4; ++i) p.v[i] = q[i];
   for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  set_pose_kernel<<<1, 1, 0, c.stream>>>(c.lm.p, p, 0, 0.0);
+  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 0, 0.0));
   count_launches(1);
   int rc;
   if ((rc = c.solve_launch(max_num_iterations, huber_a, 0))) return rc;

@@ -19,12 +19,14 @@ namespace ilsm {
 
 __global__ void cube_gather_kernel(const float4* __restrict__ slabs, int cap, const GatherItem* __restrict__ items,
                                    float4* __restrict__ out) {
+  pdl_entry();
   const GatherItem it = items[blockIdx.y];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < it.count; t += gridDim.x * blockDim.x)
     out[it.offset + t] = slabs[(size_t)it.slab * cap + t];
 }
 
 __global__ void cube_zero_counts_kernel(int* cnt, const int* __restrict__ slabs, int n) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) cnt[slabs[i]] = 0;
 }
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(1024)
                        int nc_host, int ns_host, const LmState* __restrict__ st, int world_frame, int cenW, int cenH, int cenD,
                        const int* __restrict__ slab_of, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
                        float4* __restrict__ world_tmp, int tmp_stride, int* err) {
+  pdl_entry();
   extern __shared__ u64 keys[];
   const bool corner = blockIdx.x == 0;
   const float4* stack = corner ? stack_c : stack_s;
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(1024)
     cube_filter_kernel(const int* __restrict__ valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
                        float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err) {
+  pdl_entry();
   extern __shared__ u64 keys[];
   const int v = blockIdx.x >> 1;
   const bool corner = (blockIdx.x & 1) == 0;
@@ -235,8 +239,8 @@ int CubeMapH::roll(const double t[3]) {
     const int n = (int)recycled.size() < kCNum ? (int)recycled.size() : kCNum;
     for (int i = 0; i < n; ++i) p[i] = recycled[i];
     ILSM_CUDA(cudaMemcpyAsync(zero_list.p, p, n * sizeof(int), cudaMemcpyHostToDevice, s));
-    cube_zero_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(cnt_c.p, zero_list.p, n);
-    cube_zero_counts_kernel<<<(n + 255) / 256, 256, 0, s>>>(cnt_s.p, zero_list.p, n);
+    ILSM_CUDA(launch_pdl(cube_zero_counts_kernel, dim3((n + 255) / 256), dim3(256), 0, s, cnt_c.p, zero_list.p, n));
+    ILSM_CUDA(launch_pdl(cube_zero_counts_kernel, dim3((n + 255) / 256), dim3(256), 0, s, cnt_s.p, zero_list.p, n));
     ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
     ILSM_CUDA(cudaStreamSynchronize(s));
     count_launches(2);
@@ -260,18 +264,15 @@ int CubeMapH::gather(int* n_mc, int* n_ms) {
   if ((rc = from_c.reserve(tot_c + 4)) || (rc = from_s.reserve(tot_s + 4))) return rc;
   if (n_valid == 0) return ILSM_OK;
   ILSM_CUDA(cudaMemcpyAsync(items.p, it, 250 * sizeof(GatherItem), cudaMemcpyHostToDevice, s));
-  if (tot_c > 0) cube_gather_kernel<<<dim3(8, n_valid), 256, 0, s>>>(slabs_c.p, cap, items.p, from_c.p);
-  if (tot_s > 0) cube_gather_kernel<<<dim3(8, n_valid), 256, 0, s>>>(slabs_s.p, cap, items.p + 125, from_s.p);
+  if (tot_c > 0) ILSM_CUDA(launch_pdl(cube_gather_kernel, dim3(8, n_valid), dim3(256), 0, s, slabs_c.p, cap, items.p, from_c.p));
+  if (tot_s > 0) ILSM_CUDA(launch_pdl(cube_gather_kernel, dim3(8, n_valid), dim3(256), 0, s, slabs_s.p, cap, items.p + 125, from_s.p));
   count_launches(2);
   return check_launch("cube_gather");
 }
 
 int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_frame) {
   cudaStream_t s = ctx->stream;
-  cube_insert_kernel<<<2, 1024, kVoxelBlockMax * sizeof(u64), s>>>(stack_c.p, stack_s.p, d_counts, nc_host, ns_host, ctx->lm.p,
-                                                                    world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p,
-                                                                    slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p,
-                                                                    kVoxelBlockMax, err.p);
+  ILSM_CUDA(launch_pdl(cube_insert_kernel, dim3(2), dim3(1024), kVoxelBlockMax * sizeof(u64), s, stack_c.p, stack_s.p, d_counts, nc_host, ns_host, ctx->lm.p, world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p, kVoxelBlockMax, err.p));
   count_launches(1);
   return check_launch("cube_insert");
 }
@@ -282,8 +283,7 @@ int CubeMapH::filter_valid() {
   int* p = pin.p + kCNum + 1024;
   for (int v = 0; v < n_valid; ++v) p[v] = slab_of[valid[v]];
   ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
-  cube_filter_kernel<<<2 * n_valid, 1024, kVoxelBlockMax * sizeof(u64), s>>>(valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p,
-                                                                             cap, line_res, plane_res, scratch.p, err.p);
+  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), kVoxelBlockMax * sizeof(u64), s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p));
   count_launches(1);
   return check_launch("cube_filter");
 }
@@ -426,6 +426,7 @@ static int stage_clouds(CubeMapH& m, const float* corner, int nc, const float* s
 }
 
 __global__ void pack_xyzi_kernel(const float* __restrict__ in, int n, int stride_f, int ioff, float4* __restrict__ out) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = in + (size_t)i * stride_f;
@@ -454,8 +455,8 @@ ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, in
     const size_t off_s = ((size_t)kc * stride_bytes + 255) & ~(size_t)255;
     const float* d_c = m.raw.p;
     const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
-    if (kc) pack_xyzi_kernel<<<(kc + 255) / 256, 256, 0, c.stream>>>(d_c, kc, stride_bytes / 4, ioff, m.stack_c.p);
-    if (ks) pack_xyzi_kernel<<<(ks + 255) / 256, 256, 0, c.stream>>>(d_s, ks, stride_bytes / 4, ioff, m.stack_s.p);
+    if (kc) ILSM_CUDA(launch_pdl(pack_xyzi_kernel, dim3((kc + 255) / 256), dim3(256), 0, c.stream, d_c, kc, stride_bytes / 4, ioff, m.stack_c.p));
+    if (ks) ILSM_CUDA(launch_pdl(pack_xyzi_kernel, dim3((ks + 255) / 256), dim3(256), 0, c.stream, d_s, ks, stride_bytes / 4, ioff, m.stack_s.p));
     count_launches(2);
     if ((rc = m.insert(nullptr, kc, ks, 1))) return rc;
     ILSM_CUDA(cudaStreamSynchronize(c.stream));  // staging buffers are reused by the next chunk

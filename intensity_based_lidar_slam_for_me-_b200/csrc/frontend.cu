@@ -32,6 +32,7 @@ __device__ __forceinline__ void project_one(float x, float y, float z, float int
 __global__ void project_kernel(const float* __restrict__ cloud, int n, int stride_f, int ioff,
                                unsigned char* __restrict__ img_range, unsigned char* __restrict__ img_inten,
                                float4* __restrict__ track) {
+  pdl_entry();
   const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i0 >= n) return;
   unsigned char r8[4] = {0, 0, 0, 0}, i8[4] = {0, 0, 0, 0};
@@ -80,6 +81,7 @@ constexpr int kStFirst = 0, kStLast = 1, kStStar = 2, kStErr = 3, kStRing = 4, k
               kStFlat = 196, kStLFlat = 260, kStInts = 324;
 
 __global__ void fe_init_kernel(int* st) {
+  pdl_entry();
   const int i = threadIdx.x;
   if (i < kStInts) st[i] = (i == kStFirst || i == kStStar) ? INT_MAX : (i == kStLast ? -1 : 0);
 }
@@ -88,6 +90,7 @@ __global__ void fe_init_kernel(int* st) {
 __global__ void fe_tag_kernel(const float* __restrict__ in, int n, int stride_f, float thr2,
                               unsigned char* __restrict__ scanid, float* __restrict__ ori_raw, int* st,
                               int* __restrict__ chunk_hist) {
+  pdl_entry();
   __shared__ int hist[kRings];
   if (threadIdx.x < kRings) hist[threadIdx.x] = 0;
   __syncthreads();
@@ -155,6 +158,7 @@ __device__ __forceinline__ float ori_first_half(float ori, float startOri) {
 // pass 2: the halfPassed latch = first valid point (input order) whose first-half azimuth exceeds startOri + pi
 __global__ void fe_star_kernel(const float* __restrict__ in, int n, int stride_f, const unsigned char* __restrict__ scanid,
                                const float* __restrict__ ori_raw, int* st) {
+  pdl_entry();
   if (st[kStLast] < 0) return;
   const OriRef ref = ori_reference(in, stride_f, st);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,6 +174,7 @@ __global__ void fe_star_kernel(const float* __restrict__ in, int n, int stride_f
 // pass 3a: per ring, exclusive prefix of the chunk histograms (one block per ring, chunks scanned 256 at a time)
 constexpr int kFeChunk = 256;
 __global__ void __launch_bounds__(256) fe_scan_kernel(const int* __restrict__ chunk_hist, int chunks, int* __restrict__ chunk_base) {
+  pdl_entry();
   __shared__ int wsum[8];
   __shared__ int carry_s;
   const int ring = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(kFeChunk) fe_bucket_kernel(const float* __rest
                                                              const float* __restrict__ ori_raw, const int* __restrict__ st,
                                                              const int* __restrict__ chunk_base, float4* __restrict__ cloud,
                                                              int* __restrict__ src_index) {
+  pdl_entry();
   __shared__ int ring_off[kRings];
   __shared__ int wcnt[kFeChunk / 32][kRings];
   if (st[kStLast] < 0) return;
@@ -254,6 +260,7 @@ __global__ void __launch_bounds__(kFeChunk) fe_bucket_kernel(const float* __rest
 // pass 4: curvature over the concatenated cloud (scanRegistration.cpp:397-412), exact left-to-right float sums
 __global__ void fe_curvature_kernel(const float4* __restrict__ cloud, const int* __restrict__ st, float* __restrict__ curv,
                                     int* __restrict__ label, unsigned char* __restrict__ picked) {
+  pdl_entry();
   int N = 0;
   for (int r = 0; r < kRings; ++r) N += st[kStRing + r];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +305,7 @@ __device__ __forceinline__ void ring_bounds(const int* st, int ring, int& S, int
 // (std::sort(cloudSortInd + sp, cloudSortInd + ep + 1, comp) with the tie order fixed by index)
 __global__ void __launch_bounds__(256) fe_sort_kernel(const float* __restrict__ curv, int* __restrict__ st,
                                                       int* __restrict__ sort_ind) {
+  pdl_entry();
   __shared__ u64 keys[kMaxSeg];
   const int ring = blockIdx.x / 6, j = blockIdx.x % 6;
   int S, E;
@@ -351,6 +359,7 @@ __global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ 
                                                      int* __restrict__ label, unsigned char* __restrict__ g_picked,
                                                      int* __restrict__ ring_sharp, int* __restrict__ ring_lsharp,
                                                      int* __restrict__ ring_flat) {
+  pdl_entry();
   __shared__ float4 s_cloud[kPickCap];
   __shared__ float s_curv[kPickCap];
   __shared__ int s_sort[kPickCap];
@@ -468,6 +477,7 @@ __global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) fe_lessflat_kernel(const float4* __restrict__ cloud, const int* __restrict__ label,
                                                           int* __restrict__ st, float4* __restrict__ ring_pts,
                                                           float4* __restrict__ ring_out, int ring_cap, float leaf) {
+  pdl_entry();
   __shared__ u64 keys[kMaxRingLF];
   __shared__ int s_m;
   const int ring = blockIdx.x;
@@ -518,6 +528,7 @@ __global__ void fe_compact_kernel(const int* __restrict__ st, const int* __restr
                                   const float4* __restrict__ ring_out, int ring_cap, int* __restrict__ sharp,
                                   int* __restrict__ lsharp, int* __restrict__ flat, float4* __restrict__ lflat,
                                   int* __restrict__ counts /* n_cloud, n_sharp, n_lsharp, n_flat, n_lflat */) {
+  pdl_entry();
   const int ring = blockIdx.x;
   int o_s = 0, o_ls = 0, o_f = 0, o_lf = 0;
   for (int r = 0; r < ring; ++r) {
@@ -540,6 +551,7 @@ __global__ void fe_compact_kernel(const int* __restrict__ st, const int* __restr
 // gather selected points of a cloud by index (less-sharp / sharp / flat clouds)
 __global__ void gather_points_kernel(const float4* __restrict__ cloud, const int* __restrict__ idx, const int* __restrict__ n_ptr,
                                      int slot, float4* __restrict__ out) {
+  pdl_entry();
   const int n = n_ptr[slot];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = cloud[idx[i]];
@@ -551,6 +563,7 @@ __global__ void __launch_bounds__(1024) voxelgrid_kernel(const float* __restrict
                                                          int n_slot, int stride_f, int ioff, float leaf,
                                                          float4* __restrict__ packed, float4* __restrict__ out,
                                                          int* __restrict__ n_out, int* err) {
+  pdl_entry();
   extern __shared__ u64 dyn_keys[];
   const int n = n_ptr ? n_ptr[n_slot] : n_host;
   if (n > kVoxelMax) {
@@ -576,8 +589,7 @@ int Ctx::project_dev(const float* d_cloud, int n, int stride_bytes, unsigned cha
   if (n <= 0) return ILSM_OK;
   const int stride_f = stride_bytes / 4, ioff = stride_bytes >= 32 ? 4 : 3;
   const int threads = 256, blocks = ((n + 3) / 4 + threads - 1) / threads;
-  project_kernel<<<blocks, threads, 0, stream>>>(d_cloud, n, stride_f, ioff, d_range, d_inten,
-                                                 reinterpret_cast<float4*>(d_track));
+  ILSM_CUDA(launch_pdl(project_kernel, dim3(blocks), dim3(threads), 0, stream, d_cloud, n, stride_f, ioff, d_range, d_inten, reinterpret_cast<float4*>(d_track)));
   count_launches(1);
   return check_launch("project");
 }
@@ -600,24 +612,19 @@ int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_rang
   f.ring_cap = ring_cap;
   const int stride_f = stride_bytes / 4;
   const int T = 256, B = (n + T - 1) / T;
-  fe_init_kernel<<<1, 352, 0, stream>>>(f.stats.p);
+  ILSM_CUDA(launch_pdl(fe_init_kernel, dim3(1), dim3(352), 0, stream, f.stats.p));
   if (n > 0) {
-    fe_tag_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, min_range * min_range, f.scanid.p, f.ori.p, f.stats.p,
-                                       f.chunk_hist.p);
-    fe_star_kernel<<<B, T, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p);
-    fe_scan_kernel<<<kRings, 256, 0, stream>>>(f.chunk_hist.p, B, f.chunk_base.p);
-    fe_bucket_kernel<<<B, kFeChunk, 0, stream>>>(d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.chunk_base.p,
-                                                 f.cloud.p, f.src_index.p);
-    fe_curvature_kernel<<<B, T, 0, stream>>>(f.cloud.p, f.stats.p, f.curv.p, f.label.p, f.picked.p);
-    fe_sort_kernel<<<kRings * 6, 256, 0, stream>>>(f.curv.p, f.stats.p, f.sort_ind.p);
-    fe_pick_kernel<<<kRings, 32, 0, stream>>>(f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p,
-                                              f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p);
-    fe_lessflat_kernel<<<kRings, 256, 0, stream>>>(f.cloud.p, f.label.p, f.stats.p, f.ring_pts.p, f.ring_out.p, ring_cap,
-                                                   0.2f);
+    ILSM_CUDA(launch_pdl(fe_tag_kernel, dim3(B), dim3(T), 0, stream, d_in, n, stride_f, min_range * min_range, f.scanid.p, f.ori.p, f.stats.p, f.chunk_hist.p));
+    ILSM_CUDA(launch_pdl(fe_star_kernel, dim3(B), dim3(T), 0, stream, d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p));
+    ILSM_CUDA(launch_pdl(fe_scan_kernel, dim3(kRings), dim3(256), 0, stream, f.chunk_hist.p, B, f.chunk_base.p));
+    ILSM_CUDA(launch_pdl(fe_bucket_kernel, dim3(B), dim3(kFeChunk), 0, stream, d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.chunk_base.p, f.cloud.p, f.src_index.p));
+    ILSM_CUDA(launch_pdl(fe_curvature_kernel, dim3(B), dim3(T), 0, stream, f.cloud.p, f.stats.p, f.curv.p, f.label.p, f.picked.p));
+    ILSM_CUDA(launch_pdl(fe_sort_kernel, dim3(kRings * 6), dim3(256), 0, stream, f.curv.p, f.stats.p, f.sort_ind.p));
+    ILSM_CUDA(launch_pdl(fe_pick_kernel, dim3(kRings), dim3(32), 0, stream, f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p));
+    ILSM_CUDA(launch_pdl(fe_lessflat_kernel, dim3(kRings), dim3(256), 0, stream, f.cloud.p, f.label.p, f.stats.p, f.ring_pts.p, f.ring_out.p, ring_cap, 0.2f));
     count_launches(8);
   }
-  fe_compact_kernel<<<kRings, 128, 0, stream>>>(f.stats.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p, f.ring_out.p,
-                                                ring_cap, f.sharp.p, f.lsharp.p, f.flat.p, f.lflat.p, f.counts.p);
+  ILSM_CUDA(launch_pdl(fe_compact_kernel, dim3(kRings), dim3(128), 0, stream, f.stats.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p, f.ring_out.p, ring_cap, f.sharp.p, f.lsharp.p, f.flat.p, f.lflat.p, f.counts.p));
   count_launches(2);
   return check_launch("extract_features");
 }
@@ -632,15 +639,14 @@ int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int
   ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int P = 1;
   while (P < cap) P <<= 1;
-  voxelgrid_kernel<<<1, 1024, (size_t)P * sizeof(u64), stream>>>(d_in, n, d_n, n_slot, stride_bytes / 4, ioff, leaf,
-                                                                  fe.vox_packed.p, d_out, d_n_out, fe.stats.p + kStErr);
+  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), stream, d_in, n, d_n, n_slot, stride_bytes / 4, ioff, leaf, fe.vox_packed.p, d_out, d_n_out, fe.stats.p + kStErr));
   count_launches(1);
   return check_launch("voxelgrid");
 }
 
 int Ctx::gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out) {
   if (max_n <= 0) return ILSM_OK;
-  gather_points_kernel<<<(max_n + 255) / 256, 256, 0, stream>>>(d_cloud, d_idx, d_counts, slot, d_out);
+  ILSM_CUDA(launch_pdl(gather_points_kernel, dim3((max_n + 255) / 256), dim3(256), 0, stream, d_cloud, d_idx, d_counts, slot, d_out));
   count_launches(1);
   return check_launch("gather");
 }

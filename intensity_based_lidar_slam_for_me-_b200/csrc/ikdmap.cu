@@ -23,6 +23,7 @@ struct VoxSlot {
 };
 
 __global__ void vox_clear_kernel(VoxSlot* t, uint32_t size) {
+  pdl_entry();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < size) t[i].key = kEmptyKey, t[i].best_new = ~0ull, t[i].best_old = ~0ull;
 }
@@ -65,6 +66,7 @@ __device__ __forceinline__ uint32_t vox_hash(u64 key, int log2_size) { return ha
 
 __global__ void vox_new_kernel(const float* __restrict__ src, int n, int stride_f, float ds, VoxSlot* table, uint32_t mask,
                                int log2_size, uint32_t* __restrict__ slot_of, float4* __restrict__ packed) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = src + (size_t)i * stride_f;
@@ -90,6 +92,7 @@ __global__ void vox_new_kernel(const float* __restrict__ src, int n, int stride_
 
 __global__ void vox_old_kernel(const float4* __restrict__ pts, int n, float ds, VoxSlot* table, uint32_t mask, int log2_size,
                                uint32_t* __restrict__ slot_of) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = pts[i];
@@ -118,6 +121,7 @@ __global__ void vox_old_kernel(const float4* __restrict__ pts, int n, float ds, 
 // keep flags: [0, n_old) existing points, [n_old, n_old + n_new) new points
 __global__ void vox_decide_kernel(const VoxSlot* __restrict__ table, const uint32_t* __restrict__ slot_old, int n_old,
                                   const uint32_t* __restrict__ slot_new, int n_new, uint32_t* __restrict__ keep) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_old + n_new) return;
   uint32_t k = 0;
@@ -149,6 +153,7 @@ __global__ void vox_decide_kernel(const VoxSlot* __restrict__ table, const uint3
 constexpr int kScanBlock = 1024;
 __global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const uint32_t* __restrict__ in, int n, uint32_t* __restrict__ out,
                                                                 uint32_t* __restrict__ block_sums) {
+  pdl_entry();
   __shared__ uint32_t wsum[32];
   const int i = blockIdx.x * kScanBlock + threadIdx.x;
   const uint32_t v = i < n ? in[i] : 0u;
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_block_kernel(const uint32_t* 
   if (i < n) out[i] = wsum[warp] + inc - v;
 }
 __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* sums, int nb, uint32_t* total) {
+  pdl_entry();
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(uint32_t* sums, int nb,
 __global__ void compact_points_kernel(const float4* __restrict__ old_pts, int n_old, const float4* __restrict__ new_pts,
                                       int n_new, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pos,
                                       const uint32_t* __restrict__ block_off, float4* __restrict__ out) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_old + n_new || !keep[i]) return;
   const uint32_t o = pos[i] + block_off[i / kScanBlock];
@@ -241,16 +248,14 @@ int Map::insert_dev(const float* d_src, int n_new, int stride_bytes, int policy,
   VoxSlot* table = reinterpret_cast<VoxSlot*>(vox_table.p);
   const int T = 256;
   if (policy == 1) {
-    vox_clear_kernel<<<(tsize + T - 1) / T, T, 0, s>>>(table, tsize);
-    vox_new_kernel<<<(n_new + T - 1) / T, T, 0, s>>>(d_src, n_new, stride_bytes / 4, ds, table, tsize - 1, log2,
-                                                      ins_slot_new.p, ins_new.p);
+    ILSM_CUDA(launch_pdl(vox_clear_kernel, dim3((tsize + T - 1) / T), dim3(T), 0, s, table, tsize));
+    ILSM_CUDA(launch_pdl(vox_new_kernel, dim3((n_new + T - 1) / T), dim3(T), 0, s, d_src, n_new, stride_bytes / 4, ds, table, tsize - 1, log2, ins_slot_new.p, ins_new.p));
     if (n_old > 0)
-      vox_old_kernel<<<(n_old + T - 1) / T, T, 0, s>>>(orig.p, n_old, ds, table, tsize - 1, log2, ins_slot_old.p);
-    vox_decide_kernel<<<((int)tot + T - 1) / T, T, 0, s>>>(table, ins_slot_old.p, n_old, ins_slot_new.p, n_new, ins_keep.p);
-    scan_block_kernel<<<nb, kScanBlock, 0, s>>>(ins_keep.p, (int)tot, ins_pos.p, ins_bsum.p);
-    scan_sums_kernel<<<1, 1024, 0, s>>>(ins_bsum.p, nb, ins_bsum.p + nb);
-    compact_points_kernel<<<((int)tot + T - 1) / T, T, 0, s>>>(orig.p, n_old, ins_new.p, n_new, ins_keep.p, ins_pos.p,
-                                                               ins_bsum.p, ins_out.p);
+      ILSM_CUDA(launch_pdl(vox_old_kernel, dim3((n_old + T - 1) / T), dim3(T), 0, s, orig.p, n_old, ds, table, tsize - 1, log2, ins_slot_old.p));
+    ILSM_CUDA(launch_pdl(vox_decide_kernel, dim3(((int)tot + T - 1) / T), dim3(T), 0, s, table, ins_slot_old.p, n_old, ins_slot_new.p, n_new, ins_keep.p));
+    ILSM_CUDA(launch_pdl(scan_block_kernel, dim3(nb), dim3(kScanBlock), 0, s, ins_keep.p, (int)tot, ins_pos.p, ins_bsum.p));
+    ILSM_CUDA(launch_pdl(scan_sums_kernel, dim3(1), dim3(1024), 0, s, ins_bsum.p, nb, ins_bsum.p + nb));
+    ILSM_CUDA(launch_pdl(compact_points_kernel, dim3(((int)tot + T - 1) / T), dim3(T), 0, s, orig.p, n_old, ins_new.p, n_new, ins_keep.p, ins_pos.p, ins_bsum.p, ins_out.p));
     count_launches(n_old > 0 ? 7 : 6);
     // the survivor count decides the grid of the rebuild: one small D2H read (the reference's Add_Points is
     // synchronous too and returns the number of points it added)
@@ -261,9 +266,8 @@ int Map::insert_dev(const float* d_src, int n_new, int stride_bytes, int policy,
   }
   // plain append (downsample_on = false)
   ILSM_CUDA(cudaMemcpyAsync(ins_out.p, orig.p, (size_t)n_old * 16, cudaMemcpyDeviceToDevice, s));
-  vox_clear_kernel<<<(tsize + T - 1) / T, T, 0, s>>>(table, tsize);
-  vox_new_kernel<<<(n_new + T - 1) / T, T, 0, s>>>(d_src, n_new, stride_bytes / 4, 1.0f, table, tsize - 1, log2,
-                                                    ins_slot_new.p, ins_out.p + n_old);
+  ILSM_CUDA(launch_pdl(vox_clear_kernel, dim3((tsize + T - 1) / T), dim3(T), 0, s, table, tsize));
+  ILSM_CUDA(launch_pdl(vox_new_kernel, dim3((n_new + T - 1) / T), dim3(T), 0, s, d_src, n_new, stride_bytes / 4, 1.0f, table, tsize - 1, log2, ins_slot_new.p, ins_out.p + n_old));
   count_launches(2);
   return build_dev(reinterpret_cast<const float*>(ins_out.p), (int)tot, 16, cell);
 }

@@ -23,6 +23,19 @@ void count_launches(int k);
     if (e__ != cudaSuccess) return ::ilsm::fail_cuda(e__, #call); \
   } while (0)
 
+// Launch with programmatic stream serialization: the kernel's launch latency overlaps the tail of its predecessor
+// (the short kernels of a registration are launch-latency-bound).  The kernel must start with pdl_entry().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Grow-only device buffer (HBM is plentiful: 180 GB; reallocation would serialise the stream).
 template <typename T>
 struct DevBuf {

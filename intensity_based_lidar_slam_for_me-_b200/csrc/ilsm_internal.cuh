@@ -39,6 +39,16 @@ struct GridView {
   int n;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled while its predecessor
+// in the stream is still running; it must not touch anything the predecessor produces before pdl_wait(), which
+// returns once the predecessor has completed and its writes are visible.  pdl_launch_dependents() lets the NEXT
+// kernel's launch overlap this one.  Both are no-ops for ordinary launches.  Every kernel launched through
+// launch_pdl() calls pdl_entry() first.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ int voxel_coord(float x, float inv_cell) { return __float2int_rd(__fmul_rn(x, inv_cell)); }
 
 __device__ __forceinline__ u64 pack_voxel(int cx, int cy, int cz) {

@@ -15,6 +15,7 @@
 namespace ilsm {
 
 __global__ void grid_clear_kernel(GridCell* cells, uint32_t size, int* bbox, uint32_t* counters) {
+  pdl_entry();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < size) {
     uint4 e;
@@ -36,6 +37,7 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
                                   uint32_t mask, int log2_size, float4* __restrict__ orig,
                                   uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
                                   uint32_t* counters) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool in = i < n;
@@ -80,6 +82,7 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
 // Every occupied slot gets a contiguous range of the sorted array (warp-aggregated atomicAdd on one cursor) and
 // the bounding box of occupied voxels is reduced per block (6 atomics per block instead of 6 per voxel).
 __global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* counters, int* bbox) {
+  pdl_entry();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cnt = 0;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
@@ -142,6 +145,7 @@ __global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* coun
 __global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, const GridCell* __restrict__ cells,
                                     const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of,
                                     float4* __restrict__ sorted) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t slot = slot_of[i];
@@ -157,6 +161,7 @@ __global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, cons
 template <int K>
 __global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __restrict__ q, int nq, int stride_f, int k_out,
                                                   float max_d2, int32_t* __restrict__ idx, float* __restrict__ d2) {
+  pdl_entry();
   __shared__ WarpScratch scratch[4];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int bb[6];
@@ -224,14 +229,14 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
   log2_size = want_log2;
   table_size = want_size;
   const int T = 256;
-  grid_clear_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, bbox.p, counters.p);
+  ILSM_CUDA(launch_pdl(grid_clear_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, bbox.p, counters.p));
   if (n_pts > 0) {
     const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
-    grid_count_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(d_src, n_pts, stride_bytes / 4, ioff, inv_cell, cells.p,
-                                                         table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p,
-                                                         counters.p);
-    grid_alloc_kernel<<<(table_size + T - 1) / T, T, 0, s>>>(cells.p, table_size, counters.p, bbox.p);
-    grid_scatter_kernel<<<(n_pts + T - 1) / T, T, 0, s>>>(orig.p, n_pts, cells.p, slot_of.p, rank_of.p, sorted.p);
+    ILSM_CUDA(launch_pdl(grid_count_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, d_src, n_pts, stride_bytes / 4, ioff, inv_cell,
+                         cells.p, table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p, counters.p));
+    ILSM_CUDA(launch_pdl(grid_alloc_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, counters.p, bbox.p));
+    ILSM_CUDA(launch_pdl(grid_scatter_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, (const float4*)orig.p, n_pts,
+                         (const GridCell*)cells.p, (const uint32_t*)slot_of.p, (const uint32_t*)rank_of.p, sorted.p));
   }
   count_launches(n_pts > 0 ? 4 : 1);
   ILSM_CUDA(cudaEventRecord(ready, s));
@@ -254,12 +259,13 @@ GridView Map::view() const {
 }
 
 template <int K>
-static void launch_knn(const GridView& g, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
+static int launch_knn(const GridView& g, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
                        float* d_d2, cudaStream_t s, int sm_count) {
   // one warp per query; at most ~16 resident warps per SM, further queries are taken grid-stride
   long long blocks = ((long long)nq + 3) / 4, cap = (long long)sm_count * 4 * 4;
   if (blocks > cap) blocks = cap;
-  knn_kernel<K><<<(unsigned)blocks, 128, 0, s>>>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2);
+  ILSM_CUDA(launch_pdl(knn_kernel<K>, dim3((unsigned)blocks), dim3(128), 0, s, g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2));
+  return ILSM_OK;
 }
 
 int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2) {
@@ -275,12 +281,14 @@ int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_di
     if (rc) return rc;
   }
   int stride_f = stride_bytes / 4;
+  int rc;
   if (k == 1)
-    launch_knn<1>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+    rc = launch_knn<1>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
   else if (k <= 5)
-    launch_knn<5>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+    rc = launch_knn<5>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
   else
-    launch_knn<8>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+    rc = launch_knn<8>(g, d_q, nq, stride_f, k, max_d2, d_idx, d_d2, s, ctx->sm_count);
+  if (rc) return rc;
   count_launches(1);
   return check_launch("knn");
 }

@@ -18,6 +18,7 @@ constexpr int kDescWords = 8;  // 256-bit ORB descriptor
 
 __global__ void __launch_bounds__(128) hamming_argmin_kernel(const uint32_t* __restrict__ q, int nq, const uint32_t* __restrict__ t,
                                                              int nt, int* __restrict__ best_idx, int* __restrict__ best_dist) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 4 + warp;
   if (i >= nq) return;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(1024) match_finalize_kernel(int nq, const int*
                                                               const int* __restrict__ best_q, int cross_check, double fraction,
                                                               ilsm_dmatch* __restrict__ matches, ilsm_dmatch* __restrict__ good,
                                                               int* __restrict__ counts) {
+  pdl_entry();
   extern __shared__ u64 keys[];
   __shared__ int wc[32];
   __shared__ int s_base;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(1024) match_finalize_kernel(int nq, const int*
 // point pairs -> front_end_residual factors (type 3: p = source point, a = destination point)
 __global__ void align_factors_kernel(const float* __restrict__ src, const float* __restrict__ dst, int n, int stride_f, int* type,
                                      float4* p, double4* a, double4* b) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* s = src + (size_t)i * stride_f;
@@ -153,14 +156,13 @@ ILSM_API int ilsm_orb_match(ilsm_ctx* ctx, const uint8_t* cur_desc, int n_cur, c
   ilsm_dmatch* d_good = d_matches + n_cur;
   ILSM_CUDA(cudaMemcpyAsync(d_q, cur_desc, wq * 4, cudaMemcpyHostToDevice, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(d_t, prev_desc, wt * 4, cudaMemcpyHostToDevice, c.stream));
-  hamming_argmin_kernel<<<(n_cur + 3) / 4, 128, 0, c.stream>>>(d_q, n_cur, d_t, n_prev, best_t, dist_q);
-  if (cross_check) hamming_argmin_kernel<<<(n_prev + 3) / 4, 128, 0, c.stream>>>(d_t, n_prev, d_q, n_cur, best_q, dist_t);
+  ILSM_CUDA(launch_pdl(hamming_argmin_kernel, dim3((n_cur + 3) / 4), dim3(128), 0, c.stream, d_q, n_cur, d_t, n_prev, best_t, dist_q));
+  if (cross_check) ILSM_CUDA(launch_pdl(hamming_argmin_kernel, dim3((n_prev + 3) / 4), dim3(128), 0, c.stream, d_t, n_prev, d_q, n_cur, best_q, dist_t));
   int P = 1;
   while (P < n_cur) P <<= 1;
   const size_t smem = (size_t)P * sizeof(u64);
   ILSM_CUDA(cudaFuncSetAttribute(match_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelBlockMax * sizeof(u64))));
-  match_finalize_kernel<<<1, 1024, smem, c.stream>>>(n_cur, best_t, dist_q, best_q, cross_check ? 1 : 0, keep_fraction, d_matches,
-                                                     d_good, counts);
+  ILSM_CUDA(launch_pdl(match_finalize_kernel, dim3(1), dim3(1024), smem, c.stream, n_cur, best_t, dist_q, best_q, cross_check ? 1 : 0, keep_fraction, d_matches, d_good, counts));
   count_launches(cross_check ? 3 : 2);
   if ((rc = check_launch("orb_match"))) return rc;
   int* pin = reinterpret_cast<int*>(c.pinned.p);
@@ -194,7 +196,7 @@ ILSM_API int ilsm_align_points(ilsm_ctx* ctx, const float* src_xyz, const float*
   if (n > 0) {
     ILSM_CUDA(cudaMemcpyAsync(d_src, src_xyz, bytes, cudaMemcpyHostToDevice, c.stream));
     ILSM_CUDA(cudaMemcpyAsync(d_dst, dst_xyz, bytes, cudaMemcpyHostToDevice, c.stream));
-    align_factors_kernel<<<(n + 255) / 256, 256, 0, c.stream>>>(d_src, d_dst, n, stride_bytes / 4, f.type.p, f.p.p, f.a.p, f.b.p);
+    ILSM_CUDA(launch_pdl(align_factors_kernel, dim3((n + 255) / 256), dim3(256), 0, c.stream, d_src, d_dst, n, stride_bytes / 4, f.type.p, f.p.p, f.a.p, f.b.p));
     count_launches(1);
   }
   double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 2048);

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
                      int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv,
                      const int* __restrict__ d_counts) {
+  pdl_entry();
   __shared__ WarpScratch scratch[kAssocThreads / 32];
   if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -323,6 +324,7 @@ __device__ __forceinline__ void ring_walk(const float4* __restrict__ pts, int n,
 __global__ void __launch_bounds__(kAssocThreads, 5)
     odom_associate_kernel(GridView gc, GridView gs, const float* __restrict__ sharp, int nsh, const float* __restrict__ flat,
                           int nfl, int stride_f, const LmState* __restrict__ st, FactorView fv) {
+  pdl_entry();
   __shared__ WarpScratch scratch[kAssocThreads / 32];
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = gridDim.x * (kAssocThreads / 32);
@@ -828,6 +830,7 @@ struct SolveParams {
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThreads, 1)
     solve_cluster_kernel(FactorView fv, int n, LmState* st, SolveParams prm, const int* __restrict__ d_counts) {
+  pdl_entry();
   __shared__ double core[kCoreWords];
   if (d_counts) n = d_counts[0] + d_counts[1];
   __shared__ double red[kSolveThreads / 32][kSumStride];
@@ -929,6 +932,7 @@ constexpr int kEvalThreads = 384, kEvalBlocksPerSm = 1;
 
 __global__ void __launch_bounds__(kEvalThreads, kEvalBlocksPerSm)
     normal_eq_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials, double* __restrict__ eval_out) {
+  pdl_entry();
   __shared__ double red[kEvalThreads / 32][kSumStride];
   __shared__ int is_last;
   double acc[kSumStride];
@@ -1043,8 +1047,8 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   // one warp per stack point, capped at one resident wave (5 blocks x 4 warps per SM at this register budget)
   long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
   if (blocks > cap) blocks = cap;
-  associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(gc, gs, d_corner, nc, d_surf, ns, stride_f, lm.p, prm, fv,
-                                                                   d_stack_counts);
+  ILSM_CUDA(launch_pdl(associate_kernel, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc, d_surf, ns,
+                       stride_f, (const LmState*)lm.p, prm, fv, d_stack_counts));
   count_launches(1);
   return check_launch("associate");
 }
@@ -1063,8 +1067,8 @@ int Ctx::odom_associate_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, con
   FactorView fv = factor_view(fac, false);
   long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
   if (blocks > cap) blocks = cap;
-  odom_associate_kernel<<<(unsigned)blocks, kAssocThreads, 0, stream>>>(mc->view(), ms->view(), d_sharp, nsh, d_flat, nfl,
-                                                                        stride_bytes / 4, lm.p, fv);
+  ILSM_CUDA(launch_pdl(odom_associate_kernel, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, mc->view(), ms->view(),
+                       d_sharp, nsh, d_flat, nfl, stride_bytes / 4, (const LmState*)lm.p, fv));
   count_launches(1);
   return check_launch("odom_associate");
 }
@@ -1086,7 +1090,8 @@ int Ctx::solve_launch(int max_iter, double huber_a, int pass) {
   prm.arm = 1;
   prm.huber_a = huber_a;
   FactorView fv = factor_view(fac, false);
-  solve_cluster_kernel<<<kClusterSize, kSolveThreads, 0, stream>>>(fv, fac.n, lm.p, prm, d_stack_counts);
+  ILSM_CUDA(launch_pdl(solve_cluster_kernel, dim3(kClusterSize), dim3(kSolveThreads), 0, stream, fv, fac.n, lm.p, prm,
+                       d_stack_counts));
   count_launches(1);
   return check_launch("solve");
 }
@@ -1109,13 +1114,15 @@ int eval_only_launch(Ctx* c, double* d_out) {
   int rc;
   if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
   FactorView fv = factor_view(c->fac, false);
-  normal_eq_kernel<<<(unsigned)blocks, kEvalThreads, 0, c->stream>>>(fv, c->fac.n, c->lm.p, c->partials.p, d_out);
+  ILSM_CUDA(launch_pdl(normal_eq_kernel, dim3((unsigned)blocks), dim3(kEvalThreads), 0, c->stream, fv, c->fac.n, c->lm.p,
+                       c->partials.p, d_out));
   count_launches(1);
   return check_launch("normal_eq");
 }
 
 // copy factor SoA -> AoS records on the device for ilsm_associate's host output
 __global__ void factors_export_kernel(FactorView fv, int n, int nc, ilsm_factor* out) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   ilsm_factor f;
@@ -1136,7 +1143,7 @@ __global__ void factors_export_kernel(FactorView fv, int n, int nc, ilsm_factor*
 int factors_export(Ctx* c, ilsm_factor* d_out) {
   if (c->fac.n == 0) return ILSM_OK;
   FactorView fv = factor_view(c->fac, false);
-  factors_export_kernel<<<(c->fac.n + 255) / 256, 256, 0, c->stream>>>(fv, c->fac.n, c->fac.nc, d_out);
+  ILSM_CUDA(launch_pdl(factors_export_kernel, dim3((c->fac.n + 255) / 256), dim3(256), 0, c->stream, fv, c->fac.n, c->fac.nc, d_out));
   count_launches(1);
   return check_launch("factors_export");
 }

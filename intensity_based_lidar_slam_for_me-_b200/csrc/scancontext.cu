@@ -42,10 +42,12 @@ __device__ __forceinline__ int float_order(float f) {  // monotone float -> int 
 __device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
 __global__ void sc_make_clear_kernel(int* bins) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kDesc) bins[i] = float_order(-1000.0f);
 }
 __global__ void sc_make_kernel(const float* __restrict__ pts, int n, int stride_f, int* bins) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = pts + (size_t)i * stride_f;
@@ -61,6 +63,7 @@ __global__ void sc_make_kernel(const float* __restrict__ pts, int n, int stride_
   atomicMax(&bins[(ring - 1) * kNS + (sector - 1)], float_order(z));
 }
 __global__ void sc_make_finish_kernel(const int* bins, float* desc) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kDesc) {
     const float v = order_float(bins[i]);
@@ -72,6 +75,7 @@ __global__ void sc_make_finish_kernel(const int* bins, float* desc) {
 // scoring
 // ---------------------------------------------------------------------------------------------------
 __global__ void sc_query_prep_kernel(const float* __restrict__ qdesc, ScQuery* q) {
+  pdl_entry();
   const int c = threadIdx.x;
   for (int i = threadIdx.x; i < kDesc; i += blockDim.x) q->desc[i] = (double)qdesc[i];
   if (c < kNS) {
@@ -116,6 +120,7 @@ __device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { re
 __global__ void __launch_bounds__(kScWarps * 32, 2)
     sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, int k, u64* __restrict__ part_d,
                     int* __restrict__ part_id, int* __restrict__ part_sh) {
+  pdl_entry();
   extern __shared__ __align__(16) unsigned char sc_smem_raw[];
   ScBlockSmem& sm = *reinterpret_cast<ScBlockSmem*>(sc_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,6 +303,7 @@ constexpr int kFinalThreads = 1024, kFinalPer = 8;
 __global__ void __launch_bounds__(kFinalThreads)
     sc_topk_final_kernel(const u64* __restrict__ part_d, const int* __restrict__ part_id, const int* __restrict__ part_sh, int n,
                          int id_offset, int k, double* __restrict__ o_dist, int* __restrict__ o_id, int* __restrict__ o_shift) {
+  pdl_entry();
   __shared__ u64 s_d[32];
   __shared__ int s_id[32], s_sh[32];
   __shared__ int s_win;
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(kFinalThreads)
 // (distance, id) strictly above round j-1's winner (ids are unique across shards), so the result is the same
 // ascending (distance, id) order as ilsm_sc_merge_topk on the host.
 __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int shards, int k, unsigned char* __restrict__ out) {
+  pdl_entry();
   const int lane = threadIdx.x;
   const size_t rec = (size_t)16 * k;
   u64 last_d = 0;
@@ -400,8 +407,7 @@ __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int sh
 }
 
 int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out) {
-  sc_merge_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned char*>(d_packed), shards, k,
-                                             reinterpret_cast<unsigned char*>(d_out));
+  ILSM_CUDA(launch_pdl(sc_merge_kernel, dim3(1), dim3(32), 0, ctx->stream, reinterpret_cast<const unsigned char*>(d_packed), shards, k, reinterpret_cast<unsigned char*>(d_out)));
   count_launches(1);
   return check_launch("sc_merge");
 }
@@ -432,9 +438,9 @@ int ScDb::make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc) {
   int rc;
   if ((rc = bins.reserve(kDesc))) return rc;
   cudaStream_t s = ctx->stream;
-  sc_make_clear_kernel<<<(kDesc + 255) / 256, 256, 0, s>>>(bins.p);
-  if (n > 0) sc_make_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_pts, n, stride_bytes / 4, bins.p);
-  sc_make_finish_kernel<<<(kDesc + 255) / 256, 256, 0, s>>>(bins.p, d_desc);
+  ILSM_CUDA(launch_pdl(sc_make_clear_kernel, dim3((kDesc + 255) / 256), dim3(256), 0, s, bins.p));
+  if (n > 0) ILSM_CUDA(launch_pdl(sc_make_kernel, dim3((n + 255) / 256), dim3(256), 0, s, d_pts, n, stride_bytes / 4, bins.p));
+  ILSM_CUDA(launch_pdl(sc_make_finish_kernel, dim3((kDesc + 255) / 256), dim3(256), 0, s, bins.p, d_desc));
   count_launches(n > 0 ? 3 : 2);
   return check_launch("sc_make");
 }
@@ -454,11 +460,9 @@ int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, do
     return rc;
   cudaStream_t s = ctx->stream;
   ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
-  sc_query_prep_kernel<<<1, 64, 0, s>>>(d_qdesc, query.p);
-  sc_score_kernel<<<(unsigned)blocks, kScWarps * 32, sizeof(ScBlockSmem), s>>>(db.p, n_search, query.p, k, part_d.p, part_id.p,
-                                                                              part_sh.p);
-  sc_topk_final_kernel<<<1, kFinalThreads, 0, s>>>(part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id,
-                                                   d_shift);
+  ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(1), dim3(64), 0, s, d_qdesc, query.p));
+  ILSM_CUDA(launch_pdl(sc_score_kernel, dim3((unsigned)blocks), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, db.p, n_search, query.p, k, part_d.p, part_id.p, part_sh.p));
+  ILSM_CUDA(launch_pdl(sc_topk_final_kernel, dim3(1), dim3(kFinalThreads), 0, s, part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id, d_shift));
   count_launches(3);
   return check_launch("sc_query");
 }
