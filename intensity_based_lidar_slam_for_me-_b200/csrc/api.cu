@@ -91,6 +91,9 @@ int Ctx::init(int dev) {
   ILSM_CUDA(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
   ILSM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  ILSM_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+  ILSM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  ILSM_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   int rc;
   if ((rc = lm.reserve(1))) return rc;
   ILSM_CUDA(cudaMemsetAsync(lm.p, 0, sizeof(LmState), stream));
@@ -108,8 +111,11 @@ void Ctx::release() {
   fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
   lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
   fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
+  if (aux) cudaStreamSynchronize(aux), cudaStreamDestroy(aux);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (stream) cudaStreamDestroy(stream);
-  stream = nullptr;
+  stream = nullptr, aux = nullptr, ev_fork = nullptr, ev_join = nullptr;
 }
 
 void Map::release() {

@@ -304,7 +304,7 @@ using namespace ilsm;
 namespace ilsm {
 int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
-                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats) {
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready) {
   Ctx& c = *m.ctx;
   // transformAssociateToMap (laserMapping.cpp:138-142)
   const QuatH qo{q_wodom[0], q_wodom[1], q_wodom[2], q_wodom[3]};
@@ -316,12 +316,16 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
   if ((rc = m.roll(tw))) return rc;
   int n_mc = 0, n_ms = 0;
   if ((rc = m.gather(&n_mc, &n_ms))) return rc;
-  // stacks: VoxelGrid(line_res) / VoxelGrid(plane_res) of the incoming feature clouds (:608-616), sizes stay on the device
-  if ((rc = m.stack_c.reserve(nc + 4)) || (rc = m.stack_s.reserve(ns + 4))) return rc;
-  const int ioff = stride_bytes >= 32 ? 4 : 3;
-  ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
-  if (nc > 0 && (rc = c.voxelgrid_dev(d_c, nc, nullptr, 0, stride_bytes, ioff, m.line_res, m.stack_c.p, m.stack_n.p))) return rc;
-  if (ns > 0 && (rc = c.voxelgrid_dev(d_s, ns, nullptr, 0, stride_bytes, ioff, m.plane_res, m.stack_s.p, m.stack_n.p + 1))) return rc;
+  // stacks: VoxelGrid(line_res) / VoxelGrid(plane_res) of the incoming feature clouds (:608-616), sizes stay on the
+  // device; the full-loop pipeline has already produced them on its side stream (stacks_ready)
+  if (!stacks_ready) {
+    if ((rc = m.stack_c.reserve(nc + 4)) || (rc = m.stack_s.reserve(ns + 4))) return rc;
+    const int ioff = stride_bytes >= 32 ? 4 : 3;
+    ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
+    if ((rc = c.voxelgrid_pair_dev(d_c, nc, m.line_res, m.stack_c.p, d_s, ns, m.plane_res, m.stack_s.p, stride_bytes, ioff,
+                                   m.stack_n.p, c.stream)))
+      return rc;
+  }
   // pose in
   double pose[7] = {qw.x, qw.y, qw.z, qw.w, tw[0], tw[1], tw[2]};
   double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 1024);
@@ -488,7 +492,7 @@ ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int 
   const size_t off_s = ((size_t)nc * stride_bytes + 255) & ~(size_t)255;
   const float* d_c = m.raw.p;
   const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
-  return cubemap_frame_core(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, q_w, t_w, o, report, stats);
+  return cubemap_frame_core(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, q_w, t_w, o, report, stats, false);
 }
 
 ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out) {

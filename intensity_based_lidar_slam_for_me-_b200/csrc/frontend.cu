@@ -557,28 +557,39 @@ __global__ void gather_points_kernel(const float4* __restrict__ cloud, const int
   if (i < n) out[i] = cloud[idx[i]];
 }
 
-// stand-alone VoxelGrid of one cloud by one block (n <= kVoxelMax); n may come from device memory (n_ptr)
+// stand-alone VoxelGrid, one block per job (n <= kVoxelMax per job); n may come from device memory (n_ptr).  The two
+// feature stacks of a frame (corner / surf) are two jobs of one launch.
 constexpr int kVoxelMax = kVoxelBlockMax;
-__global__ void __launch_bounds__(1024) voxelgrid_kernel(const float* __restrict__ in, int n_host, const int* __restrict__ n_ptr,
-                                                         int n_slot, int stride_f, int ioff, float leaf,
-                                                         float4* __restrict__ packed, float4* __restrict__ out,
-                                                         int* __restrict__ n_out, int* err) {
+struct VoxJob {
+  const float* in;
+  const int* n_ptr;
+  float4* packed;
+  float4* out;
+  int* n_out;
+  int n_host, n_slot, stride_f, ioff;
+  float leaf;
+};
+struct VoxJobs {
+  VoxJob j[2];
+};
+__global__ void __launch_bounds__(1024) voxelgrid_kernel(VoxJobs jobs, int* err) {
   pdl_entry();
   extern __shared__ u64 dyn_keys[];
-  const int n = n_ptr ? n_ptr[n_slot] : n_host;
+  const VoxJob& jb = jobs.j[blockIdx.x];
+  const int n = jb.n_ptr ? jb.n_ptr[jb.n_slot] : jb.n_host;
   if (n > kVoxelMax) {
-    if (threadIdx.x == 0) atomicOr(err, 8), *n_out = 0;
+    if (threadIdx.x == 0) atomicOr(err, 8), *jb.n_out = 0;
     return;
   }
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const float* p = in + (size_t)t * stride_f;
-    packed[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + ioff));
+    const float* p = jb.in + (size_t)t * jb.stride_f;
+    jb.packed[t] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + jb.ioff));
   }
   __syncthreads();
   int P = 1;
   while (P < n) P <<= 1;
-  const int nvox = n > 0 ? voxelgrid_block(packed, n, leaf, dyn_keys, P, out, err) : 0;
-  if (threadIdx.x == 0) *n_out = nvox;
+  const int nvox = n > 0 ? voxelgrid_block(jb.packed, n, jb.leaf, dyn_keys, P, jb.out, err) : 0;
+  if (threadIdx.x == 0) *jb.n_out = nvox;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -635,13 +646,32 @@ int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int
   const int cap = d_n ? kVoxelMax : n;
   if (!d_n && n > kVoxelMax) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: more than 16384 points per call");
   if ((rc = fe.vox_packed.reserve(cap + 4)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
-  const size_t smem = (size_t)kVoxelMax * sizeof(u64);
-  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelMax * sizeof(u64))));
   int P = 1;
   while (P < cap) P <<= 1;
-  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), stream, d_in, n, d_n, n_slot, stride_bytes / 4, ioff, leaf, fe.vox_packed.p, d_out, d_n_out, fe.stats.p + kStErr));
+  VoxJobs jobs = {};
+  jobs.j[0] = VoxJob{d_in, d_n, fe.vox_packed.p, d_out, d_n_out, n, n_slot, stride_bytes / 4, ioff, leaf};
+  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), stream, jobs, fe.stats.p + kStErr));
   count_launches(1);
   return check_launch("voxelgrid");
+}
+
+// The corner and surf stacks of a frame in ONE launch (two blocks) on stream `s`: host-side counts, packed xyzi inputs.
+int Ctx::voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
+                            float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s) {
+  if (nc > kVoxelMax || ns > kVoxelMax) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: more than 16384 points per cloud");
+  int rc;
+  if ((rc = fe.vox_packed.reserve((size_t)2 * kVoxelMax + 8)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
+  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelMax * sizeof(u64))));
+  const int big = nc > ns ? nc : ns;
+  int P = 1;
+  while (P < big) P <<= 1;
+  VoxJobs jobs = {};
+  jobs.j[0] = VoxJob{d_c, nullptr, fe.vox_packed.p, d_out_c, d_n_out2, nc, 0, stride_bytes / 4, ioff, leaf_c};
+  jobs.j[1] = VoxJob{d_s, nullptr, fe.vox_packed.p + kVoxelMax, d_out_s, d_n_out2 + 1, ns, 0, stride_bytes / 4, ioff, leaf_s};
+  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), (size_t)P * sizeof(u64), s, jobs, fe.stats.p + kStErr));
+  count_launches(1);
+  return check_launch("voxelgrid_pair");
 }
 
 int Ctx::gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out) {

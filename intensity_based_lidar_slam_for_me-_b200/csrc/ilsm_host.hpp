@@ -173,6 +173,8 @@ struct Ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;                       // side stream: work of a frame that does not depend on the odometry
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::mutex mu;
   DevBuf<LmState> lm;
   DevBuf<double> partials;  // [blocks][32]
@@ -200,6 +202,8 @@ struct Ctx {
   int features_dev(const float* d_in, int n, int stride_bytes, float min_range);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);
+  int voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
+                         float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s);
   int gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out);
   int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                    const ilsm_reg_opts& o);

@@ -113,6 +113,19 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
       (rc = c.gather_dev(c.fe.cloud.p, c.fe.lsharp.p, c.fe.counts.p, 2, n_lsharp, s.lsharp.p)) ||
       (rc = c.gather_dev(c.fe.cloud.p, c.fe.flat.p, c.fe.counts.p, 3, n_flat, s.flat.p)))
     return rc;
+  // ---- the mapping stacks (VoxelGrid of the less-sharp / less-flat clouds, laserMapping.cpp:608-616) depend only on the
+  // front end: they run on the side stream while the odometry solves on the main one
+  if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
+  CubeMapH& cm = s.cube->m;
+  if ((rc = cm.stack_c.reserve(n_lsharp + 4)) || (rc = cm.stack_s.reserve(n_lflat + 4))) return rc;
+  ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+  ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+  ILSM_CUDA(cudaMemsetAsync(cm.stack_n.p, 0, 4 * sizeof(int), c.aux));
+  if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, cm.line_res, cm.stack_c.p,
+                                 reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
+                                 cm.stack_n.p, c.aux)))
+    return rc;
+  ILSM_CUDA(cudaEventRecord(c.ev_join, c.aux));
   // ---- laserOdometry
   if (!s.inited) {
     s.inited = true;
@@ -153,12 +166,12 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
       (rc = s.last_surf.build_dev(reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
     return rc;
   // ---- laserMapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
-  if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
+  ILSM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
   ilsm_reg_opts mo;
   ilsm_reg_opts_default(&mo);
   rc = cubemap_frame_core(s.cube->m, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
                           reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
-                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr);
+                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true);
   if (rc) return rc;
   s.frames++;
   return ILSM_OK;
