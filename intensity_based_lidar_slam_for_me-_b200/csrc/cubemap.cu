@@ -159,8 +159,10 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
       (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
       (rc = stack_n.reserve(4)) || (rc = valid_d.reserve(128)) || (rc = err.reserve(4)) || (rc = items.reserve(256)) ||
       (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) ||
-      (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)))
+      (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)) ||
+      (rc = pin_counts.reserve(2 * kCNum + 16)))
     return rc;
+  ILSM_CUDA(cudaEventCreateWithFlags(&ev_tail, cudaEventDisableTiming));
   slab_of.resize(kCNum);
   for (int i = 0; i < kCNum; ++i) slab_of[i] = i;
   cnt_c_h.assign(kCNum, 0), cnt_s_h.assign(kCNum, 0);
@@ -179,6 +181,10 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
 
 void CubeMapH::release() {
   if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx && ctx->aux) cudaStreamSynchronize(ctx->aux);
+  if (ev_tail) cudaEventDestroy(ev_tail);
+  ev_tail = nullptr;
+  pin_counts.release();
   map_c.release(), map_s.release();
   slabs_c.release(), slabs_s.release(), from_c.release(), from_s.release(), stack_c.release(), stack_s.release();
   scratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release();
@@ -270,16 +276,16 @@ int CubeMapH::gather(int* n_mc, int* n_ms) {
   return check_launch("cube_gather");
 }
 
-int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_frame) {
-  cudaStream_t s = ctx->stream;
+int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_frame, cudaStream_t s) {
+  if (!s) s = ctx->stream;
   ILSM_CUDA(launch_pdl(cube_insert_kernel, dim3(2), dim3(1024), kVoxelBlockMax * sizeof(u64), s, stack_c.p, stack_s.p, d_counts, nc_host, ns_host, ctx->lm.p, world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p, kVoxelBlockMax, err.p));
   count_launches(1);
   return check_launch("cube_insert");
 }
 
-int CubeMapH::filter_valid() {
+int CubeMapH::filter_valid(cudaStream_t s) {
   if (n_valid == 0) return ILSM_OK;
-  cudaStream_t s = ctx->stream;
+  if (!s) s = ctx->stream;
   int* p = pin.p + kCNum + 1024;
   for (int v = 0; v < n_valid; ++v) p[v] = slab_of[valid[v]];
   ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -289,11 +295,32 @@ int CubeMapH::filter_valid() {
 }
 
 // the host mirror of the counts (needed by the next gather and by the guard of :624)
-int CubeMapH::fetch_counts() {
-  cudaStream_t s = ctx->stream;
-  std::vector<int>& c = cnt_c_h;
-  ILSM_CUDA(cudaMemcpyAsync(c.data(), cnt_c.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
-  ILSM_CUDA(cudaMemcpyAsync(cnt_s_h.data(), cnt_s.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
+int CubeMapH::fetch_counts(cudaStream_t s) {
+  if (!s) s = ctx->stream;
+  // pinned staging: a D2H copy into pageable memory would block the host until it has run
+  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p, cnt_c.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p + kCNum, cnt_s.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
+  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p + 2 * kCNum, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  counts_in_flight = true;
+  return ILSM_OK;
+}
+
+// After the stream that ran fetch_counts has been synchronised (or its event waited for): refresh the host mirror.
+int CubeMapH::adopt_counts() {
+  if (!counts_in_flight) return 0;
+  memcpy(cnt_c_h.data(), pin_counts.p, kCNum * sizeof(int));
+  memcpy(cnt_s_h.data(), pin_counts.p + kCNum, kCNum * sizeof(int));
+  counts_in_flight = false;
+  return pin_counts.p[2 * kCNum];
+}
+
+// Deferred tail of the previous frame (insertion + per-cube VoxelGrid + count fetch on the side stream): wait for it.
+int CubeMapH::wait_tail() {
+  if (tail_pending) {
+    ILSM_CUDA(cudaEventSynchronize(ev_tail));
+    tail_pending = false;
+    tail_flags |= adopt_counts();
+  }
   return ILSM_OK;
 }
 
@@ -304,8 +331,13 @@ using namespace ilsm;
 namespace ilsm {
 int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
-                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready) {
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready,
+                       bool defer_tail) {
   Ctx& c = *m.ctx;
+  {
+    int rcw = m.wait_tail();
+    if (rcw) return rcw;
+  }
   // transformAssociateToMap (laserMapping.cpp:138-142)
   const QuatH qo{q_wodom[0], q_wodom[1], q_wodom[2], q_wodom[3]};
   QuatH qw = qmul_h(m.q_wmap_wodom, qo);
@@ -342,15 +374,28 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
     c.d_stack_counts = nullptr;
     if (rc) return rc;
   }
-  // insertion with the optimised pose (still on the device) + per-cube VoxelGrid of the valid cubes
-  if ((rc = m.insert(m.stack_n.p, 0, 0, 0)) || (rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
+  // pose, report and stack sizes come back first; the insertion with the optimised pose (still on the device) and the
+  // per-cube VoxelGrid of the valid cubes follow -- on the side stream when the caller defers them (full-loop
+  // pipeline: they overlap the next frame's upload and front end, wait_tail() joins them)
   unsigned char* pin = c.pinned.p;
   int* pin_i = m.pin.p + kCNum + 2048;
   ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin_i, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  cudaStream_t ts = defer_tail ? c.aux : c.stream;
+  if (defer_tail) {
+    ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+    ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+  }
+  if ((rc = m.insert(m.stack_n.p, 0, 0, 0, ts)) || (rc = m.filter_valid(ts)) || (rc = m.fetch_counts(ts))) return rc;
+  if (defer_tail) {
+    ILSM_CUDA(cudaEventRecord(m.ev_tail, c.aux));
+    m.tail_pending = true;
+  }
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  pin_i[0] = m.tail_flags;  // capacity flags: of this frame when synchronous, up to the previous frame when deferred
+  if (!defer_tail) pin_i[0] |= m.adopt_counts();
+  m.tail_flags = 0;
   const double* out = reinterpret_cast<const double*>(pin);
   for (int i = 0; i < 4; ++i) q_w[i] = out[i];
   for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
@@ -446,7 +491,7 @@ ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, in
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
   int rc;
-  if ((rc = m.roll(centre))) return rc;
+  if ((rc = m.wait_tail()) || (rc = m.roll(centre))) return rc;
   const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
   // large seeds are inserted in chunks of at most kVoxelBlockMax points per stack (the insert kernel sorts in smem)
   const int chunk = kVoxelBlockMax;
@@ -466,10 +511,13 @@ ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, in
     ILSM_CUDA(cudaStreamSynchronize(c.stream));  // staging buffers are reused by the next chunk
   }
   if ((rc = m.filter_valid()) || (rc = m.fetch_counts())) return rc;
-  int* pin = m.pin.p + kCNum + 2048;
-  ILSM_CUDA(cudaMemcpyAsync(pin, m.err.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
-  if (pin[0]) return fail(ILSM_ERR_OUT_OF_MEMORY, "cube map: a cube exceeded its slab capacity");
+  const int flags = m.adopt_counts() | m.tail_flags;
+  m.tail_flags = 0;
+  if (flags) {
+    cudaMemsetAsync(m.err.p, 0, sizeof(int), c.stream);
+    return fail(ILSM_ERR_OUT_OF_MEMORY, "cube map: a cube exceeded its slab capacity");
+  }
   return ILSM_OK;
 }
 
@@ -492,7 +540,7 @@ ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int 
   const size_t off_s = ((size_t)nc * stride_bytes + 255) & ~(size_t)255;
   const float* d_c = m.raw.p;
   const float* d_s = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m.raw.p) + off_s);
-  return cubemap_frame_core(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, q_w, t_w, o, report, stats, false);
+  return cubemap_frame_core(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, q_w, t_w, o, report, stats, false, false);
 }
 
 ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, float* out_xyzi, int capacity, int* n_out) {
@@ -501,6 +549,10 @@ ILSM_API int ilsm_cubemap_cube(ilsm_cubemap* cm, int which, int cube_index, floa
   CubeMapH& m = cm->m;
   std::lock_guard<std::mutex> lk(m.ctx->mu);
   ILSM_CUDA(cudaSetDevice(m.ctx->device));
+  {
+    int rcw = m.wait_tail();  // a deferred insertion of the last frame may still be running
+    if (rcw) return rcw;
+  }
   const int sl = m.slab_of[cube_index];
   const int n = which == 0 ? m.cnt_c_h[sl] : m.cnt_s_h[sl];
   *n_out = n;

@@ -50,16 +50,22 @@ struct CubeMapH {
   void release();
   int roll(const double t[3]);
   int gather(int* n_mc, int* n_ms);
-  int insert(const int* d_counts, int nc_host, int ns_host, int world_frame);
-  int filter_valid();
-  int fetch_counts();
+  int insert(const int* d_counts, int nc_host, int ns_host, int world_frame, cudaStream_t s = nullptr);
+  int filter_valid(cudaStream_t s = nullptr);
+  int fetch_counts(cudaStream_t s = nullptr);
+  int adopt_counts();
+  int wait_tail();
+  PinnedBuf<int> pin_counts;
+  cudaEvent_t ev_tail = nullptr;
+  bool tail_pending = false, counts_in_flight = false;
+  int tail_flags = 0;
 };
 
 
 // One iteration of process() (laserMapping.cpp:327-1002) with the feature clouds already on the device.
 int cubemap_frame_core(CubeMapH& m, const float* d_corner_last, int nc, const float* d_surf_last, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
-                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready);
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready, bool defer_tail);
 
 }  // namespace ilsm
 

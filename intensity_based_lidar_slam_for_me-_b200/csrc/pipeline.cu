@@ -127,6 +127,9 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
     return rc;
   ILSM_CUDA(cudaEventRecord(c.ev_join, c.aux));
   // ---- laserOdometry
+  // the previous frame's deferred map insertion (side stream) reads the mapped pose from the LM state the odometry is
+  // about to overwrite: order the main stream after it (long finished by now -- it overlapped this frame's front end)
+  if (cm.tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.stream, cm.ev_tail, 0));
   if (!s.inited) {
     s.inited = true;
   } else {
@@ -171,7 +174,7 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
   ilsm_reg_opts_default(&mo);
   rc = cubemap_frame_core(s.cube->m, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
                           reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
-                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true);
+                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true);
   if (rc) return rc;
   s.frames++;
   return ILSM_OK;

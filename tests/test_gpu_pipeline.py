@@ -54,6 +54,18 @@ def test_sequence_matches_oracle(ctx, oracle_mod, ilsm):
         qr, tr = rel_pose(S, q0, t0, q, t)
         if k > 1:
             assert np.linalg.norm(gtm - tr) < 0.3, (k, gtm, tr)
+    # the map itself: every occupied cube of the oracle's window is identical on the device (this also joins the
+    # insertion of the last frame, which the pipeline defers to its side stream)
+    view = slam.cubemap()
+    occupied = [i for i in range(4851) if len(oslam.cube.cube(1, i)) or len(oslam.cube.cube(0, i))]
+    assert len(occupied) >= 2
+    n_pts = 0
+    for idx in occupied:
+        for which in (0, 1):
+            g, w = view.cube(which, idx), oslam.cube.cube(which, idx)
+            assert g.shape == w.shape and np.array_equal(g, w), (idx, which)
+            n_pts += len(g)
+    assert n_pts > 2000
     slam.close()
 
 
