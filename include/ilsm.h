@@ -346,6 +346,40 @@ ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int 
 ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
                             int* n_out);
 
+/* ------------------------------------------------------- ground-plane extraction (feeds mapOptimization) ---- */
+typedef struct ilsm_ground ilsm_ground;
+
+typedef struct ilsm_ground_opts {
+  double z_min, z_max;        /* screening band: -2.0 <= z <= -0.45   image_handler.h_ouster:50 */
+  double distance_threshold;  /* seg.setDistanceThreshold(0.01)       :60 */
+  double probability;         /* pcl::SACSegmentation default 0.99 */
+  int32_t max_iterations;     /* pcl::SACSegmentation default 50 (at most 62 here) */
+  int32_t seed;               /* seed of the declared sampler (PCL's rand() is unpinned) */
+  double band;                /* height <= 0.03                        :85 */
+  double max_angle_deg;       /* plane_normal . z > cos(15 deg)        :75 */
+} ilsm_ground_opts;
+
+typedef struct ilsm_ground_info {
+  int32_t n_band;           /* points in the screening band */
+  int32_t best_hypothesis;  /* index of the winning sample triple (-1: none) */
+  int32_t n_best_inliers;
+  int32_t iterations;       /* RANSAC iterations the adaptive loop ran */
+  int32_t accepted;         /* the refitted plane passed the 15-degree test */
+  int32_t reserved;
+} ilsm_ground_info;
+
+ILSM_API void ilsm_ground_opts_default(ilsm_ground_opts* o);
+ILSM_API int ilsm_ground_create(ilsm_ctx* ctx, ilsm_ground** out);
+ILSM_API void ilsm_ground_destroy(ilsm_ground* g);
+
+/* z-band screening, RANSAC plane (PCL 1.10 RandomSampleConsensus loop: best-so-far, adaptive k, all 64 candidate
+ * planes scored in parallel on the device), least-squares refit of the winner's inliers, 15-degree acceptance, then
+ * the points of the WHOLE input within `band` of the plane and z < 0, in input order, as 16-byte pcl::PointXYZ
+ * (out_xyz capacity in points; *n_out = number found).  coeff_abcd = the refitted plane (float, normal oriented up).
+ * Replaces: ImageHandler::groundPlaneExtraction  image_handler.h_ouster:41-100 (called at mapOptimization.cpp:136). */
+ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int stride_bytes, const ilsm_ground_opts* opts,
+                                 float* out_xyz, int capacity, int* n_out, float coeff_abcd[4], ilsm_ground_info* info);
+
 /* --------------------------------------- intensity-image feature back end (ORB matching + 3D-3D alignment) ---- */
 
 /* cv::DMatch layout (queryIdx, trainIdx, imgIdx, distance): a std::vector<cv::DMatch> can be filled in place. */

@@ -65,6 +65,16 @@ class SlamStats(C.Structure):
                 ("cubemap", CubeMapStats)]
 
 
+class GroundOpts(C.Structure):
+    _fields_ = [("z_min", C.c_double), ("z_max", C.c_double), ("distance_threshold", C.c_double), ("probability", C.c_double),
+                ("max_iterations", C.c_int32), ("seed", C.c_int32), ("band", C.c_double), ("max_angle_deg", C.c_double)]
+
+
+class GroundInfo(C.Structure):
+    _fields_ = [("n_band", C.c_int32), ("best_hypothesis", C.c_int32), ("n_best_inliers", C.c_int32), ("iterations", C.c_int32),
+                ("accepted", C.c_int32), ("reserved", C.c_int32)]
+
+
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
@@ -128,6 +138,10 @@ def load_library(path: str | None = None):
         "ilsm_slam_destroy": (None, [vp]),
         "ilsm_slam_cubemap": (vp, [vp]),
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
+        "ilsm_ground_opts_default": (None, [C.POINTER(GroundOpts)]),
+        "ilsm_ground_create": (i32, [vp, C.POINTER(vp)]),
+        "ilsm_ground_destroy": (None, [vp]),
+        "ilsm_ground_extract": (i32, [vp, vp, i32, i32, C.POINTER(GroundOpts), vp, i32, C.POINTER(i32), vp, C.POINTER(GroundInfo)]),
         "ilsm_orb_match": (i32, [vp, vp, i32, vp, i32, i32, i32, f64, vp, C.POINTER(i32), vp, C.POINTER(i32)]),
         "ilsm_align_points": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
@@ -585,3 +599,39 @@ class Slam:
         _check(self._lib.ilsm_slam_frame(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
                                          _ptr(tm), C.byref(st)))
         return qo, to, qm, tm, st
+
+
+class GroundExtractor:
+    """ilsm_ground: ImageHandler::groundPlaneExtraction (image_handler.h_ouster:41-100)."""
+
+    def __init__(self, ctx: Context):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_ground_create(ctx._h, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_ground_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, cloud, **kw):
+        a, n, stride = _cloud(cloud)
+        o = GroundOpts()
+        self._lib.ilsm_ground_opts_default(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        n_out = C.c_int(0)
+        co = np.zeros(4, np.float32)
+        info = GroundInfo()
+        _check(self._lib.ilsm_ground_extract(self._h, _ptr(a), n, stride, C.byref(o), _ptr(out), n, C.byref(n_out), _ptr(co),
+                                             C.byref(info)))
+        return out[:n_out.value, :3].copy(), co, info

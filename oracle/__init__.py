@@ -496,3 +496,121 @@ def align_points(src_xyz, dst_xyz, qt0=(0, 0, 0, 1, 0, 0, 0), max_iter=20, huber
     f["p"] = src.astype(np.float64)
     f["a"] = dst.astype(np.float64)
     return solve(f, np.array(qt0, np.float64), max_iter, huber_a)
+
+
+# ------------------------------------------------------------------------------------------------
+# ground-plane extraction (ImageHandler::groundPlaneExtraction, image_handler.h_ouster:41-100)
+# ------------------------------------------------------------------------------------------------
+def ground_sample_triples(m, count=64, seed=1):
+    """The DECLARED sampler (PCL's rand()-based one is unpinned): LCG x <- 1664525 x + 1013904223 (mod 2^32),
+    index = (x >> 8) mod m, three distinct indices per hypothesis."""
+    x = np.uint64(seed & 0xFFFFFFFF)
+    out = np.zeros((count, 3), np.int32)
+
+    def nxt():
+        nonlocal x
+        x = (x * np.uint64(1664525) + np.uint64(1013904223)) & np.uint64(0xFFFFFFFF)
+        return int(x >> np.uint64(8)) % m
+    for h in range(count):
+        a = nxt()
+        b = nxt()
+        while b == a:
+            b = nxt()
+        c = nxt()
+        while c == a or c == b:
+            c = nxt()
+        out[h] = (a, b, c)
+    return out
+
+
+def _plane_from_triple(p0, p1, p2):
+    """SampleConsensusModelPlane::computeModelCoefficients in float32, left-to-right, no FMA.  Returns (coeff[4], ok)."""
+    f = np.float32
+    a = (p1 - p0).astype(f)
+    b = (p2 - p0).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = (a / b).astype(f)
+    if r[0] == r[1] and r[2] == r[1]:
+        return np.zeros(4, f), False
+    n = np.array([f(a[1] * b[2]) - f(a[2] * b[1]), f(a[2] * b[0]) - f(a[0] * b[2]), f(a[0] * b[1]) - f(a[1] * b[0])], f)
+    nn = np.sqrt(f(f(f(n[0] * n[0]) + f(n[1] * n[1])) + f(n[2] * n[2])))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n = (n / nn).astype(f)
+    d = f(-1.0) * f(f(f(n[0] * p0[0]) + f(n[1] * p0[1])) + f(n[2] * p0[2]))
+    return np.array([n[0], n[1], n[2], d], f), bool(np.all(np.isfinite(n)))
+
+
+def ground_plane(cloud, z_min=-2.0, z_max=-0.45, dist_thresh=0.01, max_iterations=50, probability=0.99, seed=1,
+                 band=0.03, max_angle_deg=15.0):
+    """groundPlaneExtraction restated: z-band screening, RANSAC plane (PCL 1.10 RandomSampleConsensus::computeModel loop
+    with the declared sampler; inlier test |a x + b y + c z + d| < threshold in float), least-squares refit of the best
+    model's inliers (PCA, smallest eigenvector, oriented upward; sums in double -- PCL's float accumulation order is
+    not reproducible in parallel), acceptance n . z > cos(15 deg), ground = points within `band` of the plane with z < 0
+    (input order).  Returns (ground_xyz, coeff float32[4], info dict)."""
+    f = np.float32
+    pts = np.ascontiguousarray(np.asarray(cloud, np.float32)[:, :3])
+    z = pts[:, 2].astype(np.float64)
+    scr = pts[(z >= z_min) & (z <= z_max)]
+    m = len(scr)
+    info = dict(n_band=m, best=-1, n_best=0, iterations=0, accepted=False)
+    empty = np.zeros((0, 3), np.float32)
+    if m < 3:
+        return empty, np.zeros(4, f), info
+    n_hyp = 64
+    tri = ground_sample_triples(m, n_hyp, seed)
+    models, valid, counts = [], [], []
+    thr = f(dist_thresh)
+    for h in range(n_hyp):
+        co, ok = _plane_from_triple(scr[tri[h, 0]], scr[tri[h, 1]], scr[tri[h, 2]])
+        models.append(co)
+        valid.append(ok)
+        if ok:
+            dd = ((f(co[0]) * scr[:, 0] + f(co[1]) * scr[:, 1]).astype(f) + f(co[2]) * scr[:, 2]).astype(f) + f(co[3])
+            counts.append(int((np.abs(dd.astype(f)) < thr).sum()))
+        else:
+            counts.append(0)
+    # replay of RandomSampleConsensus::computeModel (PCL 1.10 ransac.hpp:48-140)
+    k, it, skipped, h = 1.0, 0, 0, 0
+    n_best, best = 0, -1
+    log_p = np.log(1.0 - probability)
+    eps = np.finfo(np.float64).eps
+    while it < k and skipped < max_iterations * 10 and h < n_hyp:
+        if not valid[h]:
+            skipped += 1
+            h += 1
+            continue
+        if counts[h] > n_best:
+            n_best, best = counts[h], h
+            w = n_best / float(m)
+            p_no = 1.0 - w ** 3
+            p_no = min(max(p_no, eps), 1.0 - eps)
+            k = log_p / np.log(p_no)
+        it += 1
+        h += 1
+        if it > max_iterations:
+            break
+    info.update(best=best, n_best=n_best, iterations=it, counts=np.array(counts), triples=tri)
+    if best < 0:
+        return empty, np.zeros(4, f), info
+    co = models[best]
+    dd = ((f(co[0]) * scr[:, 0] + f(co[1]) * scr[:, 1]).astype(f) + f(co[2]) * scr[:, 2]).astype(f) + f(co[3])
+    inl = scr[np.abs(dd.astype(f)) < thr].astype(np.float64)
+    if len(inl) > 3:  # optimizeModelCoefficients
+        c = inl.mean(axis=0)
+        q = inl - c
+        cov = q.T @ q / len(inl)
+        wv, vv = np.linalg.eigh(cov)
+        nrm = vv[:, 0]
+        if nrm[2] < 0:
+            nrm = -nrm
+        co = np.array([nrm[0], nrm[1], nrm[2], -float(nrm @ c)], np.float64).astype(f)
+    A, B, C_, D = [float(v) for v in co]
+    info["coeff"] = co
+    if not (f(C_) > np.cos(max_angle_deg * np.pi / 180.0)):
+        return empty, co, info
+    info["accepted"] = True
+    P = pts.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        height = np.abs(A * P[:, 0] + B * P[:, 1] + C_ * P[:, 2] + D) / np.sqrt(A * A + B * B + C_ * C_)
+        keep = (height <= band) & (P[:, 2] < 0.0)
+    return pts[keep], co, info
