@@ -251,7 +251,7 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device(f"cuda:{local_rank}")
 
     ilsm._build.build()
-    c = workload(seed_shift=rank)  # one independent frame/sequence per rank
+    c = workload()  # replicas: every rank registers the same frame against its own copy of the map (fixed work per GPU)
     ctx = ilsm.Context(local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     mc, ms = ctx.new_map(), ctx.new_map()
