@@ -341,7 +341,8 @@ ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int 
                                    ilsm_features* out);
 
 /* pcl::VoxelGrid<PointXYZI>::filter with a cubic leaf: centroid of every field per voxel, output in ascending
- * voxel index; points of one voxel are accumulated in input order.  n <= 16384 per call in this version.
+ * voxel index; points of one voxel are accumulated in input order.  Up to 16384 points are handled by one block (one
+ * launch); larger clouds (< 2^24 points) by a tiled multi-block sort.
  * Replaces: downSizeFilterCorner/Surf.filter  laserMapping.cpp:608-616 ; voxel_grid_.filter mapOptimization.cpp:368-370 */
 ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
                             int* n_out);
@@ -379,6 +380,42 @@ ILSM_API void ilsm_ground_destroy(ilsm_ground* g);
  * Replaces: ImageHandler::groundPlaneExtraction  image_handler.h_ouster:41-100 (called at mapOptimization.cpp:136). */
 ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int stride_bytes, const ilsm_ground_opts* opts,
                                  float* out_xyz, int capacity, int* n_out, float coeff_abcd[4], ilsm_ground_info* info);
+
+/* ----------------------------------------------- mapOptimization: the mapping node spot.launch starts ---- */
+typedef struct ilsm_mapopt ilsm_mapopt;
+
+typedef struct ilsm_mapopt_stats {
+  ilsm_ground_info ground;
+  float ground_coeff[4];
+  int32_t n_ground;          /* RANSAC ground points of the frame */
+  int32_t n_plane_in;        /* pc_plane points appended */
+  int32_t n_query;           /* points after VoxelGrid(0.8) */
+  int32_t ran_optimization;  /* 0 on the first callback (tree build only) */
+  int32_t converged;         /* summary.termination_type == ceres::CONVERGENCE  mapOptimization.cpp:448 */
+  int32_t map_size;          /* points in the ground map after Add_Points */
+  ilsm_solve_summary solve;
+  double q_key[4], t_key[3]; /* cur_keyframe pose used for the insertion: optimised if converged, else predicted */
+  double reserved;
+} ilsm_mapopt_stats;
+
+/* voxel_leaf = voxel_grid_ leaf (0.8, mapOptimization.cpp:578), downsample_size = ikd-Tree box (0.4, :504);
+ * <= 0 selects those defaults. */
+ILSM_API int ilsm_mapopt_create(ilsm_ctx* ctx, float voxel_leaf, float downsample_size, ilsm_mapopt** out);
+ILSM_API void ilsm_mapopt_destroy(ilsm_mapopt* mo);
+ILSM_API int ilsm_mapopt_map_size(const ilsm_mapopt* mo);
+/* ikdtree->flatten: the ground map in map order (packed xyz0). */
+ILSM_API int ilsm_mapopt_map_points(ilsm_mapopt* mo, float* out_xyz0, int capacity, int* n_out);
+
+/* One mapOptimizationCallback iteration (mapOptimization.cpp:99-500, LiDAR part): ground extraction from the organised
+ * frame, + pc_plane (the less-flat cloud of scanRegistration), first call: tree build at the predicted pose; afterwards
+ * VoxelGrid(0.8), 5-NN plane association against the ground map, LidarPlaneNormFactor solve (one pass, 10 iterations,
+ * Huber 0.1), transformUpdate only on CONVERGENCE, Add_Points(0.4 m boxes) at the keyframe pose.  q_w / t_w return the
+ * parameter block after the solve (Ceres writes it in place whatever the termination type); stats->q_key / t_key the
+ * pose the map was extended with.  Replaces: mapOptimization::mapOptimizationCallback, LiDAR residuals only (the ORB
+ * point-to-point blocks are dead code in the reference: `&& false` at :251, sliding window size 0). */
+ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, int stride_bytes, const float* plane_xyz, int n_plane,
+                               int plane_stride_bytes, const double q_wodom_xyzw[4], const double t_wodom[3], double q_w_xyzw[4],
+                               double t_w[3], const ilsm_ground_opts* gopts, ilsm_mapopt_stats* stats);
 
 /* --------------------------------------- intensity-image feature back end (ORB matching + 3D-3D alignment) ---- */
 

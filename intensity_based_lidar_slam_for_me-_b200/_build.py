@@ -26,12 +26,33 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stale():
-    if not os.path.exists(LIB):
+STAMP = LIB + ".stamp"
+LOCK = os.path.join(HERE, ".build.lock")
+
+
+def _fingerprint(extra_flags=()):
+    """Content hash of every source, header and flag that goes into the library.  mtimes are useless here: the tree is
+    copied to the GPU box (fresh mtimes in arbitrary order), and a stale verdict there would make every rank of a
+    multi-GPU launch rebuild the library at the same time."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h")))
+    deps.append(os.path.join(HERE, "..", "include", "ilsm.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    h.update(repr((NVCC_FLAGS, sorted(FMAD.items()), list(extra_flags))).encode())
+    return h.hexdigest()
+
+
+def _stale(lib=LIB, extra_flags=()):
+    if not os.path.exists(lib) or not os.path.exists(lib + ".stamp"):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ilsm.h"), __file__]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        return open(lib + ".stamp").read().strip() != _fingerprint(extra_flags)
+    except OSError:
+        return True
 
 
 def nvcc_path():
@@ -39,9 +60,22 @@ def nvcc_path():
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB, obj_dir: str = OBJ) -> str:
-    """One nvcc -c per source (in parallel), then one link into libilsm_cuda.so (or `lib`, for instrumented variants)."""
-    if not force and lib == LIB and not _stale():
+    """One nvcc -c per source (in parallel), then one link into libilsm_cuda.so (or `lib`, for instrumented variants).
+    Serialised across processes with a file lock: the ranks of a torchrun launch all call this."""
+    if not force and not _stale(lib, extra_flags):
         return lib
+    import fcntl
+    with open(LOCK, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(lib, extra_flags):  # another process built it while we waited
+                return lib
+            return _build_locked(verbose, extra_flags, lib, obj_dir)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose, extra_flags, lib, obj_dir):
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in sources():
@@ -58,8 +92,12 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str =
         if verbose:
             print(out)
         objs.append(obj)
-    r = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs,
+    tmp = lib + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs,
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, lib)  # atomic: a concurrent dlopen never sees a half-written library
+    with open(lib + ".stamp", "w") as fh:
+        fh.write(_fingerprint(extra_flags))
     return lib

@@ -75,6 +75,12 @@ class GroundInfo(C.Structure):
                 ("accepted", C.c_int32), ("reserved", C.c_int32)]
 
 
+class MapOptStats(C.Structure):
+    _fields_ = [("ground", GroundInfo), ("ground_coeff", C.c_float * 4), ("n_ground", C.c_int32), ("n_plane_in", C.c_int32),
+                ("n_query", C.c_int32), ("ran_optimization", C.c_int32), ("converged", C.c_int32), ("map_size", C.c_int32),
+                ("solve", SolveSummary), ("q_key", C.c_double * 4), ("t_key", C.c_double * 3), ("reserved", C.c_double)]
+
+
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
@@ -142,6 +148,11 @@ def load_library(path: str | None = None):
         "ilsm_ground_create": (i32, [vp, C.POINTER(vp)]),
         "ilsm_ground_destroy": (None, [vp]),
         "ilsm_ground_extract": (i32, [vp, vp, i32, i32, C.POINTER(GroundOpts), vp, i32, C.POINTER(i32), vp, C.POINTER(GroundInfo)]),
+        "ilsm_mapopt_create": (i32, [vp, f32, f32, C.POINTER(vp)]),
+        "ilsm_mapopt_destroy": (None, [vp]),
+        "ilsm_mapopt_map_size": (i32, [vp]),
+        "ilsm_mapopt_map_points": (i32, [vp, vp, i32, C.POINTER(i32)]),
+        "ilsm_mapopt_frame": (i32, [vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, C.POINTER(GroundOpts), C.POINTER(MapOptStats)]),
         "ilsm_orb_match": (i32, [vp, vp, i32, vp, i32, i32, i32, f64, vp, C.POINTER(i32), vp, C.POINTER(i32)]),
         "ilsm_align_points": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, f64, C.POINTER(SolveSummary)]),
         "ilsm_associate_dev": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, C.POINTER(RegOpts)]),
@@ -635,3 +646,49 @@ class GroundExtractor:
         _check(self._lib.ilsm_ground_extract(self._h, _ptr(a), n, stride, C.byref(o), _ptr(out), n, C.byref(n_out), _ptr(co),
                                              C.byref(info)))
         return out[:n_out.value, :3].copy(), co, info
+
+
+class MapOptimization:
+    """ilsm_mapopt: mapOptimization::mapOptimizationCallback (the mapping node spot.launch starts), one frame per call."""
+
+    def __init__(self, ctx: Context, voxel_leaf: float = 0.8, downsample_size: float = 0.4):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.ilsm_mapopt_create(ctx._h, voxel_leaf, downsample_size, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self._ctx, "_h", None):
+            self._lib.ilsm_mapopt_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self._lib.ilsm_mapopt_map_size(self._h))
+
+    def map_points(self):
+        n = C.c_int(0)
+        _check(self._lib.ilsm_mapopt_map_points(self._h, None, 0, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), np.float32)
+        _check(self._lib.ilsm_mapopt_map_points(self._h, _ptr(out), n.value, C.byref(n)))
+        return out[:n.value, :3].copy()
+
+    def frame(self, cloud, plane_cloud, q_wodom, t_wodom, **ground_kw):
+        a, n, stride = _cloud(cloud)
+        p, npl, pstride = _cloud(plane_cloud)
+        qo, to = np.array(q_wodom, np.float64), np.array(t_wodom, np.float64)
+        qw, tw = np.zeros(4), np.zeros(3)
+        go = GroundOpts()
+        self._lib.ilsm_ground_opts_default(C.byref(go))
+        for k, v in ground_kw.items():
+            setattr(go, k, v)
+        st = MapOptStats()
+        _check(self._lib.ilsm_mapopt_frame(self._h, _ptr(a), n, stride, _ptr(p), npl, pstride, _ptr(qo), _ptr(to), _ptr(qw), _ptr(tw),
+                                           C.byref(go), C.byref(st)))
+        return qw, tw, st

@@ -104,7 +104,7 @@ int Ctx::init(int dev) {
 
 void Ctx::release() {
   if (stream) cudaStreamSynchronize(stream);
-  fe.chunk_hist.release(), fe.chunk_base.release(), fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
+  fe.vg_keys.release(), fe.vg_state.release(), fe.vg_chunk.release(), fe.chunk_hist.release(), fe.chunk_base.release(), fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
   fe.src_index.release(), fe.label.release(), fe.sort_ind.release(), fe.ring_sharp.release(), fe.ring_lsharp.release();
   fe.ring_flat.release(), fe.sharp.release(), fe.lsharp.release(), fe.flat.release(), fe.counts.release();
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
@@ -613,9 +613,12 @@ ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_
   int rc;
   if ((rc = c.fe.raw.reserve(bytes / 4 + 4)) || (rc = c.fe.vox_out.reserve(n + 4)) || (rc = c.fe.vox_n.reserve(4))) return rc;
   ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
-  if ((rc = c.voxelgrid_dev(c.fe.raw.p, n, nullptr, 0, stride_bytes, stride_bytes >= 32 ? 4 : 3, leaf, c.fe.vox_out.p,
-                            c.fe.vox_n.p)))
-    return rc;
+  const int ioff = stride_bytes >= 32 ? 4 : 3;
+  if (n <= 16384)  // one block sorts in shared memory; larger clouds take the tiled multi-block path
+    rc = c.voxelgrid_dev(c.fe.raw.p, n, nullptr, 0, stride_bytes, ioff, leaf, c.fe.vox_out.p, c.fe.vox_n.p);
+  else
+    rc = c.voxelgrid_large_dev(c.fe.raw.p, n, stride_bytes, ioff, leaf, c.fe.vox_out.p, c.fe.vox_n.p);
+  if (rc) return rc;
   int* pin = reinterpret_cast<int*>(c.pinned.p);
   ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.vox_n.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaStreamSynchronize(c.stream));

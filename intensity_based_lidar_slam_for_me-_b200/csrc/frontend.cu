@@ -593,6 +593,190 @@ __global__ void __launch_bounds__(1024) voxelgrid_kernel(VoxJobs jobs, int* err)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// VoxelGrid of clouds that do not fit one block (n > 16384, e.g. mapOptimization's ground + less-flat cloud): the
+// same PCL semantics as voxelgrid_block, spread over the GPU.  bbox reduction -> keys (voxel << 24 | order) -> tiled
+// bitonic sort (16384-key tiles sorted in registers/shuffles/shared memory, cross-tile stages through global memory)
+// -> run heads -> per-chunk head counts + scan -> ordered float centroids.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kVgTile = 16384;
+__device__ __forceinline__ int fenc(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float fdec(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void vg_init_kernel(VgState* st) {
+  pdl_entry();
+  if (threadIdx.x < 3) st->mn[threadIdx.x] = fenc(__int_as_float(0x7f800000)), st->mx[threadIdx.x] = fenc(__int_as_float(0xff800000));
+  if (threadIdx.x == 3) st->n_out = 0;
+}
+
+__global__ void __launch_bounds__(256) vg_pack_bbox_kernel(const float* __restrict__ in, int n, int stride_f, int ioff,
+                                                           float4* __restrict__ packed, VgState* st) {
+  pdl_entry();
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const float* p = in + (size_t)t * stride_f;
+    const float4 v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + ioff));
+    packed[t] = v;
+    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+      mn[0] = fminf(mn[0], v.x), mn[1] = fminf(mn[1], v.y), mn[2] = fminf(mn[2], v.z);
+      mx[0] = fmaxf(mx[0], v.x), mx[1] = fmaxf(mx[1], v.y), mx[2] = fmaxf(mx[2], v.z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) atomicMin(&st->mn[a], fenc(mn[a])), atomicMax(&st->mx[a], fenc(mx[a]));
+  }
+}
+
+__global__ void __launch_bounds__(256) vg_keys_kernel(const float4* __restrict__ packed, int n, int P, float leaf, const VgState* st,
+                                                      u64* __restrict__ keys, int* err) {
+  pdl_entry();
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = __float2int_rd(__fmul_rn(fdec(st->mn[a]), inv));
+    div_b[a] = __float2int_rd(__fmul_rn(fdec(st->mx[a]), inv)) - min_b[a] + 1;
+  }
+  const long long mul1 = div_b[0], mul2 = (long long)div_b[0] * div_b[1];
+  const bool too_small = mul2 * div_b[2] >= (1ll << 31);  // pcl: "Leaf size is too small for the input dataset"
+  if (too_small && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 2);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < P; t += gridDim.x * blockDim.x) {
+    u64 key = ~0ull;
+    if (t < n && !too_small) {
+      const float4 p = packed[t];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)min_b[0]));
+        const int i1 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)min_b[1]));
+        const int i2 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)min_b[2]));
+        const long long idx = i0 + i1 * mul1 + i2 * mul2;
+        key = ((u64)idx << 24) | (uint32_t)t;
+      }
+    }
+    keys[t] = key;
+  }
+}
+
+// one 16384-key tile per block (E = 16 keys per thread).  merge_only == 0: full sort of the tile (stages 2 .. tile);
+// merge_only == 1: the partner distances tile/2 .. 1 of stage k (after the cross-tile exchanges of that stage).
+__global__ void __launch_bounds__(1024) vg_sort_tile_kernel(u64* __restrict__ keys, unsigned k, int merge_only) {
+  pdl_entry();
+  extern __shared__ u64 tile[];
+  const unsigned base = blockIdx.x * (unsigned)kVgTile;
+  for (int t = threadIdx.x; t < kVgTile; t += blockDim.x) tile[t] = keys[base + t];
+  __syncthreads();
+  if (merge_only) bitonic_sort_regs<16>(tile, kVgTile, base, k, k, true);
+  else bitonic_sort_regs<16>(tile, kVgTile, base, 2u, (unsigned)kVgTile, false);
+  for (int t = threadIdx.x; t < kVgTile; t += blockDim.x) keys[base + t] = tile[t];
+}
+
+// cross-tile compare-exchange of stage k at partner distance j >= tile
+__global__ void __launch_bounds__(256) vg_sort_global_kernel(u64* __restrict__ keys, unsigned P, unsigned k, unsigned j) {
+  pdl_entry();
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < P / 2; t += gridDim.x * blockDim.x) {
+    const unsigned i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));  // index with bit j clear
+    const unsigned p = i | j;
+    const u64 a = keys[i], b = keys[p];
+    const bool up = (i & k) == 0;
+    if ((a > b) == up) keys[i] = b, keys[p] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) vg_head_count_kernel(const u64* __restrict__ keys, int P, int* __restrict__ chunk_cnt) {
+  pdl_entry();
+  __shared__ int wc[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  bool head = false;
+  if (t < P && keys[t] != ~0ull) head = t == 0 || (keys[t] >> 24) != (keys[t - 1] >> 24);
+  const unsigned b = __ballot_sync(0xffffffffu, head);
+  if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += wc[w];
+    chunk_cnt[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) vg_scan_kernel(const int* __restrict__ chunk_cnt, int chunks, int* __restrict__ chunk_base,
+                                                       int* __restrict__ total, int* __restrict__ total2) {
+  pdl_entry();
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < chunks; c0 += 1024) {
+    const int c = c0 + threadIdx.x;
+    const int v = c < chunks ? chunk_cnt[c] : 0;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) wbase += wsum[w];
+      tot += wsum[w];
+    }
+    const int carry = carry_s;
+    if (c < chunks) chunk_base[c] = carry + wbase + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *total = carry_s;
+    if (total2) *total2 = carry_s;
+  }
+}
+
+__global__ void __launch_bounds__(256) vg_centroid_kernel(const u64* __restrict__ keys, int P, const float4* __restrict__ packed,
+                                                          const int* __restrict__ chunk_base, float4* __restrict__ out) {
+  pdl_entry();
+  __shared__ int wc[8];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool head = false;
+  if (t < P && keys[t] != ~0ull) head = t == 0 || (keys[t] >> 24) != (keys[t - 1] >> 24);
+  const unsigned b = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) wc[warp] = __popc(b);
+  __syncthreads();
+  if (!head) return;
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += wc[w];
+  const int slot = chunk_base[blockIdx.x] + wbase + __popc(b & ((1u << lane) - 1u));
+  const u64 vox = keys[t] >> 24;
+  int cnt = 1;
+  while (t + cnt < P && (keys[t + cnt] >> 24) == vox) ++cnt;
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  for (int e0 = 0; e0 < cnt; e0 += 4) {
+    float4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = e0 + u < cnt ? packed[(int)(keys[t + e0 + u] & 0xFFFFFF)] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e0 + u < cnt) sx = __fadd_rn(sx, q[u].x), sy = __fadd_rn(sy, q[u].y), sz = __fadd_rn(sz, q[u].z), si = __fadd_rn(si, q[u].w);
+  }
+  const float c = (float)cnt;
+  out[slot] = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), __fdiv_rn(si, c));
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 int Ctx::project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
@@ -672,6 +856,43 @@ int Ctx::voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_ou
   ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), (size_t)P * sizeof(u64), s, jobs, fe.stats.p + kStErr));
   count_launches(1);
   return check_launch("voxelgrid_pair");
+}
+
+// VoxelGrid of n > 16384 points (up to 2^24): see the vg_* kernels above.  d_n_out receives the voxel count.
+int Ctx::voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out) {
+  if (n >= (1 << 24)) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: at most 2^24 points");
+  unsigned P = kVgTile;
+  while (P < (unsigned)n) P <<= 1;
+  const int chunks = (int)(P / 256);
+  int rc;
+  if ((rc = fe.vox_packed.reserve((size_t)n + 8)) || (rc = fe.vg_keys.reserve(P)) || (rc = fe.vg_state.reserve(1)) ||
+      (rc = fe.vg_chunk.reserve(2 * (size_t)chunks + 8)) || (rc = fe.stats.reserve(kStInts + 8)))
+    return rc;
+  cudaStream_t s = stream;
+  ILSM_CUDA(cudaFuncSetAttribute(vg_sort_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVgTile * sizeof(u64))));
+  const int grid = sm_count * 4;
+  int launches = 0;
+  ILSM_CUDA(launch_pdl(vg_init_kernel, dim3(1), dim3(32), 0, s, fe.vg_state.p));
+  ILSM_CUDA(launch_pdl(vg_pack_bbox_kernel, dim3(grid), dim3(256), 0, s, d_in, n, stride_bytes / 4, ioff, fe.vox_packed.p, fe.vg_state.p));
+  ILSM_CUDA(launch_pdl(vg_keys_kernel, dim3(grid), dim3(256), 0, s, (const float4*)fe.vox_packed.p, n, (int)P, leaf,
+                       (const VgState*)fe.vg_state.p, fe.vg_keys.p, fe.stats.p + kStErr));
+  ILSM_CUDA(launch_pdl(vg_sort_tile_kernel, dim3(P / kVgTile), dim3(1024), kVgTile * sizeof(u64), s, fe.vg_keys.p, 0u, 0));
+  launches += 4;
+  for (unsigned k = 2u * kVgTile; k <= P; k <<= 1) {
+    for (unsigned j = k >> 1; j >= (unsigned)kVgTile; j >>= 1) {
+      ILSM_CUDA(launch_pdl(vg_sort_global_kernel, dim3(grid), dim3(256), 0, s, fe.vg_keys.p, P, k, j));
+      ++launches;
+    }
+    ILSM_CUDA(launch_pdl(vg_sort_tile_kernel, dim3(P / kVgTile), dim3(1024), kVgTile * sizeof(u64), s, fe.vg_keys.p, k, 1));
+    ++launches;
+  }
+  ILSM_CUDA(launch_pdl(vg_head_count_kernel, dim3(chunks), dim3(256), 0, s, (const u64*)fe.vg_keys.p, (int)P, fe.vg_chunk.p));
+  ILSM_CUDA(launch_pdl(vg_scan_kernel, dim3(1), dim3(1024), 0, s, (const int*)fe.vg_chunk.p, chunks, fe.vg_chunk.p + chunks,
+                       &fe.vg_state.p->n_out, d_n_out));
+  ILSM_CUDA(launch_pdl(vg_centroid_kernel, dim3(chunks), dim3(256), 0, s, (const u64*)fe.vg_keys.p, (int)P,
+                       (const float4*)fe.vox_packed.p, (const int*)(fe.vg_chunk.p + chunks), d_out));
+  count_launches(launches + 3);
+  return check_launch("voxelgrid_large");
 }
 
 int Ctx::gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out) {

@@ -316,21 +316,19 @@ ILSM_API void ilsm_ground_destroy(ilsm_ground* g) {
   delete g;
 }
 
-ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int stride_bytes, const ilsm_ground_opts* opts,
-                                 float* out_xyz, int capacity, int* n_out, float coeff_abcd[4], ilsm_ground_info* info) {
-  if (!g || !n_out || (n > 0 && !xyz)) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: null argument");
-  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: bad n/stride");
-  ilsm_ground_opts o;
-  if (opts) o = *opts; else ilsm_ground_opts_default(&o);
-  if (o.max_iterations < 1 || o.max_iterations > 62) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: max_iterations must be in [1, 62]");
+}  // extern "C"
+
+namespace ilsm {
+// The extraction with the frame taken from the host (from_host) or already on the device; the ground points stay on
+// the device in g->b.out (packed xyz0, *n_out of them).  Caller holds the context mutex.
+int ground_extract_core(ilsm_ground* g, const float* xyz, bool from_host, int n, int stride_bytes, const ilsm_ground_opts& o,
+                        int* n_out, float coeff_abcd[4], ilsm_ground_info* info) {
   *n_out = 0;
   if (info) memset(info, 0, sizeof(*info)), info->best_hypothesis = -1;
   if (coeff_abcd) coeff_abcd[0] = coeff_abcd[1] = coeff_abcd[2] = coeff_abcd[3] = 0.f;
   if (n == 0) return ILSM_OK;
   Ctx& c = *g->ctx;
   GroundBufs& b = g->b;
-  std::lock_guard<std::mutex> lk(c.mu);
-  ILSM_CUDA(cudaSetDevice(c.device));
   const int chunks = (n + kGroundChunk - 1) / kGroundChunk;
   const size_t bytes = (size_t)n * stride_bytes;
   int rc;
@@ -341,7 +339,7 @@ ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int st
     return rc;
   cudaStream_t s = c.stream;
   const int sf = stride_bytes / 4;
-  ILSM_CUDA(cudaMemcpyAsync(b.raw.p, xyz, bytes, cudaMemcpyHostToDevice, s));
+  ILSM_CUDA(cudaMemcpyAsync(b.raw.p, xyz, bytes, from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
   // 1. screening: stable compaction of the z band
   ILSM_CUDA(launch_pdl(ground_count_kernel, dim3(chunks), dim3(kGroundChunk), 0, s, (const float*)b.raw.p, n, sf, 0, o.z_min, o.z_max,
                        (const float*)nullptr, o.band, b.chunk_cnt.p));
@@ -418,13 +416,34 @@ ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int st
   *n_out = ng;
   if (coeff_abcd) for (int i = 0; i < 4; ++i) coeff_abcd[i] = pin_f[i];
   if (info) info->accepted = pin_f[4] != 0.f;
+  return check_launch("ground_extract");
+}
+
+const float4* ground_points_dev(ilsm_ground* g) { return g->b.out.p; }
+}  // namespace ilsm
+
+extern "C" {
+
+ILSM_API int ilsm_ground_extract(ilsm_ground* g, const float* xyz, int n, int stride_bytes, const ilsm_ground_opts* opts,
+                                 float* out_xyz, int capacity, int* n_out, float coeff_abcd[4], ilsm_ground_info* info) {
+  if (!g || !n_out || (n > 0 && !xyz)) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: null argument");
+  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: bad n/stride");
+  ilsm_ground_opts o;
+  if (opts) o = *opts; else ilsm_ground_opts_default(&o);
+  if (o.max_iterations < 1 || o.max_iterations > 62) return fail(ILSM_ERR_INVALID_ARG, "ground_extract: max_iterations must be in [1, 62]");
+  Ctx& c = *g->ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  int rc = ground_extract_core(g, xyz, true, n, stride_bytes, o, n_out, coeff_abcd, info);
+  if (rc) return rc;
+  const int ng = *n_out;
   if (ng > 0 && out_xyz) {
     const int kcp = ng < capacity ? ng : capacity;
     // pcl::PointXYZ layout: 16-byte points (x, y, z, pad)
-    ILSM_CUDA(cudaMemcpyAsync(out_xyz, b.out.p, (size_t)kcp * 16, cudaMemcpyDeviceToHost, s));
-    ILSM_CUDA(cudaStreamSynchronize(s));
+    ILSM_CUDA(cudaMemcpyAsync(out_xyz, g->b.out.p, (size_t)kcp * 16, cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));
   }
-  return check_launch("ground_extract");
+  return ILSM_OK;
 }
 
 }  // extern "C"

@@ -154,11 +154,20 @@ struct FactorBufs {
   int n = 0, nc = 0;
 };
 
+struct VgState {      // device-resident scalars of one multi-block VoxelGrid
+  int mn[3], mx[3];   // ordered-int encoded float min / max of the finite points
+  int n_out;
+  int pad;
+};
+
 // Front-end scratch and outputs (device-resident between the front end and the registration).
 struct FeBufs {
   DevBuf<unsigned char> scanid, picked;
   DevBuf<float> ori, curv;
   DevBuf<int> stats, src_index, label, sort_ind, ring_sharp, ring_lsharp, ring_flat, sharp, lsharp, flat, counts;
+  DevBuf<u64> vg_keys;            // multi-block VoxelGrid: sort keys, state, per-chunk head counts / bases
+  DevBuf<VgState> vg_state;
+  DevBuf<int> vg_chunk;
   DevBuf<int> chunk_hist, chunk_base;  // ring counts per 256-point chunk of the frame and their per-ring prefix
   DevBuf<float4> cloud, ring_pts, ring_out, lflat, vox_packed;
   DevBuf<float> raw;                 // staged caller frame
@@ -202,6 +211,7 @@ struct Ctx {
   int features_dev(const float* d_in, int n, int stride_bytes, float min_range);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);
+  int voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out);
   int voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
                          float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s);
   int gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out);

@@ -12,9 +12,14 @@ constexpr int kVoxelBlockMax = 16384;  // points one block can sort in shared me
 // is below E stay inside the thread, steps with E <= j < 32 E go through warp shuffles, and only the steps with
 // j >= 32 E (15 of the 91 steps at P = 8192 with 1024 threads) exchange through shared memory with a barrier.  The
 // shared-memory exchange uses a striped layout (element e of thread t at e * blockDim + t): conflict-free.
+// `base` = global index of keys[0] and [k_first, k_last] = the stages to run make the same routine one tile of a
+// multi-block sort: a tile sorts itself with k = 2 .. P (direction from the GLOBAL index), and after the cross-tile
+// exchanges of a stage k > P it finishes that stage's partner distances P/2 .. 1 (merge_only).
 template <int E>
-static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
+static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P, unsigned base = 0u, unsigned k_first = 2u,
+                                                         unsigned k_last = 0u, bool merge_only = false) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (k_last == 0u) k_last = (unsigned)P;
   u64 r[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
@@ -24,8 +29,8 @@ static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
   __syncthreads();
   const bool active = tid * E < P;  // P < blockDim.x: the idle threads hold sentinels and stay out of memory
   const int ns = E == 1 ? P : nt;   // stripe length (E > 1 implies P == E * blockDim.x)
-  for (int k = 2; k <= P; k <<= 1) {
-    int j = k >> 1;
+  for (unsigned k = k_first; k <= k_last; k <<= 1) {
+    int j = merge_only ? P >> 1 : (int)(k >> 1);
     for (; j >= 32 * E; j >>= 1) {  // partner in another warp: striped exchange through shared memory
       const int tj = j / E;
       if (active) {
@@ -38,7 +43,7 @@ static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
         for (int e = 0; e < E; ++e) {
           const int idx = tid * E + e;
           const u64 o = keys[e * ns + (tid ^ tj)];
-          const bool want_min = ((idx & j) == 0) == ((idx & k) == 0);
+          const bool want_min = ((idx & j) == 0) == (((base + (unsigned)idx) & k) == 0);
           r[e] = want_min ? (o < r[e] ? o : r[e]) : (o > r[e] ? o : r[e]);
         }
       }
@@ -50,7 +55,7 @@ static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
       for (int e = 0; e < E; ++e) {
         const int idx = tid * E + e;
         const u64 o = __shfl_xor_sync(0xffffffffu, r[e], lj);
-        const bool want_min = ((idx & j) == 0) == ((idx & k) == 0);
+        const bool want_min = ((idx & j) == 0) == (((base + (unsigned)idx) & k) == 0);
         r[e] = want_min ? (o < r[e] ? o : r[e]) : (o > r[e] ? o : r[e]);
       }
     }
@@ -61,7 +66,7 @@ static __device__ __forceinline__ void bitonic_sort_regs(u64* keys, int P) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           if ((e & jj) == 0) {
-            const bool up = ((tid * E + e) & k) == 0;
+            const bool up = ((base + (unsigned)(tid * E + e)) & k) == 0;
             const u64 a = r[e], b = r[e | jj];
             const bool sw = (a > b) == up;
             r[e] = sw ? b : a;

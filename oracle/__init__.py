@@ -614,3 +614,62 @@ def ground_plane(cloud, z_min=-2.0, z_max=-0.45, dist_thresh=0.01, max_iteration
         height = np.abs(A * P[:, 0] + B * P[:, 1] + C_ * P[:, 2] + D) / np.sqrt(A * A + B * B + C_ * C_)
         keep = (height <= band) & (P[:, 2] < 0.0)
     return pts[keep], co, info
+
+
+# ------------------------------------------------------------------------------------------------
+# mapOptimization::mapOptimizationCallback, LiDAR part (mapOptimization.cpp:99-500)
+# ------------------------------------------------------------------------------------------------
+def _quat_to_mat(q):  # Eigen::Quaterniond::toRotationMatrix
+    x, y, z, w = q
+    tx, ty, tz = 2 * x, 2 * y, 2 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz, tyy, tyz, tzz = tx * x, ty * x, tz * x, ty * y, tz * y, tz * z
+    return np.array([[1 - (tyy + tzz), txy - twz, txz + twy], [txy + twz, 1 - (txx + tzz), tyz - twx],
+                     [txz - twy, tyz + twx, 1 - (txx + tyy)]])
+
+
+def _transform_cloud(q, t, pts):
+    """pcl::transformPointCloud with an Eigen::Matrix4d: double math, rows summed left to right, float store."""
+    R = _quat_to_mat(q)
+    p = np.asarray(pts, np.float32)[:, :3].astype(np.float64)
+    out = np.empty((len(p), 3), np.float32)
+    for a in range(3):
+        out[:, a] = (((R[a, 0] * p[:, 0] + R[a, 1] * p[:, 1]) + R[a, 2] * p[:, 2]) + t[a]).astype(np.float32)
+    return out
+
+
+class MapOptimization:
+    def __init__(self, voxel_leaf=0.8, downsample_size=0.4):
+        self.leaf, self.ds = voxel_leaf, downsample_size
+        self.map = None
+        self.q_wmap_wodom = np.array([0, 0, 0, 1.0])
+        self.t_wmap_wodom = np.zeros(3)
+
+    def frame(self, cloud, plane_cloud, q_wodom, t_wodom, **ground_kw):
+        g, coeff, ginfo = ground_plane(cloud, **ground_kw)
+        merged = np.concatenate([g, np.asarray(plane_cloud, np.float32)[:, :3]]).astype(np.float32)
+        q_wodom, t_wodom = np.asarray(q_wodom, np.float64), np.asarray(t_wodom, np.float64)
+        qw = _qmul(self.q_wmap_wodom, q_wodom)
+        tw = _qrot(self.q_wmap_wodom, t_wodom) + self.t_wmap_wodom
+        info = dict(ground=ginfo, n_ground=len(g), ran_optimization=0, converged=False)
+        if self.map is None:
+            self.map = _transform_cloud(qw, tw, merged)
+            info["map_size"] = len(self.map)
+            return np.concatenate([qw, tw]), info
+        m4 = np.zeros((len(merged), 4), np.float32)
+        m4[:, :3] = merged
+        stack = voxelgrid(m4, self.leaf)
+        fac = associate(np.zeros((0, 3), np.float32), self.map, np.zeros((0, 4), np.float32), stack, np.concatenate([qw, tw]))
+        x, sm = solve(fac, np.concatenate([qw, tw]), 10, 0.1)
+        conv = sm.termination == 0
+        qk, tk = (x[:4], x[4:]) if conv else (qw, tw)
+        if conv:  # transformUpdate
+            n2 = float(q_wodom @ q_wodom)
+            qinv = np.array([-q_wodom[0], -q_wodom[1], -q_wodom[2], q_wodom[3]]) / n2
+            self.q_wmap_wodom = _qmul(qk, qinv)
+            self.t_wmap_wodom = tk - _qrot(self.q_wmap_wodom, t_wodom)
+        world = _transform_cloud(qk, tk, stack)
+        self.map = ikd_add_points(self.map, world, self.ds, True)
+        info.update(ran_optimization=1, converged=bool(conv), n_query=len(stack), summary=sm, map_size=len(self.map),
+                    n_plane_factors=int((fac["type"] == 2).sum()), key=np.concatenate([qk, tk]))
+        return x, info

@@ -94,6 +94,23 @@ def test_voxelgrid_bit_exact(ctx, oracle_mod, cfg_full, leaf):
     assert np.array_equal(ctx.voxelgrid(one, leaf), one)
 
 
+@pytest.mark.parametrize("n,leaf", [(16385, 0.4), (40000, 0.8), (65536, 0.2), (150000, 0.4)])
+def test_voxelgrid_large_clouds_bit_exact(ctx, oracle_mod, ilsm, cfg_full, n, leaf):
+    """More than 16384 points (mapOptimization filters ground + less-flat clouds of ~40k points, mapOptimization.cpp:
+    368-370): the tiled multi-block sort path gives the same voxels, order and float centroids as the oracle."""
+    rng = np.random.default_rng(n)
+    base = cfg_full["map_surf"]
+    pts = np.zeros((n, 4), np.float32)
+    pick = rng.integers(0, len(base), n)
+    pts[:, :3] = base[pick, :3] + rng.normal(0, 0.05, (n, 3)).astype(np.float32)
+    pts[:, 3] = rng.uniform(0, 64, n).astype(np.float32)
+    pts[5, 0] = np.nan  # PCL skips non-finite points
+    got = ctx.voxelgrid(pts, leaf)
+    want = oracle_mod.voxelgrid(pts, leaf)
+    assert got.shape == want.shape and len(got) > 1000
+    assert np.array_equal(got, want)
+
+
 def test_frame_to_pose_pipeline_matches_oracle(ctx, oracle_mod, ilsm, cfg_full):
     """Raw frame -> features -> stacks (0.4 / 0.8 VoxelGrid, laserMapping.cpp:608-616) -> registration, GPU vs oracle."""
     c = cfg_full
