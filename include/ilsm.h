@@ -268,6 +268,10 @@ typedef struct ilsm_slam_stats {
  * cube_capacity as in ilsm_cubemap_create. */
 ILSM_API int ilsm_slam_create(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
                               ilsm_slam** out);
+/* The same front end and odometry with mapOptimization (ilsm_mapopt) as the mapping stage -- the node spot.launch
+ * starts.  In ilsm_slam_stats the mapping summary is pass[0]; cubemap.n_map_surf = ground-map size,
+ * cubemap.n_stack_surf = query points after VoxelGrid(0.8), cubemap.n_valid = 1 when the solve CONVERGED. */
+ILSM_API int ilsm_slam_create_mapopt(ilsm_ctx* ctx, float voxel_leaf, float downsample_size, float min_range, ilsm_slam** out);
 ILSM_API void ilsm_slam_destroy(ilsm_slam* slam);
 /* The cube map owned by the pipeline (for ilsm_cubemap_cube / ilsm_cubemap_insert_world). */
 ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam);

@@ -141,6 +141,7 @@ def load_library(path: str | None = None):
                                      C.POINTER(CubeMapStats)]),
         "ilsm_cubemap_cube": (i32, [vp, i32, i32, vp, i32, C.POINTER(i32)]),
         "ilsm_slam_create": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
+        "ilsm_slam_create_mapopt": (i32, [vp, f32, f32, f32, C.POINTER(vp)]),
         "ilsm_slam_destroy": (None, [vp]),
         "ilsm_slam_cubemap": (vp, [vp]),
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
@@ -576,11 +577,16 @@ class Slam:
     the GPU.  frame() returns (q_odom, t_odom, q_map, t_map, stats)."""
 
     def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.8, min_range: float = 0.3,
-                 cube_capacity: int = 0):
+                 cube_capacity: int = 0, mapping: str = "laserMapping", voxel_leaf: float = 0.8, downsample_size: float = 0.4):
         self._ctx = ctx
         self._lib = ctx._lib
         h = C.c_void_p()
-        _check(self._lib.ilsm_slam_create(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
+        if mapping == "laserMapping":
+            _check(self._lib.ilsm_slam_create(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
+        elif mapping == "mapOptimization":
+            _check(self._lib.ilsm_slam_create_mapopt(ctx._h, voxel_leaf, downsample_size, min_range, C.byref(h)))
+        else:
+            raise ValueError("mapping must be 'laserMapping' or 'mapOptimization'")
         self._h = h
 
     def close(self):

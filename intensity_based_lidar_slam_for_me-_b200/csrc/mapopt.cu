@@ -142,17 +142,15 @@ ILSM_API int ilsm_mapopt_map_points(ilsm_mapopt* mo, float* out_xyzi, int capaci
   return ILSM_OK;
 }
 
-ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, int stride_bytes, const float* plane_xyz, int n_plane,
-                               int plane_stride_bytes, const double q_wodom[4], const double t_wodom[3], double q_w[4],
-                               double t_w[3], const ilsm_ground_opts* gopts, ilsm_mapopt_stats* stats) {
-  if (!mo || !q_wodom || !t_wodom || !q_w || !t_w || (n > 0 && !frame_xyz) || (n_plane > 0 && !plane_xyz))
-    return fail(ILSM_ERR_INVALID_ARG, "mapopt_frame: null argument");
-  if (n < 0 || n_plane < 0 || stride_bytes < 12 || stride_bytes % 4 || plane_stride_bytes < 12 || plane_stride_bytes % 4)
-    return fail(ILSM_ERR_INVALID_ARG, "mapopt_frame: bad n/stride");
+}  // extern "C"
+
+namespace ilsm {
+// one callback iteration; frame / plane clouds on the host (from_host) or already on the device.  Caller holds the mutex.
+int mapopt_frame_core(ilsm_mapopt* mo, const float* frame_xyz, int n, int stride_bytes, const float* plane_xyz, int n_plane,
+                      int plane_stride_bytes, bool from_host, const double q_wodom[4], const double t_wodom[3], double q_w[4],
+                      double t_w[3], const ilsm_ground_opts* gopts, ilsm_mapopt_stats* stats) {
   MapOptH& m = mo->m;
   Ctx& c = *m.ctx;
-  std::lock_guard<std::mutex> lk(c.mu);
-  ILSM_CUDA(cudaSetDevice(c.device));
   if (stats) memset(stats, 0, sizeof(*stats));
   ilsm_ground_opts go;
   if (gopts) go = *gopts; else ilsm_ground_opts_default(&go);
@@ -160,7 +158,7 @@ ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, i
   int rc, n_ground = 0;
   ilsm_ground_info ginfo;
   float coeff[4];
-  if ((rc = ground_extract_core(m.ground, frame_xyz, true, n, stride_bytes, go, &n_ground, coeff, &ginfo))) return rc;
+  if ((rc = ground_extract_core(m.ground, frame_xyz, from_host, n, stride_bytes, go, &n_ground, coeff, &ginfo))) return rc;
   // GroundPointOut += pc_plane
   const int n_all = n_ground + n_plane;
   const size_t pbytes = (size_t)n_plane * plane_stride_bytes;
@@ -171,9 +169,13 @@ ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, i
   if (n_ground > 0)
     ILSM_CUDA(cudaMemcpyAsync(m.merged.p, ground_points_dev(m.ground), (size_t)n_ground * 16, cudaMemcpyDeviceToDevice, s));
   if (n_plane > 0) {
-    ILSM_CUDA(cudaMemcpyAsync(m.plane_raw.p, plane_xyz, pbytes, cudaMemcpyHostToDevice, s));
-    ILSM_CUDA(launch_pdl(mo_pack_kernel, dim3((n_plane + 255) / 256), dim3(256), 0, s, (const float*)m.plane_raw.p, n_plane,
-                         plane_stride_bytes / 4, m.merged.p + n_ground));
+    const float* d_plane = plane_xyz;
+    if (from_host) {
+      ILSM_CUDA(cudaMemcpyAsync(m.plane_raw.p, plane_xyz, pbytes, cudaMemcpyHostToDevice, s));
+      d_plane = m.plane_raw.p;
+    }
+    ILSM_CUDA(launch_pdl(mo_pack_kernel, dim3((n_plane + 255) / 256), dim3(256), 0, s, d_plane, n_plane, plane_stride_bytes / 4,
+                         m.merged.p + n_ground));
     count_launches(1);
   }
   // transformAssociateToMap (mapOptimization.cpp:730-735)
@@ -271,6 +273,23 @@ ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, i
     for (int i = 0; i < 3; ++i) stats->t_key[i] = tk[i];
   }
   return ILSM_OK;
+}
+}  // namespace ilsm
+
+extern "C" {
+
+ILSM_API int ilsm_mapopt_frame(ilsm_mapopt* mo, const float* frame_xyz, int n, int stride_bytes, const float* plane_xyz, int n_plane,
+                               int plane_stride_bytes, const double q_wodom[4], const double t_wodom[3], double q_w[4],
+                               double t_w[3], const ilsm_ground_opts* gopts, ilsm_mapopt_stats* stats) {
+  if (!mo || !q_wodom || !t_wodom || !q_w || !t_w || (n > 0 && !frame_xyz) || (n_plane > 0 && !plane_xyz))
+    return fail(ILSM_ERR_INVALID_ARG, "mapopt_frame: null argument");
+  if (n < 0 || n_plane < 0 || stride_bytes < 12 || stride_bytes % 4 || plane_stride_bytes < 12 || plane_stride_bytes % 4)
+    return fail(ILSM_ERR_INVALID_ARG, "mapopt_frame: bad n/stride");
+  Ctx& c = *mo->m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return mapopt_frame_core(mo, frame_xyz, n, stride_bytes, plane_xyz, n_plane, plane_stride_bytes, true, q_wodom, t_wodom, q_w, t_w,
+                           gopts, stats);
 }
 
 }  // extern "C"

@@ -13,7 +13,13 @@
 
 #include "ilsm_cubemap.hpp"
 
+struct ilsm_mapopt;
+
 namespace ilsm {
+
+int mapopt_frame_core(ilsm_mapopt* mo, const float* frame_xyz, int n, int stride_bytes, const float* plane_xyz, int n_plane,
+                      int plane_stride_bytes, bool from_host, const double q_wodom[4], const double t_wodom[3], double q_w[4],
+                      double t_w[3], const ilsm_ground_opts* gopts, ilsm_mapopt_stats* stats);  // mapopt.cu
 
 // voxel edge of the "last frame" search structures: the odometry gate is 5 m (DISTANCE_SQ_THRESHOLD 25,
 // laserOdometry.cpp:31), the clouds are sparse (a few thousand points)
@@ -21,7 +27,8 @@ constexpr float kOdomCell = 1.0f;
 
 struct SlamH {
   Ctx* ctx = nullptr;
-  ilsm_cubemap* cube = nullptr;
+  ilsm_cubemap* cube = nullptr;   // mapping = laserMapping (rolling cube map)
+  ilsm_mapopt* mapopt = nullptr;  // mapping = mapOptimization (ground map), the node spot.launch starts
   Map last_corner, last_surf;  // kdtreeCornerLast / kdtreeSurfLast (laserOdometry.cpp:807-808)
   DevBuf<float4> sharp, flat, lsharp;
   bool inited = false;        // systemInited (laserOdometry.cpp:384)
@@ -42,22 +49,45 @@ struct ilsm_slam {
 
 extern "C" {
 
-ILSM_API int ilsm_slam_create(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
-                              ilsm_slam** out) {
+static int slam_create_common(ilsm_ctx* ctx, float min_range, ilsm_slam** out, ilsm_slam** h_out) {
   if (!ctx || !out) return fail(ILSM_ERR_INVALID_ARG, "slam_create: null argument");
   ilsm_slam* h = new (std::nothrow) ilsm_slam();
   if (!h) return fail(ILSM_ERR_OUT_OF_MEMORY, "host allocation failed");
   h->s.ctx = &ctx->c;
   h->s.min_range = min_range > 0.f ? min_range : 0.3f;
-  int rc = ilsm_cubemap_create(ctx, line_res, plane_res, cube_capacity, &h->s.cube);
-  if (rc == ILSM_OK) {
+  int rc;
+  {
     std::lock_guard<std::mutex> lk(ctx->c.mu);
     cudaSetDevice(ctx->c.device);
     if (!(rc = h->s.last_corner.init(&ctx->c))) rc = h->s.last_surf.init(&ctx->c);
   }
   if (rc) {
-    if (h->s.cube) ilsm_cubemap_destroy(h->s.cube);
     delete h;
+    return rc;
+  }
+  *h_out = h;
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_slam_create(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                              ilsm_slam** out) {
+  ilsm_slam* h = nullptr;
+  int rc = slam_create_common(ctx, min_range, out, &h);
+  if (rc) return rc;
+  if ((rc = ilsm_cubemap_create(ctx, line_res, plane_res, cube_capacity, &h->s.cube))) {
+    ilsm_slam_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_slam_create_mapopt(ilsm_ctx* ctx, float voxel_leaf, float downsample_size, float min_range, ilsm_slam** out) {
+  ilsm_slam* h = nullptr;
+  int rc = slam_create_common(ctx, min_range, out, &h);
+  if (rc) return rc;
+  if ((rc = ilsm_mapopt_create(ctx, voxel_leaf, downsample_size, &h->s.mapopt))) {
+    ilsm_slam_destroy(h);
     return rc;
   }
   *out = h;
@@ -74,11 +104,13 @@ ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
     s.last_corner.release(), s.last_surf.release();
     s.sharp.release(), s.flat.release(), s.lsharp.release();
   }
-  ilsm_cubemap_destroy(s.cube);
+  if (s.cube) ilsm_cubemap_destroy(s.cube);
+  if (s.mapopt) ilsm_mapopt_destroy(s.mapopt);
   delete slam;
 }
 
 ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam) { return slam ? slam->s.cube : nullptr; }
+ILSM_API ilsm_mapopt* ilsm_slam_mapopt(ilsm_slam* slam) { return slam ? slam->s.mapopt : nullptr; }
 
 ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom[4],
                              double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
@@ -116,20 +148,23 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
   // ---- the mapping stacks (VoxelGrid of the less-sharp / less-flat clouds, laserMapping.cpp:608-616) depend only on the
   // front end: they run on the side stream while the odometry solves on the main one
   if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
-  CubeMapH& cm = s.cube->m;
-  if ((rc = cm.stack_c.reserve(n_lsharp + 4)) || (rc = cm.stack_s.reserve(n_lflat + 4))) return rc;
-  ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
-  ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
-  ILSM_CUDA(cudaMemsetAsync(cm.stack_n.p, 0, 4 * sizeof(int), c.aux));
-  if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, cm.line_res, cm.stack_c.p,
-                                 reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
-                                 cm.stack_n.p, c.aux)))
-    return rc;
-  ILSM_CUDA(cudaEventRecord(c.ev_join, c.aux));
+  CubeMapH* cmp = s.cube ? &s.cube->m : nullptr;
+  if (cmp) {
+    CubeMapH& cm = *cmp;
+    if ((rc = cm.stack_c.reserve(n_lsharp + 4)) || (rc = cm.stack_s.reserve(n_lflat + 4))) return rc;
+    ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
+    ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+    ILSM_CUDA(cudaMemsetAsync(cm.stack_n.p, 0, 4 * sizeof(int), c.aux));
+    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, cm.line_res, cm.stack_c.p,
+                                   reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
+                                   cm.stack_n.p, c.aux)))
+      return rc;
+    ILSM_CUDA(cudaEventRecord(c.ev_join, c.aux));
+  }
   // ---- laserOdometry
   // the previous frame's deferred map insertion (side stream) reads the mapped pose from the LM state the odometry is
   // about to overwrite: order the main stream after it (long finished by now -- it overlapped this frame's front end)
-  if (cm.tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.stream, cm.ev_tail, 0));
+  if (cmp && cmp->tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.stream, cmp->ev_tail, 0));
   if (!s.inited) {
     s.inited = true;
   } else {
@@ -168,13 +203,27 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
   if ((rc = s.last_corner.build_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, 16, kOdomCell)) ||
       (rc = s.last_surf.build_dev(reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
     return rc;
-  // ---- laserMapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
-  ILSM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
-  ilsm_reg_opts mo;
-  ilsm_reg_opts_default(&mo);
-  rc = cubemap_frame_core(s.cube->m, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
-                          reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
-                          stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true);
+  // ---- mapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
+  if (cmp) {  // laserMapping: rolling cube map
+    ILSM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
+    ilsm_reg_opts mo;
+    ilsm_reg_opts_default(&mo);
+    rc = cubemap_frame_core(*cmp, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
+                            reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
+                            stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true);
+  } else {    // mapOptimization: ground extraction from the frame already on the device + the less-flat cloud
+    ilsm_mapopt_stats ms;
+    rc = mapopt_frame_core(s.mapopt, c.fe.raw.p, n, stride_bytes, reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, false,
+                           q_odom, t_odom, q_map, t_map, nullptr, &ms);
+    if (!rc && stats) {
+      stats->mapping.passes = ms.ran_optimization;
+      stats->mapping.pass[0] = ms.solve;
+      stats->cubemap.ran_optimization = ms.ran_optimization;
+      stats->cubemap.n_map_surf = ms.map_size;
+      stats->cubemap.n_stack_surf = ms.n_query;
+      stats->cubemap.n_valid = ms.converged;
+    }
+  }
   if (rc) return rc;
   s.frames++;
   return ILSM_OK;

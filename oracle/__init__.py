@@ -414,8 +414,9 @@ class Slam:
     use_aloam), t_w_curr += q_w_curr * t_last_curr, q_w_curr *= q_last_curr (:716-717), last clouds <- less-sharp /
     less-flat (:793-808), then one process() iteration of laserMapping with the odometry pose."""
 
-    def __init__(self, line_res=0.4, plane_res=0.8, min_range=0.3):
-        self.cube = CubeMap(line_res, plane_res)
+    def __init__(self, line_res=0.4, plane_res=0.8, min_range=0.3, mapping="laserMapping"):
+        self.cube = CubeMap(line_res, plane_res) if mapping == "laserMapping" else None
+        self.mapopt = None if mapping == "laserMapping" else MapOptimization()
         self.min_range = min_range
         self.inited = False
         self.para = np.array([0, 0, 0, 1, 0, 0, 0.0])
@@ -438,8 +439,11 @@ class Slam:
             self.q_w_curr = _qmul(self.q_w_curr, self.para[:4])
         self.last_corner, self.last_surf = lsharp.copy(), lflat.copy()
         qt_odom = np.concatenate([self.q_w_curr, self.t_w_curr])
-        qt_map, msums, st = self.cube.frame(lsharp, lflat, qt_odom)
-        return qt_odom, qt_map, dict(features=f, odometry=odo, mapping=msums, cubemap=st)
+        if self.cube is not None:
+            qt_map, msums, st = self.cube.frame(lsharp, lflat, qt_odom)
+            return qt_odom, qt_map, dict(features=f, odometry=odo, mapping=msums, cubemap=st)
+        qt_map, info = self.mapopt.frame(cloud, lflat, self.q_w_curr, self.t_w_curr)
+        return qt_odom, qt_map, dict(features=f, odometry=odo, mapopt=info)
 
 
 # ------------------------------------------------------------------------------------------------

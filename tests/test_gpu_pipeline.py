@@ -87,3 +87,28 @@ def test_fork_mode_skips_odometry_optimisation(ctx, oracle_mod, ilsm):
         assert np.linalg.norm(gtm - wmap[4:]) < 1e-4 and S.quat_angle(gqm, wmap[:4]) < 1e-4
     assert st.ran_odometry == 1
     slam.close()
+
+
+def test_launched_pipeline_with_mapoptimization_matches_oracle(ctx, oracle_mod, ilsm):
+    """spot.launch starts scanRegistration + laserOdometry + the mapOptimization node: the same loop with the ground-map
+    mapping stage (ground extraction from the frame already on the device), over open ground."""
+    S = ilsm.synth
+    scene = S.Scene(S.SEED_MAP)
+    q0, t0 = S.default_pose()
+    slam = ilsm.Slam(ctx, min_range=0.3, mapping="mapOptimization")
+    oslam = oracle_mod.Slam(min_range=0.3, mapping="mapOptimization")
+    for k in range(6):
+        q = S.quat_mul(q0, S.quat_from_rotvec([0, 0, 0.02 * k]))
+        t = t0 + np.array([0.25 * k, 0.05 * k, 0.0])
+        cloud, _ = S.make_frame(scene, q, t, seed=700 + k)
+        gqo, gto, gqm, gtm, st = slam.frame(cloud)
+        wodom, wmap, info = oslam.frame(cloud)
+        assert np.linalg.norm(gto - wodom[4:]) < 1e-4 and S.quat_angle(gqo, wodom[:4]) < 1e-4, k
+        assert np.linalg.norm(gtm - wmap[4:]) < 1e-4 and S.quat_angle(gqm, wmap[:4]) < 1e-4, k
+        mi = info["mapopt"]
+        assert st.cubemap.ran_optimization == mi["ran_optimization"] == (1 if k else 0)
+        assert st.cubemap.n_map_surf == mi["map_size"]
+        if k:
+            assert st.cubemap.n_stack_surf == mi["n_query"] and bool(st.cubemap.n_valid) == mi["converged"]
+            assert st.mapping.pass_[0].num_plane_factors == mi["n_plane_factors"]
+    slam.close()

@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--oracle-frames", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--mapping", default="laserMapping", choices=["laserMapping", "mapOptimization"],
+                    help="mapping stage: the rolling cube map of laserMapping.cpp or the ground map of mapOptimization.cpp "
+                         "(the node spot.launch starts)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -69,7 +72,7 @@ def main():
     ctx = ilsm.Context(local)
 
     def run(n, keep=False, slam=None):
-        slam = slam or ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+        slam = slam or ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping)
         out, times = [], []
         for k in range(n):
             t0 = time.perf_counter()
@@ -80,7 +83,7 @@ def main():
         return out, times, slam
 
     run(min(args.warmup, F))[2].close()
-    slam_timed = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)  # the 2 x 4851 x 8192-point cube slabs are allocated outside the timed region
+    slam_timed = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping)  # the 2 x 4851 x 8192-point cube slabs are allocated outside the timed region
     ctx.sync()
     if dist is not None:
         dist.barrier()
@@ -105,7 +108,7 @@ def main():
             tr = R0.T @ (poses[k][1] - t0p)
             err.append(np.linalg.norm(est[k][3] - tr))
         line = {"metric": "full odometry+mapping loop, frames/s (synthetic OS0-64 corridor)", "value": world * F / wall_max,
-                "unit": "frames/s", "n_gpus": world, "frames_per_sequence": F, "ms_per_frame": 1e3 * wall_max / F,
+                "unit": "frames/s", "n_gpus": world, "mapping": args.mapping, "frames_per_sequence": F, "ms_per_frame": 1e3 * wall_max / F,
                 "ms_per_frame_median": 1e3 * float(np.median(times)), "scaling": "weak",
                 "h2d_bytes_per_frame": int(clouds[0].nbytes), "d2h_bytes_per_frame": 2 * 56 + 400,
                 "gpu_launches_per_frame": launches / F, "ate_rmse_m": float(np.sqrt(np.mean(np.square(err)))),
@@ -115,7 +118,7 @@ def main():
         no = min(args.oracle_frames, F)
         if no > 0 and world == 1:
             import oracle
-            osl = oracle.Slam(0.4, 0.8, 0.3)
+            osl = oracle.Slam(0.4, 0.8, 0.3, mapping=args.mapping)
             dts, drs = [], []
             t1 = time.perf_counter()
             ores = [osl.frame(clouds[k]) for k in range(no)]
