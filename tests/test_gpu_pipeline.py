@@ -112,3 +112,30 @@ def test_launched_pipeline_with_mapoptimization_matches_oracle(ctx, oracle_mod, 
             assert st.cubemap.n_stack_surf == mi["n_query"] and bool(st.cubemap.n_valid) == mi["converged"]
             assert st.mapping.pass_[0].num_plane_factors == mi["n_plane_factors"]
     slam.close()
+
+
+@pytest.mark.parametrize("mapping", ["laserMapping", "mapOptimization"])
+def test_pipeline_survives_degenerate_frames(ctx, ilsm, mapping):
+    """No-return frames (all zeros), NaN points and an empty cloud must not fault: the reference's guards (feature
+    counts, map-size guard of laserMapping.cpp:624, RANSAC with < 3 band points) all have device-side equivalents."""
+    S = ilsm.synth
+    scene = S.Scene(corridor=True, length=60.0)
+    slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096, mapping=mapping)
+    zeros = np.zeros((65536, 4), np.float32)
+    qo, to, qm, tm, st = slam.frame(zeros)                      # nothing but no-returns
+    assert st.n_cloud == 0 and np.all(np.isfinite(tm)) and np.all(np.isfinite(qm))
+    q = S.quat_from_rotvec([0, 0, 0.0])
+    good, _ = S.make_frame(scene, q, np.array([2.0, 0.0, 1.2]), seed=1)
+    qo, to, qm, tm, st = slam.frame(good)
+    assert st.n_cloud > 10000 and np.all(np.isfinite(tm))
+    bad = good.copy()
+    bad[::7, :3] = np.nan                                        # NaN returns sprinkled over the frame
+    qo, to, qm, tm, st = slam.frame(bad)
+    assert np.all(np.isfinite(tm)) and np.all(np.isfinite(qm)) and np.all(np.isfinite(to))
+    qo, to, qm, tm, st = slam.frame(zeros)                      # and an empty frame in the middle of a run
+    assert np.all(np.isfinite(tm))
+    qo, to, qm, tm, st = slam.frame(good)
+    assert np.all(np.isfinite(tm)) and st.n_cloud > 10000
+    qo, to, qm, tm, st = slam.frame(np.zeros((0, 4), np.float32))
+    assert st.n_cloud == 0
+    slam.close()
