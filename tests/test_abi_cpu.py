@@ -44,6 +44,42 @@ def test_struct_layouts_match_ctypes(ilsm):
     assert b.FACTOR_DTYPE.itemsize == 80
 
 
+def test_every_struct_layout_matches_the_c_header(ilsm, tmp_path):
+    """sizeof of every struct of include/ilsm.h as gcc lays it out == the ctypes / numpy mirror in binding.py."""
+    import subprocess
+    from ilsm_b200 import binding as b
+    pairs = {"ilsm_reg_opts": b.RegOpts, "ilsm_solve_summary": b.SolveSummary, "ilsm_reg_report": b.RegReport,
+             "ilsm_feature_counts": b.FeatureCounts, "ilsm_features": b.Features, "ilsm_cubemap_stats": b.CubeMapStats,
+             "ilsm_slam_stats": b.SlamStats, "ilsm_ground_opts": b.GroundOpts, "ilsm_ground_info": b.GroundInfo,
+             "ilsm_mapopt_stats": b.MapOptStats}
+    names = list(pairs) + ["ilsm_dmatch", "ilsm_factor"]
+    src = tmp_path / "s.c"
+    src.write_text('#include <stdio.h>\n#include "ilsm.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}\n")
+    exe = tmp_path / "s"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    got = dict(zip(names, sizes))
+    for n, t in pairs.items():
+        assert got[n] == ctypes.sizeof(t), (n, got[n], ctypes.sizeof(t))
+    assert got["ilsm_dmatch"] == b.DMATCH_DTYPE.itemsize == 16 and got["ilsm_factor"] == b.FACTOR_DTYPE.itemsize
+
+
+def test_null_handles_are_rejected_not_dereferenced(ilsm):
+    """Argument validation runs before any CUDA call: usable without a GPU, negative status + error text."""
+    lib = ilsm.load_library()
+    n = ctypes.c_int(0)
+    assert lib.ilsm_map_build(None, None, 0, 16, 0.0) < 0
+    assert lib.ilsm_knn(None, None, 0, 16, 5, 0.0, None, None) < 0
+    assert lib.ilsm_register(None, None, None, None, 0, None, 0, 16, None, None, None, None) < 0
+    assert lib.ilsm_voxelgrid(None, None, 0, 16, 0.4, None, ctypes.byref(n)) < 0
+    assert lib.ilsm_slam_frame(None, None, 0, 16, 1, None, None, None, None, None) < 0
+    assert lib.ilsm_mapopt_frame(None, None, 0, 16, None, 0, 16, None, None, None, None, None, None) < 0
+    assert lib.ilsm_orb_match(None, None, 0, None, 0, 32, 1, 0.3, None, ctypes.byref(n), None, ctypes.byref(n)) < 0
+    assert lib.ilsm_ground_extract(None, None, 0, 16, None, None, 0, ctypes.byref(n), None, None) < 0
+    assert b"null" in lib.ilsm_last_error() or b"bad" in lib.ilsm_last_error()
+
+
 def test_no_cpu_fallback(ilsm):
     """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
     import torch
