@@ -168,8 +168,9 @@ def config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts):
         ctx.associate_dev(mc, ms, d_c.data_ptr(), Qb // 8, d_s.data_ptr(), Qb - Qb // 8, 16, pose_t.data_ptr(), opts)
         ctx.sync()
     t = timed(lambda: ctx.eval_normal_eq_dev(pose_t.data_ptr(), out32.data_ptr()))
-    byt = Qb * 84
-    out["jtj"] = {"factors": Qb, "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
+    # every factor slot read once: type 4 B + point 16 B + (normal | point_a) 32 B, + point_b 32 B for the corner slots
+    byt = Qb * 52 + (Qb // 8) * 32
+    out["jtj"] = {"factors": Qb, "corner_slots": Qb // 8, "kernel": "normal_eq_bulk_kernel", "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
                   "achieved_GBs": byt / t / 1e6, "frac": byt / t / 1e6 / peak, "bound": "hbm"}
     gm.close(), mc.close(), ms.close()
     return out

@@ -195,6 +195,7 @@ struct Ctx {
   FeBufs fe;
   const int* d_stack_counts = nullptr;  // when set, associate/solve read {nc, ns} from the device (cube-map path)
   size_t partial_blocks = 0;
+  bool bulk_attr_set = false;  // normal_eq_bulk_kernel's dynamic shared-memory opt-in done on this device
 
   int init(int dev);
   void release();

@@ -187,7 +187,7 @@ ILSM_API int ilsm_align_points(ilsm_ctx* ctx, const float* src_xyz, const float*
   int rc;
   FactorBufs& f = c.fac;
   const size_t bytes = (size_t)n * stride_bytes;
-  if ((rc = f.type.reserve(n + 1)) || (rc = f.p.reserve(n + 1)) || (rc = f.a.reserve(n + 1)) || (rc = f.b.reserve(n + 1)) ||
+  if ((rc = f.type.reserve(n + 4)) || (rc = f.p.reserve(n + 1)) || (rc = f.a.reserve(n + 1)) || (rc = f.b.reserve(n + 1)) ||
       (rc = c.stack_raw.reserve(2 * (bytes / 4) + 16)))
     return rc;
   f.n = n, f.nc = n;

@@ -1011,6 +1011,155 @@ __global__ void __launch_bounds__(kEvalThreads, kEvalBlocksPerSm)
 }
 
 // ---------------------------------------------------------------------------------------------------
+// normal_eq_bulk_kernel: the same evaluation for LARGE factor sets (config 3: many frames' correspondences in one
+// launch), where the kernel is HBM-bound.  The register-prefetch kernel above keeps one record per thread in flight
+// (~32 KB per SM, 37 % of the copy peak).  Here one producer thread streams 384-factor tiles of the four SoA arrays
+// into a ring of shared-memory stages with bulk async copies (cp.async.bulk, the 1-D TMA path: UBLKCP) that complete
+// on an mbarrier; the 12 consumer warps wait for a stage, pull their factor into registers, release the stage (one
+// mbarrier arrive per warp) and evaluate.  Up to kBulkStages x 32 KB are in flight per SM, independent of the
+// consumers' register budget.  Tiles that lie entirely in the surf range (i >= nc) never fetch the `b` array
+// (plane factors do not use it).  Tile -> CTA assignment is static, sums are combined in a fixed order: deterministic.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBulkTile = 384;                  // factors per stage = consumer threads
+constexpr int kBulkThreads = kBulkTile + 32;    // + one producer warp
+constexpr int kBulkStages = 6;
+constexpr int kBulkStageBytes = kBulkTile * (4 + 16 + 32 + 32);
+constexpr size_t kBulkSmemBytes = (size_t)kBulkStages * kBulkStageBytes + 2 * kBulkStages * 8 + 128;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kBulkThreads, 1)
+    normal_eq_bulk_kernel(FactorView fv, int n, int nc, LmState* st, double* __restrict__ partials,
+                          double* __restrict__ eval_out) {
+  pdl_entry();
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ double red[kBulkTile / 32][kSumStride];
+  __shared__ int is_last;
+  // stage layout: a[T] double4 | b[T] double4 | p[T] float4 | type[T] int
+  const uint32_t smem0 = smem_u32(bulk_smem);
+  const uint32_t bar0 = smem0 + kBulkStages * kBulkStageBytes;  // full[kBulkStages], then empty[kBulkStages]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kBulkStages; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(bar0 + 8 * (kBulkStages + s), kBulkTile / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ntiles = (n + kBulkTile - 1) / kBulkTile;
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  double acc[kSumStride];
+#pragma unroll
+  for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
+
+  if (warp == kBulkTile / 32) {
+    // ---- producer: one thread keeps the ring full
+    if (lane == 0) {
+#pragma unroll 1
+      for (int k = 0; k < my_tiles; ++k) {
+        const int s = k % kBulkStages, use = k / kBulkStages;
+        if (use > 0) mbar_wait(bar0 + 8 * (kBulkStages + s), (use - 1) & 1);
+        const size_t base = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * kBulkTile;
+        const uint32_t cnt = (uint32_t)min((size_t)kBulkTile, (size_t)n - base);
+        const bool need_b = base < (size_t)nc;
+        const uint32_t ty_bytes = ((cnt * 4u) + 15u) & ~15u;  // the type array has >= 64 ints of slack behind n
+        const uint32_t full = bar0 + 8 * s, dst = smem0 + s * kBulkStageBytes;
+        mbar_expect_tx(full, cnt * 32u + (need_b ? cnt * 32u : 0u) + cnt * 16u + ty_bytes);
+        bulk_g2s(dst, fv.a + base, cnt * 32u, full);
+        if (need_b) bulk_g2s(dst + kBulkTile * 32, fv.b + base, cnt * 32u, full);
+        bulk_g2s(dst + kBulkTile * 64, fv.p + base, cnt * 16u, full);
+        bulk_g2s(dst + kBulkTile * 80, fv.type + base, ty_bytes, full);
+      }
+    }
+  } else {
+    // ---- consumers
+    const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
+    const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
+    const double huber_a = st->huber_a;
+#pragma unroll 1
+    for (int k = 0; k < my_tiles; ++k) {
+      const int s = k % kBulkStages, use = k / kBulkStages;
+      mbar_wait(bar0 + 8 * s, use & 1);
+      const unsigned char* stg = bulk_smem + (size_t)s * kBulkStageBytes;
+      const size_t i = (size_t)(blockIdx.x + (size_t)k * gridDim.x) * kBulkTile + tid;
+      int ty = 0;
+      float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);
+      double4 fa = make_double4(0, 0, 0, 0), fb = fa;
+      if (i < (size_t)n) {
+        ty = reinterpret_cast<const int*>(stg + kBulkTile * 80)[tid];
+        if (ty) {
+          pf = reinterpret_cast<const float4*>(stg + kBulkTile * 64)[tid];
+          fa = reinterpret_cast<const double4*>(stg)[tid];
+          if (ty == 1) fb = reinterpret_cast<const double4*>(stg + kBulkTile * 32)[tid];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (kBulkStages + s));  // the stage may be refilled while we evaluate
+      if (ty) eval_factor(ty, pf, fa, fb, q, t, huber_a, acc);
+    }
+  }
+  const double mine = warp_reduce_transpose(acc, lane);  // the producer warp contributes zeros
+  if (warp < kBulkTile / 32) red[warp][lane] = mine;
+  __syncthreads();
+  if (tid < kSumStride) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < kBulkTile / 32; ++w) v += red[w][tid];
+    partials[(size_t)blockIdx.x * kSumStride + tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    unsigned tk = atomicAdd(&st->ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < kSumStride) {  // <= 148 blocks: a fixed-order sum per column
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    unsigned b = 0;
+    for (; b + 3 < gridDim.x; b += 4) {
+      v0 += __ldcg(partials + (size_t)b * kSumStride + tid);
+      v1 += __ldcg(partials + (size_t)(b + 1) * kSumStride + tid);
+      v2 += __ldcg(partials + (size_t)(b + 2) * kSumStride + tid);
+      v3 += __ldcg(partials + (size_t)(b + 3) * kSumStride + tid);
+    }
+    for (; b < gridDim.x; ++b) v0 += __ldcg(partials + (size_t)b * kSumStride + tid);
+    eval_out[tid] = (v0 + v1) + (v2 + v3);
+  }
+  if (tid == 0) st->ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static FactorView factor_view(FactorBufs& f, bool want_knn) {
@@ -1028,7 +1177,7 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
                        const ilsm_reg_opts& o, bool want_knn) {
   const int n = nc + ns;
   int rc;
-  if ((rc = fac.type.reserve(n + 1)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
+  if ((rc = fac.type.reserve(n + 4)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
       (rc = fac.b.reserve(n + 1)))
     return rc;
   if (want_knn && ((rc = fac.knn_idx.reserve((size_t)n * 5 + 1)) || (rc = fac.knn_d2.reserve((size_t)n * 5 + 1))))
@@ -1057,7 +1206,7 @@ int Ctx::odom_associate_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, con
                             int stride_bytes) {
   const int n = nsh + nfl;
   int rc;
-  if ((rc = fac.type.reserve(n + 1)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
+  if ((rc = fac.type.reserve(n + 4)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
       (rc = fac.b.reserve(n + 1)))
     return rc;
   fac.n = n;
@@ -1108,6 +1257,22 @@ int Ctx::register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const flo
 
 // stand-alone evaluation (ilsm_eval_normal_eq): candidate pose must already be in lm->cq/ct, huber in lm->huber_a
 int eval_only_launch(Ctx* c, double* d_out) {
+  // bandwidth regime (at least one 384-factor tile per SM): the bulk-copy staged kernel, one persistent CTA per SM
+  const long long ntiles = ((long long)c->fac.n + kBulkTile - 1) / kBulkTile;
+  if (ntiles >= c->sm_count) {
+    if (!c->bulk_attr_set) {
+      ILSM_CUDA(cudaFuncSetAttribute(normal_eq_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBulkSmemBytes));
+      c->bulk_attr_set = true;
+    }
+    const int blocks = c->sm_count;
+    int rc;
+    if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
+    FactorView fv = factor_view(c->fac, false);
+    ILSM_CUDA(launch_pdl(normal_eq_bulk_kernel, dim3((unsigned)blocks), dim3(kBulkThreads), kBulkSmemBytes, c->stream, fv, c->fac.n,
+                         c->fac.nc, c->lm.p, c->partials.p, d_out));
+    count_launches(1);
+    return check_launch("normal_eq_bulk");
+  }
   long long blocks = ((long long)c->fac.n + kEvalThreads - 1) / kEvalThreads, cap = (long long)c->sm_count * kEvalBlocksPerSm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;

@@ -148,7 +148,7 @@ def main():
             emit({"case": "associate", "N": n_map, "Q": Q, "ms": t_as, "points_per_s": Q / t_as * 1e3,
                   "algorithmic_bytes": byt, "GBs": byt / t_as / 1e6, "frac": byt / t_as / 1e6 / peak})
             t_j, t_jmin = timed(lambda: ctx.eval_normal_eq_dev(d_pose.data_ptr(), d_out32.data_ptr()), args.reps)
-            byt = Q * 84 + ((Q + 255) // 256) * 256
+            byt = Q * 52 + ncq * 32 + ((Q + 383) // 384) * 256
             emit({"case": "jtj", "N": n_map, "Q": Q, "ms": t_j, "ms_min": t_jmin, "factors_per_s": Q / t_j * 1e3,
                   "algorithmic_bytes": byt, "GBs": byt / t_j / 1e6, "frac": byt / t_j / 1e6 / peak})
         if args.jtj_batch and N == Ns[-1]:
@@ -161,7 +161,7 @@ def main():
                     ctx.associate_dev(mc, ms, d_c.data_ptr(), ncq, d_s.data_ptr(), Qb - ncq, 16, d_pose.data_ptr(), opts)
                     ctx.sync()
                 t_j, t_jmin = timed(lambda: ctx.eval_normal_eq_dev(d_pose.data_ptr(), d_out32.data_ptr()), args.reps)
-                byt = Qb * 84 + ((Qb + 255) // 256) * 256
+                byt = Qb * 52 + ncq * 32 + 148 * 256  # slots read once (b only for corner slots) + per-CTA partial sums
                 emit({"case": "jtj_batched", "Q": Qb, "ms": t_j, "ms_min": t_jmin, "factors_per_s": Qb / t_j * 1e3,
                       "algorithmic_bytes": byt, "GBs": byt / t_j / 1e6, "frac": byt / t_j / 1e6 / peak})
         mc.close(), ms.close(), gmap.close()
