@@ -30,7 +30,7 @@ int check_launch(const char* where) {
   return ILSM_OK;
 }
 
-int eval_only_launch(Ctx* c, double* d_out);
+int eval_only_launch(Ctx* c, double* d_out, const double* d_pose7 = nullptr, double huber_a = 0.0);
 int factors_export(Ctx* c, ilsm_factor* d_out);
 int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out);
 
@@ -47,15 +47,6 @@ __global__ void set_pose_kernel(LmState* st, Pose7 p, int also_candidate, double
     for (int i = 0; i < 3; ++i) st->ct[i] = p.v[4 + i];
     st->huber_a = huber_a;
   }
-}
-
-// candidate pose <- device pose (ilsm_eval_normal_eq_dev)
-__global__ void set_pose_dev_kernel(LmState* st, const double* __restrict__ pose7, double huber_a) {
-  pdl_entry();
-  const int i = threadIdx.x;
-  if (i < 4) st->cq[i] = pose7[i];
-  if (i >= 4 && i < 7) st->ct[i - 4] = pose7[i];
-  if (i == 7) st->huber_a = huber_a;
 }
 
 __global__ void pose_io_kernel(LmState* st, double* pose7, ilsm_reg_report* report, int direction) {
@@ -794,9 +785,7 @@ ILSM_API int ilsm_eval_normal_eq_dev(ilsm_ctx* ctx, const double* d_pose7, doubl
   Ctx& c = ctx->c;
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
-  ILSM_CUDA(launch_pdl(set_pose_dev_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, huber_a));
-  count_launches(1);
-  return eval_only_launch(&c, d_out32);
+  return eval_only_launch(&c, d_out32, d_pose7, huber_a);  // the kernel reads the pose straight from d_pose7
 }
 
 ILSM_API int ilsm_solve_dev(ilsm_ctx* ctx, const double* d_pose7_in, int max_num_iterations, double huber_a) {

@@ -425,10 +425,10 @@ __device__ __forceinline__ void acc_row(double (&acc)[kSumStride], const double 
 
 // LidarEdgeFactor (hpp:243-293) / LidarPlaneNormFactor (hpp:199-240) at pose (q,t) with the closed-form tangent
 // Jacobians of EigenQuaternionParameterization and the HuberLoss corrector.
-__device__ __forceinline__ void eval_factor(int type, const float4 pf, const double4 fa, const double4 fb,
-                                            const double (&q)[4], const double (&t)[3], double huber_a,
-                                            double (&acc)[kSumStride]) {
-  D3 Rp = quat_rotate(q, d3((double)pf.x, (double)pf.y, (double)pf.z));
+// Rp = q * curr_point is passed in: the LM solver rotates with Eigen's _transformVector form (quat_rotate), the bulk
+// J^T J kernel with the rotation matrix of the (launch-constant) pose.
+__device__ __forceinline__ void eval_factor_rp(int type, const D3 Rp, const double4 fa, const double4 fb,
+                                               const double (&t)[3], double huber_a, double (&acc)[kSumStride]) {
   D3 lp = d3(Rp.x + t[0], Rp.y + t[1], Rp.z + t[2]);
   if (type == 1) {
     D3 u = d3(lp.x - fa.x, lp.y - fa.y, lp.z - fa.z), v = d3(lp.x - fb.x, lp.y - fb.y, lp.z - fb.z);
@@ -501,6 +501,12 @@ __device__ __forceinline__ void eval_factor(int type, const float4 pf, const dou
       acc_row(acc, jr, sc * rr[a]);
     }
   }
+}
+
+__device__ __forceinline__ void eval_factor(int type, const float4 pf, const double4 fa, const double4 fb,
+                                            const double (&q)[4], const double (&t)[3], double huber_a,
+                                            double (&acc)[kSumStride]) {
+  eval_factor_rp(type, quat_rotate(q, d3((double)pf.x, (double)pf.y, (double)pf.z)), fa, fb, t, huber_a, acc);
 }
 
 // Transposing warp reduction: 32 lanes x 32 values -> lane L returns the warp total of value L
@@ -931,16 +937,20 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
 constexpr int kEvalThreads = 384, kEvalBlocksPerSm = 1;
 
 __global__ void __launch_bounds__(kEvalThreads, kEvalBlocksPerSm)
-    normal_eq_kernel(FactorView fv, int n, LmState* st, double* __restrict__ partials, double* __restrict__ eval_out) {
+    normal_eq_kernel(FactorView fv, int n, LmState* st, const double* __restrict__ pose7, double huber_in,
+                     double* __restrict__ partials, double* __restrict__ eval_out) {
   pdl_entry();
   __shared__ double red[kEvalThreads / 32][kSumStride];
   __shared__ int is_last;
   double acc[kSumStride];
 #pragma unroll
   for (int i = 0; i < kSumStride; ++i) acc[i] = 0.0;
-  const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
-  const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
-  const double huber_a = st->huber_a;
+  // pose from the caller's device buffer when given, else the candidate pose of the LM state
+  const double* pq = pose7 ? pose7 : st->cq;
+  const double* pt = pose7 ? pose7 + 4 : st->ct;
+  const double q[4] = {pq[0], pq[1], pq[2], pq[3]};
+  const double t[3] = {pt[0], pt[1], pt[2]};
+  const double huber_a = pose7 ? huber_in : st->huber_a;
   // persistent grid-stride loop: the 32 running sums stay in registers across factors, so the reduction cost is paid
   // once per thread; the next factor's record is in flight while the current one is evaluated.  Only the bytes a
   // factor type needs are read: type 0 (gate / fit failed) 4 B, plane 52 B, edge 84 B.
@@ -1013,15 +1023,15 @@ __global__ void __launch_bounds__(kEvalThreads, kEvalBlocksPerSm)
 // ---------------------------------------------------------------------------------------------------
 // normal_eq_bulk_kernel: the same evaluation for LARGE factor sets (config 3: many frames' correspondences in one
 // launch), where the kernel is HBM-bound.  The register-prefetch kernel above keeps one record per thread in flight
-// (~32 KB per SM, 37 % of the copy peak).  Here one producer thread streams 384-factor tiles of the four SoA arrays
+// (~32 KB per SM, 37 % of the copy peak).  Here one producer thread streams 352-factor tiles of the four SoA arrays
 // into a ring of shared-memory stages with bulk async copies (cp.async.bulk, the 1-D TMA path: UBLKCP) that complete
-// on an mbarrier; the 12 consumer warps wait for a stage, pull their factor into registers, release the stage (one
-// mbarrier arrive per warp) and evaluate.  Up to kBulkStages x 32 KB are in flight per SM, independent of the
+// on an mbarrier; the 11 consumer warps wait for a stage, pull their factor into registers, release the stage (one
+// mbarrier arrive per warp) and evaluate.  Up to kBulkStages x 29 KB are in flight per SM, independent of the
 // consumers' register budget.  Tiles that lie entirely in the surf range (i >= nc) never fetch the `b` array
 // (plane factors do not use it).  Tile -> CTA assignment is static, sums are combined in a fixed order: deterministic.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kBulkTile = 384;                  // factors per stage = consumer threads
-constexpr int kBulkThreads = kBulkTile + 32;    // + one producer warp
+constexpr int kBulkTile = 352;                  // factors per stage = consumer threads (11 warps)
+constexpr int kBulkThreads = kBulkTile + 32;    // + one producer warp = 12 warps, 3 per SM sub-partition
 constexpr int kBulkStages = 6;
 constexpr int kBulkStageBytes = kBulkTile * (4 + 16 + 32 + 32);
 constexpr size_t kBulkSmemBytes = (size_t)kBulkStages * kBulkStageBytes + 2 * kBulkStages * 8 + 128;
@@ -1054,9 +1064,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// 12 warps and not 13: registers are allocated per SM sub-partition (4 x 16 K), so a 13th warp would cap the kernel at
+// 128 registers per thread (spills in the tile loop).
 __global__ void __launch_bounds__(kBulkThreads, 1)
-    normal_eq_bulk_kernel(FactorView fv, int n, int nc, LmState* st, double* __restrict__ partials,
-                          double* __restrict__ eval_out) {
+    normal_eq_bulk_kernel(FactorView fv, int n, int nc, LmState* st, const double* __restrict__ pose7, double huber_in,
+                          double* __restrict__ partials, double* __restrict__ eval_out) {
   pdl_entry();
   extern __shared__ __align__(128) unsigned char bulk_smem[];
   __shared__ double red[kBulkTile / 32][kSumStride];
@@ -1100,10 +1112,18 @@ __global__ void __launch_bounds__(kBulkThreads, 1)
       }
     }
   } else {
-    // ---- consumers
-    const double q[4] = {st->cq[0], st->cq[1], st->cq[2], st->cq[3]};
-    const double t[3] = {st->ct[0], st->ct[1], st->ct[2]};
-    const double huber_a = st->huber_a;
+    // ---- consumers (pose from the caller's device buffer when given, else the candidate pose of the LM state)
+    const double* pq = pose7 ? pose7 : st->cq;
+    const double* pt = pose7 ? pose7 + 4 : st->ct;
+    const double q[4] = {pq[0], pq[1], pq[2], pq[3]};
+    const double t[3] = {pt[0], pt[1], pt[2]};
+    const double huber_a = pose7 ? huber_in : st->huber_a;
+    // Eigen::Quaterniond::toRotationMatrix of the pose, once per thread (the pose is constant for the launch)
+    const double tx = 2.0 * q[0], ty2 = 2.0 * q[1], tz = 2.0 * q[2];
+    const double twx = tx * q[3], twy = ty2 * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty2 * q[0], txz = tz * q[0];
+    const double tyy = ty2 * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    const double R00 = 1.0 - (tyy + tzz), R01 = txy - twz, R02 = txz + twy, R10 = txy + twz, R11 = 1.0 - (txx + tzz),
+                 R12 = tyz - twx, R20 = txz - twy, R21 = tyz + twx, R22 = 1.0 - (txx + tyy);
 #pragma unroll 1
     for (int k = 0; k < my_tiles; ++k) {
       const int s = k % kBulkStages, use = k / kBulkStages;
@@ -1123,7 +1143,11 @@ __global__ void __launch_bounds__(kBulkThreads, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + 8 * (kBulkStages + s));  // the stage may be refilled while we evaluate
-      if (ty) eval_factor(ty, pf, fa, fb, q, t, huber_a, acc);
+      if (ty) {
+        const double px = (double)pf.x, py = (double)pf.y, pz = (double)pf.z;
+        eval_factor_rp(ty, d3(R00 * px + R01 * py + R02 * pz, R10 * px + R11 * py + R12 * pz, R20 * px + R21 * py + R22 * pz),
+                       fa, fb, t, huber_a, acc);
+      }
     }
   }
   const double mine = warp_reduce_transpose(acc, lane);  // the producer warp contributes zeros
@@ -1255,9 +1279,10 @@ int Ctx::register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const flo
   return ILSM_OK;
 }
 
-// stand-alone evaluation (ilsm_eval_normal_eq): candidate pose must already be in lm->cq/ct, huber in lm->huber_a
-int eval_only_launch(Ctx* c, double* d_out) {
-  // bandwidth regime (at least one 384-factor tile per SM): the bulk-copy staged kernel, one persistent CTA per SM
+// stand-alone evaluation (ilsm_eval_normal_eq): pose and Huber width from d_pose7 / huber_a, or (d_pose7 == nullptr)
+// the candidate pose lm->cq/ct and lm->huber_a
+int eval_only_launch(Ctx* c, double* d_out, const double* d_pose7, double huber_a) {
+  // bandwidth regime (at least one 352-factor tile per SM): the bulk-copy staged kernel, one persistent CTA per SM
   const long long ntiles = ((long long)c->fac.n + kBulkTile - 1) / kBulkTile;
   if (ntiles >= c->sm_count) {
     if (!c->bulk_attr_set) {
@@ -1269,7 +1294,7 @@ int eval_only_launch(Ctx* c, double* d_out) {
     if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
     FactorView fv = factor_view(c->fac, false);
     ILSM_CUDA(launch_pdl(normal_eq_bulk_kernel, dim3((unsigned)blocks), dim3(kBulkThreads), kBulkSmemBytes, c->stream, fv, c->fac.n,
-                         c->fac.nc, c->lm.p, c->partials.p, d_out));
+                         c->fac.nc, c->lm.p, d_pose7, huber_a, c->partials.p, d_out));
     count_launches(1);
     return check_launch("normal_eq_bulk");
   }
@@ -1280,7 +1305,7 @@ int eval_only_launch(Ctx* c, double* d_out) {
   if ((rc = c->partials.reserve((size_t)blocks * kSumStride + kSumStride))) return rc;
   FactorView fv = factor_view(c->fac, false);
   ILSM_CUDA(launch_pdl(normal_eq_kernel, dim3((unsigned)blocks), dim3(kEvalThreads), 0, c->stream, fv, c->fac.n, c->lm.p,
-                       c->partials.p, d_out));
+                       d_pose7, huber_a, c->partials.p, d_out));
   count_launches(1);
   return check_launch("normal_eq");
 }

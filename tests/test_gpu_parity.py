@@ -189,13 +189,13 @@ def test_eval_normal_eq_parity(ctx, oracle_mod, cfg_small):
 
 
 def test_eval_normal_eq_bulk_kernel_parity(ctx, oracle_mod, cfg_small):
-    """Above one 384-factor tile per SM the J^T J evaluation switches to the bulk-copy (TMA) staged kernel: same sums
+    """Above one 352-factor tile per SM the J^T J evaluation switches to the bulk-copy (TMA) staged kernel: same sums
     as the oracle (1e-5 relative stated, ~1e-12 observed), run-to-run identical, ragged last tile and a tile that
     straddles the corner / surf boundary included."""
     c = cfg_small
     mc, ms = _maps(ctx, c)
     rng = np.random.default_rng(5)
-    corner = c["corner"][rng.integers(0, len(c["corner"]), 9001)]          # 23.4 tiles: the 24th is mixed
+    corner = c["corner"][rng.integers(0, len(c["corner"]), 9001)]          # 25.6 tiles: the 26th is mixed
     surf = c["surf"][rng.integers(0, len(c["surf"]), 148 * 384 + 12345)]   # > one tile per SM, ragged tail
     qt = pose7(c["q0"], c["t0"])
     ctx.associate(mc, ms, corner, surf, c["q0"], c["t0"])

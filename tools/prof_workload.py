@@ -63,7 +63,7 @@ def main():
             d_mc2, d_ms2 = pad4(c2["map_corner"]), pad4(c2["map_surf"])
             mc2 = ctx.new_map().build_dev(d_mc2.data_ptr(), len(d_mc2), 16)
             ms2 = ctx.new_map().build_dev(d_ms2.data_ptr(), len(d_ms2), 16)
-            Qb = 1 << 20
+            Qb = 1 << 22
             sens = np.zeros((Qb, 4), np.float32)
             sens[:, :3] = c2["cloud"][np.arange(Qb) % 65536, :3]
             d_c2, d_s2 = torch.from_numpy(sens[:Qb // 8].copy()).to(dev), torch.from_numpy(sens[Qb // 8:].copy()).to(dev)

@@ -47,7 +47,8 @@ def main():
     dev = torch.device("cuda:0")
     ctx = ilsm.Context(0)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    from bench import L2Flush
+    flush = L2Flush(torch, dev)  # 256 MiB write + 256 MiB read: cold and clean L2 before every timed launch
     peak = peak_gbs()
     opts = ilsm.default_opts()
     out = open(args.out, "w") if args.out else None
