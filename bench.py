@@ -103,7 +103,7 @@ class L2Flush:
 
     def __init__(self, torch, dev):
         self.w = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        self.r = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
+        self.r = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # float: one reduce kernel, no widening copy
         self.sink = None
 
     def zero_(self):
@@ -188,6 +188,85 @@ def config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts):
     out["jtj"] = {"factors": Qb, "corner_slots": Qb // 8, "kernel": "normal_eq_bulk_kernel", "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
                   "achieved_GBs": byt / t / 1e6, "frac": byt / t / 1e6 / peak, "bound": "hbm"}
     gm.close(), mc.close(), ms.close()
+    return out
+
+
+def config2_point(ilsm, torch, ctx, frames, oracle_frames):
+    """BASELINE configs[1] on a bounded sample: the full per-frame loop (scanRegistration -> laserOdometry -> laserMapping)
+    on a synthetic OS0-64 corridor sequence through ilsm_slam_frame (H2D of the organised frame and D2H of both poses
+    inside the timed region), the chained CPU oracle on the first frames of the same sequence, and the largest pose
+    difference between the two.  tools/sequence_bench.py is the full-length version."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from sequence_bench import corridor_sequence
+    S = ilsm.synth
+    clouds, poses = corridor_sequence(S, frames, 0x5EED0100, length=0.2 * frames + 30.0)
+    pinned = [torch.from_numpy(c).pin_memory() for c in clouds]
+    views = [p.numpy() for p in pinned]
+    warm = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+    for k in range(5):
+        warm.frame(views[k])
+    warm.close()
+    slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+    ctx.sync()
+    l0 = ilsm.launch_count()
+    est, times = [], []
+    for k in range(frames):
+        t0 = time.perf_counter()
+        qo, to, qm, tm, st = slam.frame(views[k])
+        times.append(time.perf_counter() - t0)
+        est.append((qm, tm))
+    launches = ilsm.launch_count() - l0
+    slam.close()
+    wall = float(np.sum(times))
+    q0, t0p = poses[0]
+    R0 = S.quat_to_mat(q0)
+    err = [float(np.linalg.norm(est[k][1] - R0.T @ (poses[k][1] - t0p))) for k in range(frames)]
+    out = {"workload": f"configs[1] sample: {frames}-frame synthetic OS0-64 corridor, full odometry + mapping loop per frame",
+           "value": frames / wall, "unit": "frames/s", "ms_per_frame": 1e3 * wall / frames,
+           "ms_per_frame_median": 1e3 * float(np.median(times)), "h2d_bytes_per_frame": int(clouds[0].nbytes),
+           "d2h_bytes_per_frame": 2 * 56 + 400, "gpu_launches_per_frame": launches / frames,
+           "ate_rmse_m": float(np.sqrt(np.mean(np.square(err)))),
+           "timing": "host wall clock around the blocking ilsm_slam_frame calls"}
+    # config 4 on one GPU: independent sequences replayed concurrently (one context = one stream + one host thread each;
+    # the per-frame chain is latency-bound, so sequences interleave on the SMs).  ctypes releases the GIL in the C call.
+    n_seq = 4
+    ctxs = [ilsm.Context(ctx.device) for _ in range(n_seq)]
+    slams = [ilsm.Slam(c, 0.4, 0.8, 0.3, 8192) for c in ctxs]
+    for sl in slams:
+        for k in range(3):
+            sl.frame(views[k])
+    slams = [(sl.close(), ilsm.Slam(c, 0.4, 0.8, 0.3, 8192))[1] for sl, c in zip(slams, ctxs)]
+    last = [None] * n_seq
+
+    def replay(i):
+        for k in range(frames):
+            last[i] = slams[i].frame(views[k])[3]
+
+    threads = [threading.Thread(target=replay, args=(i,)) for i in range(n_seq)]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    wall_c = time.perf_counter() - t0
+    same = all(np.array_equal(last[i], est[-1][1]) for i in range(n_seq))
+    for sl, c in zip(slams, ctxs):
+        sl.close(), c.close()
+    out["concurrent_sequences"] = {"sequences": n_seq, "value": n_seq * frames / wall_c, "unit": "frames/s",
+                                   "identical_to_single_stream": bool(same),
+                                   "note": "configs[3] shape on one GPU: independent sequences, one context/stream/host thread each"}
+    no = min(oracle_frames, frames)
+    if no > 0:
+        import oracle
+        osl = oracle.Slam(0.4, 0.8, 0.3)
+        t1 = time.perf_counter()
+        ores = [osl.frame(clouds[k]) for k in range(no)]
+        cpu_wall = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": no / cpu_wall, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": f"first {no} frames of the same sequence through the chained CPU oracle"}
+        out["max_pose_diff_vs_oracle"] = {
+            "m": max(float(np.linalg.norm(est[k][1] - ores[k][1][4:])) for k in range(no)),
+            "rad": max(float(S.quat_angle(est[k][0], ores[k][1][:4])) for k in range(no)), "frames": no}
     return out
 
 
@@ -404,6 +483,9 @@ def run_gpu(args, rank, world, local_rank):
     sweep = None
     if rank == 0 and world == 1 and not args.no_sweep:
         sweep = config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts)
+    seq = None
+    if rank == 0 and world == 1 and not args.no_sequence:
+        seq = config2_point(ilsm, torch, ctx, args.sequence_frames, 0 if args.no_cpu else args.sequence_oracle_frames)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, reps_cpu, el = cpu_registrations_per_s(c, args.cpu_seconds, 5)
@@ -434,6 +516,8 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clocks,
             "pose_error_m": err_t,
         }
+        if seq is not None:
+            line["config2"] = seq
         if sweep is not None:
             line["config3"] = sweep
         if cpu is not None:
@@ -453,6 +537,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-3 (bandwidth regime) measurements")
+    ap.add_argument("--no-sequence", action="store_true", help="skip the config-2 (full loop on a corridor sequence) sample")
+    ap.add_argument("--sequence-frames", type=int, default=150)
+    ap.add_argument("--sequence-oracle-frames", type=int, default=25)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
