@@ -351,6 +351,36 @@ ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int 
 ILSM_API int ilsm_voxelgrid(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float leaf, float* out_xyzi,
                             int* n_out);
 
+/* --------------------------------------------------- sensor_msgs/PointCloud2 wire format -> packed points ---- */
+
+/* Where the fields the path reads sit inside one point of a sensor_msgs/PointCloud2 `data` blob (the message's
+ * `fields[]`: name, offset, datatype).  x, y, z must be FLOAT32 (PCL's field map accepts nothing else for PointXYZI);
+ * intensity may be FLOAT32 (what pcl::fromROSMsg maps) or, as an extension, UINT8 / UINT16 / UINT32 / FLOAT64
+ * (converted to float); off_intensity < 0 = no such field (intensity 0).  Big-endian blobs are rejected. */
+typedef struct ilsm_pc2_layout {
+  int32_t point_step;         /* bytes per point (>= 12) */
+  int32_t off_x, off_y, off_z;
+  int32_t off_intensity;
+  int32_t intensity_datatype; /* sensor_msgs/PointField: 2 UINT8, 4 UINT16, 6 UINT32, 7 FLOAT32, 8 FLOAT64 */
+  int32_t is_bigendian;
+  int32_t reserved;
+} ilsm_pc2_layout;
+
+/* Ouster OS0/OS1 driver layout: point_step 48, x 0, y 4, z 8, intensity FLOAT32 at 16. */
+ILSM_API void ilsm_pc2_layout_ouster(ilsm_pc2_layout* l);
+
+/* `data` (n_points * point_step bytes, row padding already skipped) -> n_points packed xyzi floats, on the device.
+ * The blob is uploaded as it is and unpacked by a kernel: the host-side repacking loop of pcl::fromROSMsg disappears.
+ * Replaces: pcl::fromROSMsg(*laserCloudMsg, laserCloudIn)  scanRegistration.cpp:235 ; image_handler.h_ouster:44,106 */
+ILSM_API int ilsm_pc2_unpack(ilsm_ctx* ctx, const uint8_t* data, int n_points, const ilsm_pc2_layout* layout, float* out_xyzi);
+ILSM_API int ilsm_pc2_unpack_dev(ilsm_ctx* ctx, const uint8_t* d_data, int n_points, const ilsm_pc2_layout* layout,
+                                 float* d_out_xyzi);
+
+/* ilsm_slam_frame fed with the raw message blob (same outputs). */
+ILSM_API int ilsm_slam_frame_pc2(ilsm_slam* slam, const uint8_t* data, int n_points, const ilsm_pc2_layout* layout, int use_aloam,
+                                 double q_odom_xyzw[4], double t_odom[3], double q_map_xyzw[4], double t_map[3],
+                                 ilsm_slam_stats* stats);
+
 /* ------------------------------------------------------- ground-plane extraction (feeds mapOptimization) ---- */
 typedef struct ilsm_ground ilsm_ground;
 

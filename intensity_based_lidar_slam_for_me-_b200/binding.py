@@ -65,6 +65,13 @@ class SlamStats(C.Structure):
                 ("cubemap", CubeMapStats)]
 
 
+class Pc2Layout(C.Structure):
+    """ilsm_pc2_layout: where x / y / z / intensity sit inside one point of a sensor_msgs/PointCloud2 blob."""
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("intensity_datatype", C.c_int32), ("is_bigendian", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class GroundOpts(C.Structure):
     _fields_ = [("z_min", C.c_double), ("z_max", C.c_double), ("distance_threshold", C.c_double), ("probability", C.c_double),
                 ("max_iterations", C.c_int32), ("seed", C.c_int32), ("band", C.c_double), ("max_angle_deg", C.c_double)]
@@ -85,6 +92,12 @@ DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<
 FACTOR_DTYPE = np.dtype([("type", "<i4"), ("src", "<i4"), ("p", "<f8", 3), ("a", "<f8", 3), ("b", "<f8", 3)])
 
 _lib = None
+
+
+def pc2_layout_ouster() -> Pc2Layout:
+    lay = Pc2Layout()
+    load_library().ilsm_pc2_layout_ouster(C.byref(lay))
+    return lay
 
 
 def load_library(path: str | None = None):
@@ -145,6 +158,10 @@ def load_library(path: str | None = None):
         "ilsm_slam_destroy": (None, [vp]),
         "ilsm_slam_cubemap": (vp, [vp]),
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
+        "ilsm_slam_frame_pc2": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
+        "ilsm_pc2_layout_ouster": (None, [C.POINTER(Pc2Layout)]),
+        "ilsm_pc2_unpack": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
+        "ilsm_pc2_unpack_dev": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
         "ilsm_ground_opts_default": (None, [C.POINTER(GroundOpts)]),
         "ilsm_ground_create": (i32, [vp, C.POINTER(vp)]),
         "ilsm_ground_destroy": (None, [vp]),
@@ -264,6 +281,15 @@ class Context:
         track = np.empty((H * W, 4), np.float32)
         _check(self._lib.ilsm_project(self._h, _ptr(a), H, W, stride, _ptr(rng), _ptr(inten), _ptr(track)))
         return rng, inten, track
+
+    # -- pcl::fromROSMsg (scanRegistration.cpp:235, image_handler.h_ouster:44,106) ------------------
+    def pc2_unpack(self, blob, layout: "Pc2Layout"):
+        """sensor_msgs/PointCloud2 `data` blob -> (n, 4) packed xyzi float32."""
+        b = np.ascontiguousarray(blob, np.uint8).reshape(-1)
+        n = b.size // layout.point_step if layout.point_step > 0 else 0
+        out = np.zeros((n, 4), np.float32)
+        _check(self._lib.ilsm_pc2_unpack(self._h, _ptr(b), n, C.byref(layout), _ptr(out)))
+        return out
 
     def project_dev(self, d_cloud_ptr, H, W, stride, d_range_ptr, d_inten_ptr, d_track_ptr):
         _check(self._lib.ilsm_project_dev(self._h, d_cloud_ptr, H, W, stride, d_range_ptr, d_inten_ptr, d_track_ptr))
@@ -615,6 +641,16 @@ class Slam:
         st = SlamStats()
         _check(self._lib.ilsm_slam_frame(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
                                          _ptr(tm), C.byref(st)))
+        return qo, to, qm, tm, st
+
+    def frame_pc2(self, blob, layout: "Pc2Layout", use_aloam: bool = True):
+        """One frame handed over as the sensor_msgs/PointCloud2 `data` blob (uint8, n_points * point_step bytes)."""
+        b = np.ascontiguousarray(blob, np.uint8).reshape(-1)
+        n = b.size // layout.point_step
+        qo, to, qm, tm = np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3)
+        st = SlamStats()
+        _check(self._lib.ilsm_slam_frame_pc2(self._h, _ptr(b), n, C.byref(layout), 1 if use_aloam else 0, _ptr(qo), _ptr(to),
+                                             _ptr(qm), _ptr(tm), C.byref(st)))
         return qo, to, qm, tm, st
 
 

@@ -99,7 +99,7 @@ void Ctx::release() {
   fe.src_index.release(), fe.label.release(), fe.sort_ind.release(), fe.ring_sharp.release(), fe.ring_lsharp.release();
   fe.ring_flat.release(), fe.sharp.release(), fe.lsharp.release(), fe.flat.release(), fe.counts.release();
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
-  fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
+  fe.pc2.release(), fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
   lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
   fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
   if (aux) cudaStreamSynchronize(aux), cudaStreamDestroy(aux);
@@ -544,6 +544,65 @@ ILSM_API int ilsm_project_dev(ilsm_ctx* ctx, const float* d_xyzi, int H, int W, 
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
   return c.project_dev(d_xyzi, H * W, stride_bytes, d_range_img, d_inten_img, d_cloud_track_xyzi);
+}
+
+ILSM_API void ilsm_pc2_layout_ouster(ilsm_pc2_layout* l) {
+  if (!l) return;
+  memset(l, 0, sizeof(*l));
+  l->point_step = 48, l->off_x = 0, l->off_y = 4, l->off_z = 8, l->off_intensity = 16, l->intensity_datatype = 7;
+}
+
+}  // extern "C"
+namespace ilsm {
+int check_pc2_layout(const ilsm_pc2_layout* l) {
+  if (!l) return fail(ILSM_ERR_INVALID_ARG, "pc2: null layout");
+  if (l->is_bigendian) return fail(ILSM_ERR_INVALID_ARG, "pc2: big-endian blobs are not supported");
+  const int ps = l->point_step;
+  auto in = [ps](int off, int size) { return off >= 0 && off + size <= ps; };
+  if (ps < 12 || !in(l->off_x, 4) || !in(l->off_y, 4) || !in(l->off_z, 4)) return fail(ILSM_ERR_INVALID_ARG, "pc2: bad point_step / xyz offsets");
+  if (l->off_intensity >= 0) {
+    int sz = 0;
+    switch (l->intensity_datatype) {
+      case 2: sz = 1; break;
+      case 4: sz = 2; break;
+      case 6: case 7: sz = 4; break;
+      case 8: sz = 8; break;
+      default: return fail(ILSM_ERR_INVALID_ARG, "pc2: unsupported intensity datatype");
+    }
+    if (!in(l->off_intensity, sz)) return fail(ILSM_ERR_INVALID_ARG, "pc2: bad intensity offset");
+  }
+  return ILSM_OK;
+}
+}  // namespace ilsm
+extern "C" {
+
+ILSM_API int ilsm_pc2_unpack_dev(ilsm_ctx* ctx, const uint8_t* d_data, int n_points, const ilsm_pc2_layout* layout, float* d_out_xyzi) {
+  if (!ctx || (n_points > 0 && (!d_data || !d_out_xyzi))) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack_dev: null argument");
+  if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack_dev: bad n_points");
+  int rc = check_pc2_layout(layout);
+  if (rc) return rc;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return c.pc2_unpack_dev(d_data, n_points, *layout, reinterpret_cast<float4*>(d_out_xyzi));
+}
+
+ILSM_API int ilsm_pc2_unpack(ilsm_ctx* ctx, const uint8_t* data, int n_points, const ilsm_pc2_layout* layout, float* out_xyzi) {
+  if (!ctx || (n_points > 0 && (!data || !out_xyzi))) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack: null argument");
+  if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack: bad n_points");
+  int rc = check_pc2_layout(layout);
+  if (rc) return rc;
+  if (n_points == 0) return ILSM_OK;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const size_t bytes = (size_t)n_points * layout->point_step;
+  if ((rc = c.fe.pc2.reserve(bytes + 16)) || (rc = c.fe.raw.reserve((size_t)n_points * 4 + 4))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(c.fe.pc2.p, data, bytes, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = c.pc2_unpack_dev(c.fe.pc2.p, n_points, *layout, reinterpret_cast<float4*>(c.fe.raw.p)))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(out_xyzi, c.fe.raw.p, (size_t)n_points * 16, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
 }
 
 ILSM_API int ilsm_extract_features(ilsm_ctx* ctx, const float* xyzi, int n, int stride_bytes, float min_range,

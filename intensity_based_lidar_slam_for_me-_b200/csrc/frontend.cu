@@ -68,6 +68,58 @@ __global__ void project_kernel(const float* __restrict__ cloud, int n, int strid
 }
 
 // ---------------------------------------------------------------------------------------------------
+// sensor_msgs/PointCloud2 blob -> packed xyzi (pcl::fromROSMsg's field map, scanRegistration.cpp:235).  One thread per
+// point; the blob is read with the widest aligned loads its layout allows (Ouster: point_step 48, x/y/z at 0/4/8 ->
+// one 128-bit load + one 32-bit load per point), the output is one float4 store.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pc2_f32(const unsigned char* p) {  // unaligned-safe little-endian float
+  uint32_t v;
+  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0)
+    v = __ldg(reinterpret_cast<const uint32_t*>(p));
+  else
+    v = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+  return __uint_as_float(v);
+}
+
+__global__ void pc2_unpack_kernel(const unsigned char* __restrict__ data, int n, ilsm_pc2_layout l, float4* __restrict__ out) {
+  pdl_entry();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = data + (size_t)i * l.point_step;
+  float x, y, z;
+  if (l.off_y == l.off_x + 4 && l.off_z == l.off_x + 8 && ((reinterpret_cast<uintptr_t>(p) + l.off_x) & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + l.off_x));
+    x = v.x, y = v.y, z = v.z;
+  } else {
+    x = pc2_f32(p + l.off_x), y = pc2_f32(p + l.off_y), z = pc2_f32(p + l.off_z);
+  }
+  float it = 0.f;
+  if (l.off_intensity >= 0) {
+    const unsigned char* q = p + l.off_intensity;
+    switch (l.intensity_datatype) {
+      case 7: it = pc2_f32(q); break;
+      case 2: it = (float)__ldg(q); break;
+      case 4: it = (float)((uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8)); break;
+      case 6: it = (float)__float_as_uint(pc2_f32(q)); break;
+      case 8: {
+        const unsigned long long lo = __float_as_uint(pc2_f32(q)), hi = __float_as_uint(pc2_f32(q + 4));
+        it = (float)__longlong_as_double((long long)(lo | (hi << 32)));
+        break;
+      }
+      default: break;
+    }
+  }
+  out[i] = make_float4(x, y, z, it);
+}
+
+int Ctx::pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layout& l, float4* d_out) {
+  if (n <= 0) return ILSM_OK;
+  ILSM_CUDA(launch_pdl(pc2_unpack_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, d_data, n, l, d_out));
+  count_launches(1);
+  return check_launch("pc2_unpack");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // feature extraction
 // ---------------------------------------------------------------------------------------------------
 constexpr int kRings = 64;

@@ -171,6 +171,7 @@ struct FeBufs {
   DevBuf<int> chunk_hist, chunk_base;  // ring counts per 256-point chunk of the frame and their per-ring prefix
   DevBuf<float4> cloud, ring_pts, ring_out, lflat, vox_packed;
   DevBuf<float> raw;                 // staged caller frame
+  DevBuf<unsigned char> pc2;         // staged sensor_msgs/PointCloud2 blob (ilsm_pc2_unpack, ilsm_slam_frame_pc2)
   DevBuf<unsigned char> img;         // projection outputs (range | intensity)
   DevBuf<float4> track;
   DevBuf<float4> vox_out;
@@ -210,6 +211,7 @@ struct Ctx {
   int project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
                   float* d_track);
   int features_dev(const float* d_in, int n, int stride_bytes, float min_range);
+  int pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layout& l, float4* d_out);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);
   int voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out);

@@ -112,11 +112,36 @@ ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
 ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam) { return slam ? slam->s.cube : nullptr; }
 ILSM_API ilsm_mapopt* ilsm_slam_mapopt(ilsm_slam* slam) { return slam ? slam->s.mapopt : nullptr; }
 
+}  // extern "C"
+namespace ilsm {
+int check_pc2_layout(const ilsm_pc2_layout* l);  // api.cu
+}
+// pc2 != nullptr: `xyzi` is a sensor_msgs/PointCloud2 data blob, unpacked on the device into packed points
+static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, const ilsm_pc2_layout* pc2, int use_aloam,
+                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats);
+extern "C" {
+
 ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom[4],
                              double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: bad n/stride");
+  return slam_frame_impl(slam, xyzi, n, stride_bytes, nullptr, use_aloam, q_odom, t_odom, q_map, t_map, stats);
+}
+
+ILSM_API int ilsm_slam_frame_pc2(ilsm_slam* slam, const uint8_t* data, int n_points, const ilsm_pc2_layout* layout, int use_aloam,
+                                 double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+  if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "slam_frame_pc2: bad n_points");
+  int rc = check_pc2_layout(layout);
+  if (rc) return rc;
+  return slam_frame_impl(slam, reinterpret_cast<const float*>(data), n_points, layout->point_step, layout, use_aloam, q_odom, t_odom,
+                         q_map, t_map, stats);
+}
+
+}  // extern "C"
+
+static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, const ilsm_pc2_layout* pc2, int use_aloam,
+                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
   if (!slam || (n > 0 && !xyzi) || !q_odom || !t_odom || !q_map || !t_map)
     return fail(ILSM_ERR_INVALID_ARG, "slam_frame: null argument");
-  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: bad n/stride");
   SlamH& s = slam->s;
   Ctx& c = *s.ctx;
   std::lock_guard<std::mutex> lk(c.mu);
@@ -125,11 +150,18 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
   int rc;
   // ---- scanRegistration: the frame is the only upload
   const size_t bytes = (size_t)n * stride_bytes;
-  if ((rc = c.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  if ((rc = c.fe.raw.reserve((pc2 ? (size_t)n * 4 : bytes / 4) + 4))) return rc;
+  if (pc2 && (rc = c.fe.pc2.reserve(bytes + 16))) return rc;
   // the previous frame's tree builds (on the maps' own streams, overlapping its mapping step) read lsharp / fe.lflat:
   // order this frame's front end after them
   if ((rc = s.last_corner.wait_ready(c.stream)) || (rc = s.last_surf.wait_ready(c.stream))) return rc;
-  if (bytes) ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  if (pc2) {  // the message blob as it is; pcl::fromROSMsg's repacking (scanRegistration.cpp:235) runs as a kernel
+    if (bytes) ILSM_CUDA(cudaMemcpyAsync(c.fe.pc2.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+    if ((rc = c.pc2_unpack_dev(c.fe.pc2.p, n, *pc2, reinterpret_cast<float4*>(c.fe.raw.p)))) return rc;
+    stride_bytes = 16;
+  } else if (bytes) {
+    ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  }
   if ((rc = c.features_dev(c.fe.raw.p, n, stride_bytes, s.min_range))) return rc;
   int* pin = reinterpret_cast<int*>(c.pinned.p);
   ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
@@ -228,5 +260,3 @@ ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stri
   s.frames++;
   return ILSM_OK;
 }
-
-}  // extern "C"

@@ -677,3 +677,40 @@ class MapOptimization:
         info.update(ran_optimization=1, converged=bool(conv), n_query=len(stack), summary=sm, map_size=len(self.map),
                     n_plane_factors=int((fac["type"] == 2).sum()), key=np.concatenate([qk, tk]))
         return x, info
+
+
+# ------------------------------------------------------------------------------------------------
+# sensor_msgs/PointCloud2 blob -> packed xyzi: the field map pcl::fromROSMsg builds for PointXYZI
+# (scanRegistration.cpp:235, image_handler.h_ouster:44,106): x, y, z FLOAT32 at their message offsets, intensity at its
+# offset (FLOAT32 in the reference's Ouster driver; other numeric types converted to float as the library's extension).
+# ------------------------------------------------------------------------------------------------
+_PC2_DTYPES = {2: "<u1", 4: "<u2", 6: "<u4", 7: "<f4", 8: "<f8"}
+
+
+def pc2_unpack(blob, point_step, off_x, off_y, off_z, off_intensity=-1, intensity_datatype=7):
+    b = np.ascontiguousarray(blob, np.uint8).reshape(-1, point_step)
+    n = len(b)
+
+    def field(off, dt):
+        w = np.dtype(dt).itemsize
+        return np.ascontiguousarray(b[:, off:off + w]).view(dt).reshape(n)
+
+    out = np.zeros((n, 4), np.float32)
+    out[:, 0], out[:, 1], out[:, 2] = field(off_x, "<f4"), field(off_y, "<f4"), field(off_z, "<f4")
+    if off_intensity >= 0:
+        out[:, 3] = field(off_intensity, _PC2_DTYPES[intensity_datatype]).astype(np.float32)
+    return out
+
+
+def pc2_pack(xyzi, point_step, off_x, off_y, off_z, off_intensity=-1, intensity_datatype=7, fill=0xAB):
+    """Test helper: the inverse (a message blob with the given layout, padding bytes = fill)."""
+    a = np.asarray(xyzi, np.float32)
+    n = len(a)
+    b = np.full((n, point_step), fill, np.uint8)
+    for k, off in enumerate((off_x, off_y, off_z)):
+        b[:, off:off + 4] = np.ascontiguousarray(a[:, k]).view(np.uint8).reshape(n, 4)
+    if off_intensity >= 0:
+        dt = np.dtype(_PC2_DTYPES[intensity_datatype])
+        b[:, off_intensity:off_intensity + dt.itemsize] = np.ascontiguousarray(a[:, 3].astype(dt)).view(np.uint8).reshape(n, dt.itemsize)
+    return b.reshape(-1)
+

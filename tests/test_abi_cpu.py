@@ -51,7 +51,7 @@ def test_every_struct_layout_matches_the_c_header(ilsm, tmp_path):
     pairs = {"ilsm_reg_opts": b.RegOpts, "ilsm_solve_summary": b.SolveSummary, "ilsm_reg_report": b.RegReport,
              "ilsm_feature_counts": b.FeatureCounts, "ilsm_features": b.Features, "ilsm_cubemap_stats": b.CubeMapStats,
              "ilsm_slam_stats": b.SlamStats, "ilsm_ground_opts": b.GroundOpts, "ilsm_ground_info": b.GroundInfo,
-             "ilsm_mapopt_stats": b.MapOptStats}
+             "ilsm_mapopt_stats": b.MapOptStats, "ilsm_pc2_layout": b.Pc2Layout}
     names = list(pairs) + ["ilsm_dmatch", "ilsm_factor"]
     src = tmp_path / "s.c"
     src.write_text('#include <stdio.h>\n#include "ilsm.h"\nint main(void){' +
