@@ -13,6 +13,7 @@
 //   laserCloudHandler             scanRegistration.cpp:189-669              ilsm::ScanRegistration
 //   process()                     laserMapping.cpp:233-1166                 ilsm::LaserMapping
 //   mapOptimizationCallback       mapOptimization.cpp:99-500                ilsm::MapOptimization
+//   callback() (odometry merge)   odom_handler_node.cpp:44-132              ilsm::OdomHandler (host arithmetic only)
 //
 // Nothing here computes: every method forwards to libilsm_cuda.so (CUDA, sm_100a).  There is no CPU fallback; without a
 // GPU the Context constructor throws ilsm::Error(ILSM_ERR_NO_DEVICE).
@@ -422,6 +423,8 @@ class ImageHandler {
 // (laserMapping.cpp:105-107), updated in place like Ceres does.
 template <typename PointT>
 class ScanToMapRegistration {
+  ContextPtr ctx_;  // declared first: the kd-trees below are built on it
+
  public:
   explicit ScanToMapRegistration(ContextPtr ctx = Context::shared())
       : ctx_(ctx), kdtreeCornerFromMap(ctx), kdtreeSurfFromMap(ctx) {
@@ -445,9 +448,6 @@ class ScanToMapRegistration {
     check(rc, "ilsm_register");
     return true;
   }
-
- private:
-  ContextPtr ctx_;
 };
 
 // ------------------------------------------------------------------------------------------------ node bodies
@@ -543,6 +543,78 @@ class MapOptimization {
  private:
   ContextPtr ctx_;
   ilsm_mapopt* mo_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------ odom_handler_node
+// callback() of odom_handler_node.cpp:44-132: merges the A-LOAM and the intensity odometry streams -- the merged pose
+// advances by the A-LOAM increment on frames flagged "/odom_skip" (child_frame_id of the intensity odometry), else by the
+// intensity increment.  Pure host arithmetic on 4x4 transforms (no GPU work on this node), kept here so that the launched
+// graph is complete above the C ABI.  Poses are {qx,qy,qz,qw, tx,ty,tz}.
+class OdomHandler {
+ public:
+  struct Mat4 {
+    double m[4][4];
+  };
+  bool aloam_odom_init = false, intensity_odom_init = false;
+  Mat4 odom_cur, aloam_prev, intensity_prev;
+
+  static Mat4 from_pose(const double p[7]) {  // Eigen::Quaterniond::toRotationMatrix + translation
+    const double x = p[0], y = p[1], z = p[2], w = p[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
+                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    Mat4 r = {{{1 - (tyy + tzz), txy - twz, txz + twy, p[4]}, {txy + twz, 1 - (txx + tzz), tyz - twx, p[5]},
+               {txz - twy, tyz + twx, 1 - (txx + tyy), p[6]}, {0, 0, 0, 1}}};
+    return r;
+  }
+  static Mat4 mul(const Mat4& a, const Mat4& b) {
+    Mat4 c;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) c.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j] + a.m[i][3] * b.m[3][j];
+    return c;
+  }
+  static Mat4 rigid_inverse(const Mat4& a) {  // the inputs are rigid transforms: inverse = [R^T, -R^T t]
+    Mat4 c = {{{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 1}}};
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) c.m[i][j] = a.m[j][i];
+      c.m[i][3] = -(a.m[0][i] * a.m[0][3] + a.m[1][i] * a.m[1][3] + a.m[2][i] * a.m[2][3]);
+    }
+    return c;
+  }
+  // Eigen::Quaterniond(rot): the branch structure of Eigen's quat_product-free conversion (trace > 0, else largest diagonal)
+  static void to_pose(const Mat4& a, double p[7]) {
+    const double (*m)[4] = a.m;
+    double t = m[0][0] + m[1][1] + m[2][2];
+    if (t > 0) {
+      t = std::sqrt(t + 1.0);
+      p[3] = 0.5 * t;
+      t = 0.5 / t;
+      p[0] = (m[2][1] - m[1][2]) * t, p[1] = (m[0][2] - m[2][0]) * t, p[2] = (m[1][0] - m[0][1]) * t;
+    } else {
+      int i = 0;
+      if (m[1][1] > m[0][0]) i = 1;
+      if (m[2][2] > m[i][i]) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+      p[i] = 0.5 * t;
+      t = 0.5 / t;
+      p[3] = (m[k][j] - m[j][k]) * t, p[j] = (m[j][i] + m[i][j]) * t, p[k] = (m[k][i] + m[i][k]) * t;
+    }
+    p[4] = m[0][3], p[5] = m[1][3], p[6] = m[2][3];
+  }
+  // returns the merged pose published on the merged-odometry topic (odom_handler_node.cpp:113-129)
+  void callback(const double aloam_odom[7], const double intensity_odom[7], const std::string& skip_flag, double merged[7]) {
+    const Mat4 aloam_odom_cur = from_pose(aloam_odom), intensity_odom_cur = from_pose(intensity_odom);
+    if (!aloam_odom_init && !intensity_odom_init) {
+      aloam_prev = aloam_odom_cur, intensity_prev = intensity_odom_cur, odom_cur = intensity_odom_cur;
+      aloam_odom_init = intensity_odom_init = true;
+    } else {
+      const Mat4 intensity_odom_diff = mul(rigid_inverse(intensity_prev), intensity_odom_cur);
+      const Mat4 aloam_odom_diff = mul(rigid_inverse(aloam_prev), aloam_odom_cur);
+      odom_cur = mul(odom_cur, skip_flag == "/odom_skip" ? aloam_odom_diff : intensity_odom_diff);
+      aloam_prev = aloam_odom_cur, intensity_prev = intensity_odom_cur;
+    }
+    to_pose(odom_cur, merged);
+  }
 };
 
 }  // namespace ilsm

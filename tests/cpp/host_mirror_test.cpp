@@ -350,8 +350,33 @@ static void test_scancontext() {
   std::printf("  loop %d, distance %.4f, yaw %.3f rad\n", hit.first, sc.lastDistance(), hit.second);
 }
 
+static void test_odom_handler() {
+  std::printf("OdomHandler::callback (odometry merge)\n");
+  ilsm::OdomHandler h;
+  auto pose = [](double yaw, double x, double y, double* p) {
+    p[0] = 0, p[1] = 0, p[2] = std::sin(yaw / 2), p[3] = std::cos(yaw / 2), p[4] = x, p[5] = y, p[6] = 0;
+  };
+  double a[7], b[7], m[7];
+  pose(0.0, 0, 0, a), pose(0.0, 0, 0, b);
+  h.callback(a, b, "", m);
+  EXPECT(std::fabs(m[3] - 1) < 1e-15 && m[4] == 0);
+  // frame 1: intensity odometry moved 1 m forward, A-LOAM 2 m: not skipped -> intensity increment
+  pose(0.0, 2, 0, a), pose(0.0, 1, 0, b);
+  h.callback(a, b, "", m);
+  EXPECT(std::fabs(m[4] - 1) < 1e-15);
+  // frame 2: flagged "/odom_skip" -> A-LOAM increment (turn 0.1 rad, +2 m in its own frame)
+  pose(0.1, 4, 0, a), pose(0.0, 1.5, 0, b);
+  h.callback(a, b, "/odom_skip", m);
+  EXPECT(std::fabs(m[4] - 3) < 1e-14 && std::fabs(m[2] - std::sin(0.05)) < 1e-15 && std::fabs(m[3] - std::cos(0.05)) < 1e-15);
+  // frame 3: intensity again: increment expressed in the merged frame (rotated by 0.1)
+  pose(0.1, 5, 0, a), pose(0.0, 2.5, 0, b);
+  h.callback(a, b, "", m);
+  EXPECT(std::fabs(m[4] - (3 + std::cos(0.1))) < 1e-14 && std::fabs(m[5] - std::sin(0.1)) < 1e-14);
+}
+
 int main() {
   try {
+    test_odom_handler();
     test_kdtree_flann();
     test_voxelgrid();
     test_ikd_tree();
