@@ -573,23 +573,25 @@ __device__ __forceinline__ constexpr int ut(int a, int b) { return a * 6 - a * (
 // A y = b for symmetric positive definite 6x6 (packed lower, destroyed) by in-place LDL^T with reciprocal pivots:
 // 6 divisions in all, everything in registers.
 __device__ __forceinline__ bool ldlt_solve6(double (&m)[21], const double (&b)[6], double (&x)[6]) {
+  // right-looking, in place: once column j is final (w_ij = L_ij d_j), the trailing sub-matrix is updated with
+  // m_ic -= L_ij w_cj (one FMA per term) and the column is overwritten with L; no second array, 6 reciprocals
   double dinv[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double dj = m[lt(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; ++k) dj -= m[lt(j, k)] * m[lt(j, k)] * m[lt(k, k)];
+    const double dj = m[lt(j, j)];
     ok = ok && (dj > 0.0);
-    m[lt(j, j)] = dj;
     dinv[j] = frcp(dj);
+    double l[6];
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) l[i] = m[lt(i, j)] * dinv[j];
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
-      double s = m[lt(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= m[lt(i, k)] * m[lt(j, k)] * m[lt(k, k)];
-      m[lt(i, j)] = s * dinv[j];
+      for (int c = j + 1; c <= i; ++c) m[lt(i, c)] = fma(-l[i], m[lt(c, j)], m[lt(i, c)]);
     }
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) m[lt(i, j)] = l[i];
   }
   if (!ok) return false;
   double z[6];
@@ -597,14 +599,14 @@ __device__ __forceinline__ bool ldlt_solve6(double (&m)[21], const double (&b)[6
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) s -= m[lt(i, k)] * z[k];
+    for (int k = 0; k < i; ++k) s = fma(-m[lt(i, k)], z[k], s);
     z[i] = s;
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i] * dinv[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) s -= m[lt(k, i)] * x[k];
+    for (int k = i + 1; k < 6; ++k) s = fma(-m[lt(k, i)], x[k], s);
     x[i] = s;
   }
   return true;
@@ -812,6 +814,35 @@ constexpr int kSolveThreads = 384;
 constexpr int kCoreWords = (int)(offsetof(LmState, report) / 8);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// mbarrier / bulk-copy primitives (sm_90+ PTX)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -820,13 +851,25 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// read a double from the shared memory of CTA `rank` of this cluster (DSMEM)
-__device__ __forceinline__ double dsmem_ld_f64(const double* local_ptr, uint32_t rank) {
-  uint32_t a = smem_u32(local_ptr), ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-  double v;
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-  return v;
+// Push one double into a peer's shared memory; the store completes 8 bytes of the transaction count of the peer's
+// mbarrier (release at cluster scope), so the peer learns about the data without a cluster-wide barrier.
+__device__ __forceinline__ void dsmem_push_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "XWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra XWAIT_DONE;\n"
+      "bra XWAIT_LOOP;\n"
+      "XWAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 
 struct SolveParams {
@@ -840,8 +883,12 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   __shared__ double core[kCoreWords];
   if (d_counts) n = d_counts[0] + d_counts[1];
   __shared__ double red[kSolveThreads / 32][kSumStride];
-  __shared__ double part[2][kSumStride];
+  // partial sums of every CTA of the cluster for the current evaluation, pushed by their owners (double-buffered by
+  // evaluation parity) + the transaction barriers that count the 8 x 32 x 8 arriving bytes
+  __shared__ double recv[2][kClusterSize][kSumStride];
+  __shared__ __align__(8) unsigned long long xbar[2];
   __shared__ double tot[kSumStride];
+  constexpr uint32_t kXferBytes = kClusterSize * kSumStride * 8;
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // factor i -> CTA (i % 8), thread (i / 8): the edge factors (3 residual rows, the first nc slots) are spread
@@ -865,9 +912,14 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
     const double* src = reinterpret_cast<const double*>(st);
     for (int w = tid; w < kCoreWords; w += kSolveThreads) core[w] = src[w];
   }
+  if (tid == 0) {
+    mbar_init(smem_u32(&xbar[0]), 1), mbar_init(smem_u32(&xbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(smem_u32(&xbar[0]), kXferBytes), mbar_expect_tx(smem_u32(&xbar[1]), kXferBytes);  // evaluations 0 and 1
+  }
   __syncthreads();
   if (tid == 0 && prm.arm) lm_arm(s, prm.max_iter, prm.huber_a, prm.pass);
-  __syncthreads();
+  cluster_sync_all();  // every CTA's barriers are armed before any peer pushes into them (also a CTA barrier)
   ilsm_reg_report* rep = rank == 0 ? &st->report : nullptr;
 
 #ifdef ILSM_DEBUG_TIMING
@@ -900,28 +952,39 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
     red[warp][lane] = mine;
     __syncthreads();
     STAMP(2);
+    const int buf = e & 1;
     if (tid < kSumStride) {
       double v = 0;
 #pragma unroll
       for (int w = 0; w < kSolveThreads / 32; ++w) v += red[w][tid];
-      part[e & 1][tid] = v;
-    }
-    cluster_sync_all();  // partials of every CTA visible cluster-wide
-    STAMP(3);
-    if (tid < kSumStride) {
-      double v = 0;
+      // push this CTA's partial into slot [rank] of every CTA (itself included): no cluster barrier, no remote loads
+      const uint32_t slot = smem_u32(&recv[buf][rank][tid]), bar = smem_u32(&xbar[buf]);
 #pragma unroll
-      for (uint32_t r = 0; r < (uint32_t)kClusterSize; ++r) v += dsmem_ld_f64(&part[e & 1][tid], r);
-      tot[tid] = v;
+      for (uint32_t r = 0; r < (uint32_t)kClusterSize; ++r) {
+        uint32_t ra, rb;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(slot), "r"(r));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar), "r"(r));
+        dsmem_push_f64(ra, v, rb);
+      }
+      STAMP(3);
+      mbar_wait_cluster(bar, (uint32_t)(e >> 1) & 1u);  // all 8 partials have landed here
+      double t8 = 0;
+#pragma unroll
+      for (int r = 0; r < kClusterSize; ++r) t8 += recv[buf][r][tid];  // same order in every CTA: identical totals
+      tot[tid] = t8;
     }
     __syncthreads();
     STAMP(4);
+    // re-arm this buffer's barrier for evaluation e + 2: a peer can only push that far ahead after it has received this
+    // CTA's partial of evaluation e + 1, which is sent after this point
+    if (tid == 0) mbar_expect_tx(smem_u32(&xbar[buf]), kXferBytes);
     if (tid == 0) lm_advance(s, rep, tot);
     STAMP(5);
     __syncthreads();
     STAMP(6);
   }
-  cluster_sync_all();  // nobody may exit while a peer can still read its shared memory
+  // no trailing cluster barrier: peers only WRITE into this CTA's shared memory, and every such write has been waited
+  // for above (all CTAs run the same number of evaluations)
   if (rank == 0) {
     double* dst = reinterpret_cast<double*>(st);
     for (int w = tid; w < kCoreWords; w += kSolveThreads) dst[w] = core[w];
@@ -1035,34 +1098,6 @@ constexpr int kBulkThreads = kBulkTile + 32;    // + one producer warp = 12 warp
 constexpr int kBulkStages = 6;
 constexpr int kBulkStageBytes = kBulkTile * (4 + 16 + 32 + 32);
 constexpr size_t kBulkSmemBytes = (size_t)kBulkStages * kBulkStageBytes + 2 * kBulkStages * 8 + 128;
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 // 12 warps and not 13: registers are allocated per SM sub-partition (4 x 16 K), so a 13th warp would cap the kernel at
 // 128 registers per thread (spills in the tile loop).
