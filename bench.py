@@ -185,7 +185,11 @@ def config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts):
     t = timed(lambda: ctx.eval_normal_eq_dev(pose_t.data_ptr(), out32.data_ptr()))
     # every factor slot read once: type 4 B + point 16 B + (normal | point_a) 32 B, + point_b 32 B for the corner slots
     byt = Qb * 52 + (Qb // 8) * 32
-    out["jtj"] = {"factors": Qb, "corner_slots": Qb // 8, "kernel": "normal_eq_bulk_kernel", "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
+    try:
+        jtj_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["config3"]["normal_eq_bulk_kernel"]
+    except Exception:
+        jtj_traffic = None
+    out["jtj"] = {"factors": Qb, "corner_slots": Qb // 8, "kernel": "normal_eq_bulk_kernel", "ncu_dram_bytes": jtj_traffic, "ms": t, "factors_per_s": Qb / t * 1e3, "algorithmic_bytes": byt,
                   "achieved_GBs": byt / t / 1e6, "frac": byt / t / 1e6 / peak, "bound": "hbm"}
     gm.close(), mc.close(), ms.close()
     return out
