@@ -350,3 +350,40 @@ def test_register_matches_oracle_regression_golden(ctx, ilsm):
         assert np.array_equal(f[key], g[key]), key
     assert len(f["less_flat"]) == int(g["n_less_flat"])
     mc.close(), ms.close()
+
+
+def test_knn_config3_full_size_sample(ctx, oracle_mod, ilsm):
+    """BASELINE configs[2] at its largest point: a 2M-point map, the whole 65536-ray frame as queries.  The oracle k-d tree
+    answers a 768-query sample (bit-exact indices and distances), and two size-independent properties hold for all of
+    them: ascending distances per query, and d2 recomputed from the returned index equals the returned d2."""
+    S = ilsm.synth
+    c = S.config1(n_map=2_000_000)
+    m = np.ascontiguousarray(np.concatenate([c["map_corner"], c["map_surf"]])[:, :3], np.float32)
+    R = S.quat_to_mat(c["q_true"])
+    q = (c["cloud"][:, :3].astype(np.float64) @ R.T + c["t_true"]).astype(np.float32)
+    lm = ctx.new_map().set_input_cloud(m)
+    idx, d2 = lm.nearest_k_search(q, 5)
+    assert (idx >= 0).all() and (np.diff(d2, axis=1) >= 0).all()
+    nb = m[idx]                                               # (Q, 5, 3)
+    dx, dy, dz = (q[:, None, 0] - nb[..., 0]), (q[:, None, 1] - nb[..., 1]), (q[:, None, 2] - nb[..., 2])
+    assert np.array_equal((dx * dx + dy * dy) + dz * dz, d2)  # FLANN L2_Simple order, float, no FMA
+    sel = np.random.default_rng(3).choice(len(q), 768, replace=False)
+    ri, rd = oracle_mod.knn_kdtree(m, q[sel], 5)
+    assert np.array_equal(idx[sel], ri) and np.array_equal(d2[sel], rd)
+    lm.close()
+
+
+def test_eval_normal_eq_is_additive_over_factor_sets(ctx, cfg_small):
+    """Size-independent property of the J^T J kernels: the sums over k copies of a factor set are k times the sums over
+    one copy (small kernel vs bulk-copy kernel, 1e-12 relative: different summation orders)."""
+    c = cfg_small
+    mc, ms = _maps(ctx, c)
+    ctx.associate(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    cost1, H1, g1 = ctx.eval_normal_eq(c["q0"], c["t0"], 0.1)
+    k = 1 + (148 * 352) // (len(c["corner"]) + len(c["surf"]))  # enough copies for one tile per SM: the bulk kernel
+    ctx.associate(mc, ms, np.tile(c["corner"], (k, 1)), np.tile(c["surf"], (k, 1)), c["q0"], c["t0"])
+    costk, Hk, gk = ctx.eval_normal_eq(c["q0"], c["t0"], 0.1)
+    assert abs(costk - k * cost1) <= 1e-12 * k * cost1
+    assert np.abs(Hk - k * H1).max() <= 1e-12 * k * np.abs(H1).max()
+    assert np.abs(gk - k * g1).max() <= 1e-11 * k * np.abs(g1).max()
+    mc.close(), ms.close()
