@@ -371,11 +371,14 @@ ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const 
   ILSM_CUDA(cudaSetDevice(c.device));
   if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
     return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
-  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, (ilsm_reg_report*)nullptr, 0));
-  count_launches(2);
-  if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
-  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, d_pose7, d_report, 1));
-  return check_launch("register_dev");
+  // the first association reads the pose straight from d_pose7 (and seeds the LM state), the last solve writes the
+  // result and the report back: no separate pose upload / download launches
+  PoseSrc src;
+  src.mode = 2, src.dptr = d_pose7;
+  PoseDst dst;
+  dst.d_pose7 = d_pose7, dst.d_report = d_report;
+  if (o.outer_iterations < 1) return ILSM_OK;
+  return c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, &src, &dst);
 }
 
 ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* d_corner, int nc,
@@ -388,9 +391,9 @@ ILSM_API int ilsm_associate_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const
   Ctx& c = ctx->c;
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
-  ILSM_CUDA(launch_pdl(pose_io_kernel, dim3(1), dim3(32), 0, c.stream, c.lm.p, const_cast<double*>(d_pose7), (ilsm_reg_report*)nullptr, 0));
-  count_launches(1);
-  return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false);
+  PoseSrc src;
+  src.mode = 2, src.dptr = d_pose7;
+  return c.associate_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, false, &src);
 }
 
 ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,
@@ -407,12 +410,12 @@ ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const floa
     return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
   const float *d_corner, *d_surf;
   if ((rc = stage_stacks(c, corner, nc, surf, ns, stride_bytes, &d_corner, &d_surf))) return rc;
-  Pose7 p;
-  for (int i = 0; i < 4; ++i) p.v[i] = q[i];
-  for (int i = 0; i < 3; ++i) p.v[4 + i] = t[i];
-  ILSM_CUDA(launch_pdl(set_pose_kernel, dim3(1), dim3(1), 0, c.stream, c.lm.p, p, 0, 0.0));
-  count_launches(1);
-  if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o))) return rc;
+  PoseSrc src;  // the initial guess travels with the first association launch
+  src.mode = 1;
+  for (int i = 0; i < 4; ++i) src.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) src.v[4 + i] = t[i];
+  if (o.outer_iterations < 1) return ILSM_OK;
+  if ((rc = c.register_dev(&mc->m, &ms->m, d_corner, nc, d_surf, ns, stride_bytes, o, &src, nullptr))) return rc;
   // pose (7 doubles, xq/xt are adjacent) and the report come back through pinned memory
   unsigned char* pin = c.pinned.p;
   ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));

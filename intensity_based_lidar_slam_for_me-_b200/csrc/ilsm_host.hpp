@@ -110,6 +110,18 @@ struct LmState {
   long long dbg[64];  // clock64() phase stamps written when ILSM_DEBUG_TIMING is compiled in (profiling aid)
 };
 
+// Where the association kernel of the FIRST pass takes the pose from, and where the solve kernel of the LAST pass
+// leaves the result: folding these into the two kernels removes the 1-warp pose upload / download launches.
+struct PoseSrc {
+  const double* dptr = nullptr;  // mode 2: 7 doubles on the device
+  double v[7] = {0, 0, 0, 1, 0, 0, 0};  // mode 1: by value (host-pointer entry points)
+  int mode = 0;                  // 0: the accepted pose already in the LM state
+};
+struct PoseDst {
+  double* d_pose7 = nullptr;           // pose after the last pass (nullptr: stays in the LM state only)
+  ilsm_reg_report* d_report = nullptr;  // the whole report (nullptr: stays in the LM state only)
+};
+
 struct Ctx;
 
 struct Map {
@@ -202,8 +214,8 @@ struct Ctx {
   void release();
   bool async_build = false;  // ilsm_set_async: host-pointer map builds return without synchronising
   int associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                    const ilsm_reg_opts& o, bool want_knn);
-  int solve_launch(int max_iter, double huber_a, int pass);  // the whole LM solve, one cluster launch
+                    const ilsm_reg_opts& o, bool want_knn, const PoseSrc* src = nullptr);
+  int solve_launch(int max_iter, double huber_a, int pass, const PoseDst* dst = nullptr);  // the whole LM solve, one cluster launch
   int odom_associate_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl, int stride_bytes);
   int odometry_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const float* d_flat, int nfl, int stride_bytes,
                    const ilsm_reg_opts& o);
@@ -219,7 +231,7 @@ struct Ctx {
                          float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s);
   int gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out);
   int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                   const ilsm_reg_opts& o);
+                   const ilsm_reg_opts& o, const PoseSrc* src = nullptr, const PoseDst* dst = nullptr);
 };
 
 // ScanContext keyframe database (one shard when the database is split across ranks).

@@ -187,8 +187,8 @@ constexpr int kAssocThreads = 128;
 // One warp per stack point (grid-stride when the stacks exceed one resident wave).
 __global__ void __launch_bounds__(kAssocThreads, 5)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
-                     int ns, int stride_f, const LmState* __restrict__ st, AssocParams prm, FactorView fv,
-                     const int* __restrict__ d_counts) {
+                     int ns, int stride_f, LmState* __restrict__ st, AssocParams prm, FactorView fv,
+                     const int* __restrict__ d_counts, PoseSrc src) {
   pdl_entry();
   __shared__ WarpScratch scratch[kAssocThreads / 32];
   if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
@@ -198,10 +198,14 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
   int bbc[6], bbs[6];
   load_bbox(gc, bbc);
   load_bbox(gs, bbs);
-  const double q[4] = {st->xq[0], st->xq[1], st->xq[2], st->xq[3]};
-  const double tx = st->xt[0], ty = st->xt[1], tz = st->xt[2];
+  // pose: the LM state (later passes), or handed in with the launch (first pass; block 0 then seeds the LM state for
+  // the solve kernel -- nobody reads the state's pose inside this launch in that case)
+  const double* p7 = src.mode == 2 ? src.dptr : (src.mode == 1 ? src.v : st->xq);  // xq[4], xt[3] are contiguous
+  const double q[4] = {p7[0], p7[1], p7[2], p7[3]};
+  const double tx = p7[4], ty = p7[5], tz = p7[6];
+  if (src.mode != 0 && blockIdx.x == 0 && threadIdx.x < 7) st->xq[threadIdx.x] = p7[threadIdx.x];
 #ifdef ILSM_DEBUG_TIMING
-#define ASTAMP(k) do { if (lane == 0 && (gid == 5 || gid == nc + 1000)) const_cast<LmState*>(st)->dbg[48 + (gid == 5 ? 0 : 8) + (k)] = clock64(); } while (0)
+#define ASTAMP(k) do { if (lane == 0 && (gid == 5 || gid == nc + 1000)) st->dbg[48 + (gid == 5 ? 0 : 8) + (k)] = clock64(); } while (0)
 #else
 #define ASTAMP(k) do { } while (0)
 #endif
@@ -875,6 +879,8 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 struct SolveParams {
   int max_iter, pass, arm;
   double huber_a;
+  double* d_pose7_out;             // non-null: the pose after this solve is also written here
+  ilsm_reg_report* d_report_out;   // non-null: the accumulated report is also written here
 };
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThreads, 1)
@@ -988,6 +994,13 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   if (rank == 0) {
     double* dst = reinterpret_cast<double*>(st);
     for (int w = tid; w < kCoreWords; w += kSolveThreads) dst[w] = core[w];
+    if (prm.d_pose7_out && tid < 7) prm.d_pose7_out[tid] = core[tid];  // xq[4], xt[3] lead the state
+    if (prm.d_report_out) {  // written to st->report by thread 0 (lm_terminate) before the barrier that ended the loop
+      const int words = (int)(sizeof(ilsm_reg_report) / 4);
+      const int32_t* rs = reinterpret_cast<const int32_t*>(&st->report);
+      int32_t* rd = reinterpret_cast<int32_t*>(prm.d_report_out);
+      for (int w = tid; w < words; w += kSolveThreads) rd[w] = rs[w];
+    }
   }
 }
 
@@ -1232,8 +1245,15 @@ static FactorView factor_view(FactorBufs& f, bool want_knn) {
   return v;
 }
 
+// empty stacks: nothing to associate, but a pose handed in with the launch must still reach the LM state
+__global__ void pose_seed_kernel(LmState* st, PoseSrc src) {
+  pdl_entry();
+  const double* p7 = src.mode == 2 ? src.dptr : src.v;
+  if (threadIdx.x < 7) st->xq[threadIdx.x] = p7[threadIdx.x];
+}
+
 int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                       const ilsm_reg_opts& o, bool want_knn) {
+                       const ilsm_reg_opts& o, bool want_knn, const PoseSrc* src) {
   const int n = nc + ns;
   int rc;
   if ((rc = fac.type.reserve(n + 4)) || (rc = fac.p.reserve(n + 1)) || (rc = fac.a.reserve(n + 1)) ||
@@ -1243,7 +1263,13 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
     return rc;
   fac.n = n;
   fac.nc = nc;
-  if (n == 0) return ILSM_OK;
+  const PoseSrc ps = src ? *src : PoseSrc();
+  if (n == 0) {
+    if (ps.mode == 0) return ILSM_OK;
+    ILSM_CUDA(launch_pdl(pose_seed_kernel, dim3(1), dim3(32), 0, stream, lm.p, ps));
+    count_launches(1);
+    return check_launch("pose_seed");
+  }
   if ((rc = mc->wait_ready(stream)) || (rc = ms->wait_ready(stream))) return rc;
   AssocParams prm;
   prm.gate_sq = o.knn_gate_sq;
@@ -1256,7 +1282,7 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
   if (blocks > cap) blocks = cap;
   ILSM_CUDA(launch_pdl(associate_kernel, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc, d_surf, ns,
-                       stride_f, (const LmState*)lm.p, prm, fv, d_stack_counts));
+                       stride_f, lm.p, prm, fv, d_stack_counts, ps));
   count_launches(1);
   return check_launch("associate");
 }
@@ -1291,12 +1317,14 @@ int Ctx::odometry_dev(Map* mc, Map* ms, const float* d_sharp, int nsh, const flo
   return ILSM_OK;
 }
 
-int Ctx::solve_launch(int max_iter, double huber_a, int pass) {
+int Ctx::solve_launch(int max_iter, double huber_a, int pass, const PoseDst* dst) {
   SolveParams prm;
   prm.max_iter = max_iter;
   prm.pass = pass;
   prm.arm = 1;
   prm.huber_a = huber_a;
+  prm.d_pose7_out = dst ? dst->d_pose7 : nullptr;
+  prm.d_report_out = dst ? dst->d_report : nullptr;
   FactorView fv = factor_view(fac, false);
   ILSM_CUDA(launch_pdl(solve_cluster_kernel, dim3(kClusterSize), dim3(kSolveThreads), 0, stream, fv, fac.n, lm.p, prm,
                        d_stack_counts));
@@ -1305,11 +1333,11 @@ int Ctx::solve_launch(int max_iter, double huber_a, int pass) {
 }
 
 int Ctx::register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
-                      const ilsm_reg_opts& o) {
+                      const ilsm_reg_opts& o, const PoseSrc* src, const PoseDst* dst) {
   for (int pass = 0; pass < o.outer_iterations; ++pass) {
-    int rc = associate_dev(mc, ms, d_corner, nc, d_surf, ns, stride_bytes, o, false);
+    int rc = associate_dev(mc, ms, d_corner, nc, d_surf, ns, stride_bytes, o, false, pass == 0 ? src : nullptr);
     if (rc) return rc;
-    if ((rc = solve_launch(o.max_num_iterations, o.huber_a, pass))) return rc;
+    if ((rc = solve_launch(o.max_num_iterations, o.huber_a, pass, pass == o.outer_iterations - 1 ? dst : nullptr))) return rc;
   }
   return ILSM_OK;
 }
