@@ -332,7 +332,7 @@ namespace ilsm {
 int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
                        const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready,
-                       bool defer_tail) {
+                       bool defer_tail, cudaEvent_t stacks_event) {
   Ctx& c = *m.ctx;
   {
     int rcw = m.wait_tail();
@@ -368,6 +368,11 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
     if ((rc = m.map_c.build_dev(reinterpret_cast<const float*>(m.from_c.p), n_mc, 16, 0.f)) ||
         (rc = m.map_s.build_dev(reinterpret_cast<const float*>(m.from_s.p), n_ms, 16, 0.f)))
       return rc;
+  }
+  // the stacks produced on the caller's side stream are first needed here: the window roll, the 5x5x3 gather and the two
+  // map builds above did not have to wait for them
+  if (stacks_event) ILSM_CUDA(cudaStreamWaitEvent(c.stream, stacks_event, 0));
+  if (optimise) {
     c.d_stack_counts = m.stack_n.p;
     rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.stack_c.p), nc, reinterpret_cast<const float*>(m.stack_s.p),
                         ns, 16, o);

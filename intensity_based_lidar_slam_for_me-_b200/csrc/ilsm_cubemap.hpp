@@ -65,7 +65,8 @@ struct CubeMapH {
 // One iteration of process() (laserMapping.cpp:327-1002) with the feature clouds already on the device.
 int cubemap_frame_core(CubeMapH& m, const float* d_corner_last, int nc, const float* d_surf_last, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
-                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready, bool defer_tail);
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready, bool defer_tail,
+                       cudaEvent_t stacks_event = nullptr);  // stacks_event: recorded after the caller's stack VoxelGrid
 
 }  // namespace ilsm
 

@@ -237,12 +237,11 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
     return rc;
   // ---- mapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
   if (cmp) {  // laserMapping: rolling cube map
-    ILSM_CUDA(cudaStreamWaitEvent(c.stream, c.ev_join, 0));
     ilsm_reg_opts mo;
     ilsm_reg_opts_default(&mo);
     rc = cubemap_frame_core(*cmp, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
                             reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
-                            stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true);
+                            stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true, c.ev_join);
   } else {    // mapOptimization: ground extraction from the frame already on the device + the less-flat cloud
     ilsm_mapopt_stats ms;
     rc = mapopt_frame_core(s.mapopt, c.fe.raw.p, n, stride_bytes, reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, false,
