@@ -115,7 +115,8 @@ void Map::release() {
   if (ctx_done) cudaEventDestroy(ctx_done);
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr, ready = nullptr, ctx_done = nullptr;
-  cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release();
+  cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release(), occ.release();
+  gen = 0, prev_n = 0, clean_size = 0;
   bbox.release(), raw.release();
   vox_table.release(), ins_new.release(), ins_out.release(), ins_slot_new.release(), ins_slot_old.release();
   ins_keep.release(), ins_pos.release(), ins_bsum.release();

@@ -133,6 +133,9 @@ struct Map {
   DevBuf<GridCell> cells;
   DevBuf<float4> sorted, orig;
   DevBuf<uint32_t> slot_of, rank_of, counters;
+  DevBuf<uint32_t> occ;      // slots claimed by the last build (what the next build has to clear)
+  int gen = 0, prev_n = 0;   // build generation (ping-pongs the occupied-voxel counter), point count of the last build
+  size_t clean_size = 0;     // cells[0, clean_size) is EMPTY apart from the slots listed in occ
   DevBuf<int> bbox;
   DevBuf<float> raw;  // staging of caller bytes for the host-pointer entry points
   // Each map builds on its own stream so that the corner and surf structures of a frame are built concurrently

@@ -4,10 +4,15 @@
 // laserOdometry.cpp:452,574,807-808) and ikd-Tree Build/Nearest_Search (mapOptimization.cpp:192,393).
 //
 // Build = 4 short kernels, no sort:
-//   clear   : table slots <- EMPTY, counters <- 0
-//   count   : every point claims its voxel slot with atomicCAS and takes a rank with atomicAdd
-//   alloc   : every occupied slot gets a contiguous range (warp-aggregated atomicAdd on one cursor)
+//   clear   : the slots the PREVIOUS build occupied <- EMPTY (its occupied-slot list), counters <- 0; a full clear of
+//             the table only when the table grew or was reallocated
+//   count   : every point claims its voxel slot with atomicCAS and takes a rank with atomicAdd; slots claimed for the
+//             first time are appended to the occupied-slot list (one atomicAdd per block)
+//   alloc   : every occupied slot (the list, not the table) gets a contiguous range (one atomicAdd per block)
 //   scatter : points are written as float4 {x,y,z,bits(index)} into their voxel's range
+// The table has >= 2 N slots (the only safe bound before the points are seen) but only the occupied voxels -- a few
+// per cent of it for a dense map -- are ever touched again: at N = 2 M the full clear + full-table alloc pass moved
+// 190 MB of the build's 480 MB.
 // The memory order of voxels/points is not deterministic, the k-NN result is: selection uses the total
 // order (d2, original index).
 #include "ilsm_host.hpp"
@@ -24,7 +29,24 @@ __global__ void grid_clear_kernel(GridCell* cells, uint32_t size, int* bbox, uin
   }
   if (i < 3) bbox[i] = INT_MAX;
   if (i >= 3 && i < 6) bbox[i] = INT_MIN;
-  if (i < 4) counters[i] = 0;  // [0] cursor, [1] inserted points, [2] skipped points
+  if (i < 6) counters[i] = 0;  // [0] cursor, [2] skipped points, [4], [5] occupied voxels (ping-pong by build generation)
+}
+
+// counters: [0] cursor, [2] skipped points, [4 + (gen & 1)] occupied voxels of build `gen`
+__global__ void grid_clear_sparse_kernel(GridCell* cells, const uint32_t* __restrict__ occ, int* bbox, uint32_t* counters,
+                                         int gen) {
+  pdl_entry();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_prev = counters[4 + ((gen - 1) & 1)];  // nobody writes this one in this launch
+  if (i < n_prev) {
+    uint4 e;
+    e.x = 0xFFFFFFFFu, e.y = 0xFFFFFFFFu, e.z = 0u, e.w = 0u;
+    reinterpret_cast<uint4*>(cells)[occ[i]] = e;
+  }
+  if (i < 3) bbox[i] = INT_MAX;
+  if (i >= 3 && i < 6) bbox[i] = INT_MIN;
+  if (i < 3) counters[i] = 0;
+  if (i == 3) counters[4 + (gen & 1)] = 0;
 }
 
 __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i, float& x, float& y, float& z) {
@@ -36,8 +58,10 @@ __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i
 __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, int ioff, float inv_cell, GridCell* cells,
                                   uint32_t mask, int log2_size, float4* __restrict__ orig,
                                   uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
-                                  uint32_t* counters) {
+                                  uint32_t* counters, uint32_t* __restrict__ occ, int gen) {
   pdl_entry();
+  __shared__ uint32_t s_wnew[8];
+  __shared__ uint32_t s_obase;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool in = i < n;
@@ -60,6 +84,8 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
   // per point.  All 32 lanes take part in the match; lanes without a point carry a key nobody shares.
   const u64 key = ok ? pack_voxel(cx, cy, cz) : (kEmptyKey - 1ull - (u64)lane);
   const unsigned peers = __match_any_sync(0xffffffffu, key);
+  bool created = false;  // this lane claimed a slot nobody had claimed before
+  uint32_t my_slot = 0;
   if (ok) {
     const int leader = __ffs(peers) - 1;
     uint32_t slot = 0, base = 0;
@@ -67,26 +93,49 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
       slot = hash_voxel(key, log2_size);
       for (;;) {
         u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
+        if (prev == kEmptyKey) created = true;
         if (prev == kEmptyKey || prev == key) break;
         slot = (slot + 1) & mask;
       }
       base = atomicAdd(&cells[slot].count, (uint32_t)__popc(peers));
+      my_slot = slot;
     }
     slot = __shfl_sync(peers, slot, leader);
     base = __shfl_sync(peers, base, leader);
     slot_of[i] = slot;
     rank_of[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   }
+  // occupied-slot list: block-wide count of newly claimed slots, ONE atomicAdd on the list cursor per block
+  const unsigned newb = __ballot_sync(0xffffffffu, created);
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) s_wnew[warp] = (uint32_t)__popc(newb);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_wnew[w];
+    s_obase = tot ? atomicAdd(&counters[4 + (gen & 1)], tot) : 0u;
+  }
+  __syncthreads();
+  if (created) {
+    uint32_t wb = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+      if (w < warp) wb += s_wnew[w];
+    occ[s_obase + wb + (uint32_t)__popc(newb & ((1u << lane) - 1u))] = my_slot;
+  }
 }
 
 // Every occupied slot gets a contiguous range of the sorted array (warp-aggregated atomicAdd on one cursor) and
 // the bounding box of occupied voxels is reduced per block (6 atomics per block instead of 6 per voxel).
-__global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* counters, int* bbox) {
+__global__ void grid_alloc_kernel(GridCell* cells, const uint32_t* __restrict__ occ, uint32_t* counters, int* bbox, int gen) {
   pdl_entry();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t size = counters[4 + (gen & 1)];  // occupied voxels of this build; the grid covers the upper bound n
   uint32_t cnt = 0;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-  if (i < size) {
+  const uint32_t i = li < size ? occ[li] : 0u;
+  if (li < size) {
     uint4 e = *reinterpret_cast<const uint4*>(cells + i);
     cnt = e.w;
     if (cnt) {
@@ -118,7 +167,7 @@ __global__ void grid_alloc_kernel(GridCell* cells, uint32_t size, uint32_t* coun
   }
   if (threadIdx.x == 0) s_base = btotal ? atomicAdd(&counters[0], btotal) : 0u;
   __syncthreads();
-  if (i < size && cnt) cells[i].start = s_base + wbase + inc - cnt;
+  if (li < size && cnt) cells[i].start = s_base + wbase + inc - cnt;
   // bounding box
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -221,23 +270,39 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
   int want_log2 = ilog2_ceil((uint32_t)(n_pts > 0 ? 2u * (uint32_t)n_pts : 2u));
   if (want_log2 < 10) want_log2 = 10;
   uint32_t want_size = 1u << want_log2;
+  const GridCell* cells_before = cells.p;
+  const uint32_t *occ_before = occ.p, *counters_before = counters.p;  // a reallocated list / counter loses the last build's record
   int rc;
   if ((rc = cells.reserve(want_size)) || (rc = sorted.reserve(n_pts + 1)) || (rc = orig.reserve(n_pts + 1)) ||
       (rc = slot_of.reserve(n_pts + 1)) || (rc = rank_of.reserve(n_pts + 1)) || (rc = bbox.reserve(8)) ||
-      (rc = counters.reserve(4)))
+      (rc = counters.reserve(8)) || (rc = occ.reserve(n_pts + 1)))
     return rc;
   log2_size = want_log2;
   table_size = want_size;
   const int T = 256;
-  ILSM_CUDA(launch_pdl(grid_clear_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, bbox.p, counters.p));
+  // Invariant: every slot of cells[0, clean_size) is EMPTY except the ones listed in occ[0, n_occ(previous build)).
+  // A build therefore only has to clear that list -- unless the table is new, or grew beyond the clean prefix.
+  const bool full_clear = gen == 0 || cells.p != cells_before || occ.p != occ_before || counters.p != counters_before ||
+                          (size_t)table_size > clean_size;
+  if (full_clear) {
+    ILSM_CUDA(launch_pdl(grid_clear_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, bbox.p, counters.p));
+    clean_size = table_size;
+  } else {
+    const int cover = prev_n > 8 ? prev_n : 8;  // the previous build's point count bounds its occupied-voxel count
+    ILSM_CUDA(launch_pdl(grid_clear_sparse_kernel, dim3((cover + T - 1) / T), dim3(T), 0, s, cells.p, (const uint32_t*)occ.p, bbox.p,
+                         counters.p, gen));
+  }
   if (n_pts > 0) {
     const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
     ILSM_CUDA(launch_pdl(grid_count_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, d_src, n_pts, stride_bytes / 4, ioff, inv_cell,
-                         cells.p, table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p, counters.p));
-    ILSM_CUDA(launch_pdl(grid_alloc_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, counters.p, bbox.p));
+                         cells.p, table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p, counters.p, occ.p, gen));
+    ILSM_CUDA(launch_pdl(grid_alloc_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, cells.p, (const uint32_t*)occ.p, counters.p, bbox.p,
+                         gen));
     ILSM_CUDA(launch_pdl(grid_scatter_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, (const float4*)orig.p, n_pts,
                          (const GridCell*)cells.p, (const uint32_t*)slot_of.p, (const uint32_t*)rank_of.p, sorted.p));
   }
+  prev_n = n_pts;
+  gen += 1;
   count_launches(n_pts > 0 ? 4 : 1);
   ILSM_CUDA(cudaEventRecord(ready, s));
   pending = true;
