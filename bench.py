@@ -412,10 +412,26 @@ def run_gpu(args, rank, world, local_rank):
         p_c, p_s = torch.from_numpy(h_c).pin_memory(), torch.from_numpy(h_s).pin_memory()
         n_mc, n_ms, n_c, n_s = p_mc.numpy(), p_ms.numpy(), p_c.numpy(), p_s.numpy()
 
+        # the C ABI called directly (ctypes), argument marshalling hoisted out of the loop: what a C++ caller pays
+        import ctypes as C
+        lib = ilsm.load_library()
+        vp = C.c_void_p
+        a_mc, a_ms, a_c, a_s = (vp(x.ctypes.data) for x in (n_mc, n_ms, n_c, n_s))
+        qq, tt = np.zeros(4), np.zeros(3)
+        a_q, a_t = vp(qq.ctypes.data), vp(tt.ctypes.data)
+        rep = ilsm.RegReport()
+        a_opts, a_rep = C.byref(opts), C.byref(rep)
+        len_mc, len_ms, len_c, len_s = len(n_mc), len(n_ms), len(n_c), len(n_s)
+        q0, t0 = np.asarray(c["q0"], np.float64), np.asarray(c["t0"], np.float64)
+
         def step_host():
-            mc.set_input_cloud(n_mc)
-            ms.set_input_cloud(n_ms)
-            return ctx.register(mc, ms, n_c, n_s, c["q0"], c["t0"], opts)
+            qq[:] = q0
+            tt[:] = t0
+            rc = lib.ilsm_map_build(mc._h, a_mc, len_mc, 16, 0.0) or lib.ilsm_map_build(ms._h, a_ms, len_ms, 16, 0.0) or \
+                lib.ilsm_register(ctx._h, mc._h, ms._h, a_c, len_c, a_s, len_s, 16, a_q, a_t, a_opts, a_rep)
+            if rc:
+                raise RuntimeError(lib.ilsm_last_error().decode())
+            return qq, tt, rep
 
         ctx.set_async(True)  # the two setInputCloud replacements overlap (see ilsm_set_async in include/ilsm.h)
         for _ in range(3):

@@ -22,6 +22,7 @@
 #ifndef ILSM_H_
 #define ILSM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -70,6 +71,12 @@ ILSM_API int ilsm_sync(ilsm_ctx* ctx);
 ILSM_API int ilsm_set_async(ilsm_ctx* ctx, int on);
 /* cudaStream_t of the context (for CUDA-event timing by the caller). */
 ILSM_API void* ilsm_stream(ilsm_ctx* ctx);
+
+/* Page-lock a caller-owned host buffer (e.g. the storage of a pcl::PointCloud or of a sensor_msgs/PointCloud2 that is
+ * reused from frame to frame) so that the host-pointer entry points copy from it by DMA instead of through a staging
+ * buffer; unregister before freeing it.  Optional: every entry point also accepts pageable memory. */
+ILSM_API int ilsm_host_register(void* ptr, size_t bytes);
+ILSM_API int ilsm_host_unregister(void* ptr);
 
 /* ------------------------------------------------------------------ K1: local map + exact k-NN ------- */
 ILSM_API int ilsm_map_create(ilsm_ctx* ctx, ilsm_map** out);

@@ -160,6 +160,8 @@ def load_library(path: str | None = None):
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_slam_frame_pc2": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_pc2_layout_ouster": (None, [C.POINTER(Pc2Layout)]),
+        "ilsm_host_register": (i32, [vp, C.c_size_t]),
+        "ilsm_host_unregister": (i32, [vp]),
         "ilsm_pc2_unpack": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
         "ilsm_pc2_unpack_dev": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
         "ilsm_ground_opts_default": (None, [C.POINTER(GroundOpts)]),

@@ -550,6 +550,17 @@ ILSM_API int ilsm_project_dev(ilsm_ctx* ctx, const float* d_xyzi, int H, int W, 
   return c.project_dev(d_xyzi, H * W, stride_bytes, d_range_img, d_inten_img, d_cloud_track_xyzi);
 }
 
+ILSM_API int ilsm_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return fail(ILSM_ERR_INVALID_ARG, "host_register: null / empty buffer");
+  ILSM_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return ILSM_OK;
+}
+ILSM_API int ilsm_host_unregister(void* ptr) {
+  if (!ptr) return fail(ILSM_ERR_INVALID_ARG, "host_unregister: null buffer");
+  ILSM_CUDA(cudaHostUnregister(ptr));
+  return ILSM_OK;
+}
+
 ILSM_API void ilsm_pc2_layout_ouster(ilsm_pc2_layout* l) {
   if (!l) return;
   memset(l, 0, sizeof(*l));

@@ -48,3 +48,15 @@ def test_cpp_host_mirror_parity(ilsm, oracle_mod, tmp_path):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all host-mirror checks passed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_replay_driver_matches_python_path(ilsm, tmp_path):
+    """tools/cpp/slam_replay.cpp (the full loop driven from C++ through the C ABI) gives bit-identical poses to the Python
+    binding on the same frames."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cpp_replay
+    out = cpp_replay.run(frames=12, sequences=1, out_dir=str(tmp_path))
+    assert out["pose_identical"], out
+    assert out["cpp"]["frames"] == 12 and out["cpp"]["frames_per_s"] > 100
