@@ -292,6 +292,24 @@ ILSM_API ilsm_cubemap* ilsm_slam_cubemap(ilsm_slam* slam);
 ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom_xyzw[4],
                              double t_odom[3], double q_map_xyzw[4], double t_map[3], ilsm_slam_stats* stats);
 
+/* The same loop with laserMapping as its own pipeline stage, the way the reference runs it as its own node: the cube map
+ * lives on a second context owned by the handle, and the process() iteration of frame k runs there while the caller's
+ * next call enqueues the front end and the odometry of frame k + 1.  ilsm_slam_frame_async returns the odometry pose of
+ * THIS frame and the mapped pose of the PREVIOUS one (*have_prev = 0 on the first call; stats->mapping / cubemap then
+ * also belong to the previous frame); ilsm_slam_flush collects the last frame's.  Pose for pose the results are those
+ * of ilsm_slam_frame (same kernels, same order within each stage). */
+ILSM_API int ilsm_slam_create_async(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                                    ilsm_slam** out);
+ILSM_API int ilsm_slam_frame_async(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom_xyzw[4],
+                                   double t_odom[3], double q_map_prev_xyzw[4], double t_map_prev[3], int* have_prev,
+                                   ilsm_slam_stats* stats);
+ILSM_API int ilsm_slam_flush(ilsm_slam* slam, double q_map_xyzw[4], double t_map[3], int* have, ilsm_slam_stats* stats);
+/* Profiling aid: host seconds spent per phase of ilsm_slam_frame[_async] since the last call of this function (reset on
+ * read): [0] upload + front-end launches, [1] wait for the previous frame's mapping (pipelined mode), [2] wait for the front
+ * end, [3] gathers / VoxelGrid / odometry launches, [4] wait for the odometry, [5] tree builds + mapping stage; pipelined mode:
+ * [6] launches and [7] waits of the mapping stage's own thread. */
+ILSM_API int ilsm_slam_host_phases(ilsm_slam* slam, double out8[8]);
+
 /* ------------------------------------------------------------------- scan-to-scan odometry (laserOdometry) ---- */
 
 /* One frame of the A-LOAM odometry optimisation.  last_corner / last_surf are maps built (ilsm_map_build) over the

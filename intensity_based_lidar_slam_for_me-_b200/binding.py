@@ -158,6 +158,10 @@ def load_library(path: str | None = None):
         "ilsm_slam_destroy": (None, [vp]),
         "ilsm_slam_cubemap": (vp, [vp]),
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
+        "ilsm_slam_create_async": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
+        "ilsm_slam_frame_async": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
+        "ilsm_slam_host_phases": (i32, [vp, vp]),
+        "ilsm_slam_flush": (i32, [vp, vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
         "ilsm_slam_frame_pc2": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_pc2_layout_ouster": (None, [C.POINTER(Pc2Layout)]),
         "ilsm_host_register": (i32, [vp, C.c_size_t]),
@@ -605,11 +609,15 @@ class Slam:
     the GPU.  frame() returns (q_odom, t_odom, q_map, t_map, stats)."""
 
     def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.8, min_range: float = 0.3,
-                 cube_capacity: int = 0, mapping: str = "laserMapping", voxel_leaf: float = 0.8, downsample_size: float = 0.4):
+                 cube_capacity: int = 0, mapping: str = "laserMapping", voxel_leaf: float = 0.8, downsample_size: float = 0.4,
+                 pipelined: bool = False):
         self._ctx = ctx
         self._lib = ctx._lib
         h = C.c_void_p()
-        if mapping == "laserMapping":
+        self.pipelined = bool(pipelined)
+        if mapping == "laserMapping" and pipelined:
+            _check(self._lib.ilsm_slam_create_async(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
+        elif mapping == "laserMapping":
             _check(self._lib.ilsm_slam_create(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
         elif mapping == "mapOptimization":
             _check(self._lib.ilsm_slam_create_mapopt(ctx._h, voxel_leaf, downsample_size, min_range, C.byref(h)))
@@ -644,6 +652,29 @@ class Slam:
         _check(self._lib.ilsm_slam_frame(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
                                          _ptr(tm), C.byref(st)))
         return qo, to, qm, tm, st
+
+    def frame_async(self, cloud, use_aloam: bool = True):
+        """Pipelined mode (ilsm_slam_create_async): returns (q_odom, t_odom) of THIS frame and (q_map, t_map) of the PREVIOUS
+        frame (None, None on the first call) while this frame's mapping keeps running on the GPU."""
+        a, n, stride = _cloud(cloud)
+        qo, to, qm, tm = np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3)
+        st, have = SlamStats(), C.c_int32(0)
+        _check(self._lib.ilsm_slam_frame_async(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
+                                               _ptr(tm), C.byref(have), C.byref(st)))
+        return (qo, to, qm, tm, st) if have.value else (qo, to, None, None, st)
+
+    def host_phases(self):
+        """Host seconds per phase since the last call (see ilsm_slam_host_phases)."""
+        out = np.zeros(8)
+        _check(self._lib.ilsm_slam_host_phases(self._h, _ptr(out)))
+        return out
+
+    def flush(self):
+        """Mapped pose of the last frame handed to frame_async (None, None when nothing is in flight)."""
+        qm, tm = np.zeros(4), np.zeros(3)
+        st, have = SlamStats(), C.c_int32(0)
+        _check(self._lib.ilsm_slam_flush(self._h, _ptr(qm), _ptr(tm), C.byref(have), C.byref(st)))
+        return (qm, tm, st) if have.value else (None, None, st)
 
     def frame_pc2(self, blob, layout: "Pc2Layout", use_aloam: bool = True):
         """One frame handed over as the sensor_msgs/PointCloud2 `data` blob (uint8, n_points * point_step bytes)."""

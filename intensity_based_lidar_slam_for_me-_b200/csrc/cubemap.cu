@@ -329,11 +329,15 @@ int CubeMapH::wait_tail() {
 using namespace ilsm;
 
 namespace ilsm {
-int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
-                       const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
-                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready,
-                       bool defer_tail, cudaEvent_t stacks_event) {
+// One process() iteration in two halves, so that the full-loop pipeline can leave the mapping of frame k running (on
+// the cube map's own context / stream) while the front end and the odometry of frame k + 1 are enqueued:
+//   cubemap_frame_enqueue : everything up to the deferred insertion -- no host synchronisation
+//   cubemap_frame_collect : waits for the pose, transformUpdate on the host, statistics
+int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
+                          const double q_wodom[4], const double t_wodom[3], const ilsm_reg_opts& o, bool stacks_ready,
+                          bool defer_tail, cudaEvent_t stacks_event) {
   Ctx& c = *m.ctx;
+  if (m.pend.active) return fail(ILSM_ERR_STATE, "cubemap: the previous frame has not been collected");
   {
     int rcw = m.wait_tail();
     if (rcw) return rcw;
@@ -397,6 +401,23 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
     ILSM_CUDA(cudaEventRecord(m.ev_tail, c.aux));
     m.tail_pending = true;
   }
+  m.pend.active = true, m.pend.qo = qo, m.pend.optimise = optimise, m.pend.n_mc = n_mc, m.pend.n_ms = n_ms;
+  m.pend.outer = o.outer_iterations, m.pend.defer_tail = defer_tail;
+  for (int i = 0; i < 3; ++i) m.pend.t_wodom[i] = t_wodom[i];
+  return ILSM_OK;
+}
+
+int cubemap_frame_collect(CubeMapH& m, double q_w[4], double t_w[3], ilsm_reg_report* report, ilsm_cubemap_stats* stats) {
+  Ctx& c = *m.ctx;
+  if (!m.pend.active) return fail(ILSM_ERR_STATE, "cubemap: no frame in flight");
+  m.pend.active = false;
+  const QuatH qo = m.pend.qo;
+  const double* t_wodom = m.pend.t_wodom;
+  const bool optimise = m.pend.optimise, defer_tail = m.pend.defer_tail;
+  const int n_mc = m.pend.n_mc, n_ms = m.pend.n_ms;
+  unsigned char* pin = c.pinned.p;
+  int* pin_i = m.pin.p + kCNum + 2048;
+  double r[3];
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
   pin_i[0] = m.tail_flags;  // capacity flags: of this frame when synchronous, up to the previous frame when deferred
   if (!defer_tail) pin_i[0] |= m.adopt_counts();
@@ -406,7 +427,7 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
   for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
   if (report && optimise) {
     memcpy(report, pin + 64, sizeof(*report));
-    report->passes = o.outer_iterations;
+    report->passes = m.pend.outer;
   }
   // transformUpdate (laserMapping.cpp:145-149)
   const QuatH qwf{q_w[0], q_w[1], q_w[2], q_w[3]};
@@ -430,6 +451,15 @@ int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, 
     return fail(ILSM_ERR_OUT_OF_MEMORY, msg);
   }
   return ILSM_OK;
+}
+
+int cubemap_frame_core(CubeMapH& m, const float* d_c, int nc, const float* d_s, int ns, int stride_bytes,
+                       const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
+                       const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready,
+                       bool defer_tail, cudaEvent_t stacks_event) {
+  int rc = cubemap_frame_enqueue(m, d_c, nc, d_s, ns, stride_bytes, q_wodom, t_wodom, o, stacks_ready, defer_tail, stacks_event);
+  if (rc) return rc;
+  return cubemap_frame_collect(m, q_w, t_w, report, stats);
 }
 }  // namespace ilsm
 

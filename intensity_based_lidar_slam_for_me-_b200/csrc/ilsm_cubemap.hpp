@@ -59,10 +59,21 @@ struct CubeMapH {
   cudaEvent_t ev_tail = nullptr;
   bool tail_pending = false, counts_in_flight = false;
   int tail_flags = 0;
+  struct Pending {  // a frame enqueued by cubemap_frame_enqueue and not yet collected
+    bool active = false, optimise = false, defer_tail = false;
+    QuatH qo{0, 0, 0, 1};
+    double t_wodom[3] = {0, 0, 0};
+    int n_mc = 0, n_ms = 0, outer = 2;
+  } pend;
 };
 
 
-// One iteration of process() (laserMapping.cpp:327-1002) with the feature clouds already on the device.
+// One iteration of process() (laserMapping.cpp:327-1002) with the feature clouds already on the device
+// (cubemap_frame_core = enqueue + collect).
+int cubemap_frame_enqueue(CubeMapH& m, const float* d_corner_last, int nc, const float* d_surf_last, int ns, int stride_bytes,
+                          const double q_wodom[4], const double t_wodom[3], const ilsm_reg_opts& o, bool stacks_ready,
+                          bool defer_tail, cudaEvent_t stacks_event = nullptr);
+int cubemap_frame_collect(CubeMapH& m, double q_w[4], double t_w[3], ilsm_reg_report* report, ilsm_cubemap_stats* stats);
 int cubemap_frame_core(CubeMapH& m, const float* d_corner_last, int nc, const float* d_surf_last, int ns, int stride_bytes,
                        const double q_wodom[4], const double t_wodom[3], double q_w[4], double t_w[3],
                        const ilsm_reg_opts& o, ilsm_reg_report* report, ilsm_cubemap_stats* stats, bool stacks_ready, bool defer_tail,

@@ -9,7 +9,10 @@
 // window indices, as the reference nodes do) and the mapped pose.
 #include <string.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <new>
+#include <thread>
 
 #include "ilsm_cubemap.hpp"
 
@@ -37,7 +40,98 @@ struct SlamH {
   double t_w_curr[3] = {0, 0, 0};
   float min_range = 0.3f;
   long long frames = 0;
+  // asynchronous mapping (ilsm_slam_create_async): the cube map lives on a second, owned context; the mapping of frame k
+  // runs there while the front end and the odometry of frame k + 1 run on the caller's context
+  ilsm_ctx* ctx2 = nullptr;
+  bool async = false, map_in_flight = false;
+  DevBuf<float4> lsharp2[2], lflat2[2];  // per-frame copies of the mapping stage's inputs (frame parity)
+  cudaEvent_t ev_fe[2] = {nullptr, nullptr};
+  // The mapping stage has its own host thread, like the reference's laserMapping node has its own process: its ~25
+  // launches per frame (3-4 us of host time each) are issued while the caller's thread launches the next front end.
+  struct MapJob {
+    int slot = 0, n_lsharp = 0, n_lflat = 0;
+    double q_odom[4] = {0, 0, 0, 1}, t_odom[3] = {0, 0, 0};
+  } job;
+  struct MapResult {
+    int rc = 0;
+    char err[256] = "";
+    double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
+    ilsm_reg_report report;
+    ilsm_cubemap_stats cstats;
+  } result;
+  std::thread worker;
+  std::mutex wmu;
+  std::condition_variable wcv;
+  bool job_posted = false, result_ready = false, stop = false;
+  // host-side phase clock (profiling aid, read with ilsm_slam_host_phases): seconds accumulated per phase
+  double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+struct PhaseClock {
+  double* acc;
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseClock(double* a) : acc(a), t(std::chrono::steady_clock::now()) {}
+  void lap(int k) {
+    const auto n = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double>(n - t).count();
+    t = n;
+  }
+};
+
+// body of the mapping stage's thread: one process() iteration per posted job, enqueue + collect on the second context
+static void mapping_worker(SlamH* sp) {
+  SlamH& s = *sp;
+  Ctx& c2 = s.ctx2->c;
+  cudaSetDevice(c2.device);
+  for (;;) {
+    SlamH::MapJob j;
+    {
+      std::unique_lock<std::mutex> lk(s.wmu);
+      s.wcv.wait(lk, [&] { return s.job_posted || s.stop; });
+      if (s.stop) return;
+      j = s.job;
+      s.job_posted = false;
+    }
+    SlamH::MapResult r;
+    {
+      std::lock_guard<std::mutex> lk2(c2.mu);
+      ilsm_reg_opts mo;
+      ilsm_reg_opts_default(&mo);
+      memset(&r.report, 0, sizeof(r.report)), memset(&r.cstats, 0, sizeof(r.cstats));
+      cudaError_t e = cudaStreamWaitEvent(c2.stream, s.ev_fe[j.slot], 0);
+      r.rc = e == cudaSuccess ? ILSM_OK : fail_cuda(e, "cudaStreamWaitEvent(mapping stage)");
+      PhaseClock wclk(s.phase_s);  // [6] mapping-stage launches, [7] wait for the mapped pose (written by this thread only)
+      if (!r.rc)
+        r.rc = cubemap_frame_enqueue(s.cube->m, reinterpret_cast<const float*>(s.lsharp2[j.slot].p), j.n_lsharp,
+                                     reinterpret_cast<const float*>(s.lflat2[j.slot].p), j.n_lflat, 16, j.q_odom, j.t_odom, mo, true, true,
+                                     s.ctx->ev_join);  // the stacks come from the caller's side stream (under its odometry)
+      wclk.lap(6);
+      if (!r.rc) r.rc = cubemap_frame_collect(s.cube->m, r.q, r.t, &r.report, &r.cstats);
+      wclk.lap(7);
+      if (r.rc) snprintf(r.err, sizeof(r.err), "%s", ilsm_last_error());  // the error text is thread-local: carry it over
+    }
+    {
+      std::lock_guard<std::mutex> lk(s.wmu);
+      s.result = r;
+      s.result_ready = true;
+    }
+    s.wcv.notify_all();
+  }
+}
+
+// wait for the mapping stage's answer to the job in flight and hand it out
+static int take_mapping_result(SlamH& s, double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+  std::unique_lock<std::mutex> lk(s.wmu);
+  s.wcv.wait(lk, [&] { return s.result_ready; });
+  s.result_ready = false;
+  s.map_in_flight = false;
+  const SlamH::MapResult& r = s.result;
+  if (r.rc) return fail(r.rc, r.err);
+  for (int i = 0; i < 4; ++i) q_map[i] = r.q[i];
+  for (int i = 0; i < 3; ++i) t_map[i] = r.t[i];
+  if (stats) stats->mapping = r.report, stats->cubemap = r.cstats;
+  return ILSM_OK;
+}
 
 }  // namespace ilsm
 
@@ -94,18 +188,59 @@ ILSM_API int ilsm_slam_create_mapopt(ilsm_ctx* ctx, float voxel_leaf, float down
   return ILSM_OK;
 }
 
+ILSM_API int ilsm_slam_create_async(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                                    ilsm_slam** out) {
+  ilsm_slam* h = nullptr;
+  int rc = slam_create_common(ctx, min_range, out, &h);
+  if (rc) return rc;
+  h->s.async = true;
+  if ((rc = ilsm_create(ctx->c.device, &h->s.ctx2)) ||
+      (rc = ilsm_cubemap_create(h->s.ctx2, line_res, plane_res, cube_capacity, &h->s.cube))) {
+    ilsm_slam_destroy(h);
+    return rc;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&h->s.ev_fe[i], cudaEventDisableTiming) != cudaSuccess) {
+      ilsm_slam_destroy(h);
+      return fail(ILSM_ERR_CUDA, "slam_create_async: event creation failed");
+    }
+  h->s.worker = std::thread(mapping_worker, &h->s);
+  *out = h;
+  return ILSM_OK;
+}
+
 ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
   if (!slam) return;
   SlamH& s = slam->s;
+  if (s.worker.joinable()) {
+    {
+      std::unique_lock<std::mutex> lk(s.wmu);
+      s.wcv.wait(lk, [&] { return !s.job_posted; });  // a posted job is taken (and finished) before the thread is told to stop
+      s.stop = true;
+    }
+    s.wcv.notify_all();
+    s.worker.join();
+  }
+  if (s.ctx2) {  // let the mapping stage drain before anything it reads goes away
+    std::lock_guard<std::mutex> lk2(s.ctx2->c.mu);
+    cudaSetDevice(s.ctx2->c.device);
+    cudaStreamSynchronize(s.ctx2->c.stream);
+    cudaStreamSynchronize(s.ctx2->c.aux);
+  }
   {
     std::lock_guard<std::mutex> lk(s.ctx->mu);
     cudaSetDevice(s.ctx->device);
     cudaStreamSynchronize(s.ctx->stream);
     s.last_corner.release(), s.last_surf.release();
     s.sharp.release(), s.flat.release(), s.lsharp.release();
+    for (int i = 0; i < 2; ++i) {
+      s.lsharp2[i].release(), s.lflat2[i].release();
+      if (s.ev_fe[i]) cudaEventDestroy(s.ev_fe[i]);
+    }
   }
   if (s.cube) ilsm_cubemap_destroy(s.cube);
   if (s.mapopt) ilsm_mapopt_destroy(s.mapopt);
+  if (s.ctx2) ilsm_destroy(s.ctx2);
   delete slam;
 }
 
@@ -118,7 +253,8 @@ int check_pc2_layout(const ilsm_pc2_layout* l);  // api.cu
 }
 // pc2 != nullptr: `xyzi` is a sensor_msgs/PointCloud2 data blob, unpacked on the device into packed points
 static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, const ilsm_pc2_layout* pc2, int use_aloam,
-                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats);
+                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats,
+                           int* have_prev = nullptr);
 extern "C" {
 
 ILSM_API int ilsm_slam_frame(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom[4],
@@ -136,18 +272,43 @@ ILSM_API int ilsm_slam_frame_pc2(ilsm_slam* slam, const uint8_t* data, int n_poi
                          q_map, t_map, stats);
 }
 
+ILSM_API int ilsm_slam_frame_async(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam, double q_odom[4],
+                                   double t_odom[3], double q_map_prev[4], double t_map_prev[3], int* have_prev,
+                                   ilsm_slam_stats* stats) {
+  if (n < 0 || stride_bytes < 12 || stride_bytes % 4) return fail(ILSM_ERR_INVALID_ARG, "slam_frame_async: bad n/stride");
+  if (!have_prev) return fail(ILSM_ERR_INVALID_ARG, "slam_frame_async: null have_prev");
+  return slam_frame_impl(slam, xyzi, n, stride_bytes, nullptr, use_aloam, q_odom, t_odom, q_map_prev, t_map_prev, stats, have_prev);
+}
+
+ILSM_API int ilsm_slam_flush(ilsm_slam* slam, double q_map[4], double t_map[3], int* have, ilsm_slam_stats* stats) {
+  if (!slam || !q_map || !t_map || !have) return fail(ILSM_ERR_INVALID_ARG, "slam_flush: null argument");
+  SlamH& s = slam->s;
+  *have = 0;
+  if (!s.async || !s.map_in_flight) return ILSM_OK;
+  std::lock_guard<std::mutex> lk(s.ctx->mu);
+  int rc = take_mapping_result(s, q_map, t_map, stats);
+  if (rc) return rc;
+  *have = 1;
+  return ILSM_OK;
+}
+
 }  // extern "C"
 
 static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, const ilsm_pc2_layout* pc2, int use_aloam,
-                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+                           double q_odom[4], double t_odom[3], double q_map[4], double t_map[3], ilsm_slam_stats* stats,
+                           int* have_prev) {
   if (!slam || (n > 0 && !xyzi) || !q_odom || !t_odom || !q_map || !t_map)
     return fail(ILSM_ERR_INVALID_ARG, "slam_frame: null argument");
   SlamH& s = slam->s;
+  if (s.async != (have_prev != nullptr))
+    return fail(ILSM_ERR_STATE, "slam_frame: ilsm_slam_create_async handles take ilsm_slam_frame_async (and only those)");
+  if (have_prev) *have_prev = 0;
   Ctx& c = *s.ctx;
   std::lock_guard<std::mutex> lk(c.mu);
   ILSM_CUDA(cudaSetDevice(c.device));
   if (stats) memset(stats, 0, sizeof(*stats));
   int rc;
+  PhaseClock clk(s.phase_s);
   // ---- scanRegistration: the frame is the only upload
   const size_t bytes = (size_t)n * stride_bytes;
   if ((rc = c.fe.raw.reserve((pc2 ? (size_t)n * 4 : bytes / 4) + 4))) return rc;
@@ -163,31 +324,51 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
     ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
   }
   if ((rc = c.features_dev(c.fe.raw.p, n, stride_bytes, s.min_range))) return rc;
+  clk.lap(0);  // upload + front-end launches
+  if (s.async && s.map_in_flight) {
+    // the previous frame's mapped pose: the mapping stage's thread has had the whole of this call so far
+    if ((rc = take_mapping_result(s, q_map, t_map, stats))) return rc;
+    *have_prev = 1;
+  }
+  clk.lap(1);  // (pipelined) wait for the previous frame's mapping
   int* pin = reinterpret_cast<int*>(c.pinned.p);
   ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  clk.lap(2);  // wait for the front end (feature counts)
   const int n_sharp = pin[1], n_lsharp = pin[2], n_flat = pin[3], n_lflat = pin[4];
   if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: a ring segment exceeds the supported size");
   if (stats) {
     stats->n_cloud = pin[0], stats->n_sharp = n_sharp, stats->n_less_sharp = n_lsharp, stats->n_flat = n_flat;
     stats->n_less_flat = n_lflat;
   }
-  if ((rc = s.sharp.reserve(n_sharp + 4)) || (rc = s.flat.reserve(n_flat + 4)) || (rc = s.lsharp.reserve(n_lsharp + 4))) return rc;
+  // the mapping stage's inputs: in asynchronous mode they are per-frame copies (frame parity), because the mapping of this
+  // frame still reads them while the next frame's front end runs
+  const int slot = (int)(s.frames & 1);
+  DevBuf<float4>& lsharp_buf = s.async ? s.lsharp2[slot] : s.lsharp;
+  if ((rc = s.sharp.reserve(n_sharp + 4)) || (rc = s.flat.reserve(n_flat + 4)) || (rc = lsharp_buf.reserve(n_lsharp + 4))) return rc;
+  if (s.async && (rc = s.lflat2[slot].reserve(n_lflat + 4))) return rc;
+  float4* const d_lsharp = lsharp_buf.p;
   if ((rc = c.gather_dev(c.fe.cloud.p, c.fe.sharp.p, c.fe.counts.p, 1, n_sharp, s.sharp.p)) ||
-      (rc = c.gather_dev(c.fe.cloud.p, c.fe.lsharp.p, c.fe.counts.p, 2, n_lsharp, s.lsharp.p)) ||
+      (rc = c.gather_dev(c.fe.cloud.p, c.fe.lsharp.p, c.fe.counts.p, 2, n_lsharp, d_lsharp)) ||
       (rc = c.gather_dev(c.fe.cloud.p, c.fe.flat.p, c.fe.counts.p, 3, n_flat, s.flat.p)))
     return rc;
+  if (s.async) {
+    if (n_lflat) ILSM_CUDA(cudaMemcpyAsync(s.lflat2[slot].p, c.fe.lflat.p, (size_t)n_lflat * sizeof(float4), cudaMemcpyDeviceToDevice, c.stream));
+    ILSM_CUDA(cudaEventRecord(s.ev_fe[slot], c.stream));
+  }
   // ---- the mapping stacks (VoxelGrid of the less-sharp / less-flat clouds, laserMapping.cpp:608-616) depend only on the
   // front end: they run on the side stream while the odometry solves on the main one
   if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
   CubeMapH* cmp = s.cube ? &s.cube->m : nullptr;
   if (cmp) {
-    CubeMapH& cm = *cmp;
+    CubeMapH& cm = *cmp;  // (pipelined mode: the mapping thread is idle here -- its previous result has been taken above)
     if ((rc = cm.stack_c.reserve(n_lsharp + 4)) || (rc = cm.stack_s.reserve(n_lflat + 4))) return rc;
     ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
     ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
+    // pipelined mode: the previous frame's deferred insertion (second context's side stream) still reads the stacks
+    if (s.async && cm.tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.aux, cm.ev_tail, 0));
     ILSM_CUDA(cudaMemsetAsync(cm.stack_n.p, 0, 4 * sizeof(int), c.aux));
-    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, cm.line_res, cm.stack_c.p,
+    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(d_lsharp), n_lsharp, cm.line_res, cm.stack_c.p,
                                    reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
                                    cm.stack_n.p, c.aux)))
       return rc;
@@ -196,7 +377,7 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   // ---- laserOdometry
   // the previous frame's deferred map insertion (side stream) reads the mapped pose from the LM state the odometry is
   // about to overwrite: order the main stream after it (long finished by now -- it overlapped this frame's front end)
-  if (cmp && cmp->tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.stream, cmp->ev_tail, 0));
+  if (cmp && !s.async && cmp->tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.stream, cmp->ev_tail, 0));
   if (!s.inited) {
     s.inited = true;
   } else {
@@ -213,7 +394,9 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
       unsigned char* pb = c.pinned.p;
       ILSM_CUDA(cudaMemcpyAsync(pb, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
       ILSM_CUDA(cudaMemcpyAsync(pb + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+      clk.lap(3);  // gathers, stack VoxelGrid, odometry launches
       ILSM_CUDA(cudaStreamSynchronize(c.stream));
+      clk.lap(4);  // wait for the odometry
       const double* o7 = reinterpret_cast<const double*>(pb);
       for (int i = 0; i < 4; ++i) s.para_q[i] = o7[i];
       for (int i = 0; i < 3; ++i) s.para_t[i] = o7[4 + i];
@@ -232,14 +415,26 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   q_odom[0] = s.q_w_curr.x, q_odom[1] = s.q_w_curr.y, q_odom[2] = s.q_w_curr.z, q_odom[3] = s.q_w_curr.w;
   for (int i = 0; i < 3; ++i) t_odom[i] = s.t_w_curr[i];
   // laserCloudCornerLast = cornerPointsLessSharp, laserCloudSurfLast = surfPointsLessFlat; rebuild both trees (:793-808)
-  if ((rc = s.last_corner.build_dev(reinterpret_cast<const float*>(s.lsharp.p), n_lsharp, 16, kOdomCell)) ||
+  if ((rc = s.last_corner.build_dev(reinterpret_cast<const float*>(d_lsharp), n_lsharp, 16, kOdomCell)) ||
       (rc = s.last_surf.build_dev(reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
     return rc;
   // ---- mapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
-  if (cmp) {  // laserMapping: rolling cube map
+  if (s.async) {
+    // laserMapping as its own stage (the reference runs it as its own node): hand this frame to the mapping thread and
+    // return; its mapped pose is collected by the next call (or by ilsm_slam_flush)
+    {
+      std::lock_guard<std::mutex> lkw(s.wmu);
+      s.job.slot = slot, s.job.n_lsharp = n_lsharp, s.job.n_lflat = n_lflat;
+      for (int i = 0; i < 4; ++i) s.job.q_odom[i] = q_odom[i];
+      for (int i = 0; i < 3; ++i) s.job.t_odom[i] = t_odom[i];
+      s.job_posted = true;
+      s.map_in_flight = true;
+    }
+    s.wcv.notify_all();
+  } else if (cmp) {  // laserMapping: rolling cube map
     ilsm_reg_opts mo;
     ilsm_reg_opts_default(&mo);
-    rc = cubemap_frame_core(*cmp, reinterpret_cast<const float*>(s.lsharp.p), n_lsharp,
+    rc = cubemap_frame_core(*cmp, reinterpret_cast<const float*>(d_lsharp), n_lsharp,
                             reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, q_odom, t_odom, q_map, t_map, mo,
                             stats ? &stats->mapping : nullptr, stats ? &stats->cubemap : nullptr, true, true, c.ev_join);
   } else {    // mapOptimization: ground extraction from the frame already on the device + the less-flat cloud
@@ -255,7 +450,14 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
       stats->cubemap.n_valid = ms.converged;
     }
   }
+  clk.lap(5);  // tree builds + mapping stage (synchronous: enqueue and wait; pipelined: enqueue only)
   if (rc) return rc;
   s.frames++;
+  return ILSM_OK;
+}
+
+extern "C" ILSM_API int ilsm_slam_host_phases(ilsm_slam* slam, double out8[8]) {
+  if (!slam || !out8) return fail(ILSM_ERR_INVALID_ARG, "slam_host_phases: null argument");
+  for (int i = 0; i < 8; ++i) out8[i] = slam->s.phase_s[i], slam->s.phase_s[i] = 0;
   return ILSM_OK;
 }

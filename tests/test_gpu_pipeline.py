@@ -139,3 +139,35 @@ def test_pipeline_survives_degenerate_frames(ctx, ilsm, mapping):
     qo, to, qm, tm, st = slam.frame(np.zeros((0, 4), np.float32))
     assert st.n_cloud == 0
     slam.close()
+
+
+def test_pipelined_mapping_stage_gives_the_same_poses(ctx, ilsm):
+    """ilsm_slam_create_async: laserMapping as its own stage on a second context (frame k's mapping overlaps frame k+1's
+    front end + odometry).  Odometry poses frame for frame and mapped poses one call later are bit-identical to the
+    synchronous loop; misuse of the two handle kinds is rejected."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from sequence_bench import corridor_sequence
+    clouds, _ = corridor_sequence(ilsm.synth, 14, 0x5EED0100, 40.0)
+    a = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096)
+    b = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096, pipelined=True)
+    sync = [a.frame(c) for c in clouds]
+    mapped = []
+    for k, c in enumerate(clouds):
+        qo, to, qm, tm, st = b.frame_async(c)
+        assert np.array_equal(qo, sync[k][0]) and np.array_equal(to, sync[k][1])
+        assert (qm is None) == (k == 0)
+        if qm is not None:
+            mapped.append((qm, tm, st.mapping.pass_[1].num_plane_factors))
+    qm, tm, st = b.flush()
+    mapped.append((qm, tm, st.mapping.pass_[1].num_plane_factors))
+    assert b.flush()[0] is None
+    assert len(mapped) == len(clouds)
+    for k in range(len(clouds)):
+        assert np.array_equal(mapped[k][0], sync[k][2]) and np.array_equal(mapped[k][1], sync[k][3]), k
+        assert mapped[k][2] == sync[k][4].mapping.pass_[1].num_plane_factors
+    with pytest.raises(ilsm.IlsmError):
+        b.frame(clouds[0])
+    with pytest.raises(ilsm.IlsmError):
+        a.frame_async(clouds[0])
+    a.close(), b.close()

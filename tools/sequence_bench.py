@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--frames", type=int, default=200)
     ap.add_argument("--oracle-frames", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--pipelined", action="store_true",
+                    help="laserMapping as its own stage (ilsm_slam_create_async): frame k's mapping overlaps frame k+1's front "
+                         "end + odometry; the mapped pose of a frame comes back one call later")
     ap.add_argument("--sequences-per-gpu", type=int, default=1,
                     help="independent sequences replayed concurrently on each GPU (one context / stream / host thread each)")
     ap.add_argument("--mapping", default="laserMapping", choices=["laserMapping", "mapOptimization"],
@@ -74,25 +77,39 @@ def main():
     ctx = ilsm.Context(local)
 
     def run(n, keep=False, slam=None):
-        slam = slam or ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping)
+        slam = slam or ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping, pipelined=args.pipelined)
         out, times = [], []
         for k in range(n):
             t0 = time.perf_counter()
-            qo, to, qm, tm, st = slam.frame(views[k])
+            if args.pipelined:
+                qo, to, qm, tm, st = slam.frame_async(views[k])
+                if keep and k > 0:
+                    out[-1] = out[-1][:2] + (qm, tm)  # the mapped pose belongs to the previous frame
+                qm = tm = None
+            else:
+                qo, to, qm, tm, st = slam.frame(views[k])
             times.append(time.perf_counter() - t0)
             if keep:
                 out.append((qo, to, qm, tm))
+        if args.pipelined and n:
+            t0 = time.perf_counter()
+            qm, tm, st = slam.flush()
+            times[-1] += time.perf_counter() - t0
+            if keep:
+                out[-1] = out[-1][:2] + (qm, tm)
         return out, times, slam
 
     run(min(args.warmup, F))[2].close()
-    slam_timed = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping)  # the 2 x 4851 x 8192-point cube slabs are allocated outside the timed region
+    slam_timed = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, mapping=args.mapping, pipelined=args.pipelined)  # the 2 x 4851 x 8192-point cube slabs are allocated outside the timed region
     ctx.sync()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = ilsm.launch_count()
     t0 = time.perf_counter()
+    slam_timed.host_phases()
     est, times, _ = run(F, keep=True, slam=slam_timed)
+    phases = slam_timed.host_phases()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     slam_timed.close()  # freeing the 2.5 GB of cube slabs is not part of the per-frame loop
@@ -142,10 +159,13 @@ def main():
             tr = R0.T @ (poses[k][1] - t0p)
             err.append(np.linalg.norm(est[k][3] - tr))
         line = {"metric": "full odometry+mapping loop, frames/s (synthetic OS0-64 corridor)", "value": world * SPG * F / wall_max,
-                "unit": "frames/s", "n_gpus": world, "sequences_per_gpu": SPG, "mapping": args.mapping, "frames_per_sequence": F, "ms_per_frame": 1e3 * wall_max / (F * SPG),
+                "unit": "frames/s", "n_gpus": world, "sequences_per_gpu": SPG, "pipelined": bool(args.pipelined), "mapping": args.mapping, "frames_per_sequence": F, "ms_per_frame": 1e3 * wall_max / (F * SPG),
                 "ms_per_frame_median": 1e3 * float(np.median(times)), "scaling": "weak",
                 "h2d_bytes_per_frame": int(clouds[0].nbytes), "d2h_bytes_per_frame": 2 * 56 + 400,
-                "gpu_launches_per_frame": launches / F, "ate_rmse_m": float(np.sqrt(np.mean(np.square(err)))),
+                "gpu_launches_per_frame": launches / F,
+                "host_phase_us_per_frame": dict(zip(["upload+fe_launch", "wait_prev_mapping", "wait_front_end", "odometry_launch",
+                                                     "wait_odometry", "trees+mapping", "mapping_thread_launch", "mapping_thread_wait"],
+                                                    [round(1e6 * x / F, 1) for x in phases[:8]])), "ate_rmse_m": float(np.sqrt(np.mean(np.square(err)))),
                 "final_position_error_m": float(err[-1]),
                 "slowest_frames_ms": [[int(i), round(1e3 * times[i], 3)] for i in np.argsort(times)[::-1][:6]],
                 "timing": "host wall clock around ilsm_slam_frame (blocking), H2D of the frame and D2H of the poses inside"}
