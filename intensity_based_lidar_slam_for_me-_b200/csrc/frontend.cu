@@ -7,6 +7,8 @@
 // Everything here is streaming / small-sort work bound by HBM bandwidth and launch latency; no tensor cores.
 // Float arithmetic that feeds integer decisions (ring id, curvature order, labels, voxel index) uses explicit
 // round-to-nearest intrinsics in the reference's evaluation order (x86-64 SSE2, no FMA).
+#include <string.h>
+
 #include "ilsm_host.hpp"
 #include "ilsm_voxel.cuh"
 
@@ -841,6 +843,12 @@ int Ctx::project_dev(const float* d_cloud, int n, int stride_bytes, unsigned cha
   return check_launch("project");
 }
 
+static inline unsigned __float_as_uint_host(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
 int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_range) {
   int rc;
   FeBufs& f = fe;
@@ -857,6 +865,49 @@ int Ctx::features_dev(const float* d_in, int n, int stride_bytes, float min_rang
     return rc;
   f.n_in = n;
   f.ring_cap = ring_cap;
+  // The chain is 10 short kernels whose launch parameters only depend on (input pointer, n, stride, min_range) and on the
+  // scratch pointers: it is captured once into a CUDA graph (programmatic-dependent-launch edges included) and replayed
+  // with ONE launch call per frame -- 10 launches cost ~32 us of host time, the replay ~8.  Any change of a parameter
+  // or a reallocated scratch buffer re-captures.
+  unsigned long long key = 1469598103934665603ull;
+  auto mix = [&key](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+  mix((unsigned long long)(uintptr_t)d_in), mix((unsigned long long)n), mix((unsigned long long)stride_bytes), mix((unsigned long long)ring_cap);
+  mix((unsigned long long)__float_as_uint_host(min_range));
+  const void* ptrs[] = {f.scanid.p, f.ori.p, f.stats.p, f.cloud.p, f.src_index.p, f.curv.p, f.label.p, f.picked.p, f.sort_ind.p,
+                        f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p, f.ring_pts.p, f.ring_out.p, f.sharp.p, f.lsharp.p, f.flat.p,
+                        f.lflat.p, f.counts.p, f.chunk_hist.p, f.chunk_base.p};
+  for (const void* q : ptrs) mix((unsigned long long)(uintptr_t)q);
+  if (fe_graph_exec && key == fe_graph_key) {
+    ILSM_CUDA(cudaGraphLaunch(fe_graph_exec, stream));
+    count_launches(n > 0 ? 10 : 2);
+    return check_launch("extract_features(graph)");
+  }
+  bool capturing = false;
+  if (fe_graphs_ok) {
+    if (fe_graph_exec) cudaGraphExecDestroy(fe_graph_exec), fe_graph_exec = nullptr;
+    capturing = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (!capturing) cudaGetLastError(), fe_graphs_ok = false;
+  }
+  int rcl = features_launch(d_in, n, stride_bytes, min_range, ring_cap);
+  if (capturing) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(stream, &g);
+    if (e == cudaSuccess && rcl == ILSM_OK) e = cudaGraphInstantiate(&fe_graph_exec, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess || rcl != ILSM_OK || !fe_graph_exec) {  // capture not possible here: plain launches from now on
+      cudaGetLastError();
+      fe_graph_exec = nullptr, fe_graphs_ok = false;
+      return features_launch(d_in, n, stride_bytes, min_range, ring_cap);
+    }
+    fe_graph_key = key;
+    ILSM_CUDA(cudaGraphLaunch(fe_graph_exec, stream));
+    return check_launch("extract_features(graph)");
+  }
+  return rcl;
+}
+
+int Ctx::features_launch(const float* d_in, int n, int stride_bytes, float min_range, int ring_cap) {
+  FeBufs& f = fe;
   const int stride_f = stride_bytes / 4;
   const int T = 256, B = (n + T - 1) / T;
   ILSM_CUDA(launch_pdl(fe_init_kernel, dim3(1), dim3(352), 0, stream, f.stats.p));

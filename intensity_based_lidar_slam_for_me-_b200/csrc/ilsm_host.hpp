@@ -226,6 +226,10 @@ struct Ctx {
   int project_dev(const float* d_cloud, int n, int stride_bytes, unsigned char* d_range, unsigned char* d_inten,
                   float* d_track);
   int features_dev(const float* d_in, int n, int stride_bytes, float min_range);
+  int features_launch(const float* d_in, int n, int stride_bytes, float min_range, int ring_cap);  // the 10 plain launches
+  cudaGraphExec_t fe_graph_exec = nullptr;  // the captured front-end chain and the parameter hash it was captured for
+  unsigned long long fe_graph_key = 0;
+  bool fe_graphs_ok = true;                 // false after a failed capture: plain launches from then on
   int pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layout& l, float4* d_out);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);

@@ -325,16 +325,16 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   }
   if ((rc = c.features_dev(c.fe.raw.p, n, stride_bytes, s.min_range))) return rc;
   clk.lap(0);  // upload + front-end launches
-  if (s.async && s.map_in_flight) {
-    // the previous frame's mapped pose: the mapping stage's thread has had the whole of this call so far
-    if ((rc = take_mapping_result(s, q_map, t_map, stats))) return rc;
-    *have_prev = 1;
-  }
-  clk.lap(1);  // (pipelined) wait for the previous frame's mapping
   int* pin = reinterpret_cast<int*>(c.pinned.p);
   ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
   clk.lap(2);  // wait for the front end (feature counts)
+  if (s.async && s.map_in_flight) {
+    // the previous frame's mapped pose: the mapping stage's thread has had this frame's upload and front end to finish
+    if ((rc = take_mapping_result(s, q_map, t_map, stats))) return rc;
+    *have_prev = 1;
+  }
+  clk.lap(1);  // (pipelined) wait for the previous frame's mapping
   const int n_sharp = pin[1], n_lsharp = pin[2], n_flat = pin[3], n_lflat = pin[4];
   if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: a ring segment exceeds the supported size");
   if (stats) {
