@@ -438,11 +438,11 @@ def run_gpu(args, rank, world, local_rank):
         rep = ilsm.RegReport()
         a_opts, a_rep = C.byref(opts), C.byref(rep)
         len_mc, len_ms, len_c, len_s = len(n_mc), len(n_ms), len(n_c), len(n_s)
-        q0, t0 = np.asarray(c["q0"], np.float64), np.asarray(c["t0"], np.float64)
+        q_init, t_init = np.asarray(c["q0"], np.float64).copy(), np.asarray(c["t0"], np.float64).copy()
 
         def step_host():
-            qq[:] = q0
-            tt[:] = t0
+            qq[:] = q_init
+            tt[:] = t_init
             rc = lib.ilsm_map_build(mc._h, a_mc, len_mc, 16, 0.0) or lib.ilsm_map_build(ms._h, a_ms, len_ms, 16, 0.0) or \
                 lib.ilsm_register(ctx._h, mc._h, ms._h, a_c, len_c, a_s, len_s, 16, a_q, a_t, a_opts, a_rep)
             if rc:
