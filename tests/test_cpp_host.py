@@ -60,3 +60,6 @@ def test_cpp_replay_driver_matches_python_path(ilsm, tmp_path):
     out = cpp_replay.run(frames=12, sequences=1, out_dir=str(tmp_path))
     assert out["pose_identical"], out
     assert out["cpp"]["frames"] == 12 and out["cpp"]["frames_per_s"] > 100
+    # and with laserMapping as its own pipeline stage (ilsm_slam_frame_async + ilsm_slam_flush): the same final poses
+    out = cpp_replay.run(frames=12, sequences=1, out_dir=str(tmp_path), pipelined=True)
+    assert out["pose_identical"] and out["cpp"]["pipelined"] == 1, out

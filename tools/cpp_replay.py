@@ -31,7 +31,7 @@ def build_driver(out_dir):
     return exe
 
 
-def run(frames=150, sequences=1, out_dir=None):
+def run(frames=150, sequences=1, out_dir=None, pipelined=False):
     import ilsm_b200 as ilsm
     from sequence_bench import corridor_sequence
     ilsm._build.build()
@@ -40,10 +40,11 @@ def run(frames=150, sequences=1, out_dir=None):
     path = os.path.join(out_dir, "frames.bin")
     np.stack(clouds).astype(np.float32).tofile(path)
     exe = build_driver(out_dir)
-    r = subprocess.run([exe, path, str(sequences)], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, path, str(sequences), "1" if pipelined else "0"], capture_output=True, text=True, timeout=600)
     if r.returncode != 0:
         raise RuntimeError(r.stdout + r.stderr)
     cpp = json.loads(r.stdout.strip().splitlines()[-1])
+    cpp["host_phases"] = r.stderr.strip().splitlines()[-1] if r.stderr.strip() else ""
     # the same replay through the Python binding
     ctx = ilsm.Context(0)
     slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
@@ -66,5 +67,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=150)
     ap.add_argument("--sequences", type=int, default=1)
+    ap.add_argument("--pipelined", action="store_true")
     a = ap.parse_args()
-    print(json.dumps(run(a.frames, a.sequences)))
+    print(json.dumps(run(a.frames, a.sequences, pipelined=a.pipelined)))
