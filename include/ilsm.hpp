@@ -14,6 +14,7 @@
 //   process()                     laserMapping.cpp:233-1166                 ilsm::LaserMapping
 //   mapOptimizationCallback       mapOptimization.cpp:99-500                ilsm::MapOptimization
 //   callback() (odometry merge)   odom_handler_node.cpp:44-132              ilsm::OdomHandler (host arithmetic only)
+//   nh.param / getParam           spot.yaml + spot.launch:4-6               ilsm::Config (load_yaml / load_launch)
 //
 // Nothing here computes: every method forwards to libilsm_cuda.so (CUDA, sm_100a).  There is no CPU fallback; without a
 // GPU the Context constructor throws ilsm::Error(ILSM_ERR_NO_DEVICE).
@@ -31,6 +32,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -543,6 +545,90 @@ class MapOptimization {
  private:
   ContextPtr ctx_;
   ilsm_mapopt* mo_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------ parameters
+// The keys the reference's nodes read from the ROS parameter server (config/spot.yaml + launch/spot.launch:4-6), for a build
+// without ROS: a two-level "key: value  # comment" reader that accepts the reference's own spot.yaml unchanged, and a
+// <param name= value=> reader for its launch file.  Defaults = the reference's nh.param defaults.
+struct Config {
+  int image_width = 1024;                  // /intensity_feature_tracker/image_width     mapOptimization.cpp:522
+  int image_height = 64;                   // /intensity_feature_tracker/image_height    scanRegistration.cpp:692 (N_SCANS)
+  double minimum_range = 0.3;              // /map_optimization_parameters/remove_radius scanRegistration.cpp:695
+  double mapping_line_resolution = 0.4;    // spot.launch:4  laserMapping.cpp:1181
+  double mapping_plane_resolution = 0.8;   // spot.launch:5  laserMapping.cpp:1183
+  int mapping_skip_frame = 1;              // spot.launch:6  laserOdometry.cpp:265
+  int sliding_window_size = 0;             // mapOptimization.cpp:538
+  int ground_plane_window_size = 2;        // mapOptimization.cpp:541
+  std::string cloud_topic = "/os_cloud_node/points";
+
+  static std::string trim(std::string v) {
+    const size_t h = v.find(" #");
+    if (h != std::string::npos) v.erase(h);
+    if (!v.empty() && v[0] == '#') v.clear();
+    while (!v.empty() && (v.back() == ' ' || v.back() == '\t' || v.back() == '\r' || v.back() == '\n')) v.pop_back();
+    size_t b = 0;
+    while (b < v.size() && (v[b] == ' ' || v[b] == '\t')) ++b;
+    v.erase(0, b);
+    if (v.size() >= 2 && (v.front() == '"' || v.front() == '\'') && v.back() == v.front()) v = v.substr(1, v.size() - 2);
+    return v;
+  }
+  void set(const std::string& section, const std::string& key, const std::string& val) {
+    if (val.empty()) return;
+    const std::string k = section.empty() ? key : section + "/" + key;
+    if (k == "intensity_feature_tracker/image_width") image_width = std::atoi(val.c_str());
+    else if (k == "intensity_feature_tracker/image_height") image_height = std::atoi(val.c_str());
+    else if (k == "intensity_feature_tracker/cloud_topic") cloud_topic = val;
+    else if (k == "map_optimization_parameters/remove_radius") minimum_range = std::atof(val.c_str());
+    else if (k == "map_optimization_parameters/sliding_window_size") sliding_window_size = std::atoi(val.c_str());
+    else if (k == "map_optimization_parameters/ground_plane_window_size") ground_plane_window_size = std::atoi(val.c_str());
+    else if (k == "mapping_line_resolution") mapping_line_resolution = std::atof(val.c_str());
+    else if (k == "mapping_plane_resolution") mapping_plane_resolution = std::atof(val.c_str());
+    else if (k == "mapping_skip_frame") mapping_skip_frame = std::atoi(val.c_str());
+  }
+  // returns false when the file cannot be opened (the defaults stay)
+  bool load_yaml(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[1024];
+    std::string section;
+    while (std::fgets(line, sizeof(line), f)) {
+      std::string l(line);
+      size_t indent = 0;
+      while (indent < l.size() && l[indent] == ' ') ++indent;
+      const size_t colon = l.find(':');
+      if (colon == std::string::npos || l[indent] == '#' || l[indent] == '\n') continue;
+      const std::string key = trim(l.substr(indent, colon - indent)), val = trim(l.substr(colon + 1));
+      if (indent == 0) {
+        section = val.empty() ? key : "";
+        if (!val.empty()) set("", key, val);
+      } else {
+        set(section, key, val);
+      }
+    }
+    std::fclose(f);
+    return true;
+  }
+  bool load_launch(const std::string& path) {  // <param name="mapping_line_resolution" type="double" value="0.4"/>
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[2048];
+    while (std::fgets(line, sizeof(line), f)) {
+      const std::string l(line);
+      const size_t p = l.find("<param"), n = l.find("name=\""), v = l.find("value=\"");
+      if (p == std::string::npos || n == std::string::npos || v == std::string::npos) continue;
+      const size_t ne = l.find('"', n + 6), ve = l.find('"', v + 7);
+      if (ne == std::string::npos || ve == std::string::npos) continue;
+      set("", l.substr(n + 6, ne - (n + 6)), l.substr(v + 7, ve - (v + 7)));
+    }
+    std::fclose(f);
+    return true;
+  }
+  void validate() const {
+    if (image_height != 64) throw Error(ILSM_ERR_INVALID_ARG, "only the 64-ring branch of scanRegistration.cpp:308-316 is implemented");
+    if (image_width <= 0 || !(mapping_line_resolution > 0) || !(mapping_plane_resolution > 0) || !(minimum_range >= 0))
+      throw Error(ILSM_ERR_INVALID_ARG, "bad parameter value");
+  }
 };
 
 // ------------------------------------------------------------------------------------------------ odom_handler_node

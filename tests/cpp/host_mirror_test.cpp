@@ -374,8 +374,35 @@ static void test_odom_handler() {
   EXPECT(std::fabs(m[4] - (3 + std::cos(0.1))) < 1e-14 && std::fabs(m[5] - std::sin(0.1)) < 1e-14);
 }
 
-int main() {
+static void test_config(const char* yaml_path) {
+  std::printf("Config::load_yaml / load_launch (the reference's parameter keys)\n");
+  ilsm::Config c;
+  EXPECT(c.load_yaml(yaml_path));
+  c.validate();
+  EXPECT(c.image_width == 1024 && c.image_height == 64 && c.minimum_range == 0.3 && c.mapping_line_resolution == 0.4 &&
+         c.mapping_plane_resolution == 0.8 && c.mapping_skip_frame == 1 && c.ground_plane_window_size == 2 &&
+         c.cloud_topic == "/os_cloud_node/points");
+  // overrides, comments, quoting and the launch-file form
+  const char* tmp = "/tmp/ilsm_cfg_test.yaml";
+  FILE* f = std::fopen(tmp, "w");
+  std::fputs("intensity_feature_tracker:\n  image_width: 2048   # wide\n  cloud_topic: '/points'\n"
+             "map_optimization_parameters:\n  remove_radius: 0.5\nmapping_line_resolution: 0.2\n", f);
+  std::fclose(f);
+  ilsm::Config d;
+  EXPECT(d.load_yaml(tmp) && d.image_width == 2048 && d.cloud_topic == "/points" && d.minimum_range == 0.5 &&
+         d.mapping_line_resolution == 0.2 && d.mapping_plane_resolution == 0.8);
+  f = std::fopen(tmp, "w");
+  std::fputs("<launch>\n  <param name=\"mapping_plane_resolution\" type=\"double\" value=\"1.6\"/>\n"
+             "  <param name=\"mapping_skip_frame\" type=\"int\" value=\"2\" />\n</launch>\n", f);
+  std::fclose(f);
+  EXPECT(d.load_launch(tmp) && d.mapping_plane_resolution == 1.6 && d.mapping_skip_frame == 2);
+  EXPECT(!d.load_yaml("/nonexistent/spot.yaml"));
+  std::remove(tmp);
+}
+
+int main(int argc, char** argv) {
   try {
+    if (argc > 1) test_config(argv[1]);
     test_odom_handler();
     test_kdtree_flann();
     test_voxelgrid();

@@ -37,14 +37,15 @@ def test_parity_program_links(ilsm, oracle_mod, tmp_path):
     assert os.path.exists(exe)
     import torch
     if not torch.cuda.is_available():  # product path fails loudly without a GPU: ilsm::Error(ILSM_ERR_NO_DEVICE), exit code 100
-        r = subprocess.run([str(exe)], capture_output=True, text=True)
+        r = subprocess.run([str(exe), os.path.join(ROOT, "config", "spot.yaml")], capture_output=True, text=True)
         assert r.returncode == 100 and "ilsm::Error -3" in r.stdout, r.stdout + r.stderr
+        assert "FAILED" not in r.stdout  # the host-only checks (Config, OdomHandler) run before the first GPU object
 
 
 @pytest.mark.gpu
 def test_cpp_host_mirror_parity(ilsm, oracle_mod, tmp_path):
     exe = _build(ilsm, oracle_mod, tmp_path)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(exe), os.path.join(ROOT, "config", "spot.yaml")], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all host-mirror checks passed" in r.stdout
