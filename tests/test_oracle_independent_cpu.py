@@ -1,0 +1,212 @@
+"""Second, independent restatements (numpy / plain Python, written from the reference text, sharing no code with
+oracle/*.cpp) of the parts of the oracle that no reference binary or library pins: projection, curvature, PCL VoxelGrid,
+ScanContext distance, the ikd-Tree down-sampled insertion.  The C++ oracle must agree with them bit for bit (float paths)
+or to 1e-12 (double paths whose summation order Eigen leaves open)."""
+import math
+
+import numpy as np
+import pytest
+
+
+# ---------------------------------------------------------------------------------------------- projection
+def _project_numpy(cloud, H, W):
+    """image_handler.h_ouster:103-140: range = sqrt(x^2+y^2+z^2) (float), u8(min(range*20, 255)), u8(min(I, 255)), cloud_track
+    zeroed where range < 0.1."""
+    x, y, z, it = (cloud[:, k].astype(np.float32) for k in range(4))
+    rng = np.sqrt((x * x + y * y) + z * z, dtype=np.float32)
+    r8 = np.minimum(rng * np.float32(20.0), np.float32(255.0)).astype(np.uint8)       # C++ float -> uchar truncation
+    i8 = np.minimum(it, np.float32(255.0)).astype(np.uint8)
+    track = cloud[:, :4].astype(np.float32).copy()
+    track[:, 3] = np.minimum(it, np.float32(255.0))   # the CLAMPED intensity is what cloud_track keeps (:121,130)
+    track[rng < np.float32(0.1)] = 0
+    return r8.reshape(H, W), i8.reshape(H, W), track
+
+
+def test_projection_vs_numpy(oracle_mod):
+    rng = np.random.default_rng(0)
+    H, W = 8, 64
+    c = rng.normal(0, 6, (H * W, 4)).astype(np.float32)
+    c[:, 3] = rng.uniform(0, 400, H * W)          # intensities above 255 saturate
+    c[::7, :3] = 0                                # no-return rays
+    c[1, :3] = [0.05, 0.02, 0.01]                 # below the 0.1 m cut
+    c[2, :3] = [30, 40, 5]                        # range * 20 > 255 saturates
+    r8, i8, tr = oracle_mod.project(c, H, W)
+    w8, wi8, wtr = _project_numpy(c, H, W)
+    assert np.array_equal(r8, w8) and np.array_equal(i8, wi8) and np.array_equal(tr, wtr)
+
+
+# ---------------------------------------------------------------------------------------------- curvature
+def test_curvature_vs_numpy(oracle_mod, ilsm):
+    """scanRegistration.cpp:397-412: diff = sum of the 10 neighbours - 10 * p, added left to right in float; c = dx^2+dy^2+dz^2."""
+    c = ilsm.synth.config1(n_map=20_000)
+    fe = oracle_mod.extract_features(c["cloud"])
+    p = fe["cloud"][:, :3].astype(np.float32)
+    n = len(p)
+    want = np.zeros(n, np.float32)
+    order = [-5, -4, -3, -2, -1, 1, 2, 3, 4, 5]   # the reference's order of terms ...
+    i = np.arange(5, n - 5)
+    d = np.zeros((len(i), 3), np.float32)
+    for o in order[:5]:
+        d = d + p[i + o]
+    d = d - np.float32(10) * p[i]                 # ... with "- 10 * p" in sixth place
+    for o in order[5:]:
+        d = d + p[i + o]
+    want[5:n - 5] = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    got = fe["curvature"]
+    assert np.array_equal(got[5:n - 5], want[5:n - 5])
+
+
+# ---------------------------------------------------------------------------------------------- VoxelGrid
+def _voxelgrid_python(cloud, leaf):
+    """PCL 1.10 VoxelGrid::applyFilter for a cubic leaf: min/max of the finite points, ijk = floor(p * inv) - min_b, index
+    = i + j * dx + k * dx * dy, points grouped by index (stable: input order inside a voxel), float centroid of all four fields,
+    output in ascending index."""
+    f32 = np.float32
+    inv = f32(1.0) / f32(leaf)
+    pts = [r for r in cloud.astype(np.float32) if np.isfinite(r[:3]).all()]
+    a = np.array(pts, np.float32)
+    min_b = [int(math.floor(float(a[:, k].min() * inv))) for k in range(3)]
+    max_b = [int(math.floor(float(a[:, k].max() * inv))) for k in range(3)]
+    dx, dy = max_b[0] - min_b[0] + 1, max_b[1] - min_b[1] + 1
+    groups = {}
+    for r in pts:
+        ijk = [int(f32(math.floor(float(r[k] * inv))) - f32(min_b[k])) for k in range(3)]
+        groups.setdefault(ijk[0] + ijk[1] * dx + ijk[2] * dx * dy, []).append(r)
+    out = []
+    for key in sorted(groups):
+        s = np.zeros(4, np.float32)
+        for r in groups[key]:
+            s = s + r[:4]
+        out.append(s / f32(len(groups[key])))
+    return np.array(out, np.float32)
+
+
+@pytest.mark.parametrize("leaf", [0.2, 0.4, 0.8])
+def test_voxelgrid_vs_python(oracle_mod, leaf):
+    rng = np.random.default_rng(int(leaf * 10))
+    c = rng.normal(0, 3, (1500, 4)).astype(np.float32)
+    c[:, 2] *= 0.1
+    c[:, 3] = rng.integers(0, 64, 1500) + 0.05
+    c[100:140, :3] = c[60:100, :3] + rng.normal(0, 0.01, (40, 3)).astype(np.float32)  # several points per voxel
+    got = oracle_mod.voxelgrid(c, leaf)
+    want = _voxelgrid_python(c, leaf)
+    assert got.shape == want.shape and len(want) < 1500
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- ScanContext distance
+def _circshift(m, s):  # Scancontext.cpp:44-68: column c moves to (c + s) % cols
+    return np.roll(m, s, axis=1)
+
+
+def _dist_direct(a, b):  # :79-101
+    num, tot = 0, 0.0
+    for c in range(a.shape[1]):
+        na, nb = np.linalg.norm(a[:, c]), np.linalg.norm(b[:, c])
+        if na == 0 or nb == 0:
+            continue
+        tot += float(a[:, c] @ b[:, c]) / (na * nb)
+        num += 1
+    return 1.0 - tot / num
+
+
+def _distance_btn(q, cand):  # :104-157
+    k1, k2 = q.mean(axis=0)[None, :], cand.mean(axis=0)[None, :]
+    best, arg = 10000000.0, 0
+    for s in range(60):
+        d = np.linalg.norm(k1 - _circshift(k2, s))
+        if d < best:
+            best, arg = d, s
+    radius = int(round(0.5 * 0.1 * 60))
+    space = sorted([arg] + [(arg + i + 60) % 60 for i in range(1, radius + 1)] + [(arg - i + 60) % 60 for i in range(1, radius + 1)])
+    bd, bs = 10000000.0, 0
+    for s in space:
+        d = _dist_direct(q, _circshift(cand, s))
+        if d < bd:
+            bd, bs = d, s
+    return bd, bs
+
+
+def test_scancontext_distance_vs_numpy(oracle_mod, ilsm):
+    db = ilsm.synth.sc_database(40).astype(np.float64)
+    qs, ids, shifts = ilsm.synth.sc_queries(db.astype(np.float32), 6)
+    for j in range(len(qs)):
+        q = qs[j].astype(np.float64)
+        for i in (int(ids[j]), (int(ids[j]) + 7) % 40):
+            d, s = oracle_mod.sc_distance(q, db[i])
+            wd, ws = _distance_btn(q, db[i])
+            assert s == ws and abs(d - wd) < 1e-12
+    # sector key / ring key
+    rk, sk = oracle_mod.sc_keys(db[3])
+    assert np.allclose(rk, db[3].mean(axis=1), rtol=0, atol=1e-15) and np.allclose(sk, db[3].mean(axis=0), rtol=0, atol=1e-15)
+
+
+def test_scancontext_descriptor_vs_numpy(oracle_mod):
+    """makeScancontext (:160-204): ring = ceil(r / 80 * 20), sector = ceil(theta / 360 * 60), max (z + 2) per bin."""
+    rng = np.random.default_rng(4)
+    p = np.zeros((4000, 3), np.float32)
+    ang, rad = rng.uniform(0, 2 * np.pi, 4000), rng.uniform(0.5, 95, 4000)   # some beyond PC_MAX_RADIUS
+    p[:, 0], p[:, 1], p[:, 2] = rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-1.8, 5, 4000)
+    want = np.full((20, 60), -1000.0)
+    for x, y, z in p:
+        zz = np.float32(np.float64(z) + 2.0)
+        r = np.sqrt(np.float32(x * x + y * y), dtype=np.float32)
+        if x >= 0 and y >= 0:
+            th = (180 / np.pi) * np.float32(math.atan(np.float32(y / x)))
+        elif x < 0 and y >= 0:
+            th = 180 - (180 / np.pi) * np.float32(math.atan(np.float32(y / -x)))
+        elif x < 0 and y < 0:
+            th = 180 + (180 / np.pi) * np.float32(math.atan(np.float32(y / x)))
+        else:
+            th = 360 - (180 / np.pi) * np.float32(math.atan(np.float32(-y / x)))
+        th = np.float32(th)
+        if float(r) > 80.0:
+            continue
+        ring = max(min(20, int(math.ceil((float(r) / 80.0) * 20))), 1)
+        sector = max(min(60, int(math.ceil((float(th) / 360.0) * 60))), 1)
+        want[ring - 1, sector - 1] = max(want[ring - 1, sector - 1], float(zz))
+    want[want == -1000.0] = 0
+    got = oracle_mod.sc_make(p)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------- ikd-Tree Add_Points
+def _add_points_python(existing, add, ds):
+    """ikd_Tree.cpp:570-640 with downsample_on: per new point, box = floor(p / ds) * ds, the stored points inside it, winner =
+    nearest to the box centre (strict <, the new point seeds the minimum); if more than one stored point is in the box or
+    the new point wins, the box is emptied and the winner stored."""
+    f32 = np.float32
+    pts = [tuple(map(f32, r)) for r in existing]
+
+    def d2(a, b):
+        return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2])
+
+    for r in add:
+        p = tuple(map(f32, r))
+        mn = [f32(math.floor(float(p[k] / f32(ds)))) * f32(ds) for k in range(3)]
+        mx = [mn[k] + f32(ds) for k in range(3)]
+        mid = tuple(f32(float(mn[k]) + (float(mx[k]) - float(mn[k])) / 2.0) for k in range(3))
+        inside = [j for j, s in enumerate(pts) if all(mn[k] <= s[k] < mx[k] for k in range(3))]
+        best, win = d2(p, mid), p
+        for j in inside:
+            d = d2(pts[j], mid)
+            if d < best:
+                best, win = d, pts[j]
+        same = all(abs(float(p[k]) - float(win[k])) < 1e-6 for k in range(3))
+        if len(inside) > 1 or same:
+            pts = [s for j, s in enumerate(pts) if j not in set(inside)] + [win]
+        # else: exactly one stored point, and it is at least as close as the new one -> nothing changes
+        elif len(inside) == 0:
+            pts.append(p)
+    return np.array(sorted(pts), np.float32)
+
+
+def test_ikd_add_points_vs_python(oracle_mod):
+    rng = np.random.default_rng(8)
+    base = (rng.uniform(-2, 2, (300, 3)) * [1, 1, 0.1]).astype(np.float32)
+    add = (rng.uniform(-2.4, 2.4, (400, 3)) * [1, 1, 0.1]).astype(np.float32)
+    add[:60] = add[60:120] + rng.normal(0, 0.02, (60, 3)).astype(np.float32)
+    got = oracle_mod.ikd_add_points(base, add, 0.4, True)
+    want = _add_points_python(base, add, 0.4)
+    g = np.array(sorted(map(tuple, got[:, :3])), np.float32)
+    assert g.shape == want.shape and np.array_equal(g, want)
