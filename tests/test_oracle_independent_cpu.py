@@ -210,3 +210,95 @@ def test_ikd_add_points_vs_python(oracle_mod):
     want = _add_points_python(base, add, 0.4)
     g = np.array(sorted(map(tuple, got[:, :3])), np.float32)
     assert g.shape == want.shape and np.array_equal(g, want)
+
+
+# ---------------------------------------------------------------------------------------------- feature labelling
+def _label_python(p, curv, ring_start, ring_end):
+    """scanRegistration.cpp:427-577 in plain Python: per ring, six segments in order; per segment a sort by curvature (ties
+    by index: the declared rule where std::sort leaves it open), <= 2 sharp + <= 20 less-sharp picks from the top, <= 4
+    flat picks from the bottom (the fourth without suppression), +-5 neighbour suppression stopped by a gap^2 > 0.05."""
+    f32 = np.float32
+    n = len(p)
+    label = np.zeros(n, np.int32)
+    picked = np.zeros(n, np.uint8)
+    sharp, lsharp, flat = [], [], []
+
+    def gap2(a, b):
+        d = p[a] - p[b]
+        return (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
+
+    def suppress(ind):
+        picked[ind] = 1
+        for l in range(1, 6):
+            if float(gap2(ind + l, ind + l - 1)) > 0.05:
+                break
+            picked[ind + l] = 1
+        for l in range(-1, -6, -1):
+            if float(gap2(ind + l, ind + l + 1)) > 0.05:
+                break
+            picked[ind + l] = 1
+
+    for s, e in zip(ring_start, ring_end):
+        if e - s < 6:
+            continue
+        for j in range(6):
+            sp, ep = s + (e - s) * j // 6, s + (e - s) * (j + 1) // 6 - 1
+            order = sorted(range(sp, ep + 1), key=lambda i: (curv[i], i))
+            largest = 0
+            for ind in reversed(order):
+                if picked[ind] == 0 and float(curv[ind]) > 0.1:
+                    largest += 1
+                    if largest <= 2:
+                        label[ind] = 2
+                        sharp.append(ind), lsharp.append(ind)
+                    elif largest <= 20:
+                        label[ind] = 1
+                        lsharp.append(ind)
+                    else:
+                        break
+                    suppress(ind)
+            smallest = 0
+            for ind in order:
+                if picked[ind] == 0 and float(curv[ind]) < 0.1:
+                    label[ind] = -1
+                    flat.append(ind)
+                    smallest += 1
+                    if smallest >= 4:
+                        break
+                    suppress(ind)
+    return label, sharp, lsharp, flat
+
+
+def test_feature_labels_vs_python(oracle_mod, ilsm):
+    c = ilsm.synth.config1(n_map=20_000)
+    fe = oracle_mod.extract_features(c["cloud"])
+    p = fe["cloud"][:, :3].astype(np.float32)
+    label, sharp, lsharp, flat = _label_python(p, fe["curvature"], fe["ring_start"], fe["ring_end"])
+    assert np.array_equal(label, fe["label"])
+    assert sharp == fe["sharp_idx"].tolist() and lsharp == fe["less_sharp_idx"].tolist() and flat == fe["flat_idx"].tolist()
+    assert len(sharp) > 100 and len(flat) > 500
+
+
+def test_ring_assignment_vs_numpy(oracle_mod, ilsm):
+    """scanRegistration.cpp:152-186, 277-374 (64-ring branch): min-range filter, angle = atan(z / sqrt(x^2 + y^2)) * 180 / pi
+    (float), scanID = int((angle + 22.5) * 1.41 + 0.5) - 1, points outside [0, 63] dropped; the output is the rings
+    concatenated, input order kept inside a ring; scanStartInd / scanEndInd carry the +5 / -6 margins (:387,393)."""
+    c = ilsm.synth.config1(n_map=20_000)
+    cloud = c["cloud"].astype(np.float32)
+    fe = oracle_mod.extract_features(cloud)
+    x, y, z = cloud[:, 0], cloud[:, 1], cloud[:, 2]
+    with np.errstate(all="ignore"):
+        ratio = (z / np.sqrt(x * x + y * y)).astype(np.float32)
+        ang = (np.arctan(ratio.astype(np.float64)) * 180 / np.pi).astype(np.float32)
+        sid = (ang.astype(np.float64) + 22.5) * 1.41 + 0.5
+        sid = np.where(np.isfinite(sid), sid, -1.0).astype(np.int64) - 1          # int(): truncation toward zero
+    keep = ((x * x + y * y) + z * z >= np.float32(0.3 * 0.3)) & (sid >= 0) & (sid <= 63)
+    want_src = np.concatenate([np.where(keep & (sid == r))[0] for r in range(64)])
+    assert np.array_equal(fe["src_index"], want_src)
+    ids = fe["cloud"][:, 3].astype(np.int32)                                      # intensity = scanID + 0.1 * relTime
+    assert np.array_equal(ids, sid[want_src])
+    assert np.array_equal(fe["cloud"][:, :3], cloud[want_src, :3])
+    for r in np.unique(ids):
+        idx = np.where(ids == r)[0]
+        assert fe["ring_start"][r] == idx[0] + 5 and fe["ring_end"][r] == idx[-1] + 1 - 6
+    assert keep.sum() < len(cloud) * 0.6 and len(np.unique(ids)) > 30   # the OS0's +-45 deg beams beyond +-22.5 deg are dropped
