@@ -302,3 +302,81 @@ def test_ring_assignment_vs_numpy(oracle_mod, ilsm):
         idx = np.where(ids == r)[0]
         assert fe["ring_start"][r] == idx[0] + 5 and fe["ring_end"][r] == idx[-1] + 1 - 6
     assert keep.sum() < len(cloud) * 0.6 and len(np.unique(ids)) > 30   # the OS0's +-45 deg beams beyond +-22.5 deg are dropped
+
+
+# ---------------------------------------------------------------------------------------------- rolling cube map
+class _CubeModel:
+    """laserMapping.cpp:70-78, 330-606, 880-1002 with the cubes keyed by WORLD cube coordinates instead of a shifted array:
+    rolling the 21 x 21 x 11 window then only means dropping the world cubes that leave it."""
+    W, H, D = 21, 21, 11
+
+    def __init__(self, line_res, plane_res):
+        self.cen = [10, 10, 5]
+        self.cubes = [{}, {}]  # corner, surf: world cube (wi, wj, wk) -> list of xyzi rows
+        self.res = (line_res, plane_res)
+
+    @staticmethod
+    def _cube(v, cen):
+        c = int((v + 25.0) / 50.0) + cen      # int(): truncation toward zero ...
+        if v + 25.0 < 0:
+            c -= 1                            # ... fixed up for negative coordinates (:333-338)
+        return c
+
+    def insert_world(self, corner, surf, centre):
+        n = (self.W, self.H, self.D)
+        ctr = [self._cube(float(centre[a]), self.cen[a]) for a in range(3)]
+        for a in range(3):                    # :341-565: keep the centre at least 3 cubes away from the border
+            while ctr[a] < 3:
+                self.cen[a] += 1
+                ctr[a] += 1
+            while ctr[a] >= n[a] - 3:
+                self.cen[a] -= 1
+                ctr[a] -= 1
+        for d in self.cubes:
+            for w in [w for w in d if not all(0 <= w[a] + self.cen[a] < n[a] for a in range(3))]:
+                del d[w]
+        for which, pts in ((0, corner), (1, surf)):
+            for r in np.asarray(pts, np.float32):   # :880-940: points outside the window are dropped
+                idx = [self._cube(float(r[a]), self.cen[a]) for a in range(3)]
+                if all(0 <= idx[a] < n[a] for a in range(3)):
+                    row = np.zeros(4, np.float32)
+                    row[:len(r)] = r[:4]
+                    self.cubes[which].setdefault(tuple(idx[a] - self.cen[a] for a in range(3)), []).append(row)
+        for i in range(ctr[0] - 2, ctr[0] + 3):     # :572-592 valid cubes, :987-1002 per-cube VoxelGrid
+            for j in range(ctr[1] - 2, ctr[1] + 3):
+                for k in range(ctr[2] - 1, ctr[2] + 2):
+                    if 0 <= i < n[0] and 0 <= j < n[1] and 0 <= k < n[2]:
+                        w = (i - self.cen[0], j - self.cen[1], k - self.cen[2])
+                        for which in (0, 1):
+                            if self.cubes[which].get(w):
+                                self.cubes[which][w] = list(_voxelgrid_python(np.array(self.cubes[which][w]), self.res[which]))
+
+    def all_points(self, which):
+        rows = [r for v in self.cubes[which].values() for r in v]
+        a = np.array(rows, np.float32).reshape(-1, 4)
+        return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def test_rolling_cube_map_vs_world_keyed_model(oracle_mod):
+    rng = np.random.default_rng(21)
+    cm = oracle_mod.CubeMap(0.4, 0.8)
+    model = _CubeModel(0.4, 0.8)
+    # a path that drags the window through several rolls on every axis, negative coordinates included
+    centres = [(0, 0, 0), (160, 0, 0), (420, -30, 0), (420, -380, 10), (90, -380, 140), (-260, 20, -40), (-262, 22, -41)]
+    for ctr in centres:
+        corner = (np.array(ctr) + rng.uniform(-70, 70, (300, 3)) * [1, 1, 0.3]).astype(np.float32)
+        surf = (np.array(ctr) + rng.uniform(-70, 70, (900, 3)) * [1, 1, 0.3]).astype(np.float32)
+        surf[:200] = surf[200:400] + rng.normal(0, 0.1, (200, 3)).astype(np.float32)   # voxel mates for the filter
+        corner4, surf4 = np.zeros((300, 4), np.float32), np.zeros((900, 4), np.float32)
+        corner4[:, :3], surf4[:, :3] = corner, surf
+        corner4[:, 3], surf4[:, 3] = rng.integers(0, 64, 300), rng.integers(0, 64, 900)
+        cm.insert_world(corner4, surf4, np.array(ctr, np.float64))
+        model.insert_world(corner4, surf4, ctr)
+        for which in (0, 1):
+            got = [cm.cube(which, i, cap=2048) for i in range(21 * 21 * 11)]
+            got = np.concatenate([g for g in got if len(g)]).reshape(-1, 4)
+            got = got[np.lexsort((got[:, 2], got[:, 1], got[:, 0]))]
+            want = model.all_points(which)
+            assert got.shape == want.shape, (ctr, which, got.shape, want.shape)
+            assert np.array_equal(got, want), (ctr, which)
+    assert model.cen != [10, 10, 5]  # the window did roll
