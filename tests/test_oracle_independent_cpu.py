@@ -380,3 +380,111 @@ def test_rolling_cube_map_vs_world_keyed_model(oracle_mod):
             assert got.shape == want.shape, (ctr, which, got.shape, want.shape)
             assert np.array_equal(got, want), (ctr, which)
     assert model.cen != [10, 10, 5]  # the window did roll
+
+
+# ---------------------------------------------------------------------------------------------- odometry association
+def _qrot(q, v):  # Eigen quaternion (x, y, z, w) applied to a vector, double
+    u = np.array(q[:3])
+    uv = 2.0 * np.cross(u, v)
+    return v + q[3] * uv + np.cross(u, uv)
+
+
+def _odom_associate_python(last_corner, last_surf, sharp, flat, qt):
+    """laserOdometry.cpp:446-689 (DISTORTION 0): TransformToStart, 1-NN (d2 < 25), then the ring walk: edges take the nearest
+    point on the rings (id, id + 2.5] / [id - 2.5, id); planes a second point on the same-or-nearer ring side and a third on
+    the other rings.  Distances of the walk are float expressions (:478-483)."""
+    f32 = np.float32
+    q, t = np.array(qt[:4], np.float64), np.array(qt[4:], np.float64)
+    out = []
+
+    def sel(p):
+        w = _qrot(q, p[:3].astype(np.float64)) + t
+        return w.astype(np.float32)
+
+    def nn(cloud, s):
+        d = cloud[:, :3] - s
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        i = int(np.argmin(d2))
+        return i, d2[i]
+
+    def sq(cloud, j, s):
+        d = cloud[j, :3] - s
+        return float((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+
+    ring_c, ring_s = last_corner[:, 3].astype(np.int32), last_surf[:, 3].astype(np.int32)
+    for i, p in enumerate(sharp):
+        s = sel(p)
+        c, d2 = nn(last_corner, s)
+        m2 = -1
+        if d2 < f32(25.0):
+            cid, best = int(ring_c[c]), 25.0
+            for j in range(c + 1, len(last_corner)):
+                if ring_c[j] <= cid:
+                    continue
+                if ring_c[j] > cid + 2.5:
+                    break
+                d = sq(last_corner, j, s)
+                if d < best:
+                    best, m2 = d, j
+            for j in range(c - 1, -1, -1):
+                if ring_c[j] >= cid:
+                    continue
+                if ring_c[j] < cid - 2.5:
+                    break
+                d = sq(last_corner, j, s)
+                if d < best:
+                    best, m2 = d, j
+        if m2 >= 0:
+            out.append((1, i, p[:3], last_corner[c, :3], last_corner[m2, :3]))
+    for i, p in enumerate(flat):
+        s = sel(p)
+        c, d2 = nn(last_surf, s)
+        m2 = m3 = -1
+        if d2 < f32(25.0):
+            cid, b2, b3 = int(ring_s[c]), 25.0, 25.0
+            for j in range(c + 1, len(last_surf)):
+                if ring_s[j] > cid + 2.5:
+                    break
+                d = sq(last_surf, j, s)
+                if ring_s[j] <= cid and d < b2:
+                    b2, m2 = d, j
+                elif ring_s[j] > cid and d < b3:
+                    b3, m3 = d, j
+            for j in range(c - 1, -1, -1):
+                if ring_s[j] < cid - 2.5:
+                    break
+                d = sq(last_surf, j, s)
+                if ring_s[j] >= cid and d < b2:
+                    b2, m2 = d, j
+                elif ring_s[j] < cid and d < b3:
+                    b3, m3 = d, j
+        if m2 >= 0 and m3 >= 0:
+            jj, ll, mm = (last_surf[k, :3].astype(np.float64) for k in (c, m2, m3))
+            n = np.cross(jj - ll, jj - mm)      # LidarPlaneFactor: ljm_norm = (j - l) x (j - m), normalised (hpp:151-152)
+            n /= np.linalg.norm(n)
+            out.append((2, i, p[:3], n, np.array([-(jj @ n), 0, 0])))
+    return out
+
+
+def test_odometry_association_vs_python(oracle_mod, ilsm):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from sequence_bench import corridor_sequence
+    clouds, _ = corridor_sequence(ilsm.synth, 2, 0x5EED0100, 40.0)
+    f0, f1 = oracle_mod.extract_features(clouds[0]), oracle_mod.extract_features(clouds[1])
+    last_corner = f0["cloud"][f0["less_sharp_idx"]]
+    last_surf = f0["less_flat"]
+    sharp, flat = f1["cloud"][f1["sharp_idx"]][:200], f1["cloud"][f1["flat_idx"]][:300]
+    qt = np.array([0.001, -0.002, 0.004, 1.0, 0.18, 0.01, -0.005])
+    qt[:4] /= np.linalg.norm(qt[:4])
+    got = oracle_mod.odom_associate(last_corner, last_surf, sharp, flat, qt)
+    want = _odom_associate_python(last_corner, last_surf, sharp, flat, qt)
+    got = [g for g in got if g["type"] != 0]
+    assert len(got) == len(want) and sum(w[0] == 1 for w in want) > 30 and sum(w[0] == 2 for w in want) > 100
+    for g, w in zip(got, want):
+        assert g["type"] == w[0] and g["src"] == w[1]
+        assert np.array_equal(g["p"], w[2].astype(np.float64))
+        if w[0] == 1:
+            assert np.array_equal(g["a"], w[3].astype(np.float64)) and np.array_equal(g["b"], w[4].astype(np.float64))
+        else:
+            assert np.abs(g["a"] - w[3]).max() < 1e-12 and abs(g["b"][0] - w[4][0]) < 1e-10
