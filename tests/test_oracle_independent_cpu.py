@@ -488,3 +488,81 @@ def test_odometry_association_vs_python(oracle_mod, ilsm):
             assert np.array_equal(g["a"], w[3].astype(np.float64)) and np.array_equal(g["b"], w[4].astype(np.float64))
         else:
             assert np.abs(g["a"] - w[3]).max() < 1e-12 and abs(g["b"][0] - w[4][0]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------- Ceres trust-region loop
+def _quat_plus(x, d):
+    """EigenQuaternionParameterization::Plus: [sin|d| / |d| * d, cos|d|] (x) x."""
+    n = np.linalg.norm(d)
+    if n == 0:
+        return x.copy()
+    dq = np.concatenate([np.sin(n) / n * d, [np.cos(n)]])
+    a, b = dq, x
+    return np.array([a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1], a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2],
+                     a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0], a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]])
+
+
+def _ceres_lm_python(evaluate, x0, max_iter):
+    """Ceres 1.14 TrustRegionMinimizer + LevenbergMarquardtStrategy with its defaults, on (cost, J^T J, J^T r) evaluations:
+    Jacobi scaling fixed at iteration 0, D = sqrt(clamp(diag) / radius), rho test, radius update, the termination tests.
+    The damped step is solved with numpy (the oracle uses an LDL^T it wrote itself)."""
+    ftol, gtol, ptol = 1e-6, 1e-10, 1e-8
+    x = np.array(x0, np.float64)
+    cost, H, g = evaluate(x)
+    initial = cost
+    if not np.isfinite(cost):
+        return x, 2, 0, 0, 0, initial, cost
+    scale = 1.0 / (1.0 + np.sqrt(np.diag(H)))
+    radius, decrease, it, ok_steps, bad_steps = 1e4, 2.0, 0, 0, 0
+    diag = None
+    reuse = False
+    while True:
+        if it >= max_iter:
+            return x, 1, it, ok_steps, bad_steps, initial, cost          # NO_CONVERGENCE
+        gmax = max(np.abs(g[3:]).max(), np.abs(x[:4] - _quat_plus(x[:4], -g[:3])).max())
+        if gmax <= gtol:
+            return x, 0, it, ok_steps, bad_steps, initial, cost
+        if radius <= 1e-32:
+            return x, 0, it, ok_steps, bad_steps, initial, cost
+        it += 1
+        Hs, gs = H * np.outer(scale, scale), g * scale
+        if not reuse:
+            diag = np.clip(np.diag(Hs), 1e-6, 1e32)
+        reuse = True
+        y = np.linalg.solve(Hs + np.diag(diag / radius), gs)
+        model = 0.5 * (y @ gs + y @ (diag / radius * y))
+        if not (np.isfinite(y).all() and model > 0):
+            bad_steps += 1
+            radius /= decrease
+            decrease *= 2
+            continue
+        delta = -y * scale
+        cand = np.concatenate([_quat_plus(x[:4], delta[:3]), x[4:] + delta[3:]])
+        new_cost, nH, ng = evaluate(cand)
+        if np.linalg.norm(cand - x) <= ptol * (np.linalg.norm(x) + ptol):
+            return x, 0, it, ok_steps, bad_steps, initial, cost
+        change = cost - new_cost
+        if abs(change) <= ftol * cost:
+            return x, 0, it, ok_steps, bad_steps, initial, cost
+        rho = change / model
+        if rho > 1e-3:
+            x, cost, H, g = cand, new_cost, nH, ng
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            decrease, reuse = 2.0, False
+            ok_steps += 1
+        else:
+            radius /= decrease
+            decrease *= 2
+            bad_steps += 1
+
+
+@pytest.mark.parametrize("max_iter", [1, 4, 10, 30])
+def test_trust_region_loop_vs_python(oracle_mod, cfg_small, max_iter):
+    c = cfg_small
+    qt0 = np.concatenate([c["q0"], c["t0"]])
+    fac = oracle_mod.associate(c["map_corner"], c["map_surf"], c["corner"], c["surf"], qt0)
+    x, s = oracle_mod.solve(fac, qt0, max_iter, 0.1)
+    wx, term, it, ok, bad, ini, fin = _ceres_lm_python(lambda p: oracle_mod.evaluate(fac, p, 0.1), qt0, max_iter)
+    assert (s.termination, s.iterations, s.num_successful, s.num_unsuccessful) == (term, it, ok, bad)
+    assert abs(s.initial_cost - ini) <= 1e-12 * ini and abs(s.final_cost - fin) <= 1e-9 * fin
+    assert np.abs(x - wx).max() < 1e-9
