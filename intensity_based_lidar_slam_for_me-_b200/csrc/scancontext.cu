@@ -243,12 +243,20 @@ __global__ void __launch_bounds__(kScWarps * 32, 2)
     // first minimum in ascending shift order wins: arg-min on (distance, t)
     double myd = __longlong_as_double(0x7ff0000000000000ll);
     int mysh = 0, myt = 99;
+    {
+      // select this lane's shift with predicated moves, then ONE division per lane: seven `if (lane == t)` bodies would
+      // be seven serialised division sequences (~210 instructions per candidate)
+      double s_t = 0.0;
+      int sh_t = 0;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) {
-      if (lane == t) {
-        const int ek = (int)((effp >> (8 * t)) & 0xFF);
-        if (ek > 0) myd = 1.0 - sum[t] / (double)ek;
-        mysh = shifts[t], myt = t;
+      for (int t = 0; t < 7; ++t) {
+        s_t = lane == t ? sum[t] : s_t;
+        sh_t = lane == t ? shifts[t] : sh_t;
+      }
+      const int ek = lane < 7 ? (int)((effp >> (8 * lane)) & 0xFF) : 0;
+      if (lane < 7) {
+        if (ek > 0) myd = 1.0 - s_t / (double)ek;
+        mysh = sh_t, myt = lane;
       }
     }
     const bool cand_ok = lane < 7 && myd < 10000000.0;  // min_sc_dist starts at 10000000 (strict <)
