@@ -95,9 +95,10 @@ constexpr int kScWarps = 8;
 constexpr int kTopKMax = 16;
 
 // shared-memory layout of the scoring kernel (dynamic): the query once per block, one candidate per warp.
-// Candidates are staged as doubles (float -> double once, at load) so that the inner products are LDS.64 + DFMA.
+// Candidates are staged as the floats they are stored as and widened at use (exact), the query as doubles.
 struct ScWarpSmem {
-  double cd[kDesc];     // candidate descriptor
+  float cd[kDesc];      // candidate descriptor as stored (widened on use: exact); half the bytes of a double copy, so three
+                        // blocks (24 warps) fit an SM instead of two
   double ck2[2 * kNS];  // candidate sector key, stored twice: circshift index c - s + 60 needs no wrap
   double cin[kNS];      // inverse column norms (0 = empty column)
   u64 tk_d[kTopKMax];   // this warp's running top-k: distance bits, id, shift (ascending (d, id))
@@ -117,7 +118,7 @@ __device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { re
 //   fastAlignUsingVkey  (Scancontext.cpp:104-124): argmin_s || qk - circshift(ck, s) ||, first minimum wins
 //   distDirectSC        (:79-101)                : 1 - mean over columns with both norms != 0 of cos(col_q, col_c)
 //   distanceBtnScanContext (:126-157)            : the 7 shifts around the aligned one, ascending, first minimum wins
-__global__ void __launch_bounds__(kScWarps * 32, 2)
+__global__ void __launch_bounds__(kScWarps * 32, 3)
     sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, int k, u64* __restrict__ part_d,
                     int* __restrict__ part_id, int* __restrict__ part_sh) {
   pdl_entry();
@@ -131,22 +132,17 @@ __global__ void __launch_bounds__(kScWarps * 32, 2)
   __syncthreads();
   const int nwarps = gridDim.x * kScWarps;
   for (int cand = blockIdx.x * kScWarps + warp; cand < n; cand += nwarps) {
-    // stage the candidate: 4800 B of coalesced 128-bit loads, widened to double
+    // stage the candidate: 4800 B of coalesced 128-bit loads, kept as float
     const float4* src = reinterpret_cast<const float4*>(db + (size_t)cand * kDesc);
-    for (int i = lane; i < kDesc / 4; i += 32) {
-      const float4 v = __ldg(src + i);
-      double2* dst = reinterpret_cast<double2*>(w.cd + 4 * i);
-      dst[0] = make_double2((double)v.x, (double)v.y);
-      dst[1] = make_double2((double)v.z, (double)v.w);
-    }
+    for (int i = lane; i < kDesc / 4; i += 32) reinterpret_cast<float4*>(w.cd)[i] = __ldg(src + i);
     __syncwarp();
     // sector key (column means) and inverse column norms of the candidate
     for (int c = lane; c < kNS; c += 32) {
       double s = 0, n2 = 0;
-      const double* col = w.cd + c;
+      const float* col = w.cd + c;
 #pragma unroll
       for (int r = 0; r < kNR; ++r) {
-        const double v = col[r * kNS];
+        const double v = (double)col[r * kNS];
         s += v;
         n2 = fma(v, v, n2);  // v is a widened float: v * v is exact in double, so the fused form rounds identically
       }
@@ -205,7 +201,7 @@ __global__ void __launch_bounds__(kScWarps * 32, 2)
       const double iq = sm.qin[j];
       int jb[7];
       double dot[7];
-      const double* ccol[7];
+      const float* ccol[7];
 #pragma unroll
       for (int t = 0; t < 7; ++t) {
         int b = j - shifts[t];
@@ -218,7 +214,7 @@ __global__ void __launch_bounds__(kScWarps * 32, 2)
       for (int r = 0; r < kNR; ++r) {  // fully unrolled: immediate shared-memory offsets, 1 + 7 loads and 7 DFMA per row
         const double qv = qcol[r * kNS];
 #pragma unroll
-        for (int t = 0; t < 7; ++t) dot[t] = fma(qv, ccol[t][r * kNS], dot[t]);  // products of widened floats are exact
+        for (int t = 0; t < 7; ++t) dot[t] = fma(qv, (double)ccol[t][r * kNS], dot[t]);  // products of widened floats are exact
       }
 #pragma unroll
       for (int t = 0; t < 7; ++t) {
@@ -458,7 +454,7 @@ int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, do
   if (n_search < 0 || n_search > count) return fail(ILSM_ERR_INVALID_ARG, "sc_query: n_search exceeds the database");
   // two resident blocks of 8 warps per SM; fewer blocks when the shard is small.  The final merge holds at most
   // kFinalThreads * kFinalPer entries.
-  long long blocks = ((long long)n_search + kScWarps - 1) / kScWarps, cap = (long long)ctx->sm_count * 2;
+  long long blocks = ((long long)n_search + kScWarps - 1) / kScWarps, cap = (long long)ctx->sm_count * 3;  // three resident blocks per SM
   if (blocks > cap) blocks = cap;
   if (blocks * k > (long long)kFinalThreads * kFinalPer) blocks = (long long)kFinalThreads * kFinalPer / k;
   if (blocks < 1) blocks = 1;
