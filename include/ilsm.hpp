@@ -13,6 +13,7 @@
 //   laserCloudHandler             scanRegistration.cpp:189-669              ilsm::ScanRegistration
 //   process()                     laserMapping.cpp:233-1166                 ilsm::LaserMapping
 //   mapOptimizationCallback       mapOptimization.cpp:99-500                ilsm::MapOptimization
+//   the three LiDAR nodes chained (/os_cloud_node/points -> poses)           ilsm::LoamPipeline (synchronous or pipelined)
 //   callback() (odometry merge)   odom_handler_node.cpp:44-132              ilsm::OdomHandler (host arithmetic only)
 //   nh.param / getParam           spot.yaml + spot.launch:4-6               ilsm::Config (load_yaml / load_launch)
 //
@@ -545,6 +546,55 @@ class MapOptimization {
  private:
   ContextPtr ctx_;
   ilsm_mapopt* mo_ = nullptr;
+};
+
+// The three LiDAR nodes chained on one GPU (ilsm_slam): scanRegistration -> laserOdometry -> laserMapping, inter-node
+// clouds resident in HBM.  pipelined = true runs laserMapping as its own stage (second context + host thread inside the
+// handle, like the reference's separate node): frame() then returns the mapped pose of the PREVIOUS frame
+// (has_mapped_pose false on the first call) and flush() the last one.
+class LoamPipeline {
+ public:
+  LoamPipeline(float lineRes = 0.4f, float planeRes = 0.8f, float minimum_range = 0.3f, bool pipelined = false,
+               int cube_capacity = 0, ContextPtr ctx = Context::shared())
+      : ctx_(std::move(ctx)), pipelined_(pipelined) {
+    check(pipelined ? ilsm_slam_create_async(ctx_->get(), lineRes, planeRes, minimum_range, cube_capacity, &slam_)
+                    : ilsm_slam_create(ctx_->get(), lineRes, planeRes, minimum_range, cube_capacity, &slam_),
+          "ilsm_slam_create");
+  }
+  ~LoamPipeline() { ilsm_slam_destroy(slam_); }
+  LoamPipeline(const LoamPipeline&) = delete;
+  LoamPipeline& operator=(const LoamPipeline&) = delete;
+  double q_odom[4] = {0, 0, 0, 1}, t_odom[3] = {0, 0, 0};  // /laser_odom_to_init of the frame just handed in
+  double q_map[4] = {0, 0, 0, 1}, t_map[3] = {0, 0, 0};    // /aft_mapped_to_init (previous frame's in pipelined mode)
+  bool has_mapped_pose = false;
+  ilsm_slam_stats stats;
+  template <typename CloudT>
+  void frame(const CloudT& laserCloudIn, bool use_aloam = true) {
+    typedef typename std::remove_reference<decltype(laserCloudIn.points[0])>::type P;
+    const int n = (int)laserCloudIn.points.size();
+    if (pipelined_) {
+      int have = 0;
+      check(ilsm_slam_frame_async(slam_, cloud_ptr(laserCloudIn), n, (int)sizeof(P), use_aloam ? 1 : 0, q_odom, t_odom, q_map, t_map,
+                                  &have, &stats), "ilsm_slam_frame_async");
+      has_mapped_pose = have != 0;
+    } else {
+      check(ilsm_slam_frame(slam_, cloud_ptr(laserCloudIn), n, (int)sizeof(P), use_aloam ? 1 : 0, q_odom, t_odom, q_map, t_map, &stats),
+            "ilsm_slam_frame");
+      has_mapped_pose = true;
+    }
+  }
+  bool flush() {  // pipelined mode: the mapped pose of the last frame; false when nothing was in flight
+    int have = 0;
+    check(ilsm_slam_flush(slam_, q_map, t_map, &have, &stats), "ilsm_slam_flush");
+    has_mapped_pose = have != 0;
+    return has_mapped_pose;
+  }
+  ilsm_slam* handle() const { return slam_; }
+
+ private:
+  ContextPtr ctx_;
+  ilsm_slam* slam_ = nullptr;
+  bool pipelined_;
 };
 
 // ------------------------------------------------------------------------------------------------ parameters

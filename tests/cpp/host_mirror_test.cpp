@@ -84,14 +84,14 @@ static float cast(const double o[3], const double d[3]) {
   return (float)best;
 }
 
-static Cloud make_frame(int H, int W, const double origin[3], double yaw, unsigned seed) {
+static Cloud make_frame(int H, int W, const double origin[3], double yaw, unsigned seed, double half_fov_deg = 22.0) {
   std::mt19937 rng(seed);
   std::normal_distribution<float> noise(0.f, 0.005f);
   std::uniform_real_distribution<float> inten(0.f, 255.f);
   Cloud c;
   c.points.resize((size_t)H * W);
   for (int u = 0; u < H; ++u) {
-    const double el = (22.0 - 44.0 * u / (H - 1)) * M_PI / 180.0;
+    const double el = (half_fov_deg - 2.0 * half_fov_deg * u / (H - 1)) * M_PI / 180.0;
     for (int v = 0; v < W; ++v) {
       // columns offset by a fraction of a step: no azimuth sits exactly on the +-pi/2 wrap thresholds of
       // scanRegistration.cpp:330-352, where the last ulp of atan2f (libm vs CUDA) would decide relTime
@@ -307,6 +307,38 @@ static void test_scan_to_map_registration() {
   EXPECT(!reg.align(few, surfMap, cornerStack, surfStack, parameters));
 }
 
+static void test_loam_pipeline() {
+  std::printf("LoamPipeline: synchronous vs pipelined mapping stage (same poses, one call later)\n");
+  // an OS0-like +-45 deg sensor: the 64-ring formula keeps the beams within +-22.5 deg (scanRegistration.cpp:308-316), which
+  // also keeps the less-flat cloud under the 16384 points one ilsm_slam_frame call accepts per feature cloud
+  const int H = 64, W = 1024, F = 6;
+  std::vector<Cloud> frames;
+  for (int k = 0; k < F; ++k) {
+    const double origin[3] = {0.5 + 0.15 * k, -0.3 + 0.02 * k, 0.0};
+    frames.push_back(make_frame(H, W, origin, 0.3 + 0.01 * k, 100 + k, 45.0));
+  }
+  ilsm::LoamPipeline sync(0.4f, 0.8f, 0.3f, false), pipe(0.4f, 0.8f, 0.3f, true);  // default cube capacity (16384 points per cube)
+  std::vector<std::vector<double>> mapped_sync, mapped_pipe;
+  for (int k = 0; k < F; ++k) {
+    sync.frame(frames[k]);
+    pipe.frame(frames[k]);
+    EXPECT(sync.has_mapped_pose && pipe.has_mapped_pose == (k > 0));
+    for (int i = 0; i < 4; ++i) EXPECT(sync.q_odom[i] == pipe.q_odom[i]);
+    for (int i = 0; i < 3; ++i) EXPECT(sync.t_odom[i] == pipe.t_odom[i]);
+    mapped_sync.push_back({sync.q_map[0], sync.q_map[1], sync.q_map[2], sync.q_map[3], sync.t_map[0], sync.t_map[1], sync.t_map[2]});
+    if (pipe.has_mapped_pose)
+      mapped_pipe.push_back({pipe.q_map[0], pipe.q_map[1], pipe.q_map[2], pipe.q_map[3], pipe.t_map[0], pipe.t_map[1], pipe.t_map[2]});
+  }
+  EXPECT(pipe.flush());
+  mapped_pipe.push_back({pipe.q_map[0], pipe.q_map[1], pipe.q_map[2], pipe.q_map[3], pipe.t_map[0], pipe.t_map[1], pipe.t_map[2]});
+  EXPECT(!pipe.flush());
+  EXPECT(mapped_pipe == mapped_sync);
+  EXPECT(sync.stats.n_less_flat > 500);
+  // informational: the sensor moved by (0.75, 0.10) m in the world, i.e. (0.746, -0.126) m in the first sensor frame (yaw 0.3)
+  std::printf("  mapped translation after %d frames: %.3f %.3f %.3f (sensor displacement in the map frame: 0.746 -0.126 0.000)\n", F,
+              sync.t_map[0], sync.t_map[1], sync.t_map[2]);
+}
+
 static void test_scancontext() {
   std::printf("SCManager::makeAndSaveScancontextAndKeys / detectLoopClosureID vs restatement\n");
   ilsm::SCManager sc;
@@ -409,6 +441,7 @@ int main(int argc, char** argv) {
     test_ikd_tree();
     test_image_handler_and_scan_registration();
     test_scan_to_map_registration();
+    test_loam_pipeline();
     test_scancontext();
   } catch (const ilsm::Error& e) {
     std::printf("ilsm::Error %d: %s\n", e.code, e.what());
