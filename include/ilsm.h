@@ -251,7 +251,8 @@ ILSM_API int ilsm_cubemap_insert_world(ilsm_cubemap* cm, const float* corner, in
  * less-sharp / less-flat clouds in the sensor frame, (q_wodom, t_wodom) the odometry pose; returns the mapped pose
  * (q_w, t_w).  transformAssociateToMap, window roll, 5x5x3 gather, stack VoxelGrid, guarded 2 x (associate + Solve),
  * transformUpdate, insertion of the stack at the optimised pose and per-cube VoxelGrid of the valid cubes.  The
- * map and q/t_wmap_wodom persist in the handle.  At most 16384 points per feature cloud. */
+ * map and q/t_wmap_wodom persist in the handle.  Feature clouds of any size below 2^24 points (clouds above 16384
+ * points take the tiled multi-block VoxelGrid); the DOWN-SAMPLED stacks must fit 16384 points each. */
 ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int nc, const float* surf_last, int ns,
                                 int stride_bytes, const double q_wodom_xyzw[4], const double t_wodom[3], double q_w_xyzw[4],
                                 double t_w[3], const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_cubemap_stats* stats);

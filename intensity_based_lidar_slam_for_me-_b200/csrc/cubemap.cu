@@ -359,7 +359,7 @@ int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_
     const int ioff = stride_bytes >= 32 ? 4 : 3;
     ILSM_CUDA(cudaMemsetAsync(m.stack_n.p, 0, 4 * sizeof(int), c.stream));
     if ((rc = c.voxelgrid_pair_dev(d_c, nc, m.line_res, m.stack_c.p, d_s, ns, m.plane_res, m.stack_s.p, stride_bytes, ioff,
-                                   m.stack_n.p, c.stream)))
+                                   m.stack_n.p, c.stream, m.err.p)))
       return rc;
   }
   // pose in
@@ -446,7 +446,7 @@ int cubemap_frame_collect(CubeMapH& m, double q_w[4], double t_w[3], ilsm_reg_re
   }
   if (pin_i[0]) {
     char msg[160];
-    snprintf(msg, sizeof(msg), "cube map: capacity exceeded (flags 0x%x: 16 stack>16384, 32 cube slab full, 64 cube>16384, 2 leaf too small)", pin_i[0]);
+    snprintf(msg, sizeof(msg), "cube map: capacity exceeded (flags 0x%x: 16 down-sampled stack>16384, 32 cube slab full, 64 cube>16384, 2 leaf too small)", pin_i[0]);
     cudaMemsetAsync(m.err.p, 0, sizeof(int), c.stream);
     return fail(ILSM_ERR_OUT_OF_MEMORY, msg);
   }
@@ -561,8 +561,8 @@ ILSM_API int ilsm_cubemap_frame(ilsm_cubemap* cm, const float* corner_last, int 
                                 const ilsm_reg_opts* opts, ilsm_reg_report* report, ilsm_cubemap_stats* stats) {
   if (!cm || !q_wodom || !t_wodom || !q_w || !t_w || (nc > 0 && !corner_last) || (ns > 0 && !surf_last))
     return fail(ILSM_ERR_INVALID_ARG, "cubemap_frame: null argument");
-  if (nc < 0 || ns < 0 || stride_bytes < 16 || stride_bytes % 4 || nc > kVoxelBlockMax || ns > kVoxelBlockMax)
-    return fail(ILSM_ERR_INVALID_ARG, "cubemap_frame: bad n/stride (at most 16384 points per feature cloud)");
+  if (nc < 0 || ns < 0 || stride_bytes < 16 || stride_bytes % 4 || nc >= (1 << 24) || ns >= (1 << 24))
+    return fail(ILSM_ERR_INVALID_ARG, "cubemap_frame: bad n/stride (fewer than 2^24 points per feature cloud)");
   CubeMapH& m = cm->m;
   Ctx& c = *m.ctx;
   std::lock_guard<std::mutex> lk(c.mu);

@@ -943,26 +943,51 @@ int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int
   return check_launch("voxelgrid");
 }
 
-// The corner and surf stacks of a frame in ONE launch (two blocks) on stream `s`: host-side counts, packed xyzi inputs.
+// The corner and surf stacks of a frame on stream `s`: ONE launch (two blocks) when both clouds fit a block, the tiled
+// multi-block path for a cloud that does not (a 64-ring sensor that keeps all its beams produces ~25 k less-flat points,
+// scanRegistration.cpp:570-589).  err = the error word the kernels OR their flags into (the caller's own, so that a
+// VoxelGrid running on a side stream never shares a word with the front end that resets its own).
 int Ctx::voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
-                            float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s) {
-  if (nc > kVoxelMax || ns > kVoxelMax) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: more than 16384 points per cloud");
+                            float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s, int* d_err) {
   int rc;
   if ((rc = fe.vox_packed.reserve((size_t)2 * kVoxelMax + 8)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
+  if (!d_err) d_err = fe.stats.p + kStErr;
   ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelMax * sizeof(u64))));
-  const int big = nc > ns ? nc : ns;
-  int P = 1;
-  while (P < big) P <<= 1;
-  VoxJobs jobs = {};
-  jobs.j[0] = VoxJob{d_c, nullptr, fe.vox_packed.p, d_out_c, d_n_out2, nc, 0, stride_bytes / 4, ioff, leaf_c};
-  jobs.j[1] = VoxJob{d_s, nullptr, fe.vox_packed.p + kVoxelMax, d_out_s, d_n_out2 + 1, ns, 0, stride_bytes / 4, ioff, leaf_s};
-  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), (size_t)P * sizeof(u64), s, jobs, fe.stats.p + kStErr));
-  count_launches(1);
-  return check_launch("voxelgrid_pair");
+  const bool big_c = nc > kVoxelMax, big_s = ns > kVoxelMax;
+  if (!big_c && !big_s) {
+    const int big = nc > ns ? nc : ns;
+    int P = 1;
+    while (P < big) P <<= 1;
+    VoxJobs jobs = {};
+    jobs.j[0] = VoxJob{d_c, nullptr, fe.vox_packed.p, d_out_c, d_n_out2, nc, 0, stride_bytes / 4, ioff, leaf_c};
+    jobs.j[1] = VoxJob{d_s, nullptr, fe.vox_packed.p + kVoxelMax, d_out_s, d_n_out2 + 1, ns, 0, stride_bytes / 4, ioff, leaf_s};
+    ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), (size_t)P * sizeof(u64), s, jobs, d_err));
+    count_launches(1);
+    return check_launch("voxelgrid_pair");
+  }
+  // at least one cloud needs the tiled path: the clouds go one after the other on `s` (they share the scratch buffers)
+  const float* in[2] = {d_c, d_s};
+  const int n[2] = {nc, ns};
+  const float leaf[2] = {leaf_c, leaf_s};
+  float4* out[2] = {d_out_c, d_out_s};
+  for (int k = 0; k < 2; ++k) {
+    if (n[k] > kVoxelMax) {
+      if ((rc = voxelgrid_large_dev(in[k], n[k], stride_bytes, ioff, leaf[k], out[k], d_n_out2 + k, s, d_err))) return rc;
+    } else {
+      int P = 1;
+      while (P < n[k]) P <<= 1;
+      VoxJobs jobs = {};
+      jobs.j[0] = VoxJob{in[k], nullptr, fe.vox_packed.p, out[k], d_n_out2 + k, n[k], 0, stride_bytes / 4, ioff, leaf[k]};
+      ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), s, jobs, d_err));
+      count_launches(1);
+    }
+  }
+  return check_launch("voxelgrid_pair(large)");
 }
 
 // VoxelGrid of n > 16384 points (up to 2^24): see the vg_* kernels above.  d_n_out receives the voxel count.
-int Ctx::voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out) {
+int Ctx::voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out,
+                             cudaStream_t s, int* d_err) {
   if (n >= (1 << 24)) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: at most 2^24 points");
   unsigned P = kVgTile;
   while (P < (unsigned)n) P <<= 1;
@@ -971,14 +996,15 @@ int Ctx::voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int iof
   if ((rc = fe.vox_packed.reserve((size_t)n + 8)) || (rc = fe.vg_keys.reserve(P)) || (rc = fe.vg_state.reserve(1)) ||
       (rc = fe.vg_chunk.reserve(2 * (size_t)chunks + 8)) || (rc = fe.stats.reserve(kStInts + 8)))
     return rc;
-  cudaStream_t s = stream;
+  if (!s) s = stream;
+  if (!d_err) d_err = fe.stats.p + kStErr;
   ILSM_CUDA(cudaFuncSetAttribute(vg_sort_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVgTile * sizeof(u64))));
   const int grid = sm_count * 4;
   int launches = 0;
   ILSM_CUDA(launch_pdl(vg_init_kernel, dim3(1), dim3(32), 0, s, fe.vg_state.p));
   ILSM_CUDA(launch_pdl(vg_pack_bbox_kernel, dim3(grid), dim3(256), 0, s, d_in, n, stride_bytes / 4, ioff, fe.vox_packed.p, fe.vg_state.p));
   ILSM_CUDA(launch_pdl(vg_keys_kernel, dim3(grid), dim3(256), 0, s, (const float4*)fe.vox_packed.p, n, (int)P, leaf,
-                       (const VgState*)fe.vg_state.p, fe.vg_keys.p, fe.stats.p + kStErr));
+                       (const VgState*)fe.vg_state.p, fe.vg_keys.p, d_err));
   ILSM_CUDA(launch_pdl(vg_sort_tile_kernel, dim3(P / kVgTile), dim3(1024), kVgTile * sizeof(u64), s, fe.vg_keys.p, 0u, 0));
   launches += 4;
   for (unsigned k = 2u * kVgTile; k <= P; k <<= 1) {

@@ -233,9 +233,10 @@ struct Ctx {
   int pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layout& l, float4* d_out);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);
-  int voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out);
+  int voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out,
+                          cudaStream_t s = nullptr, int* d_err = nullptr);
   int voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
-                         float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s);
+                         float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s, int* d_err = nullptr);
   int gather_dev(const float4* d_cloud, const int* d_idx, const int* d_counts, int slot, int max_n, float4* d_out);
   int register_dev(Map* mc, Map* ms, const float* d_corner, int nc, const float* d_surf, int ns, int stride_bytes,
                    const ilsm_reg_opts& o, const PoseSrc* src = nullptr, const PoseDst* dst = nullptr);

@@ -357,8 +357,8 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
     ILSM_CUDA(cudaEventRecord(s.ev_fe[slot], c.stream));
   }
   // ---- the mapping stacks (VoxelGrid of the less-sharp / less-flat clouds, laserMapping.cpp:608-616) depend only on the
-  // front end: they run on the side stream while the odometry solves on the main one
-  if (n_lsharp > 16384 || n_lflat > 16384) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: feature cloud exceeds 16384 points");
+  // front end: they run on the side stream while the odometry solves on the main one.  Clouds above 16384 points take
+  // the tiled multi-block VoxelGrid (no size limit below 2^24 points, like the reference).
   CubeMapH* cmp = s.cube ? &s.cube->m : nullptr;
   if (cmp) {
     CubeMapH& cm = *cmp;  // (pipelined mode: the mapping thread is idle here -- its previous result has been taken above)
@@ -368,9 +368,13 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
     // pipelined mode: the previous frame's deferred insertion (second context's side stream) still reads the stacks
     if (s.async && cm.tail_pending) ILSM_CUDA(cudaStreamWaitEvent(c.aux, cm.ev_tail, 0));
     ILSM_CUDA(cudaMemsetAsync(cm.stack_n.p, 0, 4 * sizeof(int), c.aux));
+    // Pipelined mode: the side stream reads the PER-FRAME copy of the less-flat cloud -- the next call's front end
+    // rewrites fe.lflat (and resets the front end's error word) while this VoxelGrid may still be running, and nothing
+    // orders the main stream after it there.  The VoxelGrid reports into the cube map's own error word.
+    const float4* d_lflat_vg = s.async ? s.lflat2[slot].p : c.fe.lflat.p;
     if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(d_lsharp), n_lsharp, cm.line_res, cm.stack_c.p,
-                                   reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
-                                   cm.stack_n.p, c.aux)))
+                                   reinterpret_cast<const float*>(d_lflat_vg), n_lflat, cm.plane_res, cm.stack_s.p, 16, 3,
+                                   cm.stack_n.p, c.aux, cm.err.p)))
       return rc;
     ILSM_CUDA(cudaEventRecord(c.ev_join, c.aux));
   }

@@ -18,13 +18,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+_REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
 
 
 def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present)."""
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
     stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
-    need_ref = (not os.path.exists(_REF)) and os.path.exists("/root/reference/include/nanoflann.hpp")
+    need_ref = ((not os.path.exists(_REF)) and os.path.exists("/root/reference/include/nanoflann.hpp")) or \
+        ((not os.path.exists(_REF_IKD)) and os.path.exists("/root/reference/src/ikd-Tree/ikd_Tree.cpp"))
     if force or stale or need_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
 
@@ -333,6 +335,78 @@ def ikd_add_points(existing_xyz, add_xyz, ds, downsample=True):
     out = np.zeros((len(e) + len(a) + 1, 3), np.float32)
     n = lib().orc_ikd_add_points(_p(e), len(e), _p(a), len(a), C.c_float(ds), 1 if downsample else 0, _p(out), len(out))
     return out[:n].copy()
+
+
+_ref_ikd = None
+
+
+def ref_ikd():
+    """The reference's own ikd-Tree, oracle/_ref/libref_ikd.so (None when it was never built)."""
+    global _ref_ikd
+    if _ref_ikd is None:
+        if not os.path.exists(_REF_IKD):
+            build()
+        if not os.path.exists(_REF_IKD):
+            return None
+        r = C.CDLL(_REF_IKD)
+        r.ref_ikd_create.restype = C.c_void_p
+        r.ref_ikd_create.argtypes = [C.c_float, C.c_float, C.c_float]
+        r.ref_ikd_free.argtypes = [C.c_void_p]
+        r.ref_ikd_size.argtypes = [C.c_void_p]
+        r.ref_ikd_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        r.ref_ikd_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        r.ref_ikd_add_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        r.ref_ikd_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _ref_ikd = r
+    return _ref_ikd
+
+
+class RefIkdTree:
+    """KD_TREE<pcl::PointXYZ> of the reference (src/ikd-Tree), the way mapOptimization.cpp:504 constructs it:
+    (delete criterion 0.3, balance criterion 0.6, down-sample box 0.4)."""
+
+    def __init__(self, delete_param=0.3, balance_param=0.6, box_length=0.4):
+        self._r = ref_ikd()
+        if self._r is None:
+            raise RuntimeError("oracle/_ref/libref_ikd.so not available")
+        self._h = self._r.ref_ikd_create(delete_param, balance_param, box_length)
+
+    def build(self, xyz):  # Build(points)  mapOptimization.cpp:192
+        a = _f32(xyz)
+        self._r.ref_ikd_build(self._h, _p(a), len(a), _stride(a))
+        return self
+
+    def size(self):
+        return self._r.ref_ikd_size(self._h)
+
+    def nearest(self, q_xyz, k=5):  # Nearest_Search  mapOptimization.cpp:393 -> (points nq x k x 3, d2 nq x k, found nq)
+        q = _f32(q_xyz)
+        pts = np.full((len(q), k, 3), np.nan, np.float32)
+        d2 = np.full((len(q), k), np.inf, np.float32)
+        cnt = np.zeros(len(q), np.int32)
+        self._r.ref_ikd_nearest(self._h, _p(q), len(q), _stride(q), k, _p(pts), _p(d2), _p(cnt))
+        return pts, d2, cnt
+
+    def add_points(self, xyz, downsample=True):  # Add_Points(points, true)  mapOptimization.cpp:475
+        a = _f32(xyz)
+        return self._r.ref_ikd_add_points(self._h, _p(a), len(a), _stride(a), 1 if downsample else 0)
+
+    def points(self):  # flatten(Root_Node, storage, NOT_RECORD): tree order
+        n = self.size()
+        out = np.zeros((n + 16, 3), np.float32)
+        m = self._r.ref_ikd_flatten(self._h, _p(out), len(out))
+        return out[:m].copy()
+
+    def close(self):
+        if self._h:
+            self._r.ref_ikd_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ------------------------------------------------------------------------------------------------
