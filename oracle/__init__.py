@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
+_REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 
 
 def build(force: bool = False) -> None:
@@ -26,7 +27,8 @@ def build(force: bool = False) -> None:
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
     stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
     need_ref = ((not os.path.exists(_REF)) and os.path.exists("/root/reference/include/nanoflann.hpp")) or \
-        ((not os.path.exists(_REF_IKD)) and os.path.exists("/root/reference/src/ikd-Tree/ikd_Tree.cpp"))
+        ((not os.path.exists(_REF_IKD)) and os.path.exists("/root/reference/src/ikd-Tree/ikd_Tree.cpp")) or \
+        ((not os.path.exists(_REF_FUN)) and os.path.exists("/root/reference/src/lidarFeaturePointsFunction.hpp"))
     if force or stale or need_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
 
@@ -335,6 +337,37 @@ def ikd_add_points(existing_xyz, add_xyz, ds, downsample=True):
     out = np.zeros((len(e) + len(a) + 1, 3), np.float32)
     n = lib().orc_ikd_add_points(_p(e), len(e), _p(a), len(a), C.c_float(ds), 1 if downsample else 0, _p(out), len(out))
     return out[:n].copy()
+
+
+_ref_fun = None
+
+
+def ref_functors():
+    """The reference's own Ceres cost functors on dual numbers, oracle/_ref/libref_functors.so (None when never built)."""
+    global _ref_fun
+    if _ref_fun is None:
+        if not os.path.exists(_REF_FUN):
+            build()
+        if not os.path.exists(_REF_FUN):
+            return None
+        r = C.CDLL(_REF_FUN)
+        r.ref_functor_eval.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 4
+        _ref_fun = r
+    return _ref_fun
+
+
+def ref_functor_eval(ftype, p, a, b=(0, 0, 0), c=(0, 0, 0), s=1.0, qt=(0, 0, 0, 1, 0, 0, 0)):
+    """One reference functor at pose qt = (qx, qy, qz, qw, tx, ty, tz): (residuals (R,), ambient Jacobian (R, 7)).
+    ftype: 1 LidarEdgeFactor(p, a, b, s); 2 LidarPlaneNormFactor(p, n = a, d = b[0]); 3 front_end_residual(src = p,
+    dst = a); 4 LidarPlaneFactor(p, j = a, l = b, m = c, s)."""
+    arr = [np.ascontiguousarray(v, np.float64) for v in (p, a, b, c)]
+    qt = np.ascontiguousarray(qt, np.float64)
+    q, t = qt[:4].copy(), qt[4:].copy()
+    r = np.zeros(3)
+    J = np.zeros((3, 7))
+    n = ref_functors().ref_functor_eval(int(ftype), _p(arr[0]), _p(arr[1]), _p(arr[2]), _p(arr[3]), C.c_double(s), _p(q), _p(t),
+                                        _p(r), _p(J))
+    return r[:n].copy(), J[:n].copy()
 
 
 _ref_ikd = None

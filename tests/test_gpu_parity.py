@@ -387,3 +387,36 @@ def test_eval_normal_eq_is_additive_over_factor_sets(ctx, cfg_small):
     assert np.abs(Hk - k * H1).max() <= 1e-12 * k * np.abs(H1).max()
     assert np.abs(gk - k * g1).max() <= 1e-11 * k * np.abs(g1).max()
     mc.close(), ms.close()
+
+
+def test_gpu_evaluation_matches_reference_functors(ctx, oracle_mod, cfg_small):
+    """The CUDA evaluation (cost, J^T J, J^T r) against the REFERENCE'S OWN Ceres functors
+    (lidarFeaturePointsFunction.hpp on dual numbers, oracle/_ref/libref_functors.so -- prebuilt, it travels with the
+    snapshot): factors from the GPU association, the loss switched off (huber_a = 0), and with HuberLoss(0.1) applied
+    to the reference residual blocks through Ceres' corrector (rho'' <= 0: residual and Jacobian scaled by sqrt(rho'))."""
+    if oracle_mod.ref_functors() is None:
+        pytest.skip("oracle/_ref/libref_functors.so not available")
+    from test_ref_functors_cpu import tangent
+    c = cfg_small
+    qt = np.concatenate([c["q0"], c["t0"]])
+    mc = ctx.new_map().set_input_cloud(c["map_corner"])
+    ms = ctx.new_map().set_input_cloud(c["map_surf"])
+    fac = ctx.associate(mc, ms, c["corner"], c["surf"], c["q0"], c["t0"])
+    assert (fac["type"] == 1).sum() > 20 and (fac["type"] == 2).sum() > 100
+    for huber in (0.0, 0.1):
+        cost_r, H_r, g_r = 0.0, np.zeros((6, 6)), np.zeros(6)
+        for rec in fac[fac["type"] != 0]:
+            r, J = oracle_mod.ref_functor_eval(int(rec["type"]), rec["p"], rec["a"], rec["b"], (0, 0, 0), 1.0, qt)
+            Jt = tangent(J, qt[:4])
+            s = float(r @ r)
+            rho0, sc = s, 1.0
+            if huber > 0 and s > huber * huber:
+                rho0, sc = 2 * huber * np.sqrt(s) - huber * huber, np.sqrt(huber / np.sqrt(s))
+            cost_r += 0.5 * rho0
+            H_r += (sc * Jt).T @ (sc * Jt)
+            g_r += (sc * Jt).T @ (sc * r)
+        cost, H, g = ctx.eval_normal_eq(c["q0"], c["t0"], huber)
+        # north_star: residuals within 1e-5 relative (observed ~1e-13)
+        assert abs(cost - cost_r) <= 1e-9 * cost_r, huber
+        assert np.abs(H - H_r).max() <= 1e-9 * np.abs(H_r).max() and np.abs(g - g_r).max() <= 1e-9 * np.abs(g_r).max(), huber
+    mc.close(), ms.close()
