@@ -526,8 +526,9 @@ ILSM_API int ilsm_sc_add_dev(ilsm_sc* sc, const float* d_desc_20x60, int count);
  * NUM_EXCLUDE_RECENT = 50 entries like Scancontext.cpp:270-275) with distanceBtnScanContext -- sector-key alignment
  * over 60 shifts, column-cosine distance on the 7 shifts around it, first minimum wins -- and return the k <= 16
  * best by (distance, id).  id_offset is added to the returned ids (global id of this shard's first entry).
- * Replaces: Scancontext.cpp:79-157 and the candidate loop :299-312 (scored over every entry, a superset of the
- *           reference's 10 ring-key candidates). */
+ * Replaces: Scancontext.cpp:79-157 and the candidate loop :299-312, scored over EVERY entry: a superset of the
+ *           reference's 10 ring-key candidates, so it can report a closer entry than the reference finds -- the
+ *           reference-exact search is ilsm_sc_query_candidates below. */
 ILSM_API int ilsm_sc_query_topk(ilsm_sc* sc, const float* desc_20x60, int n_search, int id_offset, int k, double* dist,
                                 int32_t* id, int32_t* shift);
 ILSM_API int ilsm_sc_query_topk_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_search, int id_offset, int k,
@@ -542,6 +543,49 @@ ILSM_API int ilsm_sc_merge_topk(const double* dist, const int32_t* id, const int
  * k x f64 distance | k x i32 id | k x i32 shift (16 k bytes); ilsm_sc_query_topk_dev can write it directly with
  * d_dist = base, d_id = base + 8 k, d_shift = base + 12 k. */
 ILSM_API int ilsm_sc_merge_topk_dev(ilsm_sc* sc, const void* d_packed, int shards, int k, void* d_out_packed);
+
+/* detectLoopClosureID's own two steps over database entries [0, n_search) (n_search < 0: all; the caller passes the
+ * size of the ring-key tree at its last refresh, i.e. it excludes the most recent NUM_EXCLUDE_RECENT = 50 entries and
+ * applies TREE_MAKING_PERIOD_ like Scancontext.cpp:270-282):
+ *   1. the num_candidates (<= 16; NUM_CANDIDATES_FROM_TREE = 10) nearest FLOAT ring keys -- polarcontext_invkeys_mat_,
+ *      row means cast to float -- under the L2 metric as nanoflann's L2_Adaptor<float> evaluates it (groups of four,
+ *      no FMA), ascending (distance, index): the result set of polarcontext_tree_->index->findNeighbors (:289-295);
+ *   2. distanceBtnScanContext (:126-157) for exactly those entries.
+ * cand_id / cand_key_d2 / cand_dist / cand_shift receive num_candidates entries in candidate order (id -1, distance
+ * +inf when the database is smaller); the caller's `candidate_dist < min_dist` loop and SC_DIST_THRES test (:299-323)
+ * then give the reference's loop id and yaw difference.  cand_key_d2 may be NULL.
+ * Replaces: SCManager::detectLoopClosureID  Scancontext.cpp:283-312 (same candidates, same result). */
+ILSM_API int ilsm_sc_query_candidates(ilsm_sc* sc, const float* desc_20x60, int n_search, int num_candidates, int32_t* cand_id,
+                                      float* cand_key_d2, double* cand_dist, int32_t* cand_shift);
+
+/* n_queries descriptors (contiguous, 1200 floats each) scored against entries [0, n_search) in one call; outputs are
+ * [n_queries][k].  The _dev form takes device descriptors and writes n_queries packed records (16 k bytes each, the
+ * layout of ilsm_sc_merge_topk_dev) without synchronising. */
+ILSM_API int ilsm_sc_query_topk_batch(ilsm_sc* sc, const float* desc_20x60, int n_queries, int n_search, int id_offset, int k,
+                                      double* dist, int32_t* id, int32_t* shift);
+ILSM_API int ilsm_sc_query_topk_batch_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_queries, int n_search, int id_offset, int k,
+                                          void* d_packed);
+
+/* The keyframe database sharded over n_ranks processes (one per GPU), contiguous id ranges: every rank holds its
+ * shard in its own ilsm_sc and the ranks share an NCCL communicator.  ilsm_sc_init_nccl adopts a communicator the
+ * host already owns (ncclComm_t passed as void*; it is not destroyed with the handle); ilsm_sc_nccl_unique_id +
+ * ilsm_sc_init_nccl_rank create one (rank 0 makes the 128-byte id, the host distributes it by its own means, every
+ * rank calls init_nccl_rank -- a collective call).  NCCL is loaded with dlopen at the first of these calls. */
+ILSM_API int ilsm_sc_nccl_unique_id(char id_out[128]);
+ILSM_API int ilsm_sc_init_nccl_rank(ilsm_sc* sc, const char id[128], int n_ranks, int rank);
+ILSM_API int ilsm_sc_init_nccl(ilsm_sc* sc, void* nccl_comm, int n_ranks, int rank);
+ILSM_API int ilsm_sc_nccl_version(int* version);
+
+/* A sharded query batch -- a COLLECTIVE call, every rank passes the same descriptors: the local shard is scored
+ * (entries [0, n_search) of this rank, ids reported as id_offset + local index), the per-rank packed top-k records of
+ * the whole batch are exchanged with ONE ncclAllGather (n_queries x 16 k bytes per rank) and merged by the same
+ * deterministic kernel on every rank (ascending (distance, id)); nothing visits the host in between.  Every rank
+ * receives the global top-k.  Without a communicator (n_ranks 1) it degenerates to ilsm_sc_query_topk_batch.
+ * Replaces: the candidate scoring of Scancontext.cpp:299-312 over a database split across GPUs (BASELINE configs[4]). */
+ILSM_API int ilsm_sc_query_topk_sharded(ilsm_sc* sc, const float* desc_20x60, int n_queries, int n_search, int id_offset, int k,
+                                        double* dist, int32_t* id, int32_t* shift);
+ILSM_API int ilsm_sc_query_topk_sharded_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_queries, int n_search, int id_offset, int k,
+                                            void* d_packed_out);
 
 #ifdef __cplusplus
 }

@@ -330,22 +330,41 @@ class SCManager {
       return;
     warn(ilsm_sc_add(sc_, last_.data(), 1), "makeAndSaveScancontextAndKeys");
   }
-  // SCManager::detectLoopClosureID   Scancontext.cpp:253-344: {loop id or -1, yaw difference in radians}.  The candidate
-  // window follows the reference: entries [0, size - NUM_EXCLUDE_RECENT) as of the last tree rebuild (every
-  // TREE_MAKING_PERIOD_ calls).  All of them are scored on the GPU (a superset of the reference's 10 ring-key
-  // candidates), best (distance, id) wins, SC_DIST_THRES decides.
+  // SCManager::detectLoopClosureID   Scancontext.cpp:253-344: {loop id or -1, yaw difference in radians}.
+  // Reference-exact by default: the search window is entries [0, size - NUM_EXCLUDE_RECENT) as of the last tree rebuild
+  // (every TREE_MAKING_PERIOD_ calls, :270-282), the NUM_CANDIDATES_FROM_TREE nearest float ring keys are selected and
+  // only those are scored (ilsm_sc_query_candidates), the first strictly smaller candidate distance wins (:299-312),
+  // SC_DIST_THRES decides.  exhaustive_search = true scores EVERY entry of the window instead (a superset: it can find
+  // a loop the ring-key pre-selection misses, so its answer may differ from the reference's).
+  bool exhaustive_search = false;
   std::pair<int, float> detectLoopClosureID() {
     const int n = ilsm_sc_size(sc_);
     if (n < NUM_EXCLUDE_RECENT + 1 || last_.empty()) return std::make_pair(-1, 0.0f);
     if (tree_making_period_conter % TREE_MAKING_PERIOD_ == 0) n_search_ = n - NUM_EXCLUDE_RECENT;
     tree_making_period_conter += 1;
-    double dist = 0;
-    int32_t id = -1, shift = 0;
-    if (n_search_ <= 0 || !warn(ilsm_sc_query_topk(sc_, last_.data(), n_search_, 0, 1, &dist, &id, &shift), "detectLoopClosureID"))
-      return std::make_pair(-1, 0.0f);
-    last_dist_ = dist;
-    const float yaw_diff_rad = (float)(shift * PC_UNIT_SECTORANGLE * M_PI / 180.0);
-    return std::make_pair(dist < SC_DIST_THRES ? (int)id : -1, yaw_diff_rad);
+    double min_dist = 10000000;
+    int nn_align = 0, nn_idx = 0;
+    if (n_search_ <= 0) return std::make_pair(-1, 0.0f);
+    if (exhaustive_search) {
+      double dist = 0;
+      int32_t id = -1, shift = 0;
+      if (!warn(ilsm_sc_query_topk(sc_, last_.data(), n_search_, 0, 1, &dist, &id, &shift), "detectLoopClosureID"))
+        return std::make_pair(-1, 0.0f);
+      if (id >= 0) min_dist = dist, nn_align = shift, nn_idx = id;
+    } else {
+      int32_t cid[16], csh[16];
+      double cd[16];
+      if (!warn(ilsm_sc_query_candidates(sc_, last_.data(), n_search_, NUM_CANDIDATES_FROM_TREE, cid, nullptr, cd, csh),
+                "detectLoopClosureID"))
+        return std::make_pair(-1, 0.0f);
+      for (int i = 0; i < NUM_CANDIDATES_FROM_TREE; ++i) {
+        if (cid[i] < 0) continue;
+        if (cd[i] < min_dist) min_dist = cd[i], nn_align = csh[i], nn_idx = cid[i];
+      }
+    }
+    last_dist_ = min_dist;
+    const float yaw_diff_rad = (float)(nn_align * PC_UNIT_SECTORANGLE * M_PI / 180.0);
+    return std::make_pair(min_dist < SC_DIST_THRES ? nn_idx : -1, yaw_diff_rad);
   }
   double lastDistance() const { return last_dist_; }
   int size() const { return ilsm_sc_size(sc_); }

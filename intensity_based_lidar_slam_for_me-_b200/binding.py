@@ -146,6 +146,15 @@ def load_library(path: str | None = None):
         "ilsm_sc_query_topk_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_merge_topk_dev": (i32, [vp, vp, i32, i32, vp]),
         "ilsm_sc_merge_topk": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
+        "ilsm_sc_query_candidates": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
+        "ilsm_sc_query_topk_batch": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "ilsm_sc_query_topk_batch_dev": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "ilsm_sc_nccl_unique_id": (i32, [vp]),
+        "ilsm_sc_init_nccl_rank": (i32, [vp, vp, i32, i32]),
+        "ilsm_sc_init_nccl": (i32, [vp, vp, i32, i32]),
+        "ilsm_sc_nccl_version": (i32, [vp]),
+        "ilsm_sc_query_topk_sharded": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "ilsm_sc_query_topk_sharded_dev": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "ilsm_odometry": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, C.POINTER(RegOpts), C.POINTER(RegReport), vp]),
         "ilsm_cubemap_create": (i32, [vp, f32, f32, i32, C.POINTER(vp)]),
         "ilsm_cubemap_destroy": (None, [vp]),
@@ -537,6 +546,70 @@ class ScanContextDb:
         _check(self._lib.ilsm_sc_query_topk_dev(self._h, d_desc_ptr, n_search, id_offset, k, d_dist_ptr, d_id_ptr,
                                                 d_shift_ptr))
 
+
+    NUM_CANDIDATES_FROM_TREE = 10  # Scancontext.h:87
+    TREE_MAKING_PERIOD = 50        # Scancontext.h:95
+
+    def query_candidates(self, desc, num_candidates=10, n_search=-1):
+        """The reference's candidate search: ring-key nearest neighbours, then distanceBtnScanContext for those only.
+        Returns (ids, float key distances, distances, shifts) in candidate order."""
+        q = np.ascontiguousarray(desc, np.float32).reshape(1200)
+        k = num_candidates
+        ids, kd2 = np.zeros(k, np.int32), np.zeros(k, np.float32)
+        dist, sh = np.zeros(k), np.zeros(k, np.int32)
+        _check(self._lib.ilsm_sc_query_candidates(self._h, _ptr(q), n_search, k, _ptr(ids), _ptr(kd2), _ptr(dist), _ptr(sh)))
+        return ids, kd2, dist, sh
+
+    def detect_loop_closure_id(self, desc, n_search=-1, exhaustive=False):
+        """SCManager::detectLoopClosureID (Scancontext.cpp:283-344) for a query descriptor against entries [0, n_search):
+        (loop id or -1, min distance, aligning shift, nearest id).  exhaustive=True scores every entry instead of the
+        10 ring-key candidates (superset; may differ from the reference)."""
+        best, arg, align = 10000000.0, 0, 0
+        if exhaustive:
+            d, i, s = self.query_topk(desc, 1, n_search)
+            if i[0] >= 0:
+                best, arg, align = float(d[0]), int(i[0]), int(s[0])
+        else:
+            ids, _, dist, sh = self.query_candidates(desc, self.NUM_CANDIDATES_FROM_TREE, n_search)
+            for ci, cd, cs in zip(ids, dist, sh):
+                if ci >= 0 and cd < best:
+                    best, arg, align = float(cd), int(ci), int(cs)
+        return (arg if best < self.SC_DIST_THRES else -1), best, align, arg
+
+    def query_topk_batch(self, descs, k=10, n_search=-1, id_offset=0):
+        q = np.ascontiguousarray(descs, np.float32).reshape(-1, 1200)
+        B = len(q)
+        dist, ids, sh = np.zeros((B, k)), np.zeros((B, k), np.int32), np.zeros((B, k), np.int32)
+        _check(self._lib.ilsm_sc_query_topk_batch(self._h, _ptr(q), B, n_search, id_offset, k, _ptr(dist), _ptr(ids), _ptr(sh)))
+        return dist, ids, sh
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(load_library().ilsm_sc_nccl_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def nccl_version() -> int:
+        v = C.c_int(0)
+        _check(load_library().ilsm_sc_nccl_version(C.byref(v)))
+        return v.value
+
+    def init_nccl_rank(self, unique_id: bytes, n_ranks: int, rank: int):
+        """Collective: every rank of the sharded database calls it with rank 0's unique id."""
+        assert len(unique_id) == 128
+        _check(self._lib.ilsm_sc_init_nccl_rank(self._h, C.c_char_p(unique_id), n_ranks, rank))
+
+    def query_topk_sharded(self, descs, k=10, n_search=-1, id_offset=0):
+        """Collective: local scoring -> one NCCL all-gather for the batch -> identical merge; every rank gets the global top-k."""
+        q = np.ascontiguousarray(descs, np.float32).reshape(-1, 1200)
+        B = len(q)
+        dist, ids, sh = np.zeros((B, k)), np.zeros((B, k), np.int32), np.zeros((B, k), np.int32)
+        _check(self._lib.ilsm_sc_query_topk_sharded(self._h, _ptr(q), B, n_search, id_offset, k, _ptr(dist), _ptr(ids), _ptr(sh)))
+        return dist, ids, sh
+
+    def query_topk_sharded_dev(self, d_desc_ptr, n_queries, k, n_search, id_offset, d_packed_out_ptr):
+        _check(self._lib.ilsm_sc_query_topk_sharded_dev(self._h, d_desc_ptr, n_queries, n_search, id_offset, k, d_packed_out_ptr))
 
     def query_packed_dev(self, d_desc_ptr, k, n_search, id_offset, d_packed_ptr):
         """Local top-k written in the packed all-gather layout (k f64 dist | k i32 id | k i32 shift)."""

@@ -32,7 +32,8 @@ int check_launch(const char* where) {
 
 int eval_only_launch(Ctx* c, double* d_out, const double* d_pose7 = nullptr, double huber_a = 0.0);
 int factors_export(Ctx* c, ilsm_factor* d_out);
-int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out);
+int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out, int batch = 1, size_t shard_stride = 0);
+void sc_nccl_release(ScDb& d);  // scancontext_api.cu
 
 struct Pose7 {
   double v[7];
@@ -715,6 +716,9 @@ ILSM_API void ilsm_sc_destroy(ilsm_sc* sc) {
     ScDb& d = sc->d;
     d.db.release(), d.bins.release(), d.query.release(), d.out_dist.release(), d.part_d.release(), d.part_id.release(), d.part_sh.release();
     d.out_id.release(), d.out_shift.release(), d.stage.release();
+    d.ringkey.release(), d.rk_part.release(), d.cand_out.release(), d.pk_local.release(), d.pk_all.release(), d.pk_out.release();
+    d.qbatch.release();
+    sc_nccl_release(d);
   }
   delete sc;
 }

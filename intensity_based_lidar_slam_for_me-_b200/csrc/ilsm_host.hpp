@@ -255,7 +255,18 @@ struct ScDb {
   DevBuf<u64> part_d;      // per-block top-k lists of the scoring kernel
   DevBuf<int> part_id, part_sh;
   DevBuf<float> stage;     // staged caller descriptors / points
+  DevBuf<float> ringkey;   // [count][20] float ring keys (polarcontext_invkeys_mat_, Scancontext.cpp:243,249)
+  DevBuf<u64> rk_part;     // ring-key candidate selection: per-block lists + the selected list
+  DevBuf<unsigned char> cand_out;  // candidate query outputs (ids | key d2 | distances | shifts)
+  // sharded queries (ilsm_sc_init_nccl): per-rank packed top-k records, the all-gathered buffer, the merged result
+  void* nccl_comm = nullptr;
+  bool nccl_owned = false;
+  int nccl_ranks = 1, nccl_rank = 0;
+  DevBuf<unsigned char> pk_local, pk_all, pk_out;
+  DevBuf<float> qbatch;
   int append_dev(const float* desc, int n_add, bool from_host);
+  int query_batch_dev(const float* d_qdesc, int B, int n_search, int id_offset, int k, unsigned char* d_packed);
+  int candidates_dev(const float* d_qdesc, int n_search, int num_cand, int* d_id, float* d_key_d2, double* d_dist, int* d_shift);
   int make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc);
   int query_dev(const float* d_qdesc, int n_search, int id_offset, int k, double* d_dist, int* d_id, int* d_shift);
 };

@@ -118,9 +118,14 @@ __device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { re
 //   fastAlignUsingVkey  (Scancontext.cpp:104-124): argmin_s || qk - circshift(ck, s) ||, first minimum wins
 //   distDirectSC        (:79-101)                : 1 - mean over columns with both norms != 0 of cos(col_q, col_c)
 //   distanceBtnScanContext (:126-157)            : the 7 shifts around the aligned one, ascending, first minimum wins
+// kList: score only the entries named by cand_keys[0, n) (low word = database index; ~0 = none) and write each one's
+// (distance, shift) to list_dist / list_shift in list order -- the candidate loop of detectLoopClosureID
+// (Scancontext.cpp:299-312) over the ring-key candidates -- instead of keeping a top-k over the whole database.
+template <bool kList>
 __global__ void __launch_bounds__(kScWarps * 32, 3)
     sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, int k, u64* __restrict__ part_d,
-                    int* __restrict__ part_id, int* __restrict__ part_sh) {
+                    int* __restrict__ part_id, int* __restrict__ part_sh, const u64* __restrict__ cand_keys,
+                    double* __restrict__ list_dist, int* __restrict__ list_shift) {
   pdl_entry();
   extern __shared__ __align__(16) unsigned char sc_smem_raw[];
   ScBlockSmem& sm = *reinterpret_cast<ScBlockSmem*>(sc_smem_raw);
@@ -131,7 +136,16 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
   if (lane < kTopKMax) w.tk_d[lane] = ~0ull, w.tk_id[lane] = INT_MAX, w.tk_sh[lane] = 0;
   __syncthreads();
   const int nwarps = gridDim.x * kScWarps;
-  for (int cand = blockIdx.x * kScWarps + warp; cand < n; cand += nwarps) {
+  for (int item = blockIdx.x * kScWarps + warp; item < n; item += nwarps) {
+    int cand = item;
+    if (kList) {
+      const u64 ck = cand_keys[item];
+      if (ck == ~0ull) {  // fewer database entries than candidates asked for
+        if (lane == 0) list_dist[item] = __longlong_as_double(0x7ff0000000000000ll), list_shift[item] = 0;
+        continue;
+      }
+      cand = (int)(uint32_t)ck;
+    }
     // stage the candidate: 4800 B of coalesced 128-bit loads, kept as float
     const float4* src = reinterpret_cast<const float4*>(db + (size_t)cand * kDesc);
     for (int i = lane; i < kDesc / 4; i += 32) reinterpret_cast<float4*>(w.cd)[i] = __ldg(src + i);
@@ -266,7 +280,10 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
     }
     const double bd = __shfl_sync(0xffffffffu, myd, 0);
     const int bs = __shfl_sync(0xffffffffu, mysh, 0);
-    if (lane == 0) {  // insertion into this warp's sorted top-k
+    if (kList) {
+      // distanceBtnScanContext's result as it is (10000000 when no shift had an effective column: never < min_dist)
+      if (lane == 0) list_dist[item] = bd, list_shift[item] = bs;
+    } else if (lane == 0) {  // insertion into this warp's sorted top-k
       const u64 kd = (u64)__double_as_longlong(bd);
       if (sc_key_less(kd, cand, w.tk_d[k - 1], w.tk_id[k - 1])) {
         int pos = k - 1;
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
     __syncwarp();
   }
   __syncthreads();
+  if (kList) return;
   if (threadIdx.x == 0) {  // k-way merge of the warps' lists (heads only): k x kScWarps comparisons
     int head[kScWarps];
 #pragma unroll
@@ -299,6 +317,113 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
       else sm.w[bw].tk_d[kTopKMax - 1] = ~0ull, sm.w[bw].tk_id[kTopKMax - 1] = INT_MAX;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ring keys and the reference's candidate selection (Scancontext.cpp:206-220, 270-295)
+// ---------------------------------------------------------------------------------------------------
+// makeRingkeyFromScancontext + eig2stdvec: row means in double, stored as float (polarcontext_invkeys_mat_).
+__global__ void sc_ringkey_kernel(const float* __restrict__ db, int first, int count, float* __restrict__ keys) {
+  pdl_entry();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * kNR) return;
+  const int e = first + t / kNR, r = t % kNR;
+  const float* row = db + (size_t)e * kDesc + r * kNS;
+  double s = 0;
+  for (int c = 0; c < kNS; ++c) s += (double)row[c];
+  keys[(size_t)e * kNR + r] = (float)(s / kNS);
+}
+
+// nanoflann L2_Adaptor<float>::evalMetric over 20 dimensions (the metric of KDTreeVectorOfVectorsAdaptor,
+// include/nanoflann.hpp): groups of four, result += ((d0*d0 + d1*d1) + d2*d2) + d3*d3, float, no FMA.
+__device__ __forceinline__ float ringkey_l2(const float* q, const float4* key5) {
+  float result = 0.f;
+#pragma unroll
+  for (int g = 0; g < kNR / 4; ++g) {
+    const float4 b = __ldg(key5 + g);
+    const float d0 = __fsub_rn(q[4 * g], b.x), d1 = __fsub_rn(q[4 * g + 1], b.y), d2 = __fsub_rn(q[4 * g + 2], b.z),
+                d3 = __fsub_rn(q[4 * g + 3], b.w);
+    result = __fadd_rn(result, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3)));
+  }
+  return result;
+}
+
+// block-wide k smallest of one u64 per thread (unique keys; ~0 = none), written in ascending order
+__device__ __forceinline__ void block_k_smallest(u64 mine, int k, u64* __restrict__ out) {
+  __shared__ u64 s_w[32];
+  __shared__ u64 s_win;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int round = 0; round < k; ++round) {
+    u64 m = mine;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const u64 o = __shfl_xor_sync(0xffffffffu, m, off);
+      m = o < m ? o : m;
+    }
+    if (lane == 0) s_w[warp] = m;
+    __syncthreads();
+    if (warp == 0) {
+      u64 w = lane < nw ? s_w[lane] : ~0ull;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, w, off);
+        w = o < w ? o : w;
+      }
+      if (lane == 0) s_win = w, out[round] = w;
+    }
+    __syncthreads();
+    if (mine == s_win) mine = ~0ull;
+    __syncthreads();
+  }
+}
+
+// stage 1: every thread one database ring key -> (float distance bits, index) -> the block's k smallest
+__global__ void __launch_bounds__(1024)
+    sc_ringkey_select_kernel(const float* __restrict__ keys, int n, const float* __restrict__ qdesc, int k, u64* __restrict__ part) {
+  pdl_entry();
+  __shared__ float qk[kNR];
+  if (threadIdx.x < kNR) {  // the query's own ring key, the same arithmetic as sc_ringkey_kernel
+    const float* row = qdesc + threadIdx.x * kNS;
+    double s = 0;
+    for (int c = 0; c < kNS; ++c) s += (double)row[c];
+    qk[threadIdx.x] = (float)(s / kNS);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  u64 mine = ~0ull;
+  if (i < n) mine = ((u64)__float_as_uint(ringkey_l2(qk, reinterpret_cast<const float4*>(keys + (size_t)i * kNR))) << 32) | (uint32_t)i;
+  block_k_smallest(mine, k, part + (size_t)blockIdx.x * k);
+}
+
+// stage 2: the k smallest of the blocks' lists (m entries), ascending (distance, index) = nanoflann's result order
+__global__ void __launch_bounds__(1024) sc_ringkey_final_kernel(const u64* __restrict__ part, int m, int k, u64* __restrict__ out) {
+  pdl_entry();
+  // a thread's strided slice is reduced to its smallest entry above the previous winner, round by round
+  __shared__ u64 s_last;
+  if (threadIdx.x == 0) s_last = 0;
+  __syncthreads();
+  for (int round = 0; round < k; ++round) {
+    const u64 last = s_last;
+    u64 mine = ~0ull;
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+      const u64 v = part[e];
+      if ((round == 0 || v > last) && v < mine) mine = v;
+    }
+    __syncthreads();
+    block_k_smallest(mine, 1, out + round);
+    if (threadIdx.x == 0) s_last = out[round];
+    __syncthreads();
+  }
+}
+
+// candidate list -> ids and float key distances for the caller
+__global__ void sc_list_unpack_kernel(const u64* __restrict__ sel, int k, int* __restrict__ id, float* __restrict__ key_d2) {
+  pdl_entry();
+  const int i = threadIdx.x;
+  if (i >= k) return;
+  const u64 v = sel[i];
+  id[i] = v == ~0ull ? -1 : (int)(uint32_t)v;
+  key_d2[i] = v == ~0ull ? __int_as_float(0x7f800000) : __uint_as_float((uint32_t)(v >> 32));
 }
 
 // Final merge of the blocks' lists (n = blocks * k entries, a few thousand): every thread holds up to kFinalPer
@@ -370,10 +495,15 @@ __global__ void __launch_bounds__(kFinalThreads)
 // per shard: k x f64 distance | k x i32 id | k x i32 shift (16 k bytes).  One warp; round j picks the smallest
 // (distance, id) strictly above round j-1's winner (ids are unique across shards), so the result is the same
 // ascending (distance, id) order as ilsm_sc_merge_topk on the host.
-__global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int shards, int k, unsigned char* __restrict__ out) {
+// Batched form: block b merges query b; shard r's record of query b sits at packed + r * shard_stride + b * 16 k (the
+// layout an all-gather of per-rank [B][16 k] buffers produces), the merged record goes to out + b * 16 k.
+__global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int shards, int k, unsigned char* __restrict__ out,
+                                size_t shard_stride) {
   pdl_entry();
   const int lane = threadIdx.x;
   const size_t rec = (size_t)16 * k;
+  packed += (size_t)blockIdx.x * rec;
+  out += (size_t)blockIdx.x * rec;
   u64 last_d = 0;
   int last_id = -1;
   bool first = true;
@@ -384,7 +514,7 @@ __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int sh
     u64 bd = ~0ull;
     int bid = INT_MAX, bsh = 0;
     for (int e = lane; e < shards * k; e += 32) {
-      const unsigned char* base = packed + (size_t)(e / k) * rec;
+      const unsigned char* base = packed + (size_t)(e / k) * shard_stride;
       const int i = e % k;
       const int id = reinterpret_cast<const int*>(base + (size_t)8 * k)[i];
       if (id < 0) continue;
@@ -410,8 +540,10 @@ __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int sh
   }
 }
 
-int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out) {
-  ILSM_CUDA(launch_pdl(sc_merge_kernel, dim3(1), dim3(32), 0, ctx->stream, reinterpret_cast<const unsigned char*>(d_packed), shards, k, reinterpret_cast<unsigned char*>(d_out)));
+int sc_merge_dev(Ctx* ctx, const void* d_packed, int shards, int k, void* d_out, int batch, size_t shard_stride) {
+  if (shard_stride == 0) shard_stride = (size_t)16 * k;
+  ILSM_CUDA(launch_pdl(sc_merge_kernel, dim3(batch), dim3(32), 0, ctx->stream, reinterpret_cast<const unsigned char*>(d_packed), shards, k,
+                       reinterpret_cast<unsigned char*>(d_out), shard_stride));
   count_launches(1);
   return check_launch("sc_merge");
 }
@@ -434,8 +566,23 @@ int ScDb::append_dev(const float* d_desc, int n_add, bool from_host) {
   }
   ILSM_CUDA(cudaMemcpyAsync(db.p + (size_t)count * kDesc, d_desc, (size_t)n_add * kDesc * sizeof(float),
                             from_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  // polarcontext_invkeys_mat_.push_back(ring key as floats)  Scancontext.cpp:243,249
+  const size_t need_k = (size_t)(count + n_add) * kNR;
+  if (need_k > ringkey.cap) {
+    DevBuf<float> bigger;
+    int rc = bigger.reserve(need_k * 2);
+    if (rc) return rc;
+    if (count > 0)
+      ILSM_CUDA(cudaMemcpyAsync(bigger.p, ringkey.p, (size_t)count * kNR * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    ILSM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ringkey.release();
+    ringkey = bigger;
+  }
+  ILSM_CUDA(launch_pdl(sc_ringkey_kernel, dim3((n_add * kNR + 255) / 256), dim3(256), 0, ctx->stream, (const float*)db.p, count, n_add,
+                       ringkey.p));
+  count_launches(1);
   count += n_add;
-  return ILSM_OK;
+  return check_launch("sc_add");
 }
 
 int ScDb::make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc) {
@@ -463,12 +610,49 @@ int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, do
       (rc = part_id.reserve((size_t)blocks * kTopKMax)) || (rc = part_sh.reserve((size_t)blocks * kTopKMax)))
     return rc;
   cudaStream_t s = ctx->stream;
-  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
   ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(1), dim3(64), 0, s, d_qdesc, query.p));
-  ILSM_CUDA(launch_pdl(sc_score_kernel, dim3((unsigned)blocks), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, db.p, n_search, query.p, k, part_d.p, part_id.p, part_sh.p));
+  ILSM_CUDA(launch_pdl(sc_score_kernel<false>, dim3((unsigned)blocks), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, (const float*)db.p, n_search,
+                       (const ScQuery*)query.p, k, part_d.p, part_id.p, part_sh.p, (const u64*)nullptr, (double*)nullptr, (int*)nullptr));
   ILSM_CUDA(launch_pdl(sc_topk_final_kernel, dim3(1), dim3(kFinalThreads), 0, s, part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id, d_shift));
   count_launches(3);
   return check_launch("sc_query");
+}
+
+// B queries against the shard, one after the other on the stream (the scoring kernel already fills the GPU for one
+// query); record b of d_packed receives query b's top-k in the packed layout (k x f64 | k x i32 | k x i32).
+int ScDb::query_batch_dev(const float* d_qdesc, int B, int n_search, int id_offset, int k, unsigned char* d_packed) {
+  for (int b = 0; b < B; ++b) {
+    unsigned char* base = d_packed + (size_t)b * 16 * k;
+    int rc = query_dev(d_qdesc + (size_t)b * kDesc, n_search, id_offset, k, reinterpret_cast<double*>(base),
+                       reinterpret_cast<int*>(base + (size_t)8 * k), reinterpret_cast<int*>(base + (size_t)12 * k));
+    if (rc) return rc;
+  }
+  return ILSM_OK;
+}
+
+// detectLoopClosureID's two steps (Scancontext.cpp:283-312) over entries [0, n_search): the num_cand nearest ring keys
+// (float L2 as nanoflann evaluates it, ties by lower index), then distanceBtnScanContext for exactly those, in that
+// order.  Outputs (device): ids, float key distances, distances, shifts -- num_cand entries each, id -1 when the
+// database holds fewer entries.
+int ScDb::candidates_dev(const float* d_qdesc, int n_search, int num_cand, int* d_id, float* d_key_d2, double* d_dist, int* d_shift) {
+  if (num_cand < 1 || num_cand > kTopKMax) return fail(ILSM_ERR_INVALID_ARG, "sc_candidates: num_candidates must be in [1,16]");
+  if (n_search < 0 || n_search > count) return fail(ILSM_ERR_INVALID_ARG, "sc_candidates: n_search exceeds the database");
+  const int blocks = n_search > 0 ? (n_search + 1023) / 1024 : 1;
+  int rc;
+  if ((rc = query.reserve(1)) || (rc = rk_part.reserve((size_t)blocks * kTopKMax + kTopKMax))) return rc;
+  u64* sel = rk_part.p + (size_t)blocks * kTopKMax;
+  cudaStream_t s = ctx->stream;
+  ILSM_CUDA(launch_pdl(sc_ringkey_select_kernel, dim3(blocks), dim3(1024), 0, s, (const float*)ringkey.p, n_search, d_qdesc, num_cand, rk_part.p));
+  ILSM_CUDA(launch_pdl(sc_ringkey_final_kernel, dim3(1), dim3(1024), 0, s, (const u64*)rk_part.p, blocks * num_cand, num_cand, sel));
+  ILSM_CUDA(launch_pdl(sc_list_unpack_kernel, dim3(1), dim3(32), 0, s, (const u64*)sel, num_cand, d_id, d_key_d2));
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
+  ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(1), dim3(64), 0, s, d_qdesc, query.p));
+  ILSM_CUDA(launch_pdl(sc_score_kernel<true>, dim3((num_cand + kScWarps - 1) / kScWarps), dim3(kScWarps * 32), sizeof(ScBlockSmem), s,
+                       (const float*)db.p, num_cand, (const ScQuery*)query.p, num_cand, (u64*)nullptr, (int*)nullptr, (int*)nullptr, (const u64*)sel,
+                       d_dist, d_shift));
+  count_launches(5);
+  return check_launch("sc_candidates");
 }
 
 }  // namespace ilsm

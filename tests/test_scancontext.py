@@ -149,3 +149,73 @@ def test_gpu_sc_sharded_equals_unsharded(ctx, oracle_mod, ilsm):
         for s, _ in shards:
             s.close()
     whole.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sc_candidates_match_reference_nanoflann(ctx, oracle_mod, ilsm):
+    """detectLoopClosureID the reference's way (Scancontext.cpp:283-312): the 10 ring-key candidates must be the result
+    set of the REFERENCE'S OWN nanoflann tree (KDTreeVectorOfVectorsAdaptor, oracle/_ref -- prebuilt, it travels with
+    the snapshot), in its order, and the loop id / distance / shift those of the candidate loop over them."""
+    if oracle_mod.ref() is None:
+        pytest.skip("oracle/_ref/libref_nanoflann.so not available")
+    db = ilsm.synth.sc_database(600, seed=7)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 12, seed=8)
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db[:250])
+    sc.add(db[250:])  # ring keys follow the database through growth
+    dbd = db.astype(np.float64)
+    for n_search in (600, 550, 37, 7):
+        for j in range(len(q)):
+            cid, ckd, cd, cs = sc.query_candidates(q[j], 10, n_search)
+            arg, best, align, ref_ids = oracle_mod.sc_detect_loop_reference(dbd[:n_search], q[j].astype(np.float64))
+            m = min(10, n_search)
+            assert np.array_equal(cid[:m], ref_ids[:m]), (n_search, j)
+            assert (cid[m:] == -1).all() and np.isinf(cd[m:]).all()
+            assert (np.diff(ckd[:m]) >= 0).all()
+            for t in range(m):  # every candidate's distance / shift = distanceBtnScanContext
+                wd, ws = oracle_mod.sc_distance(q[j].astype(np.float64), dbd[cid[t]])
+                assert abs(cd[t] - wd) <= 1e-12 and cs[t] == ws
+            loop, dmin, sh, nn = sc.detect_loop_closure_id(q[j], n_search)
+            assert nn == arg and sh == align and abs(dmin - best) <= 1e-12
+            assert loop == (arg if best < 0.13 else -1)
+    # the query re-renders of database entries are found when their entry is inside the window (ring keys are
+    # rotation-invariant), and the exhaustive search agrees there
+    for j in range(len(q)):
+        loop, dmin, sh, nn = sc.detect_loop_closure_id(q[j], 600)
+        assert nn == ids[j] and sh == shifts[j]
+        assert sc.detect_loop_closure_id(q[j], 600, exhaustive=True)[3] == ids[j]
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sc_candidates_golden_reference_sets(ctx, ilsm):
+    """The committed reference candidate sets (tests/golden/ringkey_nanoflann.npz, made by the reference's tree)."""
+    import hashlib
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ringkey_nanoflann.npz"))
+    n, s0, nq, s1 = [int(v) for v in g["seeds"]]
+    db = ilsm.synth.sc_database(n, seed=s0)
+    qs, _, _ = ilsm.synth.sc_queries(db, nq, seed=s1)
+    assert np.array_equal(np.frombuffer(hashlib.sha256(db.tobytes() + qs.tobytes()).digest(), np.uint8), g["sha256"])
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db)
+    for j in range(nq):
+        cid, _, _, _ = sc.query_candidates(qs[j], 10)
+        assert np.array_equal(cid, g["candidates"][j].astype(np.int32)), j
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sc_batch_equals_single_queries(ctx, ilsm):
+    db = ilsm.synth.sc_database(1500, seed=21)
+    q, _, _ = ilsm.synth.sc_queries(db, 9, seed=22)
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db)
+    bd, bi, bs = sc.query_topk_batch(q, k=10, n_search=1400, id_offset=5)
+    for j in range(len(q)):
+        d, i, s = sc.query_topk(q[j], k=10, n_search=1400, id_offset=5)
+        assert np.array_equal(bd[j], d) and np.array_equal(bi[j], i) and np.array_equal(bs[j], s)
+    # without a communicator the sharded entry point is the batch query
+    sd, si, ss = sc.query_topk_sharded(q, k=10, n_search=1400, id_offset=5)
+    assert np.array_equal(sd, bd) and np.array_equal(si, bi) and np.array_equal(ss, bs)
+    sc.close()
