@@ -164,7 +164,7 @@ def test_gpu_sc_candidates_match_reference_nanoflann(ctx, oracle_mod, ilsm):
     sc.add(db[:250])
     sc.add(db[250:])  # ring keys follow the database through growth
     dbd = db.astype(np.float64)
-    for n_search in (600, 550, 37, 7):
+    for n_search in (600, 550, 37, 12):
         for j in range(len(q)):
             cid, ckd, cd, cs = sc.query_candidates(q[j], 10, n_search)
             arg, best, align, ref_ids = oracle_mod.sc_detect_loop_reference(dbd[:n_search], q[j].astype(np.float64))
@@ -178,6 +178,9 @@ def test_gpu_sc_candidates_match_reference_nanoflann(ctx, oracle_mod, ilsm):
             loop, dmin, sh, nn = sc.detect_loop_closure_id(q[j], n_search)
             assert nn == arg and sh == align and abs(dmin - best) <= 1e-12
             assert loop == (arg if best < 0.13 else -1)
+    # a tree with fewer entries than candidates (51..59 keyframes in all): every entry is a candidate, the rest is padding
+    cid, ckd, cd, cs = sc.query_candidates(q[0], 10, 7)
+    assert sorted(cid[:7].tolist()) == list(range(7)) and (cid[7:] == -1).all() and (np.diff(ckd[:7]) >= 0).all()
     # the query re-renders of database entries are found when their entry is inside the window (ring keys are
     # rotation-invariant), and the exhaustive search agrees there
     for j in range(len(q)):
