@@ -208,11 +208,11 @@ def os0_dirs(H=64, W=1024, fov_deg=45.0):
     return d.reshape(-1, 3)
 
 
-def make_frame(scene, q_ws, t_ws, seed=SEED_FRAME, H=64, W=1024, noise=0.01, max_range=50.0, stride_floats=4):
+def make_frame(scene, q_ws, t_ws, seed=SEED_FRAME, H=64, W=1024, noise=0.01, max_range=50.0, stride_floats=4, fov_deg=45.0):
     """Organised H*W cloud in the SENSOR frame: float32 rows [x y z intensity] (or PCL 8-float PointXYZI when
     stride_floats=8: x y z pad intensity pad pad pad).  Returns (cloud, tag)."""
     rng = np.random.default_rng(seed)
-    d_s = os0_dirs(H, W)
+    d_s = os0_dirs(H, W, fov_deg)
     R = quat_to_mat(np.asarray(q_ws, np.float64))
     rng_, tag = scene.raycast(np.asarray(t_ws, np.float64), d_s @ R.T, max_range)
     r = rng_ + rng.normal(0.0, noise, size=len(rng_))

@@ -171,3 +171,41 @@ def test_pipelined_mapping_stage_gives_the_same_poses(ctx, ilsm):
     with pytest.raises(ilsm.IlsmError):
         a.frame_async(clouds[0])
     a.close(), b.close()
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_feature_clouds_above_16384_points(ctx, oracle_mod, ilsm, pipelined):
+    """A 64-ring sensor whose beams all fall inside the reference's +-22.5 degree ring formula keeps every return
+    (scanRegistration.cpp:308-316, 570-589): ~17.7 k less-flat points per frame in the open scene -- more than one block's
+    VoxelGrid sorts.  The full loop routes such clouds through the tiled multi-block VoxelGrid and must still match the
+    chained oracle, in the synchronous loop and with the mapping stage pipelined."""
+    S = ilsm.synth
+    scene = S.Scene()
+    q0, t0 = S.default_pose()
+    frames = []
+    for k in range(4):
+        q = S.quat_mul(q0, S.quat_from_rotvec([0.0, 0.0, 0.01 * k]))
+        t = np.asarray(t0) + [0.15 * k, 0.02 * k, 0.0]
+        frames.append(S.make_frame(scene, q, t, seed=0x5EED0700 + k, fov_deg=22.0)[0])
+    slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 16384, pipelined=pipelined)
+    oslam = oracle_mod.Slam(0.4, 0.8, 0.3)
+    want, got = [], []
+    for k, cloud in enumerate(frames):
+        wodom, wmap, info = oslam.frame(cloud)
+        want.append(wmap)
+        if pipelined:
+            r = slam.frame_async(cloud)
+            st = r[4]
+            if r[2] is not None:
+                got.append((r[2], r[3]))
+        else:
+            gqo, gto, gqm, gtm, st = slam.frame(cloud)
+            got.append((gqm, gtm))
+        assert st.n_less_flat == len(info["features"]["less_flat"]) and st.n_less_flat > 16384, (k, st.n_less_flat)
+        assert st.n_less_sharp == len(info["features"]["less_sharp_idx"])
+    if pipelined:
+        got.append(slam.flush()[:2])
+    assert len(got) == len(want)
+    for k, ((gq, gt), w) in enumerate(zip(got, want)):
+        assert np.linalg.norm(gt - w[4:]) < 1e-4 and S.quat_angle(gq, w[:4]) < 1e-4, k
+    slam.close()
