@@ -91,6 +91,7 @@ int Ctx::init(int dev) {
   ILSM_CUDA(cudaMemsetAsync(lm.p, 0, sizeof(LmState), stream));
   if ((rc = pinned.reserve(4096))) return rc;
   ILSM_CUDA(cudaStreamSynchronize(stream));
+  if (const char* e2 = getenv("ILSM_KNN_BINNED_MIN")) knn_binned_min = atoi(e2) > 0 ? atoi(e2) : 0x7fffffff;
   return ILSM_OK;
 }
 
@@ -103,6 +104,8 @@ void Ctx::release() {
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
   fe.pc2.release(), fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
   lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
+  if (qbin) qbin->release(), delete qbin, qbin = nullptr;
+  qwork.release();
   fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
   if (aux) cudaStreamSynchronize(aux), cudaStreamDestroy(aux);
   if (ev_fork) cudaEventDestroy(ev_fork);

@@ -210,6 +210,9 @@ struct Ctx {
   FactorBufs fac;
   FeBufs fe;
   const int* d_stack_counts = nullptr;  // when set, associate/solve read {nc, ns} from the device (cube-map path)
+  Map* qbin = nullptr;        // query binning of the throughput k-NN path (knn_binned.cu): the query cloud grouped by voxel
+  DevBuf<int> qwork;          // its work items (4 ints each) + the item counter
+  int knn_binned_min = 8192;  // query sets at least this large take the binned path (ILSM_KNN_BINNED_MIN overrides)
   size_t partial_blocks = 0;
   bool bulk_attr_set = false;  // normal_eq_bulk_kernel's dynamic shared-memory opt-in done on this device
 

@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(128) knn_kernel(GridView g, const float* __res
   }
 }
 
+int knn_binned_dev(Ctx* ctx, Map* m, const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2);
+
 static inline int ilog2_ceil(uint32_t v) {
   int l = 0;
   while ((1u << l) < v) ++l;
@@ -338,6 +340,9 @@ int Map::knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_di
     return fail(ILSM_ERR_INVALID_ARG, "knn: bad nq/k/stride");
   if (table_size == 0) return fail(ILSM_ERR_STATE, "knn: map not built");
   if (nq == 0) return ILSM_OK;
+  // throughput regime: bin the queries by voxel and serve each group with one warp (knn_binned.cu); small query sets are
+  // latency-bound and keep one warp per query
+  if (nq >= ctx->knn_binned_min && n > 0) return knn_binned_dev(ctx, this, d_q, nq, stride_bytes, k, max_dist, d_idx, d_d2);
   GridView g = view();
   float max_d2 = max_dist > 0.f ? max_dist * max_dist : 0.f;
   cudaStream_t s = ctx->stream;

@@ -420,3 +420,49 @@ def test_gpu_evaluation_matches_reference_functors(ctx, oracle_mod, cfg_small):
         assert abs(cost - cost_r) <= 1e-9 * cost_r, huber
         assert np.abs(H - H_r).max() <= 1e-9 * np.abs(H_r).max() and np.abs(g - g_r).max() <= 1e-9 * np.abs(g_r).max(), huber
     mc.close(), ms.close()
+
+
+@pytest.mark.parametrize("k,max_dist", [(5, 0.0), (1, 0.0), (8, 0.0), (5, 1.0)])
+def test_knn_binned_path_equals_per_query_path(ilsm, ctx, oracle_mod, cfg_small, k, max_dist):
+    """The query-binned search (one warp per group of <= 32 queries of a voxel, knn_binned.cu) forced onto a mixed query
+    set -- groups of every size from 1 to 70 queries per voxel, exact duplicates, far-away queries that need ring
+    expansion or the brute-force sweep, NaN / out-of-range queries -- must return exactly what the per-query kernel and
+    the oracle return."""
+    import os
+    rng = np.random.default_rng(1000 + k)
+    m = cfg_small["map_surf"]
+    parts = []
+    anchors = m[rng.integers(0, len(m), 120)]
+    for i, a in enumerate(anchors):                       # i + 1 queries inside one 1 m voxel around a map point
+        base = np.floor(a[:3]) + 0.5
+        parts.append(base + rng.uniform(-0.49, 0.49, ((i % 70) + 1, 3)))
+    parts.append(np.repeat(m[5:6, :3], 40, axis=0))       # 40 identical queries
+    parts.append(rng.uniform(-300, 300, (200, 3)))        # mostly empty neighbourhoods
+    parts.append(np.array([[np.nan, 0, 0], [0, np.inf, 0], [3e6, 0, 0], [0, 0, -2e6]]))
+    q = np.concatenate(parts).astype(np.float32)
+    rng.shuffle(q)
+    os.environ["ILSM_KNN_BINNED_MIN"] = "1"
+    try:
+        bctx = ilsm.Context(0)
+    finally:
+        del os.environ["ILSM_KNN_BINNED_MIN"]
+    bm = bctx.new_map().set_input_cloud(m)
+    pm = ctx.new_map().set_input_cloud(m)
+    bi, bd = bm.nearest_k_search(q, k, max_dist=max_dist)
+    pi, pd = pm.nearest_k_search(q, k, max_dist=max_dist)
+    finite = np.isfinite(q).all(axis=1)
+    if max_dist > 0:
+        ins = pd < max_dist * max_dist
+        assert np.array_equal(bi[ins], pi[ins]) and np.array_equal(bd[ins], pd[ins])
+    else:
+        assert np.array_equal(bi[finite], pi[finite]) and np.array_equal(bd[finite], pd[finite])
+        ok = finite & (np.abs(q) < 1e6).all(axis=1)
+        ri, rd = oracle_mod.knn_kdtree(m, q[ok], k)
+        assert np.array_equal(bi[ok], ri) and np.array_equal(bd[ok], rd)
+    # a map with fewer points than k, and a rebuilt query binning on the same context
+    tiny = bctx.new_map().set_input_cloud(m[:3])
+    ti, td = tiny.nearest_k_search(q[:50], k)
+    kk = min(k, 3)
+    f50 = np.isfinite(q[:50]).all(axis=1)
+    assert (ti[f50][:, kk:] == -1).all() and (ti[f50][:, :kk] >= 0).all()
+    bm.close(), pm.close(), tiny.close(), bctx.close()
