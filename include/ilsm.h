@@ -175,6 +175,22 @@ ILSM_API int ilsm_register_dev(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* ma
                       const float* d_surf, int ns, int stride_bytes, double* d_pose7, const ilsm_reg_opts* opts,
                       ilsm_reg_report* d_report);
 
+/* One organised LiDAR frame registered against two prebuilt maps -- SURVEY 8d config 1 as the reference pipeline runs it:
+ * laserCloudHandler (min-range filter, ring bucketing, curvature, labelling, per-ring VoxelGrid;
+ * scanRegistration.cpp:189-669), cornerPointsLessSharp / surfPointsLessFlat become the mapping inputs
+ * (laserOdometry.cpp:793-796), downSizeFilterCorner / downSizeFilterSurf with mapping_line_resolution /
+ * mapping_plane_resolution (laserMapping.cpp:608-616), then the association + solve block (:640-861) from the initial
+ * guess q, t, which is overwritten with the optimised pose.  sizes_out (may be NULL) = {less-sharp points, less-flat
+ * points, corner stack, surf stack}.  The feature clouds stay on the device between the stages; the call synchronises
+ * once for the feature counts (they size the VoxelGrid sorts) and once for the pose.  The _dev form takes the frame and
+ * the pose (7 doubles, updated in place) on the device and returns without the final synchronisation. */
+ILSM_API int ilsm_register_frame(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* xyzi, int n, int stride_bytes,
+                                 float min_range, float line_res, float plane_res, double q_xyzw[4], double t_xyz[3],
+                                 const ilsm_reg_opts* opts, ilsm_reg_report* report, int32_t sizes_out[4]);
+ILSM_API int ilsm_register_frame_dev(ilsm_ctx* ctx, ilsm_map* map_corner, ilsm_map* map_surf, const float* d_xyzi, int n,
+                                     int stride_bytes, float min_range, float line_res, float plane_res, double* d_pose7,
+                                     const ilsm_reg_opts* opts);
+
 /* One correspondence record, in the reference functors' own terms (lidarFeaturePointsFunction.hpp). */
 typedef struct ilsm_factor {
   int32_t type; /* 0 none, 1 LidarEdgeFactor (hpp:243-293), 2 LidarPlaneNormFactor (hpp:199-240) */

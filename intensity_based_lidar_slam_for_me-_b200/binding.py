@@ -136,6 +136,8 @@ def load_library(path: str | None = None):
         "ilsm_project_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_extract_features": (i32, [vp, vp, i32, i32, f32, C.POINTER(Features)]),
         "ilsm_voxelgrid": (i32, [vp, vp, i32, i32, f32, vp, C.POINTER(i32)]),
+        "ilsm_register_frame": (i32, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
+        "ilsm_register_frame_dev": (i32, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp]),
         "ilsm_sc_create": (i32, [vp, C.POINTER(vp)]),
         "ilsm_sc_destroy": (None, [vp]),
         "ilsm_sc_size": (i32, [vp]),
@@ -376,6 +378,22 @@ class Context:
         _check(self._lib.ilsm_align_points(self._h, _ptr(s), _ptr(d), len(s), 12, _ptr(qq), _ptr(tt), max_num_iterations,
                                            huber_a, C.byref(sm)))
         return qq, tt, sm
+
+    def register_frame(self, map_corner, map_surf, cloud, q, t, min_range=0.3, line_res=0.4, plane_res=0.8, opts: RegOpts | None = None):
+        """Front end -> stacks -> registration of one organised frame against prebuilt maps (ilsm_register_frame).
+        Returns (q, t, report, (n_less_sharp, n_less_flat, n_corner_stack, n_surf_stack))."""
+        a, n, stride = _cloud(cloud)
+        qq, tt = np.array(q, np.float64), np.array(t, np.float64)
+        rep = RegReport()
+        sizes = np.zeros(4, np.int32)
+        _check(self._lib.ilsm_register_frame(self._h, map_corner._h, map_surf._h, _ptr(a), n, stride, min_range, line_res, plane_res,
+                                             _ptr(qq), _ptr(tt), C.byref(opts) if opts is not None else None, C.byref(rep), _ptr(sizes)))
+        return qq, tt, rep, tuple(int(v) for v in sizes)
+
+    def register_frame_dev(self, map_corner, map_surf, d_cloud_ptr, n, stride, d_pose_ptr, min_range=0.3, line_res=0.4, plane_res=0.8,
+                           opts: RegOpts | None = None):
+        _check(self._lib.ilsm_register_frame_dev(self._h, map_corner._h, map_surf._h, d_cloud_ptr, n, stride, min_range, line_res,
+                                                 plane_res, d_pose_ptr, C.byref(opts) if opts is not None else None))
 
     def associate_dev(self, map_corner, map_surf, d_corner_ptr, nc, d_surf_ptr, ns, stride, d_pose_ptr,
                       opts: RegOpts | None = None):

@@ -104,6 +104,7 @@ void Ctx::release() {
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();
   fe.pc2.release(), fe.raw.release(), fe.img.release(), fe.track.release(), fe.vox_out.release(), fe.vox_n.release();
   lm.release(), partials.release(), stack_raw.release(), out_idx.release(), out_d2.release(), pinned.release();
+  rf_lsharp.release(), rf_stack_c.release(), rf_stack_s.release(), rf_stack_n.release();
   if (qbin) qbin->release(), delete qbin, qbin = nullptr;
   qwork.release();
   fac.type.release(), fac.p.release(), fac.a.release(), fac.b.release(), fac.knn_idx.release(), fac.knn_d2.release();
@@ -435,6 +436,104 @@ ILSM_API int ilsm_register(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const floa
     report->passes = o.outer_iterations;
   }
   return ILSM_OK;
+}
+
+// Front end + stacks + registration of one organised frame against two prebuilt maps, the frame already on the device.
+// One host synchronisation in the middle (the feature counts size the VoxelGrid sorts, as in the full loop).
+static int register_frame_core(Ctx& c, Map* mc, Map* ms, const float* d_frame, int n, int stride_bytes, float min_range, float line_res,
+                               float plane_res, const ilsm_reg_opts& o, const PoseSrc* src, const PoseDst* dst, int counts_out[8]) {
+  int rc;
+  if ((rc = c.features_dev(d_frame, n, stride_bytes, min_range))) return rc;
+  int* pin = reinterpret_cast<int*>(c.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  for (int i = 0; i < 8; ++i) counts_out[i] = pin[i];
+  if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "register_frame: a ring segment exceeds the supported size");
+  const int n_lsharp = pin[2], n_lflat = pin[4];
+  if ((rc = c.rf_lsharp.reserve(n_lsharp + 4)) || (rc = c.rf_stack_c.reserve(n_lsharp + 4)) || (rc = c.rf_stack_s.reserve(n_lflat + 4)) ||
+      (rc = c.rf_stack_n.reserve(4)))
+    return rc;
+  // laserCloudCornerLast = cornerPointsLessSharp, laserCloudSurfLast = surfPointsLessFlat (laserOdometry.cpp:793-796)
+  if ((rc = c.gather_dev(c.fe.cloud.p, c.fe.lsharp.p, c.fe.counts.p, 2, n_lsharp, c.rf_lsharp.p))) return rc;
+  // downSizeFilterCorner / downSizeFilterSurf (laserMapping.cpp:608-616)
+  ILSM_CUDA(cudaMemsetAsync(c.rf_stack_n.p, 0, 4 * sizeof(int), c.stream));
+  if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(c.rf_lsharp.p), n_lsharp, line_res, c.rf_stack_c.p,
+                                 reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, plane_res, c.rf_stack_s.p, 16, 3, c.rf_stack_n.p,
+                                 c.stream)))
+    return rc;
+  if (o.outer_iterations < 1) return ILSM_OK;
+  // the association / solve block with the stack sizes read on the device (laserMapping.cpp:640-861)
+  c.d_stack_counts = c.rf_stack_n.p;
+  rc = c.register_dev(mc, ms, reinterpret_cast<const float*>(c.rf_stack_c.p), n_lsharp, reinterpret_cast<const float*>(c.rf_stack_s.p), n_lflat,
+                      16, o, src, dst);
+  c.d_stack_counts = nullptr;
+  return rc;
+}
+
+ILSM_API int ilsm_register_frame(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* xyzi, int n, int stride_bytes, float min_range,
+                                 float line_res, float plane_res, double q[4], double t[3], const ilsm_reg_opts* opts,
+                                 ilsm_reg_report* report, int32_t sizes_out[4]) {
+  if (!ctx || !mc || !ms || (n > 0 && !xyzi) || !q || !t) return fail(ILSM_ERR_INVALID_ARG, "register_frame: null argument");
+  if (mc->m.ctx != &ctx->c || ms->m.ctx != &ctx->c) return fail(ILSM_ERR_INVALID_ARG, "register_frame: map belongs to another context");
+  if (n < 0 || !valid_stride(stride_bytes) || stride_bytes < 16 || !(line_res > 0.f) || !(plane_res > 0.f))
+    return fail(ILSM_ERR_INVALID_ARG, "register_frame: bad n/stride/resolution");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (report) memset(report, 0, sizeof(*report));
+  if ((o.min_corner_map > 0 && !(mc->m.n > o.min_corner_map)) || (o.min_surf_map > 0 && !(ms->m.n > o.min_surf_map)))
+    return fail(ILSM_ERR_NOT_ENOUGH_MAP, "time Map corner and surf num are not enough");
+  const size_t bytes = (size_t)n * stride_bytes;
+  int rc;
+  if ((rc = c.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, bytes, cudaMemcpyHostToDevice, c.stream));
+  PoseSrc src;
+  src.mode = 1;
+  for (int i = 0; i < 4; ++i) src.v[i] = q[i];
+  for (int i = 0; i < 3; ++i) src.v[4 + i] = t[i];
+  int counts[8];
+  if ((rc = register_frame_core(c, &mc->m, &ms->m, c.fe.raw.p, n, stride_bytes, min_range > 0.f ? min_range : 0.3f, line_res, plane_res, o,
+                                &src, nullptr, counts)))
+    return rc;
+  unsigned char* pin = c.pinned.p;
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin + 64 + sizeof(ilsm_reg_report), c.rf_stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  if (o.outer_iterations >= 1) {
+    const double* out = reinterpret_cast<const double*>(pin);
+    for (int i = 0; i < 4; ++i) q[i] = out[i];
+    for (int i = 0; i < 3; ++i) t[i] = out[4 + i];
+    if (report) {
+      memcpy(report, pin + 64, sizeof(*report));
+      report->passes = o.outer_iterations;
+    }
+  }
+  if (sizes_out) {
+    const int* sn = reinterpret_cast<const int*>(pin + 64 + sizeof(ilsm_reg_report));
+    sizes_out[0] = counts[2], sizes_out[1] = counts[4], sizes_out[2] = sn[0], sizes_out[3] = sn[1];
+  }
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_register_frame_dev(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* d_xyzi, int n, int stride_bytes,
+                                     float min_range, float line_res, float plane_res, double* d_pose7, const ilsm_reg_opts* opts) {
+  if (!ctx || !mc || !ms || (n > 0 && !d_xyzi) || !d_pose7) return fail(ILSM_ERR_INVALID_ARG, "register_frame_dev: null argument");
+  if (mc->m.ctx != &ctx->c || ms->m.ctx != &ctx->c) return fail(ILSM_ERR_INVALID_ARG, "register_frame_dev: map belongs to another context");
+  if (n < 0 || !valid_stride(stride_bytes) || stride_bytes < 16 || !(line_res > 0.f) || !(plane_res > 0.f))
+    return fail(ILSM_ERR_INVALID_ARG, "register_frame_dev: bad n/stride/resolution");
+  ilsm_reg_opts o = sanitize(opts);
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  PoseSrc src;
+  src.mode = 2, src.dptr = d_pose7;
+  PoseDst dst;
+  dst.d_pose7 = d_pose7;
+  int counts[8];
+  return register_frame_core(c, &mc->m, &ms->m, d_xyzi, n, stride_bytes, min_range > 0.f ? min_range : 0.3f, line_res, plane_res, o, &src,
+                             &dst, counts);
 }
 
 ILSM_API int ilsm_associate(ilsm_ctx* ctx, ilsm_map* mc, ilsm_map* ms, const float* corner, int nc, const float* surf, int ns,

@@ -210,6 +210,8 @@ struct Ctx {
   FactorBufs fac;
   FeBufs fe;
   const int* d_stack_counts = nullptr;  // when set, associate/solve read {nc, ns} from the device (cube-map path)
+  DevBuf<float4> rf_lsharp, rf_stack_c, rf_stack_s;  // ilsm_register_frame: less-sharp cloud and the two down-sampled stacks
+  DevBuf<int> rf_stack_n;
   Map* qbin = nullptr;        // query binning of the throughput k-NN path (knn_binned.cu): the query cloud grouped by voxel
   DevBuf<int> qwork;          // its work items (4 ints each) + the item counter
   int knn_binned_min = 8192;  // query sets at least this large take the binned path (ILSM_KNN_BINNED_MIN overrides)

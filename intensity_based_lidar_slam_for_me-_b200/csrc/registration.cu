@@ -649,199 +649,165 @@ __device__ void lm_terminate(LmState* s, ilsm_reg_report* rep, int code) {
   rep->passes = s->pass + 1;
 }
 
+// The update runs on ONE thread on purpose.  A warp-cooperative form (one matrix element per lane, LDL^T by shuffles) was
+// built and measured in round 2: 4.3-5.0 k cycles per update against 3.4 k for this one in an instrumented build, and 3.6 x
+// slower end to end in the release build, where every __shfl_sync inside the warp-0 branch is compiled into a
+// WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair.  Dependent fp64 operations cost ~35 cycles each on this part, so the update is
+// bound by its dependency chain (6 sequential pivots), not by issue slots; shuffles only lengthen that chain.
 // Consume the sums of the evaluation at the candidate pose and either terminate or emit the next candidate.
-//
-// Warp-cooperative: all 32 lanes of ONE warp call it with uniform control flow (every branch below depends only on
-// values that are identical in all lanes).  The single-threaded form of this update was half of an evaluation
-// (3.4 k of 6.9 k cycles, ~620 dependent fp64 instructions); here
-//   * the scalar bookkeeping (tolerance tests, rho, radius policy) is computed redundantly by every lane,
-//   * vector state (pose, J^T J, J^T r, scaling, LM diagonal) is moved one element per lane,
-//   * the damped 6x6 system is factorised with one matrix element per lane: lane lt(i,j) < 21 holds entry (i,j) of the
-//     lower triangle, lanes 24..29 the right-hand side; a right-looking LDL^T step is then shuffle -> reciprocal ->
-//     one FMA per lane, the forward substitution rides along column by column, the back substitution takes five more
-//     shuffle + FMA steps.  The arithmetic per element is the one of ldlt_solve6 (same products, same FMA form).
-// `s` lives in shared memory; vector state written here is visible to the other lanes after __syncwarp().
-__device__ __forceinline__ double warp_sum8(double v, int lane) {  // total of an 8-lane aligned group, broadcast from its lane 0
-#pragma unroll
-  for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  return v;
-}
-
-__device__ __noinline__ void lm_advance_warp(LmState* s, ilsm_reg_report* rep, const double* sums, const int lane) {
+__device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const double* sums) {
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
   const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16;
   const double min_diag = 1e-6, max_diag = 1e32;
-  // scalar state: read once (uniform), kept in registers, written back by lane 0 when the call ends
-  int iteration = s->iteration, invalid_run = s->invalid_run, reuse_diag = s->reuse_diag;
-  int n_success = s->n_success, n_unsuccess = s->n_unsuccess, n_edge = s->n_edge, n_plane = s->n_plane;
-  const int max_iter = s->max_iter, phase = s->phase;
-  double cost = s->cost, initial_cost = s->initial_cost, radius = s->radius, decrease_factor = s->decrease_factor;
-  double model_cost_change = s->model_cost_change;
-  const int n_evals = s->n_evals + 1;
+  s->n_evals += 1;
   const double new_cost = sums[0];
-  __syncwarp();
-  // ends the call: scalars back to shared memory, optional termination
-  auto finish = [&](int code, int new_phase) {
-    if (lane == 0) {
-      s->iteration = iteration, s->invalid_run = invalid_run, s->reuse_diag = reuse_diag;
-      s->n_success = n_success, s->n_unsuccess = n_unsuccess, s->n_evals = n_evals, s->n_edge = n_edge, s->n_plane = n_plane;
-      s->cost = cost, s->initial_cost = initial_cost, s->radius = radius, s->decrease_factor = decrease_factor;
-      s->model_cost_change = model_cost_change, s->phase = new_phase;
-      if (code >= 0) lm_terminate(s, rep, code);
-    }
-    __syncwarp();
-  };
-  if (phase == 0) {
-    n_edge = (int)sums[28];
-    n_plane = (int)sums[29];
-    cost = new_cost;
-    initial_cost = new_cost;
-    if (lane < 27) s->H[lane] = sums[1 + lane];  // H[21] and g[6] are adjacent in LmState, like sums[1..27]
-    if (n_edge + n_plane == 0) {  // Ceres: no residual blocks -> parameter blocks dropped -> CONVERGENCE
-      finish(ILSM_CONVERGENCE, phase);
+  if (s->phase == 0) {
+    s->n_edge = (int)sums[28];
+    s->n_plane = (int)sums[29];
+    s->cost = new_cost;
+    s->initial_cost = new_cost;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) s->H[i] = sums[1 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s->g[i] = sums[22 + i];
+    if (s->n_edge + s->n_plane == 0) {  // Ceres: no residual blocks -> parameter blocks dropped -> CONVERGENCE
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    if (lane < 6) s->scale[lane] = frcp(1.0 + fsqrt(sums[1 + ut(lane, lane)]));
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      s->scale[a] = frcp(1.0 + fsqrt(s->H[k]));
+      k += 6 - a;
+    }
   } else {
-    // |x - candidate|^2 and |x|^2 over the 7 ambient coordinates (xq[4], xt[3] and cq[4], ct[3] are contiguous)
-    double d = 0.0, xv = 0.0;
-    if (lane < 7) xv = s->xq[lane], d = xv - s->cq[lane];
-    const double step2 = __shfl_sync(0xffffffffu, warp_sum8(d * d, lane), 0);
-    const double x2 = __shfl_sync(0xffffffffu, warp_sum8(xv * xv, lane), 0);
+    double step2 = 0, x2 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double d = s->xq[i] - s->cq[i];
+      step2 += d * d;
+      x2 += s->xq[i] * s->xq[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double d = s->xt[i] - s->ct[i];
+      step2 += d * d;
+      x2 += s->xt[i] * s->xt[i];
+    }
     // |step| <= ptol (|x| + ptol); |x| >= ~1 (unit quaternion) so the square-root test is only reached when the
     // cheap squared bound says it can possibly hold
     if (step2 <= 1.001 * parameter_tolerance * parameter_tolerance * (x2 + 1.0) &&
         sqrt(step2) <= parameter_tolerance * (sqrt(x2) + parameter_tolerance)) {
-      finish(ILSM_CONVERGENCE, phase);
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    const double cost_change = cost - new_cost;
-    if (fabs(cost_change) <= function_tolerance * cost) {
-      finish(ILSM_CONVERGENCE, phase);
+    const double cost_change = s->cost - new_cost;
+    if (fabs(cost_change) <= function_tolerance * s->cost) {
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    const double rho = cost_change * frcp(model_cost_change);
+    const double rho = cost_change * frcp(s->model_cost_change);
     if (rho > min_relative_decrease) {
-      if (lane < 7) s->xq[lane] = s->cq[lane];
-      if (lane < 27) s->H[lane] = sums[1 + lane];
-      cost = new_cost;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s->xq[i] = s->cq[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s->xt[i] = s->ct[i];
+      s->cost = new_cost;
+#pragma unroll
+      for (int i = 0; i < 21; ++i) s->H[i] = sums[1 + i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s->g[i] = sums[22 + i];
       const double w = 2.0 * rho - 1.0;
-      radius = fmin(max_radius, radius * frcp(fmax(1.0 / 3.0, 1.0 - w * w * w)));
-      decrease_factor = 2.0;
-      reuse_diag = 0;
-      n_success += 1;
+      s->radius = s->radius * frcp(fmax(1.0 / 3.0, 1.0 - w * w * w));
+      s->radius = fmin(max_radius, s->radius);
+      s->decrease_factor = 2.0;
+      s->reuse_diag = 0;
+      s->n_success += 1;
     } else {
-      radius = radius * frcp(decrease_factor);  // decrease_factor is a power of two: exact
-      decrease_factor *= 2.0;
-      reuse_diag = 1;
-      n_unsuccess += 1;
+      s->radius = s->radius * frcp(s->decrease_factor);  // decrease_factor is a power of two: exact
+      s->decrease_factor *= 2.0;
+      s->reuse_diag = 1;
+      s->n_unsuccess += 1;
     }
   }
-  __syncwarp();
-  // which matrix element this lane owns
-  const int mi = lane >= 15 ? 5 : lane >= 10 ? 4 : lane >= 6 ? 3 : lane >= 3 ? 2 : lane >= 1 ? 1 : 0;
-  const int mj = lane - mi * (mi + 1) / 2;       // valid for lane < 21
-  const bool is_m = lane < 21;
-  const int ra = lane - 24;                      // right-hand-side row for lanes 24..29
-  const bool is_b = ra >= 0 && ra < 6;
   // FinalizeIterationAndCheckIfMinimizerCanContinue + ComputeTrustRegionStep, repeated over invalid steps
 #pragma unroll 1
   for (;;) {
-    if (iteration >= max_iter) {
-      finish(ILSM_NO_CONVERGENCE, phase);
+    if (s->iteration >= s->max_iter) {
+      lm_terminate(s, rep, ILSM_NO_CONVERGENCE);
       return;
     }
     {  // gradient_max_norm = |x - Plus(x, -g)|_inf in the ambient space; the translation rows are exactly |g_t|,
        // so the quaternion rows (one sincos) only matter when those are already below the tolerance
       double m = fmax(fmax(fabs(s->g[3]), fabs(s->g[4])), fabs(s->g[5]));
       if (m <= gradient_tolerance) {
-        double ng[3] = {-s->g[0], -s->g[1], -s->g[2]}, xq[4] = {s->xq[0], s->xq[1], s->xq[2], s->xq[3]}, qp[4];
-        quat_plus_d(xq, ng, qp);
+        double ng[3] = {-s->g[0], -s->g[1], -s->g[2]}, qp[4];
+        quat_plus_d(s->xq, ng, qp);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m = fmax(m, fabs(xq[i] - qp[i]));
+        for (int i = 0; i < 4; ++i) m = fmax(m, fabs(s->xq[i] - qp[i]));
         if (m <= gradient_tolerance) {
-          finish(ILSM_CONVERGENCE, phase);
+          lm_terminate(s, rep, ILSM_CONVERGENCE);
           return;
         }
       }
     }
-    if (radius <= min_radius) {
-      finish(ILSM_CONVERGENCE, phase);
+    if (s->radius <= min_radius) {
+      lm_terminate(s, rep, ILSM_CONVERGENCE);
       return;
     }
-    iteration += 1;
-    if (!reuse_diag) {
-      if (lane < 6) {
-        const double sc = s->scale[lane];
-        s->diag[lane] = fmin(fmax(s->H[ut(lane, lane)] * sc * sc, min_diag), max_diag);
+    s->iteration += 1;
+    double gs[6], m[21], y[6], step[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) gs[a] = s->g[a] * s->scale[a];
+    if (!s->reuse_diag) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double haa = s->H[ut(a, a)] * s->scale[a] * s->scale[a];
+        s->diag[a] = fmin(fmax(haa, min_diag), max_diag);
       }
-      __syncwarp();
     }
-    const double inv_radius = frcp(radius);
-    // lane value: scaled, damped matrix entry (lanes 0..20) / scaled gradient (lanes 24..29)
-    double v = 0.0, gs = 0.0, dd = 0.0;
-    if (is_m) v = s->H[ut(mj, mi)] * s->scale[mj] * s->scale[mi] + (mi == mj ? s->diag[mi] * inv_radius : 0.0);
-    if (is_b) gs = s->g[ra] * s->scale[ra], dd = s->diag[ra] * inv_radius, v = gs;
-    bool ok = true;
-    double dinv_mine = 0.0;  // lanes 24..29: reciprocal pivot of their own row
+    const double inv_radius = frcp(s->radius);
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
-      const double dp = __shfl_sync(0xffffffffu, v, lt(p, p));
-      ok = ok && (dp > 0.0);
-      const double dinv = frcp(dp);
-      if (ra == p) dinv_mine = dinv;
-      // right-looking update of the trailing sub-matrix with the pre-scaled column p
-      const bool trail = is_m && mj > p;
-      const double mip = __shfl_sync(0xffffffffu, v, trail ? lt(mi, p) : lane);
-      const double mjp = __shfl_sync(0xffffffffu, v, trail ? lt(mj, p) : lane);
-      if (trail) v = fma(-(mip * dinv), mjp, v);
-      if (is_m && mj == p && mi > p) v = v * dinv;  // column p becomes L
-      // forward substitution rides along: z_p is final, rows r > p take  s_r -= L_rp z_p
-      const bool sub = is_b && ra > p;
-      const double zp = __shfl_sync(0xffffffffu, v, 24 + p);
-      const double lrp = __shfl_sync(0xffffffffu, v, sub ? lt(ra, p) : lane);
-      if (sub) v = fma(-lrp, zp, v);
-    }
-    // back substitution: y = D^-1 z, then x_i final from i = 5 down, rows r < i take  y_r -= L_ir x_i
-    if (is_b) v = v * dinv_mine;
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
-    for (int i = 5; i > 0; --i) {
-      const bool sub = is_b && ra < i;
-      const double xi = __shfl_sync(0xffffffffu, v, 24 + i);
-      const double lir = __shfl_sync(0xffffffffu, v, sub ? lt(i, ra) : lane);
-      if (sub) v = fma(-lir, xi, v);
-    }
-    const double y = v;  // lanes 24..29: solution of (H + D) y = g in the scaled space
-    reuse_diag = 1;
-    ok = ok && !__any_sync(0xffffffffu, is_b && !isfinite(y));
-    double mcc = 0.0;
+      for (int j = 0; j <= i; ++j)
+        m[lt(i, j)] = s->H[ut(j, i)] * s->scale[j] * s->scale[i] + (i == j ? s->diag[i] * inv_radius : 0.0);
+    bool ok = ldlt_solve6(m, gs, y);
+    s->reuse_diag = 1;
+    double mcc = 0;
     if (ok) {
-      // model_cost_change = -(step^T g + 1/2 step^T H step) with step = -y and (H + D) y = g  =  1/2 (y^T g + y^T D y)
-      const double t = is_b ? y * gs + y * y * dd : 0.0;  // lanes 24..31 form an aligned group of eight
-      mcc = 0.5 * __shfl_sync(0xffffffffu, warp_sum8(t, lane), 24);
+      // model_cost_change = -(step^T g + 1/2 step^T H step) with step = -y and (H + D) y = g
+      //                   = 1/2 (y^T g + y^T D y)
+      double yg = 0, yDy = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        step[a] = -y[a];
+        yg += y[a] * gs[a];
+        yDy += y[a] * y[a] * (s->diag[a] * inv_radius);
+        ok = ok && isfinite(y[a]);
+      }
+      mcc = 0.5 * (yg + yDy);
     }
     if (!ok || !(mcc > 0.0)) {  // HandleInvalidStep
-      n_unsuccess += 1;
-      if (++invalid_run >= 5) {
-        finish(ILSM_FAILURE, phase);
+      s->n_unsuccess += 1;
+      if (++s->invalid_run >= 5) {
+        lm_terminate(s, rep, ILSM_FAILURE);
         return;
       }
-      radius = radius * frcp(decrease_factor);
-      decrease_factor *= 2.0;
-      reuse_diag = 1;
+      s->radius = s->radius * frcp(s->decrease_factor);
+      s->decrease_factor *= 2.0;
+      s->reuse_diag = 1;
       continue;
     }
-    invalid_run = 0;
-    model_cost_change = mcc;
-    const double delta = is_b ? -y * s->scale[ra] : 0.0;
-    // candidate = Plus(x, delta): the rotation part is needed by every lane that writes a quaternion component
-    const double d3v[3] = {__shfl_sync(0xffffffffu, delta, 24), __shfl_sync(0xffffffffu, delta, 25), __shfl_sync(0xffffffffu, delta, 26)};
-    const double xq[4] = {s->xq[0], s->xq[1], s->xq[2], s->xq[3]};
-    double cq[4];
-    quat_plus_d(xq, d3v, cq);
-    if (lane < 4) s->cq[lane] = lane == 0 ? cq[0] : lane == 1 ? cq[1] : lane == 2 ? cq[2] : cq[3];
-    if (is_b && ra >= 3) s->ct[ra - 3] = s->xt[ra - 3] + delta;
-    finish(-1, 1);
+    s->invalid_run = 0;
+    s->model_cost_change = mcc;
+    double delta[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) delta[a] = step[a] * s->scale[a];
+    quat_plus_d(s->xq, delta, s->cq);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s->ct[i] = s->xt[i] + delta[3 + i];
+    s->phase = 1;
     return;
   }
 }
@@ -1023,7 +989,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
     // re-arm this buffer's barrier for evaluation e + 2: a peer can only push that far ahead after it has received this
     // CTA's partial of evaluation e + 1, which is sent after this point
     if (tid == 0) mbar_expect_tx(smem_u32(&xbar[buf]), kXferBytes);
-    if (warp == 0) lm_advance_warp(s, rep, tot, lane);
+    if (tid == 0) lm_advance(s, rep, tot);
     STAMP(5);
     __syncthreads();
     STAMP(6);

@@ -225,6 +225,72 @@ def make_frame(scene, q_ws, t_ws, seed=SEED_FRAME, H=64, W=1024, noise=0.01, max
     return cloud, tag
 
 
+def make_frames_torch(scene, poses, seed0, device, H=64, W=1024, noise=0.01, max_range=50.0, fov_deg=45.0, out=None):
+    """The same sensor model as make_frame for a whole sequence, ray-cast on the GPU with torch (data generation only:
+    a 2000-frame sequence takes seconds instead of half an hour with the numpy ray-caster).  poses: [(q_ws, t_ws)];
+    frame k uses torch seed seed0 + k for the range noise and the intensities.  Returns a pinned (F, H*W, 4) float32
+    host tensor of organised sensor-frame clouds (x y z intensity; no-return = 0).  Boxes further than max_range from the
+    sensor are culled per frame; poles are handled like Scene.raycast.  Not bit-identical to make_frame (float64 on the
+    GPU, another noise stream) -- both the CUDA path and the oracle consume the arrays it returns."""
+    import torch
+    F = len(poses)
+    if out is None:
+        out = torch.empty((F, H * W, 4), dtype=torch.float32).pin_memory()
+    d_s = torch.from_numpy(os0_dirs(H, W, fov_deg)).to(device)
+    boxes = torch.from_numpy(np.asarray(scene.boxes, np.float64).reshape(-1, 6)).to(device)
+    poles = torch.from_numpy(np.asarray(scene.poles, np.float64).reshape(-1, 5)).to(device)
+    inf = float("inf")
+    gen = torch.Generator(device=device)
+    for k, (q, t) in enumerate(poses):
+        R = torch.from_numpy(quat_to_mat(np.asarray(q, np.float64))).to(device)
+        o = torch.from_numpy(np.asarray(t, np.float64)).to(device)
+        d = d_s @ R.T
+        best = torch.where(d[:, 2] < -1e-9, -o[2] / d[:, 2], torch.full_like(d[:, 2], inf))
+        inv = 1.0 / torch.where(d.abs() < 1e-12, torch.full_like(d, 1e-12), d)
+        if len(boxes):
+            # cull by the box's distance to the sensor in the xy plane
+            cx = torch.clamp(o[0], boxes[:, 0], boxes[:, 3]) - o[0]
+            cy = torch.clamp(o[1], boxes[:, 1], boxes[:, 4]) - o[1]
+            near = boxes[(cx * cx + cy * cy) <= (max_range + 1.0) ** 2]
+            if len(near):
+                t0 = (near[None, :, :3] - o) * inv[:, None, :]
+                t1 = (near[None, :, 3:] - o) * inv[:, None, :]
+                tn = torch.minimum(t0, t1).amax(dim=2)
+                tf = torch.maximum(t0, t1).amin(dim=2)
+                hit = (tn <= tf) & (tn > 1e-6)
+                best = torch.minimum(best, torch.where(hit, tn, torch.full_like(tn, inf)).amin(dim=1))
+        if len(poles):
+            ox, oy = o[0] - poles[None, :, 0], o[1] - poles[None, :, 1]
+            a = (d[:, 0] ** 2 + d[:, 1] ** 2)[:, None]
+            bq = 2 * (ox * d[:, 0:1] + oy * d[:, 1:2])
+            cq = ox * ox + oy * oy - poles[None, :, 2] ** 2
+            disc = bq * bq - 4 * a * cq
+            tt = torch.where((disc > 0) & (a > 1e-12), (-bq - torch.sqrt(disc.clamp_min(0))) / (2 * a), torch.full_like(disc, inf))
+            z = o[2] + tt * d[:, 2:3]
+            ok = (tt > 1e-6) & (z >= poles[None, :, 3]) & (z <= poles[None, :, 4])
+            best = torch.minimum(best, torch.where(ok, tt, torch.full_like(tt, inf)).amin(dim=1))
+        ok = torch.isfinite(best) & (best <= max_range)
+        gen.manual_seed(int(seed0) + k)
+        r = best + noise * torch.randn(len(best), generator=gen, device=device, dtype=torch.float64)
+        inten = 255.0 * torch.rand(len(best), generator=gen, device=device, dtype=torch.float64)
+        r = torch.where(ok, r, torch.zeros_like(r))
+        cloud = torch.zeros((H * W, 4), dtype=torch.float32, device=device)
+        cloud[:, :3] = (d_s * r[:, None]).to(torch.float32)
+        cloud[:, 3] = torch.where(ok, inten, torch.zeros_like(inten)).to(torch.float32)
+        out[k].copy_(cloud, non_blocking=True)
+    torch.cuda.synchronize(device)
+    return out
+
+
+def corridor_poses(n_frames, step=0.2):
+    """SURVEY 8d config 2 trajectory: `step` m per frame forward along the corridor, sinusoidal yaw +-5 degrees."""
+    poses = []
+    for k in range(n_frames):
+        yaw = np.deg2rad(5.0) * np.sin(2 * np.pi * k / 50.0)
+        poses.append((quat_from_rotvec([0.0, 0.0, yaw]), np.array([2.0 + step * k, 0.1 * np.sin(k / 15.0), 1.2])))
+    return poses
+
+
 def voxel_centroid_np(pts, leaf):
     """Plain numpy voxel-centroid thinning used only to synthesise feature stacks (NOT the PCL restatement)."""
     if len(pts) == 0:
