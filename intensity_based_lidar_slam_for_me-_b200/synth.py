@@ -363,6 +363,41 @@ def sc_database(n, seed=SEED_SC):
     return d
 
 
+SC_CHUNK = 1000
+
+
+def sc_database_chunk(ci, n_total):
+    """Chunk ci (SC_CHUNK keyframes, seeded by its index) of a database of n_total keyframes: every rank of a sharded run
+    generates its own shard -- and the source entries of the queries -- without materialising the whole database."""
+    return sc_database(min(SC_CHUNK, n_total - ci * SC_CHUNK), seed=SEED_SC + 17 * ci)
+
+
+def sc_database_range(lo, hi, n_total):
+    """Descriptors [lo, hi) of the chunk-seeded database."""
+    parts = []
+    for ci in range(lo // SC_CHUNK, (hi + SC_CHUNK - 1) // SC_CHUNK):
+        c = sc_database_chunk(ci, n_total)
+        parts.append(c[max(lo, ci * SC_CHUNK) - ci * SC_CHUNK: min(hi, (ci + 1) * SC_CHUNK) - ci * SC_CHUNK])
+    return np.concatenate(parts) if parts else np.zeros((0, 20, 60), np.float32)
+
+
+def sc_chunked_queries(n_total, n_q, seed=SEED_SC + 1, noise=0.05, exclude_recent=50):
+    """n_q queries against the chunk-seeded database: entries older than the newest `exclude_recent` re-rendered with a
+    known yaw shift + noise.  Returns (queries (n_q, 20, 60), true ids, true shifts)."""
+    rng = np.random.default_rng(seed)
+    ids = np.sort(rng.integers(0, n_total - exclude_recent, n_q))  # sorted: consecutive queries share source chunks
+    shifts = rng.integers(0, 60, n_q)
+    q = np.empty((n_q, 20, 60), np.float32)
+    cache = (-1, None)
+    for j, (i, s) in enumerate(zip(ids, shifts)):
+        ci = int(i) // SC_CHUNK
+        if cache[0] != ci:
+            cache = (ci, sc_database_chunk(ci, n_total))
+        d = np.roll(cache[1][int(i) - ci * SC_CHUNK], int(s), axis=1).astype(np.float32)
+        q[j] = d + rng.normal(0.0, noise, d.shape).astype(np.float32) * (d != 0)
+    return q, ids.astype(np.int32), shifts.astype(np.int32)
+
+
 def sc_queries(db, n_q, seed=SEED_SC + 1, noise=0.05):
     """Queries = database entries re-rendered with a yaw shift of U{0..59} sectors plus N(0, noise) on the occupied
     bins, so the true id and shift are known.  Returns (queries, true ids, true shifts)."""

@@ -20,6 +20,7 @@ _LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
+_REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
 
 def build(force: bool = False) -> None:
@@ -28,7 +29,8 @@ def build(force: bool = False) -> None:
     stale = (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
     need_ref = ((not os.path.exists(_REF)) and os.path.exists("/root/reference/include/nanoflann.hpp")) or \
         ((not os.path.exists(_REF_IKD)) and os.path.exists("/root/reference/src/ikd-Tree/ikd_Tree.cpp")) or \
-        ((not os.path.exists(_REF_FUN)) and os.path.exists("/root/reference/src/lidarFeaturePointsFunction.hpp"))
+        ((not os.path.exists(_REF_FUN)) and os.path.exists("/root/reference/src/lidarFeaturePointsFunction.hpp")) or \
+        ((not os.path.exists(_REF_ALOAM)) and os.path.exists("/root/reference/include/nanoflann.hpp"))
     if force or stale or need_ref:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
 
@@ -104,6 +106,20 @@ def knn_kdtree(map_xyz, q_xyz, k=5):
     d2 = np.empty((len(q), k), np.float32)
     lib().orc_knn_kdtree(_p(m), len(m), m.strides[0], _p(q), len(q), q.strides[0], k, _p(idx), _p(d2))
     return idx, d2
+
+
+def knn_kdtree_omp(map_xyz, q_xyz, k=5, threads=0, tree="own"):
+    """k-NN only, OpenMP over the host cores: (idx, d2, threads used, build seconds, query seconds)."""
+    m, q = _f32(map_xyz), _f32(q_xyz)
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    L = lib() if tree == "own" else lib_nanoflann()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_aloam.so not available")
+    bs, qs = C.c_double(0), C.c_double(0)
+    used = L.orc_knn_kdtree_omp(_p(m), len(m), m.strides[0], _p(q), len(q), q.strides[0], k, _p(idx), _p(d2), int(threads),
+                                C.byref(bs), C.byref(qs))
+    return idx, d2, used, bs.value, qs.value
 
 
 class RefKdTree:
@@ -182,12 +198,32 @@ def solve(factors, qt, max_iter=4, huber_a=0.1):
     return x, s
 
 
-def register_aloam(map_corner, map_surf, corner, surf, qt, outer=2, max_iter=4):
+_lib_nf = None
+
+
+def lib_nanoflann():
+    """The same restatement compiled on the reference's vendored nanoflann tree (oracle/_ref/libref_aloam.so): the k-d
+    tree of the CPU baseline ("Ceres + kd-tree").  None when it was never built."""
+    global _lib_nf
+    if _lib_nf is None:
+        if not os.path.exists(_REF_ALOAM):
+            build()
+        if not os.path.exists(_REF_ALOAM):
+            return None
+        _lib_nf = C.CDLL(_REF_ALOAM)
+    return _lib_nf
+
+
+def register_aloam(map_corner, map_surf, corner, surf, qt, outer=2, max_iter=4, tree="own"):
+    """tree = "own": the oracle's private k-d tree; "nanoflann": the reference's vendored nanoflann (CPU baseline)."""
     mc, ms, c, s = _f32(map_corner), _f32(map_surf), _f32(corner), _f32(surf)
     x = np.array(qt, np.float64)
     sums = (SolveSummary * outer)()
     nf = np.zeros(2 * outer, np.int32)
-    n = lib().orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), _stride(mc), _p(c), len(c), _p(s), len(s),
+    L = lib() if tree == "own" else lib_nanoflann()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_aloam.so not available")
+    n = L.orc_register_aloam(_p(mc), len(mc), _p(ms), len(ms), _stride(mc), _p(c), len(c), _p(s), len(s),
                                  _stride(c) if len(c) else _stride(s), _p(x), outer, max_iter, sums, _p(nf))
     return x, list(sums)[:n], nf
 

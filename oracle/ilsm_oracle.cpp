@@ -14,12 +14,15 @@
 // Build: see oracle/Makefile (g++ -O3 -std=c++14 -ffp-contract=off, the reference's flags
 // CMakeLists.txt:5-6: -O3, no -march, hence no FMA contraction).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <limits>
 #include <numeric>
 #include <vector>
+#include <atomic>
+#include <thread>
 
 #define ORC_API extern "C" __attribute__((visibility("default")))
 
@@ -95,6 +98,50 @@ inline const float* pt(const float* base, int stride_f, int i) { return base + (
 // bound fl((q-split)^2) which is <= the float distance of every point behind the split plane because
 // float subtraction, squaring and adding non-negative terms are all monotone under round-to-nearest,
 // so results are identical to brute force including ties.
+#ifdef ORC_USE_NANOFLANN
+// CPU-baseline variant (oracle/_ref/libref_aloam.so, built only where /root/reference exists): the same restatement
+// with the k-d tree replaced by the REFERENCE'S OWN vendored nanoflann 1.3.2 (include/nanoflann.hpp) -- the port of
+// FLANN's KDTreeSingleIndex that pcl::KdTreeFLANN wraps (laserMapping.cpp:631-634), leaf size 15 like PCL's
+// KDTreeSingleIndexParams(15), L2_Simple<float>, NANOFLANN_FIRST_MATCH (lower index wins ties, the tie-break of this
+// repository).  Same build / knn interface as the private tree below, same results (tests pin both to each other).
+}  // namespace (reopened below)
+#define NANOFLANN_FIRST_MATCH 1
+#include <nanoflann.hpp>
+#include <memory>
+namespace {
+struct KdTree {
+  const float* base = nullptr;
+  int stride_f = 0, n = 0;
+  struct Cloud {
+    const float* base;
+    size_t n;
+    int stride_f;
+    inline size_t kdtree_get_point_count() const { return n; }
+    inline float kdtree_get_pt(const size_t idx, const size_t dim) const { return base[idx * stride_f + dim]; }
+    template <class BBOX>
+    bool kdtree_get_bbox(BBOX&) const { return false; }
+  };
+  typedef nanoflann::KDTreeSingleIndexAdaptor<nanoflann::L2_Simple_Adaptor<float, Cloud>, Cloud, 3, int32_t> Tree;
+  std::unique_ptr<Cloud> cloud;
+  std::unique_ptr<Tree> tree;
+  void build(const float* b, int n_, int stride_f_) {
+    base = b, n = n_, stride_f = stride_f_;
+    cloud.reset(new Cloud{b, (size_t)n_, stride_f_});
+    tree.reset(new Tree(3, *cloud, nanoflann::KDTreeSingleIndexAdaptorParams(15)));
+    tree->buildIndex();
+  }
+  void knn(const float* q, int k, int32_t* idx, float* d2) const {
+    size_t found = 0;
+    if (n > 0) {
+      nanoflann::KNNResultSet<float, int32_t> rs((size_t)k);
+      rs.init(idx, d2);
+      tree->findNeighbors(rs, q, nanoflann::SearchParams(10));
+      found = rs.size();
+    }
+    for (int j = (int)found; j < k; ++j) idx[j] = -1, d2[j] = INFINITY;
+  }
+};
+#else
 struct KdTree {
   const float* base = nullptr;
   int stride_f = 0, n = 0;
@@ -170,6 +217,8 @@ struct KdTree {
     }
   }
 };
+
+#endif  // ORC_USE_NANOFLANN
 
 // ------------------------------------------------------------------------------------------------
 // Fits (laserMapping.cpp:681-722 line; :756-796 plane; mapOptimization.cpp:395-427 plane)
@@ -705,6 +754,38 @@ ORC_API void orc_transform_points(const double qt[7], const float* in, int n, in
   Quat q{qt[0], qt[1], qt[2], qt[3]};
   V3 t{qt[4], qt[5], qt[6]};
   for (int i = 0; i < n; ++i) associate_to_map(q, t, pt(in, stride_bytes / 4, i), out_xyz + 3 * (size_t)i);
+}
+
+// k-NN only, spread over `threads` host threads (<= 0: all hardware threads): the "B-knn-omp" CPU baseline of
+// BASELINE.md section 3 (laserMapping.cpp:673,753 queried from a parallel loop; std::thread instead of OpenMP -- this
+// image ships libgomp.so.1 without its spec file, so -fopenmp does not link).  build_s / query_s receive the wall time
+// of the two phases; returns the number of threads used.
+ORC_API int orc_knn_kdtree_omp(const float* map, int n, int map_stride_bytes, const float* q, int nq, int q_stride_bytes, int k,
+                               int32_t* idx, float* d2, int threads, double* build_s, double* query_s) {
+  const auto t0 = std::chrono::steady_clock::now();
+  KdTree tree;
+  tree.build(map, n, map_stride_bytes / 4);
+  const auto t1 = std::chrono::steady_clock::now();
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads < 1) threads = 1;
+  std::atomic<int> next(0);
+  const int chunk = 256, qs = q_stride_bytes / 4;
+  auto work = [&]() {
+    for (;;) {
+      const int lo = next.fetch_add(chunk);
+      if (lo >= nq) return;
+      const int hi = lo + chunk < nq ? lo + chunk : nq;
+      for (int i = lo; i < hi; ++i) tree.knn(q + (size_t)i * qs, k, idx + (size_t)i * k, d2 + (size_t)i * k);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  const auto t2 = std::chrono::steady_clock::now();
+  if (build_s) *build_s = std::chrono::duration<double>(t1 - t0).count();
+  if (query_s) *query_s = std::chrono::duration<double>(t2 - t1).count();
+  return threads;
 }
 
 ORC_API int orc_fit_line(const float nb[15], OrcFactor* f) {
