@@ -91,6 +91,12 @@ ILSM_API int ilsm_map_size(const ilsm_map* map);
  *           ikdtree->Build(points)                                                mapOptimization.cpp:192 */
 ILSM_API int ilsm_map_build(ilsm_map* map, const float* xyz, int n, int stride_bytes, float cell);
 ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int stride_bytes, float cell);
+/* Both search structures of a frame in one call: three launches build the two maps side by side (the reference builds
+ * them on consecutive lines).  Same semantics as two ilsm_map_build_dev calls.
+ * Replaces: kdtreeCornerFromMap->setInputCloud(...); kdtreeSurfFromMap->setInputCloud(...);  laserMapping.cpp:631-634
+ *           kdtreeCornerLast->setInputCloud(...); kdtreeSurfLast->setInputCloud(...);          laserOdometry.cpp:807-808 */
+ILSM_API int ilsm_map_build_pair_dev(ilsm_map* map_a, const float* d_xyz_a, int n_a, ilsm_map* map_b, const float* d_xyz_b, int n_b,
+                                     int stride_bytes, float cell);
 /* Builds run on the map's own stream (the corner and surf structures of a frame are built concurrently); every entry
  * point that uses a map orders itself after its build.  ilsm_map_join makes the CONTEXT stream wait for the build
  * without using the map (for CUDA-event timing of the build on the context stream). */

@@ -136,6 +136,7 @@ def load_library(path: str | None = None):
         "ilsm_project_dev": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "ilsm_extract_features": (i32, [vp, vp, i32, i32, f32, C.POINTER(Features)]),
         "ilsm_voxelgrid": (i32, [vp, vp, i32, i32, f32, vp, C.POINTER(i32)]),
+        "ilsm_map_build_pair_dev": (i32, [vp, vp, i32, vp, vp, i32, i32, C.c_float]),
         "ilsm_register_frame": (i32, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
         "ilsm_register_frame_dev": (i32, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp]),
         "ilsm_sc_create": (i32, [vp, C.POINTER(vp)]),
@@ -472,6 +473,11 @@ class LocalMap:
 
     def build_dev(self, d_ptr: int, n: int, stride: int, cell: float = 0.0):
         _check(self._lib.ilsm_map_build_dev(self._h, d_ptr, n, stride, cell))
+        return self
+
+    def build_pair_dev(self, d_ptr: int, n: int, other: "LocalMap", d_ptr_other: int, n_other: int, stride: int, cell: float = 0.0):
+        """This map and `other` (the corner and surf structures of a frame) built by one set of three launches."""
+        _check(self._lib.ilsm_map_build_pair_dev(self._h, d_ptr, n, other._h, d_ptr_other, n_other, stride, cell))
         return self
 
     def join(self):

@@ -122,7 +122,7 @@ void Map::release() {
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr, ready = nullptr, ctx_done = nullptr;
   cells.release(), sorted.release(), orig.release(), slot_of.release(), rank_of.release(), counters.release(), occ.release();
-  gen = 0, prev_n = 0, clean_size = 0;
+  gen = 0, cur = 0, table_cap = 0, occ_cap = 0, clean_size[0] = clean_size[1] = 0, filled_n[0] = filled_n[1] = 0;
   bbox.release(), raw.release();
   vox_table.release(), ins_new.release(), ins_out.release(), ins_slot_new.release(), ins_slot_old.release();
   ins_keep.release(), ins_pos.release(), ins_bsum.release();
@@ -250,6 +250,16 @@ ILSM_API int ilsm_map_build_dev(ilsm_map* map, const float* d_xyz, int n, int st
   std::lock_guard<std::mutex> lk(map->m.ctx->mu);
   ILSM_CUDA(cudaSetDevice(map->m.ctx->device));
   return map->m.build_dev(d_xyz, n, stride_bytes, cell);
+}
+
+ILSM_API int ilsm_map_build_pair_dev(ilsm_map* map_a, const float* d_xyz_a, int n_a, ilsm_map* map_b, const float* d_xyz_b, int n_b,
+                                     int stride_bytes, float cell) {
+  if (!map_a || !map_b || (n_a > 0 && !d_xyz_a) || (n_b > 0 && !d_xyz_b)) return fail(ILSM_ERR_INVALID_ARG, "map_build_pair_dev: null argument");
+  if (n_a < 0 || n_b < 0 || !valid_stride(stride_bytes)) return fail(ILSM_ERR_INVALID_ARG, "map_build_pair_dev: bad n/stride");
+  Ctx& c = *map_a->m.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return build_pair_dev(&map_a->m, d_xyz_a, n_a, &map_b->m, d_xyz_b, n_b, stride_bytes, cell);
 }
 
 ILSM_API int ilsm_map_join(ilsm_map* map) {

@@ -369,8 +369,8 @@ int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_
   ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
   const bool optimise = n_mc > o.min_corner_map && n_ms > o.min_surf_map;  // laserMapping.cpp:624
   if (optimise) {
-    if ((rc = m.map_c.build_dev(reinterpret_cast<const float*>(m.from_c.p), n_mc, 16, 0.f)) ||
-        (rc = m.map_s.build_dev(reinterpret_cast<const float*>(m.from_s.p), n_ms, 16, 0.f)))
+    if ((rc = build_pair_dev(&m.map_c, reinterpret_cast<const float*>(m.from_c.p), n_mc, &m.map_s, reinterpret_cast<const float*>(m.from_s.p),
+                             n_ms, 16, 0.f)))
       return rc;
   }
   // the stacks produced on the caller's side stream are first needed here: the window roll, the 5x5x3 gather and the two

@@ -123,6 +123,8 @@ struct PoseDst {
 };
 
 struct Ctx;
+struct Map;
+int build_pair_dev(Map* a, const float* d_a, int na, Map* b, const float* d_b, int nb, int stride_bytes, float cell_size);
 
 struct Map {
   Ctx* ctx = nullptr;
@@ -133,9 +135,17 @@ struct Map {
   DevBuf<GridCell> cells;
   DevBuf<float4> sorted, orig;
   DevBuf<uint32_t> slot_of, rank_of, counters;
-  DevBuf<uint32_t> occ;      // slots claimed by the last build (what the next build has to clear)
-  int gen = 0, prev_n = 0;   // build generation (ping-pongs the occupied-voxel counter), point count of the last build
-  size_t clean_size = 0;     // cells[0, clean_size) is EMPTY apart from the slots listed in occ
+  // Two hash tables, occupied-slot lists, counter sets and boxes per map, used alternately: build g fills table g & 1
+  // while its scatter launch empties the other one (the slots listed by the build before), so no clear pass is ever on
+  // the critical path.  Table t = cells.p + t * table_cap, list t = occ.p + t * occ_cap, set t = counters.p + 8 t,
+  // box t = bbox.p + 8 t.
+  DevBuf<uint32_t> occ;
+  uint32_t table_cap = 0;    // slots allocated per table
+  size_t occ_cap = 0;        // entries allocated per list
+  int gen = 0;               // build generation
+  int cur = 0;               // table of the last build (what view() shows)
+  size_t clean_size[2] = {0, 0};  // table t is EMPTY in [0, clean_size[t]) ...
+  int filled_n[2] = {0, 0};       // ... unless filled_n[t] != 0: it still holds a build of (at most) that many voxels
   DevBuf<int> bbox;
   DevBuf<float> raw;  // staging of caller bytes for the host-pointer entry points
   // Each map builds on its own stream so that the corner and surf structures of a frame are built concurrently
@@ -153,6 +163,10 @@ struct Map {
   int init(Ctx* c);
   int wait_ready(cudaStream_t user);
   int build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size);
+  int prepare_build(const float* d_src, int n_pts, int stride_bytes, float cell_size, cudaStream_t s, void* job_out);
+  const GridCell* cur_cells() const { return cells.p + (size_t)cur * table_cap; }
+  const uint32_t* cur_occ() const { return occ.p + (size_t)cur * occ_cap; }
+  const uint32_t* cur_counters() const { return counters.p + 8 * cur; }
   int knn_dev(const float* d_q, int nq, int stride_bytes, int k, float max_dist, int32_t* d_idx, float* d_d2);
   GridView view() const;
   void release();

@@ -280,15 +280,15 @@ static int launch_binned(Ctx* ctx, Map* m, Map* qb, const float* d_q, int nq, in
   QWork* work = reinterpret_cast<QWork*>(ctx->qwork.p);
   uint32_t* n_work = reinterpret_cast<uint32_t*>(ctx->qwork.p + (size_t)4 * qwork_items(nq));
   ILSM_CUDA(cudaMemsetAsync(n_work, 0, sizeof(uint32_t), s));
-  ILSM_CUDA(launch_pdl(qbin_work_kernel, dim3((nq + 255) / 256), dim3(256), 0, s, (const GridCell*)qb->cells.p, (const uint32_t*)qb->occ.p,
-                       (const uint32_t*)qb->counters.p, occ_slot, work, n_work));
+  ILSM_CUDA(launch_pdl(qbin_work_kernel, dim3((nq + 255) / 256), dim3(256), 0, s, qb->cur_cells(), qb->cur_occ(),
+                       qb->cur_counters(), occ_slot, work, n_work));
   // one warp per group; grid = a few resident waves, further groups are taken grid-stride
   long long blocks = ((long long)nq + 3) / 4, cap = (long long)ctx->sm_count * 16;
   if (blocks > cap) blocks = cap;
   ILSM_CUDA(launch_pdl(knn_binned_kernel<K>, dim3((unsigned)blocks), dim3(128), 0, s, g, (const float4*)qb->sorted.p, (const QWork*)work,
                        (const uint32_t*)n_work, k, max_d2, d_idx, d_d2));
   ILSM_CUDA(launch_pdl(knn_outlier_kernel<K>, dim3(ctx->sm_count), dim3(128), 0, s, g, d_q, nq, stride_f, (const uint32_t*)qb->slot_of.p,
-                       (const uint32_t*)qb->counters.p, k, max_d2, d_idx, d_d2));
+                       qb->cur_counters(), k, max_d2, d_idx, d_d2));
   count_launches(3);
   return ILSM_OK;
 }
@@ -304,7 +304,7 @@ int knn_binned_dev(Ctx* ctx, Map* m, const float* d_q, int nq, int stride_bytes,
   Map* qb = ctx->qbin;
   if ((rc = ctx->qwork.reserve((size_t)4 * qwork_items(nq) + 16))) return rc;  // QWork = 4 ints; the counter sits behind the list
   // the query cloud through the map build's count / alloc / scatter: queries grouped by voxel, original index in .w
-  const int occ_slot = 4 + (qb->gen & 1);
+  const int occ_slot = 4;  // occupied-voxel count of the build's own counter set
   if ((rc = qb->build_dev(d_q, nq, stride_bytes, m->cell))) return rc;
   if ((rc = m->wait_ready(ctx->stream)) || (rc = qb->wait_ready(ctx->stream))) return rc;
   const float max_d2 = max_dist > 0.f ? max_dist * max_dist : 0.f;

@@ -19,6 +19,35 @@
 
 namespace ilsm {
 
+// One build job = one map.  A launch serves one or two jobs (the corner and surf structures of a frame): blocks
+// [0, nb0) work for job 0, the rest for job 1.
+struct BuildJob {
+  const float* src;
+  int n, stride_f, ioff;
+  float inv_cell;
+  GridCell* cells;       // the table this build fills (EMPTY on entry)
+  uint32_t mask;
+  int log2_size;
+  float4* orig;
+  float4* sorted;
+  uint32_t *slot_of, *rank_of;
+  uint32_t* counters;    // this build's set: [0] range cursor, [2] skipped points, [4] occupied voxels, [6] scatter ticket
+  uint32_t* occ;         // slots claimed by this build
+  int* bbox;             // this build's bounding box of occupied voxels
+  // the OTHER table of the map (filled two builds ago, searched until this build started): cleaned while this build
+  // scatters, so that the next build finds it empty -- no clear pass on anybody's critical path
+  GridCell* o_cells;
+  const uint32_t* o_occ;
+  uint32_t* o_counters;
+  int* o_bbox;
+  int o_cover;           // upper bound of the other table's occupied-slot count (its build's point count), 0: nothing to clean
+  int blocks;            // blocks of this job in the count / alloc / scatter launches
+};
+struct BuildJobs {
+  BuildJob j[2];
+  int nb0;
+};
+
 __global__ void grid_clear_kernel(GridCell* cells, uint32_t size, int* bbox, uint32_t* counters) {
   pdl_entry();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -29,24 +58,7 @@ __global__ void grid_clear_kernel(GridCell* cells, uint32_t size, int* bbox, uin
   }
   if (i < 3) bbox[i] = INT_MAX;
   if (i >= 3 && i < 6) bbox[i] = INT_MIN;
-  if (i < 6) counters[i] = 0;  // [0] cursor, [2] skipped points, [4], [5] occupied voxels (ping-pong by build generation)
-}
-
-// counters: [0] cursor, [2] skipped points, [4 + (gen & 1)] occupied voxels of build `gen`
-__global__ void grid_clear_sparse_kernel(GridCell* cells, const uint32_t* __restrict__ occ, int* bbox, uint32_t* counters,
-                                         int gen) {
-  pdl_entry();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n_prev = counters[4 + ((gen - 1) & 1)];  // nobody writes this one in this launch
-  if (i < n_prev) {
-    uint4 e;
-    e.x = 0xFFFFFFFFu, e.y = 0xFFFFFFFFu, e.z = 0u, e.w = 0u;
-    reinterpret_cast<uint4*>(cells)[occ[i]] = e;
-  }
-  if (i < 3) bbox[i] = INT_MAX;
-  if (i >= 3 && i < 6) bbox[i] = INT_MIN;
-  if (i < 3) counters[i] = 0;
-  if (i == 3) counters[4 + (gen & 1)] = 0;
+  if (i < 8) counters[i] = 0;
 }
 
 __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i, float& x, float& y, float& z) {
@@ -55,29 +67,28 @@ __device__ __forceinline__ bool load_point(const float* src, int stride_f, int i
   return isfinite(x) && isfinite(y) && isfinite(z);
 }
 
-__global__ void grid_count_kernel(const float* __restrict__ src, int n, int stride_f, int ioff, float inv_cell, GridCell* cells,
-                                  uint32_t mask, int log2_size, float4* __restrict__ orig,
-                                  uint32_t* __restrict__ slot_of, uint32_t* __restrict__ rank_of,
-                                  uint32_t* counters, uint32_t* __restrict__ occ, int gen) {
+__global__ void __launch_bounds__(256) grid_count_kernel(BuildJobs jobs) {
   pdl_entry();
   __shared__ uint32_t s_wnew[8];
   __shared__ uint32_t s_obase;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (int)blockIdx.x >= jobs.nb0;
+  const BuildJob& jb = jobs.j[w];
+  const int i = ((int)blockIdx.x - (w ? jobs.nb0 : 0)) * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool in = i < n;
+  const bool in = i < jb.n;
   float x = 0.f, y = 0.f, z = 0.f;
-  bool ok = in && load_point(src, stride_f, i, x, y, z);
+  bool ok = in && load_point(jb.src, jb.stride_f, i, x, y, z);
   // w keeps the caller's intensity channel (LOAM clouds carry scanID + 0.1*relTime there, laserOdometry.cpp:461)
-  if (in) orig[i] = make_float4(x, y, z, ioff >= 0 ? __ldg(src + (size_t)i * stride_f + ioff) : 0.f);
+  if (in) jb.orig[i] = make_float4(x, y, z, jb.ioff >= 0 ? __ldg(jb.src + (size_t)i * jb.stride_f + jb.ioff) : 0.f);
   int cx = 0, cy = 0, cz = 0;
   if (ok) {
-    float ux = __fmul_rn(x, inv_cell), uy = __fmul_rn(y, inv_cell), uz = __fmul_rn(z, inv_cell);
+    float ux = __fmul_rn(x, jb.inv_cell), uy = __fmul_rn(y, jb.inv_cell), uz = __fmul_rn(z, jb.inv_cell);
     ok = fabsf(ux) < (float)kCoordLim && fabsf(uy) < (float)kCoordLim && fabsf(uz) < (float)kCoordLim;
     cx = __float2int_rd(ux), cy = __float2int_rd(uy), cz = __float2int_rd(uz);
   }
   if (in && !ok) {
-    slot_of[i] = 0xFFFFFFFFu;
-    atomicAdd(&counters[2], 1u);
+    jb.slot_of[i] = 0xFFFFFFFFu;
+    atomicAdd(&jb.counters[2], 1u);
   }
   // warp-aggregated claim: map clouds arrive voxel-ordered (VoxelGrid output, cube by cube), so the lanes of a warp
   // mostly share a handful of voxels -- one atomicCAS + one atomicAdd per distinct voxel of the warp instead of one
@@ -90,20 +101,20 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
     const int leader = __ffs(peers) - 1;
     uint32_t slot = 0, base = 0;
     if (lane == leader) {
-      slot = hash_voxel(key, log2_size);
+      slot = hash_voxel(key, jb.log2_size);
       for (;;) {
-        u64 prev = atomicCAS(&cells[slot].key, kEmptyKey, key);
+        u64 prev = atomicCAS(&jb.cells[slot].key, kEmptyKey, key);
         if (prev == kEmptyKey) created = true;
         if (prev == kEmptyKey || prev == key) break;
-        slot = (slot + 1) & mask;
+        slot = (slot + 1) & jb.mask;
       }
-      base = atomicAdd(&cells[slot].count, (uint32_t)__popc(peers));
+      base = atomicAdd(&jb.cells[slot].count, (uint32_t)__popc(peers));
       my_slot = slot;
     }
     slot = __shfl_sync(peers, slot, leader);
     base = __shfl_sync(peers, base, leader);
-    slot_of[i] = slot;
-    rank_of[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    jb.slot_of[i] = slot;
+    jb.rank_of[i] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   }
   // occupied-slot list: block-wide count of newly claimed slots, ONE atomicAdd on the list cursor per block
   const unsigned newb = __ballot_sync(0xffffffffu, created);
@@ -113,30 +124,32 @@ __global__ void grid_count_kernel(const float* __restrict__ src, int n, int stri
   if (threadIdx.x == 0) {
     uint32_t tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += s_wnew[w];
-    s_obase = tot ? atomicAdd(&counters[4 + (gen & 1)], tot) : 0u;
+    for (int k = 0; k < 8; ++k) tot += s_wnew[k];
+    s_obase = tot ? atomicAdd(&jb.counters[4], tot) : 0u;
   }
   __syncthreads();
   if (created) {
     uint32_t wb = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w)
-      if (w < warp) wb += s_wnew[w];
-    occ[s_obase + wb + (uint32_t)__popc(newb & ((1u << lane) - 1u))] = my_slot;
+    for (int k = 0; k < 8; ++k)
+      if (k < warp) wb += s_wnew[k];
+    jb.occ[s_obase + wb + (uint32_t)__popc(newb & ((1u << lane) - 1u))] = my_slot;
   }
 }
 
-// Every occupied slot gets a contiguous range of the sorted array (warp-aggregated atomicAdd on one cursor) and
-// the bounding box of occupied voxels is reduced per block (6 atomics per block instead of 6 per voxel).
-__global__ void grid_alloc_kernel(GridCell* cells, const uint32_t* __restrict__ occ, uint32_t* counters, int* bbox, int gen) {
+// Every occupied slot gets a contiguous range of the sorted array (one atomicAdd on the cursor per block) and the
+// bounding box of occupied voxels is reduced per block (6 atomics per block instead of 6 per voxel).
+__global__ void __launch_bounds__(256) grid_alloc_kernel(BuildJobs jobs) {
   pdl_entry();
-  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t size = counters[4 + (gen & 1)];  // occupied voxels of this build; the grid covers the upper bound n
+  const int w = (int)blockIdx.x >= jobs.nb0;
+  const BuildJob& jb = jobs.j[w];
+  const uint32_t li = ((uint32_t)blockIdx.x - (w ? (uint32_t)jobs.nb0 : 0u)) * blockDim.x + threadIdx.x;
+  const uint32_t size = jb.counters[4];  // occupied voxels of this build; the grid covers the upper bound n
   uint32_t cnt = 0;
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-  const uint32_t i = li < size ? occ[li] : 0u;
+  const uint32_t i = li < size ? jb.occ[li] : 0u;
   if (li < size) {
-    uint4 e = *reinterpret_cast<const uint4*>(cells + i);
+    uint4 e = *reinterpret_cast<const uint4*>(jb.cells + i);
     cnt = e.w;
     if (cnt) {
       u64 key = ((u64)e.y << 32) | e.x;
@@ -161,13 +174,13 @@ __global__ void grid_alloc_kernel(GridCell* cells, const uint32_t* __restrict__ 
   __syncthreads();
   uint32_t wbase = 0, btotal = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    if (w < (int)warp) wbase += s_wsum[w];
-    btotal += s_wsum[w];
+  for (int k = 0; k < 8; ++k) {
+    if (k < (int)warp) wbase += s_wsum[k];
+    btotal += s_wsum[k];
   }
-  if (threadIdx.x == 0) s_base = btotal ? atomicAdd(&counters[0], btotal) : 0u;
+  if (threadIdx.x == 0) s_base = btotal ? atomicAdd(&jb.counters[0], btotal) : 0u;
   __syncthreads();
-  if (li < size && cnt) cells[i].start = s_base + wbase + inc - cnt;
+  if (li < size && cnt) jb.cells[i].start = s_base + wbase + inc - cnt;
   // bounding box
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
@@ -186,22 +199,47 @@ __global__ void grid_alloc_kernel(GridCell* cells, const uint32_t* __restrict__ 
   }
   __syncthreads();
   if (threadIdx.x < 3 && s_lo[threadIdx.x] != INT_MAX) {
-    atomicMin(&bbox[threadIdx.x], s_lo[threadIdx.x]);
-    atomicMax(&bbox[3 + threadIdx.x], s_hi[threadIdx.x]);
+    atomicMin(&jb.bbox[threadIdx.x], s_lo[threadIdx.x]);
+    atomicMax(&jb.bbox[3 + threadIdx.x], s_hi[threadIdx.x]);
   }
 }
 
-__global__ void grid_scatter_kernel(const float4* __restrict__ orig, int n, const GridCell* __restrict__ cells,
-                                    const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank_of,
-                                    float4* __restrict__ sorted) {
+// Points into their voxel's range -- and, with the spare parallelism of the same launch, the map's OTHER table is
+// emptied (only the slots its build occupied); the job's last block then resets that table's counters and box.
+__global__ void __launch_bounds__(256) grid_scatter_kernel(BuildJobs jobs) {
   pdl_entry();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t slot = slot_of[i];
-  if (slot == 0xFFFFFFFFu) return;
-  float4 p = orig[i];
-  p.w = __uint_as_float((uint32_t)i);
-  sorted[cells[slot].start + rank_of[i]] = p;
+  __shared__ int s_last;
+  const int w = (int)blockIdx.x >= jobs.nb0;
+  const BuildJob& jb = jobs.j[w];
+  const int i = ((int)blockIdx.x - (w ? jobs.nb0 : 0)) * blockDim.x + threadIdx.x;
+  if (i < jb.n) {
+    const uint32_t slot = jb.slot_of[i];
+    if (slot != 0xFFFFFFFFu) {
+      float4 p = jb.orig[i];
+      p.w = __uint_as_float((uint32_t)i);
+      jb.sorted[jb.cells[slot].start + jb.rank_of[i]] = p;
+    }
+  }
+  if (jb.o_cover > 0) {
+    const uint32_t n_old = jb.o_counters[4];
+    for (uint32_t k = (uint32_t)i; k < n_old; k += (uint32_t)jb.blocks * blockDim.x) {
+      uint4 e;
+      e.x = 0xFFFFFFFFu, e.y = 0xFFFFFFFFu, e.z = 0u, e.w = 0u;
+      reinterpret_cast<uint4*>(jb.o_cells)[jb.o_occ[k]] = e;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(&jb.counters[6], 1u) == (uint32_t)jb.blocks - 1u;
+    }
+    __syncthreads();
+    if (s_last) {  // every block of the job has read o_counters[4]: the other set can be reset for its next build
+      if (threadIdx.x < 8) jb.o_counters[threadIdx.x] = 0;
+      if (threadIdx.x < 3) jb.o_bbox[threadIdx.x] = INT_MAX;
+      if (threadIdx.x >= 3 && threadIdx.x < 6) jb.o_bbox[threadIdx.x] = INT_MIN;
+      if (threadIdx.x == 0) jb.counters[6] = 0;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,65 +296,129 @@ int Map::wait_ready(cudaStream_t user) {
   return ILSM_OK;
 }
 
-int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size) {
+// Sizes, allocations and table hygiene of one map for a build of n_pts points; fills the job.  The map keeps TWO hash
+// tables and alternates between them: build g fills table g & 1, which build g - 1 emptied while it scattered.
+int Map::prepare_build(const float* d_src, int n_pts, int stride_bytes, float cell_size, cudaStream_t s, void* job_out) {
+  BuildJob& jb = *static_cast<BuildJob*>(job_out);
   if (n_pts < 0 || (stride_bytes % 4) != 0 || stride_bytes < 12) return fail(ILSM_ERR_INVALID_ARG, "map_build: bad n/stride");
   if (!(cell_size > 0.f)) cell_size = 1.0f;
+  int want_log2 = ilog2_ceil((uint32_t)(n_pts > 0 ? 2u * (uint32_t)n_pts : 2u));
+  if (want_log2 < 10) want_log2 = 10;
+  const uint32_t want_size = 1u << want_log2;
+  const GridCell* cells_before = cells.p;
+  const uint32_t *occ_before = occ.p, *counters_before = counters.p;
+  const int* bbox_before = bbox.p;
+  const uint32_t cap_before = table_cap;
+  // both tables / lists live back to back in one allocation each; growing one regrows both
+  uint32_t new_cap = table_cap;
+  if (want_size > new_cap) new_cap = want_size;
+  size_t new_occ_cap = occ_cap;
+  if ((size_t)n_pts + 1 > new_occ_cap) new_occ_cap = (size_t)n_pts + (size_t)n_pts / 2 + 64;
+  int rc;
+  if ((rc = cells.reserve((size_t)2 * new_cap)) || (rc = sorted.reserve(n_pts + 1)) || (rc = orig.reserve(n_pts + 1)) ||
+      (rc = slot_of.reserve(n_pts + 1)) || (rc = rank_of.reserve(n_pts + 1)) || (rc = bbox.reserve(16)) ||
+      (rc = counters.reserve(16)) || (rc = occ.reserve(2 * new_occ_cap)))
+    return rc;
+  const bool moved = cells.p != cells_before || occ.p != occ_before || counters.p != counters_before || bbox.p != bbox_before ||
+                     new_cap != cap_before || new_occ_cap != occ_cap;
+  table_cap = new_cap, occ_cap = new_occ_cap;
+  if (moved) clean_size[0] = clean_size[1] = 0, filled_n[0] = filled_n[1] = 0;  // nothing is known about the new memory
+  const int t = gen & 1, o = t ^ 1;
+  n = n_pts;
+  cell = cell_size;
+  inv_cell = 1.0f / cell_size;
+  log2_size = want_log2;
+  table_size = want_size;
+  cur = t;
+  GridCell* tab = cells.p + (size_t)t * table_cap;
+  // Invariant: slots [0, clean_size[t]) of table t are EMPTY and its counters / box are reset -- unless filled_n[t] != 0,
+  // i.e. the table still holds a build nobody cleaned (the first builds, or a build whose successor was not run).
+  if (filled_n[t] != 0 || (size_t)table_size > clean_size[t]) {
+    const int T = 256;
+    ILSM_CUDA(launch_pdl(grid_clear_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, tab, table_size, bbox.p + 8 * t, counters.p + 8 * t));
+    count_launches(1);
+    clean_size[t] = table_size;
+    filled_n[t] = 0;
+  }
+  jb.src = d_src, jb.n = n_pts, jb.stride_f = stride_bytes / 4;
+  jb.ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
+  jb.inv_cell = inv_cell;
+  jb.cells = tab, jb.mask = table_size - 1, jb.log2_size = log2_size;
+  jb.orig = orig.p, jb.sorted = sorted.p, jb.slot_of = slot_of.p, jb.rank_of = rank_of.p;
+  jb.counters = counters.p + 8 * t, jb.occ = occ.p + (size_t)t * occ_cap, jb.bbox = bbox.p + 8 * t;
+  jb.o_cells = cells.p + (size_t)o * table_cap, jb.o_occ = occ.p + (size_t)o * occ_cap;
+  jb.o_counters = counters.p + 8 * o, jb.o_bbox = bbox.p + 8 * o;
+  jb.o_cover = filled_n[o];  // 0 when the other table is already clean
+  jb.blocks = n_pts > 0 ? (n_pts + 255) / 256 : 0;
+  if (n_pts > 0 && filled_n[o] != 0) {
+    // this build's scatter launch empties the other table: from the next build on it is clean up to the size it had
+    filled_n[o] = 0;
+  } else if (filled_n[o] != 0) {
+    jb.o_cover = 0;  // no launch to piggyback on (empty cloud): the other table stays dirty and is cleared when needed
+  }
+  filled_n[t] = n_pts > 0 ? (n_pts > 8 ? n_pts : 8) : 0;
+  gen += 1;
+  return ILSM_OK;
+}
+
+static int launch_build(BuildJobs& jobs, int n_jobs, cudaStream_t s) {
+  const int b0 = jobs.j[0].blocks, b1 = n_jobs > 1 ? jobs.j[1].blocks : 0;
+  jobs.nb0 = n_jobs > 1 ? b0 : 0x7fffffff;  // a single job owns every block
+  if (b0 + b1 == 0) return ILSM_OK;
+  if (n_jobs > 1 && b0 == 0) {  // only the second map has points: make it the only job
+    jobs.j[0] = jobs.j[1];
+    jobs.nb0 = 0x7fffffff;
+  }
+  ILSM_CUDA(launch_pdl(grid_count_kernel, dim3(b0 + b1), dim3(256), 0, s, jobs));
+  ILSM_CUDA(launch_pdl(grid_alloc_kernel, dim3(b0 + b1), dim3(256), 0, s, jobs));
+  ILSM_CUDA(launch_pdl(grid_scatter_kernel, dim3(b0 + b1), dim3(256), 0, s, jobs));
+  count_launches(3);
+  return ILSM_OK;
+}
+
+int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size) {
   cudaStream_t s = stream;
   // order this (re)build after everything already enqueued on the context stream (previous users of the map,
   // producers of d_src), then run it on the map's own stream
   ILSM_CUDA(cudaEventRecord(ctx_done, ctx->stream));
   ILSM_CUDA(cudaStreamWaitEvent(s, ctx_done, 0));
-  n = n_pts;
-  cell = cell_size;
-  inv_cell = 1.0f / cell_size;
-  int want_log2 = ilog2_ceil((uint32_t)(n_pts > 0 ? 2u * (uint32_t)n_pts : 2u));
-  if (want_log2 < 10) want_log2 = 10;
-  uint32_t want_size = 1u << want_log2;
-  const GridCell* cells_before = cells.p;
-  const uint32_t *occ_before = occ.p, *counters_before = counters.p;  // a reallocated list / counter loses the last build's record
-  int rc;
-  if ((rc = cells.reserve(want_size)) || (rc = sorted.reserve(n_pts + 1)) || (rc = orig.reserve(n_pts + 1)) ||
-      (rc = slot_of.reserve(n_pts + 1)) || (rc = rank_of.reserve(n_pts + 1)) || (rc = bbox.reserve(8)) ||
-      (rc = counters.reserve(8)) || (rc = occ.reserve(n_pts + 1)))
-    return rc;
-  log2_size = want_log2;
-  table_size = want_size;
-  const int T = 256;
-  // Invariant: every slot of cells[0, clean_size) is EMPTY except the ones listed in occ[0, n_occ(previous build)).
-  // A build therefore only has to clear that list -- unless the table is new, or grew beyond the clean prefix.
-  const bool full_clear = gen == 0 || cells.p != cells_before || occ.p != occ_before || counters.p != counters_before ||
-                          (size_t)table_size > clean_size;
-  if (full_clear) {
-    ILSM_CUDA(launch_pdl(grid_clear_kernel, dim3((table_size + T - 1) / T), dim3(T), 0, s, cells.p, table_size, bbox.p, counters.p));
-    clean_size = table_size;
-  } else {
-    const int cover = prev_n > 8 ? prev_n : 8;  // the previous build's point count bounds its occupied-voxel count
-    ILSM_CUDA(launch_pdl(grid_clear_sparse_kernel, dim3((cover + T - 1) / T), dim3(T), 0, s, cells.p, (const uint32_t*)occ.p, bbox.p,
-                         counters.p, gen));
-  }
-  if (n_pts > 0) {
-    const int ioff = stride_bytes >= 32 ? 4 : (stride_bytes >= 16 ? 3 : -1);
-    ILSM_CUDA(launch_pdl(grid_count_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, d_src, n_pts, stride_bytes / 4, ioff, inv_cell,
-                         cells.p, table_size - 1, log2_size, orig.p, slot_of.p, rank_of.p, counters.p, occ.p, gen));
-    ILSM_CUDA(launch_pdl(grid_alloc_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, cells.p, (const uint32_t*)occ.p, counters.p, bbox.p,
-                         gen));
-    ILSM_CUDA(launch_pdl(grid_scatter_kernel, dim3((n_pts + T - 1) / T), dim3(T), 0, s, (const float4*)orig.p, n_pts,
-                         (const GridCell*)cells.p, (const uint32_t*)slot_of.p, (const uint32_t*)rank_of.p, sorted.p));
-  }
-  prev_n = n_pts;
-  gen += 1;
-  count_launches(n_pts > 0 ? 4 : 1);
+  if (pending) ILSM_CUDA(cudaStreamWaitEvent(s, ready, 0));  // the previous build may have run on a partner map's stream (pair build)
+  BuildJobs jobs = {};
+  int rc = prepare_build(d_src, n_pts, stride_bytes, cell_size, s, &jobs.j[0]);
+  if (rc) return rc;
+  if ((rc = launch_build(jobs, 1, s))) return rc;
   ILSM_CUDA(cudaEventRecord(ready, s));
   pending = true;
   return check_launch("map_build");
 }
 
+// The two search structures of a frame (kdtreeCornerFromMap / kdtreeSurfFromMap, laserMapping.cpp:631-634) in ONE set of
+// three launches on map a's stream.
+int build_pair_dev(Map* a, const float* d_a, int na, Map* b, const float* d_b, int nb, int stride_bytes, float cell_size) {
+  if (!a || !b || a == b || a->ctx != b->ctx) return fail(ILSM_ERR_INVALID_ARG, "map_build_pair: two maps of one context expected");
+  Ctx* ctx = a->ctx;
+  cudaStream_t s = a->stream;
+  ILSM_CUDA(cudaEventRecord(a->ctx_done, ctx->stream));
+  ILSM_CUDA(cudaStreamWaitEvent(s, a->ctx_done, 0));
+  if (a->pending) ILSM_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // earlier builds may have run on another stream
+  if (b->pending) ILSM_CUDA(cudaStreamWaitEvent(s, b->ready, 0));
+  BuildJobs jobs = {};
+  int rc;
+  if ((rc = a->prepare_build(d_a, na, stride_bytes, cell_size, s, &jobs.j[0])) || (rc = b->prepare_build(d_b, nb, stride_bytes, cell_size, s, &jobs.j[1])))
+    return rc;
+  if ((rc = launch_build(jobs, 2, s))) return rc;
+  ILSM_CUDA(cudaEventRecord(a->ready, s));
+  ILSM_CUDA(cudaEventRecord(b->ready, s));
+  a->pending = b->pending = true;
+  return check_launch("map_build_pair");
+}
+
 GridView Map::view() const {
   GridView g;
-  g.cells = cells.p;
+  g.cells = cells.p + (size_t)cur * table_cap;
   g.sorted = sorted.p;
   g.orig = orig.p;
-  g.bbox = bbox.p;
+  g.bbox = bbox.p + 8 * cur;
   g.mask = table_size - 1;
   g.log2_size = log2_size;
   g.cell = cell;

@@ -419,8 +419,8 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   q_odom[0] = s.q_w_curr.x, q_odom[1] = s.q_w_curr.y, q_odom[2] = s.q_w_curr.z, q_odom[3] = s.q_w_curr.w;
   for (int i = 0; i < 3; ++i) t_odom[i] = s.t_w_curr[i];
   // laserCloudCornerLast = cornerPointsLessSharp, laserCloudSurfLast = surfPointsLessFlat; rebuild both trees (:793-808)
-  if ((rc = s.last_corner.build_dev(reinterpret_cast<const float*>(d_lsharp), n_lsharp, 16, kOdomCell)) ||
-      (rc = s.last_surf.build_dev(reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
+  if ((rc = build_pair_dev(&s.last_corner, reinterpret_cast<const float*>(d_lsharp), n_lsharp, &s.last_surf,
+                           reinterpret_cast<const float*>(c.fe.lflat.p), n_lflat, 16, kOdomCell)))
     return rc;
   // ---- mapping (mapping_skip_frame = 1: every frame is published, laserOdometry.cpp:810-833)
   if (s.async) {

@@ -466,3 +466,44 @@ def test_knn_binned_path_equals_per_query_path(ilsm, ctx, oracle_mod, cfg_small,
     f50 = np.isfinite(q[:50]).all(axis=1)
     assert (ti[f50][:, kk:] == -1).all() and (ti[f50][:, :kk] >= 0).all()
     bm.close(), pm.close(), tiny.close(), bctx.close()
+
+
+def test_map_rebuilds_alternate_tables_and_pair_build(ctx, oracle_mod, ilsm, cfg_small):
+    """The map alternates between two hash tables (each build's scatter launch empties the other one): a sequence of
+    rebuilds with growing, shrinking, empty and regrown clouds on ONE handle must answer every query set exactly, and
+    the pair build (both structures of a frame in one set of launches) must equal two single builds."""
+    import torch
+    rng = np.random.default_rng(77)
+    base = cfg_small["map_surf"][:, :3]
+    m = ctx.new_map()
+    for n in (3000, 17000, 500, 0, 9000, 9000, 40, 17000, 2500):
+        pts = (base[rng.choice(len(base), n, replace=False)] + rng.normal(0, 0.02, (n, 3))).astype(np.float32) if n else np.zeros((0, 3), np.float32)
+        m.set_input_cloud(pts)
+        q = (base[rng.integers(0, len(base), 300)] + rng.normal(0, 0.4, (300, 3))).astype(np.float32)
+        idx, d2 = m.nearest_k_search(q, 5)
+        if n == 0:
+            assert (idx == -1).all()
+            continue
+        ri, rd = oracle_mod.knn_kdtree(pts, q, 5)
+        assert np.array_equal(idx, ri) and np.array_equal(d2, rd), n
+    m.close()
+    # pair build on device-resident clouds, repeated (the tables alternate), against single builds
+    dev = torch.device("cuda:0")
+    a, b = ctx.new_map(), ctx.new_map()
+    sa, sb = ctx.new_map(), ctx.new_map()
+    for rep, (na, nb) in enumerate(((4000, 12000), (12000, 300), (0, 5000), (7000, 0), (6000, 6000))):
+        pa = np.zeros((na, 4), np.float32)
+        pb = np.zeros((nb, 4), np.float32)
+        pa[:, :3] = cfg_small["map_corner"][rng.choice(len(cfg_small["map_corner"]), na, replace=na > len(cfg_small["map_corner"]))][:, :3]
+        pb[:, :3] = base[rng.choice(len(base), nb, replace=False)]
+        da, db = torch.from_numpy(pa).to(dev), torch.from_numpy(pb).to(dev)
+        a.build_pair_dev(da.data_ptr(), na, b, db.data_ptr(), nb, 16)
+        ctx.sync()
+        sa.set_input_cloud(pa), sb.set_input_cloud(pb)
+        q = (base[rng.integers(0, len(base), 400)] + rng.normal(0, 0.5, (400, 3))).astype(np.float32)
+        for pm, sm_ in ((a, sa), (b, sb)):
+            i1, d1 = pm.nearest_k_search(q, 5)
+            i2, d2_ = sm_.nearest_k_search(q, 5)
+            assert np.array_equal(i1, i2) and np.array_equal(d1, d2_), rep
+    for x in (a, b, sa, sb):
+        x.close()
