@@ -56,7 +56,19 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
     QWork w{cx, cy, cz, (start << 5) | (cnt - 1)};
     work[base] = w;
   }
-  unsigned big = __ballot_sync(0xffffffffu, nch > 1);
+  // voxels with several chunks: medium ones are written out by their warp, huge ones (thousands of queries in one voxel:
+  // the no-return rays) are handed to the whole block through shared memory
+  __shared__ uint32_t s_big[8][4];
+  __shared__ int s_bigc[8][3];
+  __shared__ int s_nbig;
+  if (threadIdx.x == 0) s_nbig = 0;
+  __syncthreads();
+  const bool huge = nch > 64;
+  if (huge) {
+    const int k = atomicAdd(&s_nbig, 1);
+    if (k < 8) s_big[k][0] = base, s_big[k][1] = cnt, s_big[k][2] = start, s_bigc[k][0] = cx, s_bigc[k][1] = cy, s_bigc[k][2] = cz;
+  }
+  unsigned big = __ballot_sync(0xffffffffu, nch > 1 && !huge);
   while (big) {
     const int src = __ffs(big) - 1;
     big &= big - 1;
@@ -68,6 +80,27 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
       QWork w{x, y, z, ((s + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
       work[b + k] = w;
     }
+  }
+  __syncthreads();
+  const int nbig = s_nbig < 8 ? s_nbig : 8;
+  for (int h = 0; h < nbig; ++h) {
+    const uint32_t b = s_big[h][0], c = s_big[h][1], s = s_big[h][2];
+    const uint32_t n = (c + 31) / 32;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const uint32_t left = c - 32 * k;
+      QWork w{s_bigc[h][0], s_bigc[h][1], s_bigc[h][2], ((s + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
+      work[b + k] = w;
+    }
+  }
+  if (huge && s_nbig > 8) {  // more than 8 huge voxels in one block (not seen in practice): their own thread writes them
+    bool mine_listed = false;
+    for (int h = 0; h < 8; ++h) mine_listed = mine_listed || (s_big[h][0] == base);
+    if (!mine_listed)
+      for (uint32_t k = 0; k < nch; ++k) {
+        const uint32_t left = cnt - 32 * k;
+        QWork w{cx, cy, cz, ((start + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
+        work[base + k] = w;
+      }
   }
 }
 
@@ -104,7 +137,17 @@ __global__ void __launch_bounds__(128)
   for (uint32_t wi = blockIdx.x * 4 + warp; wi < n_work; wi += nwarps) {
     const QWork w = work[wi];
     const int cx = w.cx, cy = w.cy, cz = w.cz;
-    const uint32_t q0 = w.pack >> 5, cnt = (w.pack & 31u) + 1u;
+    const uint32_t q0 = w.pack >> 5, cnt_raw = (w.pack & 31u) + 1u;
+    // A group whose queries are all the same point (the no-return rays of a LiDAR frame all map to the sensor origin:
+    // half of an OS0-64 frame) is ONE query: it is searched once, split over the whole warp, and the result is written
+    // to every member -- instead of 32 lanes scanning the same candidates for the same answer.
+    bool same_pt = false;
+    if (cnt_raw > 1) {
+      const float4 mine = __ldg(qsorted + q0 + (lane < cnt_raw ? lane : 0u));
+      const float4 first = __ldg(qsorted + q0);
+      same_pt = __all_sync(0xffffffffu, mine.x == first.x && mine.y == first.y && mine.z == first.z);
+    }
+    const uint32_t cnt = same_pt ? 1u : cnt_raw;
     // lanes = (query, slice): nqp = pow2 >= cnt queries side by side, S = 32 / nqp slices of the candidate tile each
     const uint32_t nqp = cnt <= 1 ? 1u : 1u << (32 - __clz(cnt - 1));
     const uint32_t S = 32u / nqp;
@@ -224,7 +267,20 @@ __global__ void __launch_bounds__(128)
         best.clear();  // slice 0 carries the merged list forward
       }
     }
-    if (valid && slice == 0) {
+    if (same_pt) {
+      // after the merge every lane holds the list (S = 32 -> REDUX merge leaves it in all lanes): lane l writes member l
+      if (lane < cnt_raw) {
+        const size_t o = (size_t)__float_as_uint(__ldg(qsorted + q0 + lane).w) * k_out;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (k < k_out) {
+            const bool have = best.key[k] != kSentinel;
+            idx[o + k] = have ? cand_idx(best.key[k]) : -1;
+            d2[o + k] = have ? cand_d2(best.key[k]) : __int_as_float(0x7f800000);
+          }
+        }
+      }
+    } else if (valid && slice == 0) {
       const size_t o = (size_t)__float_as_uint(qv.w) * k_out;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
