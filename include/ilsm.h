@@ -588,6 +588,15 @@ ILSM_API int ilsm_sc_query_topk_batch(ilsm_sc* sc, const float* desc_20x60, int 
 ILSM_API int ilsm_sc_query_topk_batch_dev(ilsm_sc* sc, const float* d_desc_20x60, int n_queries, int n_search, int id_offset, int k,
                                           void* d_packed);
 
+/* Large shards (>= 4096 entries) are scored in two steps: an approximate distance of every (query, entry) pair on the
+ * tensor cores (f16 operands, fp32 accumulation, 8 queries per staged entry), then the exact fp64 scorer on the entries
+ * whose approximate distance is within a proven error bound of the k-th best (and on every pair whose sector-key
+ * alignment the approximation could not decide).  The reported top-k is the one an exact scan of every entry gives.
+ * ilsm_sc_prefilter_debug exposes the first step for tests: approx[q * n_search + c] (-1 = pair flagged for exact
+ * rescoring) and the aligned shift it used; n_queries <= 8. */
+ILSM_API int ilsm_sc_prefilter_debug(ilsm_sc* sc, const float* desc_20x60, int n_queries, int n_search, float* approx,
+                                     uint8_t* aligned_shift);
+
 /* The keyframe database sharded over n_ranks processes (one per GPU), contiguous id ranges: every rank holds its
  * shard in its own ilsm_sc and the ranks share an NCCL communicator.  ilsm_sc_init_nccl adopts a communicator the
  * host already owns (ncclComm_t passed as void*; it is not destroyed with the handle); ilsm_sc_nccl_unique_id +

@@ -152,6 +152,7 @@ def load_library(path: str | None = None):
         "ilsm_sc_query_candidates": (i32, [vp, vp, i32, i32, vp, vp, vp, vp]),
         "ilsm_sc_query_topk_batch": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "ilsm_sc_query_topk_batch_dev": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "ilsm_sc_prefilter_debug": (i32, [vp, vp, i32, i32, vp, vp]),
         "ilsm_sc_nccl_unique_id": (i32, [vp]),
         "ilsm_sc_init_nccl_rank": (i32, [vp, vp, i32, i32]),
         "ilsm_sc_init_nccl": (i32, [vp, vp, i32, i32]),
@@ -606,6 +607,15 @@ class ScanContextDb:
         dist, ids, sh = np.zeros((B, k)), np.zeros((B, k), np.int32), np.zeros((B, k), np.int32)
         _check(self._lib.ilsm_sc_query_topk_batch(self._h, _ptr(q), B, n_search, id_offset, k, _ptr(dist), _ptr(ids), _ptr(sh)))
         return dist, ids, sh
+
+    def prefilter_debug(self, descs, n_search=-1):
+        """The tensor-core prefilter alone: (approximate distances (B, n), aligned shifts (B, n)); -1 = flagged pair."""
+        q = np.ascontiguousarray(descs, np.float32).reshape(-1, 1200)
+        n = len(self) if n_search < 0 else n_search
+        D = np.zeros((len(q), n), np.float32)
+        S = np.zeros((len(q), n), np.uint8)
+        _check(self._lib.ilsm_sc_prefilter_debug(self._h, _ptr(q), len(q), n, _ptr(D), _ptr(S)))
+        return D, S
 
     @staticmethod
     def nccl_unique_id() -> bytes:

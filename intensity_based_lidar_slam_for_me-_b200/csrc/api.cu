@@ -830,6 +830,7 @@ ILSM_API void ilsm_sc_destroy(ilsm_sc* sc) {
     d.out_id.release(), d.out_shift.release(), d.stage.release();
     d.ringkey.release(), d.rk_part.release(), d.cand_out.release(), d.pk_local.release(), d.pk_all.release(), d.pk_out.release();
     d.qbatch.release();
+    d.pf_query.release(), d.pf_dist.release(), d.pf_thr.release(), d.pf_part.release(), d.pf_list.release(), d.pf_list_n.release();
     sc_nccl_release(d);
   }
   delete sc;

@@ -285,6 +285,13 @@ struct ScDb {
   DevBuf<float> qbatch;
   int append_dev(const float* desc, int n_add, bool from_host);
   int query_batch_dev(const float* d_qdesc, int B, int n_search, int id_offset, int k, unsigned char* d_packed);
+  // tensor-core prefilter + exact rescoring (scancontext_tc.cu); shards smaller than tc_min keep the plain exact scan
+  int tc_min = 4096;
+  DevBuf<unsigned char> pf_query;   // PfQuery records of the batch in flight
+  DevBuf<float> pf_dist, pf_thr;    // approximate distances [8][n], thresholds [8]
+  DevBuf<u64> pf_part, pf_list;     // selection scratch, rescoring lists [8][n]
+  DevBuf<int> pf_list_n;
+  int query_batch_tc_dev(const float* d_qdesc, int B, int n_search, int id_offset, int k, unsigned char* d_packed, unsigned char* d_shift_dbg);
   int candidates_dev(const float* d_qdesc, int n_search, int num_cand, int* d_id, float* d_key_d2, double* d_dist, int* d_shift);
   int make_dev(const float* d_pts, int n, int stride_bytes, float* d_desc);
   int query_dev(const float* d_qdesc, int n_search, int id_offset, int k, double* d_dist, int* d_id, int* d_shift);

@@ -76,6 +76,8 @@ __global__ void sc_make_finish_kernel(const int* bins, float* desc) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void sc_query_prep_kernel(const float* __restrict__ qdesc, ScQuery* q) {
   pdl_entry();
+  qdesc += (size_t)blockIdx.x * kDesc;  // one block per query of a batch
+  q += blockIdx.x;
   const int c = threadIdx.x;
   for (int i = threadIdx.x; i < kDesc; i += blockDim.x) q->desc[i] = (double)qdesc[i];
   if (c < kNS) {
@@ -121,12 +123,23 @@ __device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { re
 // kList: score only the entries named by cand_keys[0, n) (low word = database index; ~0 = none) and write each one's
 // (distance, shift) to list_dist / list_shift in list order -- the candidate loop of detectLoopClosureID
 // (Scancontext.cpp:299-312) over the ring-key candidates -- instead of keeping a top-k over the whole database.
-template <bool kList>
+// kMode 2 (indirect): the entries come from a per-query list as well (cand_keys[0, *n_ptr), built by the tensor-core
+// prefilter, scancontext_tc.cu) but the block keeps a top-k like the full scan.  blockIdx.y = query of the batch: the
+// query record, the list (list_stride entries apart) and the per-block outputs are offset by it.
+template <int kMode>
 __global__ void __launch_bounds__(kScWarps * 32, 3)
     sc_score_kernel(const float* __restrict__ db, int n, const ScQuery* __restrict__ q, int k, u64* __restrict__ part_d,
                     int* __restrict__ part_id, int* __restrict__ part_sh, const u64* __restrict__ cand_keys,
-                    double* __restrict__ list_dist, int* __restrict__ list_shift) {
+                    double* __restrict__ list_dist, int* __restrict__ list_shift, const int* __restrict__ n_ptr, int list_stride) {
   pdl_entry();
+  constexpr bool kList = kMode == 1;
+  if (kMode == 2) {
+    const int y = blockIdx.y;
+    q += y;
+    cand_keys += (size_t)y * list_stride;
+    n = min(n_ptr[y], list_stride);
+    part_d += (size_t)y * gridDim.x * k, part_id += (size_t)y * gridDim.x * k, part_sh += (size_t)y * gridDim.x * k;
+  }
   extern __shared__ __align__(16) unsigned char sc_smem_raw[];
   ScBlockSmem& sm = *reinterpret_cast<ScBlockSmem*>(sc_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -138,6 +151,7 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
   const int nwarps = gridDim.x * kScWarps;
   for (int item = blockIdx.x * kScWarps + warp; item < n; item += nwarps) {
     int cand = item;
+    if (kMode == 2) cand = (int)(uint32_t)cand_keys[item];
     if (kList) {
       const u64 ck = cand_keys[item];
       if (ck == ~0ull) {  // fewer database entries than candidates asked for
@@ -431,8 +445,14 @@ __global__ void sc_list_unpack_kernel(const u64* __restrict__ sel, int k, int* _
 constexpr int kFinalThreads = 1024, kFinalPer = 8;
 __global__ void __launch_bounds__(kFinalThreads)
     sc_topk_final_kernel(const u64* __restrict__ part_d, const int* __restrict__ part_id, const int* __restrict__ part_sh, int n,
-                         int id_offset, int k, double* __restrict__ o_dist, int* __restrict__ o_id, int* __restrict__ o_shift) {
+                         int id_offset, int k, double* __restrict__ o_dist, int* __restrict__ o_id, int* __restrict__ o_shift,
+                         unsigned char* __restrict__ o_packed) {
   pdl_entry();
+  if (o_packed) {  // batched: block b merges query b's n entries into record b of the packed output (16 k bytes each)
+    part_d += (size_t)blockIdx.x * n, part_id += (size_t)blockIdx.x * n, part_sh += (size_t)blockIdx.x * n;
+    unsigned char* rec = o_packed + (size_t)blockIdx.x * 16 * k;
+    o_dist = reinterpret_cast<double*>(rec), o_id = reinterpret_cast<int*>(rec + (size_t)8 * k), o_shift = reinterpret_cast<int*>(rec + (size_t)12 * k);
+  }
   __shared__ u64 s_d[32];
   __shared__ int s_id[32], s_sh[32];
   __shared__ int s_win;
@@ -610,18 +630,45 @@ int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, do
       (rc = part_id.reserve((size_t)blocks * kTopKMax)) || (rc = part_sh.reserve((size_t)blocks * kTopKMax)))
     return rc;
   cudaStream_t s = ctx->stream;
-  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
   ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(1), dim3(64), 0, s, d_qdesc, query.p));
-  ILSM_CUDA(launch_pdl(sc_score_kernel<false>, dim3((unsigned)blocks), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, (const float*)db.p, n_search,
-                       (const ScQuery*)query.p, k, part_d.p, part_id.p, part_sh.p, (const u64*)nullptr, (double*)nullptr, (int*)nullptr));
-  ILSM_CUDA(launch_pdl(sc_topk_final_kernel, dim3(1), dim3(kFinalThreads), 0, s, part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id, d_shift));
+  ILSM_CUDA(launch_pdl(sc_score_kernel<0>, dim3((unsigned)blocks), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, (const float*)db.p, n_search,
+                       (const ScQuery*)query.p, k, part_d.p, part_id.p, part_sh.p, (const u64*)nullptr, (double*)nullptr, (int*)nullptr,
+                       (const int*)nullptr, 0));
+  ILSM_CUDA(launch_pdl(sc_topk_final_kernel, dim3(1), dim3(kFinalThreads), 0, s, part_d.p, part_id.p, part_sh.p, (int)(blocks * k), id_offset, k, d_dist, d_id, d_shift,
+                       (unsigned char*)nullptr));
   count_launches(3);
   return check_launch("sc_query");
 }
 
 // B queries against the shard, one after the other on the stream (the scoring kernel already fills the GPU for one
 // query); record b of d_packed receives query b's top-k in the packed layout (k x f64 | k x i32 | k x i32).
+// Exact scoring of per-query candidate lists (built by the prefilter): B queries, lists list_cap entries apart, lengths
+// on the device; writes B packed top-k records.
+int sc_score_lists_dev(ScDb* d, const float* d_qdesc, int B, int k, const u64* d_lists, const int* d_list_n, int list_cap, int id_offset,
+                       int n_search, unsigned char* d_packed) {
+  Ctx* ctx = d->ctx;
+  // lists are short (tens to hundreds of entries): a few blocks per query
+  const int blocks = 16;
+  int rc;
+  if ((rc = d->query.reserve(B)) || (rc = d->part_d.reserve((size_t)B * blocks * kTopKMax)) || (rc = d->part_id.reserve((size_t)B * blocks * kTopKMax)) ||
+      (rc = d->part_sh.reserve((size_t)B * blocks * kTopKMax)))
+    return rc;
+  cudaStream_t s = ctx->stream;
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
+  ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(B), dim3(64), 0, s, d_qdesc, d->query.p));
+  ILSM_CUDA(launch_pdl(sc_score_kernel<2>, dim3(blocks, B), dim3(kScWarps * 32), sizeof(ScBlockSmem), s, (const float*)d->db.p, 0,
+                       (const ScQuery*)d->query.p, k, d->part_d.p, d->part_id.p, d->part_sh.p, d_lists, (double*)nullptr, (int*)nullptr, d_list_n,
+                       list_cap));
+  ILSM_CUDA(launch_pdl(sc_topk_final_kernel, dim3(B), dim3(kFinalThreads), 0, s, (const u64*)d->part_d.p, (const int*)d->part_id.p,
+                       (const int*)d->part_sh.p, blocks * k, id_offset, k, (double*)nullptr, (int*)nullptr, (int*)nullptr, d_packed));
+  count_launches(3);
+  return check_launch("sc_score_lists");
+}
+
 int ScDb::query_batch_dev(const float* d_qdesc, int B, int n_search, int id_offset, int k, unsigned char* d_packed) {
+  // large shards: approximate scoring of every pair on the tensor cores, exact rescoring of the few that can matter
+  if (n_search >= tc_min) return query_batch_tc_dev(d_qdesc, B, n_search, id_offset, k, d_packed, nullptr);
   for (int b = 0; b < B; ++b) {
     unsigned char* base = d_packed + (size_t)b * 16 * k;
     int rc = query_dev(d_qdesc + (size_t)b * kDesc, n_search, id_offset, k, reinterpret_cast<double*>(base),
@@ -646,11 +693,11 @@ int ScDb::candidates_dev(const float* d_qdesc, int n_search, int num_cand, int* 
   ILSM_CUDA(launch_pdl(sc_ringkey_select_kernel, dim3(blocks), dim3(1024), 0, s, (const float*)ringkey.p, n_search, d_qdesc, num_cand, rk_part.p));
   ILSM_CUDA(launch_pdl(sc_ringkey_final_kernel, dim3(1), dim3(1024), 0, s, (const u64*)rk_part.p, blocks * num_cand, num_cand, sel));
   ILSM_CUDA(launch_pdl(sc_list_unpack_kernel, dim3(1), dim3(32), 0, s, (const u64*)sel, num_cand, d_id, d_key_d2));
-  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
+  ILSM_CUDA(cudaFuncSetAttribute(sc_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScBlockSmem)));
   ILSM_CUDA(launch_pdl(sc_query_prep_kernel, dim3(1), dim3(64), 0, s, d_qdesc, query.p));
-  ILSM_CUDA(launch_pdl(sc_score_kernel<true>, dim3((num_cand + kScWarps - 1) / kScWarps), dim3(kScWarps * 32), sizeof(ScBlockSmem), s,
+  ILSM_CUDA(launch_pdl(sc_score_kernel<1>, dim3((num_cand + kScWarps - 1) / kScWarps), dim3(kScWarps * 32), sizeof(ScBlockSmem), s,
                        (const float*)db.p, num_cand, (const ScQuery*)query.p, num_cand, (u64*)nullptr, (int*)nullptr, (int*)nullptr, (const u64*)sel,
-                       d_dist, d_shift));
+                       d_dist, d_shift, (const int*)nullptr, 0));
   count_launches(5);
   return check_launch("sc_candidates");
 }

@@ -153,6 +153,33 @@ ILSM_API int ilsm_sc_query_topk_batch_dev(ilsm_sc* sc, const float* d_desc_20x60
   return sc->d.query_batch_dev(d_desc_20x60, n_queries, n_search, id_offset, k, reinterpret_cast<unsigned char*>(d_packed));
 }
 
+// Testing aid: the tensor-core prefilter alone.  approx[q * n_search + c] = approximate distance (-1: pair flagged for
+// exact rescoring), aligned_shift likewise (the sector-key alignment it used).  n_queries <= 8.
+ILSM_API int ilsm_sc_prefilter_debug(ilsm_sc* sc, const float* desc_20x60, int n_queries, int n_search, float* approx,
+                                     uint8_t* aligned_shift) {
+  if (!sc || !desc_20x60 || !approx || !aligned_shift || n_queries < 1 || n_queries > 8) return fail(ILSM_ERR_INVALID_ARG, "sc_prefilter_debug: bad argument");
+  ScDb& d = sc->d;
+  Ctx& c = *d.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (n_search < 0) n_search = d.count;
+  if (n_search < 1 || n_search > d.count) return fail(ILSM_ERR_INVALID_ARG, "sc_prefilter_debug: bad n_search");
+  int rc;
+  DevBuf<unsigned char> sh;
+  if ((rc = d.qbatch.reserve((size_t)n_queries * 1200 + 8)) || (rc = d.pk_out.reserve((size_t)n_queries * 16 * 10 + 64)) ||
+      (rc = sh.reserve((size_t)8 * n_search + 16)))
+    return rc;
+  ILSM_CUDA(cudaMemcpyAsync(d.qbatch.p, desc_20x60, (size_t)n_queries * 1200 * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  rc = d.query_batch_tc_dev(d.qbatch.p, n_queries, n_search, 0, 10, d.pk_out.p, sh.p);
+  if (!rc) {
+    ILSM_CUDA(cudaMemcpyAsync(approx, d.pf_dist.p, (size_t)n_queries * n_search * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaMemcpyAsync(aligned_shift, sh.p, (size_t)n_queries * n_search, cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  sh.release();
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------- sharded database (NCCL)
 ILSM_API int ilsm_sc_nccl_unique_id(char id_out[128]) {
   if (!id_out) return fail(ILSM_ERR_INVALID_ARG, "sc_nccl_unique_id: null argument");

@@ -222,3 +222,74 @@ def test_gpu_sc_batch_equals_single_queries(ctx, ilsm):
     sd, si, ss = sc.query_topk_sharded(q, k=10, n_search=1400, id_offset=5)
     assert np.array_equal(sd, bd) and np.array_equal(si, bi) and np.array_equal(ss, bs)
     sc.close()
+
+
+def _edge_case_db(ilsm, n, seed):
+    db = ilsm.synth.sc_database(n, seed=seed)
+    db[17] = 0.0                      # an all-empty descriptor: no effective column
+    db[18, :, 10:20] = 0.0            # partially empty columns
+    db[19] = db[3]                    # exact duplicates of other entries
+    db[20] = np.roll(db[3], 7, axis=1)
+    db[21, :, :] = db[21, :, :1]      # every column identical: the sector-key alignment is a 60-way tie
+    return db
+
+
+@pytest.mark.gpu
+def test_gpu_sc_prefilter_approximates_exact(ctx, oracle_mod, ilsm):
+    """The tensor-core prefilter (scancontext_tc.cu) against the exact scorer, pair by pair: an unflagged pair must carry
+    the exact aligned shift (fastAlignUsingVkey) and a distance within the stated bound of distanceBtnScanContext's."""
+    db = _edge_case_db(ilsm, 1500, 31)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 8, seed=32)
+    q[7] = db[21]                     # a query whose own alignment is ambiguous against everything
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db)
+    D, S = sc.prefilter_debug(q)
+    dbd, qd = db.astype(np.float64), q.astype(np.float64)
+    keys = dbd.mean(axis=1)           # sector keys: column means (Scancontext.cpp:222-235)
+    flagged = D < 0
+    assert flagged[:7].mean() < 0.05, flagged.mean()
+    worst = 0.0
+    for j in range(8):
+        qk = qd[j].mean(axis=0)
+        for c in range(0, len(db), 3):
+            if flagged[j, c]:
+                continue
+            norms = [np.linalg.norm(qk - np.roll(keys[c], s)) for s in range(60)]
+            assert int(np.argmin(norms)) == int(S[j, c]), (j, c)
+            wd, _ = oracle_mod.sc_distance(qd[j], dbd[c])
+            if wd < 1e6:
+                worst = max(worst, abs(float(D[j, c]) - wd))
+            else:
+                assert D[j, c] > 1e6
+    assert worst <= 1.5e-3, worst
+    # degenerate pairs are flagged, not guessed: the all-equal-columns entry and query
+    assert flagged[:, 21].all() and flagged[7].all()
+    sc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [10, 1, 16])
+def test_gpu_sc_tc_batch_equals_exact_scan(ctx, oracle_mod, ilsm, k):
+    """A shard large enough for the two-step path (prefilter + exact rescoring): the reported top-k must be the one the
+    exact scan of every entry gives -- ids, shifts and distances -- including empty descriptors, duplicates (distance
+    ties resolved by id) and alignment ties."""
+    db = _edge_case_db(ilsm, 6000, 41)
+    q, ids, shifts = ilsm.synth.sc_queries(db, 11, seed=42)
+    q[9] = db[21]
+    q[10] = 0.0                       # an empty query: nothing is effective
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db)
+    bd, bi, bs = sc.query_topk_batch(q, k=k, n_search=5950, id_offset=100)
+    dbd = db[:5950].astype(np.float64)
+    for j in range(len(q)):
+        wd, wi, ws = oracle_mod.sc_topk(dbd, q[j].astype(np.float64), k)
+        assert np.array_equal(bi[j], np.where(wi >= 0, wi + 100, -1)), (j, bi[j], wi)
+        assert np.array_equal(bs[j], ws), j
+        fin = np.isfinite(wd)
+        assert np.allclose(bd[j][fin], wd[fin], rtol=1e-12, atol=1e-14), j
+    for j in range(9):
+        assert bi[j, 0] == ids[j] + 100 and bs[j, 0] == shifts[j]
+    # the single-query entry point keeps the plain exact scan: same answers
+    d1, i1, s1 = sc.query_topk(q[0], k=k, n_search=5950, id_offset=100)
+    assert np.array_equal(i1, bi[0]) and np.array_equal(s1, bs[0]) and np.array_equal(d1, bd[0])
+    sc.close()
