@@ -114,6 +114,16 @@ struct ScBlockSmem {
 };
 
 __device__ __forceinline__ bool sc_key_less(u64 da, int ia, u64 db, int ib) { return da < db || (da == db && ia < ib); }
+// Distances travel through the top-k machinery as 64-bit keys whose unsigned order is the order of the doubles --
+// INCLUDING negative ones: 1 - mean(cos) of a descriptor against itself can come out as -2e-16, and raw IEEE bits would
+// sort that last.  +inf maps below the all-ones "nothing" key.
+__device__ __forceinline__ u64 dkey(double d) {
+  const u64 b = (u64)__double_as_longlong(d);
+  return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(u64 k) {
+  return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull)));
+}
 
 // One warp per candidate keyframe, grid-stride; every warp keeps its k best (distance, id) in shared memory, the
 // block merges its warps' lists at the end and writes k entries, a small second kernel merges the blocks' lists.
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(kScWarps * 32, 3)
       // distanceBtnScanContext's result as it is (10000000 when no shift had an effective column: never < min_dist)
       if (lane == 0) list_dist[item] = bd, list_shift[item] = bs;
     } else if (lane == 0) {  // insertion into this warp's sorted top-k
-      const u64 kd = (u64)__double_as_longlong(bd);
+      const u64 kd = dkey(bd);
       if (sc_key_less(kd, cand, w.tk_d[k - 1], w.tk_id[k - 1])) {
         int pos = k - 1;
         while (pos > 0 && sc_key_less(kd, cand, w.tk_d[pos - 1], w.tk_id[pos - 1])) {
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(kFinalThreads)
       if (lane == 0) {
         s_win = wi;
         const bool have = wi != INT_MAX;
-        o_dist[round] = have ? __longlong_as_double((long long)wd) : __longlong_as_double(0x7ff0000000000000ll);
+        o_dist[round] = have ? dkey_inv(wd) : __longlong_as_double(0x7ff0000000000000ll);
         o_id[round] = have ? wi + id_offset : -1;
         o_shift[round] = have ? wsft : 0;
       }
@@ -538,7 +548,7 @@ __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int sh
       const int i = e % k;
       const int id = reinterpret_cast<const int*>(base + (size_t)8 * k)[i];
       if (id < 0) continue;
-      const u64 d = (u64)__double_as_longlong(reinterpret_cast<const double*>(base)[i]);
+      const u64 d = dkey(reinterpret_cast<const double*>(base)[i]);
       const bool above = first || d > last_d || (d == last_d && id > last_id);
       if (above && (d < bd || (d == bd && id < bid))) bd = d, bid = id, bsh = reinterpret_cast<const int*>(base + (size_t)12 * k)[i];
     }
@@ -551,7 +561,7 @@ __global__ void sc_merge_kernel(const unsigned char* __restrict__ packed, int sh
     }
     const bool have = bid != INT_MAX;
     if (lane == 0) {
-      o_dist[j] = have ? __longlong_as_double((long long)bd) : __longlong_as_double(0x7ff0000000000000ll);
+      o_dist[j] = have ? dkey_inv(bd) : __longlong_as_double(0x7ff0000000000000ll);
       o_id[j] = have ? bid : -1;
       o_shift[j] = have ? bsh : 0;
     }

@@ -290,6 +290,8 @@ def test_gpu_sc_tc_batch_equals_exact_scan(ctx, oracle_mod, ilsm, k):
     for j in range(9):
         assert bi[j, 0] == ids[j] + 100 and bs[j, 0] == shifts[j]
     # the single-query entry point keeps the plain exact scan: same answers
-    d1, i1, s1 = sc.query_topk(q[0], k=k, n_search=5950, id_offset=100)
-    assert np.array_equal(i1, bi[0]) and np.array_equal(s1, bs[0]) and np.array_equal(d1, bd[0])
+    for j in (0, 9):  # 9: the query IS an entry -- its distance to itself is a tiny NEGATIVE number and must still sort first
+        d1, i1, s1 = sc.query_topk(q[j], k=k, n_search=5950, id_offset=100)
+        assert np.array_equal(i1, bi[j]) and np.array_equal(s1, bs[j]) and np.array_equal(d1, bd[j])
+    assert bi[9, 0] == 121 and abs(bd[9, 0]) < 1e-12
     sc.close()
