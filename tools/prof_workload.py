@@ -81,6 +81,14 @@ def main():
         d_sq = torch.from_numpy(q.reshape(2, 1200)).to(dev)
         pack = torch.zeros(160, dtype=torch.uint8, device=dev)
         work.append(lambda: sc.query_packed_dev(d_sq[0].data_ptr(), 10, 20_000, 0, pack.data_ptr()))
+    if "sc8" in only:  # config 5 shape: one batch of 8 queries against a 100k-keyframe shard (prefilter + selection + exact rescoring)
+        scb = ilsm.ScanContextDb(ctx)
+        for a in range(0, 100_000, 20_000):
+            scb.add(S.sc_database_range(a, a + 20_000, 100_000))
+        q8, _, _ = S.sc_chunked_queries(100_000, 8)
+        d_q8 = torch.from_numpy(q8.reshape(8, 1200)).to(dev)
+        pack8 = torch.zeros(8 * 160, dtype=torch.uint8, device=dev)
+        work.append(lambda: scb.query_topk_sharded_dev(d_q8.data_ptr(), 8, 10, 99_950, 0, pack8.data_ptr()))
     if "fe" in only:
         c3 = S.config1(n_map=20_000)
         cloud = c3["cloud"]
