@@ -19,7 +19,11 @@
 
 namespace ilsm {
 
-struct QWork {  // one group: <= 32 queries of one voxel
+constexpr int kGroup = 8;  // queries per group: every query's candidate scan is split over >= 4 lanes (32 / kGroup slices), which keeps
+                          // one warp's serial work short -- with 32-query groups the kernel's duration was the heaviest group's scan
+                          // (ncu: 18.8 % of the warps active on average)
+
+struct QWork {  // one group: <= kGroup queries of one voxel
   int cx, cy, cz;
   uint32_t pack;  // (first query in the sorted query array) << 5 | (count - 1)
 };
@@ -40,7 +44,7 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
     cx = (int)((key >> 42) & 0x1FFFFF) - kCoordOff, cy = (int)((key >> 21) & 0x1FFFFF) - kCoordOff, cz = (int)(key & 0x1FFFFF) - kCoordOff;
     start = e.z, cnt = e.w;
   }
-  const uint32_t nch = (cnt + 31) / 32;
+  const uint32_t nch = (cnt + kGroup - 1) / kGroup;
   // warp-aggregated reservation of work slots
   uint32_t inc = nch;
 #pragma unroll
@@ -74,10 +78,10 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
     big &= big - 1;
     const uint32_t b = __shfl_sync(0xffffffffu, base, src), c = __shfl_sync(0xffffffffu, cnt, src), s = __shfl_sync(0xffffffffu, start, src);
     const int x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src), z = __shfl_sync(0xffffffffu, cz, src);
-    const uint32_t n = (c + 31) / 32;
+    const uint32_t n = (c + kGroup - 1) / kGroup;
     for (uint32_t k = lane; k < n; k += 32) {
-      const uint32_t left = c - 32 * k;
-      QWork w{x, y, z, ((s + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
+      const uint32_t left = c - kGroup * k;
+      QWork w{x, y, z, ((s + kGroup * k) << 5) | ((left < kGroup ? left : kGroup) - 1)};
       work[b + k] = w;
     }
   }
@@ -85,10 +89,10 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
   const int nbig = s_nbig < 8 ? s_nbig : 8;
   for (int h = 0; h < nbig; ++h) {
     const uint32_t b = s_big[h][0], c = s_big[h][1], s = s_big[h][2];
-    const uint32_t n = (c + 31) / 32;
+    const uint32_t n = (c + kGroup - 1) / kGroup;
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-      const uint32_t left = c - 32 * k;
-      QWork w{s_bigc[h][0], s_bigc[h][1], s_bigc[h][2], ((s + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
+      const uint32_t left = c - kGroup * k;
+      QWork w{s_bigc[h][0], s_bigc[h][1], s_bigc[h][2], ((s + kGroup * k) << 5) | ((left < kGroup ? left : kGroup) - 1)};
       work[b + k] = w;
     }
   }
@@ -97,8 +101,8 @@ __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint3
     for (int h = 0; h < 8; ++h) mine_listed = mine_listed || (s_big[h][0] == base);
     if (!mine_listed)
       for (uint32_t k = 0; k < nch; ++k) {
-        const uint32_t left = cnt - 32 * k;
-        QWork w{cx, cy, cz, ((start + 32 * k) << 5) | ((left < 32 ? left : 32) - 1)};
+        const uint32_t left = cnt - kGroup * k;
+        QWork w{cx, cy, cz, ((start + kGroup * k) << 5) | ((left < kGroup ? left : kGroup) - 1)};
         work[base + k] = w;
       }
   }
@@ -238,14 +242,21 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
           for (int k = 0; k < K; ++k) best.key[k] = res[k];
         } else {
-#pragma unroll 1
-          for (uint32_t bit = nqp; bit < 32u; bit <<= 1) {
-            u64 other[K];
+          // few slices (2 or 4): K rounds of "minimum of the slices' heads" by xor shuffles over the slice bits; the lane
+          // that owns the minimum pops it (keys are unique)
+          u64 res[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) other[k] = __shfl_xor_sync(0xffffffffu, best.key[k], bit);
-#pragma unroll
-            for (int k = 0; k < K; ++k) best.insert(other[k], 0.f, 0.f, 0.f);
+          for (int k = 0; k < K; ++k) {
+            u64 m = best.key[0];
+            for (uint32_t bit = nqp; bit < 32u; bit <<= 1) {
+              const u64 o = __shfl_xor_sync(0xffffffffu, m, bit);
+              m = o < m ? o : m;
+            }
+            res[k] = m;
+            if (best.key[0] == m && m != kSentinel) best.pop_front();
           }
+#pragma unroll
+          for (int k = 0; k < K; ++k) best.key[k] = res[k];
         }
       }
       ext = best.key[K - 1] == kSentinel ? kInf : cand_d2(best.key[K - 1]);  // (S == 1: the lane's own list is the merged one)
@@ -325,8 +336,8 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// upper bound of the number of groups: every occupied voxel contributes ceil(count / 32) <= count / 32 + 1
-static inline size_t qwork_items(int nq) { return (size_t)nq + (size_t)nq / 32 + 64; }
+// upper bound of the number of groups: every occupied voxel contributes ceil(count / kGroup) <= count / kGroup + 1
+static inline size_t qwork_items(int nq) { return (size_t)nq + (size_t)nq / kGroup + 64; }
 
 template <int K>
 static int launch_binned(Ctx* ctx, Map* m, Map* qb, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
