@@ -92,6 +92,10 @@ int Ctx::init(int dev) {
   if ((rc = pinned.reserve(4096))) return rc;
   ILSM_CUDA(cudaStreamSynchronize(stream));
   if (const char* e2 = getenv("ILSM_KNN_BINNED_MIN")) knn_binned_min = atoi(e2) > 0 ? atoi(e2) : 0x7fffffff;
+  if (const char* e3 = getenv("ILSM_KNN_GROUP")) {
+    const int gsz = atoi(e3);
+    if (gsz == 1 || gsz == 2 || gsz == 4 || gsz == 8 || gsz == 16 || gsz == 32) knn_group = gsz;
+  }
   return ILSM_OK;
 }
 

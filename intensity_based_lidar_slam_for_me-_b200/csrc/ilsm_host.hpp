@@ -228,6 +228,7 @@ struct Ctx {
   DevBuf<int> rf_stack_n;
   Map* qbin = nullptr;        // query binning of the throughput k-NN path (knn_binned.cu): the query cloud grouped by voxel
   DevBuf<int> qwork;          // its work items (4 ints each) + the item counter
+  int knn_group = 8;          // queries per group of the binned search (ILSM_KNN_GROUP: 1, 2, 4, 8, 16 or 32)
   int knn_binned_min = 8192;  // query sets at least this large take the binned path (ILSM_KNN_BINNED_MIN overrides)
   size_t partial_blocks = 0;
   bool bulk_attr_set = false;  // normal_eq_bulk_kernel's dynamic shared-memory opt-in done on this device

@@ -19,7 +19,7 @@
 
 namespace ilsm {
 
-constexpr int kGroup = 8;  // queries per group: every query's candidate scan is split over >= 4 lanes (32 / kGroup slices), which keeps
+constexpr int kGroupDefault = 8;  // queries per group (runtime parameter `gsz`, a power of two <= 32): every query's candidate scan is split over >= 4 lanes (32 / kGroup slices), which keeps
                           // one warp's serial work short -- with 32-query groups the kernel's duration was the heaviest group's scan
                           // (ncu: 18.8 % of the warps active on average)
 
@@ -31,7 +31,7 @@ struct QWork {  // one group: <= kGroup queries of one voxel
 // occupied query voxels -> work items (chunks of <= 32 queries); voxels with many queries are written out by the
 // whole warp
 __global__ void qbin_work_kernel(const GridCell* __restrict__ cells, const uint32_t* __restrict__ occ, const uint32_t* __restrict__ counters,
-                                 int occ_slot, QWork* __restrict__ work, uint32_t* __restrict__ n_work) {
+                                 int occ_slot, QWork* __restrict__ work, uint32_t* __restrict__ n_work, uint32_t kGroup) {
   pdl_entry();
   const uint32_t n_occ = counters[occ_slot];
   const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // upper bound of the number of groups: every occupied voxel contributes ceil(count / kGroup) <= count / kGroup + 1
-static inline size_t qwork_items(int nq) { return (size_t)nq + (size_t)nq / kGroup + 64; }
+static inline size_t qwork_items(int nq) { return (size_t)2 * nq + 64; }
 
 template <int K>
 static int launch_binned(Ctx* ctx, Map* m, Map* qb, const float* d_q, int nq, int stride_f, int k, float max_d2, int32_t* d_idx,
@@ -348,7 +348,7 @@ static int launch_binned(Ctx* ctx, Map* m, Map* qb, const float* d_q, int nq, in
   uint32_t* n_work = reinterpret_cast<uint32_t*>(ctx->qwork.p + (size_t)4 * qwork_items(nq));
   ILSM_CUDA(cudaMemsetAsync(n_work, 0, sizeof(uint32_t), s));
   ILSM_CUDA(launch_pdl(qbin_work_kernel, dim3((nq + 255) / 256), dim3(256), 0, s, qb->cur_cells(), qb->cur_occ(),
-                       qb->cur_counters(), occ_slot, work, n_work));
+                       qb->cur_counters(), occ_slot, work, n_work, (uint32_t)ctx->knn_group));
   // one warp per group; grid = a few resident waves, further groups are taken grid-stride
   long long blocks = ((long long)nq + 3) / 4, cap = (long long)ctx->sm_count * 16;
   if (blocks > cap) blocks = cap;

@@ -33,7 +33,6 @@ constexpr int kNR = 20, kNS = 60, kDesc = kNR * kNS;
 constexpr int kPfQ = 8;            // queries per block, one warp each
 constexpr int kPfThreads = 32 * kPfQ;
 constexpr int kChStride = 40;      // halves per staged candidate column: 80 B rows -> ldmatrix / LDS.32 conflict-free
-constexpr int kChCols = 88;        // 60 columns + the first 28 again (windows run up to column 59 + 23 without wrapping)
 constexpr float kPfEps = 1.5e-3f;  // bound of |approximate - exact| distance for an unflagged pair
 
 struct PfQuery {              // prepared once per query
@@ -95,34 +94,37 @@ __global__ void __launch_bounds__(64) sc_pf_prep_kernel(const float* __restrict_
   }
 }
 
-// top-2 of a set of (value, index) pairs: best value (lowest index on ties), and the second best value
-struct Top2 {
-  float b1, b2;
-  int arg;
-};
-__device__ __forceinline__ void top2_offer(Top2& t, float v, int i) {
-  if (v > t.b1 || (v == t.b1 && i < t.arg)) {
-    t.b2 = t.b1;
-    t.b1 = v, t.arg = i;
-  } else if (v > t.b2) {
-    t.b2 = v;
-  }
+__device__ __forceinline__ void mma_f16_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {  // D = A B
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
-__device__ __forceinline__ void top2_merge(Top2& t, float b1, float b2, int arg) {
-  top2_offer(t, b1, arg);
-  if (b2 > t.b2) t.b2 = b2;
+__device__ __forceinline__ uint32_t redux_max_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+  return r;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
 // the prefilter
 // ---------------------------------------------------------------------------------------------------
 struct PfSmem {
-  float craw[2][kDesc];                       // raw candidate descriptors, double buffered
-  __align__(16) __half ch[kChCols][kChStride];  // column-normalised candidate, [column][ring], columns 60.. repeat 0..
-  __half ckh[128], ckl[128];                  // candidate sector key hi / lo at index x = (column - shift) + 64, periodic
-  float ck2_part[8];
-  unsigned cm_part[8];
-  float top[4][kPfQ][3];                      // alignment: per shift block (warp 0..3) and query: best, second best, arg
+  __align__(16) float craw[2][kDesc];           // raw candidate descriptors, double buffered (filled by cp.async)
+  __align__(16) __half ch[kNS][kChStride];      // column-normalised candidate, [column][ring]; rings 20..31 stay zero
+  __half ckh[128], ckl[128];                    // candidate sector key hi / lo at index x = (column - shift) + 64, periodic
+  uint32_t pkh[128], pkl[128];                  // the same as adjacent pairs (x, x + 1): one 32-bit load per A-fragment register
+  float corr[64][kPfQ];                         // alignment correlations [shift][query]
+  float ck2_part[4];
+  unsigned cm_part[4];
+  float ck2;
+  unsigned long long cmask;
 };
 
 // D[q * n + c] = approximate distance of query q and candidate c, or -1 when the pair is flagged for exact rescoring;
@@ -174,146 +176,129 @@ __global__ void __launch_bounds__(kPfThreads, 2)
   const bool upper = u >= 8;
   const int tt0 = u & 7;
 
+  // the padding rings of the staged candidate are written once
+  for (int i = tid; i < kNS * (kChStride - kNR); i += kPfThreads) sm.ch[i / (kChStride - kNR)][kNR + i % (kChStride - kNR)] = __float2half(0.f);
+  // first candidate of this block (4800 B = 300 x 16 B)
+  if ((int)blockIdx.x < n)
+    for (int i = tid; i < kDesc / 4; i += kPfThreads) cp_async16(&sm.craw[0][4 * i], db + (size_t)blockIdx.x * kDesc + 4 * i);
   int cur = 0;
-  // first candidate of this block
-  {
-    const int c = blockIdx.x;
-    if (c < n)
-      for (int i = tid; i < kDesc; i += kPfThreads) sm.craw[0][i] = __ldg(db + (size_t)c * kDesc + i);
-  }
 #pragma unroll 1
   for (int cand = blockIdx.x; cand < n; cand += gridDim.x) {
-    __syncthreads();  // craw[cur] complete; everybody is done with ch / keys / top of the previous candidate
-    // ---- prefetch the next candidate into registers (stored after this candidate's staging)
-    float pre[(kDesc + kPfThreads - 1) / kPfThreads];
+    cp_async_commit_wait();
+    __syncthreads();  // craw[cur] complete; everybody is done with the previous candidate's staged data
+    // ---- the next candidate streams into the other buffer while this one is processed
     const int nxt = cand + gridDim.x;
+    if (nxt < n)
+      for (int i = tid; i < kDesc / 4; i += kPfThreads) cp_async16(&sm.craw[cur ^ 1][4 * i], db + (size_t)nxt * kDesc + 4 * i);
+    // ---- stage (warps 0..3: 2 threads per column, 10 rings each): column sums, normalise, packed f16 stores; sector
+    // key hi / lo; validity mask; |key|^2
+    if (warp < 4) {
+      const int col = tid >> 1, hf = tid & 1;  // 120 threads work (col < 60)
+      float v[10], s = 0.f, ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < (kDesc + kPfThreads - 1) / kPfThreads; ++k) {
-      const int i = tid + k * kPfThreads;
-      pre[k] = (nxt < n && i < kDesc) ? __ldg(db + (size_t)nxt * kDesc + i) : 0.f;
-    }
-    // ---- stage: column sums (4 threads per column, 5 rings each), normalise, f16; sector key hi / lo; validity mask
-    {
-      const int col = tid >> 2, part = tid & 3;  // 240 threads work, 16 idle (col >= 60)
-      float v[5], s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        v[k] = col < kNS ? sm.craw[cur][(5 * part + k) * kNS + col] : 0.f;
+      for (int k = 0; k < 10; ++k) {
+        v[k] = col < kNS ? sm.craw[cur][(10 * hf + k) * kNS + col] : 0.f;
         s += v[k];
         ss = fmaf(v[k], v[k], ss);
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1), ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2), ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       const bool valid = ss > 0.f;
       const float inv = valid ? rsqrtf(ss) : 0.f;
       const float key = s / kNR;
       if (col < kNS) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.ch[col][10 * hf]);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-          const __half hv = __float2half(v[k] * inv);
-          sm.ch[col][5 * part + k] = hv;
-          if (col < kChCols - kNS) sm.ch[col + kNS][5 * part + k] = hv;
+          const __half2 h2 = __floats2half2_rn(v[2 * k] * inv, v[2 * k + 1] * inv);
+          dst[k] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        // zero padding of the unused rings 20..31 (3 per thread)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          sm.ch[col][kNR + 3 * part + k] = __float2half(0.f);
-          if (col < kChCols - kNS) sm.ch[col + kNS][kNR + 3 * part + k] = __float2half(0.f);
-        }
-        if (part == 0) {
+        if (hf == 0) {
           const __half h = __float2half(key), l = __float2half(key - __half2float(h));
-          // index x = (column - shift) + 64: x holds column (x - 64) mod 60 = (x + 56) mod 60
-#pragma unroll
-          for (int rep = 0; rep < 3; ++rep) {
-            const int x = col + 4 + 60 * rep;  // (x + 56) mod 60 == col
-            if (x < 128) sm.ckh[x] = h, sm.ckl[x] = l;
-          }
-          if (col >= 56) sm.ckh[col - 56] = h, sm.ckl[col - 56] = l;  // x = 0..3 hold columns 56..59
+          // index x = (column - shift) + 64 holds column (x + 56) mod 60
+          sm.ckh[col + 4] = h, sm.ckl[col + 4] = l;
+          sm.ckh[col + 64] = h, sm.ckl[col + 64] = l;
+          if (col < 4) sm.ckh[col + 124] = h, sm.ckl[col + 124] = l;
+          if (col >= 56) sm.ckh[col - 56] = h, sm.ckl[col - 56] = l;
         }
       }
-      const unsigned vb = __ballot_sync(0xffffffffu, valid && part == 0 && col < kNS);
-      float k2 = (part == 0 && col < kNS) ? key * key : 0.f;
+      const unsigned vb = __ballot_sync(0xffffffffu, valid && hf == 0 && col < kNS);
+      float k2 = (hf == 0 && col < kNS) ? key * key : 0.f;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) k2 += __shfl_xor_sync(0xffffffffu, k2, off);
       if (lane == 0) {
-        // lanes 0, 4, .., 28 of warp w carry columns 8 w .. 8 w + 7
-        unsigned m8 = 0;
+        unsigned m16 = 0;  // even lanes 0, 2, .., 30 of warp w carry columns 16 w .. 16 w + 15
 #pragma unroll
-        for (int k = 0; k < 8; ++k) m8 |= ((vb >> (4 * k)) & 1u) << k;
-        sm.cm_part[warp] = m8;
+        for (int k = 0; k < 16; ++k) m16 |= ((vb >> (2 * k)) & 1u) << k;
+        sm.cm_part[warp] = m16;
         sm.ck2_part[warp] = k2;
       }
-    }
-#pragma unroll
-    for (int k = 0; k < (kDesc + kPfThreads - 1) / kPfThreads; ++k) {
-      const int i = tid + k * kPfThreads;
-      if (i < kDesc) sm.craw[cur ^ 1][i] = pre[k];
-    }
-    __syncthreads();
-    // ---- alignment: warp i < 4 computes the correlations of shifts 16 i .. 16 i + 15 with all queries
-    if (warp < 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      named_barrier(1, 128);  // the four staging warps only
+      // adjacent key pairs, so that an A-fragment register of the circulant is one 32-bit load
+      if (tid < 127) {
+        sm.pkh[tid] = pack_h2(sm.ckh[tid], sm.ckh[tid + 1]);
+        sm.pkl[tid] = pack_h2(sm.ckl[tid], sm.ckl[tid + 1]);
+      }
+      if (tid == 127) {
+        sm.ck2 = (sm.ck2_part[0] + sm.ck2_part[1]) + (sm.ck2_part[2] + sm.ck2_part[3]);
+        sm.cmask = ((unsigned long long)sm.cm_part[0] | ((unsigned long long)sm.cm_part[1] << 16) | ((unsigned long long)sm.cm_part[2] << 32) |
+                    ((unsigned long long)sm.cm_part[3] << 48)) & ((1ull << kNS) - 1ull);
+      }
+      named_barrier(1, 128);
+      // ---- alignment: warp i computes the correlations of shifts 16 i .. 16 i + 15 with all queries
+      float acc[4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         // A[m][k] = ck[(column - shift) mod 60], shift = 16 warp + m, column = 16 ks + k  ->  index x = column - shift + 64
         const int x0 = 16 * ks + 2 * t - (16 * warp + g) + 64;
         uint32_t ah[4], al[4];
-        ah[0] = pack_h2(sm.ckh[x0], sm.ckh[x0 + 1]), al[0] = pack_h2(sm.ckl[x0], sm.ckl[x0 + 1]);
-        ah[1] = pack_h2(sm.ckh[x0 - 8], sm.ckh[x0 - 7]), al[1] = pack_h2(sm.ckl[x0 - 8], sm.ckl[x0 - 7]);      // shift + 8
-        ah[2] = pack_h2(sm.ckh[x0 + 8], sm.ckh[x0 + 9]), al[2] = pack_h2(sm.ckl[x0 + 8], sm.ckl[x0 + 9]);      // column + 8
-        ah[3] = pack_h2(sm.ckh[x0], sm.ckh[x0 + 1]), al[3] = pack_h2(sm.ckl[x0], sm.ckl[x0 + 1]);              // both
-        mma_f16(acc, ah, kb_h[ks][0], kb_h[ks][1]);
+        ah[0] = sm.pkh[x0], al[0] = sm.pkl[x0];
+        ah[1] = sm.pkh[x0 - 8], al[1] = sm.pkl[x0 - 8];  // shift + 8
+        ah[2] = sm.pkh[x0 + 8], al[2] = sm.pkl[x0 + 8];  // column + 8
+        ah[3] = ah[0], al[3] = al[0];                    // both
+        if (ks == 0) mma_f16_zero(acc, ah, kb_h[ks][0], kb_h[ks][1]);
+        else mma_f16(acc, ah, kb_h[ks][0], kb_h[ks][1]);
         mma_f16(acc, ah, kb_l[ks][0], kb_l[ks][1]);
         mma_f16(acc, al, kb_h[ks][0], kb_h[ks][1]);
       }
       // acc[0]: (shift 16 w + g, query 2 t), acc[1]: (same shift, query 2 t + 1), acc[2] / acc[3]: shift + 8
-      const int s0 = 16 * warp + g, s1 = s0 + 8;
-      Top2 ta{-3.4e38f, -3.4e38f, 1 << 20}, tb{-3.4e38f, -3.4e38f, 1 << 20};
-      if (s0 < kNS) top2_offer(ta, acc[0], s0), top2_offer(tb, acc[1], s0);
-      if (s1 < kNS) top2_offer(ta, acc[2], s1), top2_offer(tb, acc[3], s1);
-#pragma unroll
-      for (int off = 4; off < 32; off <<= 1) {  // over g
-        const float a1 = __shfl_xor_sync(0xffffffffu, ta.b1, off), a2 = __shfl_xor_sync(0xffffffffu, ta.b2, off);
-        const int aa = __shfl_xor_sync(0xffffffffu, ta.arg, off);
-        const float b1 = __shfl_xor_sync(0xffffffffu, tb.b1, off), b2 = __shfl_xor_sync(0xffffffffu, tb.b2, off);
-        const int ba = __shfl_xor_sync(0xffffffffu, tb.arg, off);
-        top2_merge(ta, a1, a2, aa);
-        top2_merge(tb, b1, b2, ba);
-      }
-      if (g == 0) {
-        sm.top[warp][2 * t][0] = ta.b1, sm.top[warp][2 * t][1] = ta.b2, sm.top[warp][2 * t][2] = __int_as_float(ta.arg);
-        sm.top[warp][2 * t + 1][0] = tb.b1, sm.top[warp][2 * t + 1][1] = tb.b2, sm.top[warp][2 * t + 1][2] = __int_as_float(tb.arg);
-      }
+      const int s0 = 16 * warp + g;
+      *reinterpret_cast<float2*>(&sm.corr[s0][2 * t]) = make_float2(acc[0], acc[1]);
+      *reinterpret_cast<float2*>(&sm.corr[s0 + 8][2 * t]) = make_float2(acc[2], acc[3]);
     }
     __syncthreads();
     // ---- every warp: its own query against the staged candidate
     if (has_q) {
-      Top2 al{-3.4e38f, -3.4e38f, 1 << 20};
-#pragma unroll
-      for (int w = 0; w < 4; ++w) top2_merge(al, sm.top[w][warp][0], sm.top[w][warp][1], __float_as_int(sm.top[w][warp][2]));
-      float ck2 = 0.f;
-      unsigned long long cmask = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) ck2 += sm.ck2_part[w], cmask |= (unsigned long long)sm.cm_part[w] << (8 * w);
-      cmask &= (1ull << kNS) - 1ull;
-      // |correlation error| <= 2e-5 |qk| |ck| (dropped lo x lo term 2^-22, fp32 accumulation of 192 products);
-      // the alignment is certain when the best correlation beats the runner-up by more than twice that
-      const float err = 2.0e-5f * qknorm * sqrtf(ck2) + 1e-30f;
-      const bool flagged = !(al.b1 - al.b2 > 2.f * err) || al.arg >= kNS;
-      const int a = al.arg < kNS ? al.arg : 0;
+      // best and second best correlation over the 60 shifts: order-preserving integer keys (correlations of non-negative
+      // keys are >= 0 up to rounding) with the shift in the low 6 bits, two REDUX each.  Truncating 6 mantissa bits
+      // costs 2^-17 relative, accounted for in the bound below.
+      const float c0v = sm.corr[lane][warp], c1v = lane + 32 < kNS ? sm.corr[lane + 32][warp] : 0.f;
+      uint32_t k0 = (__float_as_uint(fmaxf(c0v, 0.f)) & ~63u) | (uint32_t)(63 - lane);          // lower shift wins ties
+      uint32_t k1 = lane + 32 < kNS ? (__float_as_uint(fmaxf(c1v, 0.f)) & ~63u) | (uint32_t)(31 - lane) : 0u;
+      const uint32_t best = redux_max_u32(k0 > k1 ? k0 : k1);
+      if (k0 == best) k0 = 0u;
+      if (k1 == best) k1 = 0u;
+      const uint32_t second = redux_max_u32(k0 > k1 ? k0 : k1);
+      const int a = 63 - (int)(best & 63u);
+      const float b1 = __uint_as_float(best & ~63u), b2 = __uint_as_float(second & ~63u);
+      const unsigned long long cmask = sm.cmask;
+      // |correlation error| <= 3e-5 |qk| |ck| (hi/lo split: dropped lo x lo term 2^-22; fp32 accumulation of 192 products
+      // 1.1e-5; key truncation 7.6e-6); the alignment is certain when the best beats the runner-up by more than twice that
+      const float err = 3.0e-5f * qknorm * sqrtf(sm.ck2) + 1e-30f;
+      const bool flagged = !(b1 - b2 > 2.f * err) || a >= kNS;
       float x0 = 0.f, x1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int cb = 16 * i - a - 3;
+        int cb = 16 * i - a - 3 + (lane & 7);  // this lane's ldmatrix row of n-tile 0; +8, +16 for the next tiles
         cb += cb < 0 ? kNS : 0;
         cb += cb < 0 ? kNS : 0;  // 16 i - a - 3 >= -62
         float d[3][4];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+          int row = cb + 8 * j;
+          row -= row >= kNS ? kNS : 0;
           uint32_t b[4];
-          ldmatrix_x4(b, &sm.ch[cb + 8 * j + (lane & 7)][8 * (lane >> 3)]);
-          mma_f16(d[j], qa[i][0], b[0], b[1]);
+          ldmatrix_x4(b, &sm.ch[row][8 * (lane >> 3)]);
+          mma_f16_zero(d[j], qa[i][0], b[0], b[1]);
           mma_f16(d[j], qa[i][1], b[2], b[3]);
         }
         x0 += upper ? (d[1][0] + d[2][2]) : (d[0][0] + d[1][2]);
@@ -343,7 +328,7 @@ __global__ void __launch_bounds__(kPfThreads, 2)
       for (int off = 16; off > 0; off >>= 1) dist = fminf(dist, __shfl_xor_sync(0xffffffffu, dist, off));
       if (lane == 0) {
         D[(size_t)warp * n + cand] = flagged ? -1.f : dist;
-        if (Sh) Sh[(size_t)warp * n + cand] = (unsigned char)a;
+        if (Sh) Sh[(size_t)warp * n + cand] = (unsigned char)(a < kNS ? a : 0);
       }
     }
     cur ^= 1;

@@ -18,8 +18,9 @@ w = np.zeros((65536, 4), np.float32)
 w[:, :3] = (c["cloud"][:, :3].astype(np.float64) @ R.T + c["t_true"]).astype(np.float32)
 dev = torch.device("cuda:0")
 out = {"N": len(m), "Q": 65536}
-for name, env in (("per_query", "1000000000"), ("binned", "1")):
+for name, env, grp in (("per_query", "1000000000", "8"), ("binned_g4", "1", "4"), ("binned_g8", "1", "8"), ("binned_g16", "1", "16")):
     os.environ["ILSM_KNN_BINNED_MIN"] = env
+    os.environ["ILSM_KNN_GROUP"] = grp
     ctx = ilsm.Context(0)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=dev)
     d_m, d_q = torch.from_numpy(m).to(dev), torch.from_numpy(w).to(dev)
