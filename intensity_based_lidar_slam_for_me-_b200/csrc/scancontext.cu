@@ -658,8 +658,8 @@ int ScDb::query_dev(const float* d_qdesc, int n_search, int id_offset, int k, do
 int sc_score_lists_dev(ScDb* d, const float* d_qdesc, int B, int k, const u64* d_lists, const int* d_list_n, int list_cap, int id_offset,
                        int n_search, unsigned char* d_packed) {
   Ctx* ctx = d->ctx;
-  // lists are short (tens to hundreds of entries): a few blocks per query
-  const int blocks = 16;
+  // lists hold tens to a few thousand entries (mostly pairs whose alignment the prefilter could not decide)
+  const int blocks = 48;
   int rc;
   if ((rc = d->query.reserve(B)) || (rc = d->part_d.reserve((size_t)B * blocks * kTopKMax)) || (rc = d->part_id.reserve((size_t)B * blocks * kTopKMax)) ||
       (rc = d->part_sh.reserve((size_t)B * blocks * kTopKMax)))

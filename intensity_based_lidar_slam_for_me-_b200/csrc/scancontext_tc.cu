@@ -33,6 +33,7 @@ constexpr int kNR = 20, kNS = 60, kDesc = kNR * kNS;
 constexpr int kPfQ = 8;            // queries per block, one warp each
 constexpr int kPfThreads = 32 * kPfQ;
 constexpr int kChStride = 40;      // halves per staged candidate column: 80 B rows -> ldmatrix / LDS.32 conflict-free
+constexpr int kChCols = 84;        // 60 columns + the first 24 again: a 24-column window never wraps
 constexpr float kPfEps = 1.5e-3f;  // bound of |approximate - exact| distance for an unflagged pair
 
 struct PfQuery {              // prepared once per query
@@ -117,7 +118,7 @@ __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatil
 // ---------------------------------------------------------------------------------------------------
 struct PfSmem {
   __align__(16) float craw[2][kDesc];           // raw candidate descriptors, double buffered (filled by cp.async)
-  __align__(16) __half ch[kNS][kChStride];      // column-normalised candidate, [column][ring]; rings 20..31 stay zero
+  __align__(16) __half ch[kChCols][kChStride];  // column-normalised candidate, [column][ring] (columns 60.. repeat 0..); rings 20..31 stay zero
   __half ckh[128], ckl[128];                    // candidate sector key hi / lo at index x = (column - shift) + 64, periodic
   uint32_t pkh[128], pkl[128];                  // the same as adjacent pairs (x, x + 1): one 32-bit load per A-fragment register
   float corr[64][kPfQ];                         // alignment correlations [shift][query]
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(kPfThreads, 2)
   const int tt0 = u & 7;
 
   // the padding rings of the staged candidate are written once
-  for (int i = tid; i < kNS * (kChStride - kNR); i += kPfThreads) sm.ch[i / (kChStride - kNR)][kNR + i % (kChStride - kNR)] = __float2half(0.f);
+  for (int i = tid; i < kChCols * (kChStride - kNR); i += kPfThreads) sm.ch[i / (kChStride - kNR)][kNR + i % (kChStride - kNR)] = __float2half(0.f);
   // first candidate of this block (4800 B = 300 x 16 B)
   if ((int)blockIdx.x < n)
     for (int i = tid; i < kDesc / 4; i += kPfThreads) cp_async16(&sm.craw[0][4 * i], db + (size_t)blockIdx.x * kDesc + 4 * i);
@@ -207,10 +208,12 @@ __global__ void __launch_bounds__(kPfThreads, 2)
       const float key = s / kNR;
       if (col < kNS) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.ch[col][10 * hf]);
+        uint32_t* dup = reinterpret_cast<uint32_t*>(&sm.ch[col < kChCols - kNS ? col + kNS : col][10 * hf]);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const __half2 h2 = __floats2half2_rn(v[2 * k] * inv, v[2 * k + 1] * inv);
           dst[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          dup[k] = *reinterpret_cast<const uint32_t*>(&h2);
         }
         if (hf == 0) {
           const __half h = __float2half(key), l = __float2half(key - __half2float(h));
@@ -288,16 +291,15 @@ __global__ void __launch_bounds__(kPfThreads, 2)
       float x0 = 0.f, x1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        int cb = 16 * i - a - 3 + (lane & 7);  // this lane's ldmatrix row of n-tile 0; +8, +16 for the next tiles
+        int cb = 16 * i - a - 3;  // first candidate column of the tile row's window (24 columns, no wrap in the periodic copy)
         cb += cb < 0 ? kNS : 0;
-        cb += cb < 0 ? kNS : 0;  // 16 i - a - 3 >= -62
+        cb += cb < 0 ? kNS : 0;   // 16 i - a - 3 >= -62
+        const __half* rowp = &sm.ch[cb + (lane & 7)][8 * (lane >> 3)];
         float d[3][4];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          int row = cb + 8 * j;
-          row -= row >= kNS ? kNS : 0;
           uint32_t b[4];
-          ldmatrix_x4(b, &sm.ch[row][8 * (lane >> 3)]);
+          ldmatrix_x4(b, rowp + 8 * j * kChStride);
           mma_f16_zero(d[j], qa[i][0], b[0], b[1]);
           mma_f16(d[j], qa[i][1], b[2], b[3]);
         }
