@@ -102,7 +102,7 @@ int Ctx::init(int dev) {
 void Ctx::release() {
   if (fe_graph_exec) cudaGraphExecDestroy(fe_graph_exec), fe_graph_exec = nullptr;
   if (stream) cudaStreamSynchronize(stream);
-  fe.vg_keys.release(), fe.vg_state.release(), fe.vg_chunk.release(), fe.chunk_hist.release(), fe.chunk_base.release(), fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
+  fe.vg_hash.release(), fe.vg_keys.release(), fe.vg_state.release(), fe.vg_chunk.release(), fe.chunk_hist.release(), fe.chunk_base.release(), fe.scanid.release(), fe.picked.release(), fe.ori.release(), fe.curv.release(), fe.stats.release();
   fe.src_index.release(), fe.label.release(), fe.sort_ind.release(), fe.ring_sharp.release(), fe.ring_lsharp.release();
   fe.ring_flat.release(), fe.sharp.release(), fe.lsharp.release(), fe.flat.release(), fe.counts.release();
   fe.cloud.release(), fe.ring_pts.release(), fe.ring_out.release(), fe.lflat.release(), fe.vox_packed.release();

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(1024)
 // Per-cube VoxelGrid of the valid cubes: block (v, type) filters its slab into scratch and copies it back.
 __global__ void __launch_bounds__(1024)
     cube_filter_kernel(const int* __restrict__ valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
-                       float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err) {
+                       float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err, uint32_t* __restrict__ hscratch) {
   pdl_entry();
   extern __shared__ u64 keys[];
   const int v = blockIdx.x >> 1;
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(1024)
   float4* out = scratch + (size_t)blockIdx.x * cap;
   int P = 1;
   while (P < n) P <<= 1;
-  const int m = voxelgrid_block(pts, n, corner ? leaf_c : leaf_s, keys, P, out, err);
+  // cubes that have grown large take the hash-based VoxelGrid (only the distinct voxels are sorted)
+  const int m = n > 2048 ? voxelgrid_block_hash(pts, n, corner ? leaf_c : leaf_s, reinterpret_cast<unsigned char*>(keys),
+                                                hscratch + (size_t)blockIdx.x * kVgScratchWords, out, err)
+                         : voxelgrid_block(pts, n, corner ? leaf_c : leaf_s, keys, P, out, err);
   __syncthreads();
   for (int t = threadIdx.x; t < m; t += blockDim.x) pts[t] = out[t];
   if (threadIdx.x == 0) *cnt = m;
@@ -158,7 +161,7 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
   if ((rc = slabs_c.reserve((size_t)kCNum * cap)) || (rc = slabs_s.reserve((size_t)kCNum * cap)) ||
       (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
       (rc = stack_n.reserve(4)) || (rc = valid_d.reserve(128)) || (rc = err.reserve(4)) || (rc = items.reserve(256)) ||
-      (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) ||
+      (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) || (rc = hscratch.reserve((size_t)250 * kVgScratchWords)) ||
       (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)) ||
       (rc = pin_counts.reserve(2 * kCNum + 16)))
     return rc;
@@ -173,8 +176,7 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
   ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
   ILSM_CUDA(cudaFuncSetAttribute(cube_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kVoxelBlockMax * sizeof(u64))));
-  ILSM_CUDA(cudaFuncSetAttribute(cube_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kVoxelBlockMax * sizeof(u64))));
+  ILSM_CUDA(cudaFuncSetAttribute(cube_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVgHashSmemBytes));
   ILSM_CUDA(cudaStreamSynchronize(s));
   return ILSM_OK;
 }
@@ -187,7 +189,7 @@ void CubeMapH::release() {
   pin_counts.release();
   map_c.release(), map_s.release();
   slabs_c.release(), slabs_s.release(), from_c.release(), from_s.release(), stack_c.release(), stack_s.release();
-  scratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release();
+  scratch.release(), hscratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release();
   valid_d.release(), err.release(), zero_list.release(), items.release(), raw.release(), pin.release();
 }
 
@@ -289,7 +291,9 @@ int CubeMapH::filter_valid(cudaStream_t s) {
   int* p = pin.p + kCNum + 1024;
   for (int v = 0; v < n_valid; ++v) p[v] = slab_of[valid[v]];
   ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
-  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), kVoxelBlockMax * sizeof(u64), s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p));
+  // shared memory: the hash-based path's 192 KB only when a cube can be large enough to take it
+  const size_t smem = cap > 2048 ? kVgHashSmemBytes : (size_t)kVoxelBlockMax * sizeof(u64);
+  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), smem, s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p, hscratch.p));
   count_launches(1);
   return check_launch("cube_filter");
 }

@@ -614,6 +614,7 @@ __global__ void gather_points_kernel(const float4* __restrict__ cloud, const int
 // stand-alone VoxelGrid, one block per job (n <= kVoxelMax per job); n may come from device memory (n_ptr).  The two
 // feature stacks of a frame (corner / surf) are two jobs of one launch.
 constexpr int kVoxelMax = kVoxelBlockMax;
+constexpr int kVgHashMin = 2048;  // clouds above this size take the hash-based VoxelGrid (only the distinct voxels are sorted)
 struct VoxJob {
   const float* in;
   const int* n_ptr;
@@ -622,6 +623,7 @@ struct VoxJob {
   int* n_out;
   int n_host, n_slot, stride_f, ioff;
   float leaf;
+  uint32_t* scratch;  // kVgScratchWords words of global memory for the hash-based path (nullptr: sort-based path only)
 };
 struct VoxJobs {
   VoxJob j[2];
@@ -642,7 +644,11 @@ __global__ void __launch_bounds__(1024) voxelgrid_kernel(VoxJobs jobs, int* err)
   __syncthreads();
   int P = 1;
   while (P < n) P <<= 1;
-  const int nvox = n > 0 ? voxelgrid_block(jb.packed, n, jb.leaf, dyn_keys, P, jb.out, err) : 0;
+  int nvox = 0;
+  if (n > kVgHashMin && jb.scratch)
+    nvox = voxelgrid_block_hash(jb.packed, n, jb.leaf, reinterpret_cast<unsigned char*>(dyn_keys), jb.scratch, jb.out, err);
+  else if (n > 0)
+    nvox = voxelgrid_block(jb.packed, n, jb.leaf, dyn_keys, P, jb.out, err);
   if (threadIdx.x == 0) *jb.n_out = nvox;
 }
 
@@ -932,13 +938,14 @@ int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int
   int rc;
   const int cap = d_n ? kVoxelMax : n;
   if (!d_n && n > kVoxelMax) return fail(ILSM_ERR_INVALID_ARG, "voxelgrid: more than 16384 points per call");
-  if ((rc = fe.vox_packed.reserve(cap + 4)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
-  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelMax * sizeof(u64))));
+  if ((rc = fe.vox_packed.reserve(cap + 4)) || (rc = fe.stats.reserve(kStInts + 8)) || (rc = fe.vg_hash.reserve(2 * kVgScratchWords))) return rc;
+  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVgHashSmemBytes));
   int P = 1;
   while (P < cap) P <<= 1;
   VoxJobs jobs = {};
-  jobs.j[0] = VoxJob{d_in, d_n, fe.vox_packed.p, d_out, d_n_out, n, n_slot, stride_bytes / 4, ioff, leaf};
-  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), stream, jobs, fe.stats.p + kStErr));
+  jobs.j[0] = VoxJob{d_in, d_n, fe.vox_packed.p, d_out, d_n_out, n, n_slot, stride_bytes / 4, ioff, leaf, fe.vg_hash.p};
+  const size_t smem = cap > kVgHashMin ? kVgHashSmemBytes : (size_t)P * sizeof(u64);
+  ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), smem, stream, jobs, fe.stats.p + kStErr));
   count_launches(1);
   return check_launch("voxelgrid");
 }
@@ -950,18 +957,21 @@ int Ctx::voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int
 int Ctx::voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_out_c, const float* d_s, int ns, float leaf_s,
                             float4* d_out_s, int stride_bytes, int ioff, int* d_n_out2, cudaStream_t s, int* d_err) {
   int rc;
-  if ((rc = fe.vox_packed.reserve((size_t)2 * kVoxelMax + 8)) || (rc = fe.stats.reserve(kStInts + 8))) return rc;
+  if ((rc = fe.vox_packed.reserve((size_t)2 * kVoxelMax + 8)) || (rc = fe.stats.reserve(kStInts + 8)) || (rc = fe.vg_hash.reserve(2 * kVgScratchWords)))
+    return rc;
   if (!d_err) d_err = fe.stats.p + kStErr;
-  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kVoxelMax * sizeof(u64))));
+  ILSM_CUDA(cudaFuncSetAttribute(voxelgrid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVgHashSmemBytes));
   const bool big_c = nc > kVoxelMax, big_s = ns > kVoxelMax;
   if (!big_c && !big_s) {
     const int big = nc > ns ? nc : ns;
     int P = 1;
     while (P < big) P <<= 1;
     VoxJobs jobs = {};
-    jobs.j[0] = VoxJob{d_c, nullptr, fe.vox_packed.p, d_out_c, d_n_out2, nc, 0, stride_bytes / 4, ioff, leaf_c};
-    jobs.j[1] = VoxJob{d_s, nullptr, fe.vox_packed.p + kVoxelMax, d_out_s, d_n_out2 + 1, ns, 0, stride_bytes / 4, ioff, leaf_s};
-    ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), (size_t)P * sizeof(u64), s, jobs, d_err));
+    jobs.j[0] = VoxJob{d_c, nullptr, fe.vox_packed.p, d_out_c, d_n_out2, nc, 0, stride_bytes / 4, ioff, leaf_c, fe.vg_hash.p};
+    jobs.j[1] = VoxJob{d_s, nullptr, fe.vox_packed.p + kVoxelMax, d_out_s, d_n_out2 + 1, ns, 0, stride_bytes / 4, ioff, leaf_s,
+                       fe.vg_hash.p + kVgScratchWords};
+    const size_t smem = big > kVgHashMin ? kVgHashSmemBytes : (size_t)P * sizeof(u64);
+    ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(2), dim3(1024), smem, s, jobs, d_err));
     count_launches(1);
     return check_launch("voxelgrid_pair");
   }
@@ -977,8 +987,8 @@ int Ctx::voxelgrid_pair_dev(const float* d_c, int nc, float leaf_c, float4* d_ou
       int P = 1;
       while (P < n[k]) P <<= 1;
       VoxJobs jobs = {};
-      jobs.j[0] = VoxJob{in[k], nullptr, fe.vox_packed.p, out[k], d_n_out2 + k, n[k], 0, stride_bytes / 4, ioff, leaf[k]};
-      ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), (size_t)P * sizeof(u64), s, jobs, d_err));
+      jobs.j[0] = VoxJob{in[k], nullptr, fe.vox_packed.p, out[k], d_n_out2 + k, n[k], 0, stride_bytes / 4, ioff, leaf[k], fe.vg_hash.p};
+      ILSM_CUDA(launch_pdl(voxelgrid_kernel, dim3(1), dim3(1024), n[k] > kVgHashMin ? kVgHashSmemBytes : (size_t)P * sizeof(u64), s, jobs, d_err));
       count_launches(1);
     }
   }

@@ -41,6 +41,7 @@ struct CubeMapH {
   std::vector<int> cnt_c_h, cnt_s_h;  // host mirror of the per-slab counts
   int valid[125], n_valid = 0;
   DevBuf<float4> slabs_c, slabs_s, from_c, from_s, stack_c, stack_s, scratch, world_tmp;
+  DevBuf<uint32_t> hscratch;  // hash-based VoxelGrid scratch, one slice per cube_filter block
   DevBuf<int> cnt_c, cnt_s, slab_of_d, stack_n, valid_d, err, zero_list;
   DevBuf<GatherItem> items;
   DevBuf<float> raw;

@@ -197,6 +197,7 @@ struct FeBufs {
   DevBuf<u64> vg_keys;            // multi-block VoxelGrid: sort keys, state, per-chunk head counts / bases
   DevBuf<VgState> vg_state;
   DevBuf<int> vg_chunk;
+  DevBuf<uint32_t> vg_hash;         // hash-based block VoxelGrid: global scratch of the (at most two) blocks of a launch
   DevBuf<int> chunk_hist, chunk_base;  // ring counts per 256-point chunk of the frame and their per-ring prefix
   DevBuf<float4> cloud, ring_pts, ring_out, lflat, vox_packed;
   DevBuf<float> raw;                 // staged caller frame

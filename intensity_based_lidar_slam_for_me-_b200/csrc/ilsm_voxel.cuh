@@ -206,5 +206,194 @@ static __device__ int voxelgrid_block(const float4* __restrict__ pts, int m, flo
   return s_count;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same VoxelGrid without sorting the points: PCL orders its OUTPUT by voxel index and sums every voxel's points in
+// input order, so only the distinct voxels have to be sorted (a stack of ~9 k less-flat points falls into ~2 k voxels of
+// 0.8 m) and each voxel's few members by index.
+//   1. bounding box -> voxel index per point (as above)
+//   2. open-addressing hash of the voxel indices in shared memory (32768 slots): slot per point by atomicCAS, arrival
+//      rank inside the voxel by atomicAdd (16-bit counters, two per word)
+//   3. the occupied slots are compacted into a list (voxel index << 15 | slot) and sorted: ascending voxel index
+//   4. exclusive scan of the voxel populations in that order -> where each voxel's member list starts
+//   5. every point drops its index into its voxel's list at its arrival rank (arbitrary order)
+//   6. one thread per voxel sorts its member list by index (insertion / shell sort: lists are short) and adds the
+//      members up in that order -- the float sums of pcl::CentroidPoint, bit for bit
+// Shared memory: smem must provide kVgHashSmemBytes (192 KB); scratch = kVgScratchWords 32-bit words of global memory per
+// block.  m <= kVoxelBlockMax.  Returns the number of voxels (block-uniform).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kVgHashSlots = 32768;
+constexpr size_t kVgHashSmemBytes = (size_t)kVgHashSlots * 4 + (size_t)kVgHashSlots * 2;  // keys (reused: sort keys, member lists) + counters
+constexpr size_t kVgScratchWords = (size_t)kVoxelBlockMax + kVgHashSlots + 2 * (size_t)kVoxelBlockMax + kVoxelBlockMax;
+
+static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m, float leaf, unsigned char* smem, uint32_t* __restrict__ scratch,
+                                           float4* __restrict__ out, int* err) {
+  __shared__ float s_min[3], s_max[3];
+  __shared__ int s_V, s_carry;
+  __shared__ int wc[32];
+  uint32_t* hkeys = reinterpret_cast<uint32_t*>(smem);                       // region A, first life: the hash keys
+  u64* skeys = reinterpret_cast<u64*>(smem);                                 // region A, second life: the voxel sort keys
+  unsigned short* members = reinterpret_cast<unsigned short*>(smem);         // region A, third life: the member lists
+  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem + (size_t)kVgHashSlots * 4);  // region B: two 16-bit counters per word
+  uint32_t* g_sr = scratch;                                       // per point: slot << 16 | arrival rank (0xFFFFFFFF: skipped)
+  uint32_t* g_sp = scratch + kVoxelBlockMax;                      // per slot: list start << 16 | output position
+  u64* g_list = reinterpret_cast<u64*>(scratch + kVoxelBlockMax + kVgHashSlots);  // compacted (voxel << 15 | slot)
+  uint32_t* g_vinfo = scratch + kVoxelBlockMax + kVgHashSlots + 2 * kVoxelBlockMax;  // per output voxel: start << 16 | count
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < 3) s_min[tid] = __int_as_float(0x7f800000), s_max[tid] = __int_as_float(0xff800000);
+  if (tid == 0) s_V = 0, s_carry = 0;
+  for (int i = tid; i < kVgHashSlots; i += nt) hkeys[i] = 0xFFFFFFFFu;
+  for (int i = tid; i < kVgHashSlots / 2; i += nt) cnt32[i] = 0u;
+  __syncthreads();
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  for (int t = tid; t < m; t += nt) {
+    const float4 p = pts[t];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      mn[0] = fminf(mn[0], p.x), mn[1] = fminf(mn[1], p.y), mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x), mx[1] = fmaxf(mx[1], p.y), mx[2] = fmaxf(mx[2], p.z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int* pmn = reinterpret_cast<int*>(&s_min[a]);
+      int* pmx = reinterpret_cast<int*>(&s_max[a]);
+      if (mn[a] >= 0.f) atomicMin(pmn, __float_as_int(mn[a])); else atomicMax(reinterpret_cast<unsigned*>(pmn), __float_as_uint(mn[a]));
+      if (mx[a] >= 0.f) atomicMax(pmx, __float_as_int(mx[a])); else atomicMin(reinterpret_cast<unsigned*>(pmx), __float_as_uint(mx[a]));
+    }
+  }
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = __float2int_rd(__fmul_rn(s_min[a], inv));
+    div_b[a] = __float2int_rd(__fmul_rn(s_max[a], inv)) - min_b[a] + 1;
+  }
+  const long long mul1 = div_b[0], mul2 = (long long)div_b[0] * div_b[1];
+  if (mul2 * div_b[2] >= (1ll << 31)) {  // pcl: "Leaf size is too small for the input dataset"
+    if (tid == 0) atomicOr(err, 2);
+    return 0;
+  }
+  // ---- 2. voxel slot and arrival rank of every point
+  for (int t = tid; t < m; t += nt) {
+    const float4 p = pts[t];
+    uint32_t sr = 0xFFFFFFFFu;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const int i0 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)min_b[0]));
+      const int i1 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)min_b[1]));
+      const int i2 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)min_b[2]));
+      const uint32_t idx = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
+      uint32_t slot = (idx * 2654435761u) >> 17;
+      for (;;) {
+        const uint32_t prev = atomicCAS(&hkeys[slot], 0xFFFFFFFFu, idx);
+        if (prev == 0xFFFFFFFFu || prev == idx) break;
+        slot = (slot + 1) & (kVgHashSlots - 1);
+      }
+      const int sh = 16 * (slot & 1);
+      const uint32_t old = atomicAdd(&cnt32[slot >> 1], 1u << sh);
+      sr = (slot << 16) | ((old >> sh) & 0xFFFFu);
+    }
+    g_sr[t] = sr;
+  }
+  __syncthreads();
+  // ---- 3. occupied slots -> list, sorted by voxel index
+  for (int sl = tid; sl < kVgHashSlots; sl += nt) {
+    const uint32_t key = hkeys[sl];
+    if (key != 0xFFFFFFFFu) g_list[atomicAdd(&s_V, 1)] = ((u64)key << 15) | (u64)sl;
+  }
+  __syncthreads();
+  const int V = s_V;
+  int Pv = 32;
+  while (Pv < V) Pv <<= 1;
+  for (int j = tid; j < Pv; j += nt) skeys[j] = j < V ? g_list[j] : ~0ull;  // region A changes hands: every thread is past its hkeys reads
+  __syncthreads();
+  bitonic_sort_smem(skeys, Pv);
+  // ---- 4. exclusive scan of the populations in output order
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int j0 = 0; j0 < Pv; j0 += nt) {
+    const int j = j0 + tid;
+    uint32_t slot = 0;
+    int c = 0;
+    if (j < V) {
+      slot = (uint32_t)(skeys[j] & 0x7FFFu);
+      c = (int)((cnt32[slot >> 1] >> (16 * (slot & 1))) & 0xFFFFu);
+    }
+    int inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += o;
+    }
+    if (lane == 31) wc[warp] = inc;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+      if (w < warp) wbase += wc[w];
+      tot += wc[w];
+    }
+    const int start = s_carry + wbase + inc - c;
+    if (j < V) {
+      g_sp[slot] = ((uint32_t)start << 16) | (uint32_t)j;
+      g_vinfo[j] = ((uint32_t)start << 16) | (uint32_t)c;
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  __threadfence_block();
+  // ---- 5. member lists (region A changes hands again: the sort keys are consumed)
+  for (int t = tid; t < m; t += nt) {
+    const uint32_t sr = g_sr[t];
+    if (sr != 0xFFFFFFFFu) members[(g_sp[sr >> 16] >> 16) + (sr & 0xFFFFu)] = (unsigned short)t;
+  }
+  __syncthreads();
+  // ---- 6. per voxel: members by index, then the ordered float sums
+  for (int j = tid; j < V; j += nt) {
+    const uint32_t vi = g_vinfo[j];
+    const int start = (int)(vi >> 16), c = (int)(vi & 0xFFFFu);
+    unsigned short* L = members + start;
+    if (c <= 24) {
+      for (int a = 1; a < c; ++a) {
+        const unsigned short x = L[a];
+        int b = a - 1;
+        while (b >= 0 && L[b] > x) L[b + 1] = L[b], --b;
+        L[b + 1] = x;
+      }
+    } else {
+      const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
+      for (int gi = 0; gi < 8; ++gi) {
+        const int gap = gaps[gi];
+        for (int a = gap; a < c; ++a) {
+          const unsigned short x = L[a];
+          int b = a;
+          while (b >= gap && L[b - gap] > x) L[b] = L[b - gap], b -= gap;
+          L[b] = x;
+        }
+      }
+    }
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int e0 = 0; e0 < c; e0 += 4) {  // 4 gathers in flight, then the 4 sequential float adds (PCL's order)
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = e0 + k < c ? pts[L[e0 + k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (e0 + k < c) sx = __fadd_rn(sx, q[k].x), sy = __fadd_rn(sy, q[k].y), sz = __fadd_rn(sz, q[k].z), si = __fadd_rn(si, q[k].w);
+    }
+    const float cf = (float)c;
+    out[j] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
+  }
+  __syncthreads();
+  return V;
+}
 
 }  // namespace ilsm
