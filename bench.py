@@ -381,6 +381,8 @@ def config2_point(ilsm, torch, ctx, dev, frames, oracle_frames):
            "d2h_bytes_per_frame": 2 * 56 + 400, "gpu_launches_per_frame": launches / frames,
            "ate_rmse_m": float(np.sqrt(np.mean(np.square(err)))), "final_position_error_m": err[-1],
            "window_rolls_in_loop": len(rolls), "first_roll_frame": rolls[0] if rolls else None, "capacity_flags": flags,
+           "slowest_frames_ms": {int(k): round(1e3 * times[k], 3) for k in np.argsort(times)[-5:][::-1]},
+           "frames_over_1ms": int(np.sum(np.array(times) > 1e-3)),
            "frame_generation_s": gen_s,
            "timing": "host wall clock around the blocking ilsm_slam_frame calls"}
     # the same sequence with laserMapping as its own pipeline stage (ilsm_slam_create_async: second context + host thread,
