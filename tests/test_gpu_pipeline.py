@@ -209,3 +209,50 @@ def test_feature_clouds_above_16384_points(ctx, oracle_mod, ilsm, pipelined):
     for k, ((gq, gt), w) in enumerate(zip(got, want)):
         assert np.linalg.norm(gt - w[4:]) < 1e-4 and S.quat_angle(gq, w[:4]) < 1e-4, k
     slam.close()
+
+
+def test_long_run_with_in_loop_window_rolls_matches_oracle(ctx, oracle_mod, ilsm):
+    """laserMapping's 21x21x11 window of 50 m cubes rolls when the centre cube comes within 3 cubes of the border
+    (laserMapping.cpp:341-565): 2.2 m per frame along a 560 m corridor crosses that line three times inside the loop.
+    Every pose, the roll frames and the whole occupied map must match the chained oracle."""
+    import torch
+    S = ilsm.synth
+    F = 250
+    scene = S.Scene(corridor=True, length=2.2 * F + 30.0)
+    poses = S.corridor_poses(F, step=2.2)
+    clouds = S.make_frames_torch(scene, poses, 0x5EED0900, torch.device("cuda:0"))
+    slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+    oslam = oracle_mod.Slam(0.4, 0.8, 0.3)
+    cen, ocen = [], []
+    for k in range(F):
+        cloud = clouds[k].numpy()
+        gqo, gto, gqm, gtm, st = slam.frame(cloud)
+        wodom, wmap, info = oslam.frame(cloud)
+        assert np.linalg.norm(gtm - wmap[4:]) < 1e-4 and S.quat_angle(gqm, wmap[:4]) < 1e-4, k
+        assert np.linalg.norm(gto - wodom[4:]) < 1e-4, k
+        assert st.cubemap.flags == 0
+        cen.append(tuple(st.cubemap.cen))
+        ocen.append(tuple(info["cubemap"].cen))
+    rolls = [k for k in range(1, F) if cen[k] != cen[k - 1]]
+    assert cen == ocen and len(rolls) >= 2, rolls
+    view = slam.cubemap()
+    occupied = [i for i in range(4851) if len(oslam.cube.cube(1, i)) or len(oslam.cube.cube(0, i))]
+    assert len(occupied) >= 8
+    for idx in occupied:
+        for which in (0, 1):
+            g, w = view.cube(which, idx), oslam.cube.cube(which, idx)
+            assert g.shape == w.shape and np.array_equal(g[:, :3], w[:, :3]), (idx, which)
+    slam.close()
+
+
+def test_cube_capacity_overflow_is_reported(ctx, ilsm):
+    """A cube slab that cannot take the frame's points must not corrupt anything silently: the frame call fails with
+    ILSM_ERR_OUT_OF_MEMORY and names the capacity flag (32 = cube slab full)."""
+    S = ilsm.synth
+    frames = corridor_frames(S, 6)
+    slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 512)  # 512 points per 50 m cube: the first frames already overflow it
+    with pytest.raises(ilsm.IlsmError) as ei:
+        for cloud, _, _ in frames:
+            slam.frame(cloud)
+    assert ei.value.code == -5 and "capacity" in str(ei.value) and "0x2" in str(ei.value)
+    slam.close()
