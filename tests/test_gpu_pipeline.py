@@ -213,13 +213,13 @@ def test_feature_clouds_above_16384_points(ctx, oracle_mod, ilsm, pipelined):
 
 def test_long_run_with_in_loop_window_rolls_matches_oracle(ctx, oracle_mod, ilsm):
     """laserMapping's 21x21x11 window of 50 m cubes rolls when the centre cube comes within 3 cubes of the border
-    (laserMapping.cpp:341-565): 2.2 m per frame along a 560 m corridor crosses that line three times inside the loop.
-    Every pose, the roll frames and the whole occupied map must match the chained oracle."""
+    (laserMapping.cpp:341-565): 0.6 m per frame along a 460 m corridor crosses that line twice inside the loop (at ~375 m
+    and ~425 m of estimated travel).  Every pose, the window indices and the whole occupied map must match the chained oracle."""
     import torch
     S = ilsm.synth
-    F = 250
-    scene = S.Scene(corridor=True, length=2.2 * F + 30.0)
-    poses = S.corridor_poses(F, step=2.2)
+    F = 760
+    scene = S.Scene(corridor=True, length=0.6 * F + 30.0)
+    poses = S.corridor_poses(F, step=0.6)
     clouds = S.make_frames_torch(scene, poses, 0x5EED0900, torch.device("cuda:0"))
     slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
     oslam = oracle_mod.Slam(0.4, 0.8, 0.3)
