@@ -403,6 +403,33 @@ def config2_point(ilsm, torch, ctx, dev, frames, oracle_frames):
                                       "identical_to_synchronous": bool(all(np.array_equal(a, b[1]) for a, b in zip(mapped, est))),
                                       "note": "mapped pose of frame k returned by call k+1 (one-frame latency, like the "
                                               "reference's separate laserMapping node)"}
+    # ... and as three stages (ilsm_slam_create_staged: front end, odometry and mapping each on its own context and host
+    # thread, like the reference's three nodes; odometry pose one call later, mapped pose two calls later)
+    wall_s, smapped, sodom = None, None, None
+    for _ in range(2):
+        sslam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192, staged=True)
+        n_s = frames if _ else min(frames, 100)
+        smapped, sodom, t0 = {}, {}, time.perf_counter()
+        stimes, tp = [], t0
+        for k in range(n_s + 2):
+            fo, qo, to, fm, qm, tm, st = sslam.frame_staged(views[k] if k < n_s else None)
+            if fo >= 0:
+                sodom[fo] = to
+            if fm >= 0:
+                smapped[fm] = tm
+            tn = time.perf_counter()
+            stimes.append(tn - tp)
+            tp = tn
+        wall_s = time.perf_counter() - t0
+        phases = sslam.host_phases()
+        sslam.close()
+    out["three_stage_pipeline"] = {"value": frames / wall_s, "unit": "frames/s", "ms_per_frame": 1e3 * wall_s / frames,
+                                   "identical_to_synchronous": bool(len(smapped) == frames and all(np.array_equal(smapped[k], est[k][1]) for k in range(frames))),
+                                   "host_phase_ms_per_frame": [round(1e3 * float(p) / frames, 4) for p in phases],
+                                   "ms_per_call_median": 1e3 * float(np.median(stimes)),
+                                   "slowest_calls_ms": {int(k): round(1e3 * stimes[k], 3) for k in np.argsort(stimes)[-5:][::-1]},
+                                   "note": "odometry pose of frame k returned by call k+1, mapped pose by call k+2 (the "
+                                           "reference's three nodes have the same queue latency between them)"}
     no = min(oracle_frames, frames)
     if no > 0:
         import oracle

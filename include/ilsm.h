@@ -327,10 +327,27 @@ ILSM_API int ilsm_slam_frame_async(ilsm_slam* slam, const float* xyzi, int n, in
                                    double t_odom[3], double q_map_prev_xyzw[4], double t_map_prev[3], int* have_prev,
                                    ilsm_slam_stats* stats);
 ILSM_API int ilsm_slam_flush(ilsm_slam* slam, double q_map_xyzw[4], double t_map[3], int* have, ilsm_slam_stats* stats);
+/* The same loop as THREE stages, the way the reference runs three nodes (spot.launch: ascanRegistration, alaserOdometry,
+ * alaserMapping, each its own process fed by a topic queue): scanRegistration on an owned context with its own host
+ * thread, laserOdometry on the caller's context and thread, laserMapping on a second owned context and thread.  One call
+ * pushes frame k to the front-end stage, runs the odometry of frame k - 1 (pushed by the previous call) and collects the
+ * mapping of frame k - 2:
+ *   *odom_frame = index of the frame q_odom / t_odom belong to (-1: none yet), *map_frame likewise for q_map / t_map;
+ *   stats: counts and odometry report of *odom_frame, mapping report and cube-map statistics of *map_frame.
+ * n < 0 pushes nothing and only advances the stages (drain: two such calls after the last frame hand out everything).
+ * `xyzi` is read asynchronously by the front-end stage: it must stay valid until the NEXT call of this function returns.
+ * use_aloam travels with the frame.  Pose for pose the results are those of ilsm_slam_frame (same kernels, same order
+ * within each stage; the inter-stage clouds rotate through three device slots). */
+ILSM_API int ilsm_slam_create_staged(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                                     ilsm_slam** out);
+ILSM_API int ilsm_slam_frame_staged(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam,
+                                    double q_odom_xyzw[4], double t_odom[3], int* odom_frame, double q_map_xyzw[4],
+                                    double t_map[3], int* map_frame, ilsm_slam_stats* stats);
 /* Profiling aid: host seconds spent per phase of ilsm_slam_frame[_async] since the last call of this function (reset on
  * read): [0] upload + front-end launches, [1] wait for the previous frame's mapping (pipelined mode), [2] wait for the front
  * end, [3] gathers / VoxelGrid / odometry launches, [4] wait for the odometry, [5] tree builds + mapping stage; pipelined mode:
- * [6] launches and [7] waits of the mapping stage's own thread. */
+ * [6] launches and [7] waits of the mapping stage's own thread.  Staged mode: [2] wait for the front-end stage, [0] hand-over to it,
+ * [3] odometry launches, [1] wait for the mapping stage, [4] wait for the odometry, [5] tree builds + hand-over to the mapping stage. */
 ILSM_API int ilsm_slam_host_phases(ilsm_slam* slam, double out8[8]);
 
 /* ------------------------------------------------------------------- scan-to-scan odometry (laserOdometry) ---- */

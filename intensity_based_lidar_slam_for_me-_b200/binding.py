@@ -173,6 +173,8 @@ def load_library(path: str | None = None):
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_slam_create_async": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
         "ilsm_slam_frame_async": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
+        "ilsm_slam_create_staged": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
+        "ilsm_slam_frame_staged": (i32, [vp, vp, i32, i32, i32, vp, vp, C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
         "ilsm_slam_host_phases": (i32, [vp, vp]),
         "ilsm_slam_flush": (i32, [vp, vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
         "ilsm_slam_frame_pc2": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
@@ -717,12 +719,16 @@ class Slam:
 
     def __init__(self, ctx: Context, line_res: float = 0.4, plane_res: float = 0.8, min_range: float = 0.3,
                  cube_capacity: int = 0, mapping: str = "laserMapping", voxel_leaf: float = 0.8, downsample_size: float = 0.4,
-                 pipelined: bool = False):
+                 pipelined: bool = False, staged: bool = False):
         self._ctx = ctx
         self._lib = ctx._lib
         h = C.c_void_p()
         self.pipelined = bool(pipelined)
-        if mapping == "laserMapping" and pipelined:
+        self.staged = bool(staged)
+        self._held = []
+        if mapping == "laserMapping" and staged:
+            _check(self._lib.ilsm_slam_create_staged(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
+        elif mapping == "laserMapping" and pipelined:
             _check(self._lib.ilsm_slam_create_async(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
         elif mapping == "laserMapping":
             _check(self._lib.ilsm_slam_create(ctx._h, line_res, plane_res, min_range, cube_capacity, C.byref(h)))
@@ -769,6 +775,22 @@ class Slam:
         _check(self._lib.ilsm_slam_frame_async(self._h, _ptr(a), n, stride, 1 if use_aloam else 0, _ptr(qo), _ptr(to), _ptr(qm),
                                                _ptr(tm), C.byref(have), C.byref(st)))
         return (qo, to, qm, tm, st) if have.value else (qo, to, None, None, st)
+
+    def frame_staged(self, cloud=None, use_aloam: bool = True):
+        """Staged mode (ilsm_slam_create_staged): pushes `cloud` (None: drain step) and returns
+        (odom_frame, q_odom, t_odom, map_frame, q_map, t_map, stats); a frame index of -1 means "none in this call".  The
+        odometry pose is that of the frame pushed one call earlier, the mapped pose that of the frame two calls earlier."""
+        if cloud is None:
+            a, n, stride = None, -1, 16
+        else:
+            a, n, stride = _cloud(cloud)
+        qo, to, qm, tm = np.zeros(4), np.zeros(3), np.zeros(4), np.zeros(3)
+        fo, fm = C.c_int32(-1), C.c_int32(-1)
+        st = SlamStats()
+        _check(self._lib.ilsm_slam_frame_staged(self._h, _ptr(a) if a is not None else None, n, stride, 1 if use_aloam else 0,
+                                                _ptr(qo), _ptr(to), C.byref(fo), _ptr(qm), _ptr(tm), C.byref(fm), C.byref(st)))
+        self._held = [self._held[-1] if self._held else None, a]  # the front-end stage reads `a` until the next call returns
+        return fo.value, qo, to, fm.value, qm, tm, st
 
     def host_phases(self):
         """Host seconds per phase since the last call (see ilsm_slam_host_phases)."""

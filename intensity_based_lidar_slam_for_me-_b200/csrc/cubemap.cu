@@ -12,6 +12,8 @@
 #include <new>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "ilsm_cubemap.hpp"
 #include "ilsm_voxel.cuh"
 
@@ -25,10 +27,14 @@ __global__ void cube_gather_kernel(const float4* __restrict__ slabs, int cap, co
     out[it.offset + t] = slabs[(size_t)it.slab * cap + t];
 }
 
-__global__ void cube_zero_counts_kernel(int* cnt, const int* __restrict__ slabs, int n) {
+// recycled cubes start empty: point counts and the "first points are VoxelGrid output" marks of both cloud kinds
+__global__ void cube_zero_counts_kernel(int* cnt_c, int* cnt_s, int* filt_n, const int* __restrict__ slabs, int n) {
   pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) cnt[slabs[i]] = 0;
+  if (i < n) {
+    const int sl = slabs[i];
+    cnt_c[sl] = 0, cnt_s[sl] = 0, filt_n[sl] = 0, filt_n[kCNum + sl] = 0;
+  }
 }
 
 // laserMapping.cpp:886-896 (float coordinate widened to double, truncation, negative fix-up)
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(1024)
     cube_insert_kernel(const float4* __restrict__ stack_c, const float4* __restrict__ stack_s, const int* __restrict__ d_counts,
                        int nc_host, int ns_host, const LmState* __restrict__ st, int world_frame, int cenW, int cenH, int cenD,
                        const int* __restrict__ slab_of, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
-                       float4* __restrict__ world_tmp, int tmp_stride, int* err) {
+                       float4* __restrict__ world_tmp, int tmp_stride, int* err, int* __restrict__ clean) {
   pdl_entry();
   extern __shared__ u64 keys[];
   const bool corner = blockIdx.x == 0;
@@ -116,14 +122,20 @@ __global__ void __launch_bounds__(1024)
       const int slab = slab_of[cube];
       const int nv = cnt[slab] + len;
       cnt[slab] = nv < cap ? nv : cap;
+      clean[(corner ? 0 : kCNum) + slab] = 0;  // the cube has new points: its next VoxelGrid pass is not a no-op
     }
   }
 }
 
 // Per-cube VoxelGrid of the valid cubes: block (v, type) filters its slab into scratch and copies it back.
+// The reference re-filters all 75 valid cubes every frame (laserMapping.cpp:987-1002), most of them untouched since
+// their last pass.  A pass that changed nothing (same count, every point bit-identical) is a fixed point of a
+// deterministic function: until the cube receives a point again, filtering it is provably a no-op and is skipped
+// (clean[]: set here when a pass left the cube as it was, cleared by cube_insert_kernel).
 __global__ void __launch_bounds__(1024)
     cube_filter_kernel(const int* __restrict__ valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
-                       float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err, uint32_t* __restrict__ hscratch) {
+                       float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err, uint32_t* __restrict__ hscratch,
+                       int* __restrict__ clean, int merge_ok) {
   pdl_entry();
   extern __shared__ u64 keys[];
   const int v = blockIdx.x >> 1;
@@ -133,6 +145,8 @@ __global__ void __launch_bounds__(1024)
   int* cnt = (corner ? cnt_c : cnt_s) + slab;
   const int n = *cnt;
   if (n <= 0) return;
+  int* const cube_clean = clean + (corner ? 0 : kCNum) + slab;
+  if (*cube_clean) return;
   if (n > kVoxelBlockMax) {
     if (threadIdx.x == 0) atomicOr(err, 64);
     return;
@@ -140,13 +154,31 @@ __global__ void __launch_bounds__(1024)
   float4* out = scratch + (size_t)blockIdx.x * cap;
   int P = 1;
   while (P < n) P <<= 1;
-  // cubes that have grown large take the hash-based VoxelGrid (only the distinct voxels are sorted)
-  const int m = n > 2048 ? voxelgrid_block_hash(pts, n, corner ? leaf_c : leaf_s, reinterpret_cast<unsigned char*>(keys),
+  const float leaf = corner ? leaf_c : leaf_s;
+  // the first n_old points are what the previous pass left (one per voxel, in voxel order): merge the new ones in
+  int* const filt_n = clean + 2 * kCNum + (corner ? 0 : kCNum) + slab;
+  const int n_old = *filt_n;
+  int m = -1;
+  if (merge_ok && n_old > 0 && n_old <= n && n - n_old <= kVgMergeNew)
+    m = voxelgrid_block_merge(pts, n_old, n, leaf, reinterpret_cast<unsigned char*>(keys), out, err);
+  // otherwise: cubes that have grown large take the hash-based VoxelGrid (only the distinct voxels are sorted)
+  if (m < 0)
+    m = n > 2048 ? voxelgrid_block_hash(pts, n, corner ? leaf_c : leaf_s, reinterpret_cast<unsigned char*>(keys),
                                                 hscratch + (size_t)blockIdx.x * kVgScratchWords, out, err)
                          : voxelgrid_block(pts, n, corner ? leaf_c : leaf_s, keys, P, out, err);
   __syncthreads();
-  for (int t = threadIdx.x; t < m; t += blockDim.x) pts[t] = out[t];
-  if (threadIdx.x == 0) *cnt = m;
+  bool same = m == n;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    const float4 o = out[t];
+    if (same) {
+      const float4 p = pts[t];
+      same = __float_as_uint(o.x) == __float_as_uint(p.x) && __float_as_uint(o.y) == __float_as_uint(p.y) &&
+             __float_as_uint(o.z) == __float_as_uint(p.z) && __float_as_uint(o.w) == __float_as_uint(p.w);
+    }
+    pts[t] = o;
+  }
+  const int all_same = __syncthreads_and(same ? 1 : 0);
+  if (threadIdx.x == 0) *cnt = m, *cube_clean = all_same, *filt_n = m;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -156,10 +188,17 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
   ctx = c;
   cap = cube_cap;
   line_res = lres, plane_res = pres;
+  if (const char* e = getenv("ILSM_VG_MERGE")) vg_merge = atoi(e) != 0;  // 0: every pass takes the general VoxelGrid (A/B checks)
   int rc;
   if ((rc = map_c.init(c)) || (rc = map_s.init(c))) return rc;
+  map_c.in_line = map_s.in_line = true;  // gather -> builds -> solve is one chain on the context's stream
+  // room for a typical 5x5x3 neighbourhood up front (growth afterwards still works, at the price of a device-wide stall)
+  const int typical = 125 * cap < 262144 ? 125 * cap : 262144;
+  if ((rc = map_c.reserve_points(typical)) || (rc = map_s.reserve_points(typical)) || (rc = from_c.reserve(typical + 4)) ||
+      (rc = from_s.reserve(typical + 4)) || (rc = stack_c.reserve(kVoxelBlockMax)) || (rc = stack_s.reserve(kVoxelBlockMax)))
+    return rc;
   if ((rc = slabs_c.reserve((size_t)kCNum * cap)) || (rc = slabs_s.reserve((size_t)kCNum * cap)) ||
-      (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
+      (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = clean.reserve(4 * kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
       (rc = stack_n.reserve(4)) || (rc = valid_d.reserve(128)) || (rc = err.reserve(4)) || (rc = items.reserve(256)) ||
       (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) || (rc = hscratch.reserve((size_t)250 * kVgScratchWords)) ||
       (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)) ||
@@ -172,6 +211,7 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
   cudaStream_t s = c->stream;
   ILSM_CUDA(cudaMemsetAsync(cnt_c.p, 0, kCNum * sizeof(int), s));
   ILSM_CUDA(cudaMemsetAsync(cnt_s.p, 0, kCNum * sizeof(int), s));
+  ILSM_CUDA(cudaMemsetAsync(clean.p, 0, 4 * kCNum * sizeof(int), s));
   ILSM_CUDA(cudaMemsetAsync(err.p, 0, 4 * sizeof(int), s));
   ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
   ILSM_CUDA(cudaFuncSetAttribute(cube_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -189,7 +229,7 @@ void CubeMapH::release() {
   pin_counts.release();
   map_c.release(), map_s.release();
   slabs_c.release(), slabs_s.release(), from_c.release(), from_s.release(), stack_c.release(), stack_s.release();
-  scratch.release(), hscratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release();
+  scratch.release(), hscratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release(), clean.release();
   valid_d.release(), err.release(), zero_list.release(), items.release(), raw.release(), pin.release();
 }
 
@@ -247,11 +287,10 @@ int CubeMapH::roll(const double t[3]) {
     const int n = (int)recycled.size() < kCNum ? (int)recycled.size() : kCNum;
     for (int i = 0; i < n; ++i) p[i] = recycled[i];
     ILSM_CUDA(cudaMemcpyAsync(zero_list.p, p, n * sizeof(int), cudaMemcpyHostToDevice, s));
-    ILSM_CUDA(launch_pdl(cube_zero_counts_kernel, dim3((n + 255) / 256), dim3(256), 0, s, cnt_c.p, zero_list.p, n));
-    ILSM_CUDA(launch_pdl(cube_zero_counts_kernel, dim3((n + 255) / 256), dim3(256), 0, s, cnt_s.p, zero_list.p, n));
+    ILSM_CUDA(launch_pdl(cube_zero_counts_kernel, dim3((n + 255) / 256), dim3(256), 0, s, cnt_c.p, cnt_s.p, clean.p + 2 * kCNum, zero_list.p, n));
     ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
     ILSM_CUDA(cudaStreamSynchronize(s));
-    count_launches(2);
+    count_launches(1);
   }
   return ILSM_OK;
 }
@@ -280,7 +319,7 @@ int CubeMapH::gather(int* n_mc, int* n_ms) {
 
 int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_frame, cudaStream_t s) {
   if (!s) s = ctx->stream;
-  ILSM_CUDA(launch_pdl(cube_insert_kernel, dim3(2), dim3(1024), kVoxelBlockMax * sizeof(u64), s, stack_c.p, stack_s.p, d_counts, nc_host, ns_host, ctx->lm.p, world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p, kVoxelBlockMax, err.p));
+  ILSM_CUDA(launch_pdl(cube_insert_kernel, dim3(2), dim3(1024), kVoxelBlockMax * sizeof(u64), s, cur_stack_c(), cur_stack_s(), d_counts, nc_host, ns_host, ctx->lm.p, world_frame, cenW, cenH, cenD, slab_of_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, world_tmp.p, kVoxelBlockMax, err.p, clean.p));
   count_launches(1);
   return check_launch("cube_insert");
 }
@@ -293,7 +332,7 @@ int CubeMapH::filter_valid(cudaStream_t s) {
   ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
   // shared memory: the hash-based path's 192 KB only when a cube can be large enough to take it
   const size_t smem = cap > 2048 ? kVgHashSmemBytes : (size_t)kVoxelBlockMax * sizeof(u64);
-  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), smem, s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p, hscratch.p));
+  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), smem, s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p, hscratch.p, clean.p, vg_merge ? 1 : 0));
   count_launches(1);
   return check_launch("cube_filter");
 }
@@ -381,9 +420,9 @@ int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_
   // map builds above did not have to wait for them
   if (stacks_event) ILSM_CUDA(cudaStreamWaitEvent(c.stream, stacks_event, 0));
   if (optimise) {
-    c.d_stack_counts = m.stack_n.p;
-    rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.stack_c.p), nc, reinterpret_cast<const float*>(m.stack_s.p),
-                        ns, 16, o);
+    c.d_stack_counts = m.cur_stack_n();
+    rc = c.register_dev(&m.map_c, &m.map_s, reinterpret_cast<const float*>(m.cur_stack_c()), nc,
+                        reinterpret_cast<const float*>(m.cur_stack_s()), ns, 16, o);
     c.d_stack_counts = nullptr;
     if (rc) return rc;
   }
@@ -394,13 +433,13 @@ int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_
   int* pin_i = m.pin.p + kCNum + 2048;
   ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.stack_n.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.cur_stack_n(), 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   cudaStream_t ts = defer_tail ? c.aux : c.stream;
   if (defer_tail) {
     ILSM_CUDA(cudaEventRecord(c.ev_fork, c.stream));
     ILSM_CUDA(cudaStreamWaitEvent(c.aux, c.ev_fork, 0));
   }
-  if ((rc = m.insert(m.stack_n.p, 0, 0, 0, ts)) || (rc = m.filter_valid(ts)) || (rc = m.fetch_counts(ts))) return rc;
+  if ((rc = m.insert(m.cur_stack_n(), 0, 0, 0, ts)) || (rc = m.filter_valid(ts)) || (rc = m.fetch_counts(ts))) return rc;
   if (defer_tail) {
     ILSM_CUDA(cudaEventRecord(m.ev_tail, c.aux));
     m.tail_pending = true;

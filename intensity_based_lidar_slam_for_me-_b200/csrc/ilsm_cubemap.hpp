@@ -43,6 +43,17 @@ struct CubeMapH {
   DevBuf<float4> slabs_c, slabs_s, from_c, from_s, stack_c, stack_s, scratch, world_tmp;
   DevBuf<uint32_t> hscratch;  // hash-based VoxelGrid scratch, one slice per cube_filter block
   DevBuf<int> cnt_c, cnt_s, slab_of_d, stack_n, valid_d, err, zero_list;
+  // per slab and cloud kind: [0, 2 kCNum) the last VoxelGrid pass left the cube unchanged and nothing was inserted since;
+  // [2 kCNum, 4 kCNum) how many leading points of the cube are the output of its last pass (merge precondition)
+  DevBuf<int> clean;
+  bool vg_merge = true;
+  // stacks produced outside (staged full-loop pipeline: two sets, alternating by frame, written on the odometry stage's
+  // side stream): when set, the frame being enqueued -- solve and deferred insertion -- reads these instead of stack_*
+  const float4 *ext_c = nullptr, *ext_s = nullptr;
+  const int* ext_n = nullptr;
+  const float4* cur_stack_c() const { return ext_c ? ext_c : stack_c.p; }
+  const float4* cur_stack_s() const { return ext_s ? ext_s : stack_s.p; }
+  const int* cur_stack_n() const { return ext_n ? ext_n : stack_n.p; }
   DevBuf<GatherItem> items;
   DevBuf<float> raw;
   PinnedBuf<int> pin;

@@ -151,6 +151,10 @@ struct Map {
   // Each map builds on its own stream so that the corner and surf structures of a frame are built concurrently
   // (and their H2D copies overlap); users on the context stream wait on `ready`.
   cudaStream_t stream = nullptr;
+  // builds run in line on the context's stream, with no fork / join events: for callers whose builds have nothing to
+  // overlap with (the cube map's two search structures sit on the mapping stage's critical path, and every event call is
+  // host time there)
+  bool in_line = false;
   cudaEvent_t ready = nullptr, ctx_done = nullptr;
   bool pending = false;
 
@@ -164,6 +168,9 @@ struct Map {
   int wait_ready(cudaStream_t user);
   int build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size);
   int prepare_build(const float* d_src, int n_pts, int stride_bytes, float cell_size, cudaStream_t s, void* job_out);
+  // allocate for builds of up to n_pts points now (a buffer that grows later costs a device-wide synchronisation); only
+  // while no build is in flight
+  int reserve_points(int n_pts);
   const GridCell* cur_cells() const { return cells.p + (size_t)cur * table_cap; }
   const uint32_t* cur_occ() const { return occ.p + (size_t)cur * occ_cap; }
   const uint32_t* cur_counters() const { return counters.p + 8 * cur; }

@@ -209,38 +209,45 @@ static __device__ int voxelgrid_block(const float4* __restrict__ pts, int m, flo
 // ---------------------------------------------------------------------------------------------------
 // The same VoxelGrid without sorting the points: PCL orders its OUTPUT by voxel index and sums every voxel's points in
 // input order, so only the distinct voxels have to be sorted (a stack of ~9 k less-flat points falls into ~2 k voxels of
-// 0.8 m) and each voxel's few members by index.
+// 0.8 m) and each voxel's members ranked by index.
 //   1. bounding box -> voxel index per point (as above)
 //   2. open-addressing hash of the voxel indices in shared memory (32768 slots): slot per point by atomicCAS, arrival
 //      rank inside the voxel by atomicAdd (16-bit counters, two per word)
-//   3. the occupied slots are compacted into a list (voxel index << 15 | slot) and sorted: ascending voxel index
+//   3. the occupied slots are compacted into a list (voxel index << 15 | slot; one atomic per warp) and sorted: ascending
+//      voxel index
 //   4. exclusive scan of the voxel populations in that order -> where each voxel's member list starts
-//   5. every point drops its index into its voxel's list at its arrival rank (arbitrary order)
-//   6. one thread per voxel sorts its member list by index (insertion / shell sort: lists are short) and adds the
-//      members up in that order -- the float sums of pcl::CentroidPoint, bit for bit
+//   5. every point drops its index into its voxel's list at its arrival rank (arbitrary order), then finds its place in
+//      INDEX order by counting the smaller members of its list (all points in parallel, independent shared-memory
+//      reads -- no per-voxel serial sort) and copies itself there: the points end up grouped by voxel, in input order
+//   6. the float sums of pcl::CentroidPoint, bit for bit, over those contiguous runs: one thread per voxel for the short
+//      runs, one warp per voxel for the long ones (32 coalesced loads in flight, the sequential adds fed by shuffles)
 // Shared memory: smem must provide kVgHashSmemBytes (192 KB); scratch = kVgScratchWords 32-bit words of global memory per
 // block.  m <= kVoxelBlockMax.  Returns the number of voxels (block-uniform).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kVgHashSlots = 32768;
 constexpr size_t kVgHashSmemBytes = (size_t)kVgHashSlots * 4 + (size_t)kVgHashSlots * 2;  // keys (reused: sort keys, member lists) + counters
-constexpr size_t kVgScratchWords = (size_t)kVoxelBlockMax + kVgHashSlots + 2 * (size_t)kVoxelBlockMax + kVoxelBlockMax;
+constexpr size_t kVgScratchWords = (size_t)kVoxelBlockMax + kVgHashSlots + 2 * (size_t)kVoxelBlockMax + kVoxelBlockMax + 4 * (size_t)kVoxelBlockMax;
+constexpr int kVgWarpRun = 16;  // runs longer than this are summed by a whole warp
 
 static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m, float leaf, unsigned char* smem, uint32_t* __restrict__ scratch,
                                            float4* __restrict__ out, int* err) {
   __shared__ float s_min[3], s_max[3];
-  __shared__ int s_V, s_carry;
+  __shared__ int s_V, s_carry, s_heavy;
   __shared__ int wc[32];
   uint32_t* hkeys = reinterpret_cast<uint32_t*>(smem);                       // region A, first life: the hash keys
   u64* skeys = reinterpret_cast<u64*>(smem);                                 // region A, second life: the voxel sort keys
   unsigned short* members = reinterpret_cast<unsigned short*>(smem);         // region A, third life: the member lists
   uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem + (size_t)kVgHashSlots * 4);  // region B: two 16-bit counters per word
+  unsigned short* heavy = reinterpret_cast<unsigned short*>(cnt32);          // region B, second life: voxels with long runs
   uint32_t* g_sr = scratch;                                       // per point: slot << 16 | arrival rank (0xFFFFFFFF: skipped)
   uint32_t* g_sp = scratch + kVoxelBlockMax;                      // per slot: list start << 16 | output position
   u64* g_list = reinterpret_cast<u64*>(scratch + kVoxelBlockMax + kVgHashSlots);  // compacted (voxel << 15 | slot)
   uint32_t* g_vinfo = scratch + kVoxelBlockMax + kVgHashSlots + 2 * kVoxelBlockMax;  // per output voxel: start << 16 | count
+  float4* g_run = reinterpret_cast<float4*>(scratch + kVoxelBlockMax + kVgHashSlots + 3 * (size_t)kVoxelBlockMax);  // points by (voxel, index)
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   if (tid < 3) s_min[tid] = __int_as_float(0x7f800000), s_max[tid] = __int_as_float(0xff800000);
-  if (tid == 0) s_V = 0, s_carry = 0;
+  if (tid == 0) s_V = 0, s_carry = 0, s_heavy = 0;
   for (int i = tid; i < kVgHashSlots; i += nt) hkeys[i] = 0xFFFFFFFFu;
   for (int i = tid; i < kVgHashSlots / 2; i += nt) cnt32[i] = 0u;
   __syncthreads();
@@ -261,7 +268,7 @@ static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
     }
   }
-  if ((tid & 31) == 0) {
+  if (lane == 0) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       int* pmn = reinterpret_cast<int*>(&s_min[a]);
@@ -305,10 +312,16 @@ static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m
     g_sr[t] = sr;
   }
   __syncthreads();
-  // ---- 3. occupied slots -> list, sorted by voxel index
-  for (int sl = tid; sl < kVgHashSlots; sl += nt) {
+  // ---- 3. occupied slots -> list (one shared-memory atomic per warp and pass), sorted by voxel index
+  for (int sl0 = 0; sl0 < kVgHashSlots; sl0 += nt) {
+    const int sl = sl0 + tid;
     const uint32_t key = hkeys[sl];
-    if (key != 0xFFFFFFFFu) g_list[atomicAdd(&s_V, 1)] = ((u64)key << 15) | (u64)sl;
+    const bool occ = key != 0xFFFFFFFFu;
+    const unsigned b = __ballot_sync(0xffffffffu, occ);
+    int wbase = 0;
+    if (lane == 0 && b) wbase = atomicAdd(&s_V, __popc(b));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (occ) g_list[wbase + __popc(b & ((1u << lane) - 1u))] = ((u64)key << 15) | (u64)sl;
   }
   __syncthreads();
   const int V = s_V;
@@ -318,7 +331,6 @@ static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m
   __syncthreads();
   bitonic_sort_smem(skeys, Pv);
   // ---- 4. exclusive scan of the populations in output order
-  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   for (int j0 = 0; j0 < Pv; j0 += nt) {
     const int j = j0 + tid;
     uint32_t slot = 0;
@@ -350,50 +362,260 @@ static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m
     __syncthreads();
   }
   __threadfence_block();
-  // ---- 5. member lists (region A changes hands again: the sort keys are consumed)
+  // ---- 5. member lists (region A changes hands again: the sort keys are consumed) ...
   for (int t = tid; t < m; t += nt) {
     const uint32_t sr = g_sr[t];
     if (sr != 0xFFFFFFFFu) members[(g_sp[sr >> 16] >> 16) + (sr & 0xFFFFu)] = (unsigned short)t;
   }
   __syncthreads();
-  // ---- 6. per voxel: members by index, then the ordered float sums
+  // ... and every point to its place in (voxel, index) order; the long runs are queued for the warps (region B is free)
+  for (int t = tid; t < m; t += nt) {
+    const uint32_t sr = g_sr[t];
+    if (sr == 0xFFFFFFFFu) continue;
+    const uint32_t sp = g_sp[sr >> 16];
+    const int start = (int)(sp >> 16), c = (int)(g_vinfo[sp & 0xFFFFu] & 0xFFFFu);
+    int rank = 0;
+    if (c > 1) {
+      const unsigned short* L = members + start;
+      int u = 0;
+      if ((start & 1) && c > 0) rank += L[0] < t, u = 1;  // align to a 32-bit word, then two members per load
+      for (; u + 1 < c; u += 2) {
+        const uint32_t w2 = *reinterpret_cast<const uint32_t*>(L + u);
+        rank += (int)((w2 & 0xFFFFu) < (uint32_t)t) + (int)((w2 >> 16) < (uint32_t)t);
+      }
+      if (u < c) rank += L[u] < t;
+    }
+    g_run[start + rank] = pts[t];
+  }
+  for (int j = tid; j < V; j += nt)
+    if ((int)(g_vinfo[j] & 0xFFFFu) > kVgWarpRun) heavy[atomicAdd(&s_heavy, 1)] = (unsigned short)j;
+  __syncthreads();
+  // ---- 6. the ordered float sums: short runs, one thread per voxel
   for (int j = tid; j < V; j += nt) {
     const uint32_t vi = g_vinfo[j];
     const int start = (int)(vi >> 16), c = (int)(vi & 0xFFFFu);
-    unsigned short* L = members + start;
-    if (c <= 24) {
-      for (int a = 1; a < c; ++a) {
-        const unsigned short x = L[a];
-        int b = a - 1;
-        while (b >= 0 && L[b] > x) L[b + 1] = L[b], --b;
-        L[b + 1] = x;
-      }
-    } else {
-      const int gaps[8] = {701, 301, 132, 57, 23, 10, 4, 1};
-      for (int gi = 0; gi < 8; ++gi) {
-        const int gap = gaps[gi];
-        for (int a = gap; a < c; ++a) {
-          const unsigned short x = L[a];
-          int b = a;
-          while (b >= gap && L[b - gap] > x) L[b] = L[b - gap], b -= gap;
-          L[b] = x;
-        }
-      }
-    }
+    if (c > kVgWarpRun) continue;
+    const float4* R = g_run + start;
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    for (int e0 = 0; e0 < c; e0 += 4) {  // 4 gathers in flight, then the 4 sequential float adds (PCL's order)
-      float4 q[4];
+    for (int e0 = 0; e0 < c; e0 += 8) {  // 8 loads in flight, then the sequential float adds (PCL's order)
+      float4 q[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) q[k] = e0 + k < c ? pts[L[e0 + k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 8; ++k) q[k] = e0 + k < c ? R[e0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < 8; ++k)
         if (e0 + k < c) sx = __fadd_rn(sx, q[k].x), sy = __fadd_rn(sy, q[k].y), sz = __fadd_rn(sz, q[k].z), si = __fadd_rn(si, q[k].w);
     }
     const float cf = (float)c;
     out[j] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
   }
+  // long runs, one warp per voxel: 32 coalesced loads per round (the next round's already in flight), every lane adds
+  // the members up in order from shuffles
+  const int H = s_heavy;
+  for (int h = warp; h < H; h += nw) {
+    const int j = heavy[h];
+    const uint32_t vi = g_vinfo[j];
+    const int start = (int)(vi >> 16), c = (int)(vi & 0xFFFFu);
+    const float4* R = g_run + start;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    float4 nxt = lane < c ? R[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = 0; e0 < c; e0 += 32) {
+      const float4 q = nxt;
+      if (e0 + 32 + lane < c) nxt = R[e0 + 32 + lane];
+      const int lim = c - e0 < 32 ? c - e0 : 32;
+      for (int l = 0; l < lim; ++l) {
+        sx = __fadd_rn(sx, __shfl_sync(0xffffffffu, q.x, l)), sy = __fadd_rn(sy, __shfl_sync(0xffffffffu, q.y, l));
+        sz = __fadd_rn(sz, __shfl_sync(0xffffffffu, q.z, l)), si = __fadd_rn(si, __shfl_sync(0xffffffffu, q.w, l));
+      }
+    }
+    if (lane == 0) {
+      const float cf = (float)c;
+      out[j] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
+    }
+  }
   __syncthreads();
   return V;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// VoxelGrid of a cloud whose first n_old points are the OUTPUT of an earlier VoxelGrid pass at the same leaf size (a
+// map cube between two frames: laserMapping.cpp:987-1002 re-filters it after every insertion) followed by n - n_old new
+// points.  PCL's result is independent per voxel and ordered by voxel index, and the relative order of two voxel
+// indices does not depend on the bounding box, so when the old points still sit one per voxel in ascending voxel order
+// (checked -- a centroid that rounded across a voxel face sends the block to the general path) the pass is a MERGE:
+//   * only the new points are sorted, by (voxel, index);
+//   * every distinct new voxel finds its old centroid by binary search -- present: that centroid (lowest index, summed
+//     first) plus the new members; absent: a new output voxel;
+//   * every untouched old point moves up by the number of new voxels below it (one binary search), its value passing
+//     through the same float operations as a one-member voxel, (0 + p) / 1.
+// Bit-identical to the general path by construction; O(n log m) instead of a hash + sort of everything.
+// Shared memory: 64 KB of old keys + 16 KB of new sort keys + 20 KB of per-new-voxel tables.  Returns the number of
+// voxels, or -1 (block-uniform) when the preconditions do not hold.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kVgMergeNew = 2048;
+
+static __device__ __forceinline__ int block_excl_scan_1024(int v, int* wc, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += o;
+  }
+  __syncthreads();  // wc may still be read from the previous call
+  if (lane == 31) wc[warp] = inc;
+  __syncthreads();
+  int wbase = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) {
+    if (w < warp) wbase += wc[w];
+    tot += wc[w];
+  }
+  *total = tot;
+  return wbase + inc - v;
+}
+
+static __device__ int voxelgrid_block_merge(const float4* __restrict__ pts, int n_old, int n, float leaf, unsigned char* smem,
+                                            float4* __restrict__ out, int* err) {
+  __shared__ float s_min[3], s_max[3];
+  __shared__ int wc[32];
+  uint32_t* ek = reinterpret_cast<uint32_t*>(smem);                                     // old keys (ascending when valid)
+  u64* nk = reinterpret_cast<u64*>(smem + (size_t)kVoxelBlockMax * 4);                  // new (voxel << 24 | position)
+  uint32_t* dkey = reinterpret_cast<uint32_t*>(smem + (size_t)kVoxelBlockMax * 4 + (size_t)kVgMergeNew * 8);  // distinct new voxels
+  unsigned short* dstart = reinterpret_cast<unsigned short*>(dkey + kVgMergeNew);       // first member of each in nk (+ end)
+  unsigned short* dexcl = dstart + kVgMergeNew + 2;                                     // new-only voxels before each (+ total)
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int m = n - n_old;
+  if (tid < 3) s_min[tid] = __int_as_float(0x7f800000), s_max[tid] = __int_as_float(0xff800000);
+  __syncthreads();
+  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
+  int bad = 0;
+  for (int t = tid; t < n; t += nt) {
+    const float4 p = pts[t];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      mn[0] = fminf(mn[0], p.x), mn[1] = fminf(mn[1], p.y), mn[2] = fminf(mn[2], p.z);
+      mx[0] = fmaxf(mx[0], p.x), mx[1] = fmaxf(mx[1], p.y), mx[2] = fmaxf(mx[2], p.z);
+    } else {
+      bad = 1;  // the general path knows how to skip points
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int* pmn = reinterpret_cast<int*>(&s_min[a]);
+      int* pmx = reinterpret_cast<int*>(&s_max[a]);
+      if (mn[a] >= 0.f) atomicMin(pmn, __float_as_int(mn[a])); else atomicMax(reinterpret_cast<unsigned*>(pmn), __float_as_uint(mn[a]));
+      if (mx[a] >= 0.f) atomicMax(pmx, __float_as_int(mx[a])); else atomicMin(reinterpret_cast<unsigned*>(pmx), __float_as_uint(mx[a]));
+    }
+  }
+  if (__syncthreads_or(bad)) return -1;
+  const float inv = __fdiv_rn(1.0f, leaf);
+  int min_b[3], div_b[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = __float2int_rd(__fmul_rn(s_min[a], inv));
+    div_b[a] = __float2int_rd(__fmul_rn(s_max[a], inv)) - min_b[a] + 1;
+  }
+  const long long mul1 = div_b[0], mul2 = (long long)div_b[0] * div_b[1];
+  if (mul2 * div_b[2] >= (1ll << 31)) {  // pcl: "Leaf size is too small for the input dataset"
+    if (tid == 0) atomicOr(err, 2);
+    return 0;
+  }
+  int P = 32;
+  while (P < m) P <<= 1;
+  for (int t = tid; t < n_old + P; t += nt) {
+    uint32_t idx = 0xFFFFFFFFu;
+    if (t < n) {
+      const float4 p = pts[t];
+      const int i0 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)min_b[0]));
+      const int i1 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)min_b[1]));
+      const int i2 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)min_b[2]));
+      idx = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
+    }
+    if (t < n_old) ek[t] = idx;
+    else nk[t - n_old] = t < n ? (((u64)idx << 24) | (u64)(t - n_old)) : ~0ull;
+  }
+  __syncthreads();
+  for (int t = tid + 1; t < n_old; t += nt) bad |= ek[t - 1] >= ek[t];
+  if (__syncthreads_or(bad)) return -1;
+  bitonic_sort_smem(nk, P);
+  // distinct new voxels
+  int D = 0;
+  for (int i0 = 0; i0 < m; i0 += nt) {
+    const int i = i0 + tid;
+    const bool head = i < m && (i == 0 || (nk[i] >> 24) != (nk[i - 1] >> 24));
+    int tot;
+    const int d = D + block_excl_scan_1024(head ? 1 : 0, wc, &tot);
+    if (head) dkey[d] = (uint32_t)(nk[i] >> 24), dstart[d] = (unsigned short)i;
+    D += tot;
+  }
+  if (tid == 0) dstart[D] = (unsigned short)m;
+  __syncthreads();
+  // each distinct new voxel against the old keys; new-only voxels open an output slot
+  int n_newonly = 0;
+  for (int d0 = 0; d0 < D; d0 += nt) {
+    const int d = d0 + tid;
+    int pos = 0;
+    bool exists = false;
+    uint32_t key = 0;
+    if (d < D) {
+      key = dkey[d];
+      int lo = 0, hi = n_old;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ek[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      pos = lo;
+      exists = pos < n_old && ek[pos] == key;
+    }
+    int tot;
+    const int before = n_newonly + block_excl_scan_1024(d < D && !exists ? 1 : 0, wc, &tot);
+    if (d < D) {
+      dexcl[d] = (unsigned short)before;
+      const int b = dstart[d], c = (int)dstart[d + 1] - b;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      if (exists) {
+        const float4 e = pts[pos];
+        sx = __fadd_rn(sx, e.x), sy = __fadd_rn(sy, e.y), sz = __fadd_rn(sz, e.z), si = __fadd_rn(si, e.w);
+      }
+      for (int e0 = 0; e0 < c; e0 += 4) {
+        float4 q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          q[k] = e0 + k < c ? pts[n_old + (int)(nk[b + e0 + k] & 0xFFFFFFull)] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (e0 + k < c) sx = __fadd_rn(sx, q[k].x), sy = __fadd_rn(sy, q[k].y), sz = __fadd_rn(sz, q[k].z), si = __fadd_rn(si, q[k].w);
+      }
+      const float cf = (float)(c + (exists ? 1 : 0));
+      out[pos + before] = make_float4(__fdiv_rn(sx, cf), __fdiv_rn(sy, cf), __fdiv_rn(sz, cf), __fdiv_rn(si, cf));
+    }
+    n_newonly += tot;
+  }
+  if (tid == 0) dexcl[D] = (unsigned short)n_newonly;
+  __syncthreads();
+  // the untouched old points
+  for (int t = tid; t < n_old; t += nt) {
+    const uint32_t key = ek[t];
+    int lo = 0, hi = D;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (dkey[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < D && dkey[lo] == key) continue;  // summed with its new members above
+    const float4 p = pts[t];
+    out[t + dexcl[lo]] = make_float4(__fdiv_rn(__fadd_rn(0.f, p.x), 1.f), __fdiv_rn(__fadd_rn(0.f, p.y), 1.f),
+                                     __fdiv_rn(__fadd_rn(0.f, p.z), 1.f), __fdiv_rn(__fadd_rn(0.f, p.w), 1.f));
+  }
+  __syncthreads();
+  return n_old + n_newonly;
 }
 
 }  // namespace ilsm

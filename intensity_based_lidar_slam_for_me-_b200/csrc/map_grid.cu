@@ -361,6 +361,24 @@ int Map::prepare_build(const float* d_src, int n_pts, int stride_bytes, float ce
   return ILSM_OK;
 }
 
+int Map::reserve_points(int n_pts) {
+  if (n_pts <= 0) return ILSM_OK;
+  int want_log2 = ilog2_ceil(2u * (uint32_t)n_pts);
+  if (want_log2 < 10) want_log2 = 10;
+  const uint32_t want_size = 1u << want_log2;
+  const uint32_t new_cap = want_size > table_cap ? want_size : table_cap;
+  const size_t new_occ_cap = (size_t)n_pts + 1 > occ_cap ? (size_t)n_pts + (size_t)n_pts / 2 + 64 : occ_cap;
+  if (new_cap == table_cap && new_occ_cap == occ_cap && sorted.cap >= (size_t)n_pts + 1) return ILSM_OK;
+  int rc;
+  if ((rc = cells.reserve((size_t)2 * new_cap)) || (rc = sorted.reserve(n_pts + 1)) || (rc = orig.reserve(n_pts + 1)) ||
+      (rc = slot_of.reserve(n_pts + 1)) || (rc = rank_of.reserve(n_pts + 1)) || (rc = bbox.reserve(16)) ||
+      (rc = counters.reserve(16)) || (rc = occ.reserve(2 * new_occ_cap)))
+    return rc;
+  table_cap = new_cap, occ_cap = new_occ_cap;
+  clean_size[0] = clean_size[1] = 0, filled_n[0] = filled_n[1] = 0;  // nothing is known about the new memory
+  return ILSM_OK;
+}
+
 static int launch_build(BuildJobs& jobs, int n_jobs, cudaStream_t s) {
   const int b0 = jobs.j[0].blocks, b1 = n_jobs > 1 ? jobs.j[1].blocks : 0;
   jobs.nb0 = n_jobs > 1 ? b0 : 0x7fffffff;  // a single job owns every block
@@ -377,6 +395,16 @@ static int launch_build(BuildJobs& jobs, int n_jobs, cudaStream_t s) {
 }
 
 int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_size) {
+  if (in_line) {
+    cudaStream_t cs = ctx->stream;
+    if (pending) ILSM_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+    pending = false;
+    BuildJobs jobs = {};
+    int rc = prepare_build(d_src, n_pts, stride_bytes, cell_size, cs, &jobs.j[0]);
+    if (rc) return rc;
+    if ((rc = launch_build(jobs, 1, cs))) return rc;
+    return check_launch("map_build");
+  }
   cudaStream_t s = stream;
   // order this (re)build after everything already enqueued on the context stream (previous users of the map,
   // producers of d_src), then run it on the map's own stream
@@ -397,19 +425,28 @@ int Map::build_dev(const float* d_src, int n_pts, int stride_bytes, float cell_s
 int build_pair_dev(Map* a, const float* d_a, int na, Map* b, const float* d_b, int nb, int stride_bytes, float cell_size) {
   if (!a || !b || a == b || a->ctx != b->ctx) return fail(ILSM_ERR_INVALID_ARG, "map_build_pair: two maps of one context expected");
   Ctx* ctx = a->ctx;
-  cudaStream_t s = a->stream;
-  ILSM_CUDA(cudaEventRecord(a->ctx_done, ctx->stream));
-  ILSM_CUDA(cudaStreamWaitEvent(s, a->ctx_done, 0));
-  if (a->pending) ILSM_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // earlier builds may have run on another stream
-  if (b->pending) ILSM_CUDA(cudaStreamWaitEvent(s, b->ready, 0));
+  const bool in_line = a->in_line && b->in_line;
+  cudaStream_t s = in_line ? ctx->stream : a->stream;
+  if (in_line) {
+    if (a->pending) ILSM_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // (a build made before the maps were set in line)
+    if (b->pending) ILSM_CUDA(cudaStreamWaitEvent(s, b->ready, 0));
+    a->pending = b->pending = false;
+  } else {
+    ILSM_CUDA(cudaEventRecord(a->ctx_done, ctx->stream));
+    ILSM_CUDA(cudaStreamWaitEvent(s, a->ctx_done, 0));
+    if (a->pending) ILSM_CUDA(cudaStreamWaitEvent(s, a->ready, 0));  // earlier builds may have run on another stream
+    if (b->pending) ILSM_CUDA(cudaStreamWaitEvent(s, b->ready, 0));
+  }
   BuildJobs jobs = {};
   int rc;
   if ((rc = a->prepare_build(d_a, na, stride_bytes, cell_size, s, &jobs.j[0])) || (rc = b->prepare_build(d_b, nb, stride_bytes, cell_size, s, &jobs.j[1])))
     return rc;
   if ((rc = launch_build(jobs, 2, s))) return rc;
-  ILSM_CUDA(cudaEventRecord(a->ready, s));
-  ILSM_CUDA(cudaEventRecord(b->ready, s));
-  a->pending = b->pending = true;
+  if (!in_line) {
+    ILSM_CUDA(cudaEventRecord(a->ready, s));
+    ILSM_CUDA(cudaEventRecord(b->ready, s));
+    a->pending = b->pending = true;
+  }
   return check_launch("map_build_pair");
 }
 

@@ -7,10 +7,13 @@
 // the only upload, the two poses and a few counters the only downloads.  Host synchronisation points per frame: the
 // feature counts (sizes of the next launches), the odometry pose (the host owns q_w_curr / t_w_curr and the cube
 // window indices, as the reference nodes do) and the mapped pose.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <new>
 #include <thread>
 
@@ -43,28 +46,74 @@ struct SlamH {
   // asynchronous mapping (ilsm_slam_create_async): the cube map lives on a second, owned context; the mapping of frame k
   // runs there while the front end and the odometry of frame k + 1 run on the caller's context
   ilsm_ctx* ctx2 = nullptr;
-  bool async = false, map_in_flight = false;
+  bool async = false;
   DevBuf<float4> lsharp2[2], lflat2[2];  // per-frame copies of the mapping stage's inputs (frame parity)
   cudaEvent_t ev_fe[2] = {nullptr, nullptr};
   // The mapping stage has its own host thread, like the reference's laserMapping node has its own process: its ~25
   // launches per frame (3-4 us of host time each) are issued while the caller's thread launches the next front end.
   struct MapJob {
-    int slot = 0, n_lsharp = 0, n_lflat = 0;
+    int n_lsharp = 0, n_lflat = 0;
+    const float4 *d_lsharp = nullptr, *d_lflat = nullptr;  // this frame's copies of the two feature clouds
+    cudaEvent_t ev_in = nullptr;                           // recorded once those copies are written
+    int stack_set = -1;  // staged mode: which of the two stack sets (SlamH::stk) holds this frame's down-sampled stacks
     double q_odom[4] = {0, 0, 0, 1}, t_odom[3] = {0, 0, 0};
-  } job;
+    long long frame = -1;
+  };
   struct MapResult {
     int rc = 0;
     char err[256] = "";
     double q[4] = {0, 0, 0, 1}, t[3] = {0, 0, 0};
     ilsm_reg_report report;
     ilsm_cubemap_stats cstats;
-  } result;
+    long long frame = -1;
+  };
+  // jobs and results queue up (at most two of each: the staged loop posts frame k before it collects frame k - 1, so the
+  // mapping thread goes from one frame to the next without a round trip through the caller)
+  std::deque<MapJob> jobs;
+  std::deque<MapResult> results;
   std::thread worker;
   std::mutex wmu;
   std::condition_variable wcv;
-  bool job_posted = false, result_ready = false, stop = false;
+  bool stop = false;
+  int maps_in_flight = 0;
+  // staged mode (ilsm_slam_create_staged): the three nodes as three stages, each with its own context (streams, scratch)
+  // and host thread like the reference's three processes -- scanRegistration on ctx0 + fworker, laserOdometry on the
+  // caller's context and thread, laserMapping on ctx2 + worker.  Frame k's front end, frame k-1's odometry and frame
+  // k-2's / k-1's mapping are in flight together.  The inter-stage clouds live in three rotating slots (frame % 3): a
+  // slot is rewritten by the front end of frame k + 3, after the mapped pose of frame k has been handed out.
+  ilsm_ctx* ctx0 = nullptr;
+  bool staged = false, fe_in_flight = false;
+  struct FeSlot {
+    DevBuf<float4> sharp, flat, lsharp, lflat;
+    cudaEvent_t ev = nullptr;
+  } fslot[3];
+  struct FeJob {
+    const float* xyzi = nullptr;
+    int n = 0, stride = 16, use_aloam = 1;
+    long long frame = 0;
+  } fjob;
+  struct FeResult {
+    int rc = 0, use_aloam = 1;
+    char err[256] = "";
+    int counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long frame = 0;
+  } fres;
+  std::thread fworker;
+  std::mutex fmu;
+  std::condition_variable fcv;
+  bool fjob_posted = false, fres_ready = false, fstop = false;
+  long long pushed = 0;
+  // the two mapping stacks (VoxelGrid of the less-sharp / less-flat clouds, laserMapping.cpp:608-616), double-buffered:
+  // the odometry stage's side stream writes set k & 1 for frame k under its solve while the mapping of frame k - 1 (solve
+  // and deferred insertion) still reads the other one
+  struct StackSet {
+    DevBuf<float4> c, s;
+    DevBuf<int> n;
+    cudaEvent_t ev_ready = nullptr, ev_free = nullptr;  // stacks written / last reader (deferred insertion) enqueued
+    bool free_recorded = false;
+  } stk[2];
   // host-side phase clock (profiling aid, read with ilsm_slam_host_phases): seconds accumulated per phase
-  double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double phase_s[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [8..] mapping-stage detail (ILSM_STAGE_TRACE)
 };
 
 struct PhaseClock {
@@ -87,24 +136,35 @@ static void mapping_worker(SlamH* sp) {
     SlamH::MapJob j;
     {
       std::unique_lock<std::mutex> lk(s.wmu);
-      s.wcv.wait(lk, [&] { return s.job_posted || s.stop; });
-      if (s.stop) return;
-      j = s.job;
-      s.job_posted = false;
+      s.wcv.wait(lk, [&] { return !s.jobs.empty() || s.stop; });
+      if (s.jobs.empty()) return;  // (stop is only raised once the queue has drained)
+      j = s.jobs.front();
+      s.jobs.pop_front();
     }
     SlamH::MapResult r;
+    r.frame = j.frame;
     {
       std::lock_guard<std::mutex> lk2(c2.mu);
       ilsm_reg_opts mo;
       ilsm_reg_opts_default(&mo);
       memset(&r.report, 0, sizeof(r.report)), memset(&r.cstats, 0, sizeof(r.cstats));
-      cudaError_t e = cudaStreamWaitEvent(c2.stream, s.ev_fe[j.slot], 0);
+      cudaError_t e = cudaStreamWaitEvent(c2.stream, j.ev_in, 0);
       r.rc = e == cudaSuccess ? ILSM_OK : fail_cuda(e, "cudaStreamWaitEvent(mapping stage)");
       PhaseClock wclk(s.phase_s);  // [6] mapping-stage launches, [7] wait for the mapped pose (written by this thread only)
-      if (!r.rc)
-        r.rc = cubemap_frame_enqueue(s.cube->m, reinterpret_cast<const float*>(s.lsharp2[j.slot].p), j.n_lsharp,
-                                     reinterpret_cast<const float*>(s.lflat2[j.slot].p), j.n_lflat, 16, j.q_odom, j.t_odom, mo, true, true,
-                                     s.ctx->ev_join);  // the stacks come from the caller's side stream (under its odometry)
+      CubeMapH& cm = s.cube->m;
+      SlamH::StackSet* set = j.stack_set >= 0 ? &s.stk[j.stack_set] : nullptr;
+      if (set) cm.ext_c = set->c.p, cm.ext_s = set->s.p, cm.ext_n = set->n.p;
+      if (!r.rc) r.rc = cm.wait_tail();
+      wclk.lap(8);  // wait for the previous frame's deferred insertion
+      if (!r.rc)  // the stacks come from the odometry stage's side stream (written under its solve)
+        r.rc = cubemap_frame_enqueue(cm, reinterpret_cast<const float*>(j.d_lsharp), j.n_lsharp,
+                                     reinterpret_cast<const float*>(j.d_lflat), j.n_lflat, 16, j.q_odom, j.t_odom, mo, true, true,
+                                     set ? set->ev_ready : s.ctx->ev_join);
+      if (!r.rc && set) {  // the deferred insertion (side stream) is the set's last reader
+        e = cudaEventRecord(set->ev_free, c2.aux);
+        if (e != cudaSuccess) r.rc = fail_cuda(e, "cudaEventRecord(stack set)");
+        set->free_recorded = true;
+      }
       wclk.lap(6);
       if (!r.rc) r.rc = cubemap_frame_collect(s.cube->m, r.q, r.t, &r.report, &r.cstats);
       wclk.lap(7);
@@ -112,24 +172,99 @@ static void mapping_worker(SlamH* sp) {
     }
     {
       std::lock_guard<std::mutex> lk(s.wmu);
-      s.result = r;
-      s.result_ready = true;
+      s.results.push_back(r);
     }
     s.wcv.notify_all();
   }
 }
 
-// wait for the mapping stage's answer to the job in flight and hand it out
-static int take_mapping_result(SlamH& s, double q_map[4], double t_map[3], ilsm_slam_stats* stats) {
+static void post_mapping_job(SlamH& s, const SlamH::MapJob& j) {
+  {
+    std::lock_guard<std::mutex> lk(s.wmu);
+    s.jobs.push_back(j);
+  }
+  s.maps_in_flight++;
+  s.wcv.notify_all();
+}
+
+// wait for the mapping stage's answer to its oldest job and hand it out
+static int take_mapping_result(SlamH& s, double q_map[4], double t_map[3], ilsm_slam_stats* stats, long long* frame = nullptr) {
   std::unique_lock<std::mutex> lk(s.wmu);
-  s.wcv.wait(lk, [&] { return s.result_ready; });
-  s.result_ready = false;
-  s.map_in_flight = false;
-  const SlamH::MapResult& r = s.result;
+  s.wcv.wait(lk, [&] { return !s.results.empty(); });
+  const SlamH::MapResult r = s.results.front();
+  s.results.pop_front();
+  lk.unlock();
+  s.maps_in_flight--;
+  if (frame) *frame = r.frame;
   if (r.rc) return fail(r.rc, r.err);
   for (int i = 0; i < 4; ++i) q_map[i] = r.q[i];
   for (int i = 0; i < 3; ++i) t_map[i] = r.t[i];
   if (stats) stats->mapping = r.report, stats->cubemap = r.cstats;
+  return ILSM_OK;
+}
+
+// ---- staged mode: scanRegistration as its own stage
+static int frontend_stage(SlamH& s, Ctx& f, const SlamH::FeJob& j, SlamH::FeResult& r) {
+  const size_t bytes = (size_t)j.n * j.stride;
+  int rc;
+  if ((rc = f.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  if (bytes) ILSM_CUDA(cudaMemcpyAsync(f.fe.raw.p, j.xyzi, bytes, cudaMemcpyHostToDevice, f.stream));
+  if ((rc = f.features_dev(f.fe.raw.p, j.n, j.stride, s.min_range))) return rc;
+  int* pin = reinterpret_cast<int*>(f.pinned.p);
+  ILSM_CUDA(cudaMemcpyAsync(pin, f.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, f.stream));
+  ILSM_CUDA(cudaStreamSynchronize(f.stream));
+  if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: a ring segment exceeds the supported size");
+  for (int i = 0; i < 8; ++i) r.counts[i] = pin[i];
+  const int n_sharp = pin[1], n_lsharp = pin[2], n_flat = pin[3], n_lflat = pin[4];
+  SlamH::FeSlot& o = s.fslot[j.frame % 3];
+  if ((rc = o.sharp.reserve(n_sharp + 4)) || (rc = o.flat.reserve(n_flat + 4)) || (rc = o.lsharp.reserve(n_lsharp + 4)) ||
+      (rc = o.lflat.reserve(n_lflat + 4)))
+    return rc;
+  if ((rc = f.gather_dev(f.fe.cloud.p, f.fe.sharp.p, f.fe.counts.p, 1, n_sharp, o.sharp.p)) ||
+      (rc = f.gather_dev(f.fe.cloud.p, f.fe.lsharp.p, f.fe.counts.p, 2, n_lsharp, o.lsharp.p)) ||
+      (rc = f.gather_dev(f.fe.cloud.p, f.fe.flat.p, f.fe.counts.p, 3, n_flat, o.flat.p)))
+    return rc;
+  if (n_lflat) ILSM_CUDA(cudaMemcpyAsync(o.lflat.p, f.fe.lflat.p, (size_t)n_lflat * sizeof(float4), cudaMemcpyDeviceToDevice, f.stream));
+  ILSM_CUDA(cudaEventRecord(o.ev, f.stream));
+  return ILSM_OK;
+}
+
+static void frontend_worker(SlamH* sp) {
+  SlamH& s = *sp;
+  Ctx& f = s.ctx0->c;
+  cudaSetDevice(f.device);
+  for (;;) {
+    SlamH::FeJob j;
+    {
+      std::unique_lock<std::mutex> lk(s.fmu);
+      s.fcv.wait(lk, [&] { return s.fjob_posted || s.fstop; });
+      if (s.fstop) return;
+      j = s.fjob;
+      s.fjob_posted = false;
+    }
+    SlamH::FeResult r;
+    r.frame = j.frame, r.use_aloam = j.use_aloam;
+    {
+      std::lock_guard<std::mutex> lk2(f.mu);
+      r.rc = frontend_stage(s, f, j, r);
+      if (r.rc) snprintf(r.err, sizeof(r.err), "%s", ilsm_last_error());
+    }
+    {
+      std::lock_guard<std::mutex> lk(s.fmu);
+      s.fres = r;
+      s.fres_ready = true;
+    }
+    s.fcv.notify_all();
+  }
+}
+
+static int take_frontend_result(SlamH& s, SlamH::FeResult* out) {
+  std::unique_lock<std::mutex> lk(s.fmu);
+  s.fcv.wait(lk, [&] { return s.fres_ready; });
+  s.fres_ready = false;
+  s.fe_in_flight = false;
+  *out = s.fres;
+  if (out->rc) return fail(out->rc, out->err);
   return ILSM_OK;
 }
 
@@ -154,6 +289,7 @@ static int slam_create_common(ilsm_ctx* ctx, float min_range, ilsm_slam** out, i
     std::lock_guard<std::mutex> lk(ctx->c.mu);
     cudaSetDevice(ctx->c.device);
     if (!(rc = h->s.last_corner.init(&ctx->c))) rc = h->s.last_surf.init(&ctx->c);
+    if (!rc && !(rc = h->s.last_corner.reserve_points(16384))) rc = h->s.last_surf.reserve_points(65536);
   }
   if (rc) {
     delete h;
@@ -209,13 +345,72 @@ ILSM_API int ilsm_slam_create_async(ilsm_ctx* ctx, float line_res, float plane_r
   return ILSM_OK;
 }
 
+ILSM_API int ilsm_slam_create_staged(ilsm_ctx* ctx, float line_res, float plane_res, float min_range, int cube_capacity,
+                                     ilsm_slam** out) {
+  ilsm_slam* h = nullptr;
+  int rc = slam_create_common(ctx, min_range, out, &h);
+  if (rc) return rc;
+  h->s.staged = true;
+  if ((rc = ilsm_create(ctx->c.device, &h->s.ctx0)) || (rc = ilsm_create(ctx->c.device, &h->s.ctx2)) ||
+      (rc = ilsm_cubemap_create(h->s.ctx2, line_res, plane_res, cube_capacity, &h->s.cube))) {
+    ilsm_slam_destroy(h);
+    return rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    SlamH::FeSlot& o = h->s.fslot[i];
+    if (cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming) != cudaSuccess) {
+      ilsm_slam_destroy(h);
+      return fail(ILSM_ERR_CUDA, "slam_create_staged: event creation failed");
+    }
+    // typical 16-ring sizes up front: a growing buffer costs a device-wide synchronisation
+    if ((rc = o.sharp.reserve(1024)) || (rc = o.flat.reserve(4096)) || (rc = o.lsharp.reserve(8192)) || (rc = o.lflat.reserve(32768))) {
+      ilsm_slam_destroy(h);
+      return rc;
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    SlamH::StackSet& set = h->s.stk[i];
+    if (cudaEventCreateWithFlags(&set.ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&set.ev_free, cudaEventDisableTiming) != cudaSuccess) {
+      ilsm_slam_destroy(h);
+      return fail(ILSM_ERR_CUDA, "slam_create_staged: event creation failed");
+    }
+    if ((rc = set.c.reserve(8192)) || (rc = set.s.reserve(32768)) || (rc = set.n.reserve(4))) {
+      ilsm_slam_destroy(h);
+      return rc;
+    }
+  }
+  h->s.worker = std::thread(mapping_worker, &h->s);
+  h->s.fworker = std::thread(frontend_worker, &h->s);
+  *out = h;
+  return ILSM_OK;
+}
+
 ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
   if (!slam) return;
   SlamH& s = slam->s;
+  if (s.fworker.joinable()) {
+    {
+      std::unique_lock<std::mutex> lk(s.fmu);
+      s.fcv.wait(lk, [&] { return !s.fjob_posted; });
+      s.fstop = true;
+    }
+    s.fcv.notify_all();
+    s.fworker.join();
+  }
+  if (getenv("ILSM_STAGE_TRACE"))
+    fprintf(stderr, "[ilsm stage trace] frames %lld  tail-wait %.1f us  enqueue %.1f us  collect %.1f us per frame\n", s.frames,
+            1e6 * s.phase_s[8] / (s.frames ? s.frames : 1), 1e6 * s.phase_s[6] / (s.frames ? s.frames : 1),
+            1e6 * s.phase_s[7] / (s.frames ? s.frames : 1));
+  if (s.ctx0) {
+    std::lock_guard<std::mutex> lk0(s.ctx0->c.mu);
+    cudaSetDevice(s.ctx0->c.device);
+    cudaStreamSynchronize(s.ctx0->c.stream);
+  }
   if (s.worker.joinable()) {
     {
       std::unique_lock<std::mutex> lk(s.wmu);
-      s.wcv.wait(lk, [&] { return !s.job_posted; });  // a posted job is taken (and finished) before the thread is told to stop
+      s.wcv.wait(lk, [&] { return s.jobs.empty(); });  // posted jobs are taken (and finished) before the thread is told to stop
       s.stop = true;
     }
     s.wcv.notify_all();
@@ -237,10 +432,22 @@ ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
       s.lsharp2[i].release(), s.lflat2[i].release();
       if (s.ev_fe[i]) cudaEventDestroy(s.ev_fe[i]);
     }
+    for (int i = 0; i < 3; ++i) {
+      SlamH::FeSlot& o = s.fslot[i];
+      o.sharp.release(), o.flat.release(), o.lsharp.release(), o.lflat.release();
+      if (o.ev) cudaEventDestroy(o.ev);
+    }
+    for (int i = 0; i < 2; ++i) {
+      SlamH::StackSet& set = s.stk[i];
+      set.c.release(), set.s.release(), set.n.release();
+      if (set.ev_ready) cudaEventDestroy(set.ev_ready);
+      if (set.ev_free) cudaEventDestroy(set.ev_free);
+    }
   }
   if (s.cube) ilsm_cubemap_destroy(s.cube);
   if (s.mapopt) ilsm_mapopt_destroy(s.mapopt);
   if (s.ctx2) ilsm_destroy(s.ctx2);
+  if (s.ctx0) ilsm_destroy(s.ctx0);
   delete slam;
 }
 
@@ -284,7 +491,8 @@ ILSM_API int ilsm_slam_flush(ilsm_slam* slam, double q_map[4], double t_map[3], 
   if (!slam || !q_map || !t_map || !have) return fail(ILSM_ERR_INVALID_ARG, "slam_flush: null argument");
   SlamH& s = slam->s;
   *have = 0;
-  if (!s.async || !s.map_in_flight) return ILSM_OK;
+  if (s.staged) return fail(ILSM_ERR_STATE, "slam_flush: staged handles drain with ilsm_slam_frame_staged(n = -1)");
+  if (!s.async || s.maps_in_flight == 0) return ILSM_OK;
   std::lock_guard<std::mutex> lk(s.ctx->mu);
   int rc = take_mapping_result(s, q_map, t_map, stats);
   if (rc) return rc;
@@ -300,6 +508,7 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   if (!slam || (n > 0 && !xyzi) || !q_odom || !t_odom || !q_map || !t_map)
     return fail(ILSM_ERR_INVALID_ARG, "slam_frame: null argument");
   SlamH& s = slam->s;
+  if (s.staged) return fail(ILSM_ERR_STATE, "slam_frame: ilsm_slam_create_staged handles take ilsm_slam_frame_staged");
   if (s.async != (have_prev != nullptr))
     return fail(ILSM_ERR_STATE, "slam_frame: ilsm_slam_create_async handles take ilsm_slam_frame_async (and only those)");
   if (have_prev) *have_prev = 0;
@@ -329,7 +538,7 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   ILSM_CUDA(cudaMemcpyAsync(pin, c.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaStreamSynchronize(c.stream));
   clk.lap(2);  // wait for the front end (feature counts)
-  if (s.async && s.map_in_flight) {
+  if (s.async && s.maps_in_flight > 0) {
     // the previous frame's mapped pose: the mapping stage's thread has had this frame's upload and front end to finish
     if ((rc = take_mapping_result(s, q_map, t_map, stats))) return rc;
     *have_prev = 1;
@@ -426,15 +635,12 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   if (s.async) {
     // laserMapping as its own stage (the reference runs it as its own node): hand this frame to the mapping thread and
     // return; its mapped pose is collected by the next call (or by ilsm_slam_flush)
-    {
-      std::lock_guard<std::mutex> lkw(s.wmu);
-      s.job.slot = slot, s.job.n_lsharp = n_lsharp, s.job.n_lflat = n_lflat;
-      for (int i = 0; i < 4; ++i) s.job.q_odom[i] = q_odom[i];
-      for (int i = 0; i < 3; ++i) s.job.t_odom[i] = t_odom[i];
-      s.job_posted = true;
-      s.map_in_flight = true;
-    }
-    s.wcv.notify_all();
+    SlamH::MapJob job;
+    job.n_lsharp = n_lsharp, job.n_lflat = n_lflat, job.frame = s.frames;
+    job.d_lsharp = s.lsharp2[slot].p, job.d_lflat = s.lflat2[slot].p, job.ev_in = s.ev_fe[slot], job.stack_set = -1;
+    for (int i = 0; i < 4; ++i) job.q_odom[i] = q_odom[i];
+    for (int i = 0; i < 3; ++i) job.t_odom[i] = t_odom[i];
+    post_mapping_job(s, job);
   } else if (cmp) {  // laserMapping: rolling cube map
     ilsm_reg_opts mo;
     ilsm_reg_opts_default(&mo);
@@ -456,6 +662,134 @@ static int slam_frame_impl(ilsm_slam* slam, const float* xyzi, int n, int stride
   }
   clk.lap(5);  // tree builds + mapping stage (synchronous: enqueue and wait; pipelined: enqueue only)
   if (rc) return rc;
+  s.frames++;
+  return ILSM_OK;
+}
+
+// Staged mode, one call: collect the front end of the frame pushed by the previous call, push this frame to the front-end
+// stage, run the odometry of the collected frame here, collect the mapping of the frame before it, post the collected
+// frame to the mapping stage.  n < 0: nothing is pushed (drain).
+extern "C" ILSM_API int ilsm_slam_frame_staged(ilsm_slam* slam, const float* xyzi, int n, int stride_bytes, int use_aloam,
+                                               double q_odom[4], double t_odom[3], int* odom_frame, double q_map[4],
+                                               double t_map[3], int* map_frame, ilsm_slam_stats* stats) {
+  if (!slam || (n > 0 && !xyzi) || !q_odom || !t_odom || !q_map || !t_map || !odom_frame || !map_frame)
+    return fail(ILSM_ERR_INVALID_ARG, "slam_frame_staged: null argument");
+  if (n >= 0 && (stride_bytes < 12 || stride_bytes % 4)) return fail(ILSM_ERR_INVALID_ARG, "slam_frame_staged: bad stride");
+  SlamH& s = slam->s;
+  if (!s.staged) return fail(ILSM_ERR_STATE, "slam_frame_staged: not an ilsm_slam_create_staged handle");
+  *odom_frame = *map_frame = -1;
+  Ctx& c = *s.ctx;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  int rc;
+  PhaseClock clk(s.phase_s);
+  SlamH::FeResult fr;
+  const bool have_fe = s.fe_in_flight;
+  if (have_fe && (rc = take_frontend_result(s, &fr))) return rc;
+  clk.lap(2);  // wait for the front-end stage
+  if (n >= 0) {
+    {
+      std::lock_guard<std::mutex> lkf(s.fmu);
+      s.fjob.xyzi = xyzi, s.fjob.n = n, s.fjob.stride = stride_bytes, s.fjob.use_aloam = use_aloam, s.fjob.frame = s.pushed;
+      s.fjob_posted = true;
+    }
+    s.fcv.notify_all();
+    s.fe_in_flight = true;
+    s.pushed++;
+  }
+  clk.lap(0);  // hand-over to the front-end stage
+  if (!have_fe) {  // nothing for the odometry: first call, or the pipeline is draining
+    if (s.maps_in_flight > 0) {
+      long long mf = -1;
+      if ((rc = take_mapping_result(s, q_map, t_map, stats, &mf))) return rc;
+      *map_frame = (int)mf;
+    }
+    clk.lap(1);
+    return ILSM_OK;
+  }
+  const int n_sharp = fr.counts[1], n_lsharp = fr.counts[2], n_flat = fr.counts[3], n_lflat = fr.counts[4];
+  if (stats) {
+    stats->n_cloud = fr.counts[0], stats->n_sharp = n_sharp, stats->n_less_sharp = n_lsharp, stats->n_flat = n_flat;
+    stats->n_less_flat = n_lflat;
+  }
+  SlamH::FeSlot& o = s.fslot[fr.frame % 3];
+  ILSM_CUDA(cudaStreamWaitEvent(c.stream, o.ev, 0));
+  // ---- the mapping stacks of frame fr.frame on the side stream, under the odometry solve
+  {
+    SlamH::StackSet& set = s.stk[fr.frame & 1];
+    CubeMapH& cm = s.cube->m;  // (line_res / plane_res / err are fixed after creation)
+    if ((rc = set.c.reserve(n_lsharp + 4)) || (rc = set.s.reserve(n_lflat + 4))) return rc;
+    ILSM_CUDA(cudaStreamWaitEvent(c.aux, o.ev, 0));
+    if (set.free_recorded) ILSM_CUDA(cudaStreamWaitEvent(c.aux, set.ev_free, 0));  // frame - 2's insertion read this set
+    ILSM_CUDA(cudaMemsetAsync(set.n.p, 0, 4 * sizeof(int), c.aux));
+    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(o.lsharp.p), n_lsharp, cm.line_res, set.c.p,
+                                   reinterpret_cast<const float*>(o.lflat.p), n_lflat, cm.plane_res, set.s.p, 16, 3, set.n.p,
+                                   c.aux, cm.err.p)))
+      return rc;
+    ILSM_CUDA(cudaEventRecord(set.ev_ready, c.aux));
+  }
+  // ---- laserOdometry of frame fr.frame
+  const bool solve = s.inited && fr.use_aloam;
+  ilsm_reg_opts oo;
+  ilsm_reg_opts_default(&oo);
+  unsigned char* pb = c.pinned.p;
+  if (solve) {
+    double* pin_pose = reinterpret_cast<double*>(c.pinned.p + 2048);
+    for (int i = 0; i < 4; ++i) pin_pose[i] = s.para_q[i];
+    for (int i = 0; i < 3; ++i) pin_pose[4 + i] = s.para_t[i];
+    ILSM_CUDA(cudaMemcpyAsync(c.lm.p->xq, pin_pose, 7 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    if ((rc = c.odometry_dev(&s.last_corner, &s.last_surf, reinterpret_cast<const float*>(o.sharp.p), n_sharp,
+                             reinterpret_cast<const float*>(o.flat.p), n_flat, 16, oo)))
+      return rc;
+    ILSM_CUDA(cudaMemcpyAsync(pb, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    ILSM_CUDA(cudaMemcpyAsync(pb + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  }
+  clk.lap(3);  // odometry launches
+  if (solve) {
+    ILSM_CUDA(cudaStreamSynchronize(c.stream));
+    const double* o7 = reinterpret_cast<const double*>(pb);
+    for (int i = 0; i < 4; ++i) s.para_q[i] = o7[i];
+    for (int i = 0; i < 3; ++i) s.para_t[i] = o7[4 + i];
+    if (stats) {
+      memcpy(&stats->odometry, pb + 64, sizeof(ilsm_reg_report));
+      stats->odometry.passes = oo.outer_iterations;
+      stats->ran_odometry = 1;
+    }
+  }
+  clk.lap(4);  // wait for the odometry
+  if (!s.inited) {
+    s.inited = true;
+  } else {  // laserOdometry.cpp:716-717
+    double r[3];
+    qrot_h(s.q_w_curr, s.para_t, r);
+    for (int i = 0; i < 3; ++i) s.t_w_curr[i] = s.t_w_curr[i] + r[i];
+    s.q_w_curr = qmul_h(s.q_w_curr, QuatH{s.para_q[0], s.para_q[1], s.para_q[2], s.para_q[3]});
+  }
+  q_odom[0] = s.q_w_curr.x, q_odom[1] = s.q_w_curr.y, q_odom[2] = s.q_w_curr.z, q_odom[3] = s.q_w_curr.w;
+  for (int i = 0; i < 3; ++i) t_odom[i] = s.t_w_curr[i];
+  *odom_frame = (int)fr.frame;
+  if ((rc = build_pair_dev(&s.last_corner, reinterpret_cast<const float*>(o.lsharp.p), n_lsharp, &s.last_surf,
+                           reinterpret_cast<const float*>(o.lflat.p), n_lflat, 16, kOdomCell)))
+    return rc;
+  // this frame goes to the mapping stage BEFORE the previous frame's result is collected: the mapping thread moves on to
+  // it the moment it has finished the previous one
+  const bool collect_prev = s.maps_in_flight > 0;
+  {
+    SlamH::MapJob job;
+    job.n_lsharp = n_lsharp, job.n_lflat = n_lflat, job.frame = fr.frame;
+    job.d_lsharp = o.lsharp.p, job.d_lflat = o.lflat.p, job.ev_in = o.ev, job.stack_set = (int)(fr.frame & 1);
+    for (int i = 0; i < 4; ++i) job.q_odom[i] = q_odom[i];
+    for (int i = 0; i < 3; ++i) job.t_odom[i] = t_odom[i];
+    post_mapping_job(s, job);
+  }
+  clk.lap(5);  // tree builds + hand-over to the mapping stage
+  if (collect_prev) {
+    long long mf = -1;
+    if ((rc = take_mapping_result(s, q_map, t_map, stats, &mf))) return rc;
+    *map_frame = (int)mf;
+  }
+  clk.lap(1);  // wait for the mapping stage (the frame before)
   s.frames++;
   return ILSM_OK;
 }

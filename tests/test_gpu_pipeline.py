@@ -173,6 +173,100 @@ def test_pipelined_mapping_stage_gives_the_same_poses(ctx, ilsm):
     a.close(), b.close()
 
 
+def test_cube_merge_voxelgrid_is_bit_identical_to_the_general_pass(ctx, ilsm, monkeypatch):
+    """The per-frame VoxelGrid of a map cube merges the new points into the previous pass's output (ilsm_voxel.cuh
+    voxelgrid_block_merge) and skips cubes nothing was inserted into; ILSM_VG_MERGE=0 sends every pass through the
+    general hash / sort VoxelGrid instead.  Poses and every cube of both maps must agree bit for bit."""
+    import torch
+    S = ilsm.synth
+    frames = 160
+    scene = S.Scene(corridor=True, length=0.2 * frames + 30.0)
+    clouds = S.make_frames_torch(scene, S.corridor_poses(frames), 0x5EED0120, torch.device("cuda:0"))
+    clouds = [clouds[k].numpy() for k in range(frames)]
+    runs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ILSM_VG_MERGE", flag)
+        slam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+        poses = [slam.frame(c)[2:4] for c in clouds]
+        cm = slam.cubemap()
+        cubes = {}
+        for which in (0, 1):
+            for idx in range(21 * 21 * 11):
+                pts = cm.cube(which, idx)
+                if len(pts):
+                    cubes[(which, idx)] = pts.copy()
+        runs.append((poses, cubes))
+        slam.close()
+    (pa, ca), (pb, cb) = runs
+    for k in range(len(clouds)):
+        assert np.array_equal(pa[k][0], pb[k][0]) and np.array_equal(pa[k][1], pb[k][1]), k
+    assert sorted(ca) == sorted(cb) and len(ca) > 4
+    assert max(len(v) for v in ca.values()) > 2048, max(len(v) for v in ca.values())  # the large-cube path is exercised
+    for key in ca:
+        assert ca[key].tobytes() == cb[key].tobytes(), key
+
+
+def _run_staged(slam, clouds, use_aloam=None):
+    """Push every cloud through ilsm_slam_frame_staged, then drain; returns ({frame: (q, t)} odometry, {frame: ...} mapped,
+    {frame: stats of the call that returned its odometry})."""
+    odom, mapped, stats = {}, {}, {}
+    seq = list(clouds) + [None, None]
+    for k, c in enumerate(seq):
+        ua = True if (use_aloam is None or c is None) else use_aloam[k]
+        fo, qo, to, fm, qm, tm, st = slam.frame_staged(c, use_aloam=ua)
+        assert fo == (k - 1 if 1 <= k <= len(clouds) else -1), (k, fo)
+        assert fm == (k - 2 if 2 <= k <= len(clouds) + 1 else -1), (k, fm)
+        if fo >= 0:
+            odom[fo] = (qo, to)
+            stats[fo] = st
+        if fm >= 0:
+            mapped[fm] = (qm, tm, st.mapping.pass_[1].num_plane_factors)
+    fo, _, _, fm, _, _, _ = slam.frame_staged(None)  # an empty pipeline stays empty
+    assert fo == -1 and fm == -1
+    return odom, mapped, stats
+
+
+def test_three_stage_loop_gives_the_same_poses(ctx, ilsm):
+    """ilsm_slam_create_staged: scanRegistration, laserOdometry and laserMapping as three stages with their own contexts
+    and host threads (the reference's three nodes).  Odometry poses arrive one call later, mapped poses two calls later,
+    both bit-identical to the synchronous loop -- also when some frames skip the odometry solve (use_aloam = 0 travels
+    with the frame) and across a second sequence on the same handle kind."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from sequence_bench import corridor_sequence
+    clouds, _ = corridor_sequence(ilsm.synth, 18, 0x5EED0110, 40.0)
+    for use in (None, [k % 5 != 3 for k in range(len(clouds))]):
+        a = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096)
+        b = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096, staged=True)
+        sync = [a.frame(c, use_aloam=True if use is None else use[k]) for k, c in enumerate(clouds)]
+        odom, mapped, stats = _run_staged(b, clouds, use)
+        assert sorted(odom) == sorted(mapped) == list(range(len(clouds)))
+        for k in range(len(clouds)):
+            assert np.array_equal(odom[k][0], sync[k][0]) and np.array_equal(odom[k][1], sync[k][1]), k
+            assert np.array_equal(mapped[k][0], sync[k][2]) and np.array_equal(mapped[k][1], sync[k][3]), k
+            assert mapped[k][2] == sync[k][4].mapping.pass_[1].num_plane_factors
+            assert stats[k].n_less_flat == sync[k][4].n_less_flat and stats[k].ran_odometry == sync[k][4].ran_odometry
+        with pytest.raises(ilsm.IlsmError):
+            b.frame(clouds[0])
+        with pytest.raises(ilsm.IlsmError):
+            b.flush()
+        with pytest.raises(ilsm.IlsmError):
+            a.frame_staged(clouds[0])
+        a.close(), b.close()
+
+
+def test_three_stage_loop_destroyed_with_frames_in_flight(ctx, ilsm):
+    """Destroying a staged handle while its stages still hold frames must drain them, not hang or crash."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from sequence_bench import corridor_sequence
+    clouds, _ = corridor_sequence(ilsm.synth, 4, 0x5EED0111, 40.0)
+    b = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 4096, staged=True)
+    for c in clouds:
+        b.frame_staged(c)
+    b.close()
+
+
 @pytest.mark.parametrize("pipelined", [False, True])
 def test_feature_clouds_above_16384_points(ctx, oracle_mod, ilsm, pipelined):
     """A 64-ring sensor whose beams all fall inside the reference's +-22.5 degree ring formula keeps every return

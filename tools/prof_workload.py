@@ -3,7 +3,7 @@
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof python tools/prof_workload.py
 Sections (select with --only): reg (config-1 registration: builds, associate, solve), knn (N = 2M, Q = 65536),
 jtj (1M factors), sc (20k-keyframe shard), fe (projection + feature extraction), slam (one frame of the full loop after
-20 frames of a corridor sequence)."""
+20 frames of a corridor sequence), slamlong (one frame after 600 frames of the bench's sequence)."""
 from __future__ import annotations
 
 import argparse
@@ -107,6 +107,17 @@ def main():
             slam.frame(clouds[k])
         it = iter(clouds[20:])
         work.append(lambda: slam.frame(next(it)))
+
+    if "slamlong" in only:  # one frame of the full loop deep into the bench's corridor sequence (cubes filled)
+        nf = 604
+        scene = S.Scene(corridor=True, length=0.2 * nf + 30.0)
+        lclouds = S.make_frames_torch(scene, S.corridor_poses(nf), 0x5EED0200, dev)
+        lviews = [lclouds[k].numpy() for k in range(nf)]
+        lslam = ilsm.Slam(ctx, 0.4, 0.8, 0.3, 8192)
+        for k in range(600):
+            lslam.frame(lviews[k])
+        lit = iter(lviews[600:])
+        work.append(lambda: lslam.frame(next(lit)))
 
     for _ in range(3):  # warm-up (allocation, module load; the map builds alternate between two tables)
         for w in work:
