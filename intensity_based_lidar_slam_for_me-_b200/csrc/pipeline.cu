@@ -351,6 +351,7 @@ ILSM_API int ilsm_slam_create_staged(ilsm_ctx* ctx, float line_res, float plane_
   int rc = slam_create_common(ctx, min_range, out, &h);
   if (rc) return rc;
   h->s.staged = true;
+  h->s.last_corner.in_line = h->s.last_surf.in_line = true;  // nothing follows the tree builds on this stage's stream
   if ((rc = ilsm_create(ctx->c.device, &h->s.ctx0)) || (rc = ilsm_create(ctx->c.device, &h->s.ctx2)) ||
       (rc = ilsm_cubemap_create(h->s.ctx2, line_res, plane_res, cube_capacity, &h->s.cube))) {
     ilsm_slam_destroy(h);
@@ -715,20 +716,6 @@ extern "C" ILSM_API int ilsm_slam_frame_staged(ilsm_slam* slam, const float* xyz
   }
   SlamH::FeSlot& o = s.fslot[fr.frame % 3];
   ILSM_CUDA(cudaStreamWaitEvent(c.stream, o.ev, 0));
-  // ---- the mapping stacks of frame fr.frame on the side stream, under the odometry solve
-  {
-    SlamH::StackSet& set = s.stk[fr.frame & 1];
-    CubeMapH& cm = s.cube->m;  // (line_res / plane_res / err are fixed after creation)
-    if ((rc = set.c.reserve(n_lsharp + 4)) || (rc = set.s.reserve(n_lflat + 4))) return rc;
-    ILSM_CUDA(cudaStreamWaitEvent(c.aux, o.ev, 0));
-    if (set.free_recorded) ILSM_CUDA(cudaStreamWaitEvent(c.aux, set.ev_free, 0));  // frame - 2's insertion read this set
-    ILSM_CUDA(cudaMemsetAsync(set.n.p, 0, 4 * sizeof(int), c.aux));
-    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(o.lsharp.p), n_lsharp, cm.line_res, set.c.p,
-                                   reinterpret_cast<const float*>(o.lflat.p), n_lflat, cm.plane_res, set.s.p, 16, 3, set.n.p,
-                                   c.aux, cm.err.p)))
-      return rc;
-    ILSM_CUDA(cudaEventRecord(set.ev_ready, c.aux));
-  }
   // ---- laserOdometry of frame fr.frame
   const bool solve = s.inited && fr.use_aloam;
   ilsm_reg_opts oo;
@@ -744,6 +731,21 @@ extern "C" ILSM_API int ilsm_slam_frame_staged(ilsm_slam* slam, const float* xyz
       return rc;
     ILSM_CUDA(cudaMemcpyAsync(pb, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     ILSM_CUDA(cudaMemcpyAsync(pb + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  }
+  // ---- the mapping stacks of frame fr.frame on the side stream, under the odometry solve (enqueued after it: the solve is
+  // the longer of the two and the odometry pose is what this stage's caller waits for)
+  {
+    SlamH::StackSet& set = s.stk[fr.frame & 1];
+    CubeMapH& cm = s.cube->m;  // (line_res / plane_res / err are fixed after creation)
+    if ((rc = set.c.reserve(n_lsharp + 4)) || (rc = set.s.reserve(n_lflat + 4))) return rc;
+    ILSM_CUDA(cudaStreamWaitEvent(c.aux, o.ev, 0));
+    if (set.free_recorded) ILSM_CUDA(cudaStreamWaitEvent(c.aux, set.ev_free, 0));  // frame - 2's insertion read this set
+    ILSM_CUDA(cudaMemsetAsync(set.n.p, 0, 4 * sizeof(int), c.aux));
+    if ((rc = c.voxelgrid_pair_dev(reinterpret_cast<const float*>(o.lsharp.p), n_lsharp, cm.line_res, set.c.p,
+                                   reinterpret_cast<const float*>(o.lflat.p), n_lflat, cm.plane_res, set.s.p, 16, 3, set.n.p,
+                                   c.aux, cm.err.p)))
+      return rc;
+    ILSM_CUDA(cudaEventRecord(set.ev_ready, c.aux));
   }
   clk.lap(3);  // odometry launches
   if (solve) {
