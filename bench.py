@@ -936,7 +936,7 @@ def main():
     ap.add_argument("--config4-frames", type=int, default=200)
     ap.add_argument("--sc-keyframes", type=int, default=100_000)
     ap.add_argument("--sc-queries", type=int, default=512)
-    ap.add_argument("--sc-batch", type=int, default=16)
+    ap.add_argument("--sc-batch", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

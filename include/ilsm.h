@@ -610,7 +610,8 @@ ILSM_API int ilsm_sc_query_topk_batch_dev(ilsm_sc* sc, const float* d_desc_20x60
  * whose approximate distance is within a proven error bound of the k-th best (and on every pair whose sector-key
  * alignment the approximation could not decide).  The reported top-k is the one an exact scan of every entry gives.
  * ilsm_sc_prefilter_debug exposes the first step for tests: approx[q * n_search + c] (-1 = pair flagged for exact
- * rescoring) and the aligned shift it used; n_queries <= 8. */
+ * rescoring; <= -2 = the alignment is one of two, the value is -2 - the smaller of the two distances, a lower bound of the
+ * exact one) and the aligned shift it used; n_queries <= 8. */
 ILSM_API int ilsm_sc_prefilter_debug(ilsm_sc* sc, const float* desc_20x60, int n_queries, int n_search, float* approx,
                                      uint8_t* aligned_shift);
 

@@ -119,18 +119,18 @@ __device__ __forceinline__ void named_barrier(int id, int threads) { asm volatil
 struct PfSmem {
   __align__(16) float craw[2][kDesc];           // raw candidate descriptors, double buffered (filled by cp.async)
   __align__(16) __half ch[kChCols][kChStride];  // column-normalised candidate, [column][ring] (columns 60.. repeat 0..); rings 20..31 stay zero
-  __half ckh[128], ckl[128];                    // candidate sector key hi / lo at index x = (column - shift) + 64, periodic
-  uint32_t pkh[128], pkl[128];                  // the same as adjacent pairs (x, x + 1): one 32-bit load per A-fragment register
-  float corr[64][kPfQ];                         // alignment correlations [shift][query]
-  float ck2_part[4];
-  unsigned cm_part[4];
+  uint32_t pkh[128], pkl[128];                  // candidate sector key hi / lo as adjacent pairs (x, x + 1), x = (column - shift) + 64, periodic
+  float corr[2][64][kPfQ];                      // alignment correlations [column half][shift][query] (the two halves are added by the reader)
+  float ck2_part[8];
+  unsigned cm_part[8];
   float ck2;
   unsigned long long cmask;
 };
 
-// D[q * n + c] = approximate distance of query q and candidate c, or -1 when the pair is flagged for exact rescoring;
+// D[q * n + c] = approximate distance of query q and candidate c; -1 when the pair is flagged for exact rescoring; <= -2 when
+// its alignment is one of two (the value is -2 - the smaller of the two distances, a lower bound of the exact one);
 // Sh (optional, debugging / tests) = the aligned shift the prefilter used.
-__global__ void __launch_bounds__(kPfThreads, 2)
+__global__ void __launch_bounds__(kPfThreads, 3)
     sc_prefilter_kernel(const float* __restrict__ db, int n, const PfQuery* __restrict__ Q, int B, float* __restrict__ D,
                         unsigned char* __restrict__ Sh) {
   pdl_entry();
@@ -138,6 +138,11 @@ __global__ void __launch_bounds__(kPfThreads, 2)
   PfSmem& sm = *reinterpret_cast<PfSmem*>(pf_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
+  {  // blockIdx.y = which group of 8 queries of the batch this block serves
+    const int q0 = (int)blockIdx.y * kPfQ;
+    Q += q0, D += (size_t)q0 * n, B = B - q0 < kPfQ ? B - q0 : kPfQ;
+    if (Sh) Sh += (size_t)q0 * n;
+  }
   const bool has_q = warp < B;
   const PfQuery& myq = Q[has_q ? warp : 0];
 
@@ -156,18 +161,20 @@ __global__ void __launch_bounds__(kPfThreads, 2)
     }
   const unsigned long long qmask = myq.mask;
   const float qknorm = myq.knorm;
-  // ---- alignment warps (0..3): B fragments = the sector keys of the block's queries, query index = g
-  uint32_t kb_h[4][2], kb_l[4][2];
-  if (warp < 4) {
+  // ---- alignment: warp w owns shifts 16 (w & 3) .. + 15 and columns 32 (w >> 2) .. + 31 (two of the four k-steps);
+  // B fragments = the sector keys of the block's queries, query index = g
+  const int am = warp & 3, ak = warp >> 2;
+  uint32_t kb_h[2][2], kb_l[2][2];
+  {
     const bool qv = g < B;
     const PfQuery& kq = Q[qv ? g : 0];
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const int c0 = 16 * ks + 2 * t;
-      kb_h[ks][0] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kh[c0]) : 0u;
-      kb_h[ks][1] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kh[c0 + 8]) : 0u;
-      kb_l[ks][0] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kl[c0]) : 0u;
-      kb_l[ks][1] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kl[c0 + 8]) : 0u;
+    for (int kk = 0; kk < 2; ++kk) {
+      const int c0 = 16 * (2 * ak + kk) + 2 * t;
+      kb_h[kk][0] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kh[c0]) : 0u;
+      kb_h[kk][1] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kh[c0 + 8]) : 0u;
+      kb_l[kk][0] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kl[c0]) : 0u;
+      kb_l[kk][1] = qv ? *reinterpret_cast<const uint32_t*>(&kq.kl[c0 + 8]) : 0u;
     }
   }
   // epilogue geometry of the cosine band (see the header): accumulator (row m, column o) of a 16 x 24 tile belongs to
@@ -191,82 +198,92 @@ __global__ void __launch_bounds__(kPfThreads, 2)
     const int nxt = cand + gridDim.x;
     if (nxt < n)
       for (int i = tid; i < kDesc / 4; i += kPfThreads) cp_async16(&sm.craw[cur ^ 1][4 * i], db + (size_t)nxt * kDesc + 4 * i);
-    // ---- stage (warps 0..3: 2 threads per column, 10 rings each): column sums, normalise, packed f16 stores; sector
-    // key hi / lo; validity mask; |key|^2
-    if (warp < 4) {
-      const int col = tid >> 1, hf = tid & 1;  // 120 threads work (col < 60)
-      float v[10], s = 0.f, ss = 0.f;
+    // ---- stage (all 8 warps: 4 threads per column, rings 0-5 / 6-11 / 12-15 / 16-19): column sums, normalise, packed
+    // f16 stores; sector key hi / lo; validity mask; |key|^2
+    {
+      const int col = tid >> 2, q4 = tid & 3;  // 240 threads work (col < 60)
+      const int r0 = q4 < 2 ? 6 * q4 : 4 + 4 * q4, cnt = q4 < 2 ? 6 : 4;
+      float v[6], s = 0.f, ss = 0.f;
 #pragma unroll
-      for (int k = 0; k < 10; ++k) {
-        v[k] = col < kNS ? sm.craw[cur][(10 * hf + k) * kNS + col] : 0.f;
+      for (int k = 0; k < 6; ++k) {
+        v[k] = (col < kNS && k < cnt) ? sm.craw[cur][(r0 + k) * kNS + col] : 0.f;
         s += v[k];
         ss = fmaf(v[k], v[k], ss);
       }
       s += __shfl_xor_sync(0xffffffffu, s, 1), ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2), ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       const bool valid = ss > 0.f;
       const float inv = valid ? rsqrtf(ss) : 0.f;
       const float key = s / kNR;
       if (col < kNS) {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.ch[col][10 * hf]);
-        uint32_t* dup = reinterpret_cast<uint32_t*>(&sm.ch[col < kChCols - kNS ? col + kNS : col][10 * hf]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.ch[col][r0]);
+        uint32_t* dup = reinterpret_cast<uint32_t*>(&sm.ch[col < kChCols - kNS ? col + kNS : col][r0]);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const __half2 h2 = __floats2half2_rn(v[2 * k] * inv, v[2 * k + 1] * inv);
-          dst[k] = *reinterpret_cast<const uint32_t*>(&h2);
-          dup[k] = *reinterpret_cast<const uint32_t*>(&h2);
+        for (int k = 0; k < 3; ++k) {
+          if (2 * k < cnt) {
+            const __half2 h2 = __floats2half2_rn(v[2 * k] * inv, v[2 * k + 1] * inv);
+            dst[k] = *reinterpret_cast<const uint32_t*>(&h2);
+            dup[k] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
         }
-        if (hf == 0) {
+        if (q4 == 0) {
           const __half h = __float2half(key), l = __float2half(key - __half2float(h));
-          // index x = (column - shift) + 64 holds column (x + 56) mod 60
-          sm.ckh[col + 4] = h, sm.ckl[col + 4] = l;
-          sm.ckh[col + 64] = h, sm.ckl[col + 64] = l;
-          if (col < 4) sm.ckh[col + 124] = h, sm.ckl[col + 124] = l;
-          if (col >= 56) sm.ckh[col - 56] = h, sm.ckl[col - 56] = l;
+          // index x = (column - shift) + 64 holds column (x + 56) mod 60; the keys are kept as adjacent PAIRS
+          // pk[x] = (key[x], key[x + 1]), so that an A-fragment register of the circulant is one 32-bit load: key[x] is
+          // the low half of pk[x] and the high half of pk[x - 1]
+          __half* ph = reinterpret_cast<__half*>(sm.pkh);
+          __half* pl = reinterpret_cast<__half*>(sm.pkl);
+          auto put = [&](int x) {
+            if (x < 128) ph[2 * x] = h, pl[2 * x] = l;
+            if (x > 0) ph[2 * x - 1] = h, pl[2 * x - 1] = l;
+          };
+          put(col + 4), put(col + 64);
+          if (col < 4) put(col + 124);
+          if (col == 4) put(128);  // only the high half of pk[127]
+          if (col >= 56) put(col - 56);
         }
       }
-      const unsigned vb = __ballot_sync(0xffffffffu, valid && hf == 0 && col < kNS);
-      float k2 = (hf == 0 && col < kNS) ? key * key : 0.f;
+      const unsigned vb = __ballot_sync(0xffffffffu, valid && q4 == 0 && col < kNS);
+      float k2 = (q4 == 0 && col < kNS) ? key * key : 0.f;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) k2 += __shfl_xor_sync(0xffffffffu, k2, off);
       if (lane == 0) {
-        unsigned m16 = 0;  // even lanes 0, 2, .., 30 of warp w carry columns 16 w .. 16 w + 15
+        unsigned m8 = 0;  // lanes 0, 4, .., 28 of warp w carry columns 8 w .. 8 w + 7
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m16 |= ((vb >> (2 * k)) & 1u) << k;
-        sm.cm_part[warp] = m16;
+        for (int k = 0; k < 8; ++k) m8 |= ((vb >> (4 * k)) & 1u) << k;
+        sm.cm_part[warp] = m8;
         sm.ck2_part[warp] = k2;
       }
-      named_barrier(1, 128);  // the four staging warps only
-      // adjacent key pairs, so that an A-fragment register of the circulant is one 32-bit load
-      if (tid < 127) {
-        sm.pkh[tid] = pack_h2(sm.ckh[tid], sm.ckh[tid + 1]);
-        sm.pkl[tid] = pack_h2(sm.ckl[tid], sm.ckl[tid + 1]);
+      __syncthreads();
+      if (tid == 255) {  // (read after the next barrier, by the band phase)
+        sm.ck2 = ((sm.ck2_part[0] + sm.ck2_part[1]) + (sm.ck2_part[2] + sm.ck2_part[3])) +
+                 ((sm.ck2_part[4] + sm.ck2_part[5]) + (sm.ck2_part[6] + sm.ck2_part[7]));
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m |= (unsigned long long)sm.cm_part[w] << (8 * w);
+        sm.cmask = m & ((1ull << kNS) - 1ull);
       }
-      if (tid == 127) {
-        sm.ck2 = (sm.ck2_part[0] + sm.ck2_part[1]) + (sm.ck2_part[2] + sm.ck2_part[3]);
-        sm.cmask = ((unsigned long long)sm.cm_part[0] | ((unsigned long long)sm.cm_part[1] << 16) | ((unsigned long long)sm.cm_part[2] << 32) |
-                    ((unsigned long long)sm.cm_part[3] << 48)) & ((1ull << kNS) - 1ull);
-      }
-      named_barrier(1, 128);
-      // ---- alignment: warp i computes the correlations of shifts 16 i .. 16 i + 15 with all queries
+      // ---- alignment: the correlations of shifts 16 am .. + 15 with all queries over columns 32 ak .. + 31
       float acc[4];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        // A[m][k] = ck[(column - shift) mod 60], shift = 16 warp + m, column = 16 ks + k  ->  index x = column - shift + 64
-        const int x0 = 16 * ks + 2 * t - (16 * warp + g) + 64;
+      for (int kk = 0; kk < 2; ++kk) {
+        const int ks = 2 * ak + kk;
+        // A[m][k] = ck[(column - shift) mod 60], shift = 16 am + m, column = 16 ks + k  ->  index x = column - shift + 64
+        const int x0 = 16 * ks + 2 * t - (16 * am + g) + 64;
         uint32_t ah[4], al[4];
         ah[0] = sm.pkh[x0], al[0] = sm.pkl[x0];
         ah[1] = sm.pkh[x0 - 8], al[1] = sm.pkl[x0 - 8];  // shift + 8
         ah[2] = sm.pkh[x0 + 8], al[2] = sm.pkl[x0 + 8];  // column + 8
         ah[3] = ah[0], al[3] = al[0];                    // both
-        if (ks == 0) mma_f16_zero(acc, ah, kb_h[ks][0], kb_h[ks][1]);
-        else mma_f16(acc, ah, kb_h[ks][0], kb_h[ks][1]);
-        mma_f16(acc, ah, kb_l[ks][0], kb_l[ks][1]);
-        mma_f16(acc, al, kb_h[ks][0], kb_h[ks][1]);
+        if (kk == 0) mma_f16_zero(acc, ah, kb_h[kk][0], kb_h[kk][1]);
+        else mma_f16(acc, ah, kb_h[kk][0], kb_h[kk][1]);
+        mma_f16(acc, ah, kb_l[kk][0], kb_l[kk][1]);
+        mma_f16(acc, al, kb_h[kk][0], kb_h[kk][1]);
       }
-      // acc[0]: (shift 16 w + g, query 2 t), acc[1]: (same shift, query 2 t + 1), acc[2] / acc[3]: shift + 8
-      const int s0 = 16 * warp + g;
-      *reinterpret_cast<float2*>(&sm.corr[s0][2 * t]) = make_float2(acc[0], acc[1]);
-      *reinterpret_cast<float2*>(&sm.corr[s0 + 8][2 * t]) = make_float2(acc[2], acc[3]);
+      // acc[0]: (shift 16 am + g, query 2 t), acc[1]: (same shift, query 2 t + 1), acc[2] / acc[3]: shift + 8
+      const int s0 = 16 * am + g;
+      *reinterpret_cast<float2*>(&sm.corr[ak][s0][2 * t]) = make_float2(acc[0], acc[1]);
+      *reinterpret_cast<float2*>(&sm.corr[ak][s0 + 8][2 * t]) = make_float2(acc[2], acc[3]);
     }
     __syncthreads();
     // ---- every warp: its own query against the staged candidate
@@ -274,20 +291,30 @@ __global__ void __launch_bounds__(kPfThreads, 2)
       // best and second best correlation over the 60 shifts: order-preserving integer keys (correlations of non-negative
       // keys are >= 0 up to rounding) with the shift in the low 6 bits, two REDUX each.  Truncating 6 mantissa bits
       // costs 2^-17 relative, accounted for in the bound below.
-      const float c0v = sm.corr[lane][warp], c1v = lane + 32 < kNS ? sm.corr[lane + 32][warp] : 0.f;
+      const float c0v = sm.corr[0][lane][warp] + sm.corr[1][lane][warp];
+      const float c1v = lane + 32 < kNS ? sm.corr[0][lane + 32][warp] + sm.corr[1][lane + 32][warp] : 0.f;
       uint32_t k0 = (__float_as_uint(fmaxf(c0v, 0.f)) & ~63u) | (uint32_t)(63 - lane);          // lower shift wins ties
       uint32_t k1 = lane + 32 < kNS ? (__float_as_uint(fmaxf(c1v, 0.f)) & ~63u) | (uint32_t)(31 - lane) : 0u;
       const uint32_t best = redux_max_u32(k0 > k1 ? k0 : k1);
       if (k0 == best) k0 = 0u;
       if (k1 == best) k1 = 0u;
       const uint32_t second = redux_max_u32(k0 > k1 ? k0 : k1);
-      const int a = 63 - (int)(best & 63u);
-      const float b1 = __uint_as_float(best & ~63u), b2 = __uint_as_float(second & ~63u);
+      if (k0 == second) k0 = 0u;
+      if (k1 == second) k1 = 0u;
+      const uint32_t third = redux_max_u32(k0 > k1 ? k0 : k1);
+      const int a1 = 63 - (int)(best & 63u), a2 = 63 - (int)(second & 63u);
+      const float b1 = __uint_as_float(best & ~63u), b2 = __uint_as_float(second & ~63u), b3 = __uint_as_float(third & ~63u);
       const unsigned long long cmask = sm.cmask;
       // |correlation error| <= 3e-5 |qk| |ck| (hi/lo split: dropped lo x lo term 2^-22; fp32 accumulation of 192 products
-      // 1.1e-5; key truncation 7.6e-6); the alignment is certain when the best beats the runner-up by more than twice that
+      // 1.1e-5; key truncation 7.6e-6); the alignment is certain when the best beats the runner-up by more than twice that.
+      // When only the runner-up is that close, the true alignment is one of the two: the band is evaluated for both and
+      // the pair carries the smaller distance as a LOWER bound (dual); three or more contenders: flagged outright.
       const float err = 3.0e-5f * qknorm * sqrtf(sm.ck2) + 1e-30f;
-      const bool flagged = !(b1 - b2 > 2.f * err) || a >= kNS;
+      const bool unsure = !(b1 - b2 > 2.f * err);
+      const bool hard = a1 >= kNS || (unsure && (a2 >= kNS || !(b1 - b3 > 2.f * err)));
+      const bool dual = unsure && !hard;
+      // the band for one alignment (inlined twice: the second copy only runs for the rare dual pairs)
+      auto band = [&](const int a) -> float {
       float x0 = 0.f, x1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -328,9 +355,14 @@ __global__ void __launch_bounds__(kPfThreads, 2)
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) dist = fminf(dist, __shfl_xor_sync(0xffffffffu, dist, off));
+      return dist;
+      };
+      float dbest = band(a1 < kNS ? a1 : 0);
+      if (dual) dbest = fminf(dbest, band(a2));
       if (lane == 0) {
-        D[(size_t)warp * n + cand] = flagged ? -1.f : dist;
-        if (Sh) Sh[(size_t)warp * n + cand] = (unsigned char)(a < kNS ? a : 0);
+        // >= 0: distance (error <= kPfEps);  -1: flagged;  <= -2: dual, -2 - (lower bound of the distance)
+        D[(size_t)warp * n + cand] = hard ? -1.f : (dual ? -2.f - dbest : dbest);
+        if (Sh) Sh[(size_t)warp * n + cand] = (unsigned char)(a1 < kNS ? a1 : 0);
       }
     }
     cur ^= 1;
@@ -423,7 +455,8 @@ __global__ void __launch_bounds__(256) sc_pf_compact_kernel(const float* __restr
   const float* d = D + (size_t)q * n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float v = d[i];
-    if (v < 0.f || v <= th) {
+    // flagged pairs always; dual pairs by their lower bound; the rest by their distance
+    if (v == -1.f || (v <= -2.f ? -2.f - v <= th : (v >= 0.f && v <= th))) {
       const int pos = atomicAdd(&list_n[q], 1);
       list[(size_t)q * n + pos] = (u64)(uint32_t)i;
     }
@@ -441,21 +474,25 @@ int ScDb::query_batch_tc_dev(const float* d_qdesc, int B, int n_search, int id_o
   if (n_search < 0 || n_search > count) return fail(ILSM_ERR_INVALID_ARG, "sc_query: n_search exceeds the database");
   cudaStream_t s = ctx->stream;
   int rc;
-  for (int b0 = 0; b0 < B; b0 += kPfQ) {
-    const int nb = B - b0 < kPfQ ? B - b0 : kPfQ;
+  // the whole batch goes through every step in ONE launch each (the prefilter serves groups of 8 queries through
+  // blockIdx.y): at small shards (a database split over 8 GPUs) the per-launch costs are what a query batch pays for
+  constexpr int kBatchMax = 64;
+  for (int b0 = 0; b0 < B; b0 += kBatchMax) {
+    const int nb = B - b0 < kBatchMax ? B - b0 : kBatchMax;
+    const int groups = (nb + kPfQ - 1) / kPfQ;
     const int chunks = n_search > 0 ? (n_search + kSelChunk - 1) / kSelChunk : 1;
     const size_t part_per_q = (size_t)chunks * 8 * k;
-    if ((rc = pf_query.reserve(kPfQ * sizeof(PfQuery))) || (rc = pf_dist.reserve((size_t)kPfQ * (n_search + 1))) ||
-        (rc = pf_part.reserve(kPfQ * part_per_q + 16)) || (rc = pf_thr.reserve(kPfQ)) || (rc = pf_list_n.reserve(kPfQ)) ||
-        (rc = pf_list.reserve((size_t)kPfQ * (n_search + 1))))
+    if ((rc = pf_query.reserve((size_t)groups * kPfQ * sizeof(PfQuery))) || (rc = pf_dist.reserve((size_t)nb * (n_search + 1))) ||
+        (rc = pf_part.reserve(nb * part_per_q + 16)) || (rc = pf_thr.reserve(nb)) || (rc = pf_list_n.reserve(nb)) ||
+        (rc = pf_list.reserve((size_t)nb * (n_search + 1))))
       return rc;
     ILSM_CUDA(launch_pdl(sc_pf_prep_kernel, dim3(nb), dim3(64), 0, s, d_qdesc + (size_t)b0 * kDesc, reinterpret_cast<PfQuery*>(pf_query.p)));
     int launches = 1;
     if (n_search > 0) {
       ILSM_CUDA(cudaFuncSetAttribute(sc_prefilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PfSmem)));
-      int blocks = ctx->sm_count * 2;
+      int blocks = ctx->sm_count * 3;
       if (blocks > n_search) blocks = n_search;
-      ILSM_CUDA(launch_pdl(sc_prefilter_kernel, dim3(blocks), dim3(kPfThreads), sizeof(PfSmem), s, (const float*)db.p, n_search,
+      ILSM_CUDA(launch_pdl(sc_prefilter_kernel, dim3(blocks, groups), dim3(kPfThreads), sizeof(PfSmem), s, (const float*)db.p, n_search,
                            (const PfQuery*)pf_query.p, nb, pf_dist.p, d_shift_dbg));
       ++launches;
     }

@@ -246,12 +246,19 @@ def test_gpu_sc_prefilter_approximates_exact(ctx, oracle_mod, ilsm):
     D, S = sc.prefilter_debug(q)
     dbd, qd = db.astype(np.float64), q.astype(np.float64)
     keys = dbd.mean(axis=1)           # sector keys: column means (Scancontext.cpp:222-235)
-    flagged = D < 0
+    flagged = D < 0               # -1: flagged outright; <= -2: one of two alignments, -2 - (lower bound of the distance)
+    dual = D <= -2
     assert flagged[:7].mean() < 0.05, flagged.mean()
+    assert (D[:7] == -1).mean() < 0.01, (D[:7] == -1).mean()
     worst = 0.0
     for j in range(8):
         qk = qd[j].mean(axis=0)
         for c in range(0, len(db), 3):
+            if dual[j, c]:
+                wd, _ = oracle_mod.sc_distance(qd[j], dbd[c])
+                lo = -2.0 - float(D[j, c])
+                assert lo <= min(wd, 1e30) + 1.5e-3, (j, c, lo, wd)
+                continue
             if flagged[j, c]:
                 continue
             norms = [np.linalg.norm(qk - np.roll(keys[c], s)) for s in range(60)]

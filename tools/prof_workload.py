@@ -89,6 +89,14 @@ def main():
         d_q8 = torch.from_numpy(q8.reshape(8, 1200)).to(dev)
         pack8 = torch.zeros(8 * 160, dtype=torch.uint8, device=dev)
         work.append(lambda: scb.query_topk_sharded_dev(d_q8.data_ptr(), 8, 10, 99_950, 0, pack8.data_ptr()))
+    if "sc64" in only:  # the bench's batch: 64 queries per call against a 100k-keyframe shard
+        scc = ilsm.ScanContextDb(ctx)
+        for a in range(0, 100_000, 20_000):
+            scc.add(S.sc_database_range(a, a + 20_000, 100_000))
+        q64, _, _ = S.sc_chunked_queries(100_000, 64)
+        d_q64 = torch.from_numpy(q64.reshape(64, 1200)).to(dev)
+        pack64 = torch.zeros(64 * 160, dtype=torch.uint8, device=dev)
+        work.append(lambda: scc.query_topk_sharded_dev(d_q64.data_ptr(), 64, 10, 99_950, 0, pack64.data_ptr()))
     if "fe" in only:
         c3 = S.config1(n_map=20_000)
         cloud = c3["cloud"]
