@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <new>
@@ -76,6 +77,9 @@ struct SlamH {
   std::condition_variable wcv;
   bool stop = false;
   int maps_in_flight = 0;
+  // queue / mailbox occupancy mirrored in atomics: a stage that finds its input empty SPINS on these for up to ~100 us
+  // before it sleeps on the condition variable -- a futex wake-up costs 10-50 us, a third of a stage's time per frame
+  std::atomic<int> n_jobs{0}, n_results{0}, n_fjobs{0}, n_fres{0};
   // staged mode (ilsm_slam_create_staged): the three nodes as three stages, each with its own context (streams, scratch)
   // and host thread like the reference's three processes -- scanRegistration on ctx0 + fworker, laserOdometry on the
   // caller's context and thread, laserMapping on ctx2 + worker.  Frame k's front end, frame k-1's odometry and frame
@@ -116,6 +120,14 @@ struct SlamH {
   double phase_s[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [8..] mapping-stage detail (ILSM_STAGE_TRACE)
 };
 
+static inline void spin_until_nonzero(const std::atomic<int>& a, const bool* stop = nullptr) {
+  for (int i = 0; i < 4000 && a.load(std::memory_order_acquire) == 0 && !(stop && *stop); ++i) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 struct PhaseClock {
   double* acc;
   std::chrono::steady_clock::time_point t;
@@ -134,12 +146,14 @@ static void mapping_worker(SlamH* sp) {
   cudaSetDevice(c2.device);
   for (;;) {
     SlamH::MapJob j;
+    spin_until_nonzero(s.n_jobs, &s.stop);
     {
       std::unique_lock<std::mutex> lk(s.wmu);
       s.wcv.wait(lk, [&] { return !s.jobs.empty() || s.stop; });
       if (s.jobs.empty()) return;  // (stop is only raised once the queue has drained)
       j = s.jobs.front();
       s.jobs.pop_front();
+      s.n_jobs.fetch_sub(1, std::memory_order_relaxed);
     }
     SlamH::MapResult r;
     r.frame = j.frame;
@@ -173,6 +187,7 @@ static void mapping_worker(SlamH* sp) {
     {
       std::lock_guard<std::mutex> lk(s.wmu);
       s.results.push_back(r);
+      s.n_results.fetch_add(1, std::memory_order_release);
     }
     s.wcv.notify_all();
   }
@@ -182,6 +197,7 @@ static void post_mapping_job(SlamH& s, const SlamH::MapJob& j) {
   {
     std::lock_guard<std::mutex> lk(s.wmu);
     s.jobs.push_back(j);
+    s.n_jobs.fetch_add(1, std::memory_order_release);
   }
   s.maps_in_flight++;
   s.wcv.notify_all();
@@ -189,10 +205,12 @@ static void post_mapping_job(SlamH& s, const SlamH::MapJob& j) {
 
 // wait for the mapping stage's answer to its oldest job and hand it out
 static int take_mapping_result(SlamH& s, double q_map[4], double t_map[3], ilsm_slam_stats* stats, long long* frame = nullptr) {
+  spin_until_nonzero(s.n_results);
   std::unique_lock<std::mutex> lk(s.wmu);
   s.wcv.wait(lk, [&] { return !s.results.empty(); });
   const SlamH::MapResult r = s.results.front();
   s.results.pop_front();
+  s.n_results.fetch_sub(1, std::memory_order_relaxed);
   lk.unlock();
   s.maps_in_flight--;
   if (frame) *frame = r.frame;
@@ -235,12 +253,14 @@ static void frontend_worker(SlamH* sp) {
   cudaSetDevice(f.device);
   for (;;) {
     SlamH::FeJob j;
+    spin_until_nonzero(s.n_fjobs, &s.fstop);
     {
       std::unique_lock<std::mutex> lk(s.fmu);
       s.fcv.wait(lk, [&] { return s.fjob_posted || s.fstop; });
       if (s.fstop) return;
       j = s.fjob;
       s.fjob_posted = false;
+      s.n_fjobs.store(0, std::memory_order_relaxed);
     }
     SlamH::FeResult r;
     r.frame = j.frame, r.use_aloam = j.use_aloam;
@@ -253,15 +273,18 @@ static void frontend_worker(SlamH* sp) {
       std::lock_guard<std::mutex> lk(s.fmu);
       s.fres = r;
       s.fres_ready = true;
+      s.n_fres.store(1, std::memory_order_release);
     }
     s.fcv.notify_all();
   }
 }
 
 static int take_frontend_result(SlamH& s, SlamH::FeResult* out) {
+  spin_until_nonzero(s.n_fres);
   std::unique_lock<std::mutex> lk(s.fmu);
   s.fcv.wait(lk, [&] { return s.fres_ready; });
   s.fres_ready = false;
+  s.n_fres.store(0, std::memory_order_relaxed);
   s.fe_in_flight = false;
   *out = s.fres;
   if (out->rc) return fail(out->rc, out->err);
@@ -694,6 +717,7 @@ extern "C" ILSM_API int ilsm_slam_frame_staged(ilsm_slam* slam, const float* xyz
       std::lock_guard<std::mutex> lkf(s.fmu);
       s.fjob.xyzi = xyzi, s.fjob.n = n, s.fjob.stride = stride_bytes, s.fjob.use_aloam = use_aloam, s.fjob.frame = s.pushed;
       s.fjob_posted = true;
+      s.n_fjobs.store(1, std::memory_order_release);
     }
     s.fcv.notify_all();
     s.fe_in_flight = true;
