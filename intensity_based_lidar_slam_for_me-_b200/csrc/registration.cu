@@ -575,7 +575,11 @@ __device__ __forceinline__ constexpr int lt(int i, int j) { return i * (i + 1) /
 __device__ __forceinline__ constexpr int ut(int a, int b) { return a * 6 - a * (a - 1) / 2 + (b - a); }  // a <= b
 
 // A y = b for symmetric positive definite 6x6 (packed lower, destroyed) by in-place LDL^T with reciprocal pivots:
-// 6 divisions in all, everything in registers.
+// 6 divisions in all, everything in registers.  Measured alternatives (round 2, clock64 stamps around the update, 3.4-3.6 k
+// cycles with this solver): a division-free elimination on the packed triangle with the six reciprocals taken side by
+// side -- half the dependency depth on paper -- runs 3.65-4.0 k (its 39 live values spill in this non-inlined function);
+// keeping 1/radius and 1/model_cost_change as state, which removes two reciprocals from the chain, changes nothing
+// measurable.  The update is not a pure latency chain that shorter algebra would shrink.
 __device__ __forceinline__ bool ldlt_solve6(double (&m)[21], const double (&b)[6], double (&x)[6]) {
   // right-looking, in place: once column j is final (w_ij = L_ij d_j), the trailing sub-matrix is updated with
   // m_ic -= L_ij w_cj (one FMA per term) and the column is overwritten with L; no second array, 6 reciprocals
