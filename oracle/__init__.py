@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
+_REF_SCANREG = os.path.join(_HERE, "_ref", "libref_scanreg.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 _REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
@@ -404,6 +405,50 @@ def ref_functor_eval(ftype, p, a, b=(0, 0, 0), c=(0, 0, 0), s=1.0, qt=(0, 0, 0, 
     n = ref_functors().ref_functor_eval(int(ftype), _p(arr[0]), _p(arr[1]), _p(arr[2]), _p(arr[3]), C.c_double(s), _p(q), _p(t),
                                         _p(r), _p(J))
     return r[:n].copy(), J[:n].copy()
+
+
+_ref_scanreg = None
+
+
+def ref_scanreg():
+    """The reference's own LOAM front end (src/scanRegistration.cpp:227-589 cut out of its ROS node),
+    oracle/_ref/libref_scanreg.so (None when never built)."""
+    global _ref_scanreg
+    if _ref_scanreg is None:
+        if not os.path.exists(_REF_SCANREG):
+            build()
+        if not os.path.exists(_REF_SCANREG):
+            return None
+        r = C.CDLL(_REF_SCANREG)
+        r.ref_scanreg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 11
+        _ref_scanreg = r
+    return _ref_scanreg
+
+
+def ref_extract_features(cloud, min_range=0.3, n_scans=64):
+    """The reference code's laserCloudHandler numeric body on `cloud`: dict with the ring-ordered cloud, curvature, label,
+    the four feature clouds (xyzi rows; less_flat after the oracle's VoxelGrid stand-in, less_flat_raw before it) and
+    scanStartInd / scanEndInd."""
+    c = _f32(cloud)
+    n = len(c)
+    cap = n + 8
+    bufs = {k: np.zeros((cap, 4), np.float32) for k in ("cloud", "sharp", "less_sharp", "flat", "less_flat", "less_flat_raw")}
+    curv = np.zeros(cap, np.float32)
+    label = np.zeros(cap, np.int32)
+    rs, re_ = np.zeros(64, np.int32), np.zeros(64, np.int32)
+    cnt = np.zeros(8, np.int32)
+    r = ref_scanreg()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libref_scanreg.so not available")
+    rc = r.ref_scanreg(_p(c), n, c.strides[0], int(n_scans), C.c_double(min_range), cap, _p(bufs["cloud"]), _p(curv), _p(label),
+                       _p(bufs["sharp"]), _p(bufs["less_sharp"]), _p(bufs["flat"]), _p(bufs["less_flat"]), _p(bufs["less_flat_raw"]),
+                       _p(rs), _p(re_), _p(cnt))
+    if rc != 0:
+        raise RuntimeError("ref_scanreg failed")
+    out = {k: bufs[k][:cnt[i]].copy() for i, k in enumerate(("cloud", "sharp", "less_sharp", "flat", "less_flat", "less_flat_raw"))}
+    out["curvature"], out["label"] = curv[:cnt[0]].copy(), label[:cnt[0]].copy()
+    out["ring_start"], out["ring_end"] = rs, re_
+    return out
 
 
 _ref_ikd = None

@@ -129,3 +129,27 @@ def test_frame_to_pose_pipeline_matches_oracle(ctx, oracle_mod, ilsm, cfg_full):
     assert rep.pass_[1].num_edge_factors == wnf[2] and rep.pass_[1].num_plane_factors == wnf[3]
     assert np.linalg.norm(t - c["t_true"]) < 0.05
     mc.close(), ms.close()
+
+
+@pytest.mark.parametrize("name", ["open", "corridor", "fov22"])
+def test_feature_extraction_matches_reference_code_golden(ctx, name):
+    """The CUDA front end against outputs of the REFERENCE's own code (scanRegistration.cpp:227-589 compiled from the
+    reference tree, tests/golden/make_golden_scanreg.py): ring-ordered cloud, ring bounds, curvature, labels and the four
+    feature clouds, bit for bit on xyz (relTime differs from libm's atan2f by an ulp on the GPU and is compared to 1.6e-5
+    elsewhere; it is unused downstream with DISTORTION 0)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_scanreg import CLOUDS, KEYS, as_reference_outputs, digest, frames
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scanreg_reference.npz"))
+    cloud = dict(frames())[name]
+    assert digest(cloud) == str(gold[name + "/input_sha256"])
+    got = as_reference_outputs(ctx.extract_features(cloud))
+    for k in KEYS:
+        assert tuple(gold[f"{name}/{k}/shape"]) == got[k].shape, (name, k)
+        if k in CLOUDS:
+            assert digest(np.ascontiguousarray(got[k][:, :3])) == str(gold[f"{name}/{k}/xyz_sha256"]), (name, k)
+        else:
+            assert digest(np.ascontiguousarray(got[k])) == str(gold[f"{name}/{k}/sha256"]), (name, k)
+
+
+
