@@ -20,6 +20,7 @@ _LIB = os.path.join(_HERE, "_build", "libilsm_oracle.so")
 _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
 _REF_SCANREG = os.path.join(_HERE, "_ref", "libref_scanreg.so")
+_REF_LASERODOM = os.path.join(_HERE, "_ref", "libref_laserodom.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 _REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
@@ -449,6 +450,44 @@ def ref_extract_features(cloud, min_range=0.3, n_scans=64):
     out["curvature"], out["label"] = curv[:cnt[0]].copy(), label[:cnt[0]].copy()
     out["ring_start"], out["ring_end"] = rs, re_
     return out
+
+
+_ref_laserodom = None
+
+
+def ref_laserodom():
+    """The reference's own scan-to-scan association (src/laserOdometry.cpp:417-713 cut out of its node),
+    oracle/_ref/libref_laserodom.so (None when never built)."""
+    global _ref_laserodom
+    if _ref_laserodom is None:
+        if not os.path.exists(_REF_LASERODOM):
+            build()
+        if not os.path.exists(_REF_LASERODOM):
+            return None
+        r = C.CDLL(_REF_LASERODOM)
+        r.ref_laserodom_associate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        _ref_laserodom = r
+    return _ref_laserodom
+
+
+def ref_odom_associate(last_corner, last_surf, sharp, flat, qt):
+    """The residual blocks the reference code builds at pose qt = (qx, qy, qz, qw, tx, ty, tz): (edge (Ne, 10) = curr 3,
+    last_point_a 3, last_point_b 3, s;  plane (Np, 13) = curr 3, last_point_j / l / m 3 each, s;  the reference's own
+    (corner_correspondence, plane_correspondence) counters)."""
+    r = ref_laserodom()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libref_laserodom.so not available")
+    cl = [np.ascontiguousarray(np.asarray(a, np.float32)[:, :4]) for a in (last_corner, last_surf, sharp, flat)]
+    qt = np.ascontiguousarray(qt, np.float64)
+    q, t = qt[:4].copy(), qt[4:].copy()
+    edge = np.zeros((len(cl[2]) + 1, 10))
+    plane = np.zeros((len(cl[3]) + 1, 13))
+    cnt = np.zeros(4, np.int32)
+    rc = r.ref_laserodom_associate(_p(cl[0]), len(cl[0]), _p(cl[1]), len(cl[1]), _p(cl[2]), len(cl[2]), _p(cl[3]), len(cl[3]), _p(q), _p(t),
+                                   _p(edge), _p(plane), _p(cnt))
+    if rc != 0:
+        raise RuntimeError(f"ref_laserodom_associate failed ({rc})")
+    return edge[:cnt[0]].copy(), plane[:cnt[1]].copy(), (int(cnt[2]), int(cnt[3]))
 
 
 _ref_ikd = None

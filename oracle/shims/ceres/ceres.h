@@ -14,4 +14,56 @@ class AutoDiffCostFunction : public CostFunction {
   ~AutoDiffCostFunction() override { delete functor_; }
   Functor* functor_;
 };
+
+// The problem-building API as far as laserOdometry.cpp:417-713 uses it.  This Problem does not optimise anything: it
+// RECORDS the residual blocks it is handed (oracle/ref_laserodom.cpp reads the functors back to compare the reference's
+// data association with the oracle's), and Solve() leaves the parameters where they are.
+class LossFunction {
+ public:
+  virtual ~LossFunction() {}
+};
+class HuberLoss : public LossFunction {
+ public:
+  explicit HuberLoss(double a) : a_(a) {}
+  double a_;
+};
+class LocalParameterization {
+ public:
+  virtual ~LocalParameterization() {}
+};
+class EigenQuaternionParameterization : public LocalParameterization {};
+class Problem {
+ public:
+  struct Options {};
+  Problem() {}
+  explicit Problem(const Options&) {}
+  ~Problem();
+  void AddParameterBlock(double*, int) {}
+  void AddParameterBlock(double*, int, LocalParameterization* p) { params_ = p; }
+  void AddResidualBlock(CostFunction* f, LossFunction* l, double*, double*) {
+    loss_ = l;
+    if (sink) sink(f, sink_arg);
+    blocks_++;
+    delete f;
+  }
+  static void (*sink)(CostFunction*, void*);
+  static void* sink_arg;
+  int blocks_ = 0;
+  LossFunction* loss_ = nullptr;
+  LocalParameterization* params_ = nullptr;
+};
+inline Problem::~Problem() {
+  delete loss_;
+  delete params_;
+}
+enum LinearSolverType { DENSE_QR };
+struct Solver {
+  struct Options {
+    LinearSolverType linear_solver_type = DENSE_QR;
+    int max_num_iterations = 50;
+    bool minimizer_progress_to_stdout = false;
+  };
+  struct Summary {};
+};
+inline void Solve(const Solver::Options&, Problem*, Solver::Summary*) {}
 }  // namespace ceres

@@ -4,6 +4,7 @@
 oracle/patches/scanreg_extract.py) on three seeded synthetic frames.  The frames are regenerated from their seeds by the
 tests (numpy's generator is deterministic), so only the outputs are stored: sizes, SHA-256 of every output array, and the
 per-label histogram.  Run in the build container (needs /root/reference):  python tests/golden/make_golden_scanreg.py"""
+import functools
 import hashlib
 import os
 import sys
@@ -17,6 +18,15 @@ import ilsm_b200 as ilsm  # noqa: E402
 
 
 def frames():
+    return _frames()
+
+
+@functools.lru_cache(maxsize=1)
+def _frames():
+    return tuple(_gen_frames())
+
+
+def _gen_frames():
     S = ilsm.synth
     scene = S.Scene()
     q0, t0 = S.default_pose()

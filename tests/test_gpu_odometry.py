@@ -45,6 +45,29 @@ def test_odometry_association_parity(ctx, oracle_mod, two_frames, pose):
     mc.close(), ms.close()
 
 
+@pytest.mark.parametrize("pose", ["identity", "moved"])
+def test_odometry_association_matches_reference_code_golden(ctx, pose):
+    """The CUDA association against the residual blocks the REFERENCE's own code builds (laserOdometry.cpp:417-713 compiled
+    from the reference tree with a recording ceres::Problem, tests/golden/make_golden_laserodom.py): same sharp / flat
+    points paired, the edge factors' two points identical, the plane factors' (j, l, m) as the same unit normal + offset."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_laserodom import POSES, feature_clouds, plane_normal_form
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "laserodom_reference.npz"))
+    lc, ls, sh, fl = feature_clouds()
+    qt = POSES[pose]
+    mc, ms = ctx.new_map().set_input_cloud(lc, 1.0), ctx.new_map().set_input_cloud(ls, 1.0)
+    got = ctx.odometry(mc, ms, sh, fl, qt[:4], qt[4:], factors_only=True)
+    edge, plane = gold[pose + "/edge"], gold[pose + "/plane"]
+    fe, fp = got[got["type"] == 1], got[got["type"] == 2]
+    assert len(fe) == len(edge) and len(fp) == len(plane)
+    assert np.array_equal(fe["p"], edge[:, 0:3]) and np.array_equal(fe["a"], edge[:, 3:6]) and np.array_equal(fe["b"], edge[:, 6:9])
+    assert np.array_equal(fp["p"], plane[:, 0:3])
+    n, d = plane_normal_form(plane)
+    assert np.abs(fp["a"] - n).max() <= 1e-12 and np.abs(fp["b"][:, 0] - d).max() <= 1e-10
+    mc.close(), ms.close()
+
+
 def test_odometry_solve_parity(ctx, oracle_mod, ilsm, two_frames):
     d = two_frames
     mc, ms = _maps(ctx, d)
