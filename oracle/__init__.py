@@ -21,6 +21,7 @@ _REF = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
 _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
 _REF_SCANREG = os.path.join(_HERE, "_ref", "libref_scanreg.so")
 _REF_LASERODOM = os.path.join(_HERE, "_ref", "libref_laserodom.so")
+_REF_LASERMAPPING = os.path.join(_HERE, "_ref", "libref_lasermapping.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 _REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
@@ -490,6 +491,52 @@ def ref_odom_associate(last_corner, last_surf, sharp, flat, qt):
     return edge[:cnt[0]].copy(), plane[:cnt[1]].copy(), (int(cnt[2]), int(cnt[3]))
 
 
+_ref_lasermapping = None
+
+
+def ref_lasermapping():
+    """The reference's own map maintenance (src/laserMapping.cpp:327-623, 875-945, 984-1004 cut out of process()),
+    oracle/_ref/libref_lasermapping.so (None when never built)."""
+    global _ref_lasermapping
+    if _ref_lasermapping is None:
+        if not os.path.exists(_REF_LASERMAPPING):
+            build()
+        if not os.path.exists(_REF_LASERMAPPING):
+            return None
+        r = C.CDLL(_REF_LASERMAPPING)
+        r.ref_lasermapping_reset.argtypes = [C.c_float, C.c_float]
+        r.ref_lasermapping_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        r.ref_lasermapping_cube.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _ref_lasermapping = r
+    return _ref_lasermapping
+
+
+class RefLaserMapping:
+    """The reference code's cube map (global state of the compiled fragment: one instance at a time).  frame() = one
+    process() iteration WITHOUT the optimisation block: (pose used for the insertion (7,), window centre (3,), valid cube
+    indices in the reference's order, (map corner, map surf, stack corner, stack surf) sizes)."""
+
+    def __init__(self, line_res=0.4, plane_res=0.8):
+        self._r = ref_lasermapping()
+        if self._r is None:
+            raise RuntimeError("oracle/_ref/libref_lasermapping.so not available")
+        self._r.ref_lasermapping_reset(line_res, plane_res)
+
+    def frame(self, corner_last, surf_last, qt_odom):
+        c, s = CubeMap._x4(corner_last), CubeMap._x4(surf_last)
+        qt = np.ascontiguousarray(qt_odom, np.float64)
+        q, t = qt[:4].copy(), qt[4:].copy()
+        out, cen, nv, valid, sizes = np.zeros(7), np.zeros(3, np.int32), np.zeros(1, np.int32), np.zeros(125, np.int32), np.zeros(4, np.int32)
+        self._r.ref_lasermapping_frame(_p(c), len(c), _p(s), len(s), _p(q), _p(t), _p(out), _p(cen), _p(nv), _p(valid), _p(sizes))
+        return out, cen, valid[:nv[0]].copy(), sizes
+
+    def cube(self, which, index):
+        n = self._r.ref_lasermapping_cube(which, index, None, 0)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        self._r.ref_lasermapping_cube(which, index, _p(out), n)
+        return out[:n]
+
+
 _ref_ikd = None
 
 
@@ -598,6 +645,11 @@ class CubeMap:
         out = np.zeros((len(a), 4), np.float32)
         out[:, :min(4, a.shape[1])] = a[:, :4]
         return out
+
+    def set_solve(self, enabled: bool):
+        """False: frames keep the pose transformAssociateToMap predicts (map-logic comparisons against the reference code)."""
+        self._l.orc_cubemap_set_solve.argtypes = [C.c_void_p, C.c_int]
+        self._l.orc_cubemap_set_solve(self._h, 1 if enabled else 0)
 
     def insert_world(self, corner, surf, centre):
         c, s = self._x4(corner), self._x4(surf)

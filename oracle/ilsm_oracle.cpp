@@ -1073,6 +1073,7 @@ namespace {
 struct CubeMap {
   static constexpr int W = 21, H = 21, D = 11, NUM = W * H * D;
   int cenW = 10, cenH = 10, cenD = 5;
+  bool solve = true;  // false: the frame keeps the pose transformAssociateToMap predicts (map-logic comparisons, tests/test_ref_lasermapping_cpu.py)
   float line_res = 0.4f, plane_res = 0.8f;
   std::vector<std::vector<float>> corner, surf;  // per cube, packed xyzi
   Quat q_wmap_wodom{0, 0, 0, 1};
@@ -1190,7 +1191,7 @@ ORC_API void orc_cubemap_frame(void* h, const float* corner_last, int nc, const 
   st->n_map_corner = (int)map_c.size() / 4, st->n_map_surf = (int)map_s.size() / 4;
   st->n_stack_corner = nsc, st->n_stack_surf = nss, st->n_valid = m.n_valid;
   double qt[7] = {q_w.x, q_w.y, q_w.z, q_w.w, t_w.x, t_w.y, t_w.z};
-  if (st->n_map_corner > 10 && st->n_map_surf > 50) {
+  if (m.solve && st->n_map_corner > 10 && st->n_map_surf > 50) {
     int32_t nfac[4];
     orc_register_aloam(map_c.data(), st->n_map_corner, map_s.data(), st->n_map_surf, 16, stack_c.data(), nsc, stack_s.data(),
                        nss, 16, qt, 2, 4, summaries, nfac);
@@ -1218,6 +1219,9 @@ ORC_API void orc_cubemap_frame(void* h, const float* corner_last, int nc, const 
   for (int i = 0; i < 7; ++i) qt_out[i] = qt[i];
   st->cen[0] = m.cenW, st->cen[1] = m.cenH, st->cen[2] = m.cenD;
 }
+
+// map-logic comparisons against the reference's own code run both sides without the registration
+ORC_API void orc_cubemap_set_solve(void* h, int enabled) { static_cast<CubeMap*>(h)->solve = enabled != 0; }
 
 // contents of one cube (array index) of the current window; returns the point count
 ORC_API int orc_cubemap_cube(void* h, int which /*0 corner, 1 surf*/, int cube_index, float* out_xyzi, int cap) {

@@ -101,3 +101,28 @@ def test_guard_skips_optimisation_on_empty_map(ctx, oracle_mod, ilsm, cfg_small)
     assert np.array_equal(gq, c["q_true"]) and np.array_equal(gt, c["t_true"])
     _compare_cubes(cm, ocm, _valid_indices(c["t_true"]))
     cm.close()
+
+
+def test_cube_map_matches_reference_code_golden(ctx, ilsm):
+    """The CUDA cube map against the state of the REFERENCE's own code (laserMapping.cpp's window roll, gather, stack
+    VoxelGrids, insertion and per-cube VoxelGrid compiled from the reference tree, tests/golden/make_golden_lasermapping.py)
+    after a 61-frame walk that rolls the 21x21x11 window along every axis in both directions.  The optimisation block is
+    switched off on both sides (min_corner_map beyond any map size), so this compares the map logic: poses, window centre,
+    valid cubes, sizes per frame, and every cube of both maps bit for bit at the end."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_lasermapping import cube_state, walk
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lasermapping_reference.npz"))
+    cm = ilsm.CubeMap(ctx, 0.4, 0.8, 4096)
+    opts = ilsm.default_opts()
+    opts.min_corner_map = opts.min_surf_map = 1 << 30
+    for k, (corner, surf, qt) in enumerate(walk()):
+        q, t, rep, st = cm.frame(corner, surf, qt[:4], qt[4:], opts)
+        assert st.ran_optimization == 0 and st.flags == 0
+        assert np.array_equal(np.concatenate([q, t]), gold["poses"][k]), k
+        assert tuple(st.cen) == tuple(gold["cen"][k]) and st.n_valid == gold["n_valid"][k], k
+        assert (st.n_map_corner, st.n_map_surf, st.n_stack_corner, st.n_stack_surf) == tuple(gold["sizes"][k]), k
+    counts, digest = cube_state(cm.cube)
+    assert np.array_equal(counts, gold["counts"])
+    assert digest == str(gold["cubes_sha256"])
+    cm.close()
