@@ -507,6 +507,7 @@ def ref_lasermapping():
         r.ref_lasermapping_reset.argtypes = [C.c_float, C.c_float]
         r.ref_lasermapping_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
         r.ref_lasermapping_cube.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        r.ref_lasermapping_associate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         _ref_lasermapping = r
     return _ref_lasermapping
 
@@ -535,6 +536,22 @@ class RefLaserMapping:
         out = np.zeros((max(n, 1), 4), np.float32)
         self._r.ref_lasermapping_cube(which, index, _p(out), n)
         return out[:n]
+
+
+def ref_map_associate(map_corner, map_surf, stack_corner, stack_surf, qt):
+    """The residual blocks the reference's scan-to-map association (laserMapping.cpp:624-873) builds at pose qt: (edge (Ne, 10)
+    = curr 3, point_a 3, point_b 3, s;  plane (Np, 7) = curr 3, unit normal 3, negative_OA_dot_norm)."""
+    r = ref_lasermapping()
+    if r is None:
+        raise RuntimeError("oracle/_ref/libref_lasermapping.so not available")
+    cl = [CubeMap._x4(a) for a in (map_corner, map_surf, stack_corner, stack_surf)]
+    qt = np.ascontiguousarray(qt, np.float64)
+    edge, plane, cnt = np.zeros((len(cl[2]) + 1, 10)), np.zeros((len(cl[3]) + 1, 7)), np.zeros(2, np.int32)
+    rc = r.ref_lasermapping_associate(_p(cl[0]), len(cl[0]), _p(cl[1]), len(cl[1]), _p(cl[2]), len(cl[2]), _p(cl[3]), len(cl[3]), _p(qt),
+                                      _p(edge), _p(plane), _p(cnt))
+    if rc != 0:
+        raise RuntimeError(f"ref_lasermapping_associate failed ({rc})")
+    return edge[:cnt[0]].copy(), plane[:cnt[1]].copy()
 
 
 _ref_ikd = None

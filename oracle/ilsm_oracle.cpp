@@ -334,6 +334,23 @@ struct OrcFactor {
   double b[3];   // edge: point_b ; plane: b[0] = negative_OA_dot_norm
 };
 
+// the two dense kernels behind the fits, exported for oracle/ref_lasermapping.cpp: the reference's association block is
+// compiled against an Eigen stand-in whose SelfAdjointEigenSolver / ColPivHouseholderQR forward here (Eigen is not installed)
+ORC_API void orc_eig3(const double A[9], double w[3], double V[9]) {
+  double a[3][3], v[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = A[3 * i + j];
+  eig3(a, w, v);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[3 * i + j] = v[i][j];
+}
+ORC_API void orc_lstsq5x3(const double A[15], const double b[5], double x[3]) {
+  double a[5][3];
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = A[3 * i + j];
+  lstsq5x3(a, b, x);
+}
+
 namespace {
 
 bool fit_line(const float nb[5][3], OrcFactor* f) {

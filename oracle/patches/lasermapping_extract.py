@@ -17,6 +17,9 @@ stand-ins (pcl::PointCloud, pcl::VoxelGrid = the oracle's restatement, Eigen = o
                  :875-945  transformUpdate, insertion                      (the optimisation block :624-874 is NOT included:
                  :984-1004 per-cube VoxelGrid of the valid cubes            both sides of the comparison keep the predicted pose)
                  i.e. the duplicated :946-983 is dropped, as upstream A-LOAM has it (one insertion, one t_filter)
+  optimise.inc   :624-873  the guarded optimisation block on its own (two passes of 5-NN association, line / plane fits,
+                 residual blocks, ceres::Solve), unmodified -- ref_lasermapping_associate runs it with a ceres::Problem
+                 that records the blocks and a Solve that does nothing
 
 usage: lasermapping_extract.py <reference laserMapping.cpp> <output directory>   (a temporary build directory: the
 fragments are never stored in this repository -- only oracle/_ref/libref_lasermapping.so is kept, git-ignored)
@@ -29,6 +32,7 @@ PINNED_SHA256 = "0ad4912266f6afdcefa6ffdc815bbf5908cf7ac5ef85624f77ee9e8e39939c2
 GLOBALS = [(63, 115), (123, 129)]
 TRANSFORM = (138, 172)
 BODY = [(327, 623), (875, 945), (984, 1004)]
+OPTIMISE = (624, 873)
 
 
 def main(src, out_dir):
@@ -40,7 +44,9 @@ def main(src, out_dir):
     assert "transformAssociateToMap();" in lines[327 - 1] and "transformUpdate();" in lines[875 - 1] and "TicToc t_filter;" in lines[984 - 1]
     cut = lambda ranges: "\n".join("\n".join(lines[a - 1:b]) for a, b in ranges) + "\n"
     os.makedirs(out_dir, exist_ok=True)
-    for name, text in (("globals.inc", cut(GLOBALS)), ("transform.inc", cut([TRANSFORM])), ("body.inc", cut(BODY))):
+    assert "if (laserCloudCornerFromMapNum > 10" in lines[OPTIMISE[0] - 1]
+    for name, text in (("globals.inc", cut(GLOBALS)), ("transform.inc", cut([TRANSFORM])), ("body.inc", cut(BODY)),
+                       ("optimise.inc", cut([OPTIMISE]))):
         with open(os.path.join(out_dir, name), "w", encoding="utf-8") as f:
             f.write(text)
 

@@ -5,8 +5,11 @@
 // index with its negative fix-up, the six roll directions, the valid-cube order, the cube index of every inserted point --
 // can be compared with the reference code cube by cube.  The guarded optimisation (:624-873) is left out: both sides of the
 // comparison keep the pose transformAssociateToMap predicts.
-// Stand-ins (not the reference): pcl::PointCloud, pcl::VoxelGrid (the oracle's restatement, orc_voxelgrid), Eigen
-// (oracle/shims/eigen3, the oracle's quaternion arithmetic), pcl::KdTreeFLANN (declared by the globals, unused here).
+// ref_lasermapping_associate runs that block on its own with a recording ceres::Problem: the 5-NN gate, the line test
+// (lambda_2 > 3 lambda_1, point_a / point_b = centre +- 0.1 v_2) and the plane test (all five within 0.2) of :640-796.
+// Stand-ins (not the reference): pcl::PointCloud, pcl::VoxelGrid (the oracle's restatement, orc_voxelgrid), pcl::KdTreeFLANN
+// (exact brute force), Eigen (oracle/shims/eigen3: the oracle's quaternion arithmetic, and its eigen / QR kernels behind
+// SelfAdjointEigenSolver / colPivHouseholderQr), ceres::Problem (records) and ceres::Solve (does nothing).
 // Built only into oracle/_ref/libref_lasermapping.so (git-ignored); nothing in the product path links it.
 #include <cmath>
 #include <cstdint>
@@ -15,10 +18,11 @@
 #include <memory>
 #include <vector>
 
-#include <eigen3/Eigen/Dense>
-#include <pcl/point_types.h>
-
 #include "tic_toc.h"
+#include "lidarFeaturePointsFunction.hpp"  // the reference's functors (LidarEdgeFactor / LidarPlaneNormFactor), on the shims
+
+void (*ceres::Problem::sink)(ceres::CostFunction*, void*) = nullptr;
+void* ceres::Problem::sink_arg = nullptr;
 
 extern "C" int orc_voxelgrid(const float* in, int n, int stride_bytes, int ioff, float leaf, float* out_xyzi);  // ilsm_oracle_frontend.cpp
 
@@ -36,8 +40,26 @@ struct PointCloud {
   }
 };
 template <typename PointT>
-struct KdTreeFLANN {
+struct KdTreeFLANN {  // exact brute-force k-NN, float L2 as FLANN's L2_Simple evaluates it, ascending (distance, index)
   typedef std::shared_ptr<KdTreeFLANN<PointT>> Ptr;
+  typename PointCloud<PointT>::Ptr cloud;
+  void setInputCloud(const typename PointCloud<PointT>::Ptr& c) { cloud = c; }
+  int nearestKSearch(const PointT& q, int k, std::vector<int>& idx, std::vector<float>& d2) const {
+    idx.assign(k, 0), d2.assign(k, INFINITY);
+    int found = 0;
+    for (int i = 0; i < (int)cloud->points.size(); ++i) {
+      const PointT& p = cloud->points[i];
+      const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+      const float d = (dx * dx + dy * dy) + dz * dz;
+      if (found < k || d < d2[k - 1]) {  // insertion keeps ties in index order
+        int j = found < k ? found : k - 1;
+        while (j > 0 && d2[j - 1] > d) d2[j] = d2[j - 1], idx[j] = idx[j - 1], --j;
+        d2[j] = d, idx[j] = i;
+        if (found < k) ++found;
+      }
+    }
+    return found;
+  }
 };
 template <typename PointT>
 struct VoxelGrid {  // the ORACLE's restatement of PCL's filter, not PCL
@@ -100,6 +122,52 @@ extern "C" void ref_lasermapping_frame(const float* corner_last, int nc, const f
 #undef printf
   for (int i = 0; i < 7; ++i) qt_w[i] = parameters[i];
   cen[0] = laserCloudCenWidth, cen[1] = laserCloudCenHeight, cen[2] = laserCloudCenDepth;
+}
+
+// The guarded optimisation block (:624-873) on its own, at pose qt (q = x, y, z, w; t) against the given map and stack clouds
+// (packed xyzi): returns the residual blocks of the last pass -- edge: curr 3, point_a 3, point_b 3, s; plane: curr 3, unit
+// normal 3, negative_OA_dot_norm.  The stand-in Solve leaves the pose alone, so both passes build the same blocks (checked).
+extern "C" int ref_lasermapping_associate(const float* map_corner, int n_mc, const float* map_surf, int n_ms, const float* stack_corner,
+                                          int n_sc, const float* stack_surf, int n_ss, const double* qt, double* edge_out, double* plane_out,
+                                          int32_t* counts) {
+  fill(*laserCloudCornerFromMap, map_corner, n_mc), fill(*laserCloudSurfFromMap, map_surf, n_ms);
+  pcl::PointCloud<PointType>::Ptr laserCloudCornerStack(new pcl::PointCloud<PointType>());  // locals of process() (:595-603)
+  pcl::PointCloud<PointType>::Ptr laserCloudSurfStack(new pcl::PointCloud<PointType>());
+  fill(*laserCloudCornerStack, stack_corner, n_sc), fill(*laserCloudSurfStack, stack_surf, n_ss);
+  int laserCloudCornerFromMapNum = n_mc, laserCloudSurfFromMapNum = n_ms;
+  int laserCloudCornerStackNum = n_sc, laserCloudSurfStackNum = n_ss;
+  for (int i = 0; i < 7; ++i) parameters[i] = qt[i];
+  struct Captured {
+    std::vector<double> edge, plane;
+  } cap;
+  ceres::Problem::sink_arg = &cap;
+  ceres::Problem::sink = [](ceres::CostFunction* f, void* arg) {
+    Captured& c = *static_cast<Captured*>(arg);
+    if (auto* e = dynamic_cast<ceres::AutoDiffCostFunction<LidarEdgeFactor, 3, 4, 3>*>(f)) {
+      const LidarEdgeFactor& k = *e->functor_;
+      for (const Eigen::Vector3d* v : {&k.curr_point, &k.last_point_a, &k.last_point_b}) c.edge.insert(c.edge.end(), {v->x(), v->y(), v->z()});
+      c.edge.push_back(k.s);
+    } else if (auto* p = dynamic_cast<ceres::AutoDiffCostFunction<LidarPlaneNormFactor, 1, 4, 3>*>(f)) {
+      const LidarPlaneNormFactor& k = *p->functor_;
+      for (const Eigen::Vector3d* v : {&k.curr_point, &k.plane_unit_norm}) c.plane.insert(c.plane.end(), {v->x(), v->y(), v->z()});
+      c.plane.push_back(k.negative_OA_dot_norm);
+    }
+  };
+#define printf(...) ((void)0)
+  {
+#include "optimise.inc"
+  }
+#undef printf
+  ceres::Problem::sink = nullptr;
+  const size_t ne = cap.edge.size() / 10 / 2, np = cap.plane.size() / 7 / 2;
+  if (cap.edge.size() != ne * 20 || cap.plane.size() != np * 14) return -1;
+  if (memcmp(cap.edge.data(), cap.edge.data() + ne * 10, ne * 10 * sizeof(double)) ||
+      memcmp(cap.plane.data(), cap.plane.data() + np * 7, np * 7 * sizeof(double)))
+    return -2;
+  memcpy(edge_out, cap.edge.data(), ne * 10 * sizeof(double));
+  memcpy(plane_out, cap.plane.data(), np * 7 * sizeof(double));
+  counts[0] = (int)ne, counts[1] = (int)np;
+  return 0;
 }
 
 extern "C" int ref_lasermapping_cube(int which, int index, float* out_xyzi, int cap) {

@@ -62,6 +62,8 @@ struct Solver {
     LinearSolverType linear_solver_type = DENSE_QR;
     int max_num_iterations = 50;
     bool minimizer_progress_to_stdout = false;
+    bool check_gradients = false;
+    double gradient_check_relative_precision = 1e-8;
   };
   struct Summary {};
 };

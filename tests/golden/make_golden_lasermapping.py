@@ -4,6 +4,8 @@
 oracle/Makefile through oracle/patches/lasermapping_extract.py) after a seeded 61-frame walk that rolls the 21x21x11 window
 along every axis in both directions: per frame the insertion pose, the window centre, the number of valid cubes and the
 map / stack sizes; at the end the point count of every cube and one SHA-256 over all cube contents in index order.
+Also the residual blocks of the reference's scan-to-map association (:624-873, recording ceres::Problem) on the config-1
+shape: the 5-NN gate, the line / plane tests and point_a / point_b / unit normals as the reference code builds them.
 Run in the build container (needs /root/reference):  python tests/golden/make_golden_lasermapping.py"""
 import hashlib
 import os
@@ -44,8 +46,17 @@ def cube_state(cube_fn):
     return counts, h.hexdigest()
 
 
+def association_case():
+    """Map clouds, stacks and the initial pose of the config-1 shape (20 k-point map) for the scan-to-map association."""
+    import ilsm_b200 as ilsm
+    c = ilsm.synth.config1(n_map=20_000)
+    return c["map_corner"], c["map_surf"], c["corner"], c["surf"], np.concatenate([c["q0"], c["t0"]])
+
+
 if __name__ == "__main__":
     import oracle
+    edge, plane = oracle.ref_map_associate(*association_case())
+    print("association blocks", edge.shape, plane.shape)
     ref = oracle.RefLaserMapping(0.4, 0.8)
     poses, cens, nvalid, sizes = [], [], [], []
     for corner, surf, qt in walk():
@@ -55,4 +66,5 @@ if __name__ == "__main__":
     print("frames", len(poses), "occupied cubes", int((counts > 0).sum()), "points", int(counts.sum()), "centre changes",
           sum(tuple(a) != tuple(b) for a, b in zip(cens[1:], cens[:-1])))
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lasermapping_reference.npz"), poses=np.array(poses),
-                        cen=np.array(cens), n_valid=np.array(nvalid), sizes=np.array(sizes), counts=counts, cubes_sha256=digest)
+                        cen=np.array(cens), n_valid=np.array(nvalid), sizes=np.array(sizes), counts=counts, cubes_sha256=digest,
+                        assoc_edge=edge, assoc_plane=plane)

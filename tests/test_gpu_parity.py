@@ -166,6 +166,28 @@ def test_associate_parity(ctx, oracle_mod, cfg_small):
     mc.close(), ms.close()
 
 
+def test_associate_matches_reference_code_golden(ctx):
+    """The CUDA association against the residual blocks the REFERENCE's own code builds (laserMapping.cpp:624-873 compiled
+    from the reference tree with a recording ceres::Problem, tests/golden/make_golden_lasermapping.py): the same stack points
+    pass the 5-NN gate and the line / plane tests, and point_a / point_b / unit normal / offset agree (the fits run on
+    different eigen / QR kernels: 1e-9)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_lasermapping import association_case
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lasermapping_reference.npz"))
+    mcn, msn, c, s, qt = association_case()
+    mc, ms = ctx.new_map().set_input_cloud(mcn), ctx.new_map().set_input_cloud(msn)
+    fac = ctx.associate(mc, ms, c, s, qt[:4], qt[4:])
+    fac = fac[0] if isinstance(fac, tuple) else fac
+    edge, plane = gold["assoc_edge"], gold["assoc_plane"]
+    fe, fp = fac[fac["type"] == 1], fac[fac["type"] == 2]
+    assert len(fe) == len(edge) and len(fp) == len(plane)
+    assert np.array_equal(fe["p"], edge[:, 0:3]) and np.array_equal(fp["p"], plane[:, 0:3])
+    assert np.abs(fe["a"] - edge[:, 3:6]).max() <= 1e-9 and np.abs(fe["b"] - edge[:, 6:9]).max() <= 1e-9
+    assert np.abs(fp["a"] - plane[:, 3:6]).max() <= 1e-9 and np.abs(fp["b"][:, 0] - plane[:, 6]).max() <= 1e-9
+    mc.close(), ms.close()
+
+
 def test_eval_normal_eq_parity(ctx, oracle_mod, cfg_small):
     c = cfg_small
     mc, ms = _maps(ctx, c)

@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-from make_golden_lasermapping import cube_state, walk  # noqa: E402
+from make_golden_lasermapping import association_case, cube_state, walk  # noqa: E402
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "lasermapping_reference.npz"))
 
@@ -53,3 +53,33 @@ def test_oracle_cube_map_equals_reference_live(oracle_mod):
         if k == 30:  # every cube, mid-way (and at the end)
             assert cube_state(ref.cube)[1] == cube_state(m.cube)[1], k
     assert cube_state(ref.cube)[1] == cube_state(m.cube)[1]
+
+
+def check_association(f, edge, plane, tol):
+    fe, fp = f[f["type"] == 1], f[f["type"] == 2]
+    assert len(fe) == len(edge) and len(fp) == len(plane) and len(edge) > 100 and len(plane) > 500
+    assert np.array_equal(fe["p"], edge[:, 0:3]) and np.array_equal(fp["p"], plane[:, 0:3])  # the same stack points pass the tests
+    assert np.abs(fe["a"] - edge[:, 3:6]).max() <= tol and np.abs(fe["b"] - edge[:, 6:9]).max() <= tol
+    assert np.abs(fp["a"] - plane[:, 3:6]).max() <= tol and np.abs(fp["b"][:, 0] - plane[:, 6]).max() <= tol
+
+
+def test_oracle_map_association_equals_reference_golden(oracle_mod):
+    """laserMapping.cpp:624-873 compiled with a recording ceres::Problem: which stack points get a factor (5-NN gate
+    d2[4] < 1, lambda_2 > 3 lambda_1, all five plane distances <= 0.2) and the factors themselves.  The reference's
+    SelfAdjointEigenSolver / colPivHouseholderQr run on the oracle's kernels there, so the fits agree to the last bit."""
+    mc, ms, c, s, qt = association_case()
+    check_association(oracle_mod.associate(mc, ms, c, s, qt), GOLD["assoc_edge"], GOLD["assoc_plane"], 0.0)
+
+
+def test_oracle_map_association_equals_reference_live(oracle_mod):
+    if oracle_mod.ref_lasermapping() is None:
+        pytest.skip("oracle/_ref/libref_lasermapping.so not built (needs the reference tree)")
+    mc, ms, c, s, qt = association_case()
+    rng = np.random.default_rng(11)
+    for k in range(3):
+        q = qt.copy()
+        q[:4] += rng.normal(0, 0.003, 4)
+        q[:4] /= np.linalg.norm(q[:4])
+        q[4:] += rng.normal(0, 0.1, 3)
+        e, p = oracle_mod.ref_map_associate(mc, ms, c, s, q)
+        check_association(oracle_mod.associate(mc, ms, c, s, q), e, p, 0.0)
