@@ -5,11 +5,19 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
 // The shipped CUDA path never calls into it.
 //
-// PARITY STATUS: "parity unpinned" for everything except k-NN.  The reference ships no tests, golden
-// vectors or fixtures, cannot be compiled here (no ROS/PCL/Ceres/Eigen) and several of its files are
-// brace-damaged; the arithmetic of PCL VoxelGrid, Eigen's eigen/QR solvers and Ceres 1.14's LM loop is
-// restated from those libraries' published algorithms.  k-NN is pinned against the one reference
-// component that compiles here (vendored nanoflann 1.3.2, built into oracle/_ref by oracle/Makefile).
+// PARITY STATUS.  Pinned against the reference's OWN code, compiled from /root/reference into oracle/_ref by
+// oracle/Makefile (recipes and line-addressed cuts / repairs under oracle/patches, stand-ins under oracle/shims):
+//   * k-NN                      -- the vendored nanoflann 1.3.2 (libref_nanoflann.so)
+//   * ikd-Tree Build / Nearest_Search / Add_Points / flatten  -- src/ikd-Tree/ikd_Tree.cpp (libref_ikd.so)
+//   * residuals + Jacobians     -- the Ceres cost functors on dual numbers (libref_functors.so)
+//   * scan-to-scan association  -- laserOdometry.cpp:417-713 with a recording ceres::Problem (libref_laserodom.so)
+//   * rolling cube map, transformAssociateToMap / transformUpdate / pointAssociateToMap, insertion, valid-cube order
+//                               -- laserMapping.cpp:327-623, 875-945, 984-1004 (libref_lasermapping.so)
+//   * scan-to-map association   -- laserMapping.cpp:624-873, same library (5-NN gate, line / plane tests, point_a / point_b,
+//                                  unit normal + offset; Eigen's two solvers run on THIS file's eig3 / lstsq5x3 there)
+// "Parity unpinned" for what lives in libraries that are absent here and therefore restated from their published
+// algorithms: Ceres 1.14's trust-region loop, Eigen 3.3's SelfAdjointEigenSolver / ColPivHouseholderQR / quaternion
+// kernels, PCL's VoxelGrid.  The reference ships no tests, golden vectors or fixtures of its own.
 //
 // Build: see oracle/Makefile (g++ -O3 -std=c++14 -ffp-contract=off, the reference's flags
 // CMakeLists.txt:5-6: -O3, no -march, hence no FMA contraction).

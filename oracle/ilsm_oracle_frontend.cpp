@@ -2,9 +2,14 @@
 // projection (image_handler.h_ouster:103-140), LOAM feature extraction (scanRegistration.cpp:152-186, 244-412,
 // 427-589, upstream A-LOAM publish-once semantics) and PCL VoxelGrid (un-vendored, PCL 1.10 restated).
 //
-// PARITY STATUS: unpinned (the reference has no tests or fixtures and cannot be built here).  Decisions where the
-// reference leaves the result unspecified are fixed and documented here:
-//   * std::sort on curvature is unstable: ties are ordered by (curvature, point index) ascending.
+// PARITY STATUS: the feature extraction is PINNED against the reference's own code -- scanRegistration.cpp:227-589 cut out
+// of its ROS node (oracle/patches/scanreg_extract.py) and compiled into oracle/_ref/libref_scanreg.so: ring-ordered cloud,
+// relTime, ring bounds, curvature, labels and the four feature clouds agree bit for bit on natural frames
+// (tests/test_ref_scanreg_cpu.py, tests/golden/scanreg_reference.npz).  Unpinned: PCL's VoxelGrid (un-vendored; the compiled
+// reference fragment runs on THIS file's orc_voxelgrid) and the image projection.  Decisions where the reference leaves the
+// result unspecified are fixed and documented here:
+//   * std::sort on curvature is unstable: ties are ordered by (curvature, point index) ascending (differs from libstdc++'s
+//     introsort only under massive ties -- a perfectly regular synthetic cylinder; tested).
 //   * PCL VoxelGrid sorts voxel records with an unstable sort: points of one voxel are accumulated in ascending
 //     point index (float accumulators, like pcl::CentroidPoint).
 //   * atan()/sqrt() in the ring formula resolve to the float overloads when <math.h> is included through
