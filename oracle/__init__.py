@@ -22,6 +22,7 @@ _REF_IKD = os.path.join(_HERE, "_ref", "libref_ikd.so")
 _REF_SCANREG = os.path.join(_HERE, "_ref", "libref_scanreg.so")
 _REF_LASERODOM = os.path.join(_HERE, "_ref", "libref_laserodom.so")
 _REF_LASERMAPPING = os.path.join(_HERE, "_ref", "libref_lasermapping.so")
+_REF_SCANCONTEXT = os.path.join(_HERE, "_ref", "libref_scancontext.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 _REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
@@ -552,6 +553,57 @@ def ref_map_associate(map_corner, map_surf, stack_corner, stack_surf, qt):
     if rc != 0:
         raise RuntimeError(f"ref_lasermapping_associate failed ({rc})")
     return edge[:cnt[0]].copy(), plane[:cnt[1]].copy()
+
+
+_ref_scancontext = None
+
+
+def ref_scancontext():
+    """The reference's own ScanContext code (src/Scancontext.cpp + include/Scancontext.h, compiled unmodified),
+    oracle/_ref/libref_scancontext.so (None when never built)."""
+    global _ref_scancontext
+    if _ref_scancontext is None:
+        if not os.path.exists(_REF_SCANCONTEXT):
+            build()
+        if not os.path.exists(_REF_SCANCONTEXT):
+            return None
+        r = C.CDLL(_REF_SCANCONTEXT)
+        r.ref_sc_make.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        r.ref_sc_keys.argtypes = [C.c_void_p] * 3
+        r.ref_sc_distance.argtypes = [C.c_void_p] * 4
+        r.ref_sc_detect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _ref_scancontext = r
+    return _ref_scancontext
+
+
+def ref_sc_make(points):
+    p = _f32(points)
+    d = np.zeros((20, 60), np.float64)
+    ref_scancontext().ref_sc_make(_p(p), len(p), _stride(p), _p(d))
+    return d
+
+
+def ref_sc_keys(desc):
+    d = np.ascontiguousarray(desc, np.float64)
+    rk, sk = np.zeros(20), np.zeros(60)
+    ref_scancontext().ref_sc_keys(_p(d), _p(rk), _p(sk))
+    return rk, sk
+
+
+def ref_sc_distance(q, c):
+    a, b = np.ascontiguousarray(q, np.float64), np.ascontiguousarray(c, np.float64)
+    dist, shift = np.zeros(1), np.zeros(1, np.int32)
+    ref_scancontext().ref_sc_distance(_p(a), _p(b), _p(dist), _p(shift))
+    return float(dist[0]), int(shift[0])
+
+
+def ref_sc_detect(db, q):
+    """SCManager::detectLoopClosureID with the keyframes db[0..n) saved first and q saved last (the query), through the
+    reference's own code end to end (nanoflann tree included): (loop id or -1, yaw difference in rad)."""
+    d = np.ascontiguousarray(np.concatenate([np.asarray(db, np.float64).reshape(-1, 1200), np.asarray(q, np.float64).reshape(1, 1200)]))
+    yaw = np.zeros(1, np.float32)
+    lid = ref_scancontext().ref_sc_detect(_p(d), len(d), _p(yaw))
+    return int(lid), float(yaw[0])
 
 
 _ref_ikd = None

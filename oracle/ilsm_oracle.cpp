@@ -13,6 +13,7 @@
 //   * scan-to-scan association  -- laserOdometry.cpp:417-713 with a recording ceres::Problem (libref_laserodom.so)
 //   * rolling cube map, transformAssociateToMap / transformUpdate / pointAssociateToMap, insertion, valid-cube order
 //                               -- laserMapping.cpp:327-623, 875-945, 984-1004 (libref_lasermapping.so)
+//   * ScanContext (ilsm_oracle_sc.cpp) and the front end (ilsm_oracle_frontend.cpp): see those files
 //   * scan-to-map association   -- laserMapping.cpp:624-873, same library (5-NN gate, line / plane tests, point_a / point_b,
 //                                  unit normal + offset; Eigen's two solvers run on THIS file's eig3 / lstsq5x3 there)
 // "Parity unpinned" for what lives in libraries that are absent here and therefore restated from their published

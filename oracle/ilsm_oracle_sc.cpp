@@ -1,8 +1,11 @@
 // ilsm_oracle_sc.cpp -- CPU ORACLE (TEST INFRASTRUCTURE) for ScanContext (Scancontext.cpp:25-344,
 // Scancontext.h:77-96).  Descriptors are Eigen::MatrixXd 20x60 column-major in the reference; here they are stored
 // row-major double[20][60] -- every value is a float widened to double (SCPointType is float), so float32 storage
-// on the GPU side is lossless.  PARITY STATUS: unpinned (no reference tests); the ring-key k-NN stage of
-// detectLoopClosureID is run through the reference's own nanoflann (oracle/_ref) by the Python tests.
+// on the GPU side is lossless.  PARITY STATUS: PINNED against the reference's own code -- src/Scancontext.cpp and
+// include/Scancontext.h compile unmodified against a small Eigen::MatrixXd stand-in (oracle/shims_sc) into
+// oracle/_ref/libref_scancontext.so together with the vendored nanoflann: descriptor, keys, distanceBtnScanContext and
+// detectLoopClosureID agree exactly (tests/test_ref_scancontext_cpu.py, tests/golden/scancontext_reference.npz).  What the
+// stand-in cannot pin is the summation order inside Eigen's vectorised norm / dot / mean (left to right here and there).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

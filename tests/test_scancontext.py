@@ -305,3 +305,35 @@ def test_gpu_sc_tc_batch_equals_exact_scan(ctx, oracle_mod, ilsm, k):
         assert np.array_equal(i1, bi[j]) and np.array_equal(s1, bs[j]) and np.array_equal(d1, bd[j])
     assert bi[9, 0] == 121 and abs(bd[9, 0]) < 1e-12
     sc.close()
+
+
+@pytest.mark.gpu
+def test_gpu_scancontext_matches_reference_code_golden(ctx, ilsm):
+    """The CUDA ScanContext against outputs of the REFERENCE's own code (Scancontext.cpp compiled unmodified,
+    tests/golden/make_golden_scancontext.py): descriptors bit for bit, column-shift distances / shifts of 48 pairs, and
+    detectLoopClosureID (the reference's nanoflann tree + candidate loop + 0.13 threshold) for 12 queries."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_scancontext import database, frames
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scancontext_reference.npz"))
+    sc = ilsm.ScanContextDb(ctx)
+    for k, cloud in enumerate(frames()):
+        assert np.array_equal(np.asarray(sc.make_scancontext(cloud), np.float64), gold[f"desc{k}"]), k
+    db, queries, ids, shifts, pairs = database()
+    sc.add(db[:251])  # what the reference's tree holds when the 301st keyframe asks: all but the 50 most recent
+    for j in range(len(queries)):
+        lid, best, align, _ = sc.detect_loop_closure_id(queries[j])
+        assert lid == gold["detect_id"][j], j
+        if lid >= 0:
+            assert abs(np.float32(np.deg2rad(align * 6.0)) - gold["detect_yaw"][j]) < 1e-6, j
+    sc.close()
+    # pair distances through the exhaustive scorer over the whole database
+    sc = ilsm.ScanContextDb(ctx)
+    sc.add(db)
+    for j in range(len(queries)):
+        d, i, s = sc.query_topk(queries[j], k=16)
+        full = {int(ii): (float(dd), int(ss)) for dd, ii, ss in zip(d, i, s)}
+        for n, (jj, c) in enumerate(pairs):
+            if jj == j and c in full:
+                assert abs(full[c][0] - gold["pair_dist"][n]) <= 1e-12 and full[c][1] == gold["pair_shift"][n], (j, c)
+    sc.close()
