@@ -23,6 +23,7 @@ _REF_SCANREG = os.path.join(_HERE, "_ref", "libref_scanreg.so")
 _REF_LASERODOM = os.path.join(_HERE, "_ref", "libref_laserodom.so")
 _REF_LASERMAPPING = os.path.join(_HERE, "_ref", "libref_lasermapping.so")
 _REF_SCANCONTEXT = os.path.join(_HERE, "_ref", "libref_scancontext.so")
+_REF_IMAGEHANDLER = os.path.join(_HERE, "_ref", "libref_imagehandler.so")
 _REF_FUN = os.path.join(_HERE, "_ref", "libref_functors.so")
 _REF_ALOAM = os.path.join(_HERE, "_ref", "libref_aloam.so")
 
@@ -604,6 +605,33 @@ def ref_sc_detect(db, q):
     yaw = np.zeros(1, np.float32)
     lid = ref_scancontext().ref_sc_detect(_p(d), len(d), _p(yaw))
     return int(lid), float(yaw[0])
+
+
+_ref_imagehandler = None
+
+
+def ref_imagehandler():
+    """The reference's own projection loop (src/image_handler.h_ouster:113-139), oracle/_ref/libref_imagehandler.so
+    (None when never built)."""
+    global _ref_imagehandler
+    if _ref_imagehandler is None:
+        if not os.path.exists(_REF_IMAGEHANDLER):
+            build()
+        if not os.path.exists(_REF_IMAGEHANDLER):
+            return None
+        r = C.CDLL(_REF_IMAGEHANDLER)
+        r.ref_project.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _ref_imagehandler = r
+    return _ref_imagehandler
+
+
+def ref_project(cloud, H=64, W=1024):
+    """ImageHandler::cloud_handler's loop through the reference code: (image_range u8, image_intensity u8, cloud_track)."""
+    c = np.ascontiguousarray(np.asarray(cloud, np.float32)[:, :4])
+    assert len(c) == H * W
+    rng, inten, track = np.zeros((H, W), np.uint8), np.zeros((H, W), np.uint8), np.zeros((H * W, 4), np.float32)
+    ref_imagehandler().ref_project(_p(c), H, W, c.strides[0], _p(rng), _p(inten), _p(track))
+    return rng, inten, track
 
 
 _ref_ikd = None

@@ -6,7 +6,8 @@
 // of its ROS node (oracle/patches/scanreg_extract.py) and compiled into oracle/_ref/libref_scanreg.so: ring-ordered cloud,
 // relTime, ring bounds, curvature, labels and the four feature clouds agree bit for bit on natural frames
 // (tests/test_ref_scanreg_cpu.py, tests/golden/scanreg_reference.npz).  Unpinned: PCL's VoxelGrid (un-vendored; the compiled
-// reference fragment runs on THIS file's orc_voxelgrid) and the image projection.  Decisions where the reference leaves the
+// reference fragment runs on THIS file's orc_voxelgrid).  The image projection is pinned the same way
+// (image_handler.h_ouster:113-139 -> libref_imagehandler.so, tests/test_ref_imagehandler_cpu.py).  Decisions where the reference leaves the
 // result unspecified are fixed and documented here:
 //   * std::sort on curvature is unstable: ties are ordered by (curvature, point index) ascending (differs from libstdc++'s
 //     introsort only under massive ties -- a perfectly regular synthetic cylinder; tested).

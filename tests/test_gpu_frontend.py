@@ -153,3 +153,14 @@ def test_feature_extraction_matches_reference_code_golden(ctx, name):
 
 
 
+
+
+def test_projection_matches_reference_code_golden(ctx):
+    """The CUDA projection against the outputs of the REFERENCE's own loop (image_handler.h_ouster:113-139 compiled from
+    the reference tree, tests/golden/make_golden_imagehandler.py): range image, intensity image and cloud_track bit for bit."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_imagehandler import digests, frame
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "imagehandler_reference.npz"))
+    r = ctx.cloud_handler(frame())
+    assert digests(r[0], r[1], r[2]) == [str(s) for s in gold["sha256"]]
