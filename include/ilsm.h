@@ -441,6 +441,15 @@ ILSM_API int ilsm_pc2_unpack(ilsm_ctx* ctx, const uint8_t* data, int n_points, c
 ILSM_API int ilsm_pc2_unpack_dev(ilsm_ctx* ctx, const uint8_t* d_data, int n_points, const ilsm_pc2_layout* layout,
                                  float* d_out_xyzi);
 
+/* The other direction: packed xyzi points -> the `data` blob of a sensor_msgs/PointCloud2 (n_points * point_step bytes;
+ * x / y / z / intensity as FLOAT32 at the layout's 4-byte-aligned offsets, every other byte zero), for the clouds the nodes
+ * publish.  ilsm_pc2_layout_pcl_xyzi = what pcl::toROSMsg emits for pcl::PointXYZI (point_step 32: x 0, y 4, z 8,
+ * intensity 16).  The _dev form reads and writes device memory and does not synchronise.
+ * Replaces: pcl::toROSMsg(...)  scanRegistration.cpp:593,599,622,630,638 ; laserMapping.cpp:1023,1043,1061 */
+ILSM_API void ilsm_pc2_layout_pcl_xyzi(ilsm_pc2_layout* l);
+ILSM_API int ilsm_pc2_pack(ilsm_ctx* ctx, const float* xyzi, int n_points, const ilsm_pc2_layout* layout, uint8_t* data_out);
+ILSM_API int ilsm_pc2_pack_dev(ilsm_ctx* ctx, const float* d_xyzi, int n_points, const ilsm_pc2_layout* layout, uint8_t* d_data_out);
+
 /* ilsm_slam_frame fed with the raw message blob (same outputs). */
 ILSM_API int ilsm_slam_frame_pc2(ilsm_slam* slam, const uint8_t* data, int n_points, const ilsm_pc2_layout* layout, int use_aloam,
                                  double q_odom_xyzw[4], double t_odom[3], double q_map_xyzw[4], double t_map[3],

@@ -772,5 +772,80 @@ class OdomHandler {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ messages out
+// What the nodes publish, as plain structs a ROS-free caller can forward (and a ROS caller copies field by field into
+// sensor_msgs::PointCloud2 / nav_msgs::Odometry / tf::StampedTransform): the wire format and the frame names of the
+// reference, nothing computed on the host.
+struct Header {
+  double stamp = 0.0;  // seconds
+  std::string frame_id;
+};
+struct PointCloud2Msg {  // sensor_msgs/PointCloud2 of a pcl::PointXYZI cloud, as pcl::toROSMsg fills it
+  Header header;
+  uint32_t height = 1, width = 0, point_step = 32, row_step = 0;
+  bool is_bigendian = false, is_dense = true;
+  struct Field {
+    const char* name;
+    uint32_t offset;
+    uint8_t datatype;  // sensor_msgs/PointField::FLOAT32 = 7
+    uint32_t count;
+  } fields[4] = {{"x", 0, 7, 1}, {"y", 4, 7, 1}, {"z", 8, 7, 1}, {"intensity", 16, 7, 1}};
+  std::vector<uint8_t> data;
+};
+struct OdometryMsg {  // nav_msgs/Odometry, the fields the reference sets
+  Header header;
+  std::string child_frame_id;
+  double orientation_xyzw[4] = {0, 0, 0, 1}, position[3] = {0, 0, 0};
+};
+struct TransformMsg {  // tf::StampedTransform
+  double stamp = 0.0;
+  std::string frame_id, child_frame_id;
+  double rotation_xyzw[4] = {0, 0, 0, 1}, origin[3] = {0, 0, 0};
+};
+
+// pcl::toROSMsg + the two header lines every publisher adds (scanRegistration.cpp:593-596 and the like): packed on the GPU
+// by ilsm_pc2_pack.  Clouds of the front end are published in "os_sensor" (:595), clouds of the mapping node in "map"
+// (laserMapping.cpp:1025,1046,1063).
+template <typename CloudT>
+inline PointCloud2Msg toROSMsg(const CloudT& cloud, double stamp, const std::string& frame_id, const ContextPtr& ctx = Context::shared()) {
+  static_assert(sizeof(cloud.points[0]) == 32, "toROSMsg: a PointXYZI-layout cloud (32-byte points) is expected");
+  PointCloud2Msg m;
+  m.header.stamp = stamp, m.header.frame_id = frame_id;
+  m.width = (uint32_t)cloud.points.size(), m.row_step = m.width * m.point_step, m.is_dense = cloud.is_dense;
+  m.data.resize((size_t)m.width * m.point_step);
+  if (m.width == 0) return m;
+  std::vector<float> packed((size_t)m.width * 4);
+  for (size_t i = 0; i < cloud.points.size(); ++i)
+    packed[4 * i] = cloud.points[i].x, packed[4 * i + 1] = cloud.points[i].y, packed[4 * i + 2] = cloud.points[i].z, packed[4 * i + 3] = cloud.points[i].intensity;
+  ilsm_pc2_layout lay;
+  ilsm_pc2_layout_pcl_xyzi(&lay);
+  check(ilsm_pc2_pack(ctx->get(), packed.data(), (int)m.width, &lay, m.data.data()), "ilsm_pc2_pack");
+  return m;
+}
+
+// /aft_mapped_to_init and its transform (laserMapping.cpp:1075-1088, 1129-1146: frame "map", child "/aft_mapped"), and
+// /laser_odom_to_init (laserOdometry.cpp:726-735: frame "camera_init", child "/laser_odom"), from a pose {qx,qy,qz,qw, tx,ty,tz}
+inline OdometryMsg make_odometry(const double q_xyzw[4], const double t[3], double stamp, const std::string& frame_id,
+                                 const std::string& child_frame_id) {
+  OdometryMsg m;
+  m.header.stamp = stamp, m.header.frame_id = frame_id, m.child_frame_id = child_frame_id;
+  for (int i = 0; i < 4; ++i) m.orientation_xyzw[i] = q_xyzw[i];
+  for (int i = 0; i < 3; ++i) m.position[i] = t[i];
+  return m;
+}
+inline OdometryMsg odomAftMapped(const double q_w_curr[4], const double t_w_curr[3], double timeLaserOdometry) {
+  return make_odometry(q_w_curr, t_w_curr, timeLaserOdometry, "map", "/aft_mapped");
+}
+inline OdometryMsg laserOdometryMsg(const double q_w_curr[4], const double t_w_curr[3], double timeSurfPointsLessFlat) {
+  return make_odometry(q_w_curr, t_w_curr, timeSurfPointsLessFlat, "camera_init", "/laser_odom");
+}
+inline TransformMsg aftMappedTransform(const OdometryMsg& o) {  // br.sendTransform(StampedTransform(transform, stamp, "map", "/aft_mapped"))
+  TransformMsg t;
+  t.stamp = o.header.stamp, t.frame_id = o.header.frame_id, t.child_frame_id = o.child_frame_id;
+  for (int i = 0; i < 4; ++i) t.rotation_xyzw[i] = o.orientation_xyzw[i];
+  for (int i = 0; i < 3; ++i) t.origin[i] = o.position[i];
+  return t;
+}
+
 }  // namespace ilsm
 #endif  // ILSM_HPP_

@@ -173,6 +173,9 @@ def load_library(path: str | None = None):
         "ilsm_slam_frame": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(SlamStats)]),
         "ilsm_slam_create_async": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
         "ilsm_slam_frame_async": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
+        "ilsm_pc2_layout_pcl_xyzi": (None, [C.POINTER(Pc2Layout)]),
+        "ilsm_pc2_pack": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
+        "ilsm_pc2_pack_dev": (i32, [vp, vp, i32, C.POINTER(Pc2Layout), vp]),
         "ilsm_slam_create_staged": (i32, [vp, f32, f32, f32, i32, C.POINTER(vp)]),
         "ilsm_slam_frame_staged": (i32, [vp, vp, i32, i32, i32, vp, vp, C.POINTER(i32), vp, vp, C.POINTER(i32), C.POINTER(SlamStats)]),
         "ilsm_slam_host_phases": (i32, [vp, vp]),
@@ -304,6 +307,17 @@ class Context:
         return rng, inten, track
 
     # -- pcl::fromROSMsg (scanRegistration.cpp:235, image_handler.h_ouster:44,106) ------------------
+    def pc2_pack(self, cloud, layout: "Pc2Layout | None" = None):
+        """(n, 4) packed xyzi -> the `data` blob of a sensor_msgs/PointCloud2 (uint8, n * point_step); default layout =
+        pcl::toROSMsg of pcl::PointXYZI."""
+        a = np.ascontiguousarray(np.asarray(cloud, np.float32)[:, :4])
+        if layout is None:
+            layout = Pc2Layout()
+            self._lib.ilsm_pc2_layout_pcl_xyzi(C.byref(layout))
+        out = np.empty(len(a) * layout.point_step, np.uint8)
+        _check(self._lib.ilsm_pc2_pack(self._h, _ptr(a), len(a), C.byref(layout), _ptr(out)))
+        return out
+
     def pc2_unpack(self, blob, layout: "Pc2Layout"):
         """sensor_msgs/PointCloud2 `data` blob -> (n, 4) packed xyzi float32."""
         b = np.ascontiguousarray(blob, np.uint8).reshape(-1)

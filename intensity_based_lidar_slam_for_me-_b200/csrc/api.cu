@@ -709,6 +709,55 @@ int check_pc2_layout(const ilsm_pc2_layout* l) {
 }  // namespace ilsm
 extern "C" {
 
+ILSM_API void ilsm_pc2_layout_pcl_xyzi(ilsm_pc2_layout* l) {
+  if (!l) return;
+  memset(l, 0, sizeof(*l));
+  l->point_step = 32, l->off_x = 0, l->off_y = 4, l->off_z = 8, l->off_intensity = 16, l->intensity_datatype = 7;
+}
+
+// a layout a blob can be WRITTEN with: FLOAT32 fields on 4-byte offsets that do not overlap
+static int check_pc2_pack_layout(const ilsm_pc2_layout* l) {
+  int rc = check_pc2_layout(l);
+  if (rc) return rc;
+  if (l->point_step % 4 || l->off_x % 4 || l->off_y % 4 || l->off_z % 4) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack: fields must sit on 4-byte offsets");
+  if (l->off_intensity >= 0 && (l->intensity_datatype != 7 || l->off_intensity % 4))
+    return fail(ILSM_ERR_INVALID_ARG, "pc2_pack: intensity is written as FLOAT32 on a 4-byte offset");
+  const int o[4] = {l->off_x, l->off_y, l->off_z, l->off_intensity};
+  for (int a = 0; a < 4; ++a)
+    for (int b = a + 1; b < 4; ++b)
+      if (o[a] >= 0 && o[a] == o[b]) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack: overlapping fields");
+  return ILSM_OK;
+}
+
+ILSM_API int ilsm_pc2_pack_dev(ilsm_ctx* ctx, const float* d_xyzi, int n_points, const ilsm_pc2_layout* layout, uint8_t* d_data_out) {
+  if (!ctx || (n_points > 0 && (!d_xyzi || !d_data_out))) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack_dev: null argument");
+  if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack_dev: bad n_points");
+  int rc = check_pc2_pack_layout(layout);
+  if (rc) return rc;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  return c.pc2_pack_dev(reinterpret_cast<const float4*>(d_xyzi), n_points, *layout, d_data_out);
+}
+
+ILSM_API int ilsm_pc2_pack(ilsm_ctx* ctx, const float* xyzi, int n_points, const ilsm_pc2_layout* layout, uint8_t* data_out) {
+  if (!ctx || (n_points > 0 && (!xyzi || !data_out))) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack: null argument");
+  if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "pc2_pack: bad n_points");
+  int rc = check_pc2_pack_layout(layout);
+  if (rc) return rc;
+  if (n_points == 0) return ILSM_OK;
+  Ctx& c = ctx->c;
+  std::lock_guard<std::mutex> lk(c.mu);
+  ILSM_CUDA(cudaSetDevice(c.device));
+  const size_t bytes = (size_t)n_points * layout->point_step;
+  if ((rc = c.fe.pc2.reserve(bytes + 16)) || (rc = c.fe.raw.reserve((size_t)n_points * 4 + 4))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(c.fe.raw.p, xyzi, (size_t)n_points * 16, cudaMemcpyHostToDevice, c.stream));
+  if ((rc = c.pc2_pack_dev(reinterpret_cast<const float4*>(c.fe.raw.p), n_points, *layout, c.fe.pc2.p))) return rc;
+  ILSM_CUDA(cudaMemcpyAsync(data_out, c.fe.pc2.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+  ILSM_CUDA(cudaStreamSynchronize(c.stream));
+  return ILSM_OK;
+}
+
 ILSM_API int ilsm_pc2_unpack_dev(ilsm_ctx* ctx, const uint8_t* d_data, int n_points, const ilsm_pc2_layout* layout, float* d_out_xyzi) {
   if (!ctx || (n_points > 0 && (!d_data || !d_out_xyzi))) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack_dev: null argument");
   if (n_points < 0) return fail(ILSM_ERR_INVALID_ARG, "pc2_unpack_dev: bad n_points");

@@ -121,6 +121,31 @@ int Ctx::pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layou
   return check_launch("pc2_unpack");
 }
 
+// The other direction (pcl::toROSMsg of the clouds the nodes publish): packed xyzi -> point_step-byte records with x / y / z
+// / intensity as FLOAT32 at the layout's offsets, every other byte zero (PCL leaves its padding floats as they are in memory;
+// subscribers read fields by offset).  One thread per 4 bytes of output: coalesced stores whatever the point step.
+__global__ void pc2_pack_kernel(const float4* __restrict__ in, int n, ilsm_pc2_layout l, uint32_t* __restrict__ out) {
+  pdl_entry();
+  const int wpp = l.point_step >> 2;  // 32-bit words per point (point_step is a multiple of 4)
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= (long long)n * wpp) return;
+  const int i = (int)(w / wpp), off = (int)(w - (long long)i * wpp) << 2;
+  uint32_t v = 0u;
+  if (off == l.off_x || off == l.off_y || off == l.off_z || (l.off_intensity >= 0 && off == l.off_intensity)) {
+    const float4 p = __ldg(in + i);
+    v = __float_as_uint(off == l.off_x ? p.x : off == l.off_y ? p.y : off == l.off_z ? p.z : p.w);
+  }
+  out[w] = v;
+}
+
+int Ctx::pc2_pack_dev(const float4* d_in, int n, const ilsm_pc2_layout& l, unsigned char* d_out) {
+  if (n <= 0) return ILSM_OK;
+  const long long words = (long long)n * (l.point_step >> 2);
+  ILSM_CUDA(launch_pdl(pc2_pack_kernel, dim3((unsigned)((words + 255) / 256)), dim3(256), 0, stream, d_in, n, l, reinterpret_cast<uint32_t*>(d_out)));
+  count_launches(1);
+  return check_launch("pc2_pack");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // feature extraction
 // ---------------------------------------------------------------------------------------------------

@@ -259,6 +259,7 @@ struct Ctx {
   unsigned long long fe_graph_key = 0;
   bool fe_graphs_ok = true;                 // false after a failed capture: plain launches from then on
   int pc2_unpack_dev(const unsigned char* d_data, int n, const ilsm_pc2_layout& l, float4* d_out);
+  int pc2_pack_dev(const float4* d_in, int n, const ilsm_pc2_layout& l, unsigned char* d_out);
   int voxelgrid_dev(const float* d_in, int n, const int* d_n, int n_slot, int stride_bytes, int ioff, float leaf,
                     float4* d_out, int* d_n_out);
   int voxelgrid_large_dev(const float* d_in, int n, int stride_bytes, int ioff, float leaf, float4* d_out, int* d_n_out,

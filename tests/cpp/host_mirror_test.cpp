@@ -406,6 +406,34 @@ static void test_odom_handler() {
   EXPECT(std::fabs(m[4] - (3 + std::cos(0.1))) < 1e-14 && std::fabs(m[5] - std::sin(0.1)) < 1e-14);
 }
 
+static void test_messages_out() {
+  std::printf("toROSMsg / odomAftMapped / aftMappedTransform (messages out)\n");
+  ilsm::PointCloud<ilsm::PointXYZI> cloud;
+  for (int i = 0; i < 1000; ++i) {
+    ilsm::PointXYZI p;
+    p.x = 0.5f * i, p.y = -1.25f * i, p.z = 3.0f + i, p.intensity = (float)(i % 64) + 0.1f;
+    cloud.push_back(p);
+  }
+  const ilsm::PointCloud2Msg m = ilsm::toROSMsg(cloud, 12.5, "os_sensor");
+  EXPECT(m.width == 1000 && m.height == 1 && m.point_step == 32 && m.row_step == 32000 && m.data.size() == 32000);
+  EXPECT(m.header.frame_id == "os_sensor" && m.header.stamp == 12.5 && m.fields[3].offset == 16 && m.fields[3].datatype == 7);
+  bool same = true, zeros = true;
+  for (int i = 0; i < 1000; ++i) {
+    float f[8];
+    std::memcpy(f, &m.data[32 * (size_t)i], 32);
+    same = same && f[0] == cloud[i].x && f[1] == cloud[i].y && f[2] == cloud[i].z && f[4] == cloud[i].intensity;
+    zeros = zeros && f[3] == 0.f && f[5] == 0.f && f[6] == 0.f && f[7] == 0.f;
+  }
+  EXPECT(same && zeros);
+  EXPECT(ilsm::toROSMsg(ilsm::PointCloud<ilsm::PointXYZI>(), 0.0, "map").data.empty());
+  const double q[4] = {0, 0, std::sin(0.2), std::cos(0.2)}, t[3] = {1, 2, 3};
+  const ilsm::OdometryMsg o = ilsm::odomAftMapped(q, t, 7.0);
+  const ilsm::TransformMsg tf = ilsm::aftMappedTransform(o);
+  EXPECT(o.header.frame_id == "map" && o.child_frame_id == "/aft_mapped" && o.position[2] == 3 && o.orientation_xyzw[3] == std::cos(0.2));
+  EXPECT(tf.frame_id == "map" && tf.child_frame_id == "/aft_mapped" && tf.stamp == 7.0 && tf.origin[1] == 2 && tf.rotation_xyzw[2] == std::sin(0.2));
+  EXPECT(ilsm::laserOdometryMsg(q, t, 1.0).header.frame_id == "camera_init");
+}
+
 static void test_config(const char* yaml_path) {
   std::printf("Config::load_yaml / load_launch (the reference's parameter keys)\n");
   ilsm::Config c;
@@ -436,6 +464,7 @@ int main(int argc, char** argv) {
   try {
     if (argc > 1) test_config(argv[1]);
     test_odom_handler();
+    test_messages_out();
     test_kdtree_flann();
     test_voxelgrid();
     test_ikd_tree();

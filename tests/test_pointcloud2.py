@@ -93,3 +93,30 @@ def test_gpu_full_loop_from_message_blobs(ctx, ilsm, oracle_mod):
             assert np.array_equal(u, v)
         assert ra[4].n_less_flat == rb[4].n_less_flat and ra[4].n_sharp == rb[4].n_sharp
     a.close(), b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lay", [l for l in LAYOUTS if l[5] == 7 and l[0] % 4 == 0 and l[1] % 4 == 0])
+def test_gpu_pc2_pack_round_trip(ctx, ilsm, oracle_mod, lay):
+    """ilsm_pc2_pack (pcl::toROSMsg of the published clouds): the blob unpacks to the same points (GPU and numpy
+    restatement), the fields sit where the layout says and every other byte is zero; the default layout is PCL's
+    PointXYZI (point_step 32, intensity at 16)."""
+    a = _points(3001, seed=3)
+    L = ilsm.Pc2Layout(lay[0], lay[1], lay[2], lay[3], lay[4], lay[5], 0, 0)
+    blob = ctx.pc2_pack(a, L)
+    assert blob.size == len(a) * lay[0]
+    want = a.copy()
+    if lay[4] < 0:
+        want[:, 3] = 0
+    assert np.array_equal(oracle_mod.pc2_unpack(blob, *lay).view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(ctx.pc2_unpack(blob, L).view(np.uint32), want.view(np.uint32))
+    rec = blob.reshape(len(a), lay[0])
+    used = np.zeros(lay[0], bool)
+    for off in (lay[1], lay[2], lay[3]) + ((lay[4],) if lay[4] >= 0 else ()):
+        used[off:off + 4] = True
+    assert not rec[:, ~used].any()
+    d = ctx.pc2_pack(a)  # default: pcl::PointXYZI
+    assert d.size == len(a) * 32 and np.array_equal(d.reshape(-1, 32)[:, 16:20].view(np.float32)[:, 0].view(np.uint32), a[:, 3].view(np.uint32))
+    assert ctx.pc2_pack(np.zeros((0, 4), np.float32)).size == 0
+    with pytest.raises(ilsm.IlsmError):
+        ctx.pc2_pack(a, ilsm.Pc2Layout(26, 2, 6, 10, 14, 4, 0, 0))  # unaligned / integer intensity cannot be written
