@@ -468,22 +468,28 @@ __global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ 
   for (int j = 0; j < 6; ++j) {
     const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
     if (ep - sp + 1 > kMaxSeg) continue;  // flagged by the sort kernel
-    // ---- sharp / less sharp: descending curvature
+    // ---- sharp / less sharp: descending curvature.  A window of 32 sorted entries is loaded once (index, curvature
+    // test); after every pick only the picked flags of the lanes behind it are read again -- the picks of a window are a
+    // dependent chain, and the index / curvature loads were two thirds of its length.
     int largest = 0;
     int k = ep;
-    while (k >= sp) {
+    bool stop = false;
+    while (k >= sp && !stop) {
       const int kk = k - lane;
       int ind = -1;
-      bool elig = false, low = false;
+      bool low = false;
       if (kk >= sp) {
         ind = sort_ind[kk];
-        const float c = curv[ind];
-        low = !((double)c > 0.1);
-        elig = !low && picked[ind] == 0;
+        low = !((double)curv[ind] > 0.1);
       }
-      const unsigned em = __ballot_sync(0xffffffffu, elig), lm = __ballot_sync(0xffffffffu, low);
-      const int fe = em ? __ffs(em) - 1 : 32, fl = lm ? __ffs(lm) - 1 : 32;
-      if (fe < fl) {  // an eligible point before the curvature drops to <= 0.1
+      const unsigned lm = __ballot_sync(0xffffffffu, low);
+      const int fl = lm ? __ffs(lm) - 1 : 32;  // sorted: from here on the curvature is <= 0.1 and nothing qualifies
+      unsigned avail = __ballot_sync(0xffffffffu, kk >= sp && !low) & (fl < 32 ? (1u << fl) - 1u : 0xffffffffu);
+      while (avail) {
+        const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
+        const unsigned em = __ballot_sync(0xffffffffu, elig);
+        if (!em) break;
+        const int fe = __ffs(em) - 1;
         const int pick = __shfl_sync(0xffffffffu, ind, fe);
         ++largest;
         if (largest <= 2) {
@@ -500,32 +506,35 @@ __global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ 
           }
           ++n_lsharp;
         } else {
+          stop = true;
           break;
         }
         mark_neighbours(cloud, picked, pick, lane);
-        k -= fe + 1;
-      } else if (fl < 32) {
-        break;  // sorted: everything further has curvature <= 0.1 and can never qualify
-      } else {
-        k -= 32;
+        avail &= ~((2u << fe) - 1u);  // the lanes up to the pick are behind us (fe = 31: 2u << 31 wraps to 0, mask = all)
       }
+      if (fl < 32) break;
+      k -= 32;
     }
     // ---- flat: ascending curvature, four picks, the fourth does not suppress its neighbours
     int smallest = 0;
     k = sp;
-    while (k <= ep) {
+    stop = false;
+    while (k <= ep && !stop) {
       const int kk = k + lane;
       int ind = -1;
-      bool elig = false, high = false;
+      bool high = false;
       if (kk <= ep) {
         ind = sort_ind[kk];
-        const float c = curv[ind];
-        high = !((double)c < 0.1);
-        elig = !high && picked[ind] == 0;
+        high = !((double)curv[ind] < 0.1);
       }
-      const unsigned em = __ballot_sync(0xffffffffu, elig), hm = __ballot_sync(0xffffffffu, high);
-      const int fe = em ? __ffs(em) - 1 : 32, fh = hm ? __ffs(hm) - 1 : 32;
-      if (fe < fh) {
+      const unsigned hm = __ballot_sync(0xffffffffu, high);
+      const int fh = hm ? __ffs(hm) - 1 : 32;
+      unsigned avail = __ballot_sync(0xffffffffu, kk <= ep && !high) & (fh < 32 ? (1u << fh) - 1u : 0xffffffffu);
+      while (avail) {
+        const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
+        const unsigned em = __ballot_sync(0xffffffffu, elig);
+        if (!em) break;
+        const int fe = __ffs(em) - 1;
         const int pick = __shfl_sync(0xffffffffu, ind, fe);
         if (lane == 0) {
           label[pick] = -1;
@@ -533,14 +542,15 @@ __global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ 
         }
         ++n_flat;
         ++smallest;
-        if (smallest >= 4) break;
+        if (smallest >= 4) {
+          stop = true;
+          break;
+        }
         mark_neighbours(cloud, picked, pick, lane);
-        k += fe + 1;
-      } else if (fh < 32) {
-        break;
-      } else {
-        k += 32;
+        avail &= ~((2u << fe) - 1u);
       }
+      if (fh < 32) break;
+      k += 32;
     }
     __syncwarp();
   }
