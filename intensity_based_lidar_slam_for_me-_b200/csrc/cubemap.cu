@@ -19,10 +19,16 @@
 
 namespace ilsm {
 
-__global__ void cube_gather_kernel(const float4* __restrict__ slabs, int cap, const GatherItem* __restrict__ items,
-                                   float4* __restrict__ out) {
+constexpr size_t kLmHostBytes = offsetof(LmState, report) + sizeof(ilsm_reg_report);  // what a frame reads back of the LM state
+
+// grid (8, n_valid, 2): z = cloud kind
+__global__ void cube_gather_kernel(const float4* __restrict__ slabs_c, const float4* __restrict__ slabs_s, int cap,
+                                   const __grid_constant__ GatherItems items, float4* __restrict__ out_c, float4* __restrict__ out_s) {
   pdl_entry();
-  const GatherItem it = items[blockIdx.y];
+  const bool surf = blockIdx.z != 0;
+  const GatherItem it = items.it[(surf ? 125 : 0) + blockIdx.y];
+  const float4* slabs = surf ? slabs_s : slabs_c;
+  float4* out = surf ? out_s : out_c;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < it.count; t += gridDim.x * blockDim.x)
     out[it.offset + t] = slabs[(size_t)it.slab * cap + t];
 }
@@ -133,14 +139,14 @@ __global__ void __launch_bounds__(1024)
 // deterministic function: until the cube receives a point again, filtering it is provably a no-op and is skipped
 // (clean[]: set here when a pass left the cube as it was, cleared by cube_insert_kernel).
 __global__ void __launch_bounds__(1024)
-    cube_filter_kernel(const int* __restrict__ valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
+    cube_filter_kernel(const __grid_constant__ ValidSlabs valid_slabs, float4* slabs_c, float4* slabs_s, int* cnt_c, int* cnt_s, int cap,
                        float leaf_c, float leaf_s, float4* __restrict__ scratch, int* err, uint32_t* __restrict__ hscratch,
                        int* __restrict__ clean, int merge_ok) {
   pdl_entry();
   extern __shared__ u64 keys[];
   const int v = blockIdx.x >> 1;
   const bool corner = (blockIdx.x & 1) == 0;
-  const int slab = valid_slabs[v];
+  const int slab = valid_slabs.slab[v];
   float4* pts = (corner ? slabs_c : slabs_s) + (size_t)slab * cap;
   int* cnt = (corner ? cnt_c : cnt_s) + slab;
   const int n = *cnt;
@@ -198,21 +204,22 @@ int CubeMapH::init(Ctx* c, float lres, float pres, int cube_cap) {
       (rc = from_s.reserve(typical + 4)) || (rc = stack_c.reserve(kVoxelBlockMax)) || (rc = stack_s.reserve(kVoxelBlockMax)))
     return rc;
   if ((rc = slabs_c.reserve((size_t)kCNum * cap)) || (rc = slabs_s.reserve((size_t)kCNum * cap)) ||
-      (rc = cnt_c.reserve(kCNum)) || (rc = cnt_s.reserve(kCNum)) || (rc = clean.reserve(4 * kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
-      (rc = stack_n.reserve(4)) || (rc = valid_d.reserve(128)) || (rc = err.reserve(4)) || (rc = items.reserve(256)) ||
+      (rc = cnt_all.reserve(2 * kCNum + 4)) || (rc = clean.reserve(4 * kCNum)) || (rc = slab_of_d.reserve(kCNum)) ||
+      (rc = stack_n.reserve(4)) ||
       (rc = zero_list.reserve(kCNum)) || (rc = scratch.reserve((size_t)250 * cap)) || (rc = hscratch.reserve((size_t)250 * kVgScratchWords)) ||
       (rc = world_tmp.reserve((size_t)2 * kVoxelBlockMax)) || (rc = pin.reserve(2 * kCNum + 4096)) ||
       (rc = pin_counts.reserve(2 * kCNum + 16)))
     return rc;
+  // the two count arrays and the error word sit back to back (cnt_all): the host mirror is refreshed with ONE copy per frame;
+  // cnt_c / cnt_s / err are views into it (cap 0: not owned)
+  cnt_c.p = cnt_all.p, cnt_s.p = cnt_all.p + kCNum, err.p = cnt_all.p + 2 * kCNum;
   ILSM_CUDA(cudaEventCreateWithFlags(&ev_tail, cudaEventDisableTiming));
   slab_of.resize(kCNum);
   for (int i = 0; i < kCNum; ++i) slab_of[i] = i;
   cnt_c_h.assign(kCNum, 0), cnt_s_h.assign(kCNum, 0);
   cudaStream_t s = c->stream;
-  ILSM_CUDA(cudaMemsetAsync(cnt_c.p, 0, kCNum * sizeof(int), s));
-  ILSM_CUDA(cudaMemsetAsync(cnt_s.p, 0, kCNum * sizeof(int), s));
+  ILSM_CUDA(cudaMemsetAsync(cnt_all.p, 0, (2 * kCNum + 4) * sizeof(int), s));
   ILSM_CUDA(cudaMemsetAsync(clean.p, 0, 4 * kCNum * sizeof(int), s));
-  ILSM_CUDA(cudaMemsetAsync(err.p, 0, 4 * sizeof(int), s));
   ILSM_CUDA(cudaMemcpyAsync(slab_of_d.p, slab_of.data(), kCNum * sizeof(int), cudaMemcpyHostToDevice, s));
   ILSM_CUDA(cudaFuncSetAttribute(cube_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kVoxelBlockMax * sizeof(u64))));
@@ -229,8 +236,9 @@ void CubeMapH::release() {
   pin_counts.release();
   map_c.release(), map_s.release();
   slabs_c.release(), slabs_s.release(), from_c.release(), from_s.release(), stack_c.release(), stack_s.release();
-  scratch.release(), hscratch.release(), world_tmp.release(), cnt_c.release(), cnt_s.release(), slab_of_d.release(), stack_n.release(), clean.release();
-  valid_d.release(), err.release(), zero_list.release(), items.release(), raw.release(), pin.release();
+  cnt_c.p = cnt_s.p = err.p = nullptr;  // views into cnt_all
+  scratch.release(), hscratch.release(), world_tmp.release(), cnt_all.release(), slab_of_d.release(), stack_n.release(), clean.release();
+  zero_list.release(), raw.release(), pin.release();
 }
 
 static int cube_coord_h(double v, int cen) {
@@ -299,7 +307,8 @@ int CubeMapH::roll(const double t[3]) {
 int CubeMapH::gather(int* n_mc, int* n_ms) {
   cudaStream_t s = ctx->stream;
   int tot_c = 0, tot_s = 0;
-  GatherItem* it = reinterpret_cast<GatherItem*>(pin.p + kCNum);
+  GatherItems gi;
+  GatherItem* it = gi.it;
   for (int v = 0; v < n_valid; ++v) {
     const int sl = slab_of[valid[v]];
     it[v] = GatherItem{sl, tot_c, cnt_c_h[sl]};
@@ -310,10 +319,10 @@ int CubeMapH::gather(int* n_mc, int* n_ms) {
   int rc;
   if ((rc = from_c.reserve(tot_c + 4)) || (rc = from_s.reserve(tot_s + 4))) return rc;
   if (n_valid == 0) return ILSM_OK;
-  ILSM_CUDA(cudaMemcpyAsync(items.p, it, 250 * sizeof(GatherItem), cudaMemcpyHostToDevice, s));
-  if (tot_c > 0) ILSM_CUDA(launch_pdl(cube_gather_kernel, dim3(8, n_valid), dim3(256), 0, s, slabs_c.p, cap, items.p, from_c.p));
-  if (tot_s > 0) ILSM_CUDA(launch_pdl(cube_gather_kernel, dim3(8, n_valid), dim3(256), 0, s, slabs_s.p, cap, items.p + 125, from_s.p));
-  count_launches(2);
+  for (int v = n_valid; v < 125; ++v) it[v] = it[125 + v] = GatherItem{0, 0, 0};
+  if (tot_c + tot_s > 0)
+    ILSM_CUDA(launch_pdl(cube_gather_kernel, dim3(8, n_valid, 2), dim3(256), 0, s, slabs_c.p, slabs_s.p, cap, gi, from_c.p, from_s.p));
+  count_launches(1);
   return check_launch("cube_gather");
 }
 
@@ -327,12 +336,11 @@ int CubeMapH::insert(const int* d_counts, int nc_host, int ns_host, int world_fr
 int CubeMapH::filter_valid(cudaStream_t s) {
   if (n_valid == 0) return ILSM_OK;
   if (!s) s = ctx->stream;
-  int* p = pin.p + kCNum + 1024;
-  for (int v = 0; v < n_valid; ++v) p[v] = slab_of[valid[v]];
-  ILSM_CUDA(cudaMemcpyAsync(valid_d.p, p, n_valid * sizeof(int), cudaMemcpyHostToDevice, s));
+  ValidSlabs vs;
+  for (int v = 0; v < 125; ++v) vs.slab[v] = v < n_valid ? slab_of[valid[v]] : 0;
   // shared memory: the hash-based path's 192 KB only when a cube can be large enough to take it
   const size_t smem = cap > 2048 ? kVgHashSmemBytes : (size_t)kVoxelBlockMax * sizeof(u64);
-  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), smem, s, valid_d.p, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p, hscratch.p, clean.p, vg_merge ? 1 : 0));
+  ILSM_CUDA(launch_pdl(cube_filter_kernel, dim3(2 * n_valid), dim3(1024), smem, s, vs, slabs_c.p, slabs_s.p, cnt_c.p, cnt_s.p, cap, line_res, plane_res, scratch.p, err.p, hscratch.p, clean.p, vg_merge ? 1 : 0));
   count_launches(1);
   return check_launch("cube_filter");
 }
@@ -341,9 +349,7 @@ int CubeMapH::filter_valid(cudaStream_t s) {
 int CubeMapH::fetch_counts(cudaStream_t s) {
   if (!s) s = ctx->stream;
   // pinned staging: a D2H copy into pageable memory would block the host until it has run
-  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p, cnt_c.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
-  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p + kCNum, cnt_s.p, kCNum * sizeof(int), cudaMemcpyDeviceToHost, s));
-  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p + 2 * kCNum, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  ILSM_CUDA(cudaMemcpyAsync(pin_counts.p, cnt_all.p, (2 * kCNum + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));  // cnt_c | cnt_s | err
   counts_in_flight = true;
   return ILSM_OK;
 }
@@ -431,8 +437,9 @@ int cubemap_frame_enqueue(CubeMapH& m, const float* d_c, int nc, const float* d_
   // pipeline: they overlap the next frame's upload and front end, wait_tail() joins them)
   unsigned char* pin = c.pinned.p;
   int* pin_i = m.pin.p + kCNum + 2048;
-  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p->xq, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  ILSM_CUDA(cudaMemcpyAsync(pin + 64, &c.lm.p->report, sizeof(ilsm_reg_report), cudaMemcpyDeviceToHost, c.stream));
+  // pose and report in ONE copy: the LM state up to the end of the report is contiguous (xq first)
+  static_assert(offsetof(LmState, xq) == 0 && kLmHostBytes <= 1024, "the pose-in staging area starts at pinned + 1024");
+  ILSM_CUDA(cudaMemcpyAsync(pin, c.lm.p, kLmHostBytes, cudaMemcpyDeviceToHost, c.stream));
   ILSM_CUDA(cudaMemcpyAsync(pin_i + 1, m.cur_stack_n(), 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   cudaStream_t ts = defer_tail ? c.aux : c.stream;
   if (defer_tail) {
@@ -469,7 +476,7 @@ int cubemap_frame_collect(CubeMapH& m, double q_w[4], double t_w[3], ilsm_reg_re
   for (int i = 0; i < 4; ++i) q_w[i] = out[i];
   for (int i = 0; i < 3; ++i) t_w[i] = out[4 + i];
   if (report && optimise) {
-    memcpy(report, pin + 64, sizeof(*report));
+    memcpy(report, pin + offsetof(LmState, report), sizeof(*report));
     report->passes = m.pend.outer;
   }
   // transformUpdate (laserMapping.cpp:145-149)

@@ -12,6 +12,15 @@ constexpr int kCW = 21, kCH = 21, kCD = 11, kCNum = kCW * kCH * kCD;
 struct GatherItem {
   int slab, offset, count;
 };
+// Launch parameters passed BY VALUE (kernel parameter space): the 2 x 125 gather items and the valid-cube list of a frame used
+// to be staged in pinned memory and copied to the device before their kernels -- one API call each on the mapping stage's
+// host-bound critical path.
+struct GatherItems {
+  GatherItem it[250];  // [0, 125): corner cubes, [125, 250): surf cubes
+};
+struct ValidSlabs {
+  int slab[125];
+};
 
 struct QuatH {
   double x, y, z, w;
@@ -42,7 +51,9 @@ struct CubeMapH {
   int valid[125], n_valid = 0;
   DevBuf<float4> slabs_c, slabs_s, from_c, from_s, stack_c, stack_s, scratch, world_tmp;
   DevBuf<uint32_t> hscratch;  // hash-based VoxelGrid scratch, one slice per cube_filter block
-  DevBuf<int> cnt_c, cnt_s, slab_of_d, stack_n, valid_d, err, zero_list;
+  DevBuf<int> cnt_all;              // cnt_c | cnt_s | err, contiguous
+  DevBuf<int> cnt_c, cnt_s, err;    // views into cnt_all (not owned)
+  DevBuf<int> slab_of_d, stack_n, zero_list;
   // per slab and cloud kind: [0, 2 kCNum) the last VoxelGrid pass left the cube unchanged and nothing was inserted since;
   // [2 kCNum, 4 kCNum) how many leading points of the cube are the output of its last pass (merge precondition)
   DevBuf<int> clean;
@@ -54,7 +65,6 @@ struct CubeMapH {
   const float4* cur_stack_c() const { return ext_c ? ext_c : stack_c.p; }
   const float4* cur_stack_s() const { return ext_s ? ext_s : stack_s.p; }
   const int* cur_stack_n() const { return ext_n ? ext_n : stack_n.p; }
-  DevBuf<GatherItem> items;
   DevBuf<float> raw;
   PinnedBuf<int> pin;
 
