@@ -226,11 +226,14 @@ static int frontend_stage(SlamH& s, Ctx& f, const SlamH::FeJob& j, SlamH::FeResu
   const size_t bytes = (size_t)j.n * j.stride;
   int rc;
   if ((rc = f.fe.raw.reserve(bytes / 4 + 4))) return rc;
+  PhaseClock fclk(s.phase_s);  // [9] upload + front-end launches, [10] wait for the feature counts, [11] gathers (this thread only)
   if (bytes) ILSM_CUDA(cudaMemcpyAsync(f.fe.raw.p, j.xyzi, bytes, cudaMemcpyHostToDevice, f.stream));
   if ((rc = f.features_dev(f.fe.raw.p, j.n, j.stride, s.min_range))) return rc;
   int* pin = reinterpret_cast<int*>(f.pinned.p);
   ILSM_CUDA(cudaMemcpyAsync(pin, f.fe.counts.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, f.stream));
+  fclk.lap(9);
   ILSM_CUDA(cudaStreamSynchronize(f.stream));
+  fclk.lap(10);
   if (pin[5]) return fail(ILSM_ERR_INVALID_ARG, "slam_frame: a ring segment exceeds the supported size");
   for (int i = 0; i < 8; ++i) r.counts[i] = pin[i];
   const int n_sharp = pin[1], n_lsharp = pin[2], n_flat = pin[3], n_lflat = pin[4];
@@ -244,6 +247,7 @@ static int frontend_stage(SlamH& s, Ctx& f, const SlamH::FeJob& j, SlamH::FeResu
     return rc;
   if (n_lflat) ILSM_CUDA(cudaMemcpyAsync(o.lflat.p, f.fe.lflat.p, (size_t)n_lflat * sizeof(float4), cudaMemcpyDeviceToDevice, f.stream));
   ILSM_CUDA(cudaEventRecord(o.ev, f.stream));
+  fclk.lap(11);
   return ILSM_OK;
 }
 
@@ -423,9 +427,11 @@ ILSM_API void ilsm_slam_destroy(ilsm_slam* slam) {
     s.fworker.join();
   }
   if (getenv("ILSM_STAGE_TRACE"))
-    fprintf(stderr, "[ilsm stage trace] frames %lld  tail-wait %.1f us  enqueue %.1f us  collect %.1f us per frame\n", s.frames,
+    fprintf(stderr, "[ilsm stage trace] frames %lld  mapping: tail-wait %.1f us  enqueue %.1f us  collect %.1f us   front end: launches %.1f us  "
+                    "wait %.1f us  gathers %.1f us per frame\n", s.frames,
             1e6 * s.phase_s[8] / (s.frames ? s.frames : 1), 1e6 * s.phase_s[6] / (s.frames ? s.frames : 1),
-            1e6 * s.phase_s[7] / (s.frames ? s.frames : 1));
+            1e6 * s.phase_s[7] / (s.frames ? s.frames : 1), 1e6 * s.phase_s[9] / (s.frames ? s.frames : 1),
+            1e6 * s.phase_s[10] / (s.frames ? s.frames : 1), 1e6 * s.phase_s[11] / (s.frames ? s.frames : 1));
   if (s.ctx0) {
     std::lock_guard<std::mutex> lk0(s.ctx0->c.mu);
     cudaSetDevice(s.ctx0->c.device);
