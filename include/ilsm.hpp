@@ -616,6 +616,49 @@ class LoamPipeline {
   bool pipelined_;
 };
 
+// The same three nodes as three STAGES (ilsm_slam_create_staged): scanRegistration, laserOdometry and laserMapping each on
+// its own context and host thread inside the handle, the way the reference runs three processes.  push(cloud) hands frame k
+// to the front-end stage and returns what has come out of the other two: the odometry pose of frame k - 1 and the mapped
+// pose of frame k - 2 (frame indices in odom_frame / map_frame, -1 while the stages fill); drain() advances the stages
+// without a new frame -- two calls after the last push hand out everything.  The cloud handed to push() is read
+// asynchronously: the object keeps its own copy until the next call returns.
+class StagedLoamPipeline {
+ public:
+  StagedLoamPipeline(float lineRes = 0.4f, float planeRes = 0.8f, float minimum_range = 0.3f, int cube_capacity = 0,
+                     ContextPtr ctx = Context::shared())
+      : ctx_(std::move(ctx)) {
+    check(ilsm_slam_create_staged(ctx_->get(), lineRes, planeRes, minimum_range, cube_capacity, &slam_), "ilsm_slam_create_staged");
+  }
+  ~StagedLoamPipeline() { ilsm_slam_destroy(slam_); }
+  StagedLoamPipeline(const StagedLoamPipeline&) = delete;
+  StagedLoamPipeline& operator=(const StagedLoamPipeline&) = delete;
+  int odom_frame = -1, map_frame = -1;
+  double q_odom[4] = {0, 0, 0, 1}, t_odom[3] = {0, 0, 0};  // /laser_odom_to_init of frame odom_frame
+  double q_map[4] = {0, 0, 0, 1}, t_map[3] = {0, 0, 0};    // /aft_mapped_to_init of frame map_frame
+  ilsm_slam_stats stats;
+  template <typename CloudT>
+  void push(const CloudT& laserCloudIn, bool use_aloam = true) {
+    typedef typename std::remove_reference<decltype(laserCloudIn.points[0])>::type P;
+    std::vector<float>& keep = held_[turn_ ^= 1];
+    const size_t floats = laserCloudIn.points.size() * (sizeof(P) / 4);
+    keep.resize(floats);
+    if (floats) std::memcpy(keep.data(), laserCloudIn.points.data(), floats * 4);
+    check(ilsm_slam_frame_staged(slam_, keep.data(), (int)laserCloudIn.points.size(), (int)sizeof(P), use_aloam ? 1 : 0, q_odom, t_odom,
+                                 &odom_frame, q_map, t_map, &map_frame, &stats), "ilsm_slam_frame_staged");
+  }
+  void drain() {
+    check(ilsm_slam_frame_staged(slam_, nullptr, -1, 16, 1, q_odom, t_odom, &odom_frame, q_map, t_map, &map_frame, &stats),
+          "ilsm_slam_frame_staged");
+  }
+  ilsm_slam* handle() const { return slam_; }
+
+ private:
+  ContextPtr ctx_;
+  ilsm_slam* slam_ = nullptr;
+  std::vector<float> held_[2];
+  int turn_ = 0;
+};
+
 // ------------------------------------------------------------------------------------------------ parameters
 // The keys the reference's nodes read from the ROS parameter server (config/spot.yaml + launch/spot.launch:4-6), for a build
 // without ROS: a two-level "key: value  # comment" reader that accepts the reference's own spot.yaml unchanged, and a

@@ -308,7 +308,7 @@ static void test_scan_to_map_registration() {
 }
 
 static void test_loam_pipeline() {
-  std::printf("LoamPipeline: synchronous vs pipelined mapping stage (same poses, one call later)\n");
+  std::printf("LoamPipeline: synchronous vs pipelined mapping stage vs three stages (same poses, one / two calls later)\n");
   // an OS0-like +-45 deg sensor: the 64-ring formula keeps the beams within +-22.5 deg (scanRegistration.cpp:308-316), which
   // also keeps the less-flat cloud under the 16384 points one ilsm_slam_frame call accepts per feature cloud
   const int H = 64, W = 1024, F = 6;
@@ -334,6 +334,20 @@ static void test_loam_pipeline() {
   EXPECT(!pipe.flush());
   EXPECT(mapped_pipe == mapped_sync);
   EXPECT(sync.stats.n_less_flat > 500);
+  // ... and as three stages: odometry one call later, mapped pose two calls later, the same numbers
+  ilsm::StagedLoamPipeline staged(0.4f, 0.8f, 0.3f);
+  std::vector<std::vector<double>> mapped_staged(F);
+  int n_mapped = 0;
+  for (int k = 0; k < F + 2; ++k) {
+    if (k < F) staged.push(frames[k]);
+    else staged.drain();
+    EXPECT(staged.odom_frame == (k >= 1 && k <= F ? k - 1 : -1) && staged.map_frame == (k >= 2 ? k - 2 : -1));
+    if (staged.map_frame >= 0) {
+      mapped_staged[staged.map_frame] = {staged.q_map[0], staged.q_map[1], staged.q_map[2], staged.q_map[3], staged.t_map[0], staged.t_map[1], staged.t_map[2]};
+      ++n_mapped;
+    }
+  }
+  EXPECT(n_mapped == F && mapped_staged == mapped_sync);
   // informational: the sensor moved by (0.75, 0.10) m in the world, i.e. (0.746, -0.126) m in the first sensor frame (yaw 0.3)
   std::printf("  mapped translation after %d frames: %.3f %.3f %.3f (sensor displacement in the map frame: 0.746 -0.126 0.000)\n", F,
               sync.t_map[0], sync.t_map[1], sync.t_map[2]);
