@@ -429,135 +429,202 @@ __device__ __forceinline__ void mark_neighbours(const float4* cloud, unsigned ch
   __syncwarp();
 }
 
-// pass 6: one warp per ring walks the six segments in order (the picks of one segment suppress neighbours that
-// may belong to the next, so segments stay sequential; rings are independent).  32 sorted entries are tested per
-// step, the first eligible one is taken, its neighbours are marked, and the test is repeated.
+// pass 6: feature picking (scanRegistration.cpp:427-565), one block of six warps per ring.
+// Inside a segment the picks are a dependent chain (the first eligible entry in sorted order is taken, its neighbours are
+// suppressed, the test is repeated): one warp walks it, 32 sorted entries per window -- the window's indices and curvature
+// tests are loaded once, after every pick only the picked flags of the lanes behind it are read again.
+// Between segments the reference is sequential too, but the coupling is thin: segment j + 1 depends on segment j only
+// through the picked flags segment j's picks leave on the FIRST FIVE points of segment j + 1 (a pick suppresses at most five
+// neighbours ahead), and an initially suppressed point changes the outcome only if segment j + 1 would have picked it.
+// So the six segments are picked SPECULATIVELY in parallel, each warp on private flags, and then checked in order: a
+// segment whose own picks avoid the points its predecessor's final run suppressed is exactly the sequential result;
+// otherwise it is re-run with those points suppressed (and its successor is checked against the new run).  Rings with a
+// segment shorter than 11 points (a predecessor's suppression could reach past it) and rings that do not fit the staging
+// buffers take the sequential order on one warp.
 constexpr int kPickCap = 1536;  // ring points staged in shared memory (an OS0-64 ring has 1024)
-__global__ void __launch_bounds__(32) fe_pick_kernel(const float4* __restrict__ g_cloud, const float* __restrict__ g_curv,
-                                                     const int* __restrict__ g_sort_ind, int* __restrict__ st,
-                                                     int* __restrict__ label, unsigned char* __restrict__ g_picked,
-                                                     int* __restrict__ ring_sharp, int* __restrict__ ring_lsharp,
-                                                     int* __restrict__ ring_flat) {
+constexpr int kPickWarps = 6;
+
+struct SegPicks {  // what one segment's run picked, in pick order (labels are written once the run is final)
+  int n_sharp, n_lsharp, n_flat;
+  int sharp[2], lsharp[20], flat[4];
+};
+
+__device__ __forceinline__ void pick_segment(const float4* cloud, const float* curv, const int* sort_ind, unsigned char* picked, int sp,
+                                             int ep, int lane, SegPicks* out) {
+  int n_sharp = 0, n_lsharp = 0, n_flat = 0;
+  // ---- sharp / less sharp: descending curvature
+  int largest = 0;
+  int k = ep;
+  bool stop = false;
+  while (k >= sp && !stop) {
+    const int kk = k - lane;
+    int ind = -1;
+    bool low = false;
+    if (kk >= sp) {
+      ind = sort_ind[kk];
+      low = !((double)curv[ind] > 0.1);
+    }
+    const unsigned lm = __ballot_sync(0xffffffffu, low);
+    const int fl = lm ? __ffs(lm) - 1 : 32;  // sorted: from here on the curvature is <= 0.1 and nothing qualifies
+    unsigned avail = __ballot_sync(0xffffffffu, kk >= sp && !low) & (fl < 32 ? (1u << fl) - 1u : 0xffffffffu);
+    while (avail) {
+      const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
+      const unsigned em = __ballot_sync(0xffffffffu, elig);
+      if (!em) break;
+      const int fe = __ffs(em) - 1;
+      const int pick = __shfl_sync(0xffffffffu, ind, fe);
+      ++largest;
+      if (largest <= 2) {
+        if (lane == 0) out->sharp[n_sharp] = pick, out->lsharp[n_lsharp] = pick;
+        ++n_sharp, ++n_lsharp;
+      } else if (largest <= 20) {
+        if (lane == 0) out->lsharp[n_lsharp] = pick;
+        ++n_lsharp;
+      } else {
+        stop = true;
+        break;
+      }
+      mark_neighbours(cloud, picked, pick, lane);
+      avail &= ~((2u << fe) - 1u);  // the lanes up to the pick are behind us (fe = 31: 2u << 31 wraps to 0, mask = all)
+    }
+    if (fl < 32) break;
+    k -= 32;
+  }
+  // ---- flat: ascending curvature, four picks, the fourth does not suppress its neighbours
+  int smallest = 0;
+  k = sp;
+  stop = false;
+  while (k <= ep && !stop) {
+    const int kk = k + lane;
+    int ind = -1;
+    bool high = false;
+    if (kk <= ep) {
+      ind = sort_ind[kk];
+      high = !((double)curv[ind] < 0.1);
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, high);
+    const int fh = hm ? __ffs(hm) - 1 : 32;
+    unsigned avail = __ballot_sync(0xffffffffu, kk <= ep && !high) & (fh < 32 ? (1u << fh) - 1u : 0xffffffffu);
+    while (avail) {
+      const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
+      const unsigned em = __ballot_sync(0xffffffffu, elig);
+      if (!em) break;
+      const int fe = __ffs(em) - 1;
+      const int pick = __shfl_sync(0xffffffffu, ind, fe);
+      if (lane == 0) out->flat[n_flat] = pick;
+      ++n_flat;
+      ++smallest;
+      if (smallest >= 4) {
+        stop = true;
+        break;
+      }
+      mark_neighbours(cloud, picked, pick, lane);
+      avail &= ~((2u << fe) - 1u);
+    }
+    if (fh < 32) break;
+    k += 32;
+  }
+  __syncwarp();
+  if (lane == 0) out->n_sharp = n_sharp, out->n_lsharp = n_lsharp, out->n_flat = n_flat;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * kPickWarps) fe_pick_kernel(const float4* __restrict__ g_cloud, const float* __restrict__ g_curv,
+                                                                   const int* __restrict__ g_sort_ind, int* __restrict__ st,
+                                                                   int* __restrict__ label, unsigned char* __restrict__ g_picked,
+                                                                   int* __restrict__ ring_sharp, int* __restrict__ ring_lsharp,
+                                                                   int* __restrict__ ring_flat) {
   pdl_entry();
   __shared__ float4 s_cloud[kPickCap];
   __shared__ float s_curv[kPickCap];
   __shared__ int s_sort[kPickCap];
-  __shared__ unsigned char s_picked[kPickCap];
-  const int ring = blockIdx.x, lane = threadIdx.x;
+  __shared__ unsigned char s_picked[kPickWarps][kPickCap];
+  __shared__ SegPicks s_seg[kPickWarps];
+  const int ring = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int S, E;
   ring_bounds(st, ring, S, E);
   if (E - S < 6) return;
-  // every access of this ring's picking falls into [S - 5, E + 6): stage it once, the sequential picks then run on
-  // shared-memory latency instead of a dependent global round trip per step
+  // every access of this ring's picking falls into [S - 5, E + 6): stage it once, the picks then run on shared-memory latency
   const int base = S - 5, cnt = E + 6 - base;
-  const float4* cloud = g_cloud;
-  const float* curv = g_curv;
-  const int* sort_ind = g_sort_ind;
-  unsigned char* picked = g_picked;
-  if (cnt <= kPickCap) {
-    for (int t = lane; t < cnt; t += 32) {
+  const bool staged = cnt <= kPickCap;
+  const int sp = S + (E - S) * warp / 6, ep = S + (E - S) * (warp + 1) / 6 - 1;  // this warp's segment (:440-441)
+  const bool seg_ok = ep - sp + 1 <= kMaxSeg;                                    // larger ones are flagged by the sort kernel and skipped
+  const bool parallel = staged && (E - S) / 6 >= 11;                             // every segment at least 11 points long
+  if (tid < kPickWarps) s_seg[tid].n_sharp = s_seg[tid].n_lsharp = s_seg[tid].n_flat = 0;
+  if (staged) {
+    for (int t = tid; t < cnt; t += blockDim.x) {
       s_cloud[t] = g_cloud[base + t];
       s_curv[t] = g_curv[base + t];
       s_sort[t] = g_sort_ind[base + t];
-      s_picked[t] = 0;
     }
-    __syncwarp();
-    cloud = s_cloud - base, curv = s_curv - base, sort_ind = s_sort - base, picked = s_picked - base;
+    for (int t = tid; t < kPickWarps * kPickCap / 4; t += blockDim.x) reinterpret_cast<uint32_t*>(&s_picked[0][0])[t] = 0u;
   }
-  int n_sharp = 0, n_lsharp = 0, n_flat = 0;
-  for (int j = 0; j < 6; ++j) {
-    const int sp = S + (E - S) * j / 6, ep = S + (E - S) * (j + 1) / 6 - 1;
-    if (ep - sp + 1 > kMaxSeg) continue;  // flagged by the sort kernel
-    // ---- sharp / less sharp: descending curvature.  A window of 32 sorted entries is loaded once (index, curvature
-    // test); after every pick only the picked flags of the lanes behind it are read again -- the picks of a window are a
-    // dependent chain, and the index / curvature loads were two thirds of its length.
-    int largest = 0;
-    int k = ep;
-    bool stop = false;
-    while (k >= sp && !stop) {
-      const int kk = k - lane;
-      int ind = -1;
-      bool low = false;
-      if (kk >= sp) {
-        ind = sort_ind[kk];
-        low = !((double)curv[ind] > 0.1);
-      }
-      const unsigned lm = __ballot_sync(0xffffffffu, low);
-      const int fl = lm ? __ffs(lm) - 1 : 32;  // sorted: from here on the curvature is <= 0.1 and nothing qualifies
-      unsigned avail = __ballot_sync(0xffffffffu, kk >= sp && !low) & (fl < 32 ? (1u << fl) - 1u : 0xffffffffu);
-      while (avail) {
-        const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
-        const unsigned em = __ballot_sync(0xffffffffu, elig);
-        if (!em) break;
-        const int fe = __ffs(em) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, fe);
-        ++largest;
-        if (largest <= 2) {
-          if (lane == 0) {
-            label[pick] = 2;
-            ring_sharp[ring * 12 + n_sharp] = pick;
-            ring_lsharp[ring * 120 + n_lsharp] = pick;
+  __syncthreads();
+  if (parallel) {
+    const float4* cloud = s_cloud - base;
+    const float* curv = s_curv - base;
+    const int* sort_ind = s_sort - base;
+    unsigned char* mine = s_picked[warp] - base;
+    if (seg_ok) pick_segment(cloud, curv, sort_ind, mine, sp, ep, lane, &s_seg[warp]);
+    __syncthreads();
+    // in segment order: the points this segment's predecessor (final run) suppressed among its first five
+#pragma unroll 1
+    for (int j = 1; j < kPickWarps; ++j) {
+      if (warp == j && seg_ok) {
+        const unsigned char* prev = s_picked[j - 1] - base;
+        const unsigned inc = __ballot_sync(0xffffffffu, lane < 5 && prev[sp + lane] != 0);
+        if (inc) {
+          const SegPicks& r = s_seg[j];
+          bool hit = false;  // did this segment's run pick one of them?  (the lists hold at most 20 + 4 picks)
+          if (lane < r.n_lsharp) hit = (unsigned)(r.lsharp[lane] - sp) < 5u && ((inc >> (r.lsharp[lane] - sp)) & 1u);
+          if (lane >= 24 && lane - 24 < r.n_flat) hit = (unsigned)(r.flat[lane - 24] - sp) < 5u && ((inc >> (r.flat[lane - 24] - sp)) & 1u);
+          if (__any_sync(0xffffffffu, hit)) {  // yes: pick it again, with those points suppressed from the start
+            for (int t = sp - 5 + lane; t <= ep + 5; t += 32) mine[t] = 0;
+            __syncwarp();
+            if (lane < 5 && ((inc >> lane) & 1u)) mine[sp + lane] = 1;
+            __syncwarp();
+            pick_segment(cloud, curv, sort_ind, mine, sp, ep, lane, &s_seg[j]);
           }
-          ++n_sharp, ++n_lsharp;
-        } else if (largest <= 20) {
-          if (lane == 0) {
-            label[pick] = 1;
-            ring_lsharp[ring * 120 + n_lsharp] = pick;
-          }
-          ++n_lsharp;
-        } else {
-          stop = true;
-          break;
         }
-        mark_neighbours(cloud, picked, pick, lane);
-        avail &= ~((2u << fe) - 1u);  // the lanes up to the pick are behind us (fe = 31: 2u << 31 wraps to 0, mask = all)
       }
-      if (fl < 32) break;
-      k -= 32;
+      __syncthreads();
     }
-    // ---- flat: ascending curvature, four picks, the fourth does not suppress its neighbours
-    int smallest = 0;
-    k = sp;
-    stop = false;
-    while (k <= ep && !stop) {
-      const int kk = k + lane;
-      int ind = -1;
-      bool high = false;
-      if (kk <= ep) {
-        ind = sort_ind[kk];
-        high = !((double)curv[ind] < 0.1);
+  } else {
+    // sequential order on one warp, one set of flags for the whole ring (shared when the ring is staged, else global)
+    if (warp == 0) {
+      const float4* cloud = staged ? s_cloud - base : g_cloud;
+      const float* curv = staged ? s_curv - base : g_curv;
+      const int* sort_ind = staged ? s_sort - base : g_sort_ind;
+      unsigned char* picked = staged ? s_picked[0] - base : g_picked;
+      for (int j = 0; j < 6; ++j) {
+        const int spj = S + (E - S) * j / 6, epj = S + (E - S) * (j + 1) / 6 - 1;
+        if (epj - spj + 1 > kMaxSeg) continue;
+        pick_segment(cloud, curv, sort_ind, picked, spj, epj, lane, &s_seg[j]);
       }
-      const unsigned hm = __ballot_sync(0xffffffffu, high);
-      const int fh = hm ? __ffs(hm) - 1 : 32;
-      unsigned avail = __ballot_sync(0xffffffffu, kk <= ep && !high) & (fh < 32 ? (1u << fh) - 1u : 0xffffffffu);
-      while (avail) {
-        const bool elig = ((avail >> lane) & 1u) && picked[ind] == 0;
-        const unsigned em = __ballot_sync(0xffffffffu, elig);
-        if (!em) break;
-        const int fe = __ffs(em) - 1;
-        const int pick = __shfl_sync(0xffffffffu, ind, fe);
-        if (lane == 0) {
-          label[pick] = -1;
-          ring_flat[ring * 24 + n_flat] = pick;
-        }
-        ++n_flat;
-        ++smallest;
-        if (smallest >= 4) {
-          stop = true;
-          break;
-        }
-        mark_neighbours(cloud, picked, pick, lane);
-        avail &= ~((2u << fe) - 1u);
-      }
-      if (fh < 32) break;
-      k += 32;
     }
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) {
-    st[kStSharp + ring] = n_sharp;
-    st[kStLSharp + ring] = n_lsharp;
-    st[kStFlat + ring] = n_flat;
+  // ---- labels and the ring's three index lists, segments in order (the reference appends as it goes)
+  int o_sharp = 0, o_lsharp = 0, o_flat = 0;
+  for (int j = 0; j < warp; ++j) o_sharp += s_seg[j].n_sharp, o_lsharp += s_seg[j].n_lsharp, o_flat += s_seg[j].n_flat;
+  const SegPicks& r = s_seg[warp];
+  if (lane < r.n_lsharp) {
+    const int pick = r.lsharp[lane];
+    label[pick] = lane < r.n_sharp ? 2 : 1;  // the first (up to two) picks of a segment are the sharp ones
+    ring_lsharp[ring * 120 + o_lsharp + lane] = pick;
+    if (lane < r.n_sharp) ring_sharp[ring * 12 + o_sharp + lane] = pick;
+  }
+  if (lane < r.n_flat) {
+    const int pick = r.flat[lane];
+    label[pick] = -1;
+    ring_flat[ring * 24 + o_flat + lane] = pick;
+  }
+  if (tid == 0) {
+    int ns = 0, nl = 0, nf = 0;
+    for (int j = 0; j < kPickWarps; ++j) ns += s_seg[j].n_sharp, nl += s_seg[j].n_lsharp, nf += s_seg[j].n_flat;
+    st[kStSharp + ring] = ns;
+    st[kStLSharp + ring] = nl;
+    st[kStFlat + ring] = nf;
   }
 }
 
@@ -959,7 +1026,7 @@ int Ctx::features_launch(const float* d_in, int n, int stride_bytes, float min_r
     ILSM_CUDA(launch_pdl(fe_bucket_kernel, dim3(B), dim3(kFeChunk), 0, stream, d_in, n, stride_f, f.scanid.p, f.ori.p, f.stats.p, f.chunk_base.p, f.cloud.p, f.src_index.p));
     ILSM_CUDA(launch_pdl(fe_curvature_kernel, dim3(B), dim3(T), 0, stream, f.cloud.p, f.stats.p, f.curv.p, f.label.p, f.picked.p));
     ILSM_CUDA(launch_pdl(fe_sort_kernel, dim3(kRings * 6), dim3(256), 0, stream, f.curv.p, f.stats.p, f.sort_ind.p));
-    ILSM_CUDA(launch_pdl(fe_pick_kernel, dim3(kRings), dim3(32), 0, stream, f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p));
+    ILSM_CUDA(launch_pdl(fe_pick_kernel, dim3(kRings), dim3(32 * kPickWarps), 0, stream, f.cloud.p, f.curv.p, f.sort_ind.p, f.stats.p, f.label.p, f.picked.p, f.ring_sharp.p, f.ring_lsharp.p, f.ring_flat.p));
     ILSM_CUDA(launch_pdl(fe_lessflat_kernel, dim3(kRings), dim3(256), 0, stream, f.cloud.p, f.label.p, f.stats.p, f.ring_pts.p, f.ring_out.p, ring_cap, 0.2f));
     count_launches(8);
   }
