@@ -447,7 +447,8 @@ static __device__ int voxelgrid_block_hash(const float4* __restrict__ pts, int m
 //     first) plus the new members; absent: a new output voxel;
 //   * every untouched old point moves up by the number of new voxels below it (one binary search), its value passing
 //     through the same float operations as a one-member voxel, (0 + p) / 1.
-// Bit-identical to the general path by construction; O(n log m) instead of a hash + sort of everything.
+// Bit-identical to the general path by construction; O(n log m) instead of a hash + sort of everything, and one pass over
+// the cube instead of three (the keys are taken relative to the first point's voxel: no bounding box is needed for an order).
 // Shared memory: 64 KB of old keys + 16 KB of new sort keys + 20 KB of per-new-voxel tables.  Returns the number of
 // voxels, or -1 (block-uniform) when the preconditions do not hold.
 // ---------------------------------------------------------------------------------------------------
@@ -475,69 +476,42 @@ static __device__ __forceinline__ int block_excl_scan_1024(int v, int* wc, int* 
 
 static __device__ int voxelgrid_block_merge(const float4* __restrict__ pts, int n_old, int n, float leaf, unsigned char* smem,
                                             float4* __restrict__ out, int* err) {
-  __shared__ float s_min[3], s_max[3];
+  __shared__ int s_ref[3];
   __shared__ int wc[32];
   uint32_t* ek = reinterpret_cast<uint32_t*>(smem);                                     // old keys (ascending when valid)
   u64* nk = reinterpret_cast<u64*>(smem + (size_t)kVoxelBlockMax * 4);                  // new (voxel << 24 | position)
   uint32_t* dkey = reinterpret_cast<uint32_t*>(smem + (size_t)kVoxelBlockMax * 4 + (size_t)kVgMergeNew * 8);  // distinct new voxels
   unsigned short* dstart = reinterpret_cast<unsigned short*>(dkey + kVgMergeNew);       // first member of each in nk (+ end)
   unsigned short* dexcl = dstart + kVgMergeNew + 2;                                     // new-only voxels before each (+ total)
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int tid = threadIdx.x, nt = blockDim.x;
   const int m = n - n_old;
-  if (tid < 3) s_min[tid] = __int_as_float(0x7f800000), s_max[tid] = __int_as_float(0xff800000);
-  __syncthreads();
-  float mn[3] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
-  float mx[3] = {__int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000)};
-  int bad = 0;
-  for (int t = tid; t < n; t += nt) {
-    const float4 p = pts[t];
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-      mn[0] = fminf(mn[0], p.x), mn[1] = fminf(mn[1], p.y), mn[2] = fminf(mn[2], p.z);
-      mx[0] = fmaxf(mx[0], p.x), mx[1] = fmaxf(mx[1], p.y), mx[2] = fmaxf(mx[2], p.z);
-    } else {
-      bad = 1;  // the general path knows how to skip points
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
-      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      int* pmn = reinterpret_cast<int*>(&s_min[a]);
-      int* pmx = reinterpret_cast<int*>(&s_max[a]);
-      if (mn[a] >= 0.f) atomicMin(pmn, __float_as_int(mn[a])); else atomicMax(reinterpret_cast<unsigned*>(pmn), __float_as_uint(mn[a]));
-      if (mx[a] >= 0.f) atomicMax(pmx, __float_as_int(mx[a])); else atomicMin(reinterpret_cast<unsigned*>(pmx), __float_as_uint(mx[a]));
-    }
-  }
-  if (__syncthreads_or(bad)) return -1;
+  // Voxel keys RELATIVE TO THE FIRST POINT'S VOXEL instead of the bounding box PCL uses: only the order of two keys and their
+  // equality matter here, and (z, y, x)-lexicographic order does not depend on the origin -- this saves the bounding-box pass
+  // over the cube.  A cube spans 50 m (125 voxels of 0.4 m), so +-255 voxels per axis is ample; anything outside (or a
+  // non-finite point) sends the block to the general path, which also owns PCL's "leaf size too small" diagnosis.
   const float inv = __fdiv_rn(1.0f, leaf);
-  int min_b[3], div_b[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    min_b[a] = __float2int_rd(__fmul_rn(s_min[a], inv));
-    div_b[a] = __float2int_rd(__fmul_rn(s_max[a], inv)) - min_b[a] + 1;
+  if (tid == 0) {
+    const float4 p = pts[0];
+    s_ref[0] = __float2int_rz(floorf(__fmul_rn(p.x, inv))), s_ref[1] = __float2int_rz(floorf(__fmul_rn(p.y, inv)));
+    s_ref[2] = __float2int_rz(floorf(__fmul_rn(p.z, inv)));
   }
-  const long long mul1 = div_b[0], mul2 = (long long)div_b[0] * div_b[1];
-  if (mul2 * div_b[2] >= (1ll << 31)) {  // pcl: "Leaf size is too small for the input dataset"
-    if (tid == 0) atomicOr(err, 2);
-    return 0;
-  }
+  __syncthreads();
+  const int r0 = s_ref[0], r1 = s_ref[1], r2 = s_ref[2];
+  int bad = 0;
   int P = 32;
   while (P < m) P <<= 1;
   for (int t = tid; t < n_old + P; t += nt) {
     uint32_t idx = 0xFFFFFFFFu;
     if (t < n) {
       const float4 p = pts[t];
-      const int i0 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)min_b[0]));
-      const int i1 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)min_b[1]));
-      const int i2 = __float2int_rz(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)min_b[2]));
-      idx = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = __float2int_rz(floorf(__fmul_rn(p.x, inv))) - r0 + 256, i1 = __float2int_rz(floorf(__fmul_rn(p.y, inv))) - r1 + 256;
+        const int i2 = __float2int_rz(floorf(__fmul_rn(p.z, inv))) - r2 + 256;
+        if ((unsigned)i0 < 512u && (unsigned)i1 < 512u && (unsigned)i2 < 512u) idx = (uint32_t)(i0 | (i1 << 9) | (i2 << 18));
+        else bad = 1;
+      } else {
+        bad = 1;
+      }
     }
     if (t < n_old) ek[t] = idx;
     else nk[t - n_old] = t < n ? (((u64)idx << 24) | (u64)(t - n_old)) : ~0ull;
