@@ -255,6 +255,9 @@ def config3_point(ilsm, torch, ctx, ext, flush, dev, peak, opts):
         ms.build_dev(d_ms.data_ptr(), len(hs), 16)
         ctx.associate_dev(mc, ms, d_c.data_ptr(), Qb // 8, d_s.data_ptr(), Qb - Qb // 8, 16, pose_t.data_ptr(), opts)
         ctx.sync()
+    t_as = timed(lambda: ctx.associate_dev(mc, ms, d_c.data_ptr(), Qb // 8, d_s.data_ptr(), Qb - Qb // 8, 16, pose_t.data_ptr(), opts), reps=5)
+    out["associate"] = {"points": Qb, "corner": Qb // 8, "kernel": "associate_kernel (transform + exact 5-NN + line / plane fit per point)",
+                        "ms": t_as, "points_per_s": Qb / t_as * 1e3}
     t = timed(lambda: ctx.eval_normal_eq_dev(pose_t.data_ptr(), out32.data_ptr()))
     # every factor slot read once: type 4 B + point 16 B + (normal | point_a) 32 B, + point_b 32 B for the corner slots
     byt = Qb * 52 + (Qb // 8) * 32

@@ -184,16 +184,30 @@ struct AssocParams {
 
 constexpr int kAssocThreads = 128;
 
-// One warp per stack point (grid-stride when the stacks exceed one resident wave).
+constexpr int kAssocWarps = kAssocThreads / 32;
+constexpr int kAssocChunk = 32;  // points a block gathers before one warp fits them (8 per warp)
+constexpr int kNbStride = 21;    // floats per gathered point (odd: the fitting lanes read conflict-free)
+
+// One warp per stack point for the 5-NN, one LANE per stack point for the fit.  A block works through chunks of
+// 4 * per_warp consecutive points (per_warp = 1 when the launch has a warp for every point -- the per-frame case --
+// up to 8 for large stacks): its warps run the searches and leave the five neighbours in shared memory, then the
+// lanes of warp 0 fit the chunk together while the other warps start on the next chunk (double-buffered).  A warp
+// instruction occupies the fp64 pipe for the same time whether 1 or 32 lanes are active, so fitting on lane 0 of every
+// warp -- 20 single-lane instruction streams per SM queueing behind one another -- cost more than the search itself.
+// kMulti = false: the launch has a warp for every point (per_warp = 1, one chunk of 4 per block, nothing to loop over).
+template <bool kMulti>
 __global__ void __launch_bounds__(kAssocThreads, 5)
     associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
                      int ns, int stride_f, LmState* __restrict__ st, AssocParams prm, FactorView fv,
-                     const int* __restrict__ d_counts, PoseSrc src) {
+                     const int* __restrict__ d_counts, PoseSrc src, int per_warp_arg) {
   pdl_entry();
-  __shared__ WarpScratch scratch[kAssocThreads / 32];
+  __shared__ WarpScratch scratch[kAssocWarps];
+  // 5 neighbours (x,y,z), [15] gate flag, [16..18] the point
+  __shared__ float s_nb[kMulti ? 2 : 1][kMulti ? kAssocChunk : kAssocWarps][kNbStride];
+  __shared__ int s_next[2];  // next unclaimed point of the chunk (kMulti)
+  const int per_warp = kMulti ? per_warp_arg : 1;
   if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = gridDim.x * (kAssocThreads / 32);
   // everything that does not depend on the point is fetched up front so that the latencies overlap
   int bbc[6], bbs[6];
   load_bbox(gc, bbc);
@@ -209,63 +223,95 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
 #else
 #define ASTAMP(k) do { } while (0)
 #endif
+  const int total = nc + ns;
+  const int chunk = per_warp * kAssocWarps;
+  if (kMulti) {
+    if (threadIdx.x < 2) s_next[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  int it = 0;
 #pragma unroll 1
-  for (int gid = blockIdx.x * (kAssocThreads / 32) + warp; gid < nc + ns; gid += nwarps) {
-    ASTAMP(0);
-    const bool is_corner = gid < nc;
-    const float* pp = is_corner ? corner + (size_t)gid * stride_f : surf + (size_t)(gid - nc) * stride_f;
-    const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
-    // pointAssociateToMap: double math, float store
-    const D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
-    const float qx = __double2float_rn(dadd(pw.x, tx));
-    const float qy = __double2float_rn(dadd(pw.y, ty));
-    const float qz = __double2float_rn(dadd(pw.z, tz));
-    ASTAMP(1);
-    KnnResult<5, true> res;  // the neighbours' coordinates travel with the keys: no dependent gather before the fit
-    GridView g;  // field-wise select keeps everything in registers (no local-memory copy of the parameter structs)
-    g.cells = is_corner ? gc.cells : gs.cells;
-    g.sorted = is_corner ? gc.sorted : gs.sorted;
-    g.orig = nullptr;
-    g.bbox = nullptr;
-    g.mask = is_corner ? gc.mask : gs.mask;
-    g.log2_size = is_corner ? gc.log2_size : gs.log2_size;
-    g.cell = is_corner ? gc.cell : gs.cell;
-    g.inv_cell = is_corner ? gc.inv_cell : gs.inv_cell;
-    g.n = is_corner ? gc.n : gs.n;
-    int bb[6];
+  for (int base = blockIdx.x * chunk; base < total; base += gridDim.x * chunk, ++it) {
+    const int buf = kMulti ? (it & 1) : 0;
+    const int cn = min(chunk, total - base);
+    // the other buffer's cursor was last touched before the barrier that ended the previous chunk
+    if (kMulti && threadIdx.x == 0) s_next[buf ^ 1] = 0;
+#pragma unroll 1
+    for (int turn = 0;; ++turn) {
+      int j = (int)warp;
+      if (kMulti) {
+        if (lane == 0) j = atomicAdd(&s_next[buf], 1);
+        j = __shfl_sync(0xffffffffu, j, 0);
+      } else if (turn) {
+        break;
+      }
+      if (j >= cn) break;
+      const int gid = base + j;
+      ASTAMP(0);
+      const bool is_corner = gid < nc;
+      const float* pp = is_corner ? corner + (size_t)gid * stride_f : surf + (size_t)(gid - nc) * stride_f;
+      const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
+      // pointAssociateToMap: double math, float store
+      const D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
+      const float qx = __double2float_rn(dadd(pw.x, tx));
+      const float qy = __double2float_rn(dadd(pw.y, ty));
+      const float qz = __double2float_rn(dadd(pw.z, tz));
+      ASTAMP(1);
+      KnnResult<5, true> res;  // the neighbours' coordinates travel with the keys: no dependent gather before the fit
+      GridView g;  // field-wise select keeps everything in registers (no local-memory copy of the parameter structs)
+      g.cells = is_corner ? gc.cells : gs.cells;
+      g.sorted = is_corner ? gc.sorted : gs.sorted;
+      g.orig = nullptr;
+      g.bbox = nullptr;
+      g.mask = is_corner ? gc.mask : gs.mask;
+      g.log2_size = is_corner ? gc.log2_size : gs.log2_size;
+      g.cell = is_corner ? gc.cell : gs.cell;
+      g.inv_cell = is_corner ? gc.inv_cell : gs.inv_cell;
+      g.n = is_corner ? gc.n : gs.n;
+      int bb[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) bb[i] = is_corner ? bbc[i] : bbs[i];
-    knn_search<5, true>(g, bb, qx, qy, qz, prm.gate_sq, lane, scratch[warp], res);
-    ASTAMP(2);
-    if (lane == 0) {
-      const bool gate = res.key[4] != kSentinel && cand_d2(res.key[4]) < prm.gate_sq;
+      for (int i = 0; i < 6; ++i) bb[i] = is_corner ? bbc[i] : bbs[i];
+      knn_search<5, true>(g, bb, qx, qy, qz, prm.gate_sq, lane, scratch[warp], res);
+      ASTAMP(2);
+      if (lane == 0) {
+        float* r = s_nb[buf][j];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[3 * k] = res.x[k], r[3 * k + 1] = res.y[k], r[3 * k + 2] = res.z[k];
+        r[15] = (res.key[4] != kSentinel && cand_d2(res.key[4]) < prm.gate_sq) ? 1.f : 0.f;
+        r[16] = px, r[17] = py, r[18] = pz;
+        if (fv.knn_idx) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const bool have = res.key[k] != kSentinel;
+            fv.knn_idx[(size_t)gid * 5 + k] = have ? cand_idx(res.key[k]) : -1;
+            fv.knn_d2[(size_t)gid * 5 + k] = have ? cand_d2(res.key[k]) : __int_as_float(0x7f800000);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0 && (int)lane < cn) {
+      const float* r = s_nb[buf][lane];
+      const int fid = base + (int)lane;
       int type = 0;
       double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, w = 0;
-      if (gate) {
+      if (r[15] != 0.f) {
         float nb[5][3];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) nb[k][0] = res.x[k], nb[k][1] = res.y[k], nb[k][2] = res.z[k];
-        if (is_corner) {
+        for (int k = 0; k < 5; ++k) nb[k][0] = r[3 * k], nb[k][1] = r[3 * k + 1], nb[k][2] = r[3 * k + 2];
+        if (fid < nc) {
           if (fit_line(nb, prm.line_ratio, a, b)) type = 1;
         } else {
           if (fit_plane(nb, prm.plane_tol, a, w)) type = 2;
         }
       }
-      ASTAMP(3);
-      fv.type[gid] = type;
-      fv.p[gid] = make_float4(px, py, pz, 0.f);
-      fv.a[gid] = make_double4(a[0], a[1], a[2], w);
-      fv.b[gid] = make_double4(b[0], b[1], b[2], 0.0);
-      if (fv.knn_idx) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const bool have = res.key[k] != kSentinel;
-          fv.knn_idx[(size_t)gid * 5 + k] = have ? cand_idx(res.key[k]) : -1;
-          fv.knn_d2[(size_t)gid * 5 + k] = have ? cand_d2(res.key[k]) : __int_as_float(0x7f800000);
-        }
-      }
+      fv.type[fid] = type;
+      fv.p[fid] = make_float4(r[16], r[17], r[18], 0.f);
+      fv.a[fid] = make_double4(a[0], a[1], a[2], w);
+      fv.b[fid] = make_double4(b[0], b[1], b[2], 0.0);
     }
-    __syncwarp();
+    if (!kMulti) break;
   }
 }
 
@@ -1287,11 +1333,20 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   GridView gc = mc->view(), gs = ms->view();
   FactorView fv = factor_view(fac, want_knn);
   const int stride_f = stride_bytes / 4;
-  // one warp per stack point, capped at one resident wave (5 blocks x 4 warps per SM at this register budget)
+  // one warp per stack point when one resident wave (5 blocks x 4 warps per SM at this register budget) covers the
+  // stacks, else up to 8 points per warp and chunk
   long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
-  if (blocks > cap) blocks = cap;
-  ILSM_CUDA(launch_pdl(associate_kernel, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc, d_surf, ns,
-                       stride_f, lm.p, prm, fv, d_stack_counts, ps));
+  int per_warp = 1;
+  if (blocks > cap) {
+    per_warp = (int)std::min<long long>(8, (n + cap * 4 - 1) / (cap * 4));
+    blocks = std::min(cap, ((long long)n + 4 * per_warp - 1) / (4 * per_warp));
+  }
+  if (per_warp > 1)
+    ILSM_CUDA(launch_pdl(associate_kernel<true>, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc,
+                         d_surf, ns, stride_f, lm.p, prm, fv, d_stack_counts, ps, per_warp));
+  else
+    ILSM_CUDA(launch_pdl(associate_kernel<false>, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc,
+                         d_surf, ns, stride_f, lm.p, prm, fv, d_stack_counts, ps, 1));
   count_launches(1);
   return check_launch("associate");
 }
