@@ -188,59 +188,70 @@ constexpr int kAssocWarps = kAssocThreads / 32;
 constexpr int kAssocChunk = 32;  // points a block gathers before one warp fits them (8 per warp)
 constexpr int kNbStride = 21;    // floats per gathered point (odd: the fitting lanes read conflict-free)
 
-// One warp per stack point for the 5-NN, one LANE per stack point for the fit.  A block works through chunks of
-// 4 * per_warp consecutive points (per_warp = 1 when the launch has a warp for every point -- the per-frame case --
-// up to 8 for large stacks): its warps run the searches and leave the five neighbours in shared memory, then the
-// lanes of warp 0 fit the chunk together while the other warps start on the next chunk (double-buffered).  A warp
-// instruction occupies the fp64 pipe for the same time whether 1 or 32 lanes are active, so fitting on lane 0 of every
-// warp -- 20 single-lane instruction streams per SM queueing behind one another -- cost more than the search itself.
-// kMulti = false: the launch has a warp for every point (per_warp = 1, one chunk of 4 per block, nothing to loop over).
-template <bool kMulti>
-__global__ void __launch_bounds__(kAssocThreads, 5)
-    associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
-                     int ns, int stride_f, LmState* __restrict__ st, AssocParams prm, FactorView fv,
-                     const int* __restrict__ d_counts, PoseSrc src, int per_warp_arg) {
-  pdl_entry();
-  __shared__ WarpScratch scratch[kAssocWarps];
-  // 5 neighbours (x,y,z), [15] gate flag, [16..18] the point
-  __shared__ float s_nb[kMulti ? 2 : 1][kMulti ? kAssocChunk : kAssocWarps][kNbStride];
-  __shared__ int s_next[2];  // next unclaimed point of the chunk (kMulti)
-  const int per_warp = kMulti ? per_warp_arg : 1;
-  if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // everything that does not depend on the point is fetched up front so that the latencies overlap
-  int bbc[6], bbs[6];
-  load_bbox(gc, bbc);
-  load_bbox(gs, bbs);
-  // pose: the LM state (later passes), or handed in with the launch (first pass; block 0 then seeds the LM state for
-  // the solve kernel -- nobody reads the state's pose inside this launch in that case)
-  const double* p7 = src.mode == 2 ? src.dptr : (src.mode == 1 ? src.v : st->xq);  // xq[4], xt[3] are contiguous
-  const double q[4] = {p7[0], p7[1], p7[2], p7[3]};
-  const double tx = p7[4], ty = p7[5], tz = p7[6];
-  if (src.mode != 0 && blockIdx.x == 0 && threadIdx.x < 7) st->xq[threadIdx.x] = p7[threadIdx.x];
+struct AssocShared {
+  WarpScratch scratch[kAssocWarps];
+  float nb[2][kAssocChunk][kNbStride];  // 5 neighbours (x,y,z), [15] gate flag, [16..18] the point
+  int next[2];                          // next unclaimed point of the chunk (chunks of more than one point per warp)
+  int bb[12];                           // bounding boxes of the two maps, pose (kept here by the looping variants:
+  double pose[7];                       // in registers across the fit they cost spills)
+};
+
 #ifdef ILSM_DEBUG_TIMING
 #define ASTAMP(k) do { if (lane == 0 && (gid == 5 || gid == nc + 1000)) st->dbg[48 + (gid == 5 ? 0 : 8) + (k)] = clock64(); } while (0)
 #else
 #define ASTAMP(k) do { } while (0)
 #endif
-  const int total = nc + ns;
-  const int chunk = per_warp * kAssocWarps;
-  if (kMulti) {
-    if (threadIdx.x < 2) s_next[threadIdx.x] = 0;
+
+// One warp per stack point for the 5-NN, one LANE per stack point for the fit.  A block works through chunks of
+// 4 * per_warp consecutive points: its warps run the searches and leave the five neighbours in shared memory, then the
+// lanes of warp 0 fit the chunk together while the other warps start on the next chunk (double-buffered).  A warp
+// instruction occupies the fp64 pipe for the same time whether 1 or 32 lanes are active, so fitting on lane 0 of every
+// warp -- 20 single-lane instruction streams per SM queueing behind one another -- cost more than the search itself.
+//   kLoop = false : the launch has a warp for every point (per-frame stacks): one round, everything in registers
+//   kLoop = true  : several rounds; kDynamic: up to 8 points per warp and chunk, claimed through a shared cursor
+template <bool kLoop, bool kDynamic>
+__device__ __forceinline__ void associate_rounds(AssocShared& sh, const GridView& gc, const GridView& gs,
+                                                 const float* __restrict__ corner, int nc, const float* __restrict__ surf, int ns,
+                                                 int stride_f, LmState* __restrict__ st, const AssocParams& prm,
+                                                 const FactorView& fv, const PoseSrc& src, int per_warp) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // pose: the LM state (later passes), or handed in with the launch (first pass; block 0 then seeds the LM state for
+  // the solve kernel -- nobody reads the state's pose inside this launch in that case)
+  const double* p7 = src.mode == 2 ? src.dptr : (src.mode == 1 ? src.v : st->xq);  // xq[4], xt[3] are contiguous
+  int bbr[12];
+  double pr[7];
+  if (!kLoop) {
+    // everything that does not depend on the point is fetched up front so that the latencies overlap
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bbr[i] = __ldg(gc.bbox + i), bbr[6 + i] = __ldg(gs.bbox + i);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pr[i] = p7[i];
+    if (src.mode != 0 && blockIdx.x == 0 && threadIdx.x < 7) st->xq[threadIdx.x] = p7[threadIdx.x];
+  } else {
+    if (threadIdx.x < 7) {
+      const double v = p7[threadIdx.x];
+      sh.pose[threadIdx.x] = v;
+      if (src.mode != 0 && blockIdx.x == 0) st->xq[threadIdx.x] = v;
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 38) sh.bb[threadIdx.x - 32] = gc.bbox[threadIdx.x - 32];
+    if (threadIdx.x >= 64 && threadIdx.x < 70) sh.bb[6 + threadIdx.x - 64] = gs.bbox[threadIdx.x - 64];
+    if (kDynamic && threadIdx.x >= 96 && threadIdx.x < 98) sh.next[threadIdx.x - 96] = 0;
     __syncthreads();
   }
+  const int total = nc + ns;
+  const int chunk = per_warp * kAssocWarps;
   int it = 0;
 #pragma unroll 1
   for (int base = blockIdx.x * chunk; base < total; base += gridDim.x * chunk, ++it) {
-    const int buf = kMulti ? (it & 1) : 0;
+    const int buf = kLoop ? (it & 1) : 0;
     const int cn = min(chunk, total - base);
     // the other buffer's cursor was last touched before the barrier that ended the previous chunk
-    if (kMulti && threadIdx.x == 0) s_next[buf ^ 1] = 0;
+    if (kDynamic && threadIdx.x == 0) sh.next[buf ^ 1] = 0;
 #pragma unroll 1
     for (int turn = 0;; ++turn) {
       int j = (int)warp;
-      if (kMulti) {
-        if (lane == 0) j = atomicAdd(&s_next[buf], 1);
+      if (kDynamic) {
+        if (lane == 0) j = atomicAdd(&sh.next[buf], 1);
         j = __shfl_sync(0xffffffffu, j, 0);
       } else if (turn) {
         break;
@@ -252,6 +263,14 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
       const float* pp = is_corner ? corner + (size_t)gid * stride_f : surf + (size_t)(gid - nc) * stride_f;
       const float px = __ldg(pp), py = __ldg(pp + 1), pz = __ldg(pp + 2);
       // pointAssociateToMap: double math, float store
+      double q[4], tx, ty, tz;
+      if (kLoop) {
+        q[0] = sh.pose[0], q[1] = sh.pose[1], q[2] = sh.pose[2], q[3] = sh.pose[3];
+        tx = sh.pose[4], ty = sh.pose[5], tz = sh.pose[6];
+      } else {
+        q[0] = pr[0], q[1] = pr[1], q[2] = pr[2], q[3] = pr[3];
+        tx = pr[4], ty = pr[5], tz = pr[6];
+      }
       const D3 pw = quat_rotate(q, d3((double)px, (double)py, (double)pz));
       const float qx = __double2float_rn(dadd(pw.x, tx));
       const float qy = __double2float_rn(dadd(pw.y, ty));
@@ -270,11 +289,11 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
       g.n = is_corner ? gc.n : gs.n;
       int bb[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) bb[i] = is_corner ? bbc[i] : bbs[i];
-      knn_search<5, true>(g, bb, qx, qy, qz, prm.gate_sq, lane, scratch[warp], res);
+      for (int i = 0; i < 6; ++i) bb[i] = kLoop ? sh.bb[(is_corner ? 0 : 6) + i] : (is_corner ? bbr[i] : bbr[6 + i]);
+      knn_search<5, true>(g, bb, qx, qy, qz, prm.gate_sq, lane, sh.scratch[warp], res);
       ASTAMP(2);
       if (lane == 0) {
-        float* r = s_nb[buf][j];
+        float* r = sh.nb[buf][j];
 #pragma unroll
         for (int k = 0; k < 5; ++k) r[3 * k] = res.x[k], r[3 * k + 1] = res.y[k], r[3 * k + 2] = res.z[k];
         r[15] = (res.key[4] != kSentinel && cand_d2(res.key[4]) < prm.gate_sq) ? 1.f : 0.f;
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
     }
     __syncthreads();
     if (warp == 0 && (int)lane < cn) {
-      const float* r = s_nb[buf][lane];
+      const float* r = sh.nb[buf][lane];
       const int fid = base + (int)lane;
       int type = 0;
       double a[3] = {0, 0, 0}, b[3] = {0, 0, 0}, w = 0;
@@ -311,7 +330,28 @@ __global__ void __launch_bounds__(kAssocThreads, 5)
       fv.a[fid] = make_double4(a[0], a[1], a[2], w);
       fv.b[fid] = make_double4(b[0], b[1], b[2], 0.0);
     }
-    if (!kMulti) break;
+    if (!kLoop) break;
+  }
+}
+
+// kMulti = false: one point per warp and round, statically assigned (per-frame stacks: normally a single round).
+template <bool kMulti>
+__global__ void __launch_bounds__(kAssocThreads, 5)
+    associate_kernel(GridView gc, GridView gs, const float* __restrict__ corner, int nc, const float* __restrict__ surf,
+                     int ns, int stride_f, LmState* __restrict__ st, AssocParams prm, FactorView fv,
+                     const int* __restrict__ d_counts, PoseSrc src, int per_warp) {
+  pdl_entry();
+  __shared__ AssocShared sh;
+  if (d_counts) nc = d_counts[0], ns = d_counts[1];  // stack sizes produced on the device (VoxelGrid outputs)
+  const int total = nc + ns, wave = (int)gridDim.x * kAssocWarps;
+  if (kMulti) {
+    // with device-side sizes the host only knows an upper bound: the chunk size follows the real total
+    if (d_counts) per_warp = min(8, max(1, (total + wave - 1) / wave));
+    associate_rounds<true, true>(sh, gc, gs, corner, nc, surf, ns, stride_f, st, prm, fv, src, per_warp);
+  } else if (total <= wave) {
+    associate_rounds<false, false>(sh, gc, gs, corner, nc, surf, ns, stride_f, st, prm, fv, src, 1);
+  } else {
+    associate_rounds<true, false>(sh, gc, gs, corner, nc, surf, ns, stride_f, st, prm, fv, src, 1);
   }
 }
 
@@ -1334,19 +1374,21 @@ int Ctx::associate_dev(Map* mc, Map* ms, const float* d_corner, int nc, const fl
   FactorView fv = factor_view(fac, want_knn);
   const int stride_f = stride_bytes / 4;
   // one warp per stack point when one resident wave (5 blocks x 4 warps per SM at this register budget) covers the
-  // stacks, else up to 8 points per warp and chunk
-  long long blocks = ((long long)n + 3) / 4, cap = (long long)sm_count * 5;
+  // stacks, else up to 8 points per warp and chunk.  With device-side sizes n is an upper bound (the clouds before their
+  // VoxelGrid): the one-point-per-warp kernel, which loops if it must, unless the bound is far beyond a wave.
+  const long long cap = (long long)sm_count * 5;
+  const bool multi = d_stack_counts ? (long long)n > cap * 4 * 8 : (long long)n > cap * 4;
   int per_warp = 1;
-  if (blocks > cap) {
+  long long blocks = std::min(cap, ((long long)n + 3) / 4);
+  if (multi) {
     per_warp = (int)std::min<long long>(8, (n + cap * 4 - 1) / (cap * 4));
     blocks = std::min(cap, ((long long)n + 4 * per_warp - 1) / (4 * per_warp));
-  }
-  if (per_warp > 1)
     ILSM_CUDA(launch_pdl(associate_kernel<true>, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc,
                          d_surf, ns, stride_f, lm.p, prm, fv, d_stack_counts, ps, per_warp));
-  else
+  } else {
     ILSM_CUDA(launch_pdl(associate_kernel<false>, dim3((unsigned)blocks), dim3(kAssocThreads), 0, stream, gc, gs, d_corner, nc,
                          d_surf, ns, stride_f, lm.p, prm, fv, d_stack_counts, ps, 1));
+  }
   count_launches(1);
   return check_launch("associate");
 }

@@ -166,6 +166,49 @@ def test_associate_parity(ctx, oracle_mod, cfg_small):
     mc.close(), ms.close()
 
 
+@pytest.mark.parametrize("copies", [3, 14])
+def test_associate_parity_stacks_larger_than_one_wave(ctx, oracle_mod, cfg_small, copies):
+    """Stacks with more points than the launch has warps (2960 on a B200): the kernel gathers chunks of up to 32 points per
+    block and fits them on the lanes of one warp; 14 copies exceed 8 points per warp, so a block walks several chunks and
+    one chunk straddles the corner / surf boundary.  Same factors as the oracle, point by point."""
+    c = cfg_small
+    rng = np.random.default_rng(17 + copies)
+    def tile(a):
+        b = np.tile(a, (copies, 1)).astype(np.float32)
+        b[:, :3] += rng.normal(0.0, 0.02, (len(b), 3)).astype(np.float32)
+        return b
+    corner, surf = tile(c["corner"]), tile(c["surf"])
+    assert len(corner) + len(surf) > 2960 * (8 if copies > 8 else 1)
+    mc, ms = _maps(ctx, c)
+    qt = pose7(c["q0"], c["t0"])
+    fac = ctx.associate(mc, ms, corner, surf, c["q0"], c["t0"])
+    fac = fac[0] if isinstance(fac, tuple) else fac
+    want = oracle_mod.associate(c["map_corner"], c["map_surf"], corner, surf, qt)
+    _cmp_factors(fac, want)
+    assert (fac["type"] == 1).sum() > 50 * copies and (fac["type"] == 2).sum() > 300 * copies
+    mc.close(), ms.close()
+
+
+@pytest.mark.parametrize("line_res,plane_res", [(0.4, 0.8), (0.1, 0.2)])
+def test_register_frame_parity(ctx, oracle_mod, ilsm, cfg_full, line_res, plane_res):
+    """ilsm_register_frame (front end -> VoxelGrid stacks -> association / solve with the stack sizes read on the device)
+    against the chained oracle.  With the fine leaves the stacks (about 9 k points) exceed the warps of the association
+    launch, which only knows the pre-filter sizes: its one-point-per-warp kernel then takes several rounds."""
+    c = cfg_full
+    frame = np.ascontiguousarray(c["cloud"][:, :4], np.float32)
+    mc, ms = _maps(ctx, c)
+    q, t, rep, sizes = ctx.register_frame(mc, ms, frame, c["q0"], c["t0"], 0.3, line_res, plane_res)
+    f = oracle_mod.extract_features(frame)
+    sc_ = oracle_mod.voxelgrid(f["cloud"][f["less_sharp_idx"]], line_res)
+    ss_ = oracle_mod.voxelgrid(f["less_flat"], plane_res)
+    assert sizes == (len(f["less_sharp_idx"]), len(f["less_flat"]), len(sc_), len(ss_))
+    if line_res < 0.4:
+        assert len(sc_) + len(ss_) > 2960
+    x, _, _ = oracle_mod.register_aloam(c["map_corner"], c["map_surf"], sc_, ss_, pose7(c["q0"], c["t0"]))
+    assert np.linalg.norm(t - x[4:]) < 1e-6 and ilsm.synth.quat_angle(q, x[:4]) < 1e-6
+    mc.close(), ms.close()
+
+
 def test_associate_matches_reference_code_golden(ctx):
     """The CUDA association against the residual blocks the REFERENCE's own code builds (laserMapping.cpp:624-873 compiled
     from the reference tree with a recording ceres::Problem, tests/golden/make_golden_lasermapping.py): the same stack points
