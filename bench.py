@@ -699,7 +699,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -916,13 +916,35 @@ def run_gpu(args, rank, world, local_rank):
                          ("cpu_baseline", cpu), ("cpu_baselines", cpu_more)):
             if val is not None:
                 line[key] = val
-        print(json.dumps(line), flush=True)
+        emit(line)
     mc.close(), ms.close(), ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native code prints there too (the NCCL banner; the reference's ikd-Tree,
+    timed as a CPU baseline, announces its rebuild thread with printf), so file descriptor 1 is pointed at stderr for the
+    whole run and the result line goes to a private duplicate of the original stdout."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)

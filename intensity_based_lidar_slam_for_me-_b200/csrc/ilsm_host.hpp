@@ -232,6 +232,7 @@ struct Ctx {
   FactorBufs fac;
   FeBufs fe;
   const int* d_stack_counts = nullptr;  // when set, associate/solve read {nc, ns} from the device (cube-map path)
+  int solve_wide = -1;                  // LM solve as a 16-CTA cluster (1) or the portable 8 (0); -1: not probed yet
   DevBuf<float4> rf_lsharp, rf_stack_c, rf_stack_s;  // ilsm_register_frame: less-sharp cloud and the two down-sampled stacks
   DevBuf<int> rf_stack_n;
   Map* qbin = nullptr;        // query binning of the throughput k-NN path (knn_binned.cu): the query cloud grouped by voxel

@@ -745,6 +745,9 @@ __device__ void lm_terminate(LmState* s, ilsm_reg_report* rep, int code) {
 // WARPSYNC.COLLECTIVE / ENDCOLLECTIVE pair.  Dependent fp64 operations cost ~35 cycles each on this part, so the update is
 // bound by its dependency chain (6 sequential pivots), not by issue slots; shuffles only lengthen that chain.
 // Consume the sums of the evaluation at the candidate pose and either terminate or emit the next candidate.
+// (a template only so that every kernel gets its own copy, compiled to ITS register budget: a shared copy is held to the
+// smallest budget of its callers, and the update is faster with the 255 registers a 192-thread block allows)
+template <int kCopy>
 __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const double* sums) {
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
   const double min_relative_decrease = 1e-3, min_radius = 1e-32, max_radius = 1e16;
@@ -908,8 +911,11 @@ __device__ __noinline__ void lm_advance(LmState* s, ilsm_reg_report* rep, const 
 // warp -> CTA (shared memory) -> cluster (distributed shared memory), every CTA advances an identical copy of
 // the LM state machine (no broadcast needed), one cluster barrier per evaluation (double-buffered partials).
 // ---------------------------------------------------------------------------------------------------
-constexpr int kClusterSize = 8;
-constexpr int kSolveThreads = 384;
+// The LM solve runs as ONE thread-block cluster.  16 CTAs x 192 threads (a non-portable cluster size, B200 schedules it)
+// when the device can place such a cluster, else 8 x 384: the same 3072 threads, but 6 instead of 12 warps per SM share
+// an SM's fp64 pipe during the evaluation (solve 19.8 -> 18.4 us at config 1).
+constexpr int kClusterSize = 8, kSolveThreads = 384;
+constexpr int kClusterSizeWide = 16, kSolveThreadsWide = 192;
 constexpr int kCoreWords = (int)(offsetof(LmState, report) / 8);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -978,23 +984,24 @@ struct SolveParams {
   ilsm_reg_report* d_report_out;   // non-null: the accumulated report is also written here
 };
 
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThreads, 1)
+template <int kCS, int kThr>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kThr, 1)
     solve_cluster_kernel(FactorView fv, int n, LmState* st, SolveParams prm, const int* __restrict__ d_counts) {
   pdl_entry();
   __shared__ double core[kCoreWords];
   if (d_counts) n = d_counts[0] + d_counts[1];
-  __shared__ double red[kSolveThreads / 32][kSumStride];
+  __shared__ double red[kThr / 32][kSumStride];
   // partial sums of every CTA of the cluster for the current evaluation, pushed by their owners (double-buffered by
   // evaluation parity) + the transaction barriers that count the 8 x 32 x 8 arriving bytes
-  __shared__ double recv[2][kClusterSize][kSumStride];
+  __shared__ double recv[2][kCS][kSumStride];
   __shared__ __align__(8) unsigned long long xbar[2];
   __shared__ double tot[kSumStride];
-  constexpr uint32_t kXferBytes = kClusterSize * kSumStride * 8;
+  constexpr uint32_t kXferBytes = kCS * kSumStride * 8;
   const uint32_t rank = cluster_ctarank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // factor i -> CTA (i % 8), thread (i / 8): the edge factors (3 residual rows, the first nc slots) are spread
   // evenly over the CTAs instead of all landing on CTA 0
-  const int cl_tid = tid * kClusterSize + (int)rank, cl_n = kClusterSize * kSolveThreads;
+  const int cl_tid = tid * kCS + (int)rank, cl_n = kCS * kThr;
   LmState* s = reinterpret_cast<LmState*>(core);  // only the fields before `report` exist in this copy
 
   // factor of the first round stays in registers for every evaluation
@@ -1011,7 +1018,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   }
   {
     const double* src = reinterpret_cast<const double*>(st);
-    for (int w = tid; w < kCoreWords; w += kSolveThreads) core[w] = src[w];
+    for (int w = tid; w < kCoreWords; w += kThr) core[w] = src[w];
   }
   if (tid == 0) {
     mbar_init(smem_u32(&xbar[0]), 1), mbar_init(smem_u32(&xbar[1]), 1);
@@ -1057,11 +1064,11 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
     if (tid < kSumStride) {
       double v = 0;
 #pragma unroll
-      for (int w = 0; w < kSolveThreads / 32; ++w) v += red[w][tid];
+      for (int w = 0; w < kThr / 32; ++w) v += red[w][tid];
       // push this CTA's partial into slot [rank] of every CTA (itself included): no cluster barrier, no remote loads
       const uint32_t slot = smem_u32(&recv[buf][rank][tid]), bar = smem_u32(&xbar[buf]);
 #pragma unroll
-      for (uint32_t r = 0; r < (uint32_t)kClusterSize; ++r) {
+      for (uint32_t r = 0; r < (uint32_t)kCS; ++r) {
         uint32_t ra, rb;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(slot), "r"(r));
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(bar), "r"(r));
@@ -1071,7 +1078,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
       mbar_wait_cluster(bar, (uint32_t)(e >> 1) & 1u);  // all 8 partials have landed here
       double t8 = 0;
 #pragma unroll
-      for (int r = 0; r < kClusterSize; ++r) t8 += recv[buf][r][tid];  // same order in every CTA: identical totals
+      for (int r = 0; r < kCS; ++r) t8 += recv[buf][r][tid];  // same order in every CTA: identical totals
       tot[tid] = t8;
     }
     __syncthreads();
@@ -1079,7 +1086,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
     // re-arm this buffer's barrier for evaluation e + 2: a peer can only push that far ahead after it has received this
     // CTA's partial of evaluation e + 1, which is sent after this point
     if (tid == 0) mbar_expect_tx(smem_u32(&xbar[buf]), kXferBytes);
-    if (tid == 0) lm_advance(s, rep, tot);
+    if (tid == 0) lm_advance<kThr>(s, rep, tot);
     STAMP(5);
     __syncthreads();
     STAMP(6);
@@ -1088,13 +1095,13 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSolveThr
   // for above (all CTAs run the same number of evaluations)
   if (rank == 0) {
     double* dst = reinterpret_cast<double*>(st);
-    for (int w = tid; w < kCoreWords; w += kSolveThreads) dst[w] = core[w];
+    for (int w = tid; w < kCoreWords; w += kThr) dst[w] = core[w];
     if (prm.d_pose7_out && tid < 7) prm.d_pose7_out[tid] = core[tid];  // xq[4], xt[3] lead the state
     if (prm.d_report_out) {  // written to st->report by thread 0 (lm_terminate) before the barrier that ended the loop
       const int words = (int)(sizeof(ilsm_reg_report) / 4);
       const int32_t* rs = reinterpret_cast<const int32_t*>(&st->report);
       int32_t* rd = reinterpret_cast<int32_t*>(prm.d_report_out);
-      for (int w = tid; w < words; w += kSolveThreads) rd[w] = rs[w];
+      for (int w = tid; w < words; w += kThr) rd[w] = rs[w];
     }
   }
 }
@@ -1432,8 +1439,29 @@ int Ctx::solve_launch(int max_iter, double huber_a, int pass, const PoseDst* dst
   prm.d_pose7_out = dst ? dst->d_pose7 : nullptr;
   prm.d_report_out = dst ? dst->d_report : nullptr;
   FactorView fv = factor_view(fac, false);
-  ILSM_CUDA(launch_pdl(solve_cluster_kernel, dim3(kClusterSize), dim3(kSolveThreads), 0, stream, fv, fac.n, lm.p, prm,
-                       d_stack_counts));
+  if (solve_wide < 0) {  // first solve of this context: can the device place a 16-CTA cluster?
+    solve_wide = 0;
+    auto* k16 = solve_cluster_kernel<kClusterSizeWide, kSolveThreadsWide>;
+    if (cudaFuncSetAttribute(k16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kClusterSizeWide), cfg.blockDim = dim3(kSolveThreadsWide);
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = kClusterSizeWide, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+      cfg.attrs = &at, cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, k16, &cfg) == cudaSuccess && n_clusters >= 1) solve_wide = 1;
+    }
+    (void)cudaGetLastError();
+    if (const char* e = getenv("ILSM_SOLVE_CLUSTER"))
+      if (atoi(e) == 8) solve_wide = 0;
+  }
+  if (solve_wide)
+    ILSM_CUDA(launch_pdl(solve_cluster_kernel<kClusterSizeWide, kSolveThreadsWide>, dim3(kClusterSizeWide), dim3(kSolveThreadsWide), 0,
+                         stream, fv, fac.n, lm.p, prm, d_stack_counts));
+  else
+    ILSM_CUDA(launch_pdl(solve_cluster_kernel<kClusterSize, kSolveThreads>, dim3(kClusterSize), dim3(kSolveThreads), 0, stream, fv,
+                         fac.n, lm.p, prm, d_stack_counts));
   count_launches(1);
   return check_launch("solve");
 }

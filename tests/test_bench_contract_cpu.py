@@ -27,6 +27,7 @@ def test_reference_arm_single_process(oracle_mod):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr
+    assert len(r.stdout.strip().splitlines()) == 1, r.stdout  # ONE line on stdout: native prints go to stderr
     _check_line(r.stdout, 1)
 
 
