@@ -4,8 +4,10 @@
 // Replaces the association + ceres::Solve block of laserMapping.cpp:640-861 and mapOptimization.cpp:377-450:
 //   associate_kernel : pointAssociateToMap (double math, float store) -> exact 5-NN in the voxel hash ->
 //                      gate d2[4] < 1 -> 3x3 scatter-matrix eigen (corner) / 5x3 pivoted-QR plane (surf),
-//                      all in registers; one factor slot per stack point.
-//   eval_kernel      : LidarEdgeFactor / LidarPlaneNormFactor residuals with closed-form tangent Jacobians
+//                      one warp per point for the search, one lane per point (of one warp per block) for the fit;
+//                      one factor slot per stack point.
+//   solve_cluster_kernel (one thread-block cluster per ceres::Solve) / normal_eq_*_kernel (one evaluation over an
+//                      ordinary grid): LidarEdgeFactor / LidarPlaneNormFactor residuals with closed-form tangent Jacobians
 //                      (hpp:199-293 + EigenQuaternionParameterization), HuberLoss(0.1) corrector, warp-shuffle +
 //                      block reduction of cost/JtJ/Jtr, deterministic cross-block sum by the last block, which
 //                      then advances the trust-region state machine (Ceres 1.14 TrustRegionMinimizer +
